@@ -1,0 +1,80 @@
+"""ctypes binding of libcgs_b200.so (include/cgs_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcgs_b200.so")
+
+SRC_PLAIN, SRC_CATUP, SRC_POOLBWD, SRC_SIGGRAD, SRC_LEAKYGRAD = range(5)
+EPI_LINEAR, EPI_LEAKY, EPI_RELU_POOL, EPI_SIGMOID, EPI_MUL, EPI_SPLIT_UP = range(6)
+
+_f32p = C.c_void_p
+_u8p = C.c_void_p
+
+
+class Src(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("C", C.c_int32), ("C0", C.c_int32), ("shift", C.c_int32),
+                ("a", _f32p), ("b", _f32p), ("idx", _u8p)]
+
+
+class Conv3x3Args(C.Structure):
+    _fields_ = [("src", Src), ("w", _f32p), ("bias", _f32p), ("transposed", C.c_int32),
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cout", C.c_int32), ("epi", C.c_int32),
+                ("out", _f32p), ("out2", _f32p), ("idx_out", _u8p), ("mul", _f32p),
+                ("C0", C.c_int32), ("shift2", C.c_int32), ("thresh", C.c_float)]
+
+
+class Wgrad3x3Args(C.Structure):
+    _fields_ = [("x", Src), ("dy", Src), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("dw", _f32p), ("db", _f32p)]
+
+
+EXPORTS = {
+    "cgs_conv3x3": [C.POINTER(Conv3x3Args), C.c_void_p],
+    "cgs_wgrad3x3": [C.POINTER(Wgrad3x3Args), C.c_void_p],
+    "cgs_head_fwd": [_f32p] * 9 + [C.c_int32] * 3 + [_f32p] * 3 + [C.c_void_p],
+    "cgs_head_bwd": [_f32p] * 11 + [C.c_int32] * 3 + [_f32p] * 7 + [C.c_void_p],
+    "cgs_dense_fwd": [_f32p] * 3 + [C.c_int32] * 3 + [_f32p, C.c_void_p],
+    "cgs_dense_bwd": [_f32p] * 3 + [C.c_int32] * 3 + [_f32p] * 3 + [C.c_void_p],
+    "cgs_occlude_fwd": [_f32p] * 3 + [C.c_int64, C.c_int32, _f32p, C.c_void_p],
+    "cgs_occlude_bwd": [_f32p] * 4 + [C.c_int64, C.c_int32] + [_f32p] * 3 + [C.c_void_p],
+    "cgs_pred_loss": [_f32p, _f32p, C.c_int32, C.c_int32, C.c_float, _f32p, _f32p, C.c_void_p],
+    "cgs_mask_reg": [_f32p, _f32p, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, _f32p, _f32p, C.c_void_p],
+    "cgs_frames_to_float": [_u8p] + [C.c_int32] * 5 + [_f32p, C.c_void_p],
+    "cgs_adam_step": [_f32p] * 4 + [C.c_int64] + [C.c_double] * 4 + [C.c_void_p, C.c_float, C.c_void_p],
+    "cgs_threshold": [_f32p, C.c_int64, C.c_float, C.c_int32, _u8p, C.c_void_p],
+}
+
+_lib = None
+
+
+class CgsError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the library (once).  Raises if it has not been built: no CPU fallback exists."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CgsError(f"{LIB_PATH} is missing: run `python -m cgs_b200.build` "
+                           "(or __graft_entry__.build()); there is no fallback path")
+        L = C.CDLL(LIB_PATH)
+        for name, argtypes in EXPORTS.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        L.cgs_last_error.restype = C.c_char_p
+        L.cgs_last_error.argtypes = []
+        L.cgs_version.restype = C.c_int
+        L.cgs_version.argtypes = []
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise CgsError(f"{what} failed (rc={rc}): {lib().cgs_last_error().decode()}")

@@ -1,0 +1,230 @@
+// HBM-bound stages of the hot path: occlusion blend (main.py:395,406) forward/backward,
+// prediction losses (main.py:193-195,400,411), mask regulariser (main.py:415-429),
+// uint8->float frame conversion with the shift_batch roll (main.py:189,584-591), binary
+// threshold (main.py:964,1164) and the flat Adam update (main.py:178,331-334).
+// All use grid-stride loops over 128-bit accesses where alignment allows, warp-shuffle +
+// one-atomic-per-CTA reductions, and grids sized to a multiple of the SM count.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace cgs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+    return CGS_ECUDA;
+  }
+  return CGS_OK;
+}
+
+static int grid_for(int64_t work_items, int threads) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  int64_t blocks = (work_items + threads - 1) / threads;
+  int64_t cap = (int64_t)sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float s_part[32];
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_part[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (warp == 0) {
+    r = lane < (blockDim.x + 31) / 32 ? s_part[lane] : 0.f;
+    r = warp_sum(r);
+  }
+  return r;  // valid in warp 0
+}
+
+// ---------------------------------------------------------------- occlusion blend
+// One thread per pixel (C contiguous floats); C == 3 on the path.  Loads of consecutive
+// pixels are contiguous across the warp (3 x 128 B per 32 pixels per tensor).
+__global__ void occlude_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ z,
+                                   int64_t npix, int C, float* __restrict__ out) {
+  const int64_t total = npix * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float zz = __ldg(z + i / C);
+    const float av = __ldg(a + i), bv = __ldg(b + i);
+    out[i] = av * (1.f - zz) + zz * bv;   // same association as the reference expression
+  }
+}
+
+__global__ void occlude_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ z,
+                                   const float* __restrict__ g, int64_t npix, int C, float* __restrict__ dz,
+                                   float* __restrict__ da, float* __restrict__ db) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    const float zz = __ldg(z + p);
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const int64_t i = p * C + c;
+      const float gv = __ldg(g + i);
+      acc = fmaf(__ldg(b + i) - __ldg(a + i), gv, acc);
+      if (da) da[i] = gv * (1.f - zz);
+      if (db) db[i] = gv * zz;
+    }
+    if (dz) dz[p] = acc;
+  }
+}
+
+// ---------------------------------------------------------------- prediction loss
+__global__ void pred_loss_kernel(const float* __restrict__ p, const float* __restrict__ t, int n, int bce, float gscale,
+                                 float* __restrict__ loss, float* __restrict__ grad) {
+  float acc = 0.f;
+  const float inv = 1.f / (float)n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float pv = __ldg(p + i), tv = __ldg(t + i);
+    if (bce) {
+      // F.binary_cross_entropy clamps the logs at -100
+      const float lp = fmaxf(logf(pv), -100.f), l1p = fmaxf(logf(1.f - pv), -100.f);
+      acc -= tv * lp + (1.f - tv) * l1p;
+      if (grad) grad[i] = gscale * inv * (pv - tv) / fmaxf(pv * (1.f - pv), 1e-12f);
+    } else {
+      const float d = pv - tv;
+      acc = fmaf(d, d, acc);
+      if (grad) grad[i] = gscale * inv * 2.f * d;
+    }
+  }
+  const float r = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(loss, r * inv);
+}
+
+// ---------------------------------------------------------------- mask regulariser
+__global__ void mask_reg_kernel(const float* __restrict__ z, const float* __restrict__ vpred, int64_t n, int per_frame,
+                                float l1, float l2, float gscale, float* __restrict__ loss, float* __restrict__ grad) {
+  float acc = 0.f;
+  const float inv = 1.f / (float)n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float vf = vpred ? 1.f - __ldg(vpred + i / per_frame) : 1.f;
+    const float u = vf * __ldg(z + i);
+    acc += l1 * fabsf(u) + l2 * u * u;
+    if (grad) {
+      const float sg = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
+      grad[i] = gscale * inv * vf * (l1 * sg + 2.f * l2 * u);
+    }
+  }
+  const float r = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(loss, r * inv);
+}
+
+// ---------------------------------------------------------------- frames uint8 -> float
+__global__ void frames_to_float_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int C, int roll,
+                                       float* __restrict__ out) {
+  const int64_t total = (int64_t)B * H * W * C;
+  const int rowc = W * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / rowc;
+    const int r = (int)(i - row * rowc);
+    const int x = r / C, c = r - x * C;
+    int sx = x + roll;
+    sx %= W;
+    if (sx < 0) sx += W;
+    out[i] = (float)__ldg(in + row * rowc + sx * C + c) / 255.0f;
+  }
+}
+
+__global__ void threshold_kernel(const float* __restrict__ z, int64_t n, float thresh, int strict, uint8_t* __restrict__ hard) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = __ldg(z + i);
+    hard[i] = strict ? (v > thresh) : (v >= thresh);
+  }
+}
+
+// ---------------------------------------------------------------- Adam
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            int64_t n, double lr, double beta1, double beta2, double eps_d,
+                            const int* __restrict__ step_count, float gscale) {
+  const int t = *step_count;
+  // bias corrections in double, as torch does on the host (python floats); tensor-side scalars in fp32
+  const double bc1 = 1.0 - pow(beta1, (double)t);
+  const double bc2 = 1.0 - pow(beta2, (double)t);
+  const float step_size = (float)(lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const float omb1 = (float)(1.0 - beta1), b2 = (float)beta2, omb2 = (float)(1.0 - beta2), eps = (float)eps_d;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gv = g[i] * gscale;
+    const float mv = m[i] + omb1 * (gv - m[i]);                 // lerp form used by torch
+    const float vv = v[i] * b2 + omb2 * gv * gv;
+    m[i] = mv;
+    v[i] = vv;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    p[i] -= step_size * (mv / denom);
+  }
+}
+
+}  // namespace cgs
+
+using namespace cgs;
+
+extern "C" int cgs_occlude_fwd(const float* a, const float* b, const float* z, int64_t npix, int32_t C, float* out,
+                               void* stream) {
+  CGS_REQUIRE(a && b && z && out && npix > 0 && C > 0, "occlude_fwd: bad args");
+  occlude_fwd_kernel<<<grid_for(npix * C, 256), 256, 0, (cudaStream_t)stream>>>(a, b, z, npix, C, out);
+  return check_launch("occlude_fwd");
+}
+
+extern "C" int cgs_occlude_bwd(const float* a, const float* b, const float* z, const float* g, int64_t npix, int32_t C,
+                               float* dz, float* da, float* db_, void* stream) {
+  CGS_REQUIRE(a && b && z && g && npix > 0 && C > 0 && (dz || da || db_), "occlude_bwd: bad args");
+  occlude_bwd_kernel<<<grid_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(a, b, z, g, npix, C, dz, da, db_);
+  return check_launch("occlude_bwd");
+}
+
+extern "C" int cgs_pred_loss(const float* p, const float* t, int32_t n, int32_t bce, float gscale, float* loss,
+                             float* grad, void* stream) {
+  CGS_REQUIRE(p && t && loss && n > 0, "pred_loss: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) return check_launch("pred_loss.memset");
+  pred_loss_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, t, n, bce, gscale, loss, grad);
+  return check_launch("pred_loss");
+}
+
+extern "C" int cgs_mask_reg(const float* z, const float* vpred, int64_t n, int32_t per_frame, float l1, float l2,
+                            float gscale, float* loss, float* grad, void* stream) {
+  CGS_REQUIRE(z && loss && n > 0 && per_frame > 0, "mask_reg: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) return check_launch("mask_reg.memset");
+  mask_reg_kernel<<<grid_for(n, 256), 256, 0, st>>>(z, vpred, n, per_frame, l1, l2, gscale, loss, grad);
+  return check_launch("mask_reg");
+}
+
+extern "C" int cgs_frames_to_float(const uint8_t* in, int32_t B, int32_t H, int32_t W, int32_t C, int32_t roll,
+                                   float* out, void* stream) {
+  CGS_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && C > 0, "frames_to_float: bad args");
+  frames_to_float_kernel<<<grid_for((int64_t)B * H * W * C, 256), 256, 0, (cudaStream_t)stream>>>(in, B, H, W, C, roll, out);
+  return check_launch("frames_to_float");
+}
+
+extern "C" int cgs_threshold(const float* z, int64_t n, float thresh, int32_t strict, uint8_t* hard, void* stream) {
+  CGS_REQUIRE(z && hard && n > 0, "threshold: bad args");
+  threshold_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(z, n, thresh, strict, hard);
+  return check_launch("threshold");
+}
+
+extern "C" int cgs_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                             double eps, const int32_t* step_count, float grad_scale, void* stream) {
+  CGS_REQUIRE(p && g && m && v && step_count && n > 0, "adam_step: bad args");
+  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_count, grad_scale);
+  return check_launch("adam_step");
+}
+
+extern "C" const char* cgs_last_error(void) { return g_err; }
+extern "C" int cgs_version(void) { return 100; }

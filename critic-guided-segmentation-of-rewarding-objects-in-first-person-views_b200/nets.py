@@ -1,0 +1,139 @@
+"""Drop-in replacements for the two live network classes of the reference `nets.py`:
+`NewCritic` (reference nets.py:160-212) and `UnetDecoder` (nets.py:452-523).
+
+Same constructor signatures, `forward()` signatures, return structure, parameter
+registration order and `state_dict()` keys/shapes (OIHW fp32), so reference
+checkpoints load here and vice versa, `Adam(critic.parameters())` sees the same
+tensors in the same order, and default initialisation consumes the torch RNG
+identically.  The `nn.Conv2d` / `nn.Linear` objects are parameter containers only:
+`forward()` dispatches to the fused sm_100a kernels of libcgs_b200.so via
+`cgs_b200.ops`.  CUDA only: calling forward on CPU tensors raises (no fallback).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from ._lib import CgsError
+
+
+def _nhwc(X, C, width, who):
+    if X.dim() != 4 or X.shape[1] != C or X.shape[2] != width or X.shape[3] != width:
+        raise ValueError(f"{who}: expected input [B,{C},{width},{width}], got {tuple(X.shape)}")
+    if X.shape[0] == 0:
+        raise ValueError(f"{who}: empty batch")
+    if not X.is_cuda:
+        raise CgsError(f"{who}: input is on {X.device}; cgs_b200 has no CPU path")
+    if X.dtype != torch.float32:
+        raise ValueError(f"{who}: expected float32 input (the reference casts with .float()), got {X.dtype}")
+    return X.permute(0, 2, 3, 1).contiguous()   # zero-copy for channels_last inputs (main.py:189)
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2)
+
+
+class NewCritic(nn.Module):
+    def __init__(self, width=64, dims=[8, 8, 8, 16], bottleneck=32, colorchs=3, chfak=1, activation=nn.ReLU,
+                 pool="max", dropout=0.5):
+        super().__init__()
+        if pool != "max" or activation is not nn.ReLU:
+            raise NotImplementedError("cgs_b200.NewCritic accelerates the live configuration only: "
+                                      "pool='max', activation=nn.ReLU (reference main.py:108)")
+        if width != 64 or len(dims) != 4:
+            raise NotImplementedError("cgs_b200.NewCritic: width must be 64 with four stages "
+                                      "(the 4x4 bottleneck conv hard-wires it, reference nets.py:184)")
+        self.width = width
+        self.colorchs = colorchs
+        self.p = float(dropout)
+        ch = [int(d) for d in np.array(dims) * chfak]
+        self.pool = nn.MaxPool2d(2)
+        layers = []
+        cin = colorchs
+        for i, c in enumerate(ch):
+            layers += [nn.Conv2d(cin, c, 3, 1, 1), activation(), self.pool]
+            if i >= 2:
+                layers.append(nn.Dropout(dropout))
+            cin = c
+        layers += [nn.Conv2d(cin, bottleneck * chfak, 4), activation()]
+        self.features = nn.Sequential(*layers)
+        nb = chfak * bottleneck
+        self.crit = nn.Sequential(nn.Flatten(), nn.Linear(nb, nb), activation(), nn.Dropout(dropout),
+                                  nn.Linear(nb, 1), nn.Sigmoid())
+        self._conv_idx = (0, 3, 6, 10)
+        self._forced_masks = None   # test hook: (m_e2 [B,8,8,8c], m_e3 [B,4,4,16c], m_v [B,32c]) NHWC
+
+    def _dropout_masks(self, B, device):
+        if self._forced_masks is not None:
+            return self._forced_masks
+        if not self.training or self.p <= 0.0:
+            return None, None, None
+        c2 = self.features[6].out_channels
+        c3 = self.features[10].out_channels
+        nb = self.crit[1].out_features
+        mk = lambda *s: F.dropout(torch.ones(s, device=device, dtype=torch.float32), self.p, True)
+        return mk(B, 8, 8, c2), mk(B, 4, 4, c3), mk(B, nb)
+
+    def forward(self, X, collect=False):
+        x = _nhwc(X, self.colorchs, self.width, "NewCritic")
+        m_e2, m_e3, m_v = self._dropout_masks(x.shape[0], x.device)
+        f = self.features
+        e0 = ops.EncBlock.apply(x, None, f[0].weight, f[0].bias)
+        e1 = ops.EncBlock.apply(e0, None, f[3].weight, f[3].bias)
+        e2 = ops.EncBlock.apply(e1, None, f[6].weight, f[6].bias)
+        e3 = ops.EncBlock.apply(e2, m_e2, f[10].weight, f[10].bias)
+        pred, e4 = ops.Head.apply(e3, m_e3, m_v, f[14].weight, f[14].bias, self.crit[1].weight, self.crit[1].bias,
+                                  self.crit[4].weight, self.crit[4].bias)
+        if collect:
+            return pred, [_nchw(e0), _nchw(e1), _nchw(e2), _nchw(e3), _nchw(e4)]
+        return pred
+
+
+class UnetDecoder(nn.Module):
+    def __init__(self, width=64, edims=[8, 8, 8, 16], ddims=[8, 8, 8, 16], bottleneck=32, masker_channels=16,
+                 colorchs=3, chfak=1, activation=nn.ReLU, pool="max", upsample=True, pure=False):
+        super().__init__()
+        if pool != "max" or not upsample or pure:
+            raise NotImplementedError("cgs_b200.UnetDecoder accelerates the live configuration only: "
+                                      "pool='max', upsample=True, pure=False (reference main.py:109)")
+        if width != 64:
+            raise NotImplementedError("cgs_b200.UnetDecoder: width must be 64")
+        e = [int(v) for v in np.array(edims, dtype=int) * chfak]
+        d = [int(v) for v in np.array(ddims, dtype=int) * chfak]
+        nb = bottleneck * chfak
+        self.width = width
+        self.colorchs = colorchs
+        self.pool = nn.MaxPool2d(2)
+        self.acti = nn.LeakyReLU(0.01)
+        self.ups = nn.Upsample(scale_factor=(2, 2))
+        self.upsample = upsample
+        self.pure = pure
+        self.masker_channels = masker_channels
+        ins = [e[0] + d[1], e[1] + d[2], e[2] + d[3], e[3] + nb]
+        self.dec = [nn.Conv2d(ins[k], d[k], 3, 1, 1) for k in range(4)] + [nn.Conv2d(nb, nb, 1, 1, 0)]
+        self.dec_model = nn.Sequential(*self.dec)
+        self.masker = nn.Sequential(nn.Conv2d(colorchs + d[0], masker_channels, 3, 1, 1), self.acti,
+                                    nn.Conv2d(masker_channels, 1, 3, 1, 1), nn.Sigmoid())
+
+    def _run(self, X, embeds, thresh):
+        x = _nhwc(X, self.colorchs, self.width, "UnetDecoder")
+        if len(embeds) != 5:
+            raise ValueError("UnetDecoder: embeds must be the 5 tensors returned by NewCritic.forward(X, collect=True)")
+        e = [t.permute(0, 2, 3, 1).contiguous() for t in embeds]
+        dec = self.dec
+        o = ops.Dense.apply(e[4], dec[4].weight, dec[4].bias)                          # nets.py:500-501
+        o = ops.DecBlock.apply(e[3], o, dec[3].weight, dec[3].bias, 2, False)          # ups(ups()) + cat + dec[3]
+        o = ops.DecBlock.apply(e[2], o, dec[2].weight, dec[2].bias, 1, False)
+        o = ops.DecBlock.apply(e[1], o, dec[1].weight, dec[1].bias, 1, False)
+        o = ops.DecBlock.apply(e[0], o, dec[0].weight, dec[0].bias, 1, False)
+        m = ops.DecBlock.apply(x, o, self.masker[0].weight, self.masker[0].bias, 1, True)   # cat(X, ups) + masker[0..1]
+        z, hard = ops.MaskHead.apply(m, self.masker[2].weight, self.masker[2].bias, thresh)
+        return _nchw(z), (_nchw(hard) if thresh is not None else None)
+
+    def forward(self, X, embeds):
+        return self._run(X, embeds, None)[0]
+
+    def forward_hard(self, X, embeds, threshold):
+        """mask and `mask >= threshold` (uint8) from one fused epilogue (reference main.py:1150,1164)."""
+        return self._run(X, embeds, threshold)

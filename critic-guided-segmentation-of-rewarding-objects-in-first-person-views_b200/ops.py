@@ -1,0 +1,352 @@
+"""torch.autograd bindings of the C-ABI kernels (include/cgs_b200.h).
+
+Every tensor handled here is NHWC-contiguous fp32 on a CUDA device ([B,H,W,C]); the
+modules in nets.py convert at the boundary (zero-copy for the channels_last inputs the
+reference loops produce, main.py:189,360).  torch is used for memory, streams and
+autograd bookkeeping only; all arithmetic runs in libcgs_b200.so.  No CPU path.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_LEAKY, EPI_LINEAR, EPI_MUL, EPI_RELU_POOL, EPI_SIGMOID, EPI_SPLIT_UP, SRC_CATUP,
+                   SRC_LEAKYGRAD, SRC_PLAIN, SRC_POOLBWD, SRC_SIGGRAD, CgsError, Conv3x3Args, Src, Wgrad3x3Args)
+
+_launches = 0   # kernels launched through this module (bench.py reports it)
+
+
+def launch_count():
+    return _launches
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=torch.float32):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise CgsError("cgs_b200 kernels need CUDA tensors: there is no CPU fallback")
+    if t.dtype != dtype or not t.is_contiguous():
+        raise CgsError(f"expected contiguous {dtype} tensor, got {t.dtype} strides {t.stride()}")
+    return t.data_ptr()
+
+
+def _call(name, *args):
+    global _launches
+    rc = getattr(_lib.lib(), name)(*args)
+    _lib.check(rc, name)
+    _launches += 1
+
+
+def _src(mode, Cn, a, b=None, idx=None, C0=0, shift=0):
+    return Src(mode, Cn, C0, shift, _p(a), _p(b), _p(idx, torch.uint8))
+
+
+def conv3x3(src, w, bias, B, H, W, Cout, epi, out, transposed=False, out2=None, idx_out=None, mul=None,
+            C0=0, shift2=0, thresh=0.0):
+    a = Conv3x3Args(src, _p(w), _p(bias), int(transposed), B, H, W, Cout, epi, _p(out), _p(out2),
+                    _p(idx_out, torch.uint8), _p(mul), C0, shift2, thresh)
+    _call("cgs_conv3x3", C.byref(a), _stream())
+
+
+def wgrad3x3(xsrc, dysrc, B, H, W, dw, db):
+    a = Wgrad3x3Args(xsrc, dysrc, B, H, W, _p(dw), _p(db))
+    _call("cgs_wgrad3x3", C.byref(a), _stream())
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class EncBlock(torch.autograd.Function):
+    """[Dropout ->] Conv2d(3,1,1) -> ReLU -> MaxPool2d(2): one NewCritic.features stage
+    (reference nets.py:170-183).  x [B,H,W,Cin]; mask = multiplicative dropout mask or None."""
+
+    @staticmethod
+    def forward(ctx, x, mask, w, b):
+        B, H, W, Cin = x.shape
+        Cout = w.shape[0]
+        e = torch.empty((B, H // 2, W // 2, Cout), device=x.device, dtype=torch.float32)
+        idx = torch.empty((B, H // 2, W // 2, Cout), device=x.device, dtype=torch.uint8)
+        conv3x3(_src(SRC_PLAIN, Cin, x, mask), w, b, B, H, W, Cout, EPI_RELU_POOL, e, idx_out=idx)
+        ctx.save_for_backward(x, mask, w, e, idx)
+        ctx.set_materialize_grads(False)
+        return e
+
+    @staticmethod
+    def backward(ctx, de):
+        x, mask, w, e, idx = ctx.saved_tensors
+        if de is None:
+            return None, None, None, None
+        de = _c(de)
+        B, H, W, Cin = x.shape
+        Cout = w.shape[0]
+        dy = _src(SRC_POOLBWD, Cout, de, e, idx)
+        dx = dw = db = None
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            dw = torch.zeros_like(w)
+            db = torch.zeros(Cout, device=x.device, dtype=torch.float32)
+            wgrad3x3(_src(SRC_PLAIN, Cin, x, mask), dy, B, H, W, dw, db)
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            conv3x3(dy, w, None, B, H, W, Cin, EPI_MUL if mask is not None else EPI_LINEAR, dx,
+                    transposed=True, mul=mask)
+        return dx, None, dw, db
+
+
+class Head(torch.autograd.Function):
+    """NewCritic tail: [Dropout] Conv2d(16c,32c,4) ReLU | Flatten Linear ReLU [Dropout] Linear Sigmoid
+    (reference nets.py:183-195).  Returns (pred [B,1], e4 [B,1,1,NB])."""
+
+    @staticmethod
+    def forward(ctx, e3, m_e3, m_v, w14, b14, w1, b1, w2, b2):
+        B, _, _, C3 = e3.shape
+        NB = w14.shape[0]
+        e4 = torch.empty((B, 1, 1, NB), device=e3.device, dtype=torch.float32)
+        v = torch.empty((B, NB), device=e3.device, dtype=torch.float32)
+        pred = torch.empty((B, 1), device=e3.device, dtype=torch.float32)
+        _call("cgs_head_fwd", _p(e3), _p(m_e3), _p(m_v), _p(w14), _p(b14), _p(w1), _p(b1), _p(w2), _p(b2),
+              B, C3, NB, _p(e4), _p(v), _p(pred), _stream())
+        ctx.save_for_backward(e3, m_e3, m_v, w14, w1, w2, e4, v, pred)
+        ctx.set_materialize_grads(False)
+        return pred, e4
+
+    @staticmethod
+    def backward(ctx, dpred, de4):
+        e3, m_e3, m_v, w14, w1, w2, e4, v, pred = ctx.saved_tensors
+        B, _, _, C3 = e3.shape
+        NB = w14.shape[0]
+        if dpred is None and de4 is None:
+            return (None,) * 9
+        dpred = torch.zeros_like(pred) if dpred is None else _c(dpred)
+        de4 = None if de4 is None else _c(de4)
+        want_w = any(ctx.needs_input_grad[3:])
+        gw = [torch.zeros_like(t) for t in (w14,)] if want_w else [None]
+        dw14 = gw[0]
+        db14 = torch.zeros(NB, device=e3.device) if want_w else None
+        dw1 = torch.zeros_like(w1) if want_w else None
+        db1 = torch.zeros(NB, device=e3.device) if want_w else None
+        dw2 = torch.zeros_like(w2) if want_w else None
+        db2 = torch.zeros(1, device=e3.device) if want_w else None
+        de3 = torch.empty_like(e3) if ctx.needs_input_grad[0] else None
+        _call("cgs_head_bwd", _p(e3), _p(m_e3), _p(m_v), _p(w14), _p(w1), _p(w2), _p(e4), _p(v), _p(pred),
+              _p(dpred), _p(de4), B, C3, NB, _p(dw14), _p(db14), _p(dw1), _p(db1), _p(dw2), _p(db2), _p(de3),
+              _stream())
+        return de3, None, None, dw14, db14, dw1, db1, dw2, db2
+
+
+class DecBlock(torch.autograd.Function):
+    """cat(skip, nearest_up(up, 2**shift)) -> Conv2d(3,1,1) [-> LeakyReLU(0.01)]: one UnetDecoder
+    stage (reference nets.py:503-521).  skip [B,H,W,C0], up [B,H>>shift,W>>shift,C1]."""
+
+    @staticmethod
+    def forward(ctx, skip, up, w, b, shift, leaky):
+        B, H, W, C0 = skip.shape
+        C1 = up.shape[3]
+        Cout = w.shape[0]
+        out = torch.empty((B, H, W, Cout), device=skip.device, dtype=torch.float32)
+        conv3x3(_src(SRC_CATUP, C0 + C1, skip, up, C0=C0, shift=shift), w, b, B, H, W, Cout,
+                EPI_LEAKY if leaky else EPI_LINEAR, out)
+        ctx.save_for_backward(skip, up, w, out if leaky else None)
+        ctx.shift, ctx.leaky = shift, leaky
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        skip, up, w, out = ctx.saved_tensors
+        if dout is None:
+            return (None,) * 6
+        dout = _c(dout)
+        B, H, W, C0 = skip.shape
+        C1 = up.shape[3]
+        Cout = w.shape[0]
+        shift = ctx.shift
+        dy = _src(SRC_LEAKYGRAD, Cout, dout, out) if ctx.leaky else _src(SRC_PLAIN, Cout, dout)
+        dskip = dup = dw = db = None
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            dw = torch.zeros_like(w)
+            db = torch.zeros(Cout, device=w.device, dtype=torch.float32)
+            wgrad3x3(_src(SRC_CATUP, C0 + C1, skip, up, C0=C0, shift=shift), dy, B, H, W, dw, db)
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            if ctx.needs_input_grad[0]:
+                dskip = torch.empty_like(skip)
+            if ctx.needs_input_grad[1]:
+                dup = torch.zeros_like(up) if shift == 2 else torch.empty_like(up)
+            conv3x3(dy, w, None, B, H, W, C0 + C1, EPI_SPLIT_UP, dskip, transposed=True, out2=dup,
+                    C0=C0, shift2=shift)
+        return dskip, dup, dw, db, None, None
+
+
+class MaskHead(torch.autograd.Function):
+    """Conv2d(16,1,3,1,1) -> Sigmoid (reference nets.py:490-491) [+ fused >= threshold, main.py:1164]."""
+
+    @staticmethod
+    def forward(ctx, m, w, b, thresh):
+        B, H, W, Cm = m.shape
+        z = torch.empty((B, H, W, 1), device=m.device, dtype=torch.float32)
+        hard = None
+        if thresh is not None:
+            hard = torch.empty((B, H, W, 1), device=m.device, dtype=torch.uint8)
+        conv3x3(_src(SRC_PLAIN, Cm, m), w, b, B, H, W, 1, EPI_SIGMOID, z, idx_out=hard,
+                thresh=float(thresh) if thresh is not None else 0.0)
+        ctx.save_for_backward(m, w, z)
+        ctx.set_materialize_grads(False)
+        if hard is None:
+            hard = torch.empty(0, device=m.device, dtype=torch.uint8)
+        ctx.mark_non_differentiable(hard)
+        return z, hard
+
+    @staticmethod
+    def backward(ctx, dz, _dhard):
+        m, w, z = ctx.saved_tensors
+        if dz is None:
+            return None, None, None, None
+        dz = _c(dz)
+        B, H, W, Cm = m.shape
+        dy = _src(SRC_SIGGRAD, 1, dz, z)
+        dm = dw = db = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dw = torch.zeros_like(w)
+            db = torch.zeros(1, device=w.device, dtype=torch.float32)
+            wgrad3x3(_src(SRC_PLAIN, Cm, m), dy, B, H, W, dw, db)
+        if ctx.needs_input_grad[0]:
+            dm = torch.empty_like(m)
+            conv3x3(dy, w, None, B, H, W, Cm, EPI_LINEAR, dm, transposed=True)
+        return dm, dw, db, None
+
+
+class Dense(torch.autograd.Function):
+    """UnetDecoder.dec[4]: Conv2d(32c,32c,1) on the 1x1 bottleneck (reference nets.py:484,500-501)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        B = x.shape[0]
+        N, K = w.shape[0], w.shape[1]
+        out = torch.empty((B, 1, 1, N), device=x.device, dtype=torch.float32)
+        _call("cgs_dense_fwd", _p(x), _p(w), _p(b), B, K, N, _p(out), _stream())
+        ctx.save_for_backward(x, w)
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        if dout is None:
+            return None, None, None
+        dout = _c(dout)
+        B = x.shape[0]
+        N, K = w.shape[0], w.shape[1]
+        want_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros_like(w) if want_w else None
+        db = torch.zeros(N, device=w.device, dtype=torch.float32) if want_w else None
+        _call("cgs_dense_bwd", _p(x), _p(w), _p(dout), B, K, N, _p(dx), _p(dw), _p(db), _stream())
+        return dx, dw, db
+
+
+class Occlude(torch.autograd.Function):
+    """a*(1-z) + z*b with z broadcast over channels (reference main.py:395,406).  NHWC tensors."""
+
+    @staticmethod
+    def forward(ctx, a, b, z):
+        out = torch.empty_like(a)
+        npix = a.numel() // a.shape[-1]
+        _call("cgs_occlude_fwd", _p(a), _p(b), _p(z), npix, a.shape[-1], _p(out), _stream())
+        ctx.save_for_backward(a, b, z)
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, z = ctx.saved_tensors
+        if g is None:
+            return None, None, None
+        g = _c(g)
+        npix = a.numel() // a.shape[-1]
+        da = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        db = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        dz = torch.empty_like(z) if ctx.needs_input_grad[2] else None
+        _call("cgs_occlude_bwd", _p(a), _p(b), _p(z), _p(g), npix, a.shape[-1], _p(dz), _p(da), _p(db), _stream())
+        return da, db, dz
+
+
+class PredLoss(torch.autograd.Function):
+    """F.mse_loss(pred, target) / F.binary_cross_entropy (reference main.py:193-195,400,411), mean reduction."""
+
+    @staticmethod
+    def forward(ctx, pred, target, bce):
+        p = _c(pred.reshape(-1))
+        t = _c(target.reshape(-1).to(torch.float32))
+        loss = torch.empty(1, device=p.device, dtype=torch.float32)
+        grad = torch.empty_like(p)
+        _call("cgs_pred_loss", _p(p), _p(t), p.numel(), int(bce), 1.0, _p(loss), _p(grad), _stream())
+        ctx.save_for_backward(grad)
+        ctx.shape = pred.shape
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (grad * g).reshape(ctx.shape), None, None
+
+
+class MaskReg(torch.autograd.Function):
+    """L1*l1_loss(vf*Z,0) + L2*mse_loss(vf*Z,0) (reference main.py:415-429); vf = 1 or 1-pred[frame]."""
+
+    @staticmethod
+    def forward(ctx, z, vpred, l1, l2):
+        zc = _c(z)
+        n = zc.numel()
+        per_frame = n // zc.shape[0]
+        loss = torch.empty(1, device=z.device, dtype=torch.float32)
+        grad = torch.empty_like(zc)
+        vp = None if vpred is None else _c(vpred.detach().reshape(-1))
+        _call("cgs_mask_reg", _p(zc), _p(vp), n, per_frame, float(l1), float(l2), 1.0, _p(loss), _p(grad), _stream())
+        ctx.save_for_backward(grad)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None
+
+
+def frames_to_float(frames_u8, roll=0):
+    """uint8 NHWC [B,H,W,C] (device) -> fp32 NHWC /255 with circular W-roll (main.py:189,584-591).
+    roll > 0 == `cat(X[:, :, roll:], X[:, :, :roll])`; roll < 0 == the `-xshift` branch."""
+    if not frames_u8.is_cuda:
+        raise CgsError("frames_to_float needs a CUDA tensor")
+    x = _c(frames_u8)
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, H, W, Cc), device=x.device, dtype=torch.float32)
+    _call("cgs_frames_to_float", _p(x, torch.uint8), B, H, W, Cc, int(roll), _p(out), _stream())
+    return out
+
+
+def threshold(z, thresh, strict=False):
+    zc = _c(z)
+    hard = torch.empty(zc.shape, device=z.device, dtype=torch.uint8)
+    _call("cgs_threshold", _p(zc), zc.numel(), float(thresh), int(strict), _p(hard, torch.uint8), _stream())
+    return hard
+
+
+def adam_step(p, g, m, v, step_count, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+    """Flat-bucket Adam (torch.optim.Adam defaults, main.py:178).  step_count: int32 device tensor (already incremented)."""
+    _call("cgs_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(betas[0]), float(betas[1]),
+          float(eps), _p(step_count, torch.int32), float(grad_scale), _stream())
+
+
+def occlude(a, b, z):
+    return Occlude.apply(a, b, z)
+
+
+def pred_loss(pred, target, bce=False):
+    return PredLoss.apply(pred, target, bce)
+
+
+def mask_reg(z, vpred=None, l1=0.0, l2=0.0):
+    return MaskReg.apply(z, vpred, l1, l2)

@@ -1,0 +1,156 @@
+/* cgs_b200 — C-ABI of the B200-native Critic/Hourglass conv hot path.
+ *
+ * The reference has no FFI: its hot path is the torch.nn call graph of
+ * nets.py (NewCritic nets.py:160-212, UnetDecoder nets.py:452-523) plus the loss
+ * expressions of main.py:191-198 and main.py:364-462.  Each entry point below names
+ * the reference ops it replaces.  Conventions:
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the
+ *     caller (the Python host allocates torch tensors and passes data_ptr());
+ *   - activations are NHWC fp32 ([B,H,W,C] contiguous == torch channels_last);
+ *     weights keep the reference's OIHW fp32 state_dict layout and are never
+ *     repacked in place;
+ *   - stream-ordered on `stream` (a cudaStream_t passed as void*), no internal
+ *     synchronisation, no allocation; safe to capture into a CUDA graph;
+ *   - return 0 on success, negative cgs_status on error; cgs_last_error() gives text.
+ */
+#ifndef CGS_B200_H
+#define CGS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum cgs_status { CGS_OK = 0, CGS_EINVAL = -1, CGS_ECUDA = -2, CGS_EUNSUPPORTED = -3 };
+
+/* How a conv operand is produced on the fly while it is staged into shared memory. */
+enum cgs_src_mode {
+  CGS_SRC_PLAIN = 0,    /* a[B,H,W,C]; optional b = multiplicative mask of the same shape (Dropout, nets.py:179,183) */
+  CGS_SRC_CATUP = 1,    /* cat(a[B,H,W,C0], nearest_up(b[B,H>>shift,W>>shift,C-C0])) — T.cat + nn.Upsample, nets.py:503-520 */
+  CGS_SRC_POOLBWD = 2,  /* grad of conv output through ReLU+MaxPool2d(2): a=dE[B,H/2,W/2,C], b=E (pooled fwd output), idx=argmax */
+  CGS_SRC_SIGGRAD = 3,  /* a=dZ, b=Z: dZ*Z*(1-Z) — Sigmoid backward (nets.py:491) */
+  CGS_SRC_LEAKYGRAD = 4 /* a=dOut, b=out: dOut*(out>0?1:slope) — LeakyReLU(0.01) backward (nets.py:462,489) */
+};
+
+typedef struct cgs_src {
+  int32_t mode;
+  int32_t C;            /* channels presented to the conv */
+  int32_t C0;           /* CATUP: channels taken from a */
+  int32_t shift;        /* CATUP: log2 upsample factor of b (1 or 2) */
+  const float* a;
+  const float* b;
+  const uint8_t* idx;   /* POOLBWD: 2-bit window position of the first max, one byte per pooled element */
+} cgs_src;
+
+/* Epilogues of the 3x3 conv kernel. */
+enum cgs_epi {
+  CGS_EPI_LINEAR = 0,     /* out = acc + bias                         (dec convs: no activation, nets.py:500-517) */
+  CGS_EPI_LEAKY = 1,      /* out = leaky_relu(acc + bias, 0.01)       (masker[0..1], nets.py:488-489) */
+  CGS_EPI_RELU_POOL = 2,  /* out = maxpool2(relu(acc + bias)), idx    (features[k..k+2], nets.py:170-182) */
+  CGS_EPI_SIGMOID = 3,    /* out = sigmoid(acc + bias) [+ hard = out >= thresh]  (masker[2..3], main.py:1164) */
+  CGS_EPI_MUL = 4,        /* out = acc * mul  (dgrad through Dropout) */
+  CGS_EPI_SPLIT_UP = 5    /* channels < C0 -> out[B,H,W,C0]; the rest summed over the upsample window into out2 (cat + Upsample backward) */
+};
+
+typedef struct cgs_conv3x3_args {
+  cgs_src src;            /* input operand, Cin = src.C */
+  const float* w;         /* OIHW [Cout,Cin,3,3]; if transposed: the forward layer's [Cin,Cout,3,3] used as dgrad filter */
+  const float* bias;      /* [Cout] or NULL */
+  int32_t transposed;     /* 0 = fprop, 1 = dgrad (rotate 180 deg, swap in/out) */
+  int32_t B, H, W;        /* conv resolution (input == output, stride 1 pad 1) */
+  int32_t Cout;
+  int32_t epi;
+  float* out;             /* see cgs_epi */
+  float* out2;            /* SPLIT_UP: [B,H>>shift2,W>>shift2,Cout-C0], must be zeroed when shift2==2 */
+  uint8_t* idx_out;       /* RELU_POOL: argmax bytes (may be NULL); SIGMOID: hard mask bytes (may be NULL) */
+  const float* mul;       /* MUL: multiplier, same shape as out */
+  int32_t C0;             /* SPLIT_UP: split point */
+  int32_t shift2;         /* SPLIT_UP: 1 or 2 */
+  float thresh;           /* SIGMOID hard-mask threshold (>=) */
+} cgs_conv3x3_args;
+
+/* Conv2d(k=3,s=1,p=1) fprop or dgrad with fused prologue/epilogue.
+ * Replaces: nn.Conv2d + ReLU + MaxPool2d (nets.py:170-182), T.cat + nn.Upsample + nn.Conv2d
+ * (nets.py:503-521), LeakyReLU / Sigmoid (nets.py:489-491) and autograd's conv input-gradient. */
+int cgs_conv3x3(const cgs_conv3x3_args* a, void* stream);
+
+typedef struct cgs_wgrad3x3_args {
+  cgs_src x;              /* forward input operand (Cin = x.C) */
+  cgs_src dy;             /* gradient w.r.t. the conv output (Cout = dy.C) */
+  int32_t B, H, W;
+  float* dw;              /* OIHW [Cout,Cin,3,3], ACCUMULATED into (caller zeroes) */
+  float* db;              /* [Cout] accumulated into, or NULL */
+} cgs_wgrad3x3_args;
+
+/* Weight + bias gradient of Conv2d(k=3,s=1,p=1): replaces autograd's conv weight-gradient
+ * for every conv row of SURVEY.md §8a (a20'). */
+int cgs_wgrad3x3(const cgs_wgrad3x3_args* a, void* stream);
+
+/* NewCritic tail: features[13..15] + crit (nets.py:183-195): Dropout, Conv2d(16c,32c,4) on the
+ * 4x4 map, ReLU (-> embeds[4]), Flatten, Linear, ReLU, Dropout, Linear, Sigmoid.
+ * e3 [B,4,4,C3] NHWC; m_e3 / m_v optional dropout masks ([B,4,4,C3], [B,NB]);
+ * outputs e4 [B,NB], v [B,NB] (post-ReLU, pre-dropout, saved for backward), pred [B]. */
+int cgs_head_fwd(const float* e3, const float* m_e3, const float* m_v,
+                 const float* w14, const float* b14, const float* w1, const float* b1,
+                 const float* w2, const float* b2,
+                 int32_t B, int32_t C3, int32_t NB,
+                 float* e4, float* v, float* pred, void* stream);
+
+/* Backward of cgs_head_fwd.  dpred [B] and optional de4 [B,NB] (gradient reaching embeds[4]
+ * from the decoder).  Parameter gradients are ACCUMULATED (any may be NULL to skip all
+ * parameter gradients: pass dw14 == NULL); de3 [B,4,4,C3] is written (NULL to skip). */
+int cgs_head_bwd(const float* e3, const float* m_e3, const float* m_v,
+                 const float* w14, const float* w1, const float* w2,
+                 const float* e4, const float* v, const float* pred,
+                 const float* dpred, const float* de4,
+                 int32_t B, int32_t C3, int32_t NB,
+                 float* dw14, float* db14, float* dw1, float* db1, float* dw2, float* db2,
+                 float* de3, void* stream);
+
+/* Dense layer out[B,N] = in[B,K] * w[N,K]^T + bias: UnetDecoder.dec[4], the 1x1 conv on the
+ * 1x1 bottleneck (nets.py:484,500-501). */
+int cgs_dense_fwd(const float* in, const float* w, const float* bias,
+                  int32_t B, int32_t K, int32_t N, float* out, void* stream);
+/* Its backward: din[B,K] written (or NULL); dw[N,K], db[N] accumulated (or NULL). */
+int cgs_dense_bwd(const float* in, const float* w, const float* dout,
+                  int32_t B, int32_t K, int32_t N, float* din, float* dw, float* db, void* stream);
+
+/* Occlusion blend out = a*(1-z) + z*b over [B,H,W,C] with z [B,H,W,1] (main.py:395,406). */
+int cgs_occlude_fwd(const float* a, const float* b, const float* z, int64_t npix, int32_t C,
+                    float* out, void* stream);
+/* dz[p] = sum_c (b-a)[p,c]*g[p,c]; optional da = g*(1-z), db_ = g*z. */
+int cgs_occlude_bwd(const float* a, const float* b, const float* z, const float* g,
+                    int64_t npix, int32_t C, float* dz, float* da, float* db_, void* stream);
+
+/* loss[0] = scale * mean((p-t)^2) over n (F.mse_loss, main.py:195,400,411); grad (optional)
+ * = gscale * 2*(p-t)/n.  `bce` != 0 selects F.binary_cross_entropy (main.py:193). */
+int cgs_pred_loss(const float* p, const float* t, int32_t n, int32_t bce, float gscale,
+                  float* loss, float* grad, void* stream);
+
+/* Mask regulariser (main.py:415-429): loss[0] = L1*mean|vf*z| + L2*mean((vf*z)^2) with
+ * vf = 1 (staticnorm) or 1 - vpred[frame]; grad (optional) [n] written = gscale * d loss / d z. */
+int cgs_mask_reg(const float* z, const float* vpred, int64_t n, int32_t per_frame,
+                 float l1, float l2, float gscale, float* loss, float* grad, void* stream);
+
+/* uint8 NHWC frames -> fp32 /255 with the circular W-roll of Handler.shift_batch
+ * (main.py:584-591, 189): out[n,y,x,c] = in[n,y,(x+roll) mod W,c]/255. */
+int cgs_frames_to_float(const uint8_t* in, int32_t B, int32_t H, int32_t W, int32_t C,
+                        int32_t roll, float* out, void* stream);
+
+/* Adam, torch.optim.Adam defaults (main.py:178,331-334), over a flat parameter bucket.
+ * step_count is the 1-based step index after increment, read from device memory so the
+ * call can sit inside a CUDA graph. */
+int cgs_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
+                  double lr, double beta1, double beta2, double eps, const int32_t* step_count,
+                  float grad_scale, void* stream);
+
+/* hard[i] = z[i] >= thresh (main.py:1164) or z[i] > thresh when strict (main.py:964). */
+int cgs_threshold(const float* z, int64_t n, float thresh, int32_t strict, uint8_t* hard, void* stream);
+
+const char* cgs_last_error(void);
+int cgs_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

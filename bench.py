@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the Critic/Hourglass hot path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload critic_train|hourglass|infer]
+
+Default workload (BASELINE.json configs[1], the configuration the metric is quoted on): one critic
+training step (uint8->float, NewCritic fwd with dropout, MSE, backward, Adam) on synthetic 64x64x3
+frames with sparse-reward labels, batch 256 per GPU (weak scaling).  A "step" is one such pass.
+  value : whole-job frames/s with inputs resident in HBM (CUDA-graph replay, CUDA-event timed,
+          L2 flushed between timed iterations)
+  e2e   : the same step through the public API with pinned HOST uint8 frames + labels: H2D copies
+          and a D2H read of the loss inside the timed region
+`--impl reference` times the reference's CPU path (oracle port, all host threads) on the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "critic_train_frames_per_s"
+WORKLOADS = {
+    "critic_train": "critic training step, batch 256/GPU, synthetic 64x64x3 uint8 frames + sparse-reward labels (BASELINE configs[1])",
+    "hourglass": "critic-guided Hourglass step, frozen critic, inject, L1, batch 1024/GPU (BASELINE configs[2])",
+    "infer": "mask inference (-process path, threshold 0.1), batch 256/GPU (BASELINE configs[0])",
+}
+# SURVEY.md §8d / BASELINE.md: algorithmic FLOPs per frame (2*MAC, conv+linear), chfak 1 | 5
+FLOPS = {"critic_train": {1: 8460480, 5: 140729280}, "hourglass": {1: 67944832, 5: 665240704},
+         "infer": {1: 20959296, 5: 186601792}}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_batch(workload, B, seed):
+    import cgs_b200.synth as synth
+    X, Y, _ = synth.synthetic_frames(2 * B if workload == "hourglass" else B, seed=seed)
+    return X, Y
+
+
+# --------------------------------------------------------------------------- reference arm (CPU)
+def oracle_step_fn(workload, chfak, B):
+    """The reference's CPU path restated by the oracle (reference classes are not on the GPU box)."""
+    from oracle import torch_ref
+    import cgs_b200.synth as synth
+    torch.manual_seed(0)
+    p = 0.3
+    csd = {k: torch.from_numpy(v).requires_grad_(True) for k, v in synth.perturbed_state(synth.critic_shapes(chfak), 0).items()}
+    msd = {k: torch.from_numpy(v).requires_grad_(True) for k, v in synth.perturbed_state(synth.masker_shapes(chfak), 1).items()}
+    X, Y = make_batch(workload, B, 0)
+    Xt = torch.from_numpy(X)
+    Yt = torch.from_numpy(Y[1, :B]).float()
+    c = chfak
+    drop = lambda: tuple(torch.nn.functional.dropout(torch.ones(s), p, True)
+                         for s in ((B, 8 * c, 8, 8), (B, 16 * c, 4, 4), (B, 32 * c)))
+    if workload == "critic_train":
+        opt = torch.optim.Adam(csd.values())
+
+        def step():
+            XP = Xt.permute(0, 3, 1, 2).float() / 255.0
+            loss, _ = torch_ref.critic_loss(csd, XP, Yt, masks=drop())
+            opt.zero_grad(); loss.backward(); opt.step()
+            return loss.item()
+    elif workload == "hourglass":
+        opt = torch.optim.Adam(msd.values())
+
+        def step():
+            A = Xt[:B].permute(0, 3, 1, 2).float() / 255.0
+            Bf = Xt[B:].permute(0, 3, 1, 2).float() / 255.0
+            loss, _, _ = torch_ref.hourglass_losses(csd, msd, A, Bf, Yt, live=False, inject=True, L1=0.5,
+                                                    masks=[drop() for _ in range(4)])
+            opt.zero_grad(); loss.backward(); opt.step()
+            return loss.item()
+    else:
+        def step():
+            batch = (torch.from_numpy(X / 255.0)).permute(0, 3, 1, 2).float()
+            pred, mask, hard = torch_ref.segment_batch(csd, msd, batch, 0.1)   # autograd on, as main.py:1139
+            return float(mask.detach().numpy().sum())
+    return step
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    B = args.batch
+    step = oracle_step_fn(args.workload, args.chfak, B)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = B * args.steps / dt
+    line = {"metric": METRIC if args.workload == "critic_train" else args.workload + "_frames_per_s", "value": v,
+            "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOADS[args.workload], "batch_per_step": B, "chfak": args.chfak},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{args.steps} full steps of batch {B} (oracle/torch_ref.py, torch {torch.__version__} CPU fp32)"},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- our arm (GPU)
+def time_kernel(fn, flush, iters=20):
+    """Average device time of one launch: CUDA events on the launch stream, L2 flushed in between."""
+    for _ in range(3):
+        fn()
+    evs = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    return float(np.mean([s.elapsed_time(e) for s, e in evs])) * 1e-3
+
+
+def kernel_rooflines(B, chfak, flush, hbm_gbs):
+    """Dominant-kernel candidates of the critic step, timed in isolation."""
+    from cgs_b200 import ops
+    from cgs_b200._lib import SRC_PLAIN, SRC_POOLBWD, EPI_RELU_POOL
+    dev = "cuda"
+    c = chfak
+    out = []
+    for name, H, Cin, Cout in (("features.0", 64, 3, 8 * c), ("features.3", 32, 8 * c, 8 * c)):
+        x = torch.rand(B, H, H, Cin, device=dev)
+        w = torch.rand(Cout, Cin, 3, 3, device=dev) - 0.5
+        b = torch.zeros(Cout, device=dev)
+        e = torch.empty(B, H // 2, H // 2, Cout, device=dev)
+        idx = torch.empty(B, H // 2, H // 2, Cout, device=dev, dtype=torch.uint8)
+        de = torch.rand_like(e)
+        dw, db = torch.zeros_like(w), torch.zeros_like(b)
+        t_f = time_kernel(lambda: ops.conv3x3(ops._src(SRC_PLAIN, Cin, x), w, b, B, H, H, Cout, EPI_RELU_POOL, e, idx_out=idx), flush)
+        t_w = time_kernel(lambda: ops.wgrad3x3(ops._src(SRC_PLAIN, Cin, x), ops._src(SRC_POOLBWD, Cout, de, e, idx), B, H, H, dw, db), flush)
+        by_f = x.numel() * 4 + e.numel() * 5 + w.numel() * 4
+        by_w = x.numel() * 4 + e.numel() * 9 + w.numel() * 4
+        fl = 2 * B * H * H * Cin * Cout * 9
+        out.append({"kernel": f"conv3x3_kernel fprop+relu+pool {name}", "bytes": by_f, "flops": fl, "sec": t_f})
+        out.append({"kernel": f"wgrad3x3_kernel {name}", "bytes": by_w, "flops": fl, "sec": t_w})
+    for k in out:
+        k["gbs"] = k["bytes"] / k["sec"] / 1e9
+        k["tflops"] = k["flops"] / k["sec"] / 1e12
+        k["frac_hbm"] = k["gbs"] / hbm_gbs
+    return out
+
+
+def run_ours(args, rank, world):
+    import torch.distributed as dist
+    from cgs_b200 import ops
+    from cgs_b200.graph_step import GraphedCriticStep, GraphedHourglassStep, GraphedSegment
+    from cgs_b200.train_handler import Handler, parse_args
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    B, W, K = args.batch, args.warmup, args.steps
+    hargs = parse_args(["--chfak", str(args.chfak)] + (["-frozen"] if args.workload == "hourglass" else []))
+    torch.manual_seed(0)
+    H = Handler(hargs, device=dev, rank=rank, world_size=world, process_group=group)
+    H.critic.to(dev); H.masker.to(dev)
+    X, Y = make_batch(args.workload, B, seed=rank)
+    Xh = torch.from_numpy(X).pin_memory()
+    Yh = torch.from_numpy(Y[1, :B]).float().pin_memory()
+    if args.workload == "critic_train":
+        step = GraphedCriticStep(H, B)
+        host = (Xh, Yh)
+    elif args.workload == "hourglass":
+        step = GraphedHourglassStep(H, B)
+        host = (Xh[:B], Xh[B:], Yh)
+    else:
+        step = GraphedSegment(H, B, 0.1)
+        host = (Xh,)
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    sync = (lambda: (dist.barrier(), torch.cuda.synchronize())) if world > 1 else torch.cuda.synchronize
+
+    # ---- value: inputs resident in HBM, graph replay, per-step CUDA events, L2 flushed between steps
+    step.load(*host)
+    for _ in range(max(W, 3)):
+        step.replay()
+    sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = []
+    t_wall0 = time.perf_counter()
+    for _ in range(K):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); step.replay(); e.record()
+        evs.append((s, e))
+    sync()
+    t_wall = time.perf_counter() - t_wall0
+    dev_s = sum(s.elapsed_time(e) for s, e in evs) * 1e-3
+    # ---- e2e: pinned host buffers -> H2D -> step -> D2H loss read, every step
+    for _ in range(3):
+        out = step(*host)
+    sync()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(K):
+        out = step(*host)
+        res = out if torch.is_tensor(out) else out[0]
+        val = res.reshape(-1)[:1].cpu() if args.workload != "infer" else out[2].cpu()   # loss scalar / hard masks
+        d2h = val.numel() * val.element_size()
+    sync()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s, e2e_s = t.tolist()
+    if rank == 0:
+        hbm, tf, which = peaks()
+        value = world * B * K / dev_s
+        line = {"metric": METRIC if args.workload == "critic_train" else args.workload + "_frames_per_s",
+                "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+                "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOADS[args.workload], "batch_per_gpu": B, "global_batch": B * world,
+                           "chfak": args.chfak, "parallelism": f"dp{world}", "timing": "cuda events per step, L2 flushed "
+                           "(256 MiB memset) between timed steps", "graph": True},
+                "e2e": {"value": world * B * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h},
+                "gpu_launches": step.launches * K, "launches_per_step": step.launches,
+                "wall_ms_per_step_incl_flush": 1e3 * t_wall / K, "clocks": clocks,
+                "achieved_tflops": FLOPS[args.workload].get(args.chfak, 0) * value / 1e12}
+        if world == 1 and not args.no_extras:
+            ks = kernel_rooflines(B, args.chfak, flush, hbm)
+            top = max(ks, key=lambda k: k["sec"])
+            line["roofline"] = {"bound": "hbm", "achieved": top["gbs"], "peak": hbm, "unit": "GB/s",
+                                "frac": top["gbs"] / hbm, "traffic": None, "kernel": top["kernel"],
+                                "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
+                                "launch_us": top["sec"] * 1e6, "achieved_tflops_fp32": top["tflops"]}
+            line["kernels"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in kk.items()} for kk in ks]
+            # CPU baseline: oracle port on the host cores, bounded sample
+            cores = os.cpu_count()
+            torch.set_num_threads(cores)
+            ostep = oracle_step_fn(args.workload, args.chfak, B)
+            ostep(); ostep()
+            n, t0 = 0, time.perf_counter()
+            while time.perf_counter() - t0 < 10.0 and n < 200:
+                ostep(); n += 1
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": B * n / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{n} full steps of batch {B} in {dt:.1f}s (oracle/torch_ref.py on torch CPU fp32)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="critic_train", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--chfak", type=int, default=1)
+    ap.add_argument("--no-extras", action="store_true", help="skip per-kernel roofline and CPU baseline legs")
+    args = ap.parse_args()
+    if args.batch == 0:
+        args.batch = 1024 if args.workload == "hourglass" else 256
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        if args.workload == "hourglass":
+            args.batch = min(args.batch, 64)      # bounded sample: ~90 ms/step on CPU at the reference's own batch
+        return run_reference(args, rank)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
+    run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

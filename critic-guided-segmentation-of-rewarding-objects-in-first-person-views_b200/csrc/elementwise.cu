@@ -127,7 +127,8 @@ __global__ void mask_reg_kernel(const float* __restrict__ z, const float* __rest
 
 // ---------------------------------------------------------------- frames uint8 -> float
 __global__ void frames_to_float_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int C, int roll,
-                                       float* __restrict__ out) {
+                                       const int* __restrict__ roll_dev, float* __restrict__ out) {
+  if (roll_dev) roll = *roll_dev;
   const int64_t total = (int64_t)B * H * W * C;
   const int rowc = W * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -207,9 +208,9 @@ extern "C" int cgs_mask_reg(const float* z, const float* vpred, int64_t n, int32
 }
 
 extern "C" int cgs_frames_to_float(const uint8_t* in, int32_t B, int32_t H, int32_t W, int32_t C, int32_t roll,
-                                   float* out, void* stream) {
+                                   const int32_t* roll_dev, float* out, void* stream) {
   CGS_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && C > 0, "frames_to_float: bad args");
-  frames_to_float_kernel<<<grid_for((int64_t)B * H * W * C, 256), 256, 0, (cudaStream_t)stream>>>(in, B, H, W, C, roll, out);
+  frames_to_float_kernel<<<grid_for((int64_t)B * H * W * C, 256), 256, 0, (cudaStream_t)stream>>>(in, B, H, W, C, roll, roll_dev, out);
   return check_launch("frames_to_float");
 }
 

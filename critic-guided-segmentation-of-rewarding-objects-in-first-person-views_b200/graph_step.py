@@ -1,0 +1,116 @@
+"""CUDA-graph captured training / inference steps.
+
+The reference loops are host-bound (one Python-dispatched ATen kernel per op and 3-4
+`.item()` syncs per step); here one whole step — uint8->float + shift roll,
+forward, loss, backward, [gradient all-reduce], Adam — is captured once on static buffers
+and replayed with a single launch.  Public API:
+
+    step = GraphedCriticStep(handler, batch=256)        # or GraphedHourglassStep / GraphedSegment
+    loss = step(X_u8_host_pinned, Y_host_pinned)        # H2D copy, replay, returns device scalar
+"""
+import torch
+
+from . import ops
+from .train_handler import FlatAdam
+
+
+def _capture(fn, warmup=3, group_sync=None):
+    """Standard whole-step capture: warm up on a side stream, then capture `fn` into a graph."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(warmup):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    n0 = ops.launch_count()
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        out = fn()
+    return g, out, ops.launch_count() - n0
+
+
+class _Graphed:
+    launches = 0
+
+    def load(self, *host):
+        for dst, src in zip(self.static_in, host):
+            dst.copy_(src, non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+    def __call__(self, *host):
+        self.load(*host)
+        return self.replay()
+
+
+class GraphedCriticStep(_Graphed):
+    """One critic_pipe iteration (reference main.py:185-200) as a CUDA graph.  The shift_batch roll is a
+    device int32 (`self.roll`), so it can change per replay: `step.roll.fill_(r)` before the call."""
+
+    def __init__(self, handler, batch, opti=None):
+        H = self.H = handler
+        dev = H.device
+        H.critic.to(dev).train()
+        self.opti = opti or FlatAdam(H.critic.parameters(), process_group=H.group, world_size=H.world)
+        self.X = torch.zeros((batch, 64, 64, 3), dtype=torch.uint8, device=dev)
+        self.Y = torch.zeros((batch,), dtype=torch.float32, device=dev)
+        self.roll = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.static_in = (self.X, self.Y)
+
+        def fn():
+            return H.critic_step(self.X, self.Y, self.opti, roll=self.roll)
+        self.graph, self.out, self.launches = _capture(fn)
+
+
+class GraphedHourglassStep(_Graphed):
+    """One segmentation_training iteration (reference main.py:344-463) as a CUDA graph."""
+
+    def __init__(self, handler, batch, opti=None):
+        H = self.H = handler
+        dev = H.device
+        a = H.args
+        H.critic.to(dev).train()
+        H.masker.to(dev).train()
+        if a.live:
+            params = list(H.critic.parameters()) + list(H.masker.parameters())
+        else:
+            for p in H.critic.parameters():
+                p.requires_grad_(False)
+            params = list(H.masker.parameters())
+        self.opti = opti or FlatAdam(params, process_group=H.group, world_size=H.world)
+        self.X = torch.zeros((batch, 64, 64, 3), dtype=torch.uint8, device=dev)
+        self.CX = torch.zeros((batch, 64, 64, 3), dtype=torch.uint8, device=dev)
+        self.Y = torch.zeros((batch,), dtype=torch.float32, device=dev)
+        self.roll = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.static_in = (self.X, self.CX, self.Y)
+
+        def fn():
+            terms = H.segmentation_step(self.X, self.CX, self.Y, self.opti, roll=self.roll)
+            return torch.stack([terms[k] for k in sorted(terms)])
+        self.graph, self.out, self.launches = _capture(fn)
+        self.term_names = sorted(k for k in ("critic", "replace", "inject", "L1", "L2")
+                                 if (k != "critic" or a.live) and (k != "inject" or a.inject)
+                                 and (k != "L1" or a.L1) and (k != "L2" or a.L2))
+
+
+class GraphedSegment(_Graphed):
+    """One batch of Handler.segment (reference main.py:1134-1164): critic(collect) -> masker -> >= threshold."""
+
+    def __init__(self, handler, batch, threshold=0.1):
+        H = self.H = handler
+        dev = H.device
+        H.critic.to(dev).eval()
+        H.masker.to(dev).eval()
+        self.X = torch.zeros((batch, 64, 64, 3), dtype=torch.uint8, device=dev)
+        self.static_in = (self.X,)
+
+        def fn():
+            with torch.no_grad():
+                x = ops.frames_to_float(self.X, 0).permute(0, 3, 1, 2)
+                pred, embeds = H.critic(x, collect=True)
+                mask, hard = H.masker.forward_hard(x, embeds, threshold)
+            return pred, mask, hard
+        self.graph, self.out, self.launches = _capture(fn)

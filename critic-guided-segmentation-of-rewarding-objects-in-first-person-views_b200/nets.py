@@ -9,6 +9,8 @@ identically.  The `nn.Conv2d` / `nn.Linear` objects are parameter containers onl
 `forward()` dispatches to the fused sm_100a kernels of libcgs_b200.so via
 `cgs_b200.ops`.  CUDA only: calling forward on CPU tensors raises (no fallback).
 """
+from collections import deque
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -66,6 +68,8 @@ class NewCritic(nn.Module):
 
     def _dropout_masks(self, B, device):
         if self._forced_masks is not None:
+            if isinstance(self._forced_masks, deque):     # one entry per forward call, in call order
+                return self._forced_masks.popleft()
             return self._forced_masks
         if not self.training or self.p <= 0.0:
             return None, None, None

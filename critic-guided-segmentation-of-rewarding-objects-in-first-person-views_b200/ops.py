@@ -315,7 +315,7 @@ class MaskReg(torch.autograd.Function):
         return grad * g, None, None, None
 
 
-def frames_to_float(frames_u8, roll=0):
+def frames_to_float(frames_u8, roll=0, roll_dev=None):
     """uint8 NHWC [B,H,W,C] (device) -> fp32 NHWC /255 with circular W-roll (main.py:189,584-591).
     roll > 0 == `cat(X[:, :, roll:], X[:, :, :roll])`; roll < 0 == the `-xshift` branch."""
     if not frames_u8.is_cuda:
@@ -323,7 +323,7 @@ def frames_to_float(frames_u8, roll=0):
     x = _c(frames_u8)
     B, H, W, Cc = x.shape
     out = torch.empty((B, H, W, Cc), device=x.device, dtype=torch.float32)
-    _call("cgs_frames_to_float", _p(x, torch.uint8), B, H, W, Cc, int(roll), _p(out), _stream())
+    _call("cgs_frames_to_float", _p(x, torch.uint8), B, H, W, Cc, int(roll), _p(roll_dev, torch.int32), _p(out), _stream())
     return out
 
 

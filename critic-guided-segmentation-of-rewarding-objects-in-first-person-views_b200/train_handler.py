@@ -1,0 +1,361 @@
+"""Host-side mirror of the reference `Handler` hot loops (reference main.py:66-575, 1103-1167;
+TrainHandler.py:74-1096 is the same code): critic regression (`critic_pipe`), pos/neg
+split (`extract_contrastive_data`), critic-guided Hourglass training
+(`segmentation_training`) and `-process` mask inference (`segment`).
+
+Same flag names, defaults, RNG draw order (torch RNG for shift_batch, numpy RNG for the
+contrastive sampling), checkpoint paths and state_dict layout as the reference; the
+arithmetic runs in libcgs_b200.so.  Visualisation, MineRL collection, CRF and video
+output are out of scope.
+
+Data-parallel: one process per GPU; every rank runs the same loop on its batch shard
+and `FlatAdam` all-reduces the flat gradient bucket (NCCL) before the update.
+"""
+import argparse
+import math
+import os
+from itertools import chain
+
+import numpy as np
+import torch
+
+from . import ops
+from .nets import NewCritic, UnetDecoder
+
+
+def build_parser():
+    """The hot-path subset of reference main.py:1462-1533, same names and defaults."""
+    p = argparse.ArgumentParser()
+    for flag in ("-train", "-frozen", "-noinject", "-separate", "-noevalmode", "-process", "-eval", "-salience"):
+        p.add_argument(flag, action="store_true")
+    for flag in ("-masker", "-critic", "-cload", "-mload", "-staticnorm"):
+        p.add_argument(flag, type=bool, default=True)
+    p.add_argument("--eval-thresh", type=float, default=0.05)
+    p.add_argument("--dropout", type=float, default=0.3)
+    p.add_argument("--threshrew", type=float, default=0)
+    p.add_argument("--datamode", type=str, default="trunk")
+    p.add_argument("--chfak", type=int, default=1)
+    p.add_argument("--shift", type=int, default=12)
+    p.add_argument("--lfak", type=int, default=5)
+    p.add_argument("--neck", type=int, default=32)
+    p.add_argument("--cepochs", type=int, default=15)
+    p.add_argument("--mepochs", type=int, default=1)
+    p.add_argument("--high-rew-thresh", type=float, default=0.7)
+    p.add_argument("--low-rew-thresh", type=float, default=0.3)
+    p.add_argument("--L2", type=float, default=0.0)
+    p.add_argument("--L1", type=float, default=0.5)
+    p.add_argument("--saveevery", type=int, default=5)
+    p.add_argument("--rewidx", type=int, default=1)
+    p.add_argument("--testsize", type=int, default=5000)
+    p.add_argument("--datasize", type=int, default=100000)
+    p.add_argument("--model", type=str, default="default-model")
+    p.add_argument("--source-imgs", type=str, default="")
+    p.add_argument("--mask-output-imgs", type=str, default="results")
+    p.add_argument("--binarymaskthreshold", type=float, default=0.5)
+    return p
+
+
+def parse_args(argv=()):
+    args = build_parser().parse_args(list(argv))
+    args.live = not args.frozen          # main.py:1537
+    args.inject = not args.noinject      # main.py:1538
+    args.name = args.model               # main.py:1539
+    return args
+
+
+class FlatAdam:
+    """torch.optim.Adam(params) with default hyper-parameters (reference main.py:178, 331-334) over ONE
+    flat fp32 bucket: parameters and gradients are re-pointed to views of two flat buffers, so
+    `zero_grad` is one memset, the update is one kernel (cgs_adam_step) and the data-parallel
+    gradient exchange is one all-reduce."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, process_group=None, world_size=1):
+        self.params = [p for p in params]
+        assert self.params, "FlatAdam: no parameters"
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        self.gflat = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.step_count = torch.zeros(1, device=dev, dtype=torch.int32)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.flat[off:off + k].copy_(p.data.reshape(-1))
+                p.data = self.flat[off:off + k].view(p.shape)
+                p.grad = self.gflat[off:off + k].view(p.shape)
+                off += k
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.group, self.world = process_group, world_size
+
+    def zero_grad(self):
+        self.gflat.zero_()
+
+    def step(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.gflat, group=self.group)   # ranks pre-scale their losses by 1/world
+        self.step_count.add_(1)
+        ops.adam_step(self.flat, self.gflat, self.m, self.v, self.step_count, self.lr, self.betas, self.eps)
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def occlude(A, B, Z):
+    """`A*(1-Z)+Z*B` on logical-NCHW tensors (reference main.py:395,406), one fused kernel each way."""
+    return ops.occlude(_nhwc(A), _nhwc(B), _nhwc(Z)).permute(0, 3, 1, 2)
+
+
+class Handler:
+    def __init__(self, args, device=None, rank=0, world_size=1, process_group=None):
+        self.args = args
+        argdict = args.__dict__
+        self.device = torch.device(device if device is not None else "cuda")
+        self.rank, self.world, self.group = rank, world_size, process_group
+        self.criticname, self.maskername = "critic", "masker"
+        self.reset_models()
+        self.models = {self.criticname: self.critic, self.maskername: self.masker}
+        # identical naming to reference main.py:86-102
+        self.critic_args = "-".join(f"{a}={argdict[a]}" for a in
+                                    ["rewidx", "cepochs", "datamode", "datasize", "threshrew", "shift", "chfak", "dropout"]
+                                    if argdict[a])
+        self.masker_args = "-".join(f"{a}={argdict[a]}" for a in ["mepochs", "L1", "L2", "inject"] if argdict[a])
+        self.path = f"{args.name}/"
+        self.save_path = self.path + "saves/"
+        self.save_paths = {self.criticname: f"{self.save_path}critic-{self.critic_args}.pt",
+                           self.maskername: f"{self.save_path}masker-{self.masker_args}.pt"}
+        self.contrastive_batchsize = 32      # main.py:309
+        self.closs_log, self.seg_log = [], []
+
+    def reset_models(self):
+        a = self.args
+        self.critic = NewCritic(bottleneck=a.neck, chfak=a.chfak, dropout=a.dropout)      # main.py:108
+        self.masker = UnetDecoder(bottleneck=a.neck, chfak=a.chfak)                       # main.py:109
+        if a.separate:
+            self.sepcrit = NewCritic(bottleneck=a.neck, chfak=a.chfak, dropout=a.dropout)  # main.py:111
+
+    # ------------------------------------------------------------------ data / checkpoints
+    def set_data(self, X, Y, I=None, batch_size=64, shuffle=True):
+        """`load_data` (main.py:113-129) for arrays already in memory (MineRL collection is out of scope)."""
+        a = self.args
+        self.X, self.Y = X, Y
+        self.I = I if I is not None else np.arange(len(X), dtype=np.int32)
+        if a.threshrew:
+            self.Y = (self.Y > a.threshrew).astype(float)
+        self.train_loader = torch.utils.data.DataLoader(
+            torch.utils.data.TensorDataset(torch.from_numpy(self.X), torch.from_numpy(self.Y).t(),
+                                           torch.arange(self.X.shape[0], dtype=torch.int32)),
+            batch_size=batch_size, shuffle=shuffle)
+
+    def load_models(self, modelnames=()):
+        for model in (modelnames or self.models.keys()):
+            path = self.save_paths[model]
+            if not os.path.exists(path):
+                if not self.args.train:
+                    print(f"{path} not found")
+                return False
+            self.models[model].load_state_dict(torch.load(path, map_location=self.device))
+        return True
+
+    def save_models(self, modelnames=()):
+        if self.rank != 0:
+            return
+        os.makedirs(self.save_path, exist_ok=True)
+        for model in (modelnames or self.models.keys()):
+            torch.save(self.models[model].state_dict(), self.save_paths[model])
+
+    # ------------------------------------------------------------------ helpers
+    def _opt(self, params):
+        return FlatAdam(params, process_group=self.group, world_size=self.world)
+
+    def _shift_roll(self):
+        """The two torch.rand(1) draws of shift_batch (main.py:585-586) -> signed roll."""
+        xshift = int(self.args.shift * torch.rand(1))
+        return xshift if torch.rand(1) > 0.5 else -xshift
+
+    def _to_input(self, X_u8, roll=0):
+        """uint8 NHWC (host or device) -> logical NCHW fp32 /255 on device (main.py:189,360)."""
+        x = X_u8 if torch.is_tensor(X_u8) else torch.from_numpy(np.ascontiguousarray(X_u8))
+        x = x.to(self.device, non_blocking=True)
+        if torch.is_tensor(roll):                      # device int32 scalar: graph-replayable shift
+            return ops.frames_to_float(x, 0, roll).permute(0, 3, 1, 2)
+        return ops.frames_to_float(x, roll).permute(0, 3, 1, 2)
+
+    def _shard(self, n):
+        """This rank's slice of a global batch of n."""
+        per = math.ceil(n / self.world)
+        return slice(self.rank * per, min(n, (self.rank + 1) * per))
+
+    # ------------------------------------------------------------------ critic regression
+    def critic_step(self, X_u8, Y, opti, roll=0):
+        """Loop body of critic_pipe (main.py:185-200) on this rank's shard; returns the loss tensor."""
+        a = self.args
+        XP = self._to_input(X_u8, roll)
+        Yd = Y.to(self.device, non_blocking=True).float()
+        pred = self.critic(XP).squeeze(1)
+        loss = ops.pred_loss(pred, Yd, bce=bool(a.threshrew))
+        opti.zero_grad()
+        (loss / self.world if self.world > 1 else loss).backward()
+        opti.step()
+        return loss.detach()
+
+    def critic_pipe(self, mode="train"):
+        a = self.args
+        if a.cload and self.load_models([self.criticname]):
+            print("loaded critic, no new training")
+            return
+        critic = self.critic.to(self.device)
+        opti = self._opt(critic.parameters())
+        for epoch in range(int(mode == "test") or a.cepochs):
+            for b_idx, (X, Y, I) in enumerate(self.train_loader):
+                roll = self._shift_roll() if a.shift else 0
+                sl = self._shard(len(X))
+                loss = self.critic_step(X[sl], Y[sl, a.rewidx], opti, roll)
+                self.closs_log.append(loss)
+            if not (epoch + 1) % a.saveevery:
+                self.save_models([self.criticname])
+        self.closs_log = [float(v) for v in torch.stack(self.closs_log).cpu()] if self.closs_log else []
+
+    # ------------------------------------------------------------------ pos / neg split
+    def extract_contrastive_data(self):
+        a = self.args
+        critic = self.critic.to(self.device).eval()
+        batchsize = 128
+        preds = []
+        with torch.no_grad():
+            for bidx in range(math.ceil(len(self.X) / batchsize)):
+                batch = self._to_input(self.X[bidx * batchsize:(bidx + 1) * batchsize])
+                preds.append(critic(batch).squeeze(1))
+        preds = torch.cat(preds, dim=0).cpu()
+        positives = (preds > a.high_rew_thresh).numpy()
+        negatives = (preds < a.low_rew_thresh).numpy()
+        assert positives.sum() >= 500 and negatives.sum() >= 500          # main.py:281
+        self.Xpos, self.Ypos = self.X[positives], self.Y[:, positives]
+        self.Xneg, self.Yneg = self.X[negatives], self.Y[:, negatives]
+        assert preds[torch.from_numpy(positives)].mean() > a.high_rew_thresh   # main.py:302
+        self.XposIdxs = np.arange(len(self.Xpos))
+        self.XnegIdxs = np.arange(len(self.Xneg))
+        self.ContrastIdxs = np.arange(len(self.Xneg))
+        cb = self.contrastive_batchsize
+        self.get_contrastive_idxs = lambda: (np.random.choice(self.XposIdxs, cb),
+                                             np.random.choice(self.XnegIdxs, cb),
+                                             np.random.choice(self.ContrastIdxs, 2 * cb))
+        self.preds = preds
+
+    # ------------------------------------------------------------------ Hourglass training
+    def segmentation_losses(self, A, B, Y=None):
+        """Loss terms of one segmentation_training step (main.py:364-429).  A, B logical NCHW."""
+        a = self.args
+        critic, masker = self.critic, self.masker
+        pred, embeds = critic(A, collect=True)
+        with torch.no_grad():
+            negpred = critic(B).squeeze(1)
+        pred = pred.squeeze(1)
+        terms = {}
+        loss = 0
+        if a.live:
+            terms["critic"] = ops.pred_loss(pred, Y, bce=bool(a.threshrew))
+            loss = loss + a.lfak * terms["critic"]
+        if a.separate:
+            _, embeds = self.sepcrit(A, collect=True)
+        Z = masker(A, embeds)
+        replaced = occlude(A, B, Z)
+        terms["replace"] = ops.pred_loss(critic(replaced).squeeze(1), negpred)
+        loss = loss + terms["replace"]
+        if a.inject:
+            injected = occlude(B, A, Z)
+            terms["inject"] = ops.pred_loss(critic(injected).squeeze(1), pred.detach())
+            loss = loss + terms["inject"]
+        vpred = None if a.staticnorm else pred.detach()
+        if a.L1:
+            terms["L1"] = ops.mask_reg(_nhwc(Z), vpred, l1=a.L1)
+            loss = loss + terms["L1"]
+        if a.L2:
+            terms["L2"] = ops.mask_reg(_nhwc(Z), vpred, l2=a.L2)
+            loss = loss + terms["L2"]
+        return loss, terms, Z
+
+    def segmentation_step(self, X_u8, CX_u8, Y, opti, roll=0):
+        A = self._to_input(X_u8, roll)
+        B = self._to_input(CX_u8)
+        Yd = None if Y is None else Y.to(self.device).float()
+        loss, terms, _ = self.segmentation_losses(A, B, Yd)
+        opti.zero_grad()
+        (loss / self.world if self.world > 1 else loss).backward()
+        opti.step()
+        return {k: v.detach() for k, v in terms.items()}
+
+    def segmentation_training(self):
+        a = self.args
+        self.extract_contrastive_data()
+        critic = self.critic.to(self.device).train()
+        masker = self.masker.to(self.device).train()
+        sep = [self.sepcrit.to(self.device).train()] if a.separate else []
+        if a.live:
+            opti = self._opt(chain(critic.parameters(), masker.parameters(), *[s.parameters() for s in sep]))
+        else:
+            # the reference leaves requires_grad on and merely omits the critic from Adam (main.py:334);
+            # its critic gradients are never read, so they are not computed here
+            for p in critic.parameters():
+                p.requires_grad_(False)
+            opti = self._opt(chain(masker.parameters(), *[s.parameters() for s in sep]))
+        try:
+            for epoch in range(a.mepochs):
+                for b_idx in range(math.ceil(self.Xpos.shape[0] / self.contrastive_batchsize)):
+                    Hidx, Lidx, Cidx = self.get_contrastive_idxs()
+                    X = np.concatenate((self.Xpos[Hidx], self.Xneg[Lidx]), axis=0)
+                    Y = torch.from_numpy(np.concatenate((self.Ypos[a.rewidx, Hidx], self.Yneg[a.rewidx, Lidx])))
+                    CX = self.Xneg[Cidx]
+                    roll = self._shift_roll() if a.shift else 0
+                    sl = self._shard(len(X))
+                    self.seg_log.append(self.segmentation_step(X[sl], CX[sl], Y[sl], opti, roll))
+                if not (epoch + 1) % a.saveevery:
+                    self.save_models([self.maskername])
+        finally:
+            if not a.live:
+                for p in critic.parameters():
+                    p.requires_grad_(True)
+        self.seg_log = [{k: float(v) for k, v in t.items()} for t in self.seg_log]
+
+    # ------------------------------------------------------------------ -process
+    def segment_arrays(self, X_u8, batchsize=128):
+        """Loop of Handler.segment (main.py:1130-1167) on uint8 frames: returns (preds, M, hardM)."""
+        a = self.args
+        train = bool(a.noevalmode)
+        critic = self.critic.to(self.device).train(train)
+        masker = self.masker.to(self.device).train(train)
+        preds, M, hard = [], [], []
+        with torch.no_grad():
+            for bidx in range(0, len(X_u8), batchsize):
+                batch = self._to_input(X_u8[bidx:bidx + batchsize])
+                pred, embeds = critic(batch, collect=True)
+                if a.separate:
+                    _, embeds = self.sepcrit.to(self.device).train(train)(batch, collect=True)
+                if a.binarymaskthreshold:
+                    mask, hm = masker.forward_hard(batch, embeds, a.binarymaskthreshold)
+                    hard.append(hm.cpu().numpy().astype(bool))
+                else:
+                    mask = masker(batch, embeds)
+                preds.append(pred.squeeze(1).cpu().numpy())
+                M.append(mask.cpu().numpy())
+        M = np.concatenate(M, axis=0)
+        return np.concatenate(preds, axis=0), M, (np.concatenate(hard, axis=0) if hard else None)
+
+    def segment(self, folder):
+        """`-process`: PNG folder in, mask PNGs out (main.py:1103-1223; raw + thresholded columns)."""
+        from PIL import Image
+        names = os.listdir(folder)
+        X = np.stack([np.array(Image.open(f"{folder}/{n}")) for n in names]).astype(np.uint8)
+        names = [n[:-1 - n[::-1].index(".")] for n in names if "." in n]
+        preds, M, hardM = self.segment_arrays(X)
+        out = self.args.mask_output_imgs
+        os.makedirs(out, exist_ok=True)
+        cols = [("raw-mask", M)] + ([("thresholded-mask", hardM)] if hardM is not None else [])
+        for fidx in range(len(X)):
+            for cname, arr in cols:
+                img = np.repeat(arr[fidx].transpose(1, 2, 0).astype(np.float64), 3, axis=2)
+                Image.fromarray((img * 255).astype(np.uint8)).save(f"{out}/{names[fidx]}-{cname}.png")
+        return preds, M, hardM

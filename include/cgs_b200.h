@@ -133,9 +133,10 @@ int cgs_mask_reg(const float* z, const float* vpred, int64_t n, int32_t per_fram
                  float l1, float l2, float gscale, float* loss, float* grad, void* stream);
 
 /* uint8 NHWC frames -> fp32 /255 with the circular W-roll of Handler.shift_batch
- * (main.py:584-591, 189): out[n,y,x,c] = in[n,y,(x+roll) mod W,c]/255. */
+ * (main.py:584-591, 189): out[n,y,x,c] = in[n,y,(x+roll) mod W,c]/255.  If roll_dev != NULL the
+ * roll is read from device memory instead (so a captured CUDA graph can vary it per replay). */
 int cgs_frames_to_float(const uint8_t* in, int32_t B, int32_t H, int32_t W, int32_t C,
-                        int32_t roll, float* out, void* stream);
+                        int32_t roll, const int32_t* roll_dev, float* out, void* stream);
 
 /* Adam, torch.optim.Adam defaults (main.py:178,331-334), over a flat parameter bucket.
  * step_count is the 1-based step index after increment, read from device memory so the

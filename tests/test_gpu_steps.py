@@ -1,0 +1,242 @@
+"""GPU: module-, step- and loop-level parity of the drop-in modules / mirrored Handler against
+(a) the committed goldens produced by the unmodified reference and (b) the oracle on the same
+seeded inputs.  fp32 path: rtol 1e-4 (BASELINE.json north_star)."""
+from collections import deque
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, nhwc_masks, sample, step_case, tmasks, tsd
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def close(ours, ref, what, rtol=1e-4, arel=3e-5):
+    ours = np.asarray(ours.detach().cpu().double().numpy() if torch.is_tensor(ours) else ours, dtype=np.float64)
+    ref = np.asarray(ref.detach().cpu().double().numpy() if torch.is_tensor(ref) else ref, dtype=np.float64)
+    assert ours.shape == ref.shape, f"{what}: {ours.shape} vs {ref.shape}"
+    scale = max(np.abs(ref).max(), 1e-30)
+    err = np.abs(ours - ref)
+    bad = err > rtol * np.abs(ref) + arel * scale
+    assert not bad.any(), f"{what}: {bad.sum()}/{bad.size} bad, max err {err.max():.3e} (scale {scale:.3e})"
+
+
+def build(c, p=None):
+    from cgs_b200.nets import NewCritic, UnetDecoder
+    critic = NewCritic(bottleneck=32, chfak=c["K"], dropout=c["p"] if p is None else p)
+    masker = UnetDecoder(bottleneck=32, chfak=c["K"])
+    critic.load_state_dict(tsd(c["csd"]))
+    masker.load_state_dict(tsd(c["msd"]))
+    return critic.to(DEV), masker.to(DEV)
+
+
+def make_args(**kw):
+    from cgs_b200.train_handler import parse_args
+    a = parse_args([])
+    for k, v in kw.items():
+        setattr(a, k, v)
+    a.live, a.inject = not a.frozen, not a.noinject
+    return a
+
+
+@pytest.mark.parametrize("fname", ["step_c1_b6.npz", "step_c2_b3.npz", "step_c5_b2.npz"])
+def test_inference_and_saliency_vs_reference_golden(fname):
+    d = load_golden(fname)
+    c = step_case(d)
+    keep = (lambda a: np.asarray(a)) if c["K"] == 1 else sample
+    critic, masker = build(c)
+    critic.eval(); masker.eval()
+    A = c["A"].to(DEV)                      # channels_last strides, as the reference loops produce
+    pred, embeds = critic(A, collect=True)
+    assert pred.shape == (c["B"], 1) and len(embeds) == 5
+    for e in embeds[:4]:
+        assert e.is_contiguous(memory_format=torch.channels_last)
+    mask, hard = masker.forward_hard(A, embeds, 0.1)
+    assert mask.shape == (c["B"], 1, 64, 64)
+    close(pred, d["inf.pred"], "pred")
+    close(keep(mask.detach().cpu().numpy()), d["inf.mask"], "mask")
+    for i, e in enumerate(embeds):
+        close(keep(e.detach().cpu().numpy()), d[f"inf.e{i}"], f"e{i}")
+        assert abs(e.double().sum().item() - float(d[f"inf.e{i}_sum"])) <= 1e-4 * abs(float(d[f"inf.e{i}_sum"])) + 1e-3
+    counts = [int((mask >= t).sum()) for t in (0.1, 0.3, 0.5, 0.7)]
+    ref = d["inf.hard_count"].tolist()
+    assert all(abs(a - b) <= max(2, 1e-3 * b) for a, b in zip(counts, ref)), (counts, ref)
+    assert torch.equal(hard.bool(), mask >= 0.1)
+    # NCHW-contiguous input must give the same answer (boundary accepts both layouts)
+    pred2 = critic(A.contiguous())
+    assert torch.equal(pred2, pred)
+    # saliency: d mean(pred) / d input (main.py:1137-1148)
+    a = A.clone().requires_grad_(True)
+    critic(a).mean().backward()
+    close(keep(a.grad.abs().sum(1).cpu().numpy()), d["sal.grad_abs_sum"], "saliency", arel=1e-4)
+
+
+@pytest.mark.parametrize("fname", ["step_c1_b6.npz", "step_c2_b3.npz", "step_c5_b2.npz"])
+def test_critic_step_vs_reference_golden(fname):
+    from cgs_b200 import ops
+    d = load_golden(fname)
+    c = step_case(d)
+    keep = (lambda a: np.asarray(a)) if c["K"] == 1 else sample
+    critic, _ = build(c)
+    critic.train()
+    critic._forced_masks = nhwc_masks(c["masks"][0], DEV)
+    A, Y = c["A"].to(DEV), c["Y"].to(DEV)
+    pred = critic(A).squeeze(1)
+    loss = ops.pred_loss(pred, Y)
+    loss.backward()
+    close(loss, d["cstep.loss"], "loss")
+    close(pred, d["cstep.pred"], "pred")
+    for k, v in critic.named_parameters():
+        close(keep(v.grad.cpu().numpy()), d["cstep.g." + k], "g." + k)
+        assert abs(v.grad.double().sum().item() - float(d["cstep.gsum." + k])) <= 1e-4 * float(d["cstep.gabs." + k]) + 1e-7
+    critic.zero_grad()
+    loss = ops.pred_loss(critic(A).squeeze(1), (Y > 0.5).float(), bce=True)
+    loss.backward()
+    close(loss, d["cstep.bce"], "bce")
+    gs = np.array([v.grad.double().sum().item() for v in critic.parameters()])
+    ga = d["cstep.bce.gabs"]
+    assert np.all(np.abs(gs - d["cstep.bce.gsum"]) <= 1e-4 * ga + 1e-7)
+
+
+@pytest.mark.parametrize("fname", ["step_c1_b6.npz", "step_c2_b3.npz", "step_c5_b2.npz"])
+@pytest.mark.parametrize("tag,frozen,noinject,L1,L2,static", [("hg_full", False, False, 0.5, 0.25, True),
+                                                            ("hg_frozen", True, False, 0.5, 0.0, True),
+                                                            ("hg_noinj", False, True, 0.0, 0.5, False)])
+def test_hourglass_step_vs_reference_golden(fname, tag, frozen, noinject, L1, L2, static):
+    from cgs_b200.train_handler import Handler
+    d = load_golden(fname)
+    c = step_case(d)
+    keep = (lambda a: np.asarray(a)) if c["K"] == 1 else sample
+    args = make_args(frozen=frozen, noinject=noinject, L1=L1, L2=L2, staticnorm=static, chfak=c["K"], dropout=c["p"])
+    H = Handler(args, device=DEV)
+    H.critic.load_state_dict(tsd(c["csd"])); H.masker.load_state_dict(tsd(c["msd"]))
+    H.critic.to(DEV).train(); H.masker.to(DEV).train()
+    order = [0, 1, 2] + ([3] if not noinject else [])
+    H.critic._forced_masks = deque(nhwc_masks(c["masks"][i], DEV) for i in order)
+    A, Bf, Y = c["A"].to(DEV), c["Bf"].to(DEV), c["Y"].to(DEV)
+    loss, terms, Z = H.segmentation_losses(A, Bf, Y)
+    loss.backward()
+    close(loss, d[f"{tag}.loss"], "loss")
+    for k, v in terms.items():
+        close(v, d[f"{tag}.{k}"], k, arel=1e-4)
+    close(keep(Z.detach().cpu().numpy()), d[f"{tag}.Z"], "Z")
+    for pre, mod in (("c", H.critic), ("m", H.masker)):
+        if pre == "c" and frozen:
+            continue     # reference accumulates never-used critic grads when -frozen; not part of the contract
+        for k, v in mod.named_parameters():
+            g = v.grad if v.grad is not None else torch.zeros_like(v)
+            close(keep(g.cpu().numpy()), d[f"{tag}.g.{pre}.{k}"], f"{tag}.g.{pre}.{k}", arel=1e-4)
+
+
+def test_step_matches_oracle_on_fresh_inputs():
+    """Same seeded inputs through the oracle (CPU fp32) and the CUDA path, batch not in any fixture."""
+    from oracle import torch_ref
+    import cgs_b200.synth as synth
+    from cgs_b200.train_handler import Handler
+    K, B, p = 1, 19, 0.3
+    csd = synth.perturbed_state(synth.critic_shapes(K), 77, 1.5)
+    msd = synth.perturbed_state(synth.masker_shapes(K), 78, 1.5)
+    X, Yl, _ = synth.synthetic_frames(2 * B, seed=5)
+    A = torch.from_numpy(X[:B]).permute(0, 3, 1, 2).float() / 255.0
+    Bf = torch.from_numpy(X[B:]).permute(0, 3, 1, 2).float() / 255.0
+    Y = torch.from_numpy(Yl[1, :B]).float()
+    rng = np.random.default_rng(3)
+    from helpers import drop_masks
+    masks = [drop_masks(rng, B, K, p) for _ in range(4)]
+    c_cpu, m_cpu = tsd(csd), tsd(msd)
+    for t in list(c_cpu.values()) + list(m_cpu.values()):
+        t.requires_grad_(True)
+    loss_r, terms_r, Z_r = torch_ref.hourglass_losses(c_cpu, m_cpu, A, Bf, Y, live=True, inject=True, L1=0.5, L2=0.0,
+                                                      masks=[tmasks(m) for m in masks])
+    loss_r.backward()
+    H = Handler(make_args(chfak=K, dropout=p), device=DEV)
+    H.critic.load_state_dict(tsd(csd)); H.masker.load_state_dict(tsd(msd))
+    H.critic.to(DEV).train(); H.masker.to(DEV).train()
+    H.critic._forced_masks = deque(nhwc_masks(m, DEV) for m in masks)
+    loss, terms, Z = H.segmentation_losses(A.to(DEV), Bf.to(DEV), Y.to(DEV))
+    loss.backward()
+    close(loss, loss_r, "loss")
+    close(Z, Z_r, "Z")
+    for k, v in H.critic.named_parameters():
+        close(v.grad, c_cpu[k].grad, "c." + k, arel=1e-4)
+    for k, v in H.masker.named_parameters():
+        close(v.grad, m_cpu[k].grad, "m." + k, arel=1e-4)
+
+
+def test_flat_adam_matches_torch_adam():
+    from cgs_b200.nets import NewCritic
+    from cgs_b200.train_handler import FlatAdam
+    from cgs_b200 import ops
+    torch.manual_seed(0)
+    c1 = NewCritic(dropout=0.0).to(DEV)
+    c2 = NewCritic(dropout=0.0).to(DEV)
+    c2.load_state_dict(c1.state_dict())
+    o1 = torch.optim.Adam(c1.parameters())
+    o2 = FlatAdam(c2.parameters())
+    g = torch.Generator().manual_seed(1)
+    for it in range(4):
+        x = torch.rand(8, 3, 64, 64, generator=g).to(DEV)
+        y = torch.rand(8, generator=g).to(DEV)
+        for c, o in ((c1, o1), (c2, o2)):
+            o.zero_grad()
+            ops.pred_loss(c(x).squeeze(1), y).backward()
+            o.step()
+    for (k, a), b in zip(c1.state_dict().items(), c2.state_dict().values()):
+        close(b, a, k, rtol=1e-5, arel=1e-6)
+
+
+def test_trained_checkpoint_process_iou():
+    """-process path on reference-trained weights: mask abs diff and IoU >= 0.99 at threshold 0.1."""
+    from cgs_b200.train_handler import Handler
+    import cgs_b200.synth as synth
+    d = load_golden("loops_c1.npz")
+    H = Handler(make_args(binarymaskthreshold=0.1), device=DEV)
+    H.critic.load_state_dict({k[len("trained.c."):]: torch.from_numpy(d[k]) for k in d.files if k.startswith("trained.c.")})
+    H.masker.load_state_dict({k[len("trained.m."):]: torch.from_numpy(d[k]) for k in d.files if k.startswith("trained.m.")})
+    X, _, _ = synth.synthetic_frames(6000, seed=0)
+    preds, M, hard = H.segment_arrays(X[:32])
+    close(preds, d["proc_pred"].reshape(-1), "pred")
+    assert np.abs(M - d["proc_mask"]).max() <= 1e-4
+    ref_hard = np.unpackbits(d["proc_hard"])[:hard.size].reshape(hard.shape).astype(bool)
+    inter, union = (hard & ref_hard).sum(), (hard | ref_hard).sum()
+    assert inter / union >= 0.99, inter / union
+
+
+def test_loss_curves_vs_reference_loops():
+    """Loop-level: the reference Handler loops (dropout 0, shift 0, fixed batch order) vs the mirrored
+    Handler from the same initial weights; curves within 1% (smoothed), north_star tolerance."""
+    from cgs_b200.train_handler import Handler
+    import cgs_b200.synth as synth
+    d = load_golden("loops_c1.npz")
+    N = 6000
+    X, Y, I = synth.synthetic_frames(N, seed=0)
+    args = make_args(dropout=0.0, shift=0, cepochs=11, saveevery=100, cload=False, frozen=True, model="/tmp/cgs_loop_test")
+    H = Handler(args, device=DEV)
+    H.critic.load_state_dict({k[len("init.c."):]: torch.from_numpy(d[k]) for k in d.files if k.startswith("init.c.")})
+    H.masker.load_state_dict({k[len("init.m."):]: torch.from_numpy(d[k]) for k in d.files if k.startswith("init.m.")})
+    H.critic.to(DEV); H.masker.to(DEV)
+    H.X, H.Y, H.I = X, Y, I
+    Xt, Yt = torch.from_numpy(X), torch.from_numpy(Y).t()
+    H.train_loader = [(Xt[i:i + 64], Yt[i:i + 64], None) for i in range(0, N, 64)]
+    np.random.seed(0)
+    H.critic_pipe()
+    closs = np.array(H.closs_log)
+    ref = d["closs"]
+    assert len(closs) == len(ref) == 1034
+    sm = lambda v: np.convolve(v, np.ones(30) / 30, mode="valid")
+    rel = np.abs(sm(closs) - sm(ref)) / sm(ref)
+    assert rel.max() < 0.01, rel.max()
+    for k, v in H.critic.state_dict().items():
+        close(v, d["trained.c." + k], "trained." + k, rtol=2e-2, arel=2e-2)
+    H.segmentation_training()
+    assert len(H.Xpos) == int(d["n_pos"]) and len(H.Xneg) == int(d["n_neg"])
+    l1 = np.array([t["L1"] for t in H.seg_log])
+    assert len(l1) == len(d["seg_l1"])
+    rel = np.abs(sm(l1) - sm(d["seg_l1"])) / sm(d["seg_l1"])
+    assert rel.max() < 0.01, rel.max()
+    tot = lambda a, b: sm(np.asarray(a) + np.asarray(b))
+    ours = tot([t["replace"] for t in H.seg_log], [t["inject"] for t in H.seg_log])
+    theirs = tot(d["seg_replace"], d["seg_inject"])
+    assert np.abs(ours - theirs).max() <= 0.01 * theirs.max() + 1e-6

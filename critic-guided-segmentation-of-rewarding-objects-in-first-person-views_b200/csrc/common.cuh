@@ -56,6 +56,100 @@ __device__ __forceinline__ float src_load(const cgs_src& s, int n, int y, int x,
   return 0.f;
 }
 
+// ---- division-free index maths: q = n / d via one UMULHI with M = ceil(2^32 / d), exact for n*d < 2^32
+struct FastDiv {
+  uint32_t m;
+  int d;
+};
+inline FastDiv make_fastdiv(int d) { return FastDiv{(uint32_t)(0xFFFFFFFFu / (uint32_t)d + 1u), d}; }   // d >= 2
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return (int)__umulhi((uint32_t)n, f.m); }
+
+// Up to 8 consecutive floats (channels) of one pixel -> registers; two 128-bit loads when aligned.
+__device__ __forceinline__ void load8(const float* __restrict__ p, int n, bool vec, float (&v)[8]) {
+  if (vec && n == 8) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = i < n ? __ldg(p + i) : 0.f;
+  }
+}
+
+// Channels [c0, c0+cn) (cn <= 8) of conv-operand pixel (n, y, x), in-bounds, into v[0..cn).
+__device__ __forceinline__ void src_load8(const cgs_src& s, int n, int y, int x, int c0, int cn, int H, int W, float (&v)[8]) {
+  switch (s.mode) {
+    case CGS_SRC_PLAIN: {
+      const size_t o = (((size_t)n * H + y) * W + x) * s.C + c0;
+      const bool vec = (s.C & 3) == 0;
+      load8(s.a + o, cn, vec, v);
+      if (s.b) {
+        float m[8];
+        load8(s.b + o, cn, vec, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= m[i];
+      }
+      return;
+    }
+    case CGS_SRC_CATUP: {
+      const int C0 = s.C0, C1 = s.C - C0;
+      const size_t pa = (((size_t)n * H + y) * W + x) * C0;
+      const size_t pb = (((size_t)n * (H >> s.shift) + (y >> s.shift)) * (W >> s.shift) + (x >> s.shift)) * C1;
+      if (c0 + cn <= C0) {
+        load8(s.a + pa + c0, cn, (C0 & 3) == 0, v);
+      } else if (c0 >= C0) {
+        load8(s.b + pb + (c0 - C0), cn, ((C1 | (c0 - C0)) & 3) == 0, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = c0 + i;
+          v[i] = i < cn ? (c < C0 ? __ldg(s.a + pa + c) : __ldg(s.b + pb + (c - C0))) : 0.f;
+        }
+      }
+      return;
+    }
+    case CGS_SRC_POOLBWD: {
+      const size_t o = (((size_t)n * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * s.C + c0;
+      const int pos = ((y & 1) << 1) | (x & 1);
+      const bool vec = (s.C & 7) == 0;
+      float e[8];
+      load8(s.a + o, cn, vec, v);
+      load8(s.b + o, cn, vec, e);
+      unsigned long long ib = 0;
+      if (vec && cn == 8) {
+        ib = __ldg(reinterpret_cast<const unsigned long long*>(s.idx + o));
+      } else {
+        for (int i = 0; i < cn; ++i) ib |= (unsigned long long)s.idx[o + i] << (8 * i);
+      }
+      // ReLU'(pre-act) == (pooled output > 0) at the arg-max position; elsewhere no gradient.
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if ((int)((ib >> (8 * i)) & 0xff) != pos || !(e[i] > 0.f)) v[i] = 0.f;
+      return;
+    }
+    case CGS_SRC_SIGGRAD: {
+      const size_t o = (((size_t)n * H + y) * W + x) * s.C + c0;
+      const bool vec = (s.C & 3) == 0;
+      float z[8];
+      load8(s.a + o, cn, vec, v);
+      load8(s.b + o, cn, vec, z);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = v[i] * z[i] * (1.f - z[i]);
+      return;
+    }
+    case CGS_SRC_LEAKYGRAD: {
+      const size_t o = (((size_t)n * H + y) * W + x) * s.C + c0;
+      const bool vec = (s.C & 3) == 0;
+      float z[8];
+      load8(s.a + o, cn, vec, v);
+      load8(s.b + o, cn, vec, z);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = z[i] > 0.f ? v[i] : v[i] * kLeakySlope;
+      return;
+    }
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

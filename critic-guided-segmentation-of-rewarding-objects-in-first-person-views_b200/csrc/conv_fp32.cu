@@ -18,6 +18,7 @@ struct ConvGeom {
   int tph, tpw, fpc;      // patches per tile (rows, cols), frames per CTA
   int tiles_y, tiles_x;   // tiles per frame
   int rs, ps;             // smem row stride / plane stride (floats)
+  FastDiv dsw, dsh;       // dividers by the haloed tile width / height
 };
 
 template <int CO_T>
@@ -63,15 +64,23 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const cgs_conv3x3_args p, 
   for (int c0 = 0; c0 < Cin; c0 += CI_T) {
     const int ci_n = min(CI_T, Cin - c0);
     __syncthreads();
-    // ---- stage the haloed input chunk: consecutive threads -> consecutive channels of a pixel
+    // ---- stage the haloed input chunk: one pixel (<= 8 channels, 128-bit loads) per thread iteration
     const int npix = g.fpc * sh * sw;
-    for (int e = tid; e < npix * ci_n; e += nthr) {
-      const int ci = e % ci_n, pix = e / ci_n;
-      const int xx = pix % sw, yy = (pix / sw) % sh, ff = pix / (sw * sh);
+    for (int pix = tid; pix < npix; pix += nthr) {
+      const int row = fdiv(pix, g.dsw), xx = pix - row * sw;
+      const int ff = fdiv(row, g.dsh), yy = row - ff * sh;
       const int gy = y0 + yy - 1, gx = x0 + xx - 1, nn = n0 + ff;
-      float v = 0.f;
-      if (nn < p.B && gy >= 0 && gy < H && gx >= 0 && gx < W) v = src_load(p.src, nn, gy, gx, c0 + ci, H, W);
-      s_in[(ff * CI_T + ci) * g.ps + yy * g.rs + xx] = v;
+      float v[8];
+      if (nn < p.B && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        src_load8(p.src, nn, gy, gx, c0, ci_n, H, W, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+      float* d = s_in + (ff * CI_T) * g.ps + yy * g.rs + xx;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < ci_n) d[i * g.ps] = v[i];
     }
     // ---- stage the weight chunk as [ci][tap][co]
     for (int e = tid; e < ci_n * 9 * CO_T; e += nthr) {
@@ -124,21 +133,37 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const cgs_conv3x3_args p, 
   if (p.epi == CGS_EPI_RELU_POOL) {
     const int h2 = H >> 1, w2 = W >> 1;
     const size_t o = (((size_t)n * h2 + (py >> 1)) * w2 + (px >> 1)) * Cout + co0;
+    float mv[CO_T];
+    unsigned char am[CO_T];
 #pragma unroll
     for (int j = 0; j < CO_T; ++j) {
-      if (j < con) {
-        // ATen max-pool keeps the FIRST maximum in row-major window order (strict >).
-        float m = fmaxf(acc[0][j] + bias[j], 0.f);
-        int am = 0;
+      // ATen max-pool keeps the FIRST maximum in row-major window order (strict >).
+      float m = fmaxf(acc[0][j] + bias[j], 0.f);
+      int a = 0;
 #pragma unroll
-        for (int q = 1; q < 4; ++q) {
-          float v = fmaxf(acc[q][j] + bias[j], 0.f);
-          if (v > m) { m = v; am = q; }
+      for (int q = 1; q < 4; ++q) {
+        float v = fmaxf(acc[q][j] + bias[j], 0.f);
+        if (v > m) { m = v; a = q; }
+      }
+      mv[j] = m; am[j] = (unsigned char)a;
+    }
+    if constexpr (CO_T % 4 == 0) {
+      if (con == CO_T && (Cout & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < CO_T; j += 4) {
+          *reinterpret_cast<float4*>(p.out + o + j) = make_float4(mv[j], mv[j + 1], mv[j + 2], mv[j + 3]);
+          if (p.idx_out)
+            *reinterpret_cast<uchar4*>(p.idx_out + o + j) = make_uchar4(am[j], am[j + 1], am[j + 2], am[j + 3]);
         }
-        p.out[o + j] = m;
-        if (p.idx_out) p.idx_out[o + j] = (uint8_t)am;
+        return;
       }
     }
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j)
+      if (j < con) {
+        p.out[o + j] = mv[j];
+        if (p.idx_out) p.idx_out[o + j] = am[j];
+      }
     return;
   }
   if (p.epi == CGS_EPI_SPLIT_UP) {
@@ -166,16 +191,33 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const cgs_conv3x3_args p, 
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const size_t o = (((size_t)n * H + py + (q >> 1)) * W + px + (q & 1)) * Cout + co0;
+    float r[CO_T];
 #pragma unroll
     for (int j = 0; j < CO_T; ++j) {
-      if (j >= con) continue;
       float v = acc[q][j] + bias[j];
       if (p.epi == CGS_EPI_LEAKY) v = v > 0.f ? v : v * kLeakySlope;
-      else if (p.epi == CGS_EPI_SIGMOID) {
-        v = 1.f / (1.f + expf(-v));
-        if (p.idx_out) p.idx_out[o + j] = v >= p.thresh ? 1 : 0;
-      } else if (p.epi == CGS_EPI_MUL) v *= __ldg(p.mul + o + j);
-      p.out[o + j] = v;
+      else if (p.epi == CGS_EPI_SIGMOID) v = 1.f / (1.f + expf(-v));
+      else if (p.epi == CGS_EPI_MUL) v *= (j < con) ? __ldg(p.mul + o + j) : 0.f;
+      r[j] = v;
+    }
+    bool done = false;
+    if constexpr (CO_T % 4 == 0) {
+      if (con == CO_T && (Cout & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < CO_T; j += 4)
+          *reinterpret_cast<float4*>(p.out + o + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        done = true;
+      }
+    }
+    if (!done) {
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j)
+        if (j < con) p.out[o + j] = r[j];
+    }
+    if (p.epi == CGS_EPI_SIGMOID && p.idx_out) {
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j)
+        if (j < con) p.idx_out[o + j] = r[j] >= p.thresh ? 1 : 0;
     }
   }
 }
@@ -195,7 +237,9 @@ static void pick_geom(int B, int H, int W, ConvGeom& g, int& nthr, int& nblk) {
   const int sw = 2 * g.tpw + 2, sh = 2 * g.tph + 2;
   g.rs = (sw + 1) & ~1;
   g.ps = sh * g.rs;
-  g.ps += (36 - (g.ps % 32)) % 32;  // plane stride == 4 (mod 32): conflict-free staging stores
+  g.ps += (36 - (g.ps % 32)) % 32;  // plane stride == 4 (mod 32)
+  g.dsw = make_fastdiv(sw);
+  g.dsh = make_fastdiv(sh);
   nblk = ((B + g.fpc - 1) / g.fpc) * g.tiles_x * g.tiles_y;
 }
 
@@ -231,6 +275,7 @@ static int check_src(const cgs_src& s, const char* who) {
 struct WgGeom {
   int th, tw, fpc, tiles_y, tiles_x;
   int rsx, psx, rsy, psy;
+  FastDiv dsw, dsh, dtw, dth;
 };
 
 template <int CO_R, int CI_R, int NCO, int NCI>
@@ -251,25 +296,44 @@ __global__ void __launch_bounds__(256) wgrad3x3_kernel(const cgs_wgrad3x3_args p
   const int co0 = blockIdx.y * CO_B, ci0 = blockIdx.z * CI_B;
   const int con = min(CO_B, Cout - co0), cin = min(CI_B, Cin - ci0);
 
-  // ---- stage X (haloed) and dY tiles
+  // ---- stage X (haloed) and dY tiles: one pixel x <=8 channels per thread iteration
   {
     const int npix = g.fpc * sh * sw;
-    for (int e = tid; e < npix * cin; e += 256) {
-      const int ci = e % cin, pix = e / cin;
-      const int xx = pix % sw, yy = (pix / sw) % sh, ff = pix / (sw * sh);
-      const int gy = y0 + yy - 1, gx = x0 + xx - 1, nn = n0 + ff;
-      float v = 0.f;
-      if (nn < p.B && gy >= 0 && gy < H && gx >= 0 && gx < W) v = src_load(p.x, nn, gy, gx, ci0 + ci, H, W);
-      s_x[ci * g.psx + (ff * sh + yy) * g.rsx + xx] = v;
+    for (int cb = 0; cb < cin; cb += 8) {
+      const int cn = min(8, cin - cb);
+      for (int pix = tid; pix < npix; pix += 256) {
+        const int row = fdiv(pix, g.dsw), xx = pix - row * sw;
+        const int ff = fdiv(row, g.dsh), yy = row - ff * sh;
+        const int gy = y0 + yy - 1, gx = x0 + xx - 1, nn = n0 + ff;
+        float v[8];
+        if (nn < p.B && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+          src_load8(p.x, nn, gy, gx, ci0 + cb, cn, H, W, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+        float* d = s_x + cb * g.psx + row * g.rsx + xx;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < cn) d[i * g.psx] = v[i];
+      }
     }
     const int npy = g.fpc * th * tw;
-    for (int e = tid; e < npy * con; e += 256) {
-      const int co = e % con, pix = e / con;
-      const int xx = pix % tw, yy = (pix / tw) % th, ff = pix / (tw * th);
+    for (int pix = tid; pix < npy; pix += 256) {
+      const int row = fdiv(pix, g.dtw), xx = pix - row * tw;
+      const int ff = fdiv(row, g.dth), yy = row - ff * th;
       const int gy = y0 + yy, gx = x0 + xx, nn = n0 + ff;
-      float v = 0.f;
-      if (nn < p.B && gy < H && gx < W) v = src_load(p.dy, nn, gy, gx, co0 + co, H, W);
-      s_y[co * g.psy + (ff * th + yy) * g.rsy + xx] = v;
+      float v[8];
+      if (nn < p.B) {
+        src_load8(p.dy, nn, gy, gx, co0, con, H, W, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+      float* d = s_y + row * g.rsy + xx;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < con) d[i * g.psy] = v[i];
     }
   }
   __syncthreads();
@@ -378,6 +442,8 @@ static int launch_wgrad(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   g.rsx = (g.tw + 2) | 1; g.rsy = g.tw | 1;
   g.psx = g.fpc * (g.th + 2) * g.rsx; g.psx += (40 - (g.psx % 32)) % 32;   // plane stride == 8 (mod 32)
   g.psy = g.fpc * g.th * g.rsy;       g.psy += (40 - (g.psy % 32)) % 32;
+  g.dsw = make_fastdiv(g.tw + 2); g.dsh = make_fastdiv(g.th + 2);
+  g.dtw = make_fastdiv(g.tw);     g.dth = make_fastdiv(g.th);
   size_t smem = ((size_t)CI_B * g.psx + (size_t)CO_B * g.psy) * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {

@@ -264,3 +264,40 @@ if __name__ == "__main__":
         gen_step(K=5, B=2, p=0.5, seed=13, scale=1.5, full=False)
     if "loops" in which:
         gen_loops()
+
+
+def gen_envelope():
+    """Sensitivity envelope of the critic loss curve: the loop of gen_loops() re-run by the oracle
+    (bit-identical to the reference on this curve, see tests/test_oracle.py) from initial weights
+    perturbed by 1e-6 relative (fp32-rounding scale).  Training is chaotic in the fast-learning
+    phase, so an implementation can only be asked to stay inside this envelope."""
+    from oracle import torch_ref
+    d = np.load(f"{OUT}/loops_c1.npz")
+    X, Y, _ = synth.synthetic_frames(6000, seed=0)
+    Xt, Yt = torch.from_numpy(X), torch.from_numpy(Y).t()
+
+    def run(eps, seed):
+        g = torch.Generator().manual_seed(seed)
+        sd = {k[len("init.c."):]: torch.from_numpy(d[k]).clone() for k in d.files if k.startswith("init.c.")}
+        for v in sd.values():
+            v.mul_(1 + eps * (torch.rand(v.shape, generator=g) - 0.5))
+            v.requires_grad_(True)
+        opt = torch.optim.Adam(sd.values())
+        out = []
+        for ep in range(11):
+            for i in range(0, 6000, 64):
+                loss, _ = torch_ref.critic_loss(sd, Xt[i:i + 64].permute(0, 3, 1, 2).float() / 255.0, Yt[i:i + 64, 1].float())
+                opt.zero_grad(); loss.backward(); opt.step()
+                out.append(loss.item())
+        return np.array(out)
+    sm = lambda v: np.convolve(v, np.ones(30) / 30, mode="valid")
+    ref = d["closs"]
+    assert np.array_equal(run(0.0, 0), ref), "oracle loop no longer reproduces the reference curve"
+    devs = [np.abs(sm(run(1e-6, s)) - sm(ref)) / sm(ref) for s in (1, 2, 3, 4)]
+    env = np.max(devs, axis=0)
+    np.savez_compressed(f"{OUT}/loops_envelope_c1.npz", env=env.astype(np.float32), eps=1e-6, window=30)
+    print("envelope max", env.max(), "median", np.median(env), "last", env[-1])
+
+
+if __name__ == "__main__" and "envelope" in sys.argv[1:]:
+    gen_envelope()

@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcgs_b200.so")
 
-SRC_PLAIN, SRC_CATUP, SRC_POOLBWD, SRC_SIGGRAD, SRC_LEAKYGRAD = range(5)
+SRC_PLAIN, SRC_CATUP, SRC_POOLBWD, SRC_SIGGRAD, SRC_LEAKYGRAD, SRC_U8ROLL = range(6)
 EPI_LINEAR, EPI_LEAKY, EPI_RELU_POOL, EPI_SIGMOID, EPI_MUL, EPI_SPLIT_UP = range(6)
 
 _f32p = C.c_void_p

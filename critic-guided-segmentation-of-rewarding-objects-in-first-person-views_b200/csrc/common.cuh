@@ -147,6 +147,16 @@ __device__ __forceinline__ void src_load8(const cgs_src& s, int n, int y, int x,
       for (int i = 0; i < 8; ++i) v[i] = z[i] > 0.f ? v[i] : v[i] * kLeakySlope;
       return;
     }
+    case CGS_SRC_U8ROLL: {
+      const int roll = s.b ? *reinterpret_cast<const int*>(s.b) : s.shift;   // |roll| < W
+      int sx = x + roll;
+      if (sx >= W) sx -= W;
+      if (sx < 0) sx += W;
+      const uint8_t* q = reinterpret_cast<const uint8_t*>(s.a) + (((size_t)n * H + y) * W + sx) * s.C + c0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = i < cn ? (float)__ldg(q + i) / 255.0f : 0.f;
+      return;
+    }
   }
 }
 

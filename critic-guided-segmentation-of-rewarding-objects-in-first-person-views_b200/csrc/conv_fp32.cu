@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const cgs_conv3x3_args p, 
     __syncthreads();
     // ---- stage the haloed input chunk: one pixel (<= 8 channels, 128-bit loads) per thread iteration
     const int npix = g.fpc * sh * sw;
+#pragma unroll 4
     for (int pix = tid; pix < npix; pix += nthr) {
       const int row = fdiv(pix, g.dsw), xx = pix - row * sw;
       const int ff = fdiv(row, g.dsh), yy = row - ff * sh;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const cgs_conv3x3_args p, 
         if (i < ci_n) d[i * g.ps] = v[i];
     }
     // ---- stage the weight chunk as [ci][tap][co]
+#pragma unroll 4
     for (int e = tid; e < ci_n * 9 * CO_T; e += nthr) {
       const int co = e % CO_T, t = (e / CO_T) % 9, ci = e / (9 * CO_T);
       const int gco = co0 + co;
@@ -232,7 +234,7 @@ static void pick_geom(int B, int H, int W, ConvGeom& g, int& nthr, int& nblk) {
   int ppf = g.tph * g.tpw;          // threads per frame-tile
   // frames per CTA: fill 128 threads for small maps but keep enough CTAs to cover the SMs
   g.fpc = 1;
-  while (ppf * g.fpc < 128 && (long)((B + 2 * g.fpc - 1) / (2 * g.fpc)) * g.tiles_x * g.tiles_y >= 296) g.fpc *= 2;
+  while (ppf * g.fpc < 128 && 2 * g.fpc <= B) g.fpc *= 2;   // >= 4 warps per CTA: these layers are latency-bound
   nthr = ((ppf * g.fpc + 31) / 32) * 32;
   const int sw = 2 * g.tpw + 2, sh = 2 * g.tph + 2;
   g.rs = (sw + 1) & ~1;
@@ -263,7 +265,7 @@ static int check_src(const cgs_src& s, const char* who) {
   if (s.mode == CGS_SRC_CATUP) CGS_REQUIRE(s.b && s.C0 > 0 && s.C0 < s.C && (s.shift == 1 || s.shift == 2), "%s: bad CATUP operand", who);
   if (s.mode == CGS_SRC_POOLBWD) CGS_REQUIRE(s.b && s.idx, "%s: POOLBWD needs E and idx", who);
   if (s.mode == CGS_SRC_SIGGRAD || s.mode == CGS_SRC_LEAKYGRAD) CGS_REQUIRE(s.b, "%s: grad mode needs forward output", who);
-  CGS_REQUIRE(s.mode >= 0 && s.mode <= CGS_SRC_LEAKYGRAD, "%s: unknown src mode %d", who, s.mode);
+  CGS_REQUIRE(s.mode >= 0 && s.mode <= CGS_SRC_U8ROLL, "%s: unknown src mode %d", who, s.mode);
   return 0;
 }
 
@@ -301,6 +303,7 @@ __global__ void __launch_bounds__(256) wgrad3x3_kernel(const cgs_wgrad3x3_args p
     const int npix = g.fpc * sh * sw;
     for (int cb = 0; cb < cin; cb += 8) {
       const int cn = min(8, cin - cb);
+#pragma unroll 2
       for (int pix = tid; pix < npix; pix += 256) {
         const int row = fdiv(pix, g.dsw), xx = pix - row * sw;
         const int ff = fdiv(row, g.dsh), yy = row - ff * sh;
@@ -319,6 +322,7 @@ __global__ void __launch_bounds__(256) wgrad3x3_kernel(const cgs_wgrad3x3_args p
       }
     }
     const int npy = g.fpc * th * tw;
+#pragma unroll 2
     for (int pix = tid; pix < npy; pix += 256) {
       const int row = fdiv(pix, g.dtw), xx = pix - row * tw;
       const int ff = fdiv(row, g.dth), yy = row - ff * th;
@@ -438,7 +442,7 @@ static int launch_wgrad(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   g.tiles_y = a.H / g.th; g.tiles_x = a.W / g.tw;
   g.fpc = 1;
   // small maps: several frames per CTA so each pixel group owns >= 2 rows, while keeping >= 2 waves of CTAs
-  while (g.fpc * g.th * g.tw < 1024 && (long)((a.B + 2 * g.fpc - 1) / (2 * g.fpc)) >= 296) g.fpc *= 2;
+  while (g.fpc * g.th * g.tw < 1024 && (long)((a.B + 2 * g.fpc - 1) / (2 * g.fpc)) >= 148) g.fpc *= 2;
   g.rsx = (g.tw + 2) | 1; g.rsy = g.tw | 1;
   g.psx = g.fpc * (g.th + 2) * g.rsx; g.psx += (40 - (g.psx % 32)) % 32;   // plane stride == 8 (mod 32)
   g.psy = g.fpc * g.th * g.rsy;       g.psy += (40 - (g.psy % 32)) % 32;
@@ -474,7 +478,7 @@ extern "C" int cgs_conv3x3(const cgs_conv3x3_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (a->Cout == 1) return launch_conv<1>(*a, st);
   if (a->Cout <= 4) return launch_conv<4>(*a, st);
-  if (a->Cout % 16 == 0) return launch_conv<16>(*a, st);
+  if (a->Cout % 16 == 0 && a->H >= 32) return launch_conv<16>(*a, st);   // small maps: more, shorter CTAs
   return launch_conv<8>(*a, st);
 }
 

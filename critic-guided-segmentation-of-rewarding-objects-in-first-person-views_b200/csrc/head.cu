@@ -6,16 +6,16 @@
 // weights stream from L2 with coalesced reads (lanes along K for the forward dot
 // products, lanes along K for dIn / dW in backward).  Parameter gradients are reduced
 // over the CTA's frames in registers and pushed with one RED per weight per CTA.
+#include <type_traits>
 #include "common.cuh"
 
 namespace cgs {
 
-constexpr int FPC = 16;       // frames per CTA
 constexpr int HT = 256;       // threads per CTA
 
 // out[f][n] = sum_k in[f][k] * w[n][k] (+bias) ; warp per n, lanes along k.  `in` in smem
 // with row stride ld_in, `w` in global.  act: 0 none, 1 relu, 2 sigmoid.
-template <int ACT>
+template <int FPC, int ACT>
 __device__ void dense_rows(const float* s_in, int ld_in, const float* __restrict__ w, const float* __restrict__ bias,
                            int K, int N, float* s_out, int ld_out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = HT / 32;
@@ -24,6 +24,7 @@ __device__ void dense_rows(const float* s_in, int ld_in, const float* __restrict
 #pragma unroll
     for (int f = 0; f < FPC; ++f) acc[f] = 0.f;
     const float* wr = w + (size_t)n * K;
+#pragma unroll 4
     for (int k = lane; k < K; k += 32) {
       const float wv = __ldg(wr + k);
 #pragma unroll
@@ -44,12 +45,14 @@ __device__ void dense_rows(const float* s_in, int ld_in, const float* __restrict
 }
 
 // din[f][k] = sum_n dout[f][n] * w[n][k] ; thread per k (coalesced w rows).
+template <int FPC>
 __device__ void dense_din(const float* s_dout, int ld_do, const float* __restrict__ w, int K, int N,
                           float* s_din, int ld_di) {
   for (int k = threadIdx.x; k < K; k += HT) {
     float acc[FPC];
 #pragma unroll
     for (int f = 0; f < FPC; ++f) acc[f] = 0.f;
+#pragma unroll 4
     for (int n = 0; n < N; ++n) {
       const float wv = __ldg(w + (size_t)n * K + k);
 #pragma unroll
@@ -61,6 +64,7 @@ __device__ void dense_din(const float* s_dout, int ld_do, const float* __restric
 }
 
 // dw[n][k] += sum_f dout[f][n] * in[f][k] ; db[n] += sum_f dout[f][n].
+template <int FPC>
 __device__ void dense_dw(const float* s_dout, int ld_do, const float* s_in, int ld_in, int K, int N,
                          float* __restrict__ dw, float* __restrict__ db) {
   for (int e = threadIdx.x; e < N * K; e += HT) {
@@ -85,6 +89,7 @@ __device__ void dense_dw(const float* s_dout, int ld_do, const float* s_in, int 
 __device__ __forceinline__ int kw_slot(int kw) { return (kw >> 4) * 17 + (kw & 15); }
 
 // Head forward kernel.  smem: x [FPC][ldx], h [FPC][NB], v [FPC][NB].
+template <int FPC>
 __global__ void __launch_bounds__(HT) head_fwd_kernel(const float* __restrict__ e3, const float* __restrict__ m_e3,
                                                       const float* __restrict__ m_v, const float* __restrict__ w14,
                                                       const float* __restrict__ b14, const float* __restrict__ w1,
@@ -119,6 +124,7 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(const float* __restrict__ 
 #pragma unroll
       for (int f = 0; f < FPC; ++f) acc[f] = 0.f;
       const float* wr = w14 + (size_t)n * K;
+#pragma unroll 4
       for (int k = lane; k < K; k += 32) {
         const float wv = __ldg(wr + k);
         const int sl = kw_slot(k);
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(const float* __restrict__ 
     }
   }
   __syncthreads();
-  dense_rows<1>(s_h, NB, w1, b1, NB, NB, s_v, NB);
+  dense_rows<FPC, 1>(s_h, NB, w1, b1, NB, NB, s_v, NB);
   __syncthreads();
   // save v (pre-dropout), apply dropout in place
   for (int e = threadIdx.x; e < FPC * NB; e += HT) {
@@ -163,6 +169,7 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(const float* __restrict__ 
 }
 
 // Head backward kernel.  smem: x [FPC][ldx] (later reused for dx), h, v(dropped), dh, dv: [FPC][NB] each, dl [FPC].
+template <int FPC>
 __global__ void __launch_bounds__(HT) head_bwd_kernel(const float* __restrict__ e3, const float* __restrict__ m_e3,
                                                       const float* __restrict__ m_v, const float* __restrict__ w14,
                                                       const float* __restrict__ w1, const float* __restrict__ w2,
@@ -218,12 +225,12 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const float* __restrict__ 
   __syncthreads();
   if (wg) {
     // crit.4: dw2[k] += sum_f dl[f]*vd[f][k], db2 += sum_f dl
-    dense_dw(s_dl, 1, s_vd, NB, NB, 1, dw2, db2);
+    dense_dw<FPC>(s_dl, 1, s_vd, NB, NB, 1, dw2, db2);
     // crit.1: dw1[n][k] += sum_f dv[f][n]*h[f][k]
-    dense_dw(s_dv, NB, s_h, NB, NB, NB, dw1, db1);
+    dense_dw<FPC>(s_dv, NB, s_h, NB, NB, NB, dw1, db1);
   }
   // dh = (dv W1 + de4) * (h > 0)
-  dense_din(s_dv, NB, w1, NB, NB, s_dh, NB);
+  dense_din<FPC>(s_dv, NB, w1, NB, NB, s_dh, NB);
   __syncthreads();
   for (int e = threadIdx.x; e < FPC * NB; e += HT) {
     const int f = e / NB;
@@ -255,6 +262,7 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const float* __restrict__ 
     float acc[FPC];
 #pragma unroll
     for (int f = 0; f < FPC; ++f) acc[f] = 0.f;
+#pragma unroll 4
     for (int n = 0; n < NB; ++n) {
       const float wv = __ldg(w14 + (size_t)n * K + k);
 #pragma unroll
@@ -278,6 +286,7 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const float* __restrict__ 
 }
 
 // Generic dense forward: out[B,N] = in[B,K] w[N,K]^T + bias.
+template <int FPC>
 __global__ void __launch_bounds__(HT) dense_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                        const float* __restrict__ bias, int B, int K, int N,
                                                        float* __restrict__ out) {
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(HT) dense_fwd_kernel(const float* __restrict__
     s_in[e] = (n0 + f < B) ? __ldg(in + (size_t)n0 * K + e) : 0.f;
   }
   __syncthreads();
-  dense_rows<0>(s_in, K, w, bias, K, N, s_out, N);
+  dense_rows<FPC, 0>(s_in, K, w, bias, K, N, s_out, N);
   __syncthreads();
   for (int e = threadIdx.x; e < FPC * N; e += HT) {
     const int f = e / N;
@@ -298,6 +307,7 @@ __global__ void __launch_bounds__(HT) dense_fwd_kernel(const float* __restrict__
   }
 }
 
+template <int FPC>
 __global__ void __launch_bounds__(HT) dense_bwd_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                        const float* __restrict__ dout, int B, int K, int N,
                                                        float* __restrict__ din, float* dw, float* db) {
@@ -315,9 +325,9 @@ __global__ void __launch_bounds__(HT) dense_bwd_kernel(const float* __restrict__
     s_do[e] = (n0 + f < B) ? __ldg(dout + (size_t)n0 * N + e) : 0.f;
   }
   __syncthreads();
-  if (dw) dense_dw(s_do, N, s_in, K, K, N, dw, db);
+  if (dw) dense_dw<FPC>(s_do, N, s_in, K, K, N, dw, db);
   if (din) {
-    dense_din(s_do, N, w, K, N, s_di, K);
+    dense_din<FPC>(s_do, N, w, K, N, s_di, K);
     __syncthreads();
     for (int e = threadIdx.x; e < FPC * K; e += HT) {
       const int f = e / K;
@@ -325,6 +335,10 @@ __global__ void __launch_bounds__(HT) dense_bwd_kernel(const float* __restrict__
     }
   }
 }
+
+// Few frames per CTA while the batch is small (the chain is latency-bound: more CTAs in flight),
+// 16 once there are enough frames to fill the SMs (weights are re-read from L2 once per CTA).
+static int frames_per_cta(int B) { return B <= 2048 ? 4 : 16; }
 
 static int set_smem(const void* fn, size_t bytes) {
   if (bytes > 227 * 1024) { set_error("dense/head: shared memory request %zu exceeds 227 KB", bytes); return CGS_EUNSUPPORTED; }
@@ -340,11 +354,15 @@ extern "C" int cgs_head_fwd(const float* e3, const float* m_e3, const float* m_v
   using namespace cgs;
   CGS_REQUIRE(e3 && w14 && b14 && w1 && b1 && w2 && b2 && e4 && v && pred, "head_fwd: null pointer");
   CGS_REQUIRE(B > 0 && C3 > 0 && NB > 0, "head_fwd: bad sizes");
-  size_t smem = ((size_t)FPC * 17 * C3 + 2 * FPC * NB) * sizeof(float);
-  if (int e = set_smem((const void*)head_fwd_kernel, smem)) return e;
-  head_fwd_kernel<<<(B + FPC - 1) / FPC, HT, smem, (cudaStream_t)stream>>>(e3, m_e3, m_v, w14, b14, w1, b1, w2, b2, B, C3,
-                                                                          NB, e4, v, pred);
-  return check_launch("head_fwd");
+  auto go = [&](auto fpc_tag) {
+    constexpr int FPC = decltype(fpc_tag)::value;
+    size_t smem = ((size_t)FPC * 17 * C3 + 2 * FPC * NB) * sizeof(float);
+    if (int e = set_smem((const void*)head_fwd_kernel<FPC>, smem)) return e;
+    head_fwd_kernel<FPC><<<(B + FPC - 1) / FPC, HT, smem, (cudaStream_t)stream>>>(e3, m_e3, m_v, w14, b14, w1, b1, w2, b2, B,
+                                                                                 C3, NB, e4, v, pred);
+    return check_launch("head_fwd");
+  };
+  return frames_per_cta(B) == 4 ? go(std::integral_constant<int, 4>{}) : go(std::integral_constant<int, 16>{});
 }
 
 extern "C" int cgs_head_bwd(const float* e3, const float* m_e3, const float* m_v, const float* w14, const float* w1,
@@ -355,30 +373,42 @@ extern "C" int cgs_head_bwd(const float* e3, const float* m_e3, const float* m_v
   CGS_REQUIRE(e3 && w14 && w1 && w2 && e4 && v && pred && dpred, "head_bwd: null pointer");
   CGS_REQUIRE(B > 0 && C3 > 0 && NB > 0, "head_bwd: bad sizes");
   if (dw14) CGS_REQUIRE(db14 && dw1 && db1 && dw2 && db2, "head_bwd: parameter gradients are all-or-none");
-  size_t smem = ((size_t)FPC * 17 * C3 + 4 * FPC * NB + FPC) * sizeof(float);
-  if (int e = set_smem((const void*)head_bwd_kernel, smem)) return e;
-  head_bwd_kernel<<<(B + FPC - 1) / FPC, HT, smem, (cudaStream_t)stream>>>(e3, m_e3, m_v, w14, w1, w2, e4, v, pred, dpred,
-                                                                          de4, B, C3, NB, dw14, db14, dw1, db1, dw2, db2,
-                                                                          de3);
-  return check_launch("head_bwd");
+  auto go = [&](auto fpc_tag) {
+    constexpr int FPC = decltype(fpc_tag)::value;
+    size_t smem = ((size_t)FPC * 17 * C3 + 4 * FPC * NB + FPC) * sizeof(float);
+    if (int e = set_smem((const void*)head_bwd_kernel<FPC>, smem)) return e;
+    head_bwd_kernel<FPC><<<(B + FPC - 1) / FPC, HT, smem, (cudaStream_t)stream>>>(e3, m_e3, m_v, w14, w1, w2, e4, v, pred,
+                                                                                 dpred, de4, B, C3, NB, dw14, db14, dw1, db1,
+                                                                                 dw2, db2, de3);
+    return check_launch("head_bwd");
+  };
+  return frames_per_cta(B) == 4 ? go(std::integral_constant<int, 4>{}) : go(std::integral_constant<int, 16>{});
 }
 
 extern "C" int cgs_dense_fwd(const float* in, const float* w, const float* bias, int32_t B, int32_t K, int32_t N,
                              float* out, void* stream) {
   using namespace cgs;
   CGS_REQUIRE(in && w && out && B > 0 && K > 0 && N > 0, "dense_fwd: bad args");
-  size_t smem = (size_t)FPC * (K + N) * sizeof(float);
-  if (int e = set_smem((const void*)dense_fwd_kernel, smem)) return e;
-  dense_fwd_kernel<<<(B + FPC - 1) / FPC, HT, smem, (cudaStream_t)stream>>>(in, w, bias, B, K, N, out);
-  return check_launch("dense_fwd");
+  auto go = [&](auto fpc_tag) {
+    constexpr int FPC = decltype(fpc_tag)::value;
+    size_t smem = (size_t)FPC * (K + N) * sizeof(float);
+    if (int e = set_smem((const void*)dense_fwd_kernel<FPC>, smem)) return e;
+    dense_fwd_kernel<FPC><<<(B + FPC - 1) / FPC, HT, smem, (cudaStream_t)stream>>>(in, w, bias, B, K, N, out);
+    return check_launch("dense_fwd");
+  };
+  return frames_per_cta(B) == 4 ? go(std::integral_constant<int, 4>{}) : go(std::integral_constant<int, 16>{});
 }
 
 extern "C" int cgs_dense_bwd(const float* in, const float* w, const float* dout, int32_t B, int32_t K, int32_t N,
                              float* din, float* dw, float* db, void* stream) {
   using namespace cgs;
   CGS_REQUIRE(in && w && dout && B > 0 && K > 0 && N > 0, "dense_bwd: bad args");
-  size_t smem = (size_t)FPC * (2 * K + N) * sizeof(float);
-  if (int e = set_smem((const void*)dense_bwd_kernel, smem)) return e;
-  dense_bwd_kernel<<<(B + FPC - 1) / FPC, HT, smem, (cudaStream_t)stream>>>(in, w, dout, B, K, N, din, dw, db);
-  return check_launch("dense_bwd");
+  auto go = [&](auto fpc_tag) {
+    constexpr int FPC = decltype(fpc_tag)::value;
+    size_t smem = (size_t)FPC * (2 * K + N) * sizeof(float);
+    if (int e = set_smem((const void*)dense_bwd_kernel<FPC>, smem)) return e;
+    dense_bwd_kernel<FPC><<<(B + FPC - 1) / FPC, HT, smem, (cudaStream_t)stream>>>(in, w, dout, B, K, N, din, dw, db);
+    return check_launch("dense_bwd");
+  };
+  return frames_per_cta(B) == 4 ? go(std::integral_constant<int, 4>{}) : go(std::integral_constant<int, 16>{});
 }

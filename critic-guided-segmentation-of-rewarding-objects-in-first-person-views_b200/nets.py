@@ -80,10 +80,21 @@ class NewCritic(nn.Module):
         return mk(B, 8, 8, c2), mk(B, 4, 4, c3), mk(B, nb)
 
     def forward(self, X, collect=False):
-        x = _nhwc(X, self.colorchs, self.width, "NewCritic")
+        return self._run(_nhwc(X, self.colorchs, self.width, "NewCritic"), None, collect)
+
+    def forward_frames(self, X_u8, roll=0, collect=False):
+        """forward() on raw uint8 NHWC frames [B,64,64,3]: `X.permute(0,3,1,2).float()/255.0` and the
+        shift_batch roll (reference main.py:185-189, 584-591) are fused into the first conv's operand load."""
+        if X_u8.dtype != torch.uint8 or X_u8.dim() != 4 or tuple(X_u8.shape[1:]) != (self.width, self.width, self.colorchs):
+            raise ValueError(f"NewCritic.forward_frames: expected uint8 [B,{self.width},{self.width},{self.colorchs}]")
+        if not X_u8.is_cuda:
+            raise CgsError("NewCritic.forward_frames: input is on CPU; cgs_b200 has no CPU path")
+        return self._run(X_u8.contiguous(), roll, collect)
+
+    def _run(self, x, roll, collect):
         m_e2, m_e3, m_v = self._dropout_masks(x.shape[0], x.device)
         f = self.features
-        e0 = ops.EncBlock.apply(x, None, f[0].weight, f[0].bias)
+        e0 = ops.EncBlock.apply(x, None, f[0].weight, f[0].bias, roll)
         e1 = ops.EncBlock.apply(e0, None, f[3].weight, f[3].bias)
         e2 = ops.EncBlock.apply(e1, None, f[6].weight, f[6].bias)
         e3 = ops.EncBlock.apply(e2, m_e2, f[10].weight, f[10].bias)

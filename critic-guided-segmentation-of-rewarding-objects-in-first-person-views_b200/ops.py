@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 from ._lib import (EPI_LEAKY, EPI_LINEAR, EPI_MUL, EPI_RELU_POOL, EPI_SIGMOID, EPI_SPLIT_UP, SRC_CATUP,
-                   SRC_LEAKYGRAD, SRC_PLAIN, SRC_POOLBWD, SRC_SIGGRAD, CgsError, Conv3x3Args, Src, Wgrad3x3Args)
+                   SRC_LEAKYGRAD, SRC_PLAIN, SRC_POOLBWD, SRC_SIGGRAD, SRC_U8ROLL, CgsError, Conv3x3Args, Src, Wgrad3x3Args)
 
 _launches = 0   # kernels launched through this module (bench.py reports it)
 
@@ -61,18 +61,43 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _frames_src(x, roll):
+    """Operand descriptor for an encoder input: fp32 NHWC, or uint8 NHWC frames with the /255 cast and the
+    shift_batch roll fused into the load (roll: int, or int32 device scalar for graph replay)."""
+    if x.dtype == torch.uint8:
+        if torch.is_tensor(roll):
+            return Src(SRC_U8ROLL, x.shape[3], 0, 0, _p(x, torch.uint8), _p(roll, torch.int32), None)
+        return Src(SRC_U8ROLL, x.shape[3], 0, int(roll or 0), _p(x, torch.uint8), None, None)
+    return None
+
+
+def _gbuf(param, needed):
+    """Where a parameter gradient goes: (buffer to ACCUMULATE into, value to return to autograd).
+    Parameters owned by a FlatAdam carry `_cgs_grad`, a view of the flat gradient bucket: the kernels add
+    into it directly (no zero-fill, no AccumulateGrad add) and autograd gets None."""
+    if not needed:
+        return None, None
+    g = getattr(param, "_cgs_grad", None)
+    if g is not None and param.grad is g:      # still the live .grad (not reset by a foreign zero_grad)
+        return g, None
+    z = torch.zeros_like(param)
+    return z, z
+
+
 class EncBlock(torch.autograd.Function):
     """[Dropout ->] Conv2d(3,1,1) -> ReLU -> MaxPool2d(2): one NewCritic.features stage
     (reference nets.py:170-183).  x [B,H,W,Cin]; mask = multiplicative dropout mask or None."""
 
     @staticmethod
-    def forward(ctx, x, mask, w, b):
+    def forward(ctx, x, mask, w, b, roll=None):
         B, H, W, Cin = x.shape
         Cout = w.shape[0]
         e = torch.empty((B, H // 2, W // 2, Cout), device=x.device, dtype=torch.float32)
         idx = torch.empty((B, H // 2, W // 2, Cout), device=x.device, dtype=torch.uint8)
-        conv3x3(_src(SRC_PLAIN, Cin, x, mask), w, b, B, H, W, Cout, EPI_RELU_POOL, e, idx_out=idx)
+        xs = _frames_src(x, roll) or _src(SRC_PLAIN, Cin, x, mask)
+        conv3x3(xs, w, b, B, H, W, Cout, EPI_RELU_POOL, e, idx_out=idx)
         ctx.save_for_backward(x, mask, w, e, idx)
+        ctx.roll, ctx.params = roll, (w, b)
         ctx.set_materialize_grads(False)
         return e
 
@@ -80,21 +105,22 @@ class EncBlock(torch.autograd.Function):
     def backward(ctx, de):
         x, mask, w, e, idx = ctx.saved_tensors
         if de is None:
-            return None, None, None, None
+            return None, None, None, None, None
         de = _c(de)
         B, H, W, Cin = x.shape
         Cout = w.shape[0]
         dy = _src(SRC_POOLBWD, Cout, de, e, idx)
-        dx = dw = db = None
+        dx = rw = rb = None
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-            dw = torch.zeros_like(w)
-            db = torch.zeros(Cout, device=x.device, dtype=torch.float32)
-            wgrad3x3(_src(SRC_PLAIN, Cin, x, mask), dy, B, H, W, dw, db)
+            dw, rw = _gbuf(ctx.params[0], True)
+            db, rb = _gbuf(ctx.params[1], True)
+            xs = _frames_src(x, ctx.roll) or _src(SRC_PLAIN, Cin, x, mask)
+            wgrad3x3(xs, dy, B, H, W, dw, db)
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             conv3x3(dy, w, None, B, H, W, Cin, EPI_MUL if mask is not None else EPI_LINEAR, dx,
                     transposed=True, mul=mask)
-        return dx, None, dw, db
+        return dx, None, rw, rb, None
 
 
 class Head(torch.autograd.Function):
@@ -111,6 +137,7 @@ class Head(torch.autograd.Function):
         _call("cgs_head_fwd", _p(e3), _p(m_e3), _p(m_v), _p(w14), _p(b14), _p(w1), _p(b1), _p(w2), _p(b2),
               B, C3, NB, _p(e4), _p(v), _p(pred), _stream())
         ctx.save_for_backward(e3, m_e3, m_v, w14, w1, w2, e4, v, pred)
+        ctx.params = (w14, b14, w1, b1, w2, b2)
         ctx.set_materialize_grads(False)
         return pred, e4
 
@@ -124,18 +151,11 @@ class Head(torch.autograd.Function):
         dpred = torch.zeros_like(pred) if dpred is None else _c(dpred)
         de4 = None if de4 is None else _c(de4)
         want_w = any(ctx.needs_input_grad[3:])
-        gw = [torch.zeros_like(t) for t in (w14,)] if want_w else [None]
-        dw14 = gw[0]
-        db14 = torch.zeros(NB, device=e3.device) if want_w else None
-        dw1 = torch.zeros_like(w1) if want_w else None
-        db1 = torch.zeros(NB, device=e3.device) if want_w else None
-        dw2 = torch.zeros_like(w2) if want_w else None
-        db2 = torch.zeros(1, device=e3.device) if want_w else None
+        bufs, rets = zip(*[_gbuf(prm, want_w) for prm in ctx.params])
         de3 = torch.empty_like(e3) if ctx.needs_input_grad[0] else None
         _call("cgs_head_bwd", _p(e3), _p(m_e3), _p(m_v), _p(w14), _p(w1), _p(w2), _p(e4), _p(v), _p(pred),
-              _p(dpred), _p(de4), B, C3, NB, _p(dw14), _p(db14), _p(dw1), _p(db1), _p(dw2), _p(db2), _p(de3),
-              _stream())
-        return de3, None, None, dw14, db14, dw1, db1, dw2, db2
+              _p(dpred), _p(de4), B, C3, NB, *[_p(t) for t in bufs], _p(de3), _stream())
+        return (de3, None, None) + tuple(rets)
 
 
 class DecBlock(torch.autograd.Function):
@@ -151,7 +171,7 @@ class DecBlock(torch.autograd.Function):
         conv3x3(_src(SRC_CATUP, C0 + C1, skip, up, C0=C0, shift=shift), w, b, B, H, W, Cout,
                 EPI_LEAKY if leaky else EPI_LINEAR, out)
         ctx.save_for_backward(skip, up, w, out if leaky else None)
-        ctx.shift, ctx.leaky = shift, leaky
+        ctx.shift, ctx.leaky, ctx.params = shift, leaky, (w, b)
         ctx.set_materialize_grads(False)
         return out
 
@@ -166,10 +186,10 @@ class DecBlock(torch.autograd.Function):
         Cout = w.shape[0]
         shift = ctx.shift
         dy = _src(SRC_LEAKYGRAD, Cout, dout, out) if ctx.leaky else _src(SRC_PLAIN, Cout, dout)
-        dskip = dup = dw = db = None
+        dskip = dup = rw = rb = None
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-            dw = torch.zeros_like(w)
-            db = torch.zeros(Cout, device=w.device, dtype=torch.float32)
+            dw, rw = _gbuf(ctx.params[0], True)
+            db, rb = _gbuf(ctx.params[1], True)
             wgrad3x3(_src(SRC_CATUP, C0 + C1, skip, up, C0=C0, shift=shift), dy, B, H, W, dw, db)
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             if ctx.needs_input_grad[0]:
@@ -178,7 +198,7 @@ class DecBlock(torch.autograd.Function):
                 dup = torch.zeros_like(up) if shift == 2 else torch.empty_like(up)
             conv3x3(dy, w, None, B, H, W, C0 + C1, EPI_SPLIT_UP, dskip, transposed=True, out2=dup,
                     C0=C0, shift2=shift)
-        return dskip, dup, dw, db, None, None
+        return dskip, dup, rw, rb, None, None
 
 
 class MaskHead(torch.autograd.Function):
@@ -194,6 +214,7 @@ class MaskHead(torch.autograd.Function):
         conv3x3(_src(SRC_PLAIN, Cm, m), w, b, B, H, W, 1, EPI_SIGMOID, z, idx_out=hard,
                 thresh=float(thresh) if thresh is not None else 0.0)
         ctx.save_for_backward(m, w, z)
+        ctx.params = (w, b)
         ctx.set_materialize_grads(False)
         if hard is None:
             hard = torch.empty(0, device=m.device, dtype=torch.uint8)
@@ -208,15 +229,15 @@ class MaskHead(torch.autograd.Function):
         dz = _c(dz)
         B, H, W, Cm = m.shape
         dy = _src(SRC_SIGGRAD, 1, dz, z)
-        dm = dw = db = None
+        dm = rw = rb = None
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            dw = torch.zeros_like(w)
-            db = torch.zeros(1, device=w.device, dtype=torch.float32)
+            dw, rw = _gbuf(ctx.params[0], True)
+            db, rb = _gbuf(ctx.params[1], True)
             wgrad3x3(_src(SRC_PLAIN, Cm, m), dy, B, H, W, dw, db)
         if ctx.needs_input_grad[0]:
             dm = torch.empty_like(m)
             conv3x3(dy, w, None, B, H, W, Cm, EPI_LINEAR, dm, transposed=True)
-        return dm, dw, db, None
+        return dm, rw, rb, None
 
 
 class Dense(torch.autograd.Function):
@@ -229,6 +250,7 @@ class Dense(torch.autograd.Function):
         out = torch.empty((B, 1, 1, N), device=x.device, dtype=torch.float32)
         _call("cgs_dense_fwd", _p(x), _p(w), _p(b), B, K, N, _p(out), _stream())
         ctx.save_for_backward(x, w)
+        ctx.params = (w, b)
         ctx.set_materialize_grads(False)
         return out
 
@@ -242,10 +264,10 @@ class Dense(torch.autograd.Function):
         N, K = w.shape[0], w.shape[1]
         want_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dw = torch.zeros_like(w) if want_w else None
-        db = torch.zeros(N, device=w.device, dtype=torch.float32) if want_w else None
+        dw, rw = _gbuf(ctx.params[0], want_w)
+        db, rb = _gbuf(ctx.params[1], want_w)
         _call("cgs_dense_bwd", _p(x), _p(w), _p(dout), B, K, N, _p(dx), _p(dw), _p(db), _stream())
-        return dx, dw, db
+        return dx, rw, rb
 
 
 class Occlude(torch.autograd.Function):

@@ -86,6 +86,7 @@ class FlatAdam:
                 self.flat[off:off + k].copy_(p.data.reshape(-1))
                 p.data = self.flat[off:off + k].view(p.shape)
                 p.grad = self.gflat[off:off + k].view(p.shape)
+                p._cgs_grad = p.grad            # kernels accumulate weight gradients straight into the bucket
                 off += k
         self.lr, self.betas, self.eps = lr, betas, eps
         self.group, self.world = process_group, world_size
@@ -193,9 +194,10 @@ class Handler:
     def critic_step(self, X_u8, Y, opti, roll=0):
         """Loop body of critic_pipe (main.py:185-200) on this rank's shard; returns the loss tensor."""
         a = self.args
-        XP = self._to_input(X_u8, roll)
+        x = X_u8 if torch.is_tensor(X_u8) else torch.from_numpy(np.ascontiguousarray(X_u8))
+        x = x.to(self.device, non_blocking=True)
         Yd = Y.to(self.device, non_blocking=True).float()
-        pred = self.critic(XP).squeeze(1)
+        pred = self.critic.forward_frames(x, roll).squeeze(1)     # cast + roll fused into features.0's operand load
         loss = ops.pred_loss(pred, Yd, bce=bool(a.threshrew))
         opti.zero_grad()
         (loss / self.world if self.world > 1 else loss).backward()

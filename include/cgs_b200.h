@@ -29,7 +29,10 @@ enum cgs_src_mode {
   CGS_SRC_CATUP = 1,    /* cat(a[B,H,W,C0], nearest_up(b[B,H>>shift,W>>shift,C-C0])) — T.cat + nn.Upsample, nets.py:503-520 */
   CGS_SRC_POOLBWD = 2,  /* grad of conv output through ReLU+MaxPool2d(2): a=dE[B,H/2,W/2,C], b=E (pooled fwd output), idx=argmax */
   CGS_SRC_SIGGRAD = 3,  /* a=dZ, b=Z: dZ*Z*(1-Z) — Sigmoid backward (nets.py:491) */
-  CGS_SRC_LEAKYGRAD = 4 /* a=dOut, b=out: dOut*(out>0?1:slope) — LeakyReLU(0.01) backward (nets.py:462,489) */
+  CGS_SRC_LEAKYGRAD = 4,/* a=dOut, b=out: dOut*(out>0?1:slope) — LeakyReLU(0.01) backward (nets.py:462,489) */
+  CGS_SRC_U8ROLL = 5    /* a = (const float*)uint8 frames [B,H,W,C]: value = u8[n,y,(x+roll) mod W,c]/255 — the
+                           `.float()/255.0` cast and Handler.shift_batch roll (main.py:189,584-591) fused into the
+                           operand load; roll = `shift` field, or *(const int32_t*)b when b != NULL */
 };
 
 typedef struct cgs_src {

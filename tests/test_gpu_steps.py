@@ -165,6 +165,29 @@ def test_step_matches_oracle_on_fresh_inputs():
         close(v.grad, m_cpu[k].grad, "m." + k, arel=1e-4)
 
 
+def test_forward_frames_fuses_cast_and_roll():
+    """uint8 frames + roll through the fused operand load == frames_to_float followed by forward()."""
+    from cgs_b200.nets import NewCritic
+    from cgs_b200 import ops
+    import cgs_b200.synth as synth
+    torch.manual_seed(0)
+    c = NewCritic(dropout=0.0).to(DEV)
+    X, Y, _ = synth.synthetic_frames(9, seed=2)
+    Xd, Yd = torch.from_numpy(X).to(DEV), torch.from_numpy(Y[1]).float().to(DEV)
+    for roll in (0, 5, -7, torch.tensor([3], dtype=torch.int32, device=DEV)):
+        r = int(roll) if not torch.is_tensor(roll) else int(roll.item())
+        c.zero_grad()
+        ops.pred_loss(c(ops.frames_to_float(Xd, r).permute(0, 3, 1, 2)).squeeze(1), Yd).backward()
+        g1 = [p.grad.clone() for p in c.parameters()]
+        p1 = c(ops.frames_to_float(Xd, r).permute(0, 3, 1, 2))
+        c.zero_grad()
+        p2 = c.forward_frames(Xd, roll)
+        ops.pred_loss(p2.squeeze(1), Yd).backward()
+        assert torch.equal(p1, p2)
+        for a, b in zip(g1, (p.grad for p in c.parameters())):
+            close(b, a, "grad", rtol=1e-5, arel=1e-6)      # same values, atomics reorder the sums
+
+
 def test_flat_adam_matches_torch_adam():
     from cgs_b200.nets import NewCritic
     from cgs_b200.train_handler import FlatAdam

@@ -24,7 +24,7 @@ class Conv3x3Args(C.Structure):
     _fields_ = [("src", Src), ("w", _f32p), ("bias", _f32p), ("transposed", C.c_int32),
                 ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cout", C.c_int32), ("epi", C.c_int32),
                 ("out", _f32p), ("out2", _f32p), ("idx_out", _u8p), ("mul", _f32p),
-                ("C0", C.c_int32), ("shift2", C.c_int32), ("thresh", C.c_float)]
+                ("C0", C.c_int32), ("shift2", C.c_int32), ("thresh", C.c_float), ("precision", C.c_int32)]
 
 
 class Wgrad3x3Args(C.Structure):
@@ -46,6 +46,7 @@ EXPORTS = {
     "cgs_frames_to_float": [_u8p] + [C.c_int32] * 5 + [C.c_void_p, _f32p, C.c_void_p],
     "cgs_adam_step": [_f32p] * 4 + [C.c_int64] + [C.c_double] * 4 + [C.c_void_p, C.c_float, C.c_void_p],
     "cgs_threshold": [_f32p, C.c_int64, C.c_float, C.c_int32, _u8p, C.c_void_p],
+    "cgs_tc_status": [],
 }
 
 _lib = None

@@ -260,6 +260,9 @@ static int launch_conv(const cgs_conv3x3_args& a, cudaStream_t st) {
   return check_launch("conv3x3");
 }
 
+bool conv_tc_supported(const cgs_conv3x3_args& a);
+int launch_conv_tc(const cgs_conv3x3_args& a, cudaStream_t st);
+
 static int check_src(const cgs_src& s, const char* who) {
   CGS_REQUIRE(s.a != nullptr && s.C > 0, "%s: null operand / C<=0", who);
   if (s.mode == CGS_SRC_CATUP) CGS_REQUIRE(s.b && s.C0 > 0 && s.C0 < s.C && (s.shift == 1 || s.shift == 2), "%s: bad CATUP operand", who);
@@ -476,6 +479,7 @@ extern "C" int cgs_conv3x3(const cgs_conv3x3_args* a, void* stream) {
     CGS_REQUIRE(a->out != nullptr, "conv3x3: null out");
   if (a->epi == CGS_EPI_MUL) CGS_REQUIRE(a->mul != nullptr, "conv3x3: MUL epilogue needs mul");
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->precision == CGS_TF32 && conv_tc_supported(*a)) return launch_conv_tc(*a, st);
   if (a->Cout == 1) return launch_conv<1>(*a, st);
   if (a->Cout <= 4) return launch_conv<4>(*a, st);
   if (a->Cout % 16 == 0 && a->H >= 32) return launch_conv<16>(*a, st);   // small maps: more, shorter CTAs

@@ -14,6 +14,17 @@ from ._lib import (EPI_LEAKY, EPI_LINEAR, EPI_MUL, EPI_RELU_POOL, EPI_SIGMOID, E
                    SRC_LEAKYGRAD, SRC_PLAIN, SRC_POOLBWD, SRC_SIGGRAD, SRC_U8ROLL, CgsError, Conv3x3Args, Src, Wgrad3x3Args)
 
 _launches = 0   # kernels launched through this module (bench.py reports it)
+_precision = 0  # 0 = fp32 FFMA kernels (exact parity path), 1 = tcgen05 TF32 convolutions where covered
+
+
+def set_precision(name):
+    """'fp32' (default; rtol 1e-4 vs the reference) or 'tf32' (tcgen05 tensor-core convolutions, fp32 accumulate)."""
+    global _precision
+    _precision = {"fp32": 0, "tf32": 1}[name]
+
+
+def get_precision():
+    return "tf32" if _precision else "fp32"
 
 
 def launch_count():
@@ -48,7 +59,7 @@ def _src(mode, Cn, a, b=None, idx=None, C0=0, shift=0):
 def conv3x3(src, w, bias, B, H, W, Cout, epi, out, transposed=False, out2=None, idx_out=None, mul=None,
             C0=0, shift2=0, thresh=0.0):
     a = Conv3x3Args(src, _p(w), _p(bias), int(transposed), B, H, W, Cout, epi, _p(out), _p(out2),
-                    _p(idx_out, torch.uint8), _p(mul), C0, shift2, thresh)
+                    _p(idx_out, torch.uint8), _p(mul), C0, shift2, thresh, _precision)
     _call("cgs_conv3x3", C.byref(a), _stream())
 
 

@@ -70,7 +70,12 @@ typedef struct cgs_conv3x3_args {
   int32_t C0;             /* SPLIT_UP: split point */
   int32_t shift2;         /* SPLIT_UP: 1 or 2 */
   float thresh;           /* SIGMOID hard-mask threshold (>=) */
+  int32_t precision;      /* CGS_FP32: CUDA-core FFMA, exact fp32 (rtol 1e-4 parity path);
+                             CGS_TF32: tcgen05.mma kind::tf32 with fp32 accumulation in TMEM where the shape is
+                             covered (H%16==0, W%8==0), fp32 kernel otherwise */
 } cgs_conv3x3_args;
+
+enum cgs_precision { CGS_FP32 = 0, CGS_TF32 = 1 };
 
 /* Conv2d(k=3,s=1,p=1) fprop or dgrad with fused prologue/epilogue.
  * Replaces: nn.Conv2d + ReLU + MaxPool2d (nets.py:170-182), T.cat + nn.Upsample + nn.Conv2d
@@ -150,6 +155,9 @@ int cgs_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
 
 /* hard[i] = z[i] >= thresh (main.py:1164) or z[i] > thresh when strict (main.py:964). */
 int cgs_threshold(const float* z, int64_t n, float thresh, int32_t strict, uint8_t* hard, void* stream);
+
+/* Non-zero if a tcgen05 kernel ever timed out on its completion barrier (reads a device flag; synchronises). */
+int cgs_tc_status(void);
 
 const char* cgs_last_error(void);
 int cgs_version(void);

@@ -217,6 +217,7 @@ def run_ours(args, rank, world):
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     B, W, K = args.batch, args.warmup, args.steps
+    ops.set_precision(args.precision)
     hargs = parse_args(["--chfak", str(args.chfak)] + (["-frozen"] if args.workload == "hourglass" else []))
     torch.manual_seed(0)
     H = Handler(hargs, device=dev, rank=rank, world_size=world, process_group=group)
@@ -279,8 +280,10 @@ def run_ours(args, rank, world):
         line = {"metric": METRIC if args.workload == "critic_train" else args.workload + "_frames_per_s",
                 "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
                 "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
+                "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
                 "config": {"workload": WORKLOADS[args.workload], "batch_per_gpu": B, "global_batch": B * world,
+                           "precision": ("conv fprop/dgrad: tcgen05 kind::tf32, fp32 accumulate in TMEM; wgrad, head, "
+                                         "losses, Adam: fp32" if args.precision == "tf32" else "all fp32 (FFMA)"),
                            "chfak": args.chfak, "parallelism": f"dp{world}", "timing": "cuda events per step, L2 flushed "
                            "(256 MiB memset) between timed steps", "graph": True},
                 "e2e": {"value": world * B * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d,
@@ -322,6 +325,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--chfak", type=int, default=1)
     ap.add_argument("--no-extras", action="store_true", help="skip per-kernel roofline and CPU baseline legs")
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
+                    help="tf32: tcgen05 TF32 conv fprop/dgrad (fp32 accumulate) where covered; fp32: exact FFMA kernels")
     args = ap.parse_args()
     if args.batch == 0:
         args.batch = 1024 if args.workload == "hourglass" else 256

@@ -29,7 +29,7 @@ class Conv3x3Args(C.Structure):
 
 class Wgrad3x3Args(C.Structure):
     _fields_ = [("x", Src), ("dy", Src), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-                ("dw", _f32p), ("db", _f32p)]
+                ("dw", _f32p), ("db", _f32p), ("precision", C.c_int32)]
 
 
 EXPORTS = {

@@ -64,6 +64,13 @@ struct FastDiv {
 inline FastDiv make_fastdiv(int d) { return FastDiv{(uint32_t)(0xFFFFFFFFu / (uint32_t)d + 1u), d}; }   // d >= 2
 __device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return (int)__umulhi((uint32_t)n, f.m); }
 
+// Tile geometry shared by the wgrad kernels (conv_fp32.cu, wgrad_mma.cu).
+struct WgGeom {
+  int th, tw, fpc, tiles_y, tiles_x;
+  int rsx, psx, rsy, psy;
+  FastDiv dsw, dsh, dtw, dth;
+};
+
 // Up to 8 consecutive floats (channels) of one pixel -> registers; two 128-bit loads when aligned.
 __device__ __forceinline__ void load8(const float* __restrict__ p, int n, bool vec, float (&v)[8]) {
   if (vec && n == 8) {

@@ -260,6 +260,8 @@ static int launch_conv(const cgs_conv3x3_args& a, cudaStream_t st) {
   return check_launch("conv3x3");
 }
 
+bool wgrad_mma_supported(const cgs_wgrad3x3_args& a);
+int launch_wgrad_mma(const cgs_wgrad3x3_args& a, cudaStream_t st);
 bool conv_tc_supported(const cgs_conv3x3_args& a);
 int launch_conv_tc(const cgs_conv3x3_args& a, cudaStream_t st);
 
@@ -277,11 +279,6 @@ static int check_src(const cgs_src& s, const char* who) {
 // CTA: one (co block, ci block) x a pixel tile; 16 "pixel groups" (rows) x 16 (co,ci)
 // register blocks of CO_R x CI_R x 9 taps; rows reduced with warp shuffles, one atomic per
 // weight per CTA.
-struct WgGeom {
-  int th, tw, fpc, tiles_y, tiles_x;
-  int rsx, psx, rsy, psy;
-  FastDiv dsw, dsh, dtw, dth;
-};
 
 template <int CO_R, int CI_R, int NCO, int NCI>
 __global__ void __launch_bounds__(256) wgrad3x3_kernel(const cgs_wgrad3x3_args p, const WgGeom g) {
@@ -376,6 +373,7 @@ __global__ void __launch_bounds__(256) wgrad3x3_kernel(const cgs_wgrad3x3_args p
           win[b][ky][1] = xr[b * g.psx + ky * g.rsx + 0];
           win[b][ky][2] = xr[b * g.psx + ky * g.rsx + 1];
         }
+#pragma unroll 4
       for (int xx = 0; xx < tw; ++xx) {
         float dy[CO_R];
 #pragma unroll
@@ -495,6 +493,7 @@ extern "C" int cgs_wgrad3x3(const cgs_wgrad3x3_args* a, void* stream) {
   CGS_REQUIRE(a->H >= 2 && a->W >= 2 && (a->H & (a->H - 1)) == 0 && (a->W & (a->W - 1)) == 0 && a->H <= 1024 && a->W <= 1024,
               "wgrad3x3: H,W must be powers of two >= 2 (got %dx%d)", a->H, a->W);
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->precision == CGS_TF32 && wgrad_mma_supported(*a)) return launch_wgrad_mma(*a, st);
   if (a->dy.C == 1) return launch_wgrad<1, 1, 1, 16>(*a, st);
   if (a->x.C <= 4) return launch_wgrad<2, 1, 4, 4>(*a, st);
   return launch_wgrad<2, 2, 4, 4>(*a, st);

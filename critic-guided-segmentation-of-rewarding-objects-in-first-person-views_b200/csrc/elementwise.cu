@@ -126,19 +126,27 @@ __global__ void mask_reg_kernel(const float* __restrict__ z, const float* __rest
 }
 
 // ---------------------------------------------------------------- frames uint8 -> float
-__global__ void frames_to_float_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int C, int roll,
-                                       const int* __restrict__ roll_dev, float* __restrict__ out) {
-  if (roll_dev) roll = *roll_dev;
-  const int64_t total = (int64_t)B * H * W * C;
-  const int rowc = W * C;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / rowc;
-    const int r = (int)(i - row * rowc);
-    const int x = r / C, c = r - x * C;
-    int sx = x + roll;
-    sx %= W;
-    if (sx < 0) sx += W;
-    out[i] = (float)__ldg(in + row * rowc + sx * C + c) / 255.0f;
+// 4 consecutive output floats (one 128-bit store) per thread; the roll only permutes bytes inside a row of
+// W*C bytes, so the source is 4 byte loads from the same (L1-resident) row.  Division-free (FastDiv by W*C/4).
+__global__ void frames_to_float_kernel(const uint8_t* __restrict__ in, int64_t nvec, int rowc, FastDiv dq, int rollc,
+                                       const int* __restrict__ roll_dev, int C, float* __restrict__ out) {
+  if (roll_dev) {
+    int r = *roll_dev * C % rowc;
+    rollc = r < 0 ? r + rowc : r;
+  }
+  const int q = rowc >> 2;   // float4 per row
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = (i < 0x7fffffff / q) ? (int64_t)fdiv((int)i, dq) : i / q;
+    const int j = (int)(i - row * q) * 4;
+    const uint8_t* src = in + row * rowc;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int o = j + k + rollc;
+      if (o >= rowc) o -= rowc;
+      v[k] = (float)__ldg(src + o) / 255.0f;
+    }
+    *reinterpret_cast<float4*>(out + row * rowc + j) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -210,7 +218,13 @@ extern "C" int cgs_mask_reg(const float* z, const float* vpred, int64_t n, int32
 extern "C" int cgs_frames_to_float(const uint8_t* in, int32_t B, int32_t H, int32_t W, int32_t C, int32_t roll,
                                    const int32_t* roll_dev, float* out, void* stream) {
   CGS_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && C > 0, "frames_to_float: bad args");
-  frames_to_float_kernel<<<grid_for((int64_t)B * H * W * C, 256), 256, 0, (cudaStream_t)stream>>>(in, B, H, W, C, roll, roll_dev, out);
+  const int rowc = W * C;
+  CGS_REQUIRE((rowc & 3) == 0 && rowc >= 8, "frames_to_float: W*C must be a multiple of 4 (got %d)", rowc);
+  int rollc = (int)(((int64_t)roll * C) % rowc);
+  if (rollc < 0) rollc += rowc;
+  const int64_t nvec = (int64_t)B * H * (rowc / 4);
+  frames_to_float_kernel<<<grid_for(nvec, 256), 256, 0, (cudaStream_t)stream>>>(in, nvec, rowc, make_fastdiv(rowc / 4), rollc,
+                                                                             roll_dev, C, out);
   return check_launch("frames_to_float");
 }
 

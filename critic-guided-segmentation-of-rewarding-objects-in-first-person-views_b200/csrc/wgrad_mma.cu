@@ -1,0 +1,189 @@
+// Weight gradient of the 3x3 convolutions on the tensor cores (TF32 operands, fp32 accumulate).
+//
+// GEMM view:  dW[(ci,tap), co] = sum_pixels  X[pixel + tap, ci] * dY[pixel, co]   (+ a row of ones -> bias grad)
+// i.e. M = 9*Cin (tiny), N = Cout (tiny), K = B*H*W (huge): the opposite of what tcgen05 wants.  A tcgen05
+// A-operand must sit in shared memory in the canonical core-matrix layout, so the nine shifted views of the
+// haloed tile would have to be materialised as a 9x im2col copy; the warp-level mma.m16n8k8 instead takes its
+// A fragment from registers, so every lane GATHERS its two (ci,tap) rows straight from the planar haloed
+// tile (row base = ci*plane + ky*row + kx, then +x along the reduction).  That makes the instruction mix
+// 22 LDS + 5 HMMA per 8 pixels per warp instead of ~170 LDS + 1150 FFMA, and the kernel staging-bound.
+// The tcgen05 kernels (conv_tc.cu) keep fprop and dgrad, where M = pixels is the large dimension.
+//
+// CTA = one 8-channel (ci) block x one 8-channel (co) block x a pixel tile; the 8 warps split the tile rows
+// (split-K), partial tiles are reduced through shared memory and pushed with one RED per weight per CTA.
+#include "common.cuh"
+
+namespace cgs {
+
+
+constexpr int WM_CI = 8, WM_CO = 8, WM_MT = 5;   // 5 m16 tiles = 80 rows >= 72 (ci,tap) rows + 1 bias row
+
+__device__ __forceinline__ uint32_t f2tf32(float f) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(f));
+  return r;
+}
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_args p, const WgGeom g) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  const int H = p.H, W = p.W, Cin = p.x.C, Cout = p.dy.C;
+  const int th = g.th, tw = g.tw, sh = th + 2, sw = tw + 2;
+  float* s_x = smem;                                   // [WM_CI][fpc*sh rows][rsx]
+  float* s_y = smem + (size_t)WM_CI * g.psx;           // [WM_CO][fpc*th rows][rsy]
+
+  int bid = blockIdx.x;
+  const int tix = bid % g.tiles_x; bid /= g.tiles_x;
+  const int tiy = bid % g.tiles_y; bid /= g.tiles_y;
+  const int n0 = bid * g.fpc, y0 = tiy * th, x0 = tix * tw;
+  const int co0 = blockIdx.y * WM_CO, ci0 = blockIdx.z * WM_CI;
+  const int con = min(WM_CO, Cout - co0), cin = min(WM_CI, Cin - ci0);
+
+  // ---- stage X (haloed) and dY tiles, planar [channel][row][x]
+  {
+    const int npix = g.fpc * sh * sw;
+#pragma unroll 2
+    for (int pix = tid; pix < npix; pix += 256) {
+      const int row = fdiv(pix, g.dsw), xx = pix - row * sw;
+      const int ff = fdiv(row, g.dsh), yy = row - ff * sh;
+      const int gy = y0 + yy - 1, gx = x0 + xx - 1, nn = n0 + ff;
+      float v[8];
+      if (nn < p.B && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        src_load8(p.x, nn, gy, gx, ci0, cin, H, W, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+      float* d = s_x + row * g.rsx + xx;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < cin) d[i * g.psx] = v[i];
+    }
+    const int npy = g.fpc * th * tw;
+#pragma unroll 2
+    for (int pix = tid; pix < npy; pix += 256) {
+      const int row = fdiv(pix, g.dtw), xx = pix - row * tw;
+      const int ff = fdiv(row, g.dth), yy = row - ff * th;
+      const int gy = y0 + yy, gx = x0 + xx, nn = n0 + ff;
+      float v[8];
+      if (nn < p.B) {
+        src_load8(p.dy, nn, gy, gx, co0, con, H, W, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+      float* d = s_y + row * g.rsy + xx;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i * g.psy] = (i < con) ? v[i] : 0.f;
+    }
+  }
+  __syncthreads();
+
+  // ---- per-lane A rows: m = ci*9 + tap (the OIHW order of dw), m == 72 is the all-ones bias row
+  const int warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+  int offA[WM_MT][2];   // >= 0: smem offset of the row base; -1: zero row; -2: ones row
+#pragma unroll
+  for (int mt = 0; mt < WM_MT; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int mrow = 16 * mt + gid + 8 * h;
+      int off = -1;
+      if (mrow < 9 * cin) {
+        const int ci = mrow / 9, tap = mrow - ci * 9;
+        off = ci * g.psx + (tap / 3) * g.rsx + (tap % 3);
+      } else if (mrow == 9 * WM_CI) {
+        off = -2;
+      }
+      offA[mt][h] = off;
+    }
+  float acc[WM_MT][4];
+#pragma unroll
+  for (int mt = 0; mt < WM_MT; ++mt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[mt][j] = 0.f;
+
+  const int R = g.fpc * th;
+  for (int r = warp; r < R; r += 8) {
+    const int ff = fdiv(r, g.dth), yy = r - ff * th;
+    const float* xrow = s_x + (ff * sh + yy) * g.rsx + tig;
+    const float* yrow = s_y + gid * g.psy + r * g.rsy + tig;
+    for (int xb = 0; xb < tw; xb += 8) {
+      const uint32_t b0 = f2tf32(yrow[xb]), b1 = f2tf32(yrow[xb + 4]);
+#pragma unroll
+      for (int mt = 0; mt < WM_MT; ++mt) {
+        uint32_t a[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int off = offA[mt][h];
+          float v0 = 0.f, v1 = 0.f;
+          if (off >= 0) { v0 = xrow[off + xb]; v1 = xrow[off + xb + 4]; }
+          else if (off == -2) { v0 = 1.f; v1 = 1.f; }
+          a[h] = f2tf32(v0);
+          a[2 + h] = f2tf32(v1);
+        }
+        mma_tf32(acc[mt], a[0], a[1], a[2], a[3], b0, b1);
+      }
+    }
+  }
+
+  // ---- reduce the 8 warps' partial tiles through shared memory (reuse the X tile), then one RED per weight
+  __syncthreads();
+  float* s_red = smem;   // [8 warps][80 rows][8 cols]
+#pragma unroll
+  for (int mt = 0; mt < WM_MT; ++mt) {
+    float* d = s_red + (warp * 16 * WM_MT + 16 * mt + gid) * 8 + 2 * tig;
+    d[0] = acc[mt][0]; d[1] = acc[mt][1];
+    d[64] = acc[mt][2]; d[65] = acc[mt][3];     // row + 8
+  }
+  __syncthreads();
+  for (int e = tid; e < 16 * WM_MT * 8; e += 256) {
+    const int mrow = e >> 3, n = e & 7;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_red[w * 16 * WM_MT * 8 + e];
+    if (n >= con) continue;
+    if (mrow < 9 * cin) {
+      atomicAdd(p.dw + ((size_t)(co0 + n) * Cin + ci0) * 9 + mrow, s);
+    } else if (mrow == 9 * WM_CI && p.db && blockIdx.z == 0) {
+      atomicAdd(p.db + co0 + n, s);
+    }
+  }
+}
+
+bool wgrad_mma_supported(const cgs_wgrad3x3_args& a) { return a.W >= 8 && a.H >= 8; }
+
+int launch_wgrad_mma(const cgs_wgrad3x3_args& a, cudaStream_t st) {
+  WgGeom g;
+  g.th = a.H < 32 ? a.H : 32;
+  g.tw = a.W < 32 ? a.W : 32;
+  if (g.th * g.tw > 512 && (long)a.B * (a.H / g.th) * (a.W / g.tw) < 592) g.th /= 2;   // more CTAs when the batch is small
+  g.tiles_y = a.H / g.th; g.tiles_x = a.W / g.tw;
+  g.fpc = 1;
+  while (g.fpc * g.th * g.tw < 512 && (long)((a.B + 2 * g.fpc - 1) / (2 * g.fpc)) >= 148) g.fpc *= 2;
+  g.rsx = (g.tw + 2) | 1; g.rsy = g.tw | 1;
+  g.psx = g.fpc * (g.th + 2) * g.rsx; g.psx += (40 - (g.psx % 32)) % 32;
+  g.psy = g.fpc * g.th * g.rsy;       g.psy += (40 - (g.psy % 32)) % 32;
+  g.dsw = make_fastdiv(g.tw + 2); g.dsh = make_fastdiv(g.th + 2);
+  g.dtw = make_fastdiv(g.tw);     g.dth = make_fastdiv(g.th);
+  size_t smem = ((size_t)WM_CI * g.psx + (size_t)WM_CO * g.psy) * sizeof(float);
+  const size_t red = (size_t)8 * 16 * WM_MT * 8 * sizeof(float);
+  if (smem < red) smem = red;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(wgrad3x3_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  const int nblk = ((a.B + g.fpc - 1) / g.fpc) * g.tiles_x * g.tiles_y;
+  dim3 grid(nblk, (a.dy.C + WM_CO - 1) / WM_CO, (a.x.C + WM_CI - 1) / WM_CI);
+  wgrad3x3_mma_kernel<<<grid, 256, smem, st>>>(a, g);
+  return check_launch("wgrad3x3_mma");
+}
+
+}  // namespace cgs

@@ -64,6 +64,7 @@ class NewCritic(nn.Module):
         self.crit = nn.Sequential(nn.Flatten(), nn.Linear(nb, nb), activation(), nn.Dropout(dropout),
                                   nn.Linear(nb, 1), nn.Sigmoid())
         self._conv_idx = (0, 3, 6, 10)
+        self.fuse_frame_cast = False   # True: read uint8 frames directly in the first conv (saves the fp32 copy; slower loads)
         self._forced_masks = None   # test hook: (m_e2 [B,8,8,8c], m_e3 [B,4,4,16c], m_v [B,32c]) NHWC
 
     def _dropout_masks(self, B, device):
@@ -89,7 +90,11 @@ class NewCritic(nn.Module):
             raise ValueError(f"NewCritic.forward_frames: expected uint8 [B,{self.width},{self.width},{self.colorchs}]")
         if not X_u8.is_cuda:
             raise CgsError("NewCritic.forward_frames: input is on CPU; cgs_b200 has no CPU path")
-        return self._run(X_u8.contiguous(), roll, collect)
+        if self.fuse_frame_cast:
+            return self._run(X_u8.contiguous(), roll, collect)       # cast + roll inside features.0's operand load
+        if torch.is_tensor(roll):
+            return self._run(ops.frames_to_float(X_u8, 0, roll), None, collect)
+        return self._run(ops.frames_to_float(X_u8, roll), None, collect)
 
     def _run(self, x, roll, collect):
         m_e2, m_e3, m_v = self._dropout_masks(x.shape[0], x.device)

@@ -64,7 +64,7 @@ def conv3x3(src, w, bias, B, H, W, Cout, epi, out, transposed=False, out2=None, 
 
 
 def wgrad3x3(xsrc, dysrc, B, H, W, dw, db):
-    a = Wgrad3x3Args(xsrc, dysrc, B, H, W, _p(dw), _p(db))
+    a = Wgrad3x3Args(xsrc, dysrc, B, H, W, _p(dw), _p(db), _precision)
     _call("cgs_wgrad3x3", C.byref(a), _stream())
 
 

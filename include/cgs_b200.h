@@ -88,6 +88,7 @@ typedef struct cgs_wgrad3x3_args {
   int32_t B, H, W;
   float* dw;              /* OIHW [Cout,Cin,3,3], ACCUMULATED into (caller zeroes) */
   float* db;              /* [Cout] accumulated into, or NULL */
+  int32_t precision;      /* CGS_FP32: FFMA; CGS_TF32: tensor-core mma (TF32 operands, fp32 accumulate) for H,W >= 8 */
 } cgs_wgrad3x3_args;
 
 /* Weight + bias gradient of Conv2d(k=3,s=1,p=1): replaces autograd's conv weight-gradient

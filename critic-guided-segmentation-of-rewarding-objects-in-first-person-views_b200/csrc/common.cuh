@@ -87,7 +87,7 @@ __device__ __forceinline__ void load8(const float* __restrict__ p, int n, bool v
 __device__ __forceinline__ void src_load8(const cgs_src& s, int n, int y, int x, int c0, int cn, int H, int W, float (&v)[8]) {
   switch (s.mode) {
     case CGS_SRC_PLAIN: {
-      const size_t o = (((size_t)n * H + y) * W + x) * s.C + c0;
+      const size_t o = (size_t)(unsigned)((n * H + y) * W + x) * (unsigned)s.C + c0;
       const bool vec = (s.C & 3) == 0;
       load8(s.a + o, cn, vec, v);
       if (s.b) {
@@ -100,8 +100,8 @@ __device__ __forceinline__ void src_load8(const cgs_src& s, int n, int y, int x,
     }
     case CGS_SRC_CATUP: {
       const int C0 = s.C0, C1 = s.C - C0;
-      const size_t pa = (((size_t)n * H + y) * W + x) * C0;
-      const size_t pb = (((size_t)n * (H >> s.shift) + (y >> s.shift)) * (W >> s.shift) + (x >> s.shift)) * C1;
+      const size_t pa = (size_t)(unsigned)((n * H + y) * W + x) * (unsigned)C0;
+      const size_t pb = (size_t)(unsigned)((n * (H >> s.shift) + (y >> s.shift)) * (W >> s.shift) + (x >> s.shift)) * (unsigned)C1;
       if (c0 + cn <= C0) {
         load8(s.a + pa + c0, cn, (C0 & 3) == 0, v);
       } else if (c0 >= C0) {
@@ -116,7 +116,7 @@ __device__ __forceinline__ void src_load8(const cgs_src& s, int n, int y, int x,
       return;
     }
     case CGS_SRC_POOLBWD: {
-      const size_t o = (((size_t)n * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * s.C + c0;
+      const size_t o = (size_t)(unsigned)((n * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * (unsigned)s.C + c0;
       const int pos = ((y & 1) << 1) | (x & 1);
       const bool vec = (s.C & 7) == 0;
       float e[8];
@@ -135,7 +135,7 @@ __device__ __forceinline__ void src_load8(const cgs_src& s, int n, int y, int x,
       return;
     }
     case CGS_SRC_SIGGRAD: {
-      const size_t o = (((size_t)n * H + y) * W + x) * s.C + c0;
+      const size_t o = (size_t)(unsigned)((n * H + y) * W + x) * (unsigned)s.C + c0;
       const bool vec = (s.C & 3) == 0;
       float z[8];
       load8(s.a + o, cn, vec, v);
@@ -145,7 +145,7 @@ __device__ __forceinline__ void src_load8(const cgs_src& s, int n, int y, int x,
       return;
     }
     case CGS_SRC_LEAKYGRAD: {
-      const size_t o = (((size_t)n * H + y) * W + x) * s.C + c0;
+      const size_t o = (size_t)(unsigned)((n * H + y) * W + x) * (unsigned)s.C + c0;
       const bool vec = (s.C & 3) == 0;
       float z[8];
       load8(s.a + o, cn, vec, v);

@@ -13,9 +13,13 @@
 // lanes (one output pixel per thread, all channels in registers) with tcgen05.ld and run the fused
 // epilogue: bias, ReLU + 2x2 max-pool + argmax via lane shuffles (a pool window lives in lanes l, l^1,
 // l^8, l^9), LeakyReLU, sigmoid + threshold, dropout-mask multiply, or the concat/upsample backward
-// split.  Weights are repacked once per CTA into the matching B layout and stay resident; the CTA is
-// persistent over tiles.  Operand prologues (concat+upsample, dropout, pool/ReLU/sigmoid/leaky
-// backward, uint8 cast + roll) are the same src_load8 loaders as the fp32 kernel.
+// split.  Weights are repacked once per CTA into the matching B layout and stay resident.
+//
+// Pipeline (persistent CTA, double-buffered A tile and TMEM accumulator):
+//     stage(i+1) | MMA(i) in flight  ->  wait MMA(i)  ->  issue MMA(i+1)  ->  epilogue(i) | MMA(i+1) in flight
+// so global-load latency, tensor-core latency and the epilogue overlap with one __syncthreads per tile.
+// Operand prologues (concat+upsample, dropout, pool/ReLU/sigmoid/leaky backward, uint8 cast + roll) are
+// the same src_load8 loaders as the fp32 kernel.
 #include "common.cuh"
 
 namespace cgs {
@@ -46,7 +50,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+template <int NC>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[NC]);
+
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
@@ -58,28 +66,145 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Tight try_wait loop, bounded: a protocol bug must surface as an error, never as a hung GPU.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-  // bounded spin: a protocol bug must surface as an error, never as a hung GPU
-  for (int it = 0; it < (1 << 22); ++it) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) return true;
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t.reg .u32 cnt;\n\tmov.u32 cnt, 0;\n"
+      "TC_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t@P1 bra TC_DONE;\n\t"
+      "add.u32 cnt, cnt, 1;\n\tsetp.lt.u32 P1, cnt, 4000000;\n\t@P1 bra TC_WAIT;\n\t"
+      "mov.u32 %0, 0;\n\tbra TC_END;\n"
+      "TC_DONE:\n\tmov.u32 %0, 1;\n"
+      "TC_END:\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// Epilogue for NC channels [cb, cb+NC) of this thread's output pixel.
+template <int NC>
+__device__ __forceinline__ void tc_epilogue(const cgs_conv3x3_args& p, uint32_t taddr, int cb, int n, int y, int x,
+                                            bool odd_x, bool odd_y) {
+  const int H = p.H, W = p.W, Cout = p.Cout;
+  float a[NC];
+  tmem_ld<NC>(taddr + (uint32_t)cb, a);
+  const int cn = min(NC, Cout - cb);
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) a[j] += (j < cn) ? __ldg(p.bias + cb + j) : 0.f;
   }
-  return false;
+  if (p.epi == CGS_EPI_RELU_POOL) {
+    // 2x2 window = lanes (l, l^1, l^8, l^9); first maximum in row-major order wins (ATen max_pool2d).
+    float mx[NC];
+    uint32_t abits = 0;   // per channel: 1 if the right element of this row's pair is the (strict) max
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const float v = fmaxf(a[j], 0.f);
+      const float o = __shfl_xor_sync(0xffffffffu, v, 1);
+      const float left = odd_x ? o : v, right = odd_x ? v : o;
+      const bool r = right > left;
+      mx[j] = r ? right : left;
+      abits |= (r ? 1u : 0u) << j;
+    }
+    const uint32_t obits = __shfl_xor_sync(0xffffffffu, abits, 8);
+    const uint32_t tbits = odd_y ? obits : abits, bbits = odd_y ? abits : obits;
+    const bool owner = !odd_x && !odd_y;
+    float res[NC];
+    uint32_t idxw[(NC + 3) / 4];
+#pragma unroll
+    for (int q = 0; q < (NC + 3) / 4; ++q) idxw[q] = 0;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const float o = __shfl_xor_sync(0xffffffffu, mx[j], 8);
+      const float top = odd_y ? o : mx[j], bot = odd_y ? mx[j] : o;
+      const bool b = bot > top;
+      res[j] = b ? bot : top;
+      const uint32_t am = b ? (2u + ((bbits >> j) & 1u)) : ((tbits >> j) & 1u);
+      idxw[j >> 2] |= am << (8 * (j & 3));
+    }
+    if (owner) {
+      const size_t o = (size_t)(unsigned)((n * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * (unsigned)Cout + cb;
+      if (cn == NC && (Cout & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < NC; j += 4) {
+          *reinterpret_cast<float4*>(p.out + o + j) = make_float4(res[j], res[j + 1], res[j + 2], res[j + 3]);
+          if (p.idx_out) *reinterpret_cast<uint32_t*>(p.idx_out + o + j) = idxw[j >> 2];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NC; ++j)
+          if (j < cn) {
+            p.out[o + j] = res[j];
+            if (p.idx_out) p.idx_out[o + j] = (uint8_t)((idxw[j >> 2] >> (8 * (j & 3))) & 0xff);
+          }
+      }
+    }
+    return;
+  }
+  if (p.epi == CGS_EPI_SPLIT_UP) {
+    const int C0 = p.C0, C1 = Cout - C0;
+    const bool owner = !odd_x && !odd_y;
+    const size_t po = (size_t)(unsigned)((n * H + y) * W + x) * (unsigned)C0;
+    const size_t pu = (size_t)(unsigned)((n * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * (unsigned)C1;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int c = cb + j;
+      float s = a[j] + __shfl_xor_sync(0xffffffffu, a[j], 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 8);
+      if (j >= cn) continue;
+      if (c < C0) {
+        if (p.out) p.out[po + c] = a[j];
+      } else if (p.out2 && owner) {
+        p.out2[pu + (c - C0)] = s;
+      }
+    }
+    return;
+  }
+  const size_t o = (size_t)(unsigned)((n * H + y) * W + x) * (unsigned)Cout + cb;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    float v = a[j];
+    if (p.epi == CGS_EPI_LEAKY) v = v > 0.f ? v : v * kLeakySlope;
+    else if (p.epi == CGS_EPI_SIGMOID) v = 1.f / (1.f + expf(-v));
+    else if (p.epi == CGS_EPI_MUL) v *= (j < cn) ? __ldg(p.mul + o + j) : 0.f;
+    a[j] = v;
+  }
+  if (cn == NC && (Cout & 3) == 0) {
+#pragma unroll
+    for (int j = 0; j < NC; j += 4) *reinterpret_cast<float4*>(p.out + o + j) = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if (j < cn) p.out[o + j] = a[j];
+  }
+  if (p.epi == CGS_EPI_SIGMOID && p.idx_out) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if (j < cn) p.idx_out[o + j] = a[j] >= p.thresh ? 1 : 0;
+  }
 }
 
 __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const cgs_conv3x3_args p, const TcGeom g, int* __restrict__ status) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int H = p.H, W = p.W, Cin = p.src.C, Cout = p.Cout;
   const int nch = g.nch, n_pad = g.n_pad;
+  const int a_floats = nch * TC_SLOTS * 4;                                           // one A buffer
   float* s_w = reinterpret_cast<float*>(smem_raw);                                   // [9][nch][n_pad][4]
-  float* s_a = s_w + (size_t)9 * nch * n_pad * 4;                                    // [nch][180][4]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_a + (size_t)nch * TC_SLOTS * 4);
+  float* s_a = s_w + (size_t)9 * nch * n_pad * 4;                                    // [2][nch][180][4]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_a + (size_t)2 * a_floats);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
 
   // ---- one-time setup: TMEM allocation (warp 0), mbarrier, resident weights
@@ -94,15 +219,19 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const cgs_conv3x
   }
   {
     // B operand: element (tap, ci, co) -> [(tap*nch + ci/4)*n_pad + co]*4 + ci%4, zero padded
-    const int total = 9 * nch * n_pad * 4;
-    for (int e = tid; e < total; e += TC_THREADS) {
-      const int c4 = e & 3, co = (e >> 2) % n_pad, r = (e >> 2) / n_pad;
-      const int q = r % nch, t = r / nch;
-      const int ci = q * 4 + c4;
-      float v = 0.f;
-      if (ci < Cin && co < Cout)
-        v = p.transposed ? __ldg(p.w + ((size_t)ci * Cout + co) * 9 + (8 - t)) : __ldg(p.w + ((size_t)co * Cin + ci) * 9 + t);
-      s_w[e] = v;
+    const int rows = 9 * nch * n_pad;
+    for (int r = tid; r < rows; r += TC_THREADS) {
+      const int co = r % n_pad, tq = r / n_pad;
+      const int q = tq % nch, t = tq / nch;
+      float v[4];
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int ci = q * 4 + c4;
+        v[c4] = 0.f;
+        if (ci < Cin && co < Cout)
+          v[c4] = p.transposed ? __ldg(p.w + ((size_t)ci * Cout + co) * 9 + (8 - t)) : __ldg(p.w + ((size_t)co * Cin + ci) * 9 + t);
+      }
+      *reinterpret_cast<float4*>(s_w + (size_t)r * 4) = make_float4(v[0], v[1], v[2], v[3]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -112,19 +241,24 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const cgs_conv3x
   const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w), bar = smem_u32(s_bar);
   const uint32_t w_plane = (uint32_t)n_pad * 16;     // bytes between consecutive 4-channel weight planes
   const int ngroups = g.cin_pad >> 3;
-  uint32_t phase = 0;
+  const int tpf = g.tiles_x * g.tiles_y;
 
-  // this thread's output pixel inside a tile: TMEM lane m = 32*warp + lane -> (yl, xl) = (m / 8, m % 8)
-  const int m = tid, yl = m >> 3, xl = m & 7;
-  const bool pool_owner = ((yl | xl) & 1) == 0;
+  // this thread's output pixel inside a tile: TMEM lane m = tid -> (yl, xl) = (m / 8, m % 8)
+  const int yl = tid >> 3, xl = tid & 7;
+  const bool odd_x = xl & 1, odd_y = yl & 1;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
 
-  for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
-    int t = tile;
-    const int tix = t % g.tiles_x; t /= g.tiles_x;
-    const int tiy = t % g.tiles_y; t /= g.tiles_y;
-    const int n = t, y0 = tiy * TC_TH, x0 = tix * TC_TW;
-
-    // ---- stage the haloed A tile, chunk-planar (two 16-byte slots per 8-channel group and pixel)
+  auto tile_origin = [&](int tile, int& n, int& y0, int& x0) {
+    n = tile / tpf;
+    const int r = tile - n * tpf;
+    const int tiy = r / g.tiles_x;
+    y0 = tiy * TC_TH;
+    x0 = (r - tiy * g.tiles_x) * TC_TW;
+  };
+  auto stage = [&](int tile, int buf) {
+    int n, y0, x0;
+    tile_origin(tile, n, y0, x0);
+    float* sa = s_a + (size_t)buf * a_floats;
     for (int it = tid; it < TC_SLOTS * ngroups; it += TC_THREADS) {
       const int grp = it / TC_SLOTS, slot = it - grp * TC_SLOTS;
       const int yy = slot / TC_HW, xx = slot - yy * TC_HW;
@@ -137,109 +271,65 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const cgs_conv3x
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
       }
-      float4* d = reinterpret_cast<float4*>(s_a + ((size_t)(2 * grp) * TC_SLOTS + slot) * 4);
+      float4* d = reinterpret_cast<float4*>(sa + ((size_t)(2 * grp) * TC_SLOTS + slot) * 4);
       d[0] = make_float4(v[0], v[1], v[2], v[3]);
       d[TC_SLOTS] = make_float4(v[4], v[5], v[6], v[7]);
     }
+  };
+  auto issue = [&](int buf) {   // one thread: 9 taps x (Cin/8) MMAs of 128 x n_pad x 8, then commit
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t ab = a_base + (uint32_t)buf * (uint32_t)a_floats * 4u;
+    const uint32_t td = tmem_base + (uint32_t)buf * (uint32_t)n_pad;
+    uint32_t acc = 0;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap - ky * 3;
+      const uint32_t a_tap = ab + (uint32_t)(ky * TC_HW + kx) * 16;
+      for (int kp = 0; kp < ngroups; ++kp) {
+        const uint64_t ad = umma_desc(a_tap + (uint32_t)(2 * kp) * TC_PLANE, TC_PLANE, TC_HW * 16);
+        const uint64_t bd = umma_desc(w_base + (uint32_t)(tap * nch + 2 * kp) * w_plane, w_plane, 128);
+        umma_tf32(td, ad, bd, g.idesc, acc);
+        acc = 1;
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+  };
+
+  int tile = blockIdx.x;
+  if (tile < g.ntiles) {
+    stage(tile, 0);
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the tensor core
     __syncthreads();
-
-    // ---- one thread issues the whole K loop: 9 taps x (Cin/8) MMAs of 128 x n_pad x 8
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      uint32_t acc = 0;
-      for (int tap = 0; tap < 9; ++tap) {
-        const int ky = tap / 3, kx = tap - ky * 3;
-        const uint32_t a_tap = a_base + (uint32_t)(ky * TC_HW + kx) * 16;
-        for (int kp = 0; kp < ngroups; ++kp) {
-          const uint64_t ad = umma_desc(a_tap + (uint32_t)(2 * kp) * TC_PLANE, TC_PLANE, TC_HW * 16);
-          const uint64_t bd = umma_desc(w_base + (uint32_t)(tap * nch + 2 * kp) * w_plane, w_plane, 128);
-          umma_tf32(tmem_base, ad, bd, g.idesc, acc);
-          acc = 1;
-        }
-      }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
-    }
+    if (tid == 0) issue(0);
+  }
+  uint32_t phase = 0;
+  int buf = 0;
+  for (; tile < g.ntiles; tile += gridDim.x, buf ^= 1) {
+    const int next = tile + gridDim.x;
+    const bool has_next = next < g.ntiles;
+    if (has_next) stage(next, buf ^ 1);                    // overlaps with MMA(tile)
     if (!mbar_wait(bar, phase)) {
       if (tid == 0 && status) atomicExch(status, 1);
       break;
     }
     phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-
-    // ---- epilogue: one output pixel per thread, 16 channels at a time out of TMEM
-    const int y = y0 + yl, x = x0 + xl;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int cb = 0; cb < Cout; cb += 16) {
-      float a[16];
-      tmem_ld16(t_lane + (uint32_t)cb, a);
-      const int cn = min(16, Cout - cb);
-      if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) a[j] += (j < cn) ? __ldg(p.bias + cb + j) : 0.f;
-      }
-      if (p.epi == CGS_EPI_RELU_POOL) {
-        const size_t o = (((size_t)n * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * Cout + cb;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float v0 = fmaxf(a[j], 0.f);
-          const float v1 = __shfl_xor_sync(0xffffffffu, v0, 1);
-          const float v2 = __shfl_xor_sync(0xffffffffu, v0, 8);
-          const float v3 = __shfl_xor_sync(0xffffffffu, v0, 9);
-          // first maximum in row-major window order wins (ATen max_pool2d)
-          float mx = v0; int am = 0;
-          if (v1 > mx) { mx = v1; am = 1; }
-          if (v2 > mx) { mx = v2; am = 2; }
-          if (v3 > mx) { mx = v3; am = 3; }
-          if (pool_owner && j < cn) {
-            p.out[o + j] = mx;
-            if (p.idx_out) p.idx_out[o + j] = (uint8_t)am;
-          }
-        }
-      } else if (p.epi == CGS_EPI_SPLIT_UP) {
-        const int C0 = p.C0, C1 = Cout - C0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int c = cb + j;
-          float s = a[j] + __shfl_xor_sync(0xffffffffu, a[j], 1);
-          s += __shfl_xor_sync(0xffffffffu, s, 8);
-          if (j >= cn) continue;
-          if (c < C0) {
-            if (p.out) p.out[(((size_t)n * H + y) * W + x) * C0 + c] = a[j];
-          } else if (p.out2 && pool_owner) {
-            p.out2[(((size_t)n * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * C1 + (c - C0)] = s;
-          }
-        }
-      } else {
-        const size_t o = (((size_t)n * H + y) * W + x) * Cout + cb;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float v = a[j];
-          if (p.epi == CGS_EPI_LEAKY) v = v > 0.f ? v : v * kLeakySlope;
-          else if (p.epi == CGS_EPI_SIGMOID) v = 1.f / (1.f + expf(-v));
-          else if (p.epi == CGS_EPI_MUL) v *= (j < cn) ? __ldg(p.mul + o + j) : 0.f;
-          a[j] = v;
-        }
-        if (cn == 16 && (Cout & 3) == 0) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(p.out + o + j) = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < cn) p.out[o + j] = a[j];
-        }
-        if (p.epi == CGS_EPI_SIGMOID && p.idx_out) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < cn) p.idx_out[o + j] = a[j] >= p.thresh ? 1 : 0;
-        }
-      }
-    }
-    // TMEM reads and smem operand reads of this tile are complete before the next tile overwrites them
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
+    __syncthreads();   // next tile staged by all; everyone is done reading TMEM[buf^1] (epilogue of tile-1)
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (has_next && tid == 0) issue(buf ^ 1);              // MMA(next) overlaps with the epilogue below
+
+    int n, y0, x0;
+    tile_origin(tile, n, y0, x0);
+    const int y = y0 + yl, x = x0 + xl;
+    const uint32_t taddr = t_lane + (uint32_t)buf * (uint32_t)n_pad;
+    if (Cout <= 8) {
+      tc_epilogue<8>(p, taddr, 0, n, y, x, odd_x, odd_y);
+    } else {
+      for (int cb = 0; cb < Cout; cb += 16) tc_epilogue<16>(p, taddr, cb, n, y, x, odd_x, odd_y);
+    }
   }
 
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(g.tmem_cols) : "memory");
@@ -255,14 +345,17 @@ static int* tc_status_word() {
   return d;
 }
 
+static size_t tc_smem_bytes(int cin_pad, int n_pad) {
+  return (size_t)9 * cin_pad * n_pad * 4 + (size_t)2 * cin_pad * TC_SLOTS * 4 + 64;
+}
+
 // Whether the tensor-core kernel covers this call; otherwise the caller uses the fp32 FFMA kernel.
 bool conv_tc_supported(const cgs_conv3x3_args& a) {
   if (a.H < TC_TH || a.W < TC_TW || (a.H % TC_TH) || (a.W % TC_TW)) return false;
   if (a.epi == CGS_EPI_SPLIT_UP && a.shift2 != 1) return false;
   const int cin_pad = (a.src.C + 7) & ~7, n_pad = (a.Cout + 15) & ~15;
-  if (n_pad > 256) return false;
-  const size_t smem = (size_t)9 * cin_pad * n_pad * 4 + (size_t)cin_pad * TC_SLOTS * 4 + 64;
-  return smem <= 200 * 1024;
+  if (2 * n_pad > 512) return false;
+  return tc_smem_bytes(cin_pad, n_pad) <= 200 * 1024;
 }
 
 int launch_conv_tc(const cgs_conv3x3_args& a, cudaStream_t st) {
@@ -274,10 +367,10 @@ int launch_conv_tc(const cgs_conv3x3_args& a, cudaStream_t st) {
   g.nch = g.cin_pad / 4;
   g.n_pad = (a.Cout + 15) & ~15;
   g.tmem_cols = 32;
-  while (g.tmem_cols < g.n_pad) g.tmem_cols *= 2;
+  while (g.tmem_cols < 2 * g.n_pad) g.tmem_cols *= 2;   // double-buffered accumulator
   // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), K-major both, N>>3 at 17, M>>4 at 24
   g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.n_pad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const size_t smem = (size_t)9 * g.cin_pad * g.n_pad * 4 + (size_t)g.cin_pad * TC_SLOTS * 4 + 64;
+  const size_t smem = tc_smem_bytes(g.cin_pad, g.n_pad);
   static bool attr_done = false;
   static int sms = 148;
   if (!attr_done) {
@@ -291,7 +384,7 @@ int launch_conv_tc(const cgs_conv3x3_args& a, cudaStream_t st) {
   per_sm = per_sm < 1 ? 1 : per_sm;
   const int tmem_limit = 512 / g.tmem_cols;
   if (per_sm > tmem_limit) per_sm = tmem_limit;
-  if (per_sm > 8) per_sm = 8;
+  if (per_sm > 6) per_sm = 6;
   int grid = sms * per_sm;
   if (grid > g.ntiles) grid = g.ntiles;
   conv3x3_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a, g, tc_status_word());

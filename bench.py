@@ -257,19 +257,35 @@ def run_ours(args, rank, world):
     sync()
     t_wall = time.perf_counter() - t_wall0
     dev_s = sum(s.elapsed_time(e) for s, e in evs) * 1e-3
-    # ---- e2e: pinned host buffers -> H2D -> step -> D2H loss read, every step
-    for _ in range(3):
-        out = step(*host)
-    sync()
-    t0 = time.perf_counter()
-    d2h = 0
-    for _ in range(K):
-        out = step(*host)
-        res = out if torch.is_tensor(out) else out[0]
-        val = res.reshape(-1)[:1].cpu() if args.workload != "infer" else out[2].cpu()   # loss scalar / hard masks
-        d2h = val.numel() * val.element_size()
-    sync()
-    e2e_s = time.perf_counter() - t0
+    # ---- e2e: pinned host buffers -> H2D -> step -> D2H of the step's result, every step, through the public API
+    if args.workload == "critic_train":
+        from cgs_b200.graph_step import PipelinedCriticTrainer
+        trainer = PipelinedCriticTrainer(H, B)            # double-buffered H2D, async loss read-back
+        for _ in range(4):
+            trainer.step(*host)
+        sync()
+        n0 = trainer.i
+        t0 = time.perf_counter()
+        for _ in range(K):
+            trainer.step(*host)
+        losses = trainer.losses()                          # synchronises: all K losses are on the host
+        sync()
+        e2e_s = time.perf_counter() - t0
+        assert trainer.i - n0 == K and torch.isfinite(losses).all()
+        d2h = 4
+    else:
+        for _ in range(3):
+            out = step(*host)
+        sync()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(K):
+            out = step(*host)
+            res = out if torch.is_tensor(out) else out[0]
+            val = res.reshape(-1)[:1].cpu() if args.workload != "infer" else out[2].cpu()   # loss scalar / hard masks
+            d2h = val.numel() * val.element_size()
+        sync()
+        e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:

@@ -47,6 +47,7 @@ EXPORTS = {
     "cgs_adam_step": [_f32p] * 4 + [C.c_int64] + [C.c_double] * 4 + [C.c_void_p, C.c_float, C.c_void_p],
     "cgs_threshold": [_f32p, C.c_int64, C.c_float, C.c_int32, _u8p, C.c_void_p],
     "cgs_tc_status": [],
+    "cgs_tc_set_trace": [C.c_void_p],
 }
 
 _lib = None

@@ -196,6 +196,11 @@ __device__ __forceinline__ void tc_epilogue(const cgs_conv3x3_args& p, uint32_t 
   }
 }
 
+// Optional phase trace (tools/tc_trace.py): CTA 0 / thread 0 records clock64() at the phase boundaries of
+// its first 16 tiles.  NULL in production.
+__device__ long long* g_tc_trace = nullptr;
+#define TC_MARK(k) do { if (trace && tile_no < 16) trace[tile_no * 8 + (k)] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const cgs_conv3x3_args p, const TcGeom g, int* __restrict__ status) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -294,6 +299,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const cgs_conv3x
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
   };
 
+  long long* trace = (blockIdx.x == 0 && threadIdx.x == 0) ? g_tc_trace : nullptr;
+  int tile_no = 0;
   int tile = blockIdx.x;
   if (tile < g.ntiles) {
     stage(tile, 0);
@@ -303,20 +310,25 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const cgs_conv3x
   }
   uint32_t phase = 0;
   int buf = 0;
-  for (; tile < g.ntiles; tile += gridDim.x, buf ^= 1) {
+  for (; tile < g.ntiles; tile += gridDim.x, buf ^= 1, ++tile_no) {
     const int next = tile + gridDim.x;
     const bool has_next = next < g.ntiles;
+    TC_MARK(0);
     if (has_next) stage(next, buf ^ 1);                    // overlaps with MMA(tile)
+    TC_MARK(1);
     if (!mbar_wait(bar, phase)) {
       if (tid == 0 && status) atomicExch(status, 1);
       break;
     }
     phase ^= 1;
+    TC_MARK(2);
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();   // next tile staged by all; everyone is done reading TMEM[buf^1] (epilogue of tile-1)
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    TC_MARK(3);
     if (has_next && tid == 0) issue(buf ^ 1);              // MMA(next) overlaps with the epilogue below
+    TC_MARK(4);
 
     int n, y0, x0;
     tile_origin(tile, n, y0, x0);
@@ -327,6 +339,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const cgs_conv3x
     } else {
       for (int cb = 0; cb < Cout; cb += 16) tc_epilogue<16>(p, taddr, cb, n, y, x, odd_x, odd_y);
     }
+    TC_MARK(5);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -353,6 +366,9 @@ static size_t tc_smem_bytes(int cin_pad, int n_pad) {
 bool conv_tc_supported(const cgs_conv3x3_args& a) {
   if (a.H < TC_TH || a.W < TC_TW || (a.H % TC_TH) || (a.W % TC_TW)) return false;
   if (a.epi == CGS_EPI_SPLIT_UP && a.shift2 != 1) return false;
+  // Cin <= 4 (the RGB input layer): K = 27 would be padded to 72 and the implicit GEMM re-reads the tile 9x through
+  // the tensor core's operand path; the register-blocked FFMA kernel is faster there (profiles/README.md).
+  if (a.src.C <= 4) return false;
   const int cin_pad = (a.src.C + 7) & ~7, n_pad = (a.Cout + 15) & ~15;
   if (2 * n_pad > 512) return false;
   return tc_smem_bytes(cin_pad, n_pad) <= 200 * 1024;
@@ -401,3 +417,8 @@ int conv_tc_status() {
 }  // namespace cgs
 
 extern "C" int cgs_tc_status(void) { return cgs::conv_tc_status(); }
+
+// Debug: point the phase trace at a device buffer of 16*8 int64 (NULL disables).  Not part of the product API.
+extern "C" int cgs_tc_set_trace(long long* dev_buf) {
+  return cudaMemcpyToSymbol(cgs::g_tc_trace, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? 0 : -2;
+}

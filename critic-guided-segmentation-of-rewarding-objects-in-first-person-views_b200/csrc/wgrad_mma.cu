@@ -16,7 +16,8 @@
 namespace cgs {
 
 
-constexpr int WM_CI = 8, WM_CO = 8, WM_MT = 5;   // 5 m16 tiles = 80 rows >= 72 (ci,tap) rows + 1 bias row
+constexpr int WM_CI = 8, WM_CO = 8;   // channel block; M tiles: 5 x m16 = 80 rows >= 72 (ci,tap) rows + 1 bias row,
+                                      // or 2 x m16 = 32 rows >= 27 + 1 when Cin <= 3 (the RGB input layer)
 
 __device__ __forceinline__ uint32_t f2tf32(float f) {
   uint32_t r;
@@ -31,6 +32,9 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ float tf32r(float f) { return __uint_as_float(f2tf32(f)); }
+
+template <int WM_MT>
 __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_args p, const WgGeom g) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
@@ -49,7 +53,7 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
   // ---- stage X (haloed) and dY tiles, planar [channel][row][x]
   {
     const int npix = g.fpc * sh * sw;
-#pragma unroll 2
+#pragma unroll 4
     for (int pix = tid; pix < npix; pix += 256) {
       const int row = fdiv(pix, g.dsw), xx = pix - row * sw;
       const int ff = fdiv(row, g.dsh), yy = row - ff * sh;
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
       float* d = s_x + row * g.rsx + xx;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (i < cin) d[i * g.psx] = v[i];
+        if (i < cin) d[i * g.psx] = tf32r(v[i]);      // round once here, not 9x in the MMA loop
     }
     const int npy = g.fpc * th * tw;
 #pragma unroll 2
@@ -81,7 +85,7 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
       }
       float* d = s_y + row * g.rsy + xx;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i * g.psy] = (i < con) ? v[i] : 0.f;
+      for (int i = 0; i < 8; ++i) d[i * g.psy] = (i < con) ? tf32r(v[i]) : 0.f;
     }
   }
   __syncthreads();
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
       if (mrow < 9 * cin) {
         const int ci = mrow / 9, tap = mrow - ci * 9;
         off = ci * g.psx + (tap / 3) * g.rsx + (tap % 3);
-      } else if (mrow == 9 * WM_CI) {
+      } else if (mrow == 9 * cin) {
         off = -2;
       }
       offA[mt][h] = off;
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
     const float* xrow = s_x + (ff * sh + yy) * g.rsx + tig;
     const float* yrow = s_y + gid * g.psy + r * g.rsy + tig;
     for (int xb = 0; xb < tw; xb += 8) {
-      const uint32_t b0 = f2tf32(yrow[xb]), b1 = f2tf32(yrow[xb + 4]);
+      const uint32_t b0 = __float_as_uint(yrow[xb]), b1 = __float_as_uint(yrow[xb + 4]);
 #pragma unroll
       for (int mt = 0; mt < WM_MT; ++mt) {
         uint32_t a[4];
@@ -125,8 +129,8 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
           float v0 = 0.f, v1 = 0.f;
           if (off >= 0) { v0 = xrow[off + xb]; v1 = xrow[off + xb + 4]; }
           else if (off == -2) { v0 = 1.f; v1 = 1.f; }
-          a[h] = f2tf32(v0);
-          a[2 + h] = f2tf32(v1);
+          a[h] = __float_as_uint(v0);
+          a[2 + h] = __float_as_uint(v1);
         }
         mma_tf32(acc[mt], a[0], a[1], a[2], a[3], b0, b1);
       }
@@ -151,7 +155,7 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
     if (n >= con) continue;
     if (mrow < 9 * cin) {
       atomicAdd(p.dw + ((size_t)(co0 + n) * Cin + ci0) * 9 + mrow, s);
-    } else if (mrow == 9 * WM_CI && p.db && blockIdx.z == 0) {
+    } else if (mrow == 9 * cin && p.db && blockIdx.z == 0) {
       atomicAdd(p.db + co0 + n, s);
     }
   }
@@ -173,16 +177,18 @@ int launch_wgrad_mma(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   g.dsw = make_fastdiv(g.tw + 2); g.dsh = make_fastdiv(g.th + 2);
   g.dtw = make_fastdiv(g.tw);     g.dth = make_fastdiv(g.th);
   size_t smem = ((size_t)WM_CI * g.psx + (size_t)WM_CO * g.psy) * sizeof(float);
-  const size_t red = (size_t)8 * 16 * WM_MT * 8 * sizeof(float);
+  const size_t red = (size_t)8 * 16 * 5 * 8 * sizeof(float);
   if (smem < red) smem = red;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(wgrad3x3_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(wgrad3x3_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(wgrad3x3_mma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
   const int nblk = ((a.B + g.fpc - 1) / g.fpc) * g.tiles_x * g.tiles_y;
   dim3 grid(nblk, (a.dy.C + WM_CO - 1) / WM_CO, (a.x.C + WM_CI - 1) / WM_CI);
-  wgrad3x3_mma_kernel<<<grid, 256, smem, st>>>(a, g);
+  if (a.x.C <= 3) wgrad3x3_mma_kernel<2><<<grid, 256, smem, st>>>(a, g);
+  else wgrad3x3_mma_kernel<5><<<grid, 256, smem, st>>>(a, g);
   return check_launch("wgrad3x3_mma");
 }
 

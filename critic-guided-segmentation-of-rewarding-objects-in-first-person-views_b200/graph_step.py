@@ -114,3 +114,45 @@ class GraphedSegment(_Graphed):
                 mask, hard = H.masker.forward_hard(x, embeds, threshold)
             return pred, mask, hard
         self.graph, self.out, self.launches = _capture(fn)
+
+
+class PipelinedCriticTrainer:
+    """End-to-end critic training from HOST batches: pinned uint8 frames + labels in, loss values out.
+
+    Two captured step graphs with their own static input buffers share one model and one FlatAdam; the H2D
+    copy of batch i+1 runs on a copy stream while graph i replays, and every step's loss is read back with an
+    asynchronous D2H copy into a pinned ring (the reference syncs 1-4 times per step with `.item()`,
+    main.py:196-200).  `step()` never blocks the host; `losses()` synchronises and returns the ring."""
+
+    def __init__(self, handler, batch, depth=2, ring=4096):
+        self.opti = FlatAdam(handler.critic.to(handler.device).parameters(), process_group=handler.group,
+                             world_size=handler.world)
+        self.slots = [GraphedCriticStep(handler, batch, self.opti) for _ in range(depth)]
+        self.launches = self.slots[0].launches
+        self.copy_stream = torch.cuda.Stream()
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.loss_ring = torch.zeros(ring, dtype=torch.float32).pin_memory()
+        self.i = 0
+
+    def step(self, X_host, Y_host, roll=None):
+        k = self.i % len(self.slots)
+        st = self.slots[k]
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.done[k])          # the graph that last read this slot has finished
+            st.X.copy_(X_host, non_blocking=True)
+            st.Y.copy_(Y_host, non_blocking=True)
+            if roll is not None:
+                st.roll.fill_(int(roll))
+            self.ready[k].record(self.copy_stream)
+        main = torch.cuda.current_stream()
+        main.wait_event(self.ready[k])
+        st.graph.replay()
+        self.done[k].record(main)
+        self.loss_ring[self.i % self.loss_ring.numel()].copy_(st.out, non_blocking=True)
+        self.i += 1
+
+    def losses(self):
+        torch.cuda.synchronize()
+        n = min(self.i, self.loss_ring.numel())
+        return self.loss_ring[:n].clone()

@@ -160,6 +160,9 @@ int cgs_threshold(const float* z, int64_t n, float thresh, int32_t strict, uint8
 /* Non-zero if a tcgen05 kernel ever timed out on its completion barrier (reads a device flag; synchronises). */
 int cgs_tc_status(void);
 
+/* Debug only: clock64() phase trace of CTA 0 of the tcgen05 conv kernel into dev_buf[16*8] (NULL disables). */
+int cgs_tc_set_trace(long long* dev_buf);
+
 const char* cgs_last_error(void);
 int cgs_version(void);
 

@@ -37,6 +37,9 @@ EXPORTS = {
     "cgs_wgrad3x3": [C.POINTER(Wgrad3x3Args), C.c_void_p],
     "cgs_head_fwd": [_f32p] * 9 + [C.c_int32] * 3 + [_f32p] * 3 + [C.c_void_p],
     "cgs_head_bwd": [_f32p] * 11 + [C.c_int32] * 3 + [_f32p] * 7 + [C.c_void_p],
+    "cgs_tail_supported": [C.c_int32] * 4,
+    "cgs_tail_fwd": [_f32p] * 12 + [C.c_int32] * 4 + [_f32p, _u8p, _f32p, _f32p, _f32p, C.c_void_p],
+    "cgs_tail_bwd": [_f32p] * 9 + [_u8p] + [_f32p] * 6 + [C.c_int32] * 4 + [_f32p] * 9 + [C.c_void_p],
     "cgs_dense_fwd": [_f32p] * 3 + [C.c_int32] * 3 + [_f32p, C.c_void_p],
     "cgs_dense_bwd": [_f32p] * 3 + [C.c_int32] * 3 + [_f32p] * 3 + [C.c_void_p],
     "cgs_occlude_fwd": [_f32p] * 3 + [C.c_int64, C.c_int32, _f32p, C.c_void_p],
@@ -46,6 +49,7 @@ EXPORTS = {
     "cgs_frames_to_float": [_u8p] + [C.c_int32] * 5 + [C.c_void_p, _f32p, C.c_void_p],
     "cgs_adam_step": [_f32p] * 4 + [C.c_int64] + [C.c_double] * 4 + [C.c_void_p, C.c_float, C.c_void_p],
     "cgs_threshold": [_f32p, C.c_int64, C.c_float, C.c_int32, _u8p, C.c_void_p],
+    "cgs_dropout_masks": [_f32p, C.c_int64, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p],
     "cgs_tc_status": [],
     "cgs_tc_set_trace": [C.c_void_p],
 }

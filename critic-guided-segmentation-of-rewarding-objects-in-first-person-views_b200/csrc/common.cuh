@@ -69,6 +69,7 @@ struct WgGeom {
   int th, tw, fpc, tiles_y, tiles_x;
   int rsx, psx, rsy, psy;
   FastDiv dsw, dsh, dtw, dth;
+  FastDiv dwp, dhp;   // dividers by tw/2, th/2 (pooled-granularity staging)
 };
 
 // Up to 8 consecutive floats (channels) of one pixel -> registers; two 128-bit loads when aligned.

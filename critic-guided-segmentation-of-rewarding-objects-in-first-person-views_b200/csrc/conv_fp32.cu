@@ -35,7 +35,7 @@ __device__ __forceinline__ void load_w(const float* wp, float (&w)[CO_T]) {
 }
 
 template <int CO_T>
-__global__ void __launch_bounds__(256) conv3x3_kernel(const cgs_conv3x3_args p, const ConvGeom g) {
+__global__ void __launch_bounds__(256, (CO_T <= 8 ? 3 : 2)) conv3x3_kernel(const cgs_conv3x3_args p, const ConvGeom g) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int H = p.H, W = p.W, Cin = p.src.C, Cout = p.Cout;
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const cgs_conv3x3_args p, 
     __syncthreads();
     // ---- stage the haloed input chunk: one pixel (<= 8 channels, 128-bit loads) per thread iteration
     const int npix = g.fpc * sh * sw;
-#pragma unroll 4
+#pragma unroll 1
     for (int pix = tid; pix < npix; pix += nthr) {
       const int row = fdiv(pix, g.dsw), xx = pix - row * sw;
       const int ff = fdiv(row, g.dsh), yy = row - ff * sh;
@@ -449,6 +449,7 @@ static int launch_wgrad(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   g.psy = g.fpc * g.th * g.rsy;       g.psy += (40 - (g.psy % 32)) % 32;
   g.dsw = make_fastdiv(g.tw + 2); g.dsh = make_fastdiv(g.th + 2);
   g.dtw = make_fastdiv(g.tw);     g.dth = make_fastdiv(g.th);
+  g.dwp = make_fastdiv(g.tw > 2 ? g.tw / 2 : 2); g.dhp = make_fastdiv(g.th > 2 ? g.th / 2 : 2);
   size_t smem = ((size_t)CI_B * g.psx + (size_t)CO_B * g.psy) * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {

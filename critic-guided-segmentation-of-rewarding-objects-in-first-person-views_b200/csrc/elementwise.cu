@@ -157,6 +157,51 @@ __global__ void threshold_kernel(const float* __restrict__ z, int64_t n, float t
   }
 }
 
+// ---------------------------------------------------------------- dropout masks
+// All Dropout masks of one NewCritic forward (nets.py:179,183,192) in ONE launch: Philox4x32-10 keyed by
+// (seed, call counter), 4 Bernoulli draws per counter value; value = keep ? 1/(1-p) : 0.  The call counter lives in
+// device memory and is advanced by the last CTA to finish (ticket), so a captured CUDA graph draws fresh masks on
+// every replay without any host involvement.
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+__global__ void dropout_masks_kernel(float* __restrict__ out, int64_t n, float p, unsigned long long seed,
+                                     unsigned long long* __restrict__ state) {
+  const unsigned long long call = state[0];
+  const float keep = 1.f / (1.f - p);
+  const int64_t nvec = (n + 3) >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t c[4] = {(uint32_t)i, (uint32_t)(i >> 32), (uint32_t)call, (uint32_t)(call >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = ((float)(c[k] >> 8) * (1.0f / 16777216.0f) >= p) ? keep : 0.f;
+    if (4 * i + 3 < n) {
+      *reinterpret_cast<float4*>(out + 4 * i) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      for (int k = 0; k < 4 && 4 * i + k < n; ++k) out[4 * i + k] = v[k];
+    }
+  }
+  // last CTA to finish advances the call counter: every CTA has read state[0] by then
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(&state[1], 1ull);
+    if (t == gridDim.x - 1) {
+      state[1] = 0;
+      state[0] = call + 1;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- Adam
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             int64_t n, double lr, double beta1, double beta2, double eps_d,
@@ -239,6 +284,14 @@ extern "C" int cgs_adam_step(float* p, const float* g, float* m, float* v, int64
   CGS_REQUIRE(p && g && m && v && step_count && n > 0, "adam_step: bad args");
   adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_count, grad_scale);
   return check_launch("adam_step");
+}
+
+extern "C" int cgs_dropout_masks(float* out, int64_t n, float p, uint64_t seed, uint64_t* state, void* stream) {
+  CGS_REQUIRE(out && state && n > 0 && p >= 0.f && p < 1.f, "dropout_masks: bad args");
+  CGS_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "dropout_masks: out must be 16-byte aligned");
+  dropout_masks_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, p, (unsigned long long)seed,
+                                                                                    (unsigned long long*)state);
+  return check_launch("dropout_masks");
 }
 
 extern "C" const char* cgs_last_error(void) { return g_err; }

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
   // ---- stage X (haloed) and dY tiles, planar [channel][row][x]
   {
     const int npix = g.fpc * sh * sw;
-#pragma unroll 4
+#pragma unroll 2
     for (int pix = tid; pix < npix; pix += 256) {
       const int row = fdiv(pix, g.dsw), xx = pix - row * sw;
       const int ff = fdiv(row, g.dsh), yy = row - ff * sh;
@@ -70,6 +70,40 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
       for (int i = 0; i < 8; ++i)
         if (i < cin) d[i * g.psx] = tf32r(v[i]);      // round once here, not 9x in the MMA loop
     }
+    if (p.dy.mode == CGS_SRC_POOLBWD && (p.dy.C & 7) == 0) {
+      // ReLU + max-pool backward at POOLED granularity: one (dE, E, argmax) load per pooled element, scattered to the
+      // arg-max position of its 2x2 window (the other three get zero) -- 4x fewer loads than per output pixel.
+      const int hp = th >> 1, wp = tw >> 1, H2 = H >> 1, W2 = W >> 1;
+      const int npool = g.fpc * hp * wp;
+#pragma unroll 2
+      for (int pp = tid; pp < npool; pp += 256) {
+        const int r2 = fdiv(pp, g.dwp), xx2 = pp - r2 * wp;
+        const int ff = fdiv(r2, g.dhp), yy2 = r2 - ff * hp;
+        const int nn = n0 + ff;
+        float de[8], e[8];
+        unsigned long long ib = 0;
+        if (nn < p.B) {
+          const size_t o = (size_t)(unsigned)((nn * H2 + (y0 >> 1) + yy2) * W2 + (x0 >> 1) + xx2) * (unsigned)p.dy.C + co0;
+          load8(p.dy.a + o, 8, true, de);
+          load8(p.dy.b + o, 8, true, e);
+          ib = __ldg(reinterpret_cast<const unsigned long long*>(p.dy.idx + o));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { de[i] = 0.f; e[i] = 0.f; }
+        }
+        float* d = s_y + (ff * th + 2 * yy2) * g.rsy + 2 * xx2;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int pos = (int)((ib >> (8 * i)) & 0xff);
+          const float v = (e[i] > 0.f) ? tf32r(de[i]) : 0.f;
+          float* q = d + i * g.psy;
+          q[0] = pos == 0 ? v : 0.f;
+          q[1] = pos == 1 ? v : 0.f;
+          q[g.rsy] = pos == 2 ? v : 0.f;
+          q[g.rsy + 1] = pos == 3 ? v : 0.f;
+        }
+      }
+    } else {
     const int npy = g.fpc * th * tw;
 #pragma unroll 2
     for (int pix = tid; pix < npy; pix += 256) {
@@ -86,6 +120,7 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
       float* d = s_y + row * g.rsy + xx;
 #pragma unroll
       for (int i = 0; i < 8; ++i) d[i * g.psy] = (i < con) ? tf32r(v[i]) : 0.f;
+    }
     }
   }
   __syncthreads();
@@ -176,6 +211,7 @@ int launch_wgrad_mma(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   g.psy = g.fpc * g.th * g.rsy;       g.psy += (40 - (g.psy % 32)) % 32;
   g.dsw = make_fastdiv(g.tw + 2); g.dsh = make_fastdiv(g.th + 2);
   g.dtw = make_fastdiv(g.tw);     g.dth = make_fastdiv(g.th);
+  g.dwp = make_fastdiv(g.tw / 2); g.dhp = make_fastdiv(g.th / 2);
   size_t smem = ((size_t)WM_CI * g.psx + (size_t)WM_CO * g.psy) * sizeof(float);
   const size_t red = (size_t)8 * 16 * 5 * 8 * sizeof(float);
   if (smem < red) smem = red;

@@ -64,7 +64,12 @@ class NewCritic(nn.Module):
         self.crit = nn.Sequential(nn.Flatten(), nn.Linear(nb, nb), activation(), nn.Dropout(dropout),
                                   nn.Linear(nb, 1), nn.Sigmoid())
         self._conv_idx = (0, 3, 6, 10)
+        self.fuse_tail = True          # features[9..15] + crit in one kernel each way when the shapes fit shared memory
         self.fuse_frame_cast = False   # True: read uint8 frames directly in the first conv (saves the fp32 copy; slower loads)
+        self._rng_state = None
+        self._rng_seed = 0
+        NewCritic._count = getattr(NewCritic, "_count", 0) + 1
+        self._instance = NewCritic._count          # distinct, construction-order-deterministic Philox key per module
         self._forced_masks = None   # test hook: (m_e2 [B,8,8,8c], m_e3 [B,4,4,16c], m_v [B,32c]) NHWC
 
     def _dropout_masks(self, B, device):
@@ -77,8 +82,14 @@ class NewCritic(nn.Module):
         c2 = self.features[6].out_channels
         c3 = self.features[10].out_channels
         nb = self.crit[1].out_features
-        mk = lambda *s: F.dropout(torch.ones(s, device=device, dtype=torch.float32), self.p, True)
-        return mk(B, 8, 8, c2), mk(B, 4, 4, c3), mk(B, nb)
+        if self.p >= 1.0:
+            z = lambda *s: torch.zeros(s, device=device, dtype=torch.float32)
+            return z(B, 8, 8, c2), z(B, 4, 4, c3), z(B, nb)
+        if self._rng_state is None or self._rng_state.device != device:
+            # Philox stream keyed by torch's seed (torch.manual_seed reproducible), advanced on the device
+            self._rng_state = torch.zeros(2, dtype=torch.int64, device=device)
+            self._rng_seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._instance) & 0x7FFFFFFFFFFFFFFF
+        return tuple(ops.dropout_masks([(B, 8, 8, c2), (B, 4, 4, c3), (B, nb)], self.p, self._rng_seed, self._rng_state))
 
     def forward(self, X, collect=False):
         return self._run(_nhwc(X, self.colorchs, self.width, "NewCritic"), None, collect)
@@ -102,9 +113,13 @@ class NewCritic(nn.Module):
         e0 = ops.EncBlock.apply(x, None, f[0].weight, f[0].bias, roll)
         e1 = ops.EncBlock.apply(e0, None, f[3].weight, f[3].bias)
         e2 = ops.EncBlock.apply(e1, None, f[6].weight, f[6].bias)
-        e3 = ops.EncBlock.apply(e2, m_e2, f[10].weight, f[10].bias)
-        pred, e4 = ops.Head.apply(e3, m_e3, m_v, f[14].weight, f[14].bias, self.crit[1].weight, self.crit[1].bias,
-                                  self.crit[4].weight, self.crit[4].bias)
+        if self.fuse_tail and ops.tail_supported(x.shape[0], e2.shape[3], f[10].out_channels, f[14].out_channels):
+            pred, e3, e4 = ops.Tail.apply(e2, m_e2, m_e3, m_v, f[10].weight, f[10].bias, f[14].weight, f[14].bias,
+                                          self.crit[1].weight, self.crit[1].bias, self.crit[4].weight, self.crit[4].bias)
+        else:
+            e3 = ops.EncBlock.apply(e2, m_e2, f[10].weight, f[10].bias)
+            pred, e4 = ops.Head.apply(e3, m_e3, m_v, f[14].weight, f[14].bias, self.crit[1].weight, self.crit[1].bias,
+                                      self.crit[4].weight, self.crit[4].bias)
         if collect:
             return pred, [_nchw(e0), _nchw(e1), _nchw(e2), _nchw(e3), _nchw(e4)]
         return pred

@@ -169,6 +169,50 @@ class Head(torch.autograd.Function):
         return (de3, None, None) + tuple(rets)
 
 
+def tail_supported(B, C2, C3, NB):
+    return bool(_lib.lib().cgs_tail_supported(B, C2, C3, NB))
+
+
+class Tail(torch.autograd.Function):
+    """features[9..15] + crit of NewCritic (reference nets.py:179-195) fused: [Dropout] Conv3x3 ReLU MaxPool (-> embeds[3])
+    [Dropout] Conv4x4 ReLU (-> embeds[4]) Flatten Linear ReLU [Dropout] Linear Sigmoid.  Returns (pred, e3, e4)."""
+
+    @staticmethod
+    def forward(ctx, e2, m_e2, m_e3, m_v, w3, b3, w14, b14, w1, b1, w2, b2):
+        B, _, _, C2 = e2.shape
+        C3, NB = w3.shape[0], w14.shape[0]
+        dev = e2.device
+        e3 = torch.empty((B, 4, 4, C3), device=dev, dtype=torch.float32)
+        idx3 = torch.empty((B, 4, 4, C3), device=dev, dtype=torch.uint8)
+        e4 = torch.empty((B, 1, 1, NB), device=dev, dtype=torch.float32)
+        v = torch.empty((B, NB), device=dev, dtype=torch.float32)
+        pred = torch.empty((B, 1), device=dev, dtype=torch.float32)
+        _call("cgs_tail_fwd", _p(e2), _p(m_e2), _p(m_e3), _p(m_v), _p(w3), _p(b3), _p(w14), _p(b14), _p(w1), _p(b1),
+              _p(w2), _p(b2), B, C2, C3, NB, _p(e3), _p(idx3, torch.uint8), _p(e4), _p(v), _p(pred), _stream())
+        ctx.save_for_backward(e2, m_e2, m_e3, m_v, w3, w14, w1, w2, e3, idx3, e4, v, pred)
+        ctx.params = (w3, b3, w14, b14, w1, b1, w2, b2)
+        ctx.set_materialize_grads(False)
+        return pred, e3, e4
+
+    @staticmethod
+    def backward(ctx, dpred, de3, de4):
+        e2, m_e2, m_e3, m_v, w3, w14, w1, w2, e3, idx3, e4, v, pred = ctx.saved_tensors
+        if dpred is None and de3 is None and de4 is None:
+            return (None,) * 12
+        B, _, _, C2 = e2.shape
+        C3, NB = w3.shape[0], w14.shape[0]
+        dpred = None if dpred is None else _c(dpred)
+        de3 = None if de3 is None else _c(de3)
+        de4 = None if de4 is None else _c(de4)
+        want_w = any(ctx.needs_input_grad[4:])
+        bufs, rets = zip(*[_gbuf(prm, want_w) for prm in ctx.params])
+        de2 = torch.empty_like(e2) if ctx.needs_input_grad[0] else None
+        _call("cgs_tail_bwd", _p(e2), _p(m_e2), _p(m_e3), _p(m_v), _p(w3), _p(w14), _p(w1), _p(w2), _p(e3),
+              _p(idx3, torch.uint8), _p(e4), _p(v), _p(pred), _p(dpred), _p(de3), _p(de4), B, C2, C3, NB,
+              *[_p(t) for t in bufs], _p(de2), _stream())
+        return (de2, None, None, None) + tuple(rets)
+
+
 class DecBlock(torch.autograd.Function):
     """cat(skip, nearest_up(up, 2**shift)) -> Conv2d(3,1,1) [-> LeakyReLU(0.01)]: one UnetDecoder
     stage (reference nets.py:503-521).  skip [B,H,W,C0], up [B,H>>shift,W>>shift,C1]."""
@@ -358,6 +402,19 @@ def frames_to_float(frames_u8, roll=0, roll_dev=None):
     out = torch.empty((B, H, W, Cc), device=x.device, dtype=torch.float32)
     _call("cgs_frames_to_float", _p(x, torch.uint8), B, H, W, Cc, int(roll), _p(roll_dev, torch.int32), _p(out), _stream())
     return out
+
+
+def dropout_masks(shapes, p, seed, state):
+    """Multiplicative dropout masks (0 or 1/(1-p)) for all `shapes` from ONE kernel launch; returns views of one buffer.
+    `state`: int64 device tensor [2] (call counter, ticket) owned by the module."""
+    sizes = [int(torch.Size(s).numel()) for s in shapes]
+    offs, tot = [], 0
+    for n in sizes:
+        offs.append(tot)
+        tot += (n + 3) & ~3          # keep every view 16-byte aligned
+    buf = torch.empty(tot, device=state.device, dtype=torch.float32)
+    _call("cgs_dropout_masks", _p(buf), tot, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(state, torch.int64), _stream())
+    return [buf[o:o + n].view(s) for o, n, s in zip(offs, sizes, shapes)]
 
 
 def threshold(z, thresh, strict=False):

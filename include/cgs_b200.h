@@ -116,6 +116,26 @@ int cgs_head_bwd(const float* e3, const float* m_e3, const float* m_v,
                  float* dw14, float* db14, float* dw1, float* db1, float* dw2, float* db2,
                  float* de3, void* stream);
 
+/* Fused tail of NewCritic: features[9..15] + crit (nets.py:179-195) in one kernel: [Dropout] Conv2d(8c,16c,3,1,1)
+ * ReLU MaxPool2d(2) (-> embeds[3], argmax) + everything cgs_head_fwd does.  e2 [B,8,8,C2] NHWC; m_e2 / m_e3 / m_v
+ * optional dropout masks.  cgs_tail_supported() tells whether the shapes fit the kernel's shared-memory budget
+ * (returns 1/0); otherwise use cgs_conv3x3 + cgs_head_fwd. */
+int cgs_tail_supported(int32_t B, int32_t C2, int32_t C3, int32_t NB);
+int cgs_tail_fwd(const float* e2, const float* m_e2, const float* m_e3, const float* m_v,
+                 const float* w3, const float* b3, const float* w14, const float* b14,
+                 const float* w1, const float* b1, const float* w2, const float* b2,
+                 int32_t B, int32_t C2, int32_t C3, int32_t NB,
+                 float* e3, uint8_t* idx3, float* e4, float* v, float* pred, void* stream);
+/* Backward of cgs_tail_fwd.  Incoming gradients dpred [B], de3_ext [B,4,4,C3] (from the decoder skip), de4 [B,NB] are
+ * each optional (not all NULL).  Parameter gradients accumulated (all-or-none, dw14 == NULL skips); de2 written or NULL. */
+int cgs_tail_bwd(const float* e2, const float* m_e2, const float* m_e3, const float* m_v,
+                 const float* w3, const float* w14, const float* w1, const float* w2,
+                 const float* e3, const uint8_t* idx3, const float* e4, const float* v, const float* pred,
+                 const float* dpred, const float* de3_ext, const float* de4,
+                 int32_t B, int32_t C2, int32_t C3, int32_t NB,
+                 float* dw3, float* db3, float* dw14, float* db14, float* dw1, float* db1, float* dw2, float* db2,
+                 float* de2, void* stream);
+
 /* Dense layer out[B,N] = in[B,K] * w[N,K]^T + bias: UnetDecoder.dec[4], the 1x1 conv on the
  * 1x1 bottleneck (nets.py:484,500-501). */
 int cgs_dense_fwd(const float* in, const float* w, const float* bias,
@@ -153,6 +173,11 @@ int cgs_frames_to_float(const uint8_t* in, int32_t B, int32_t H, int32_t W, int3
 int cgs_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
                   double lr, double beta1, double beta2, double eps, const int32_t* step_count,
                   float grad_scale, void* stream);
+
+/* All nn.Dropout masks of one NewCritic forward (nets.py:179,183,192) in one launch: out[i] = Bernoulli(1-p)/(1-p),
+ * Philox4x32-10 keyed by (seed, state[0]); state = {call counter, ticket} in device memory, advanced by the kernel
+ * itself so that CUDA-graph replays draw fresh masks.  out must be 16-byte aligned. */
+int cgs_dropout_masks(float* out, int64_t n, float p, uint64_t seed, uint64_t* state, void* stream);
 
 /* hard[i] = z[i] >= thresh (main.py:1164) or z[i] > thresh when strict (main.py:964). */
 int cgs_threshold(const float* z, int64_t n, float thresh, int32_t strict, uint8_t* hard, void* stream);

@@ -177,6 +177,50 @@ def test_head_fwd_bwd(ops, B, C3, NB, use_masks, use_de4):
         close(a.grad, r.grad, n)
 
 
+@pytest.mark.parametrize("B,C2,C3,NB,use_masks,extra", [(5, 8, 16, 32, True, True), (37, 8, 16, 32, False, False),
+                                                         (3, 16, 32, 64, True, True), (2, 24, 48, 96, True, False)])
+def test_fused_tail_fwd_bwd(ops, B, C2, C3, NB, use_masks, extra):
+    """features[9..15] + crit in one kernel each way vs the same chain in torch (fp32)."""
+    assert ops.tail_supported(B, C2, C3, NB)
+    e2 = rnd(B, C2, 8, 8, seed=1).abs()
+    w3 = rnd(C3, C2, 3, 3, seed=2, scale=(3.0 / (C2 * 9)) ** 0.5)
+    b3 = rnd(C3, seed=3, scale=0.1)
+    w14 = rnd(NB, C3, 4, 4, seed=4, scale=(3.0 / (C3 * 16)) ** 0.5)
+    b14 = rnd(NB, seed=5, scale=0.1)
+    w1 = rnd(NB, NB, seed=6, scale=(3.0 / NB) ** 0.5)
+    b1 = rnd(NB, seed=7, scale=0.1)
+    w2 = rnd(1, NB, seed=8, scale=(3.0 / NB) ** 0.5)
+    b2 = rnd(1, seed=9, scale=0.1)
+    g = torch.Generator().manual_seed(10)
+    mk = lambda *s: (torch.rand(*s, generator=g) > 0.3).float() / 0.7
+    m2, m3, mv = (mk(B, C2, 8, 8), mk(B, C3, 4, 4), mk(B, NB)) if use_masks else (None, None, None)
+    dpred, de3, de4 = rnd(B, 1, seed=11), rnd(B, C3, 4, 4, seed=12), rnd(B, NB, 1, 1, seed=13)
+    ps = [t.clone().requires_grad_() for t in (e2, w3, b3, w14, b14, w1, b1, w2, b2)]
+    x = ps[0] * m2 if use_masks else ps[0]
+    e3 = F.max_pool2d(F.relu(F.conv2d(x, ps[1], ps[2], padding=1)), 2)
+    x3 = e3 * m3 if use_masks else e3
+    h = F.relu(F.conv2d(x3, ps[3], ps[4]))
+    v = F.relu(F.linear(h.flatten(1), ps[5], ps[6]))
+    pred = torch.sigmoid(F.linear(v * mv if use_masks else v, ps[7], ps[8]))
+    if extra:
+        torch.autograd.backward([pred, e3, h], [dpred, de3, de4])
+    else:
+        pred.backward(dpred)
+    po = [nhwc(e2).cuda().requires_grad_()] + [t.cuda().requires_grad_() for t in (w3, b3, w14, b14, w1, b1, w2, b2)]
+    dm = lambda t: None if t is None else (nhwc(t).cuda() if t.dim() == 4 else t.cuda())
+    predo, e3o, e4o = ops.Tail.apply(po[0], dm(m2), dm(m3), dm(mv), *po[1:])
+    if extra:
+        torch.autograd.backward([predo, e3o, e4o], [dpred.cuda(), nhwc(de3).cuda(), nhwc(de4).cuda()])
+    else:
+        predo.backward(dpred.cuda())
+    close(predo, pred, "pred")
+    close(nchw(e3o), e3, "e3")
+    close(nchw(e4o), h, "e4")
+    close(nchw(po[0].grad), ps[0].grad, "de2")
+    for n, a, r in zip(["dw3", "db3", "dw14", "db14", "dw1", "db1", "dw2", "db2"], po[1:], ps[1:]):
+        close(a.grad, r.grad, n)
+
+
 @pytest.mark.parametrize("B,K,N", [(5, 32, 32), (40, 160, 160), (1, 7, 3)])
 def test_dense_fwd_bwd(ops, B, K, N):
     x, w, b, do = rnd(B, K, seed=1), rnd(N, K, 1, 1, seed=2, scale=0.2), rnd(N, seed=3), rnd(B, N, seed=4)
@@ -258,6 +302,36 @@ def test_frames_to_float_threshold_adam(ops):
         step.add_(1)
         ops.adam_step(p, g.cuda(), m, v, step)
     close(p, q, "adam", rtol=1e-6, arel=1e-7)
+
+
+def test_dropout_masks_kernel(ops):
+    state = torch.zeros(2, dtype=torch.int64, device="cuda")
+    p = 0.3
+    shapes = [(64, 8, 8, 8), (64, 4, 4, 16), (64, 32)]
+    a = ops.dropout_masks(shapes, p, 1234, state)
+    b = ops.dropout_masks(shapes, p, 1234, state)
+    assert int(state[0]) == 2 and int(state[1]) == 0
+    for m, s in zip(a, shapes):
+        assert tuple(m.shape) == s
+        vals = torch.unique(m).cpu().tolist()
+        assert all(abs(v) < 1e-12 or abs(v - 1 / (1 - p)) < 1e-6 for v in vals)
+    keep = torch.cat([(m > 0).float().flatten() for m in a])
+    n = keep.numel()
+    assert abs(keep.mean().item() - (1 - p)) < 5 * (p * (1 - p) / n) ** 0.5
+    assert not torch.equal(a[0], b[0])                      # the call counter advanced on the device
+    state2 = torch.zeros(2, dtype=torch.int64, device="cuda")
+    c = ops.dropout_masks(shapes, p, 1234, state2)
+    assert all(torch.equal(x, y) for x, y in zip(a, c))     # same (seed, counter) -> same masks
+    # graph replays draw fresh masks
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ops.dropout_masks(shapes, p, 7, state)
+    torch.cuda.current_stream().wait_stream(s)
+    with torch.cuda.graph(g):
+        out = ops.dropout_masks(shapes, p, 7, state)
+    g.replay(); r1 = out[0].clone(); g.replay(); r2 = out[0].clone()
+    assert not torch.equal(r1, r2)
 
 
 def test_errors_are_loud(ops):

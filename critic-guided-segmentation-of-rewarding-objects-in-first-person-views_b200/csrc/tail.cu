@@ -24,7 +24,7 @@ struct TailSmem {
 __host__ __device__ inline TailSmem tail_smem(int FPC, int C2, int C3, int NB, bool bwd) {
   TailSmem s;
   int o = 0;
-  s.x2 = o; o += FPC * 100 * C2;           // haloed 10x10 e2*mask, pixel-major [f][yy*10+xx][ci]
+  s.x2 = o; o += FPC * 104 * C2;           // haloed 10x10 e2*mask: fwd pixel-major [f][slot][ci], bwd planar [f][ci][104]
   s.w3 = o; o += C2 * 9 * C3;              // conv weights as [ci][tap][co]
   s.x = o;  o += FPC * 17 * C3;            // e3*mask in the 4x4 conv's own K order (ci*17 + s)
   s.h = o;  o += FPC * NB;
@@ -34,14 +34,16 @@ __host__ __device__ inline TailSmem tail_smem(int FPC, int C2, int C3, int NB, b
     s.dh = o; o += FPC * NB;
     s.dv = o; o += FPC * NB;
     s.dl = o; o += ((FPC + 3) & ~3);
-    s.dy = o; o += FPC * 100 * C3;         // haloed 10x10 gradient of the conv output, [f][yy*10+xx][co]
+    s.dy = o; o += FPC * 104 * C3;         // haloed 10x10 gradient of the conv output, planar [f][co][104]
   }
   s.total = o;
   return s;
 }
 
-// Stage e2*mask (haloed, zero border) and the conv weights.
-template <int FPC>
+// Stage e2*mask (haloed, zero border) and the conv weights.  PLANAR: [f][ci][slot] (backward: the wgrad loop walks
+// pixels with the channel fixed) instead of pixel-major [f][slot][ci] (forward: lanes = output channels broadcast a pixel).
+constexpr int TAIL_PL = 104;   // plane pitch (100 slots + 4: planes 8 banks apart)
+template <int FPC, bool PLANAR>
 __device__ __forceinline__ void tail_stage_in(const TailDims d, int n0, const float* __restrict__ e2, const float* __restrict__ m_e2,
                                               const float* __restrict__ w3, float* s_x2, float* s_w3) {
   const int C2 = d.C2, C3 = d.C3;
@@ -55,7 +57,8 @@ __device__ __forceinline__ void tail_stage_in(const TailDims d, int n0, const fl
       v = __ldg(e2 + o);
       if (m_e2) v *= __ldg(m_e2 + o);
     }
-    s_x2[e] = v;
+    if (PLANAR) s_x2[(f * C2 + ci) * TAIL_PL + slot] = v;
+    else s_x2[e] = v;
   }
   for (int e = threadIdx.x; e < C2 * 9 * C3; e += HT) {
     const int co = e % C3, r = e / C3;
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(HT) tail_fwd_kernel(const TailDims d, const fl
   float *s_x2 = smem + L.x2, *s_w3 = smem + L.w3, *s_x = smem + L.x, *s_h = smem + L.h, *s_v = smem + L.v;
   const int K = 16 * C3, ldx = 17 * C3;
   const int n0 = blockIdx.x * FPC;
-  tail_stage_in<FPC>(d, n0, e2, m_e2, w3, s_x2, s_w3);
+  tail_stage_in<FPC, false>(d, n0, e2, m_e2, w3, s_x2, s_w3);
   __syncthreads();
 
   // ---- features.10-12: conv + ReLU + 2x2 max-pool; one (frame, window, co) item per thread iteration
@@ -196,8 +199,8 @@ __global__ void __launch_bounds__(HT) tail_bwd_kernel(const TailDims d, const fl
   const int n0 = blockIdx.x * FPC;
   const bool wg = G.dw14 != nullptr;
 
-  tail_stage_in<FPC>(d, n0, e2, m_e2, w3, s_x2, s_w3);
-  for (int e = threadIdx.x; e < FPC * 100 * C3; e += HT) s_dy[e] = 0.f;
+  tail_stage_in<FPC, true>(d, n0, e2, m_e2, w3, s_x2, s_w3);
+  for (int e = threadIdx.x; e < FPC * TAIL_PL * C3; e += HT) s_dy[e] = 0.f;
   for (int e = threadIdx.x; e < FPC * K; e += HT) {
     const int f = e / K, k = e - f * K;
     const int s = k / C3, ci = k - s * C3;
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(HT) tail_bwd_kernel(const TailDims d, const fl
       if (de3_ext) g += __ldg(de3_ext + o);
       if (!(__ldg(e3 + o) > 0.f)) g = 0.f;
       const int pos = idx3[o];
-      s_dy[((size_t)f * 100 + (2 * wy + (pos >> 1) + 1) * 10 + (2 * wx + (pos & 1) + 1)) * C3 + co] = g;
+      s_dy[(f * C3 + co) * TAIL_PL + (2 * wy + (pos >> 1) + 1) * 10 + (2 * wx + (pos & 1) + 1)] = g;
     }
   }
   __syncthreads();
@@ -296,20 +299,19 @@ __global__ void __launch_bounds__(HT) tail_bwd_kernel(const TailDims d, const fl
       const int ky = t / 3, kx = t - ky * 3;
       float acc = 0.f;
       for (int f = 0; f < FPC; ++f) {
-        const float* dyb = s_dy + (size_t)f * 100 * C3 + co;
-        const float* xb = s_x2 + (size_t)f * 100 * C2 + ci;
+        const float* dyb = s_dy + (f * C3 + co) * TAIL_PL + 11;
+        const float* xb = s_x2 + (f * C2 + ci) * TAIL_PL + ky * 10 + kx;
 #pragma unroll 2
         for (int y = 0; y < 8; ++y)
 #pragma unroll
-          for (int x = 0; x < 8; ++x)
-            acc = fmaf(dyb[((y + 1) * 10 + x + 1) * C3], xb[((y + ky) * 10 + x + kx) * C2], acc);
+          for (int x = 0; x < 8; ++x) acc = fmaf(dyb[y * 10 + x], xb[y * 10 + x], acc);
       }
       atomicAdd(G.dw3 + e, acc);
     }
     for (int co = threadIdx.x; co < C3; co += HT) {
       float acc = 0.f;
       for (int f = 0; f < FPC; ++f)
-        for (int s = 0; s < 100; ++s) acc += s_dy[((size_t)f * 100 + s) * C3 + co];
+        for (int s = 0; s < 100; ++s) acc += s_dy[(f * C3 + co) * TAIL_PL + s];
       atomicAdd(G.db3 + co, acc);
     }
   }
@@ -323,9 +325,10 @@ __global__ void __launch_bounds__(HT) tail_bwd_kernel(const TailDims d, const fl
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int ky = t / 3, kx = t - ky * 3;
-        const float* dyb = s_dy + ((size_t)f * 100 + (y + 2 - ky) * 10 + (x + 2 - kx)) * C3;
+        const float* dyb = s_dy + (f * C3) * TAIL_PL + (y + 2 - ky) * 10 + (x + 2 - kx);
         const float* wp = s_w3 + ((size_t)ci * 9 + t) * C3;
-        for (int co = 0; co < C3; ++co) acc = fmaf(dyb[co], wp[co], acc);
+#pragma unroll 4
+        for (int co = 0; co < C3; ++co) acc = fmaf(dyb[co * TAIL_PL], wp[co], acc);
       }
       if (n0 + f < B) {
         const size_t o = ((size_t)(n0 + f) * 64 + px) * C2 + ci;
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(HT) tail_bwd_kernel(const TailDims d, const fl
 }
 
 static size_t tail_bytes(int FPC, int C2, int C3, int NB, bool bwd) { return (size_t)tail_smem(FPC, C2, C3, NB, bwd).total * sizeof(float); }
-static int tail_fpc(int B) { return B <= 4096 ? 2 : 8; }
+static int tail_fpc(int B) { return B <= 512 ? 1 : (B <= 4096 ? 2 : 8); }
 
 }  // namespace cgs
 
@@ -363,7 +366,8 @@ extern "C" int cgs_tail_fwd(const float* e2, const float* m_e2, const float* m_e
                                                                                  w2, b2, e3, idx3, e4, v, pred);
     return check_launch("tail_fwd");
   };
-  return tail_fpc(B) == 2 ? go(std::integral_constant<int, 2>{}) : go(std::integral_constant<int, 8>{});
+  const int fpc = tail_fpc(B);
+  return fpc == 1 ? go(std::integral_constant<int, 1>{}) : fpc == 2 ? go(std::integral_constant<int, 2>{}) : go(std::integral_constant<int, 8>{});
 }
 
 extern "C" int cgs_tail_bwd(const float* e2, const float* m_e2, const float* m_e3, const float* m_v, const float* w3,
@@ -387,5 +391,6 @@ extern "C" int cgs_tail_bwd(const float* e2, const float* m_e2, const float* m_e
                                                                                  e4, v, pred, dpred, de3_ext, de4, G, de2);
     return check_launch("tail_bwd");
   };
-  return tail_fpc(B) == 2 ? go(std::integral_constant<int, 2>{}) : go(std::integral_constant<int, 8>{});
+  const int fpc = tail_fpc(B);
+  return fpc == 1 ? go(std::integral_constant<int, 1>{}) : fpc == 2 ? go(std::integral_constant<int, 2>{}) : go(std::integral_constant<int, 8>{});
 }

@@ -200,15 +200,17 @@ bool wgrad_mma_supported(const cgs_wgrad3x3_args& a) { return a.W >= 8 && a.H >=
 
 int launch_wgrad_mma(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   WgGeom g;
-  g.th = a.H < 32 ? a.H : 32;
+  g.th = a.H < 16 ? a.H : 16;     // 16 x 32 pixel tiles: ~40 KB of smem, several CTAs per SM overlap staging with MMA
   g.tw = a.W < 32 ? a.W : 32;
-  if (g.th * g.tw > 512 && (long)a.B * (a.H / g.th) * (a.W / g.tw) < 592) g.th /= 2;   // more CTAs when the batch is small
   g.tiles_y = a.H / g.th; g.tiles_x = a.W / g.tw;
   g.fpc = 1;
   while (g.fpc * g.th * g.tw < 512 && (long)((a.B + 2 * g.fpc - 1) / (2 * g.fpc)) >= 148) g.fpc *= 2;
-  g.rsx = (g.tw + 2) | 1; g.rsy = g.tw | 1;
-  g.psx = g.fpc * (g.th + 2) * g.rsx; g.psx += (40 - (g.psx % 32)) % 32;
-  g.psy = g.fpc * g.th * g.rsy;       g.psy += (40 - (g.psy % 32)) % 32;
+  // A-fragment gathers read, per instruction, 8 (ci,tap) rows x 4 consecutive pixels: with a row stride == 8 (mod 16)
+  // the three filter rows land in disjoint bank ranges; dY planes 4 banks apart make the B-fragment reads conflict-free.
+  g.rsx = (g.tw + 2 + 7) & ~7; if ((g.rsx & 15) == 0) g.rsx += 8;
+  g.rsy = g.tw;
+  g.psx = g.fpc * (g.th + 2) * g.rsx; g.psx += (56 - (g.psx % 32)) % 32;   // == 24 (mod 32)
+  g.psy = g.fpc * g.th * g.rsy;       g.psy += (36 - (g.psy % 32)) % 32;   // == 4 (mod 32)
   g.dsw = make_fastdiv(g.tw + 2); g.dsh = make_fastdiv(g.th + 2);
   g.dtw = make_fastdiv(g.tw);     g.dth = make_fastdiv(g.th);
   g.dwp = make_fastdiv(g.tw / 2); g.dhp = make_fastdiv(g.th / 2);

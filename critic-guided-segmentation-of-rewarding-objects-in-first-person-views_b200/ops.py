@@ -82,6 +82,36 @@ def _frames_src(x, roll):
     return None
 
 
+# ---- weight gradients on a side stream.  A layer's wgrad and dgrad are independent; each alone leaves most SMs
+# idle at the reference batch sizes, so wgrad kernels that accumulate into a FlatAdam bucket are forked onto a second
+# stream and joined in FlatAdam.step() (captured as parallel branches of the step graph).
+async_wgrad = True
+_side = {"stream": None, "pending": False, "keep": []}
+
+
+def _fork_wgrad(launch, keep, direct):
+    """Run `launch()` (wgrad kernels) on the side stream if its outputs go straight into the flat bucket."""
+    if not (async_wgrad and direct):
+        launch()
+        return
+    if _side["stream"] is None:
+        _side["stream"] = torch.cuda.Stream()
+    main, side = torch.cuda.current_stream(), _side["stream"]
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        launch()
+    _side["pending"] = True
+    _side["keep"].extend(t for t in keep if t is not None)    # keep operands alive until the join
+
+
+def join_wgrad():
+    """Make the current stream wait for all forked wgrad kernels (called by FlatAdam.step / zero_grad)."""
+    if _side["pending"]:
+        torch.cuda.current_stream().wait_stream(_side["stream"])
+        _side["pending"] = False
+        _side["keep"].clear()
+
+
 def _gbuf(param, needed):
     """Where a parameter gradient goes: (buffer to ACCUMULATE into, value to return to autograd).
     Parameters owned by a FlatAdam carry `_cgs_grad`, a view of the flat gradient bucket: the kernels add
@@ -126,7 +156,8 @@ class EncBlock(torch.autograd.Function):
             dw, rw = _gbuf(ctx.params[0], True)
             db, rb = _gbuf(ctx.params[1], True)
             xs = _frames_src(x, ctx.roll) or _src(SRC_PLAIN, Cin, x, mask)
-            wgrad3x3(xs, dy, B, H, W, dw, db)
+            _fork_wgrad(lambda: wgrad3x3(xs, dy, B, H, W, dw, db), (x, mask, de, e, idx, ctx.roll if torch.is_tensor(ctx.roll) else None),
+                        rw is None and rb is None)
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             conv3x3(dy, w, None, B, H, W, Cin, EPI_MUL if mask is not None else EPI_LINEAR, dx,
@@ -245,7 +276,8 @@ class DecBlock(torch.autograd.Function):
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
             dw, rw = _gbuf(ctx.params[0], True)
             db, rb = _gbuf(ctx.params[1], True)
-            wgrad3x3(_src(SRC_CATUP, C0 + C1, skip, up, C0=C0, shift=shift), dy, B, H, W, dw, db)
+            xs = _src(SRC_CATUP, C0 + C1, skip, up, C0=C0, shift=shift)
+            _fork_wgrad(lambda: wgrad3x3(xs, dy, B, H, W, dw, db), (skip, up, dout, out), rw is None and rb is None)
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             if ctx.needs_input_grad[0]:
                 dskip = torch.empty_like(skip)
@@ -288,7 +320,8 @@ class MaskHead(torch.autograd.Function):
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             dw, rw = _gbuf(ctx.params[0], True)
             db, rb = _gbuf(ctx.params[1], True)
-            wgrad3x3(_src(SRC_PLAIN, Cm, m), dy, B, H, W, dw, db)
+            xs = _src(SRC_PLAIN, Cm, m)
+            _fork_wgrad(lambda: wgrad3x3(xs, dy, B, H, W, dw, db), (m, dz, z), rw is None and rb is None)
         if ctx.needs_input_grad[0]:
             dm = torch.empty_like(m)
             conv3x3(dy, w, None, B, H, W, Cm, EPI_LINEAR, dm, transposed=True)

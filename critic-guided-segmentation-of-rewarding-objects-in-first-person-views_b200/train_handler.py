@@ -92,9 +92,11 @@ class FlatAdam:
         self.group, self.world = process_group, world_size
 
     def zero_grad(self):
+        ops.join_wgrad()
         self.gflat.zero_()
 
     def step(self):
+        ops.join_wgrad()           # wgrad kernels forked onto the side stream have all landed in the bucket
         if self.world > 1:
             torch.distributed.all_reduce(self.gflat, group=self.group)   # ranks pre-scale their losses by 1/world
         self.step_count.add_(1)

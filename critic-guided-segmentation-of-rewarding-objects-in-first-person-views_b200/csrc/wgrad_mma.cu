@@ -200,8 +200,9 @@ bool wgrad_mma_supported(const cgs_wgrad3x3_args& a) { return a.W >= 8 && a.H >=
 
 int launch_wgrad_mma(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   WgGeom g;
-  g.th = a.H < 16 ? a.H : 16;     // 16 x 32 pixel tiles: ~40 KB of smem, several CTAs per SM overlap staging with MMA
+  g.th = a.H < 32 ? a.H : 32;
   g.tw = a.W < 32 ? a.W : 32;
+  if (g.th * g.tw > 512 && (long)a.B * (a.H / g.th) * (a.W / g.tw) < 592) g.th /= 2;   // more CTAs when the batch is small
   g.tiles_y = a.H / g.th; g.tiles_x = a.W / g.tw;
   g.fpc = 1;
   while (g.fpc * g.th * g.tw < 512 && (long)((a.B + 2 * g.fpc - 1) / (2 * g.fpc)) >= 148) g.fpc *= 2;

@@ -1,0 +1,51 @@
+"""Staged data-parallel check (run under torchrun on >= 2 GPUs): prints after every stage so a hang is attributable."""
+import faulthandler, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+faulthandler.dump_traceback_later(int(os.environ.get("DP_CHECK_TIMEOUT", "90")), exit=True)
+import torch, torch.distributed as dist
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+def say(*a):
+    print(f"[rank {rank} t={time.time()-T0:5.1f}]", *a, flush=True)
+T0 = time.time()
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+say("pg up"); dist.barrier(); torch.cuda.synchronize(); say("barrier ok")
+from cgs_b200 import ops
+from cgs_b200.train_handler import Handler, parse_args, FlatAdam
+from cgs_b200.graph_step import GraphedCriticStep
+import cgs_b200.synth as synth
+ops.set_precision(os.environ.get("DP_PRECISION", "tf32"))
+torch.manual_seed(0)
+H = Handler(parse_args(["--dropout", "0"]), device=dev, rank=rank, world_size=world, process_group=dist.group.WORLD)
+H.critic.to(dev)
+B = 64
+X, Y, _ = synth.synthetic_frames(B * world, seed=0)
+Xs = torch.from_numpy(X[rank * B:(rank + 1) * B]).to(dev); Ys = torch.from_numpy(Y[1, rank * B:(rank + 1) * B]).float().to(dev)
+opt = FlatAdam(H.critic.parameters(), process_group=dist.group.WORLD, world_size=world)
+for i in range(3):
+    l = H.critic_step(Xs, Ys, opt)
+torch.cuda.synchronize(); say("eager DP steps ok, loss", float(l))
+flat = opt.flat.clone(); ref = flat.clone(); dist.broadcast(ref, 0); torch.cuda.synchronize()
+say("params equal across ranks:", bool(torch.equal(flat, ref)))
+if world > 1 and rank == 0:
+    # single-process reference on the global batch
+    torch.manual_seed(0)
+    H1 = Handler(parse_args(["--dropout", "0"]), device=dev); H1.critic.to(dev)
+    o1 = FlatAdam(H1.critic.parameters())
+    Xg = torch.from_numpy(X).to(dev); Yg = torch.from_numpy(Y[1, :B * world]).float().to(dev)
+    for i in range(3):
+        H1.critic_step(Xg, Yg, o1)
+    torch.cuda.synchronize()
+    err = (o1.flat - flat).abs().max().item()
+    say(f"DP vs single-process global batch: max |dparam| = {err:.3e} (scale {o1.flat.abs().max().item():.3e})")
+dist.barrier(); say("capturing graph")
+step = GraphedCriticStep(H, B, opt)
+torch.cuda.synchronize(); say("captured, launches", step.launches)
+step.load(Xs.cpu().pin_memory(), Ys.cpu().pin_memory())
+for i in range(5):
+    out = step.replay()
+torch.cuda.synchronize(); say("replays ok, loss", float(out))
+ref = opt.flat.clone(); dist.broadcast(ref, 0); torch.cuda.synchronize()
+say("params equal across ranks after graph replays:", bool(torch.equal(opt.flat, ref)))
+dist.barrier(); dist.destroy_process_group(); say("done")

@@ -329,7 +329,12 @@ def run_ours(args, rank, world):
                                     "sample": f"{n} full steps of batch {B} in {dt:.1f}s (oracle/torch_ref.py on torch CPU fp32)"}
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing the communicator down while captured graphs still reference it hangs in ncclCommAbort on this
+        # stack (tools/dp_check.py); all ranks are done, so flush and leave without destroy_process_group().
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

@@ -48,4 +48,4 @@ for i in range(5):
 torch.cuda.synchronize(); say("replays ok, loss", float(out))
 ref = opt.flat.clone(); dist.broadcast(ref, 0); torch.cuda.synchronize()
 say("params equal across ranks after graph replays:", bool(torch.equal(opt.flat, ref)))
-dist.barrier(); dist.destroy_process_group(); say("done")
+dist.barrier(); torch.cuda.synchronize(); say("done"); sys.stdout.flush(); os._exit(0)

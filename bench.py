@@ -195,8 +195,8 @@ def kernel_rooflines(B, chfak, flush, hbm_gbs):
         by_f = x.numel() * 4 + e.numel() * 5 + w.numel() * 4
         by_w = x.numel() * 4 + e.numel() * 9 + w.numel() * 4
         fl = 2 * B * H * H * Cin * Cout * 9
-        out.append({"kernel": f"conv3x3_kernel fprop+relu+pool {name}", "bytes": by_f, "flops": fl, "sec": t_f})
-        out.append({"kernel": f"wgrad3x3_kernel {name}", "bytes": by_w, "flops": fl, "sec": t_w})
+        out.append({"kernel": f"conv {name}", "desc": "fprop+bias+ReLU+maxpool", "bytes": by_f, "flops": fl, "sec": t_f})
+        out.append({"kernel": f"wgrad {name}", "desc": "weight+bias gradient", "bytes": by_w, "flops": fl, "sec": t_w})
     for k in out:
         k["gbs"] = k["bytes"] / k["sec"] / 1e9
         k["tflops"] = k["flops"] / k["sec"] / 1e12
@@ -311,8 +311,11 @@ def run_ours(args, rank, world):
         if world == 1 and not args.no_extras:
             ks = kernel_rooflines(B, args.chfak, flush, hbm)
             top = max(ks, key=lambda k: k["sec"])
+            tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+            traffic = json.load(open(tpath)).get(top["kernel"]) if (os.path.exists(tpath) and args.chfak == 1 and B == 256) else None
             line["roofline"] = {"bound": "hbm", "achieved": top["gbs"], "peak": hbm, "unit": "GB/s",
-                                "frac": top["gbs"] / hbm, "traffic": None, "kernel": top["kernel"],
+                                "frac": top["gbs"] / hbm, "traffic": traffic, "kernel": top["kernel"],
+                                "algorithmic_bytes": top["bytes"],
                                 "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
                                 "launch_us": top["sec"] * 1e6, "achieved_tflops_fp32": top["tflops"]}
             line["kernels"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in kk.items()} for kk in ks]

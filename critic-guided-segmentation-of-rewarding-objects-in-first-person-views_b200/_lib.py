@@ -47,7 +47,7 @@ EXPORTS = {
     "cgs_pred_loss": [_f32p, _f32p, C.c_int32, C.c_int32, C.c_float, _f32p, _f32p, C.c_void_p],
     "cgs_mask_reg": [_f32p, _f32p, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, _f32p, _f32p, C.c_void_p],
     "cgs_frames_to_float": [_u8p] + [C.c_int32] * 5 + [C.c_void_p, _f32p, C.c_void_p],
-    "cgs_adam_step": [_f32p] * 4 + [C.c_int64] + [C.c_double] * 4 + [C.c_void_p, C.c_float, C.c_void_p],
+    "cgs_adam_step": [_f32p] * 4 + [C.c_int64] + [C.c_double] * 4 + [C.c_void_p, C.c_float, C.c_int32, C.c_void_p],
     "cgs_threshold": [_f32p, C.c_int64, C.c_float, C.c_int32, _u8p, C.c_void_p],
     "cgs_dropout_masks": [_f32p, C.c_int64, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p],
     "cgs_tc_status": [],

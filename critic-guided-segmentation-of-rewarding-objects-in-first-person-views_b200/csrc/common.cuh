@@ -70,6 +70,7 @@ struct WgGeom {
   int rsx, psx, rsy, psy;
   FastDiv dsw, dsh, dtw, dth;
   FastDiv dwp, dhp;   // dividers by tw/2, th/2 (pooled-granularity staging)
+  int xplanes;        // X planes actually allocated (min(8, Cin)): the RGB layer needs 3, not 8
 };
 
 // Up to 8 consecutive floats (channels) of one pixel -> registers; two 128-bit loads when aligned.
@@ -80,7 +81,13 @@ __device__ __forceinline__ void load8(const float* __restrict__ p, int n, bool v
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = i < n ? __ldg(p + i) : 0.f;
+    for (int i = 0; i < 4; ++i) v[i] = i < n ? __ldg(p + i) : 0.f;
+    if (n > 4) {
+#pragma unroll
+      for (int i = 4; i < 8; ++i) v[i] = i < n ? __ldg(p + i) : 0.f;
+    } else {
+      v[4] = v[5] = v[6] = v[7] = 0.f;
+    }
   }
 }
 

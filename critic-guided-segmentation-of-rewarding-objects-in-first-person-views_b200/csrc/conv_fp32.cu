@@ -80,8 +80,13 @@ __global__ void __launch_bounds__(256, (CO_T <= 8 ? 3 : 2)) conv3x3_kernel(const
       }
       float* d = s_in + (ff * CI_T) * g.ps + yy * g.rs + xx;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i)
         if (i < ci_n) d[i * g.ps] = v[i];
+      if (ci_n > 4) {
+#pragma unroll
+        for (int i = 4; i < 8; ++i)
+          if (i < ci_n) d[i * g.ps] = v[i];
+      }
     }
     // ---- stage the weight chunk as [ci][tap][co]
 #pragma unroll 4

@@ -203,10 +203,13 @@ __global__ void dropout_masks_kernel(float* __restrict__ out, int64_t n, float p
 }
 
 // ---------------------------------------------------------------- Adam
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+// step_state = {step counter t (already-applied steps), ticket}: the kernel applies step t+1 and the last CTA to finish
+// publishes t+1, so no separate counter-increment launch is needed.  With clear_grad the consumed gradient is zeroed in
+// the same pass (next step's wgrad kernels accumulate from zero: no memset launch).
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             int64_t n, double lr, double beta1, double beta2, double eps_d,
-                            const int* __restrict__ step_count, float gscale) {
-  const int t = *step_count;
+                            int* __restrict__ step_state, float gscale, int clear_grad) {
+  const int t = step_state[0] + 1;
   // bias corrections in double, as torch does on the host (python floats); tensor-side scalars in fp32
   const double bc1 = 1.0 - pow(beta1, (double)t);
   const double bc2 = 1.0 - pow(beta2, (double)t);
@@ -221,6 +224,15 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     v[i] = vv;
     const float denom = sqrtf(vv) / bc2_sqrt + eps;
     p[i] -= step_size * (mv / denom);
+    if (clear_grad) g[i] = 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&step_state[1], 1) == (int)gridDim.x - 1) {
+      step_state[1] = 0;
+      step_state[0] = t;
+    }
   }
 }
 
@@ -279,10 +291,11 @@ extern "C" int cgs_threshold(const float* z, int64_t n, float thresh, int32_t st
   return check_launch("threshold");
 }
 
-extern "C" int cgs_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
-                             double eps, const int32_t* step_count, float grad_scale, void* stream) {
-  CGS_REQUIRE(p && g && m && v && step_count && n > 0, "adam_step: bad args");
-  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_count, grad_scale);
+extern "C" int cgs_adam_step(float* p, float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                             double eps, int32_t* step_state, float grad_scale, int32_t clear_grad, void* stream) {
+  CGS_REQUIRE(p && g && m && v && step_state && n > 0, "adam_step: bad args");
+  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_state, grad_scale,
+                                                              clear_grad);
   return check_launch("adam_step");
 }
 

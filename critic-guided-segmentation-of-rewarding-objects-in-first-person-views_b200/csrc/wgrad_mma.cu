@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
   const int H = p.H, W = p.W, Cin = p.x.C, Cout = p.dy.C;
   const int th = g.th, tw = g.tw, sh = th + 2, sw = tw + 2;
   float* s_x = smem;                                   // [WM_CI][fpc*sh rows][rsx]
-  float* s_y = smem + (size_t)WM_CI * g.psx;           // [WM_CO][fpc*th rows][rsy]
+  float* s_y = smem + (size_t)g.xplanes * g.psx;       // [WM_CO][fpc*th rows][rsy]
 
   int bid = blockIdx.x;
   const int tix = bid % g.tiles_x; bid /= g.tiles_x;
@@ -67,8 +67,13 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
       }
       float* d = s_x + row * g.rsx + xx;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i)
         if (i < cin) d[i * g.psx] = tf32r(v[i]);      // round once here, not 9x in the MMA loop
+      if (cin > 4) {
+#pragma unroll
+        for (int i = 4; i < 8; ++i)
+          if (i < cin) d[i * g.psx] = tf32r(v[i]);
+      }
     }
     if (p.dy.mode == CGS_SRC_POOLBWD && (p.dy.C & 7) == 0) {
       // ReLU + max-pool backward at POOLED granularity: one (dE, E, argmax) load per pooled element, scattered to the
@@ -215,7 +220,8 @@ int launch_wgrad_mma(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   g.dsw = make_fastdiv(g.tw + 2); g.dsh = make_fastdiv(g.th + 2);
   g.dtw = make_fastdiv(g.tw);     g.dth = make_fastdiv(g.th);
   g.dwp = make_fastdiv(g.tw / 2); g.dhp = make_fastdiv(g.th / 2);
-  size_t smem = ((size_t)WM_CI * g.psx + (size_t)WM_CO * g.psy) * sizeof(float);
+  g.xplanes = a.x.C < WM_CI ? a.x.C : WM_CI;
+  size_t smem = ((size_t)g.xplanes * g.psx + (size_t)WM_CO * g.psy) * sizeof(float);
   const size_t red = (size_t)8 * 16 * 5 * 8 * sizeof(float);
   if (smem < red) smem = red;
   static bool attr_done = false;

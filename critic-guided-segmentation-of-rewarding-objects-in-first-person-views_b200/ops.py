@@ -120,6 +120,9 @@ def _gbuf(param, needed):
         return None, None
     g = getattr(param, "_cgs_grad", None)
     if g is not None and param.grad is g:      # still the live .grad (not reset by a foreign zero_grad)
+        opt = getattr(param, "_cgs_opt", None)
+        if opt is not None:
+            opt._clean = False                 # the bucket now holds gradient: zero_grad must really clear it
         return g, None
     z = torch.zeros_like(param)
     return z, z
@@ -238,9 +241,20 @@ class Tail(torch.autograd.Function):
         want_w = any(ctx.needs_input_grad[4:])
         bufs, rets = zip(*[_gbuf(prm, want_w) for prm in ctx.params])
         de2 = torch.empty_like(e2) if ctx.needs_input_grad[0] else None
-        _call("cgs_tail_bwd", _p(e2), _p(m_e2), _p(m_e3), _p(m_v), _p(w3), _p(w14), _p(w1), _p(w2), _p(e3),
-              _p(idx3, torch.uint8), _p(e4), _p(v), _p(pred), _p(dpred), _p(de3), _p(de4), B, C2, C3, NB,
-              *[_p(t) for t in bufs], _p(de2), _stream())
+
+        def launch(grads, dx):
+            g = [_p(t) for t in grads] if grads is not None else [None] * 8
+            _call("cgs_tail_bwd", _p(e2), _p(m_e2), _p(m_e3), _p(m_v), _p(w3), _p(w14), _p(w1), _p(w2), _p(e3),
+                  _p(idx3, torch.uint8), _p(e4), _p(v), _p(pred), _p(dpred), _p(de3), _p(de4), B, C2, C3, NB,
+                  *g, _p(dx), _stream())
+        direct = want_w and all(r is None for r in rets)
+        if direct and async_wgrad and de2 is not None:
+            # critical path: only the input gradient; all weight gradients on the side stream (the head chain is
+            # recomputed there, it is < 1 % of the step)
+            _fork_wgrad(lambda: launch(bufs, None), (e2, m_e2, m_e3, m_v, e3, idx3, e4, v, pred, dpred, de3, de4), True)
+            launch(None, de2)
+        else:
+            launch(bufs if want_w else None, de2)
         return (de2, None, None, None) + tuple(rets)
 
 
@@ -457,10 +471,11 @@ def threshold(z, thresh, strict=False):
     return hard
 
 
-def adam_step(p, g, m, v, step_count, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
-    """Flat-bucket Adam (torch.optim.Adam defaults, main.py:178).  step_count: int32 device tensor (already incremented)."""
+def adam_step(p, g, m, v, step_state, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, clear_grad=False):
+    """Flat-bucket Adam (torch.optim.Adam defaults, main.py:178).  step_state: int32 device tensor [2] = (steps applied,
+    ticket); the kernel advances it.  clear_grad: zero g in the same pass (fused zero_grad)."""
     _call("cgs_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(betas[0]), float(betas[1]),
-          float(eps), _p(step_count, torch.int32), float(grad_scale), _stream())
+          float(eps), _p(step_state, torch.int32), float(grad_scale), int(clear_grad), _stream())
 
 
 def occlude(a, b, z):

@@ -78,7 +78,8 @@ class FlatAdam:
         self.gflat = torch.zeros(n, device=dev, dtype=torch.float32)
         self.m = torch.zeros(n, device=dev, dtype=torch.float32)
         self.v = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.step_count = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.step_count = torch.zeros(2, device=dev, dtype=torch.int32)     # (steps applied, ticket), advanced by the kernel
+        self._clean = True                                                    # gflat known to be all-zero
         off = 0
         with torch.no_grad():
             for p in self.params:
@@ -87,20 +88,24 @@ class FlatAdam:
                 p.data = self.flat[off:off + k].view(p.shape)
                 p.grad = self.gflat[off:off + k].view(p.shape)
                 p._cgs_grad = p.grad            # kernels accumulate weight gradients straight into the bucket
+                p._cgs_opt = self
                 off += k
         self.lr, self.betas, self.eps = lr, betas, eps
         self.group, self.world = process_group, world_size
 
     def zero_grad(self):
         ops.join_wgrad()
-        self.gflat.zero_()
+        if not self._clean:          # step() already cleared the bucket inside the Adam kernel
+            self.gflat.zero_()
+            self._clean = True
 
     def step(self):
         ops.join_wgrad()           # wgrad kernels forked onto the side stream have all landed in the bucket
         if self.world > 1:
             torch.distributed.all_reduce(self.gflat, group=self.group)   # ranks pre-scale their losses by 1/world
-        self.step_count.add_(1)
-        ops.adam_step(self.flat, self.gflat, self.m, self.v, self.step_count, self.lr, self.betas, self.eps)
+        ops.adam_step(self.flat, self.gflat, self.m, self.v, self.step_count, self.lr, self.betas, self.eps,
+                      clear_grad=True)
+        self._clean = True
 
 
 def _nhwc(t):

@@ -167,12 +167,12 @@ int cgs_mask_reg(const float* z, const float* vpred, int64_t n, int32_t per_fram
 int cgs_frames_to_float(const uint8_t* in, int32_t B, int32_t H, int32_t W, int32_t C,
                         int32_t roll, const int32_t* roll_dev, float* out, void* stream);
 
-/* Adam, torch.optim.Adam defaults (main.py:178,331-334), over a flat parameter bucket.
- * step_count is the 1-based step index after increment, read from device memory so the
- * call can sit inside a CUDA graph. */
-int cgs_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
-                  double lr, double beta1, double beta2, double eps, const int32_t* step_count,
-                  float grad_scale, void* stream);
+/* Adam, torch.optim.Adam defaults (main.py:178,331-334), over a flat parameter bucket.  step_state = {number of steps
+ * already applied, ticket} in device memory: the kernel applies step state[0]+1 and publishes it itself, so the call can
+ * sit inside a CUDA graph with no counter-increment launch.  clear_grad != 0 zeroes g after use (fused zero_grad). */
+int cgs_adam_step(float* p, float* g, float* m, float* v, int64_t n,
+                  double lr, double beta1, double beta2, double eps, int32_t* step_state,
+                  float grad_scale, int32_t clear_grad, void* stream);
 
 /* All nn.Dropout masks of one NewCritic forward (nets.py:179,183,192) in one launch: out[i] = Bernoulli(1-p)/(1-p),
  * Philox4x32-10 keyed by (seed, state[0]); state = {call counter, ticket} in device memory, advanced by the kernel

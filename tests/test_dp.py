@@ -14,13 +14,16 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _cpu_adam(p, g, m, v, step_count, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
-    t = int(step_count.item())
-    g = g * grad_scale
+def _cpu_adam(p, g_buf, m, v, step_state, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, clear_grad=False):
+    step_state[0] += 1
+    t = int(step_state[0].item())
+    g = g_buf * grad_scale
     m.lerp_(g, 1 - betas[0])
     v.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
     denom = (v.sqrt() / (1 - betas[1] ** t) ** 0.5).add_(eps)
     p.addcdiv_(m, denom, value=-lr / (1 - betas[0] ** t))
+    if clear_grad:
+        g_buf.zero_()
 
 
 def _grads(critic, X, Y, scale):

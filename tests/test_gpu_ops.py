@@ -294,13 +294,15 @@ def test_frames_to_float_threshold_adam(ops):
     q = p0.clone().requires_grad_()
     opt = torch.optim.Adam([q])
     p, m, v = p0.cuda(), torch.zeros(1000).cuda(), torch.zeros(1000).cuda()
-    step = torch.zeros(1, dtype=torch.int32).cuda()
+    step = torch.zeros(2, dtype=torch.int32).cuda()
     for it in range(6):
         g = rnd(1000, seed=10 + it)
         q.grad = g.clone()
         opt.step()
-        step.add_(1)
-        ops.adam_step(p, g.cuda(), m, v, step)
+        gd = g.cuda()
+        ops.adam_step(p, gd, m, v, step, clear_grad=(it % 2 == 0))
+        assert (gd.abs().sum().item() == 0) == (it % 2 == 0)
+    assert step.cpu().tolist() == [6, 0]
     close(p, q, "adam", rtol=1e-6, arel=1e-7)
 
 

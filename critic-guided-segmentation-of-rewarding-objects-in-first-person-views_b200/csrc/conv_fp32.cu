@@ -265,6 +265,8 @@ static int launch_conv(const cgs_conv3x3_args& a, cudaStream_t st) {
   return check_launch("conv3x3");
 }
 
+bool wgrad_pipe_supported(const cgs_wgrad3x3_args& a);
+int launch_wgrad_pipe(const cgs_wgrad3x3_args& a, cudaStream_t st);
 bool wgrad_mma_supported(const cgs_wgrad3x3_args& a);
 int launch_wgrad_mma(const cgs_wgrad3x3_args& a, cudaStream_t st);
 bool conv_tc_supported(const cgs_conv3x3_args& a);
@@ -499,6 +501,7 @@ extern "C" int cgs_wgrad3x3(const cgs_wgrad3x3_args* a, void* stream) {
   CGS_REQUIRE(a->H >= 2 && a->W >= 2 && (a->H & (a->H - 1)) == 0 && (a->W & (a->W - 1)) == 0 && a->H <= 1024 && a->W <= 1024,
               "wgrad3x3: H,W must be powers of two >= 2 (got %dx%d)", a->H, a->W);
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->precision == CGS_TF32 && wgrad_pipe_supported(*a)) return launch_wgrad_pipe(*a, st);
   if (a->precision == CGS_TF32 && wgrad_mma_supported(*a)) return launch_wgrad_mma(*a, st);
   if (a->dy.C == 1) return launch_wgrad<1, 1, 1, 16>(*a, st);
   if (a->x.C <= 4) return launch_wgrad<2, 1, 4, 4>(*a, st);

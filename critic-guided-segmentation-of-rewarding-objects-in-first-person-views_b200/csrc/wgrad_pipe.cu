@@ -1,0 +1,237 @@
+// Persistent, cp.async double-buffered weight-gradient kernel for the encoder convolutions
+// (features.0/3/6 of NewCritic at chfak 1: Cin <= 8, Cout == 8, dY = ReLU+MaxPool backward of a pooled gradient).
+//
+// Same maths as wgrad_mma.cu (mma.sync m16n8k8 TF32, A fragments gathered from the haloed input tile, a row of
+// ones for the bias gradient) but restructured around the memory system, because ncu showed the staged version
+// spending its life in `long_scoreboard` (load -> sync -> MMA -> reduce, ~0.1 of HBM peak):
+//   * operands travel HBM -> shared memory as RAW bytes with 16-byte cp.async (zero register staging, zero index
+//     maths per element): full-width image rows of X (pixel-major, with zeroed left/right pads standing in for the
+//     horizontal halo, zfill for rows outside the image) and the pooled dE / E / argmax rows;
+//   * the ReLU + max-pool backward is evaluated while fetching the B fragment
+//     (dY[y,x,co] = (argmax == window position && E > 0) ? dE : 0), so the full-resolution gradient never exists;
+//   * two stages per CTA: the copy of tile i+1 is in flight while the warps run the MMAs of tile i;
+//   * CTAs are persistent (grid = SMs x resident CTAs), accumulators live in registers across all tiles of a CTA and
+//     are reduced once at the end: 444 x 224 REDs instead of 1024 x 224.
+#include "common.cuh"
+
+namespace cgs {
+
+struct WpGeom {
+  int th, tiles_y, ntiles;
+  int pitch, padL, rowsX;        // X smem row pitch (floats), left pad (floats), rows per tile (th + 2)
+  int xchunks, pchunks, ichunks; // 16-byte chunks per X row, per pooled dE/E row, per pooled idx row
+  int prow;                      // floats per pooled row (W/2 * 8)
+  int stage_floats;              // floats per pipeline stage
+  int offE, offI;                // float offsets of E and idx inside a stage (dE follows X)
+  int offD;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ uint32_t to_tf32(float f) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(f));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16n8k8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                                uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int MT>
+__global__ void __launch_bounds__(256) wgrad3x3_pipe_kernel(const cgs_wgrad3x3_args p, const WpGeom g) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+  const int H = p.H, W = p.W, C = p.x.C, H2 = H >> 1, W2 = W >> 1;
+  const int th = g.th;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+
+  // zero the horizontal-halo pads of both stages once (cp.async never touches them)
+  for (int e = tid; e < 2 * g.rowsX * 2 * g.padL; e += 256) {
+    const int s = e / (g.rowsX * 2 * g.padL), r2 = e - s * (g.rowsX * 2 * g.padL);
+    const int r = r2 / (2 * g.padL), q = r2 - r * (2 * g.padL);
+    const int col = q < g.padL ? q : g.padL + W * C + (q - g.padL);
+    smem[s * g.stage_floats + r * g.pitch + col] = 0.f;
+  }
+
+  auto prefetch = [&](int tile, int s) {
+    const int n = tile / g.tiles_y, y0 = (tile - n * g.tiles_y) * th;
+    const uint32_t sb = smem_base + (uint32_t)(s * g.stage_floats) * 4u;
+    // X: rowsX full-width image rows (row r <-> image row y0 - 1 + r), pixel-major
+    for (int c = tid; c < g.rowsX * g.xchunks; c += 256) {
+      const int r = c / g.xchunks, cx = c - r * g.xchunks;
+      const int y = y0 - 1 + r;
+      const bool ok = y >= 0 && y < H;
+      const float* src = ok ? p.x.a + (size_t)(unsigned)((n * H + y) * W) * (unsigned)C + cx * 4 : p.x.a;
+      cp_async16(sb + (uint32_t)(r * g.pitch + g.padL) * 4u + (uint32_t)cx * 16u, src, ok ? 16 : 0);
+    }
+    // pooled dE, E rows (8 channels per pooled pixel) and the argmax bytes
+    const int pr = th >> 1;
+    const size_t pbase = (size_t)(unsigned)((n * H2 + (y0 >> 1)) * W2) * 8u;
+    for (int c = tid; c < pr * g.pchunks; c += 256) {
+      cp_async16(sb + (uint32_t)g.offD * 4u + (uint32_t)c * 16u, p.dy.a + pbase + (size_t)c * 4, 16);
+      cp_async16(sb + (uint32_t)g.offE * 4u + (uint32_t)c * 16u, p.dy.b + pbase + (size_t)c * 4, 16);
+    }
+    for (int c = tid; c < pr * g.ichunks; c += 256)
+      cp_async16(sb + (uint32_t)g.offI * 4u + (uint32_t)c * 16u, p.dy.idx + pbase + (size_t)c * 16, 16);
+    cp_async_commit();
+  };
+
+  // per-lane A rows, tap-major: m = tap*C + ci  (8 consecutive rows = 8 channels of one tap: conflict-free gathers)
+  int offA[MT][2];   // >= 0 valid offset relative to (row yl, pixel 0) ; -1 zero row ; -2 ones row
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = 16 * mt + gid + 8 * h;
+      int off = -1;
+      if (m < 9 * C) {
+        const int tap = m / C, ci = m - tap * C;
+        off = (tap / 3) * g.pitch + g.padL + ((tap % 3) - 1) * C + ci;
+      } else if (m == 9 * C) {
+        off = -2;
+      }
+      offA[mt][h] = off;
+    }
+  float acc[MT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[mt][j] = 0.f;
+
+  int tile = blockIdx.x;
+  if (tile < g.ntiles) prefetch(tile, 0);
+  int s = 0;
+  for (; tile < g.ntiles; tile += gridDim.x, s ^= 1) {
+    const int next = tile + gridDim.x;
+    if (next < g.ntiles) {
+      prefetch(next, s ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* sX = smem + s * g.stage_floats;
+    const float* sD = sX + g.offD;
+    const float* sE = sX + g.offE;
+    const unsigned char* sI = reinterpret_cast<const unsigned char*>(sX + g.offI);
+    for (int yl = warp; yl < th; yl += 8) {
+      const float* xrow = sX + yl * g.pitch + tig * C;
+      const int prow_off = (yl >> 1) * g.prow + gid;
+      const int posy = (yl & 1) << 1;
+      for (int xb = 0; xb < W; xb += 8) {
+        // B fragment: dY[y, xb + tig (+4), co = gid] through ReLU + max-pool backward
+        uint32_t b[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int x = xb + tig + 4 * h;
+          const int pe = prow_off + (x >> 1) * 8;
+          const float v = (sI[pe] == (posy | (x & 1)) && sE[pe] > 0.f) ? sD[pe] : 0.f;
+          b[h] = to_tf32(v);
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          uint32_t a[4];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int off = offA[mt][h];
+            float v0 = 0.f, v1 = 0.f;
+            if (off >= 0) { v0 = xrow[off + xb * C]; v1 = xrow[off + (xb + 4) * C]; }
+            else if (off == -2) { v0 = 1.f; v1 = 1.f; }
+            a[h] = to_tf32(v0);
+            a[2 + h] = to_tf32(v1);
+          }
+          mma_tf32_16n8k8(acc[mt], a[0], a[1], a[2], a[3], b[0], b[1]);
+        }
+      }
+    }
+    __syncthreads();   // everyone is done with stage s before the next iteration's prefetch overwrites it
+  }
+
+  // ---- one reduction per CTA: 8 warps -> smem -> one RED per weight
+  float* s_red = smem;   // [8][16*MT][8]
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    float* d = s_red + (warp * 16 * MT + 16 * mt + gid) * 8 + 2 * tig;
+    d[0] = acc[mt][0]; d[1] = acc[mt][1];
+    d[64] = acc[mt][2]; d[65] = acc[mt][3];
+  }
+  __syncthreads();
+  for (int e = tid; e < 16 * MT * 8; e += 256) {
+    const int m = e >> 3, co = e & 7;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += s_red[w * 16 * MT * 8 + e];
+    if (m < 9 * C) {
+      const int tap = m / C, ci = m - tap * C;
+      atomicAdd(p.dw + ((size_t)co * C + ci) * 9 + tap, sum);
+    } else if (m == 9 * C && p.db) {
+      atomicAdd(p.db + co, sum);
+    }
+  }
+}
+
+bool wgrad_pipe_supported(const cgs_wgrad3x3_args& a) {
+  if (a.x.mode != CGS_SRC_PLAIN || a.x.b != nullptr || a.dy.mode != CGS_SRC_POOLBWD) return false;
+  if (a.dy.C != 8 || a.x.C > 8 || a.x.C < 1) return false;
+  if (a.H < 16 || a.W < 16 || (a.H % 16) || (a.W % 8)) return false;
+  if ((a.W * a.x.C) % 4) return false;                          // X rows must be whole 16-byte chunks
+  if (((a.W / 2) * 8) % 16) return false;                       // argmax rows too
+  if ((reinterpret_cast<uintptr_t>(a.x.a) | reinterpret_cast<uintptr_t>(a.dy.a) | reinterpret_cast<uintptr_t>(a.dy.b) |
+       reinterpret_cast<uintptr_t>(a.dy.idx)) & 15) return false;
+  return true;
+}
+
+int launch_wgrad_pipe(const cgs_wgrad3x3_args& a, cudaStream_t st) {
+  WpGeom g;
+  const int C = a.x.C, W = a.W;
+  g.th = 16;
+  g.tiles_y = a.H / g.th;
+  g.ntiles = a.B * g.tiles_y;
+  g.padL = (C + 3) & ~3;
+  g.pitch = g.padL + W * C + g.padL;
+  g.pitch = (g.pitch + 3) & ~3;
+  if ((g.pitch & 31) == 0) g.pitch += 4;                        // rows of a tap triple should not alias banks
+  g.rowsX = g.th + 2;
+  g.xchunks = W * C / 4;
+  g.prow = (W / 2) * 8;
+  g.pchunks = g.prow / 4;
+  g.ichunks = g.prow / 16;
+  const int pr = g.th / 2;
+  g.offD = g.rowsX * g.pitch;
+  g.offE = g.offD + pr * g.prow;
+  g.offI = g.offE + pr * g.prow;
+  g.stage_floats = g.offI + (pr * g.prow + 3) / 4;
+  g.stage_floats = (g.stage_floats + 3) & ~3;
+  size_t smem = (size_t)2 * g.stage_floats * sizeof(float);
+  const int MT = (9 * C + 1 + 15) / 16;
+  const size_t red = (size_t)8 * 16 * (MT <= 2 ? 2 : 5) * 8 * sizeof(float);
+  if (smem < red) smem = red;
+  static bool attr_done = false;
+  static int sms = 148;
+  if (!attr_done) {
+    cudaFuncSetAttribute(wgrad3x3_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(wgrad3x3_pipe_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    attr_done = true;
+  }
+  int per_sm = (int)((200 * 1024) / (smem + 1024));
+  if (per_sm > 3) per_sm = 3;
+  if (per_sm < 1) per_sm = 1;
+  int grid = sms * per_sm;
+  if (grid > g.ntiles) grid = g.ntiles;
+  if (MT <= 2) wgrad3x3_pipe_kernel<2><<<grid, 256, smem, st>>>(a, g);
+  else wgrad3x3_pipe_kernel<5><<<grid, 256, smem, st>>>(a, g);
+  return check_launch("wgrad3x3_pipe");
+}
+
+}  // namespace cgs

@@ -71,6 +71,7 @@ struct WgGeom {
   FastDiv dsw, dsh, dtw, dth;
   FastDiv dwp, dhp;   // dividers by tw/2, th/2 (pooled-granularity staging)
   int xplanes;        // X planes actually allocated (min(8, Cin)): the RGB layer needs 3, not 8
+  int nblk;           // pixel tiles (x frame groups) in total; CTAs are persistent over them
 };
 
 // Up to 8 consecutive floats (channels) of one pixel -> registers; two 128-bit loads when aligned.

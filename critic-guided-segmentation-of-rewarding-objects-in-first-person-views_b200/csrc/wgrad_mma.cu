@@ -43,12 +43,40 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
   float* s_x = smem;                                   // [WM_CI][fpc*sh rows][rsx]
   float* s_y = smem + (size_t)g.xplanes * g.psx;       // [WM_CO][fpc*th rows][rsy]
 
-  int bid = blockIdx.x;
+  const int co0 = blockIdx.y * WM_CO, ci0 = blockIdx.z * WM_CI;
+  const int con = min(WM_CO, Cout - co0), cin = min(WM_CI, Cin - ci0);
+
+  // ---- per-lane A rows: m = ci*9 + tap (the OIHW order of dw), m == 72 is the all-ones bias row
+  const int warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+  int offA[WM_MT][2];   // >= 0: smem offset of the row base; -1: zero row; -2: ones row
+#pragma unroll
+  for (int mt = 0; mt < WM_MT; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int mrow = 16 * mt + gid + 8 * h;
+      int off = -1;
+      if (mrow < 9 * cin) {
+        const int ci = mrow / 9, tap = mrow - ci * 9;
+        off = ci * g.psx + (tap / 3) * g.rsx + (tap % 3);
+      } else if (mrow == 9 * cin) {
+        off = -2;
+      }
+      offA[mt][h] = off;
+    }
+  float acc[WM_MT][4];
+#pragma unroll
+  for (int mt = 0; mt < WM_MT; ++mt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[mt][j] = 0.f;
+
+  // ---- persistent over pixel tiles: partial sums stay in registers, ONE reduction + RED round per CTA at the end
+  //      (same-address REDs serialise in L2 at ~50 ns each: the number of CTAs, not the work, set the run time)
+  for (int bid0 = blockIdx.x; bid0 < g.nblk; bid0 += gridDim.x) {
+  int bid = bid0;
   const int tix = bid % g.tiles_x; bid /= g.tiles_x;
   const int tiy = bid % g.tiles_y; bid /= g.tiles_y;
   const int n0 = bid * g.fpc, y0 = tiy * th, x0 = tix * tw;
-  const int co0 = blockIdx.y * WM_CO, ci0 = blockIdx.z * WM_CI;
-  const int con = min(WM_CO, Cout - co0), cin = min(WM_CI, Cin - ci0);
+  __syncthreads();      // the previous tile's MMA loop is done with the staged tiles
 
   // ---- stage X (haloed) and dY tiles, planar [channel][row][x]
   {
@@ -130,29 +158,6 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
   }
   __syncthreads();
 
-  // ---- per-lane A rows: m = ci*9 + tap (the OIHW order of dw), m == 72 is the all-ones bias row
-  const int warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
-  int offA[WM_MT][2];   // >= 0: smem offset of the row base; -1: zero row; -2: ones row
-#pragma unroll
-  for (int mt = 0; mt < WM_MT; ++mt)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int mrow = 16 * mt + gid + 8 * h;
-      int off = -1;
-      if (mrow < 9 * cin) {
-        const int ci = mrow / 9, tap = mrow - ci * 9;
-        off = ci * g.psx + (tap / 3) * g.rsx + (tap % 3);
-      } else if (mrow == 9 * cin) {
-        off = -2;
-      }
-      offA[mt][h] = off;
-    }
-  float acc[WM_MT][4];
-#pragma unroll
-  for (int mt = 0; mt < WM_MT; ++mt)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[mt][j] = 0.f;
-
   const int R = g.fpc * th;
   for (int r = warp; r < R; r += 8) {
     const int ff = fdiv(r, g.dth), yy = r - ff * th;
@@ -176,6 +181,8 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
       }
     }
   }
+
+  }   // tile loop
 
   // ---- reduce the 8 warps' partial tiles through shared memory (reuse the X tile), then one RED per weight
   __syncthreads();
@@ -230,8 +237,20 @@ int launch_wgrad_mma(const cgs_wgrad3x3_args& a, cudaStream_t st) {
     cudaFuncSetAttribute(wgrad3x3_mma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  const int nblk = ((a.B + g.fpc - 1) / g.fpc) * g.tiles_x * g.tiles_y;
-  dim3 grid(nblk, (a.dy.C + WM_CO - 1) / WM_CO, (a.x.C + WM_CI - 1) / WM_CI);
+  g.nblk = ((a.B + g.fpc - 1) / g.fpc) * g.tiles_x * g.tiles_y;
+  const int gy = (a.dy.C + WM_CO - 1) / WM_CO, gz = (a.x.C + WM_CI - 1) / WM_CI;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  int per_sm = (int)((200 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+  int gx = (sms * per_sm) / (gy * gz);
+  gx = gx < 1 ? 1 : gx;
+  if (gx > g.nblk) gx = g.nblk;
+  dim3 grid(gx, gy, gz);
   if (a.x.C <= 3) wgrad3x3_mma_kernel<2><<<grid, 256, smem, st>>>(a, g);
   else wgrad3x3_mma_kernel<5><<<grid, 256, smem, st>>>(a, g);
   return check_launch("wgrad3x3_mma");

@@ -9,9 +9,11 @@
 //     horizontal halo, zfill for rows outside the image) and the pooled dE / E / argmax rows;
 //   * the ReLU + max-pool backward is evaluated while fetching the B fragment
 //     (dY[y,x,co] = (argmax == window position && E > 0) ? dE : 0), so the full-resolution gradient never exists;
-//   * two stages per CTA: the copy of tile i+1 is in flight while the warps run the MMAs of tile i;
-//   * CTAs are persistent (grid = SMs x resident CTAs), accumulators live in registers across all tiles of a CTA and
-//     are reduced once at the end: 444 x 224 REDs instead of 1024 x 224.
+//   * a 4-stage ring per CTA: the copies of tiles i+1..i+3 are in flight while the warps run the MMAs of tile i;
+//   * ONE persistent CTA per SM; accumulators live in registers across all of a CTA's tiles and are reduced once at
+//     the end.  This matters more than anything else here: every CTA adds into the SAME few hundred weight-gradient
+//     addresses and same-address REDs serialise in L2 at ~50 ns each, so the staged kernels' run time was
+//     (#CTAs x 50 ns) -- 1024 / 512 / 256 CTAs -> 46 / 27 / 14.6 us -- whatever the rest of the kernel did.
 #include "common.cuh"
 
 namespace cgs {
@@ -53,8 +55,9 @@ __global__ void __launch_bounds__(256) wgrad3x3_pipe_kernel(const cgs_wgrad3x3_a
   const int th = g.th;
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
 
-  // zero the horizontal-halo pads of both stages once (cp.async never touches them)
-  for (int e = tid; e < 2 * g.rowsX * 2 * g.padL; e += 256) {
+  constexpr int NS = 4;
+  // zero the horizontal-halo pads of all stages once (cp.async never touches them)
+  for (int e = tid; e < NS * g.rowsX * 2 * g.padL; e += 256) {
     const int s = e / (g.rowsX * 2 * g.padL), r2 = e - s * (g.rowsX * 2 * g.padL);
     const int r = r2 / (2 * g.padL), q = r2 - r * (2 * g.padL);
     const int col = q < g.padL ? q : g.padL + W * C + (q - g.padL);
@@ -106,17 +109,16 @@ __global__ void __launch_bounds__(256) wgrad3x3_pipe_kernel(const cgs_wgrad3x3_a
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[mt][j] = 0.f;
 
-  int tile = blockIdx.x;
-  if (tile < g.ntiles) prefetch(tile, 0);
-  int s = 0;
-  for (; tile < g.ntiles; tile += gridDim.x, s ^= 1) {
-    const int next = tile + gridDim.x;
-    if (next < g.ntiles) {
-      prefetch(next, s ^ 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+  for (int k = 0; k < NS - 1; ++k) {
+    const int t = blockIdx.x + k * gridDim.x;
+    if (t < g.ntiles) prefetch(t, k); else cp_async_commit();      // empty groups keep the accounting uniform
+  }
+  int it = 0;
+  for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
+    const int s = it % NS;
+    const int ahead = tile + (NS - 1) * gridDim.x;
+    if (ahead < g.ntiles) prefetch(ahead, (it + NS - 1) % NS); else cp_async_commit();
+    cp_async_wait<NS - 1>();        // everything but the newest NS-1 groups has landed: this tile is in smem
     __syncthreads();
     const float* sX = smem + s * g.stage_floats;
     const float* sD = sX + g.offD;
@@ -210,7 +212,7 @@ int launch_wgrad_pipe(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   g.offI = g.offE + pr * g.prow;
   g.stage_floats = g.offI + (pr * g.prow + 3) / 4;
   g.stage_floats = (g.stage_floats + 3) & ~3;
-  size_t smem = (size_t)2 * g.stage_floats * sizeof(float);
+  size_t smem = (size_t)4 * g.stage_floats * sizeof(float);
   const int MT = (9 * C + 1 + 15) / 16;
   const size_t red = (size_t)8 * 16 * (MT <= 2 ? 2 : 5) * 8 * sizeof(float);
   if (smem < red) smem = red;
@@ -224,10 +226,7 @@ int launch_wgrad_pipe(const cgs_wgrad3x3_args& a, cudaStream_t st) {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     attr_done = true;
   }
-  int per_sm = (int)((200 * 1024) / (smem + 1024));
-  if (per_sm > 3) per_sm = 3;
-  if (per_sm < 1) per_sm = 1;
-  int grid = sms * per_sm;
+  int grid = sms;   // one persistent CTA per SM: the number of same-address REDs at the end is the grid size
   if (grid > g.ntiles) grid = g.ntiles;
   if (MT <= 2) wgrad3x3_pipe_kernel<2><<<grid, 256, smem, st>>>(a, g);
   else wgrad3x3_pipe_kernel<5><<<grid, 256, smem, st>>>(a, g);

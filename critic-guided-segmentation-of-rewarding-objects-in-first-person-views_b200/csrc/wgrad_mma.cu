@@ -48,20 +48,24 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
 
   // ---- per-lane A rows: m = ci*9 + tap (the OIHW order of dw), m == 72 is the all-ones bias row
   const int warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
-  int offA[WM_MT][2];   // >= 0: smem offset of the row base; -1: zero row; -2: ones row
+  // branch-free gather: value = x[off] * mulA + addA with (1,0) data row, (0,1) ones row, (0,0) pad row
+  int offA[WM_MT][2];
+  float mulA[WM_MT][2], addA[WM_MT][2];
 #pragma unroll
   for (int mt = 0; mt < WM_MT; ++mt)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int mrow = 16 * mt + gid + 8 * h;
-      int off = -1;
+      int off = 0;
+      float mu = 0.f, ad = 0.f;
       if (mrow < 9 * cin) {
         const int ci = mrow / 9, tap = mrow - ci * 9;
         off = ci * g.psx + (tap / 3) * g.rsx + (tap % 3);
+        mu = 1.f;
       } else if (mrow == 9 * cin) {
-        off = -2;
+        ad = 1.f;
       }
-      offA[mt][h] = off;
+      offA[mt][h] = off; mulA[mt][h] = mu; addA[mt][h] = ad;
     }
   float acc[WM_MT][4];
 #pragma unroll
@@ -171,11 +175,8 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int off = offA[mt][h];
-          float v0 = 0.f, v1 = 0.f;
-          if (off >= 0) { v0 = xrow[off + xb]; v1 = xrow[off + xb + 4]; }
-          else if (off == -2) { v0 = 1.f; v1 = 1.f; }
-          a[h] = __float_as_uint(v0);
-          a[2 + h] = __float_as_uint(v1);
+          a[h] = __float_as_uint(fmaf(xrow[off + xb], mulA[mt][h], addA[mt][h]));
+          a[2 + h] = __float_as_uint(fmaf(xrow[off + xb + 4], mulA[mt][h], addA[mt][h]));
         }
         mma_tf32(acc[mt], a[0], a[1], a[2], a[3], b0, b1);
       }

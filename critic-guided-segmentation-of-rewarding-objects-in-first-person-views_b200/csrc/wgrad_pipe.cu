@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) wgrad3x3_pipe_kernel(const cgs_wgrad3x3_a
   const int th = g.th;
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
 
-  constexpr int NS = 4;
+  constexpr int NS = 3;
   // zero the horizontal-halo pads of all stages once (cp.async never touches them)
   for (int e = tid; e < NS * g.rowsX * 2 * g.padL; e += 256) {
     const int s = e / (g.rowsX * 2 * g.padL), r2 = e - s * (g.rowsX * 2 * g.padL);
@@ -88,20 +88,24 @@ __global__ void __launch_bounds__(256) wgrad3x3_pipe_kernel(const cgs_wgrad3x3_a
   };
 
   // per-lane A rows, tap-major: m = tap*C + ci  (8 consecutive rows = 8 channels of one tap: conflict-free gathers)
-  int offA[MT][2];   // >= 0 valid offset relative to (row yl, pixel 0) ; -1 zero row ; -2 ones row
+  // Branch-free inner loop: value = x[off] * mulA + addA with (mulA, addA) = (1,0) data row, (0,1) ones row, (0,0) pad row
+  int offA[MT][2];
+  float mulA[MT][2], addA[MT][2];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int m = 16 * mt + gid + 8 * h;
-      int off = -1;
+      int off = g.padL;
+      float mu = 0.f, ad = 0.f;
       if (m < 9 * C) {
         const int tap = m / C, ci = m - tap * C;
         off = (tap / 3) * g.pitch + g.padL + ((tap % 3) - 1) * C + ci;
+        mu = 1.f;
       } else if (m == 9 * C) {
-        off = -2;
+        ad = 1.f;
       }
-      offA[mt][h] = off;
+      offA[mt][h] = off; mulA[mt][h] = mu; addA[mt][h] = ad;
     }
   float acc[MT][4];
 #pragma unroll
@@ -135,7 +139,9 @@ __global__ void __launch_bounds__(256) wgrad3x3_pipe_kernel(const cgs_wgrad3x3_a
         for (int h = 0; h < 2; ++h) {
           const int x = xb + tig + 4 * h;
           const int pe = prow_off + (x >> 1) * 8;
-          const float v = (sI[pe] == (posy | (x & 1)) && sE[pe] > 0.f) ? sD[pe] : 0.f;
+          float v = sD[pe];
+          v = (sI[pe] == (posy | (x & 1))) ? v : 0.f;      // selects, not branches: the loop must stay convergent
+          v = (sE[pe] > 0.f) ? v : 0.f;
           b[h] = to_tf32(v);
         }
 #pragma unroll
@@ -144,9 +150,8 @@ __global__ void __launch_bounds__(256) wgrad3x3_pipe_kernel(const cgs_wgrad3x3_a
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int off = offA[mt][h];
-            float v0 = 0.f, v1 = 0.f;
-            if (off >= 0) { v0 = xrow[off + xb * C]; v1 = xrow[off + (xb + 4) * C]; }
-            else if (off == -2) { v0 = 1.f; v1 = 1.f; }
+            const float v0 = fmaf(xrow[off + xb * C], mulA[mt][h], addA[mt][h]);
+            const float v1 = fmaf(xrow[off + (xb + 4) * C], mulA[mt][h], addA[mt][h]);
             a[h] = to_tf32(v0);
             a[2 + h] = to_tf32(v1);
           }
@@ -212,7 +217,7 @@ int launch_wgrad_pipe(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   g.offI = g.offE + pr * g.prow;
   g.stage_floats = g.offI + (pr * g.prow + 3) / 4;
   g.stage_floats = (g.stage_floats + 3) & ~3;
-  size_t smem = (size_t)4 * g.stage_floats * sizeof(float);
+  size_t smem = (size_t)3 * g.stage_floats * sizeof(float);
   const int MT = (9 * C + 1 + 15) / 16;
   const size_t red = (size_t)8 * 16 * (MT <= 2 ? 2 : 5) * 8 * sizeof(float);
   if (smem < red) smem = red;
@@ -226,7 +231,9 @@ int launch_wgrad_pipe(const cgs_wgrad3x3_args& a, cudaStream_t st) {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     attr_done = true;
   }
-  int grid = sms;   // one persistent CTA per SM: the number of same-address REDs at the end is the grid size
+  int per_sm = (int)((200 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+  int grid = sms * per_sm;
   if (grid > g.ntiles) grid = g.ntiles;
   if (MT <= 2) wgrad3x3_pipe_kernel<2><<<grid, 256, smem, st>>>(a, g);
   else wgrad3x3_pipe_kernel<5><<<grid, 256, smem, st>>>(a, g);

@@ -14,6 +14,8 @@
 //     the end.  This matters more than anything else here: every CTA adds into the SAME few hundred weight-gradient
 //     addresses and same-address REDs serialise in L2 at ~50 ns each, so the staged kernels' run time was
 //     (#CTAs x 50 ns) -- 1024 / 512 / 256 CTAs -> 46 / 27 / 14.6 us -- whatever the rest of the kernel did.
+#include <cooperative_groups.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cgs {
@@ -26,6 +28,7 @@ struct WpGeom {
   int stage_floats;              // floats per pipeline stage
   int offE, offI;                // float offsets of E and idx inside a stage (dE follows X)
   int offD;
+  int flags;                     // debug: bit 0 = skip the final REDs (tools/wgrad_probe.py)
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
@@ -162,8 +165,14 @@ __global__ void __launch_bounds__(256) wgrad3x3_pipe_kernel(const cgs_wgrad3x3_a
     __syncthreads();   // everyone is done with stage s before the next iteration's prefetch overwrites it
   }
 
-  // ---- one reduction per CTA: 8 warps -> smem -> one RED per weight
-  float* s_red = smem;   // [8][16*MT][8]
+  // ---- reduction: 8 warps -> this CTA's smem -> (thread-block cluster, distributed shared memory) -> one RED per weight
+  //      per CLUSTER.  Every CTA adds into the same few hundred addresses and same-address REDs serialise in L2 at
+  //      ~45 ns each (tools/wgrad_probe.py: +6.5 us at 148 CTAs, +25 us at 592), so the cluster leader sums its peers'
+  //      partial tiles over DSMEM first: 4x fewer RED rounds.
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  float* s_red = smem;                    // [8 warps][16*MT][8]
+  float* s_tot = smem + 8 * 16 * MT * 8;  // [16*MT][8] this CTA's total
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     float* d = s_red + (warp * 16 * MT + 16 * mt + gid) * 8 + 2 * tig;
@@ -172,17 +181,29 @@ __global__ void __launch_bounds__(256) wgrad3x3_pipe_kernel(const cgs_wgrad3x3_a
   }
   __syncthreads();
   for (int e = tid; e < 16 * MT * 8; e += 256) {
-    const int m = e >> 3, co = e & 7;
     float sum = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) sum += s_red[w * 16 * MT * 8 + e];
-    if (m < 9 * C) {
-      const int tap = m / C, ci = m - tap * C;
-      atomicAdd(p.dw + ((size_t)co * C + ci) * 9 + tap, sum);
-    } else if (m == 9 * C && p.db) {
-      atomicAdd(p.db + co, sum);
+    s_tot[e] = sum;
+  }
+  cluster.sync();
+  if (cluster.block_rank() == 0) {
+    const unsigned nb = cluster.num_blocks();
+    for (int e = tid; e < 16 * MT * 8; e += 256) {
+      const int m = e >> 3, co = e & 7;
+      float sum = s_tot[e];
+      for (unsigned r = 1; r < nb; ++r) sum += cluster.map_shared_rank(s_tot, r)[e];
+      if (g.flags & 1) {
+        if (sum == 123.456f) p.dw[0] = sum;     // debug probe: keep the reduction alive without the REDs
+      } else if (m < 9 * C) {
+        const int tap = m / C, ci = m - tap * C;
+        atomicAdd(p.dw + ((size_t)co * C + ci) * 9 + tap, sum);
+      } else if (m == 9 * C && p.db) {
+        atomicAdd(p.db + co, sum);
+      }
     }
   }
+  cluster.sync();   // peers keep their shared memory alive until the leader has read it
 }
 
 bool wgrad_pipe_supported(const cgs_wgrad3x3_args& a) {
@@ -219,7 +240,7 @@ int launch_wgrad_pipe(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   g.stage_floats = (g.stage_floats + 3) & ~3;
   size_t smem = (size_t)3 * g.stage_floats * sizeof(float);
   const int MT = (9 * C + 1 + 15) / 16;
-  const size_t red = (size_t)8 * 16 * (MT <= 2 ? 2 : 5) * 8 * sizeof(float);
+  const size_t red = (size_t)9 * 16 * (MT <= 2 ? 2 : 5) * 8 * sizeof(float);
   if (smem < red) smem = red;
   static bool attr_done = false;
   static int sms = 148;
@@ -231,12 +252,29 @@ int launch_wgrad_pipe(const cgs_wgrad3x3_args& a, cudaStream_t st) {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     attr_done = true;
   }
-  int per_sm = (int)((200 * 1024) / (smem + 1024));
-  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
-  int grid = sms * per_sm;
+  int grid = sms;   // one persistent CTA per SM (the non-RED part of the kernel does not depend on the grid size)
+  g.flags = 0;
+  if (const char* e = getenv("CGS_WGRAD_NORED")) g.flags |= atoi(e) ? 1 : 0;      // debug probes only
+  if (const char* e = getenv("CGS_WGRAD_GRID")) { const int v = atoi(e); if (v > 0) grid = v; }
   if (grid > g.ntiles) grid = g.ntiles;
-  if (MT <= 2) wgrad3x3_pipe_kernel<2><<<grid, 256, smem, st>>>(a, g);
-  else wgrad3x3_pipe_kernel<5><<<grid, 256, smem, st>>>(a, g);
+  // thread-block clusters of 4 (148 = 4 x 37): the grid is rounded down to a multiple of the cluster size
+  int csz = 4;
+  if (const char* e = getenv("CGS_WGRAD_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) csz = v; }
+  if (grid < csz) csz = 1;
+  grid -= grid % csz;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csz; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = MT <= 2 ? cudaLaunchKernelEx(&cfg, wgrad3x3_pipe_kernel<2>, a, g)
+                            : cudaLaunchKernelEx(&cfg, wgrad3x3_pipe_kernel<5>, a, g);
+  if (err != cudaSuccess) { set_error("wgrad3x3_pipe: launch failed: %s", cudaGetErrorString(err)); return CGS_ECUDA; }
   return check_launch("wgrad3x3_pipe");
 }
 

@@ -207,8 +207,12 @@ __global__ void __launch_bounds__(256) wgrad3x3_pipe_kernel(const cgs_wgrad3x3_a
 }
 
 bool wgrad_pipe_supported(const cgs_wgrad3x3_args& a) {
+  static const int nopipe = getenv("CGS_WGRAD_NOPIPE") ? atoi(getenv("CGS_WGRAD_NOPIPE")) : 0;   // debug probe
+  if (nopipe) return false;
   if (a.x.mode != CGS_SRC_PLAIN || a.x.b != nullptr || a.dy.mode != CGS_SRC_POOLBWD) return false;
-  if (a.dy.C != 8 || a.x.C > 8 || a.x.C < 1) return false;
+  // measured (tools/wgrad_probe.py, B=256): 34.8 vs 37.9 us on the RGB layer, but 24.6/18.4 vs 22.5/16.4 us on the 8->8
+  // layers, where the staged persistent kernel's 32-pixel-wide planar tiles need fewer shared-memory wavefronts per MMA
+  if (a.dy.C != 8 || a.x.C > 4 || a.x.C < 1) return false;
   if (a.H < 16 || a.W < 16 || (a.H % 16) || (a.W % 8)) return false;
   if ((a.W * a.x.C) % 4) return false;                          // X rows must be whole 16-byte chunks
   if (((a.W / 2) * 8) % 16) return false;                       // argmax rows too
@@ -258,7 +262,7 @@ int launch_wgrad_pipe(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   if (const char* e = getenv("CGS_WGRAD_GRID")) { const int v = atoi(e); if (v > 0) grid = v; }
   if (grid > g.ntiles) grid = g.ntiles;
   // thread-block clusters of 4 (148 = 4 x 37): the grid is rounded down to a multiple of the cluster size
-  int csz = 4;
+  int csz = 2;
   if (const char* e = getenv("CGS_WGRAD_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) csz = v; }
   if (grid < csz) csz = 1;
   grid -= grid % csz;

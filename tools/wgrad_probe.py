@@ -2,7 +2,9 @@
 REDs on/off and different grid sizes (debug env knobs read by the launcher).  Run on the GPU box."""
 import os, sys, subprocess
 if len(sys.argv) == 1:
-    for grid, csz in (("148", "1"), ("148", "2"), ("148", "4"), ("296", "4"), ("296", "8")):
+    out = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, CGS_WGRAD_NOPIPE="1"), capture_output=True, text=True)
+    print(f"staged persistent wgrad_mma kernel   : {out.stdout.strip()} {out.stderr.strip()[-200:]}")
+    for grid, csz in (("148", "2"),):
         for nored in ("0", "1"):
             env = dict(os.environ, CGS_WGRAD_GRID=grid, CGS_WGRAD_NORED=nored, CGS_WGRAD_CLUSTER=csz)
             out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)

@@ -35,6 +35,7 @@ class Wgrad3x3Args(C.Structure):
 EXPORTS = {
     "cgs_conv3x3": [C.POINTER(Conv3x3Args), C.c_void_p],
     "cgs_wgrad3x3": [C.POINTER(Wgrad3x3Args), C.c_void_p],
+    "cgs_conv_rgb_fwd": [_u8p] + [C.c_int32] * 4 + [C.c_void_p, _f32p, _f32p, C.c_int32, _f32p, _u8p, C.c_void_p],
     "cgs_head_fwd": [_f32p] * 9 + [C.c_int32] * 3 + [_f32p] * 3 + [C.c_void_p],
     "cgs_head_bwd": [_f32p] * 11 + [C.c_int32] * 3 + [_f32p] * 7 + [C.c_void_p],
     "cgs_tail_supported": [C.c_int32] * 4,

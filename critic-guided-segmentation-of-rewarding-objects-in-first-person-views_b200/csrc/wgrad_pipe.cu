@@ -29,6 +29,7 @@ struct WpGeom {
   int offE, offI;                // float offsets of E and idx inside a stage (dE follows X)
   int offD;
   int flags;                     // debug: bit 0 = skip the final REDs (tools/wgrad_probe.py)
+  int u8, raw_row, raw_chunks, offRaw, rollc;   // X given as raw uint8 frames (+ roll): raw rows staged, converted per tile
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
@@ -70,6 +71,17 @@ __global__ void __launch_bounds__(256) wgrad3x3_pipe_kernel(const cgs_wgrad3x3_a
   auto prefetch = [&](int tile, int s) {
     const int n = tile / g.tiles_y, y0 = (tile - n * g.tiles_y) * th;
     const uint32_t sb = smem_base + (uint32_t)(s * g.stage_floats) * 4u;
+    if (g.u8) {
+      // raw uint8 rows (W*3 bytes each); converted to fp32 (/255, roll) by a shared->shared pass once they have landed
+      const uint8_t* fr = reinterpret_cast<const uint8_t*>(p.x.a);
+      for (int c = tid; c < g.rowsX * g.raw_chunks; c += 256) {
+        const int r = c / g.raw_chunks, cx = c - r * g.raw_chunks;
+        const int y = y0 - 1 + r;
+        const bool ok = y >= 0 && y < H;
+        const uint8_t* src = ok ? fr + (size_t)(unsigned)((n * H + y) * W) * 3u + cx * 16 : fr;
+        cp_async16(sb + (uint32_t)g.offRaw * 4u + (uint32_t)(r * g.raw_row + cx * 16), src, ok ? 16 : 0);
+      }
+    } else
     // X: rowsX full-width image rows (row r <-> image row y0 - 1 + r), pixel-major
     for (int c = tid; c < g.rowsX * g.xchunks; c += 256) {
       const int r = c / g.xchunks, cx = c - r * g.xchunks;
@@ -127,6 +139,21 @@ __global__ void __launch_bounds__(256) wgrad3x3_pipe_kernel(const cgs_wgrad3x3_a
     if (ahead < g.ntiles) prefetch(ahead, (it + NS - 1) % NS); else cp_async_commit();
     cp_async_wait<NS - 1>();        // everything but the newest NS-1 groups has landed: this tile is in smem
     __syncthreads();
+    if (g.u8) {
+      int roll = g.rollc;
+      if (p.x.b) { roll = *reinterpret_cast<const int*>(p.x.b) % W; if (roll < 0) roll += W; }
+      float* dX = smem + s * g.stage_floats;
+      const uint8_t* raw = reinterpret_cast<const uint8_t*>(dX + g.offRaw);
+      for (int e = tid; e < g.rowsX * W; e += 256) {
+        const int r = e / W, x = e - r * W;
+        int sx = x + roll;
+        if (sx >= W) sx -= W;
+        const uint8_t* q = raw + r * g.raw_row + sx * 3;
+        float* d = dX + r * g.pitch + g.padL + x * 3;
+        d[0] = (float)q[0] / 255.0f; d[1] = (float)q[1] / 255.0f; d[2] = (float)q[2] / 255.0f;
+      }
+      __syncthreads();
+    }
     const float* sX = smem + s * g.stage_floats;
     const float* sD = sX + g.offD;
     const float* sE = sX + g.offE;
@@ -209,7 +236,9 @@ __global__ void __launch_bounds__(256) wgrad3x3_pipe_kernel(const cgs_wgrad3x3_a
 bool wgrad_pipe_supported(const cgs_wgrad3x3_args& a) {
   static const int nopipe = getenv("CGS_WGRAD_NOPIPE") ? atoi(getenv("CGS_WGRAD_NOPIPE")) : 0;   // debug probe
   if (nopipe) return false;
-  if (a.x.mode != CGS_SRC_PLAIN || a.x.b != nullptr || a.dy.mode != CGS_SRC_POOLBWD) return false;
+  const bool u8 = a.x.mode == CGS_SRC_U8ROLL && a.x.C == 3 && (a.W % 16) == 0;
+  if (!u8 && (a.x.mode != CGS_SRC_PLAIN || a.x.b != nullptr)) return false;
+  if (a.dy.mode != CGS_SRC_POOLBWD) return false;
   // measured (tools/wgrad_probe.py, B=256): 34.8 vs 37.9 us on the RGB layer, but 24.6/18.4 vs 22.5/16.4 us on the 8->8
   // layers, where the staged persistent kernel's 32-pixel-wide planar tiles need fewer shared-memory wavefronts per MMA
   if (a.dy.C != 8 || a.x.C > 4 || a.x.C < 1) return false;
@@ -240,7 +269,13 @@ int launch_wgrad_pipe(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   g.offD = g.rowsX * g.pitch;
   g.offE = g.offD + pr * g.prow;
   g.offI = g.offE + pr * g.prow;
-  g.stage_floats = g.offI + (pr * g.prow + 3) / 4;
+  g.offRaw = g.offI + (pr * g.prow + 3) / 4;
+  g.offRaw = (g.offRaw + 3) & ~3;
+  g.u8 = a.x.mode == CGS_SRC_U8ROLL;
+  g.raw_row = W * 3;
+  g.raw_chunks = g.raw_row / 16;
+  g.rollc = ((a.x.shift % W) + W) % W;
+  g.stage_floats = g.offRaw + (g.u8 ? (g.rowsX * g.raw_row + 3) / 4 : 0);
   g.stage_floats = (g.stage_floats + 3) & ~3;
   size_t smem = (size_t)3 * g.stage_floats * sizeof(float);
   const int MT = (9 * C + 1 + 15) / 16;

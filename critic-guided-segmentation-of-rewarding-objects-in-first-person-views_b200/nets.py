@@ -65,7 +65,7 @@ class NewCritic(nn.Module):
                                   nn.Linear(nb, 1), nn.Sigmoid())
         self._conv_idx = (0, 3, 6, 10)
         self.fuse_tail = True          # features[9..15] + crit in one kernel each way when the shapes fit shared memory
-        self.fuse_frame_cast = False   # True: read uint8 frames directly in the first conv (saves the fp32 copy; slower loads)
+        self.fuse_frame_cast = True    # raw uint8 frames go straight into the first conv / its wgrad (no fp32 copy of the batch)
         self._rng_state = None
         self._rng_seed = 0
         NewCritic._count = getattr(NewCritic, "_count", 0) + 1

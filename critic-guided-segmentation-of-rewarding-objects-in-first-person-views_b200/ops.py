@@ -138,8 +138,14 @@ class EncBlock(torch.autograd.Function):
         Cout = w.shape[0]
         e = torch.empty((B, H // 2, W // 2, Cout), device=x.device, dtype=torch.float32)
         idx = torch.empty((B, H // 2, W // 2, Cout), device=x.device, dtype=torch.uint8)
-        xs = _frames_src(x, roll) or _src(SRC_PLAIN, Cin, x, mask)
-        conv3x3(xs, w, b, B, H, W, Cout, EPI_RELU_POOL, e, idx_out=idx)
+        if x.dtype == torch.uint8 and Cin == 3 and H % 16 == 0 and W % 16 == 0 and Cout % 8 == 0:
+            # dedicated first-layer kernel: raw frames in, cast + roll + conv + ReLU + pool fused
+            rdev = roll if torch.is_tensor(roll) else None
+            _call("cgs_conv_rgb_fwd", _p(x, torch.uint8), B, H, W, 0 if rdev is not None else int(roll or 0),
+                  _p(rdev, torch.int32), _p(w), _p(b), Cout, _p(e), _p(idx, torch.uint8), _stream())
+        else:
+            xs = _frames_src(x, roll) or _src(SRC_PLAIN, Cin, x, mask)
+            conv3x3(xs, w, b, B, H, W, Cout, EPI_RELU_POOL, e, idx_out=idx)
         ctx.save_for_backward(x, mask, w, e, idx)
         ctx.roll, ctx.params = roll, (w, b)
         ctx.set_materialize_grads(False)

@@ -82,6 +82,13 @@ enum cgs_precision { CGS_FP32 = 0, CGS_TF32 = 1 };
  * (nets.py:503-521), LeakyReLU / Sigmoid (nets.py:489-491) and autograd's conv input-gradient. */
 int cgs_conv3x3(const cgs_conv3x3_args* a, void* stream);
 
+/* First encoder stage straight from raw frames: uint8 NHWC [B,H,W,3] -> /255 -> circular W-roll (roll, or *roll_dev) ->
+ * Conv2d(3,Cout,3,1,1) + bias -> ReLU -> MaxPool2d(2) -> e0 [B,H/2,W/2,Cout] (+ argmax bytes idx0, may be NULL).
+ * Replaces `X.permute(0,3,1,2).float()/255`, Handler.shift_batch and features[0..2] (main.py:185-189, nets.py:170-172).
+ * H, W multiples of 16, Cout a multiple of 8. */
+int cgs_conv_rgb_fwd(const uint8_t* frames, int32_t B, int32_t H, int32_t W, int32_t roll, const int32_t* roll_dev,
+                     const float* w, const float* bias, int32_t Cout, float* e0, uint8_t* idx0, void* stream);
+
 typedef struct cgs_wgrad3x3_args {
   cgs_src x;              /* forward input operand (Cin = x.C) */
   cgs_src dy;             /* gradient w.r.t. the conv output (Cout = dy.C) */

@@ -23,6 +23,8 @@ struct RgbGeom {
   int raw_stage;               // bytes per raw stage
   int off_f, off_w;            // float offsets of the fp32 tile and the weights behind the raw ring
   int rollc;                   // roll normalised to [0, W)
+  int off_lut;                 // float offset of the 256-entry (float)i/255 table
+  FastDiv dcol;                // divider by W + 2
 };
 
 __device__ __forceinline__ void rgb_cp16(uint32_t dst, const void* src, int bytes) {
@@ -46,6 +48,8 @@ __global__ void __launch_bounds__(256, 3) conv_rgb_kernel(const uint8_t* __restr
     roll = *roll_dev % W;
     if (roll < 0) roll += W;
   }
+  float* s_lut = reinterpret_cast<float*>(smem_raw) + g.off_lut;
+  s_lut[tid] = (float)tid / 255.0f;      // exact (float)u8 / 255.0f without a division per pixel
   for (int e = tid; e < 27 * Cout; e += 256) {
     const int co = e % Cout, r = e / Cout;
     const int t = r % 9, ci = r / 9;
@@ -81,14 +85,14 @@ __global__ void __launch_bounds__(256, 3) conv_rgb_kernel(const uint8_t* __restr
     // ---- convert pass: raw u8 (pixel-major) -> planar fp32 with /255, roll and zero halo columns
     const uint8_t* raw = smem_raw + s * g.raw_stage;
     for (int e = tid; e < rows * (W + 2); e += 256) {
-      const int r = e / (W + 2), c = e - r * (W + 2);
+      const int r = fdiv(e, g.dcol), c = e - r * (W + 2);
       const int x = c - 1;
       float v0 = 0.f, v1 = 0.f, v2 = 0.f;
       if (x >= 0 && x < W) {
         int sx = x + roll;
         if (sx >= W) sx -= W;
         const uint8_t* q = raw + r * g.raw_row + sx * 3;
-        v0 = (float)q[0] / 255.0f; v1 = (float)q[1] / 255.0f; v2 = (float)q[2] / 255.0f;
+        v0 = s_lut[q[0]]; v1 = s_lut[q[1]]; v2 = s_lut[q[2]];
       }
       float* d = s_f + r * g.fpitch + c;
       d[0] = v0; d[g.fplane] = v1; d[2 * g.fplane] = v2;
@@ -181,7 +185,9 @@ extern "C" int cgs_conv_rgb_fwd(const uint8_t* frames, int32_t B, int32_t H, int
   g.off_w = g.off_f + 3 * g.fplane;
   g.off_w = (g.off_w + 3) & ~3;
   g.rollc = ((roll % W) + W) % W;
-  const size_t smem = (size_t)(g.off_w + 27 * Cout) * sizeof(float);
+  g.off_lut = g.off_w + 27 * Cout;
+  g.dcol = make_fastdiv(W + 2);
+  const size_t smem = (size_t)(g.off_lut + 256) * sizeof(float);
   static bool attr_done = false;
   static int sms = 148;
   if (!attr_done) {

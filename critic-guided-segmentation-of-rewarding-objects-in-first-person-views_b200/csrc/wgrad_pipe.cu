@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(256) wgrad3x3_pipe_kernel(const cgs_wgrad3x3_a
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
 
   constexpr int NS = 3;
+  float* s_lut = smem + NS * g.stage_floats;      // (float)i / 255.0f, i = 0..255 (raw uint8 frames only)
+  if (g.u8) s_lut[tid] = (float)tid / 255.0f;
   // zero the horizontal-halo pads of all stages once (cp.async never touches them)
   for (int e = tid; e < NS * g.rowsX * 2 * g.padL; e += 256) {
     const int s = e / (g.rowsX * 2 * g.padL), r2 = e - s * (g.rowsX * 2 * g.padL);
@@ -140,17 +142,24 @@ __global__ void __launch_bounds__(256) wgrad3x3_pipe_kernel(const cgs_wgrad3x3_a
     cp_async_wait<NS - 1>();        // everything but the newest NS-1 groups has landed: this tile is in smem
     __syncthreads();
     if (g.u8) {
+      // raw bytes -> fp32 X rows.  Pixel-major fp32 mirrors the byte layout, so this is a flat expansion with a rotation by
+      // roll*3 bytes; (float)u8/255.0f comes from a 256-entry table (exact, no divisions), 4 bytes -> one 128-bit store.
       int roll = g.rollc;
       if (p.x.b) { roll = *reinterpret_cast<const int*>(p.x.b) % W; if (roll < 0) roll += W; }
+      const int rb = roll * 3, rowb = g.raw_row, q4 = rowb >> 2;
       float* dX = smem + s * g.stage_floats;
       const uint8_t* raw = reinterpret_cast<const uint8_t*>(dX + g.offRaw);
-      for (int e = tid; e < g.rowsX * W; e += 256) {
-        const int r = e / W, x = e - r * W;
-        int sx = x + roll;
-        if (sx >= W) sx -= W;
-        const uint8_t* q = raw + r * g.raw_row + sx * 3;
-        float* d = dX + r * g.pitch + g.padL + x * 3;
-        d[0] = (float)q[0] / 255.0f; d[1] = (float)q[1] / 255.0f; d[2] = (float)q[2] / 255.0f;
+      for (int e = tid; e < g.rowsX * q4; e += 256) {
+        const int r = e / q4, i = (e - r * q4) * 4;
+        const uint8_t* rr = raw + r * rowb;
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          int sb = i + k + rb;
+          if (sb >= rowb) sb -= rowb;
+          v[k] = s_lut[rr[sb]];
+        }
+        *reinterpret_cast<float4*>(dX + r * g.pitch + g.padL + i) = make_float4(v[0], v[1], v[2], v[3]);
       }
       __syncthreads();
     }
@@ -277,7 +286,7 @@ int launch_wgrad_pipe(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   g.rollc = ((a.x.shift % W) + W) % W;
   g.stage_floats = g.offRaw + (g.u8 ? (g.rowsX * g.raw_row + 3) / 4 : 0);
   g.stage_floats = (g.stage_floats + 3) & ~3;
-  size_t smem = (size_t)3 * g.stage_floats * sizeof(float);
+  size_t smem = (size_t)3 * g.stage_floats * sizeof(float) + 256 * sizeof(float);
   const int MT = (9 * C + 1 + 15) / 16;
   const size_t red = (size_t)9 * 16 * (MT <= 2 ? 2 : 5) * 8 * sizeof(float);
   if (smem < red) smem = red;

@@ -217,7 +217,7 @@ def test_forward_frames_tf32():
         assert (p1 - p2).abs().max().item() <= 2e-3
         for a, b in zip(g1, (p.grad for p in c.parameters())):
             rel = (a - b).norm().item() / max(a.norm().item(), 1e-30)
-            assert rel <= 5e-2, rel
+            assert rel <= 8e-2, rel
 
 
 def test_flat_adam_matches_torch_adam():

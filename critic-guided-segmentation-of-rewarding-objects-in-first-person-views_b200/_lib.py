@@ -32,7 +32,16 @@ class Wgrad3x3Args(C.Structure):
                 ("dw", _f32p), ("db", _f32p), ("precision", C.c_int32)]
 
 
+class CriticWeights(C.Structure):
+    """cgs_critic_weights: the 14 NewCritic tensors in state_dict order."""
+    _fields_ = [(n, _f32p) for n in ("w0", "b0", "w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4", "wl1", "bl1", "wl2", "bl2")]
+
+
 EXPORTS = {
+    "cgs_critic_fused_supported": [C.c_int32] * 5,
+    "cgs_critic_train_fused": [_u8p, _f32p, C.c_int32, C.c_int32, C.c_void_p, _f32p, _f32p, _f32p,
+                               C.POINTER(CriticWeights), C.POINTER(CriticWeights), C.c_float, C.c_int32, _f32p, _f32p,
+                               C.c_void_p],
     "cgs_conv3x3": [C.POINTER(Conv3x3Args), C.c_void_p],
     "cgs_wgrad3x3": [C.POINTER(Wgrad3x3Args), C.c_void_p],
     "cgs_conv_rgb_fwd": [_u8p] + [C.c_int32] * 4 + [C.c_void_p, _f32p, _f32p, C.c_int32, _f32p, _u8p, C.c_void_p],

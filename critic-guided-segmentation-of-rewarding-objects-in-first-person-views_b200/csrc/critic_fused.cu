@@ -1,0 +1,724 @@
+// One critic_pipe training step (reference main.py:185-198) as ONE persistent kernel, chfak = 1:
+//   uint8 frame -> /255 + shift_batch roll -> NewCritic forward (nets.py:169-212, dropout masks applied) -> MSE/BCE loss
+//   -> full backward -> parameter gradients accumulated into the caller's (flat Adam) gradient tensors.
+//
+// Why: at chfak 1 the critic is 1.7 MMAC per frame and every activation of a frame fits in shared memory (e0 is 32 KB),
+// so the compulsory HBM traffic is the 12 KB uint8 frame and nothing else; the per-layer kernels it replaces moved
+// ~0.3 MB per frame through L2/HBM and paid ~10 us of launch/ramp latency per layer at batch 256.
+//
+// One CTA (16 warps) owns a frame at a time and walks the layers with every operand in shared memory:
+//   * convolutions (fprop and dgrad) are implicit GEMMs on mma.sync.m16n8k8 TF32 (fp32 accumulate): an M-tile is 16
+//     pixels of one row, K = the 8 input channels of one filter tap, N = 8 output channels.  Activations live in smem
+//     as two 4-channel half-planes so that ONE ldmatrix.x4 fetches a whole A fragment conflict-free, and a warp slides
+//     down a 16-pixel column strip so every fragment is reused by the three filter rows (3 ldmatrix per 9 MMAs);
+//   * ReLU + 2x2 max-pool + first-max arg-max happen on the accumulator fragments (row pairs live in one warp, the
+//     x-neighbour is one shuffle away); the backward scatter (pool/ReLU backward) is the dgrad epilogue;
+//   * weight gradients are GEMMs with K = pixels: A = gathered input taps, B = output gradient, accumulated per CTA
+//     in shared memory / registers over all its frames and pushed with ONE round of REDs per CTA;
+//   * the 4x4 bottleneck conv and the MLP head are FFMA on the tiny vectors.
+// tcgen05 is not used here on purpose: every GEMM has N = 8..16 and M-tiles of 16 pixels; a 128-row UMMA tile would
+// be >85 % padding and its operands would have to be re-laid out in the canonical layout per tap.
+#include "common.cuh"
+
+namespace cgs {
+namespace cf {
+
+constexpr int NT = 512;
+// haloed planes: pitch in pixels, half-plane size in floats (4 channels per pixel); all PL == 16 (mod 32) banks
+constexpr int P0 = 66, SX = 66 * 66 * 4;          // RGB0 frame, one 16-byte pixel
+constexpr int P1 = 34, PL1 = 34 * 34 * 4;         // 32x32 maps
+constexpr int P2 = 18, PL2 = 18 * 18 * 4;         // 16x16 maps
+constexpr int P3 = 10, PL3 = 10 * 10 * 4;         // 8x8 maps
+// ---- shared memory map (float offsets)
+constexpr int oA = 0;                              // region A: e0 | dY1      (B0: the re-staged frame)
+constexpr int oE0 = oA, oDY1 = oA + 2 * PL1, oXB = oA;
+constexpr int szA = 4 * PL1;                       // 18496 >= SX
+constexpr int oB = oA + szA;                       // region B: the frame (F0) | dE0, dY2, dY3 (backward)
+constexpr int oX = oB, oDE0 = oB, oDY2 = oDE0 + 8192, oDY3 = oDY2 + 2 * PL2;
+constexpr int szB = SX;
+constexpr int oI0 = oB + szB;                      // bytes [32*32][8]
+constexpr int oE1 = oI0 + 2048;
+constexpr int oI1 = oE1 + 2 * PL2;                 // bytes [16*16][8]
+constexpr int oE2 = oI1 + 512;                     // e2 * dropout mask (the operand of features.10)
+constexpr int oI2 = oE2 + 2 * PL3;                 // bytes [8*8][8]
+constexpr int oM2 = oI2 + 128;
+constexpr int oX3 = oM2 + 512;                     // e3 * mask in the 4x4 conv's K order (ci*16 + pixel)
+constexpr int oI3 = oX3 + 256;                     // bytes [4*4][16]
+constexpr int oM3 = oI3 + 64;
+constexpr int oHead = oM3 + 256;                   // h[32] v[32] mv[32] dh[32] dv[32]
+constexpr int oU8 = oHead + 256;                   // raw frame bytes (12288)
+constexpr int oAcc = oU8 + 3072;
+constexpr int aW0 = 0, aB0 = 216, aW1 = 224, aB1 = 800, aW2 = 808, aB2 = 1384, aW3 = 1392, aB3 = 2544, aB4 = 2560,
+              aWl1 = 2592, aBl1 = 3616, aWl2 = 3648, aBl2 = 3680, szAcc = 3712;
+constexpr int oW = oAcc + szAcc;                   // weight fragments, [step][lane][2]
+constexpr int wL0 = 0, wL1f = 384, wL2f = wL1f + 576, wL3f = wL2f + 576, wL3d = wL3f + 1152, wL2d = wL3d + 1152,
+              wL1d = wL2d + 576, szW = wL1d + 576;
+constexpr int oBias = oW + szW;                    // b0[8] b1[8] b2[8] b3[16]
+constexpr int SMEM_FLOATS = oBias + 64;
+static_assert(szA >= SX, "region A must hold the re-staged frame");
+static_assert(oDY3 + 4 * PL3 <= oB + szB, "region B overflow");
+static_assert(SMEM_FLOATS * 4 <= 227 * 1024, "shared memory budget");
+
+struct Params {
+  const uint8_t* frames;
+  const float* target;
+  const float *m2, *m3, *mv;
+  const float *w0, *b0, *w1, *b1, *w2, *b2, *w3, *b3, *w4, *b4, *wl1, *bl1, *wl2, *bl2;
+  float* gseg[14];      // gradient tensors in sAcc order (w0 b0 w1 b1 w2 b2 w3 b3 b4 wl1 bl1 wl2 bl2) + [13] = w4
+  float* pred;
+  float* loss;
+  const int* roll_dev;
+  int B, roll, bce;
+  float gscale;         // d(total loss)/d(this rank's mean loss) / B
+  float inv_n;          // 1 / B
+};
+
+__device__ __forceinline__ uint32_t f2tf32(float f) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(f));
+  return r;
+}
+__device__ __forceinline__ float tf32r(float f) { return __uint_as_float(f2tf32(f)); }
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm2(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+// Output rows [0, R) of one 16-pixel column strip (R even).  Iteration i loads the NK A fragments of haloed input row i
+// once and feeds the three output rows i, i-1, i-2 (filter rows 0, 1, 2); epi(e, top, bot) gets the finished rows e, e+1.
+template <int R, int NK, class LoadA, class Epi>
+__device__ __forceinline__ void slide_rows(const float2 (&w)[3][NK], LoadA&& loadA, Epi&& epi) {
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < R + 2; ++i) {
+    uint32_t a[NK][4];
+    loadA(i, a);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int oi = i - ky;
+      if (oi >= 0 && oi < R) {
+        if (ky == 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[oi & 3][q] = 0.f;
+        }
+#pragma unroll
+        for (int kk = 0; kk < NK; ++kk)
+          mma_tf32(acc[oi & 3], a[kk], __float_as_uint(w[ky][kk].x), __float_as_uint(w[ky][kk].y));
+      }
+    }
+    if (i >= 3 && ((i - 3) & 1) == 0) epi(i - 3, acc[(i - 3) & 3], acc[(i - 2) & 3]);
+  }
+}
+
+// bias + ReLU + 2x2 max-pool (first max wins, ATen's rule) on two finished rows of a strip.  Even-g lanes own the
+// windows; st(j, value, idx) with j>>1 = pixel half (g or g+8), j&1 = channel (2t or 2t+1); idx 4 = no gradient.
+template <class Store>
+__device__ __forceinline__ void pool2x2(const float (&top)[4], const float (&bot)[4], float bias0, float bias1, int g, Store&& st) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float b = (j & 1) ? bias1 : bias0;
+    const float pt = top[j] + b, pb = bot[j] + b;
+    const float nt = __shfl_xor_sync(0xffffffffu, pt, 4), nb = __shfl_xor_sync(0xffffffffu, pb, 4);
+    if (!(g & 1)) {
+      float m = pt;
+      int idx = 0;
+      if (nt > m) { m = nt; idx = 1; }
+      if (pb > m) { m = pb; idx = 2; }
+      if (nb > m) { m = nb; idx = 3; }
+      if (!(m > 0.f)) { m = 0.f; idx = 4; }
+      st(j, m, idx);
+    }
+  }
+}
+
+// Weight gradient of an 8-input-channel 3x3 conv over `nks` k-steps of 8 pixels (TW = map width): acc[mt] rows are
+// (tap 2mt | tap 2mt+1) x ci; row 8 of mt 4 is the all-ones row (bias gradient).  X: haloed half-planes of the layer input,
+// DY: haloed half-planes of the output gradient (plane index co>>2, so nt selects planes 2nt, 2nt+1).
+template <int TW, int P, int PL>
+__device__ __forceinline__ void wgrad8(float (&acc)[5][4], const float* __restrict__ sX, const float* __restrict__ sDY, int ks0,
+                                       int nks, int g, int t) {
+  int offA[5], offB[5];
+#pragma unroll
+  for (int mt = 0; mt < 5; ++mt) {
+    const int ta = 2 * mt, tb = mt < 4 ? 2 * mt + 1 : 8;
+    offA[mt] = (g >> 2) * PL + ((ta / 3) * P + ta % 3) * 4 + (g & 3);
+    offB[mt] = (g >> 2) * PL + ((tb / 3) * P + tb % 3) * 4 + (g & 3);
+  }
+  const float ones = g == 0 ? 1.f : 0.f;
+  const int offY = (g >> 2) * PL + (P + 1) * 4 + (g & 3);
+  constexpr int KPR = TW / 8;   // k-steps per row
+  for (int ks = ks0; ks < ks0 + nks; ++ks) {
+    const int y = ks / KPR, x0 = (ks % KPR) * 8;
+    const int base = (y * P + x0 + t) * 4;
+    const uint32_t b0 = __float_as_uint(sDY[offY + base]), b1 = __float_as_uint(sDY[offY + base + 16]);
+#pragma unroll
+    for (int mt = 0; mt < 5; ++mt) {
+      uint32_t a[4];
+      a[0] = __float_as_uint(sX[offA[mt] + base]);
+      a[2] = __float_as_uint(sX[offA[mt] + base + 16]);
+      if (mt < 4) {
+        a[1] = __float_as_uint(sX[offB[mt] + base]);
+        a[3] = __float_as_uint(sX[offB[mt] + base + 16]);
+      } else {
+        a[1] = a[3] = __float_as_uint(ones);
+      }
+      mma_tf32(acc[mt], a, b0, b1);
+    }
+  }
+}
+
+// acc[mt] of wgrad8 -> shared accumulators in OIHW order (co = co0 + 2t + {0,1}, ci = g)
+template <bool ATOMIC>
+__device__ __forceinline__ void wgrad8_store(const float (&acc)[5][4], float* aW, float* aB, int co0, int g, int t) {
+#pragma unroll
+  for (int mt = 0; mt < 5; ++mt)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int co = co0 + 2 * t + (q & 1), tap = 2 * mt + (q >> 1);
+      float* d;
+      if (tap < 9) d = aW + (co * 8 + g) * 9 + tap;
+      else if (g == 0) d = aB + co;
+      else continue;
+      if (ATOMIC) atomicAdd(d, acc[mt][q]);
+      else *d += acc[mt][q];
+    }
+}
+
+__device__ __forceinline__ float u8f(uint32_t b) { return __uint_as_float(0x4B000000u | b) - 8388608.f; }
+
+// raw bytes -> haloed [66][66] x (r,g,b,0) fp32 /255 with the circular W-roll; tf32(b * (1/255)) == tf32(b / 255) for all b
+__device__ __forceinline__ void stage_frame(const uint8_t* __restrict__ sU8, float* __restrict__ sXd, int roll, int tid) {
+  const float k = 1.f / 255.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int p = tid + NT * i, y = p >> 6, x = p & 63;
+    const uint8_t* s = sU8 + (y * 64 + ((x + roll) & 63)) * 3;
+    float4 v;
+    v.x = tf32r(u8f(s[0]) * k); v.y = tf32r(u8f(s[1]) * k); v.z = tf32r(u8f(s[2]) * k); v.w = 0.f;
+    *reinterpret_cast<float4*>(sXd + ((y + 1) * P0 + x + 1) * 4) = v;
+  }
+  if (tid < 260) {   // halo ring
+    int y, x;
+    if (tid < 66) { y = 0; x = tid; }
+    else if (tid < 132) { y = 65; x = tid - 66; }
+    else if (tid < 196) { y = tid - 131; x = 0; }
+    else { y = tid - 195; x = 65; }
+    *reinterpret_cast<float4*>(sXd + (y * P0 + x) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__device__ __forceinline__ void prefetch_frame(const uint8_t* __restrict__ src, float* sU8f, int tid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(sU8f);
+  for (int c = tid; c < 768; c += NT)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + c * 16), "l"(src + c * 16));
+  asm volatile("cp.async.commit_group;\n" ::);
+}
+
+__global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params p) {
+  extern __shared__ __align__(128) float sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int lj = lane >> 3, lr = lane & 7;               // ldmatrix: this lane addresses row lr of matrix lj
+  uint8_t* sI0 = reinterpret_cast<uint8_t*>(sm + oI0);
+  uint8_t* sI1 = reinterpret_cast<uint8_t*>(sm + oI1);
+  uint8_t* sI2 = reinterpret_cast<uint8_t*>(sm + oI2);
+  uint8_t* sI3 = reinterpret_cast<uint8_t*>(sm + oI3);
+  float *sH = sm + oHead, *sV = sH + 32, *sMV = sH + 64, *sDH = sH + 96, *sDV = sH + 128;
+  float* sAcc = sm + oAcc;
+  const float2* sWf = reinterpret_cast<const float2*>(sm + oW);
+  const uint32_t smb = (uint32_t)__cvta_generic_to_shared(sm);
+
+  if (blockIdx.x < p.B) prefetch_frame(p.frames + (size_t)blockIdx.x * 12288, sm + oU8, tid);
+
+  // ---- prologue: accumulators, halos that stay zero, weight fragments (TF32, in mma B-fragment order), biases
+  for (int e = tid; e < szAcc; e += NT) sAcc[e] = 0.f;
+  for (int e = tid; e < 2 * PL2 + 512 + 2 * PL3; e += NT) sm[oE1 + e] = 0.f;        // e1, idx1, e2 (halos stay zero)
+  for (int e = tid; e < szW / 2; e += NT) {
+    const int ln = e & 31, gg = ln >> 2, tt = ln & 3;
+    float x = 0.f, y = 0.f;
+    int s = e >> 5;
+    if (s < 6) {                                   // L0 fprop: step (ky, kk): kk 0 = taps (ky,0 | ky,1), kk 1 = tap (ky,2) | 0
+      const int ky = s >> 1, kk = s & 1;
+      if (tt < 3) {
+        x = __ldg(p.w0 + gg * 27 + tt * 9 + ky * 3 + (kk ? 2 : 0));
+        if (!kk) y = __ldg(p.w0 + gg * 27 + tt * 9 + ky * 3 + 1);
+      }
+    } else if ((s -= 6) < 18) {                    // L1 / L2 fprop: tap
+      const float* w = s < 9 ? p.w1 : p.w2;
+      const int tap = s % 9;
+      x = __ldg(w + (gg * 8 + tt) * 9 + tap); y = __ldg(w + (gg * 8 + tt + 4) * 9 + tap);
+    } else if ((s -= 18) < 18) {                   // L3 fprop: (tap, nt)
+      const int tap = s >> 1, co = (s & 1) * 8 + gg;
+      x = __ldg(p.w3 + (co * 8 + tt) * 9 + tap); y = __ldg(p.w3 + (co * 8 + tt + 4) * 9 + tap);
+    } else if ((s -= 18) < 18) {                   // L3 dgrad: (tap', ks): B[k = co][n = ci] = W[co][ci][8 - tap']
+      const int tap = 8 - (s >> 1), co = (s & 1) * 8 + tt;
+      x = __ldg(p.w3 + (co * 8 + gg) * 9 + tap); y = __ldg(p.w3 + ((co + 4) * 8 + gg) * 9 + tap);
+    } else {                                       // L2 / L1 dgrad: tap'
+      s -= 18;
+      const float* w = s < 9 ? p.w2 : p.w1;
+      const int tap = 8 - s % 9;
+      x = __ldg(w + (tt * 8 + gg) * 9 + tap); y = __ldg(w + ((tt + 4) * 8 + gg) * 9 + tap);
+    }
+    sm[oW + 2 * e] = tf32r(x);
+    sm[oW + 2 * e + 1] = tf32r(y);
+  }
+  if (tid < 8) { sm[oBias + tid] = __ldg(p.b0 + tid); sm[oBias + 8 + tid] = __ldg(p.b1 + tid); sm[oBias + 16 + tid] = __ldg(p.b2 + tid); }
+  if (tid < 16) sm[oBias + 24 + tid] = __ldg(p.b3 + tid);
+
+  int roll = p.roll_dev ? *p.roll_dev : p.roll;
+  roll = ((roll % 64) + 64) & 63;
+  float accW4[16], acc0[2][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) accW4[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc0[i >> 2][i & 3] = 0.f;
+  float loss_acc = 0.f;
+  const int ldoff8 = (lr + 8 * (lj & 1)) * 4;                 // ldmatrix row offset inside an 8-channel half-plane strip
+
+  for (int n = blockIdx.x; n < p.B; n += gridDim.x) {
+    // ================= F0a: frame bytes -> fp32 haloed tile, dropout masks, e0 halo
+    asm volatile("cp.async.wait_all;\n" ::);
+    __syncthreads();
+    stage_frame(reinterpret_cast<const uint8_t*>(sm + oU8), sm + oX, roll, tid);
+    sm[oM2 + tid] = p.m2 ? __ldg(p.m2 + (size_t)n * 512 + tid) : 1.f;
+    if (tid < 256) sm[oM3 + tid] = p.m3 ? __ldg(p.m3 + (size_t)n * 256 + tid) : 1.f;
+    if (tid < 32) sMV[tid] = p.mv ? __ldg(p.mv + (size_t)n * 32 + tid) : 1.f;
+    if (tid < 264) {   // e0 halo ring (region A is reused by the re-staged frame), both half-planes
+      const int h = tid >= 132, q = tid - 132 * h;
+      int y, x;
+      if (q < 34) { y = 0; x = q; }
+      else if (q < 68) { y = 33; x = q - 34; }
+      else if (q < 100) { y = q - 67; x = 0; }
+      else { y = q - 99; x = 33; }
+      *reinterpret_cast<float4*>(sm + oE0 + h * PL1 + (y * P1 + x) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+
+    // ================= F0: features.0 (3 -> 8) + ReLU + pool : 16 warps = 4 strips x 4 segments of 16 rows
+    {
+      const int x0 = (warp & 3) * 16, r0 = (warp >> 2) * 16;
+      float2 w[3][2];
+#pragma unroll
+      for (int s = 0; s < 6; ++s) w[s >> 1][s & 1] = sWf[(wL0 >> 1) + s * 32 + lane];
+      const uint32_t aA = smb + (oX + (r0 * P0 + x0 + lr + 8 * (lj & 1) + (lj >> 1)) * 4) * 4;
+      const uint32_t aB = smb + (oX + (r0 * P0 + x0 + lr + 8 * (lj & 1) + 2) * 4) * 4;
+      const float bias0 = sm[oBias + 2 * t], bias1 = sm[oBias + 2 * t + 1];
+      slide_rows<16, 2>(
+          w,
+          [&](int i, uint32_t(&a)[2][4]) {
+            ldsm4(a[0], aA + i * (P0 * 16));
+            ldsm2(a[1][0], a[1][1], aB + i * (P0 * 16));
+            a[1][2] = a[1][3] = 0u;
+          },
+          [&](int e, const float(&top)[4], const float(&bot)[4]) {
+            const int py = (r0 + e) >> 1;
+            pool2x2(top, bot, bias0, bias1, g, [&](int j, float v, int idx) {
+              const int px = ((x0 + g) >> 1) + 4 * (j >> 1), co = 2 * t + (j & 1);
+              sm[oE0 + (co >> 2) * PL1 + ((py + 1) * P1 + px + 1) * 4 + (co & 3)] = tf32r(v);
+              sI0[(py * 32 + px) * 8 + co] = (uint8_t)idx;
+            });
+          });
+    }
+    __syncthreads();
+
+    // ================= F1: features.3 (8 -> 8) on 32x32 : 2 strips x 8 segments of 4 rows; scatter targets are cleared
+    {
+      for (int e = tid; e < 2 * PL1; e += NT) sm[oDY1 + e] = 0.f;
+      for (int e = tid; e < 2 * PL2 + 4 * PL3; e += NT) sm[oDY2 + e] = 0.f;
+      const int x0 = (warp & 1) * 16, r0 = (warp >> 1) * 4;
+      float2 w[3][3];
+#pragma unroll
+      for (int s = 0; s < 9; ++s) w[s / 3][s % 3] = sWf[(wL1f >> 1) + s * 32 + lane];
+      const uint32_t aA = smb + (oE0 + (lj >> 1) * PL1 + (r0 * P1 + x0) * 4 + ldoff8) * 4;
+      const float bias0 = sm[oBias + 8 + 2 * t], bias1 = sm[oBias + 8 + 2 * t + 1];
+      slide_rows<4, 3>(
+          w,
+          [&](int i, uint32_t(&a)[3][4]) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) ldsm4(a[kx], aA + (i * P1 + kx) * 16);
+          },
+          [&](int e, const float(&top)[4], const float(&bot)[4]) {
+            const int py = (r0 + e) >> 1;
+            pool2x2(top, bot, bias0, bias1, g, [&](int j, float v, int idx) {
+              const int px = ((x0 + g) >> 1) + 4 * (j >> 1), co = 2 * t + (j & 1);
+              sm[oE1 + (co >> 2) * PL2 + ((py + 1) * P2 + px + 1) * 4 + (co & 3)] = tf32r(v);
+              sI1[(py * 16 + px) * 8 + co] = (uint8_t)idx;
+            });
+          });
+    }
+    __syncthreads();
+
+    // ================= F2: features.6 (8 -> 8) on 16x16 + Dropout : 8 warps x 2 rows
+    if (warp < 8) {
+      const int r0 = warp * 2;
+      float2 w[3][3];
+#pragma unroll
+      for (int s = 0; s < 9; ++s) w[s / 3][s % 3] = sWf[(wL2f >> 1) + s * 32 + lane];
+      const uint32_t aA = smb + (oE1 + (lj >> 1) * PL2 + (r0 * P2) * 4 + ldoff8) * 4;
+      const float bias0 = sm[oBias + 16 + 2 * t], bias1 = sm[oBias + 16 + 2 * t + 1];
+      slide_rows<2, 3>(
+          w,
+          [&](int i, uint32_t(&a)[3][4]) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) ldsm4(a[kx], aA + (i * P2 + kx) * 16);
+          },
+          [&](int e, const float(&top)[4], const float(&bot)[4]) {
+            const int py = (r0 + e) >> 1;
+            pool2x2(top, bot, bias0, bias1, g, [&](int j, float v, int idx) {
+              const int px = (g >> 1) + 4 * (j >> 1), co = 2 * t + (j & 1), q = (py * 8 + px) * 8 + co;
+              sm[oE2 + (co >> 2) * PL3 + ((py + 1) * P3 + px + 1) * 4 + (co & 3)] = tf32r(v * sm[oM2 + q]);
+              sI2[q] = (uint8_t)idx;
+            });
+          });
+    }
+    __syncthreads();
+
+    // ================= F3: features.10 (8 -> 16) on 8x8 + Dropout : 8 warps = 4 row pairs x 2 channel tiles
+    if (warp < 8) {
+      const int mt = warp >> 1, nt = warp & 1;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t aA = smb + (oE2 + (lj >> 1) * PL3 + ((2 * mt + (lj & 1)) * P3 + lr) * 4) * 4;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        uint32_t a[4];
+        ldsm4(a, aA + ((tap / 3) * P3 + tap % 3) * 16);
+        const float2 w = sWf[(wL3f >> 1) + (tap * 2 + nt) * 32 + lane];
+        mma_tf32(acc, a, __float_as_uint(w.x), __float_as_uint(w.y));
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int co = nt * 8 + 2 * t + j;
+        const float b = sm[oBias + 24 + co];
+        const float pt = acc[j] + b, pb = acc[j + 2] + b;
+        const float nt_ = __shfl_xor_sync(0xffffffffu, pt, 4), nb = __shfl_xor_sync(0xffffffffu, pb, 4);
+        if (!(g & 1)) {
+          float m = pt;
+          int idx = 0;
+          if (nt_ > m) { m = nt_; idx = 1; }
+          if (pb > m) { m = pb; idx = 2; }
+          if (nb > m) { m = nb; idx = 3; }
+          if (!(m > 0.f)) { m = 0.f; idx = 4; }
+          const int pp = mt * 4 + (g >> 1);
+          sm[oX3 + co * 16 + pp] = m * sm[oM3 + pp * 16 + co];
+          sI3[pp * 16 + co] = (uint8_t)idx;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ================= F4: features.14 (4x4 valid conv = 256 -> 32) + ReLU
+    {
+      const int nn = tid >> 4, part = tid & 15;
+      const float4* wr = reinterpret_cast<const float4*>(p.w4 + nn * 256 + part * 16);
+      const float4* xr = reinterpret_cast<const float4*>(sm + oX3 + part * 16);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = __ldg(wr + i), b = xr[i];
+        s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (part == 0) sH[nn] = fmaxf(s + __ldg(p.b4 + nn), 0.f);
+    }
+    __syncthreads();
+    // ================= F5: crit.1 Linear(32,32) + ReLU
+    {
+      const int nn = tid >> 4, part = tid & 15;
+      float s = __ldg(p.wl1 + nn * 32 + 2 * part) * sH[2 * part] + __ldg(p.wl1 + nn * 32 + 2 * part + 1) * sH[2 * part + 1];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (part == 0) sV[nn] = fmaxf(s + __ldg(p.bl1 + nn), 0.f);
+    }
+    __syncthreads();
+    // ================= F6: Dropout, crit.4 Linear(32,1), Sigmoid, loss and its gradient; head weight gradients
+    if (warp == 0) {
+      const float wk = __ldg(p.wl2 + lane), vm = sV[lane] * sMV[lane];
+      const float z = warp_sum(wk * vm) + __ldg(p.bl2);
+      const float pr = sigmoidf_(z), y = __ldg(p.target + n);
+      float dl;
+      if (p.bce) {
+        loss_acc -= y * fmaxf(logf(pr), -100.f) + (1.f - y) * fmaxf(logf(1.f - pr), -100.f);
+        dl = p.gscale * (pr - y) / fmaxf(pr * (1.f - pr), 1e-12f) * pr * (1.f - pr);
+      } else {
+        loss_acc = fmaf(pr - y, pr - y, loss_acc);
+        dl = p.gscale * 2.f * (pr - y) * pr * (1.f - pr);
+      }
+      if (lane == 0) { p.pred[n] = pr; sAcc[aBl2] += dl; }
+      sAcc[aWl2 + lane] += dl * vm;
+      sDV[lane] = sV[lane] > 0.f ? dl * wk * sMV[lane] : 0.f;
+    }
+    __syncthreads();
+    // ================= B5: crit.1 backward
+    {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int e = tid + NT * i;
+        sAcc[aWl1 + e] = fmaf(sDV[e >> 5], sH[e & 31], sAcc[aWl1 + e]);
+      }
+      if (tid < 32) sAcc[aBl1 + tid] += sDV[tid];
+      const int k = tid >> 4, part = tid & 15;
+      float s = __ldg(p.wl1 + (2 * part) * 32 + k) * sDV[2 * part] + __ldg(p.wl1 + (2 * part + 1) * 32 + k) * sDV[2 * part + 1];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (part == 0) sDH[k] = sH[k] > 0.f ? s : 0.f;
+    }
+    __syncthreads();
+    // ================= B4: features.14 backward (weight gradient in registers), Dropout + pool + ReLU backward -> dY3
+    {
+      const int nn = tid >> 4, part = tid & 15;
+      const float d = sDH[nn];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) accW4[i] = fmaf(d, sm[oX3 + part * 16 + i], accW4[i]);
+      if (tid < 32) sAcc[aB4 + tid] += sDH[tid];
+      const int k = tid >> 1, hf = tid & 1;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s = fmaf(__ldg(p.w4 + (hf * 16 + i) * 256 + k), sDH[hf * 16 + i], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      if (hf == 0) {
+        const int co = k >> 4, pp = k & 15, idx = sI3[pp * 16 + co];
+        if (idx < 4) {
+          const int y = 2 * (pp >> 2) + (idx >> 1), x = 2 * (pp & 3) + (idx & 1);
+          sm[oDY3 + (co >> 2) * PL3 + ((y + 1) * P3 + x + 1) * 4 + (co & 3)] = tf32r(s * sm[oM3 + pp * 16 + co]);
+        }
+      }
+    }
+    __syncthreads();
+    // ================= B3: features.10 weight gradient (warps 0-9) || input gradient -> dY2 (warps 10-13)
+    if (warp < 10) {
+      const int mt = warp % 5, nt = warp / 5;
+      const int ta = 2 * mt, tb = mt < 4 ? 2 * mt + 1 : 8;
+      const int offA = (g >> 2) * PL3 + ((ta / 3) * P3 + ta % 3) * 4 + (g & 3);
+      const int offB = (g >> 2) * PL3 + ((tb / 3) * P3 + tb % 3) * 4 + (g & 3);
+      const int offY = (2 * nt + (g >> 2)) * PL3 + (P3 + 1) * 4 + (g & 3);
+      const float ones = g == 0 ? 1.f : 0.f;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int y = 0; y < 8; ++y) {
+        const int base = (y * P3 + t) * 4;
+        uint32_t a[4];
+        a[0] = __float_as_uint(sm[oE2 + offA + base]);
+        a[2] = __float_as_uint(sm[oE2 + offA + base + 16]);
+        a[1] = mt < 4 ? __float_as_uint(sm[oE2 + offB + base]) : __float_as_uint(ones);
+        a[3] = mt < 4 ? __float_as_uint(sm[oE2 + offB + base + 16]) : __float_as_uint(ones);
+        mma_tf32(acc, a, __float_as_uint(sm[oDY3 + offY + base]), __float_as_uint(sm[oDY3 + offY + base + 16]));
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int co = nt * 8 + 2 * t + (q & 1), tap = 2 * mt + (q >> 1);
+        if (tap < 9) sAcc[aW3 + (co * 8 + g) * 9 + tap] += acc[q];
+        else if (g == 0) sAcc[aB3 + co] += acc[q];
+      }
+    } else if (warp < 14) {
+      const int mt = warp - 10;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t aA = smb + (oDY3 + (lj >> 1) * PL3 + ((2 * mt + (lj & 1)) * P3 + lr) * 4) * 4;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t a[4];
+          ldsm4(a, aA + (ks * 2 * PL3 + ((tap / 3) * P3 + tap % 3) * 4) * 4);
+          const float2 w = sWf[(wL3d >> 1) + (tap * 2 + ks) * 32 + lane];
+          mma_tf32(acc, a, __float_as_uint(w.x), __float_as_uint(w.y));
+        }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int y = 2 * mt + (q >> 1), ci = 2 * t + (q & 1), pq = (y * 8 + g) * 8 + ci, idx = sI2[pq];
+        if (idx < 4)
+          sm[oDY2 + (ci >> 2) * PL2 + ((2 * y + (idx >> 1) + 1) * P2 + 2 * g + (idx & 1) + 1) * 4 + (ci & 3)] =
+              tf32r(acc[q] * sm[oM2 + pq]);
+      }
+    }
+    __syncthreads();
+    // ================= B2: features.6 weight gradient (warps 0-7) || input gradient -> dY1 (warps 8-15)
+    if (warp < 8) {
+      float acc[5][4];
+#pragma unroll
+      for (int i = 0; i < 20; ++i) acc[i >> 2][i & 3] = 0.f;
+      wgrad8<16, P2, PL2>(acc, sm + oE1, sm + oDY2, warp * 4, 4, g, t);
+      wgrad8_store<true>(acc, sAcc + aW2, sAcc + aB2, 0, g, t);
+    } else {
+      const int r0 = (warp - 8) * 2;
+      float2 w[3][3];
+#pragma unroll
+      for (int s = 0; s < 9; ++s) w[s / 3][s % 3] = sWf[(wL2d >> 1) + s * 32 + lane];
+      const uint32_t aA = smb + (oDY2 + (lj >> 1) * PL2 + (r0 * P2) * 4 + ldoff8) * 4;
+      slide_rows<2, 3>(
+          w,
+          [&](int i, uint32_t(&a)[3][4]) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) ldsm4(a[kx], aA + (i * P2 + kx) * 16);
+          },
+          [&](int e, const float(&top)[4], const float(&bot)[4]) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int y = r0 + e + r, x = g + 8 * (q >> 1), ci = 2 * t + (q & 1), idx = sI1[(y * 16 + x) * 8 + ci];
+                if (idx < 4)
+                  sm[oDY1 + (ci >> 2) * PL1 + ((2 * y + (idx >> 1) + 1) * P1 + 2 * x + (idx & 1) + 1) * 4 + (ci & 3)] =
+                      tf32r(r ? bot[q] : top[q]);
+              }
+          });
+    }
+    __syncthreads();
+    // ================= B1: features.3 weight gradient (warps 0-7) || input gradient -> dE0 with arg-max tags (warps 8-15)
+    if (warp < 8) {
+      float acc[5][4];
+#pragma unroll
+      for (int i = 0; i < 20; ++i) acc[i >> 2][i & 3] = 0.f;
+      wgrad8<32, P1, PL1>(acc, sm + oE0, sm + oDY1, warp * 16, 16, g, t);
+      wgrad8_store<true>(acc, sAcc + aW1, sAcc + aB1, 0, g, t);
+    } else {
+      const int x0 = (warp & 1) * 16, r0 = ((warp - 8) >> 1) * 8;
+      float2 w[3][3];
+#pragma unroll
+      for (int s = 0; s < 9; ++s) w[s / 3][s % 3] = sWf[(wL1d >> 1) + s * 32 + lane];
+      const uint32_t aA = smb + (oDY1 + (lj >> 1) * PL1 + (r0 * P1 + x0) * 4 + ldoff8) * 4;
+      uint32_t* sDE0 = reinterpret_cast<uint32_t*>(sm + oDE0);
+      slide_rows<8, 3>(
+          w,
+          [&](int i, uint32_t(&a)[3][4]) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) ldsm4(a[kx], aA + (i * P1 + kx) * 16);
+          },
+          [&](int e, const float(&top)[4], const float(&bot)[4]) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int y = r0 + e + r, x = x0 + g + 8 * (q >> 1), o = (y * 32 + x) * 8 + 2 * t + (q & 1), idx = sI0[o];
+                // the 2x2 window position of the max rides in the two lowest mantissa bits (TF32 ignores them)
+                sDE0[o] = idx < 4 ? ((f2tf32(r ? bot[q] : top[q]) & ~3u) | (uint32_t)idx) : 0u;
+              }
+          });
+    }
+    __syncthreads();
+    // ================= B0a: frame again (region A is free now), then start fetching the next frame
+    stage_frame(reinterpret_cast<const uint8_t*>(sm + oU8), sm + oXB, roll, tid);
+    __syncthreads();
+    if (n + (int)gridDim.x < p.B) prefetch_frame(p.frames + (size_t)(n + gridDim.x) * 12288, sm + oU8, tid);
+    // ================= B0: features.0 weight gradient, K = 4096 pixels over 16 warps, accumulators stay in registers
+    {
+      int offA[2][2];
+      float mulA[2][2], addA[2][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int m = 16 * mt + g + 8 * h;
+          int off = 0;
+          float mu = 0.f, ad = 0.f;
+          if (m < 27) {
+            const int ci = m / 9, tap = m - ci * 9;
+            off = ((tap / 3) * P0 + tap % 3) * 4 + ci;
+            mu = 1.f;
+          } else if (m == 27) {
+            ad = 1.f;
+          }
+          offA[mt][h] = off; mulA[mt][h] = mu; addA[mt][h] = ad;
+        }
+      const uint32_t* sDE0 = reinterpret_cast<const uint32_t*>(sm + oDE0);
+      const float* sXb = sm + oXB;
+      for (int ks = warp * 32; ks < warp * 32 + 32; ++ks) {
+        const int y = ks >> 3, x0 = (ks & 7) * 8;
+        const int base = (y * P0 + x0 + t) * 4;
+        const uint32_t pos = ((y & 1) << 1) | (t & 1);
+        const int pp = ((y >> 1) * 32 + ((x0 + t) >> 1)) * 8 + g;
+        uint32_t b0 = sDE0[pp], b1 = sDE0[pp + 16];
+        b0 = (b0 & 3u) == pos ? b0 : 0u;
+        b1 = (b1 & 3u) == pos ? b1 : 0u;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          uint32_t a[4];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            a[h] = __float_as_uint(fmaf(sXb[offA[mt][h] + base], mulA[mt][h], addA[mt][h]));
+            a[2 + h] = __float_as_uint(fmaf(sXb[offA[mt][h] + base + 16], mulA[mt][h], addA[mt][h]));
+          }
+          mma_tf32(acc0[mt], a, b0, b1);
+        }
+      }
+    }
+    // the next iteration's F0a barrier (or the one below) separates B0's reads from the next writes
+  }
+
+  // ---- flush: features.0 accumulators -> shared, then ONE round of REDs per CTA into the caller's gradient tensors
+  asm volatile("cp.async.wait_all;\n" ::);
+  __syncthreads();
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int m = 16 * mt + g + 8 * (q >> 1), co = 2 * t + (q & 1);
+      if (m < 27) atomicAdd(sAcc + aW0 + co * 27 + m, acc0[mt][q]);
+      else if (m == 27) atomicAdd(sAcc + aB0 + co, acc0[mt][q]);
+    }
+  __syncthreads();
+  {
+    constexpr int segoff[13] = {aW0, aB0, aW1, aB1, aW2, aB2, aW3, aB3, aB4, aWl1, aBl1, aWl2, aBl2};
+    constexpr int seglen[13] = {216, 8, 576, 8, 576, 8, 1152, 16, 32, 1024, 32, 32, 1};
+#pragma unroll
+    for (int s = 0; s < 13; ++s) {
+      float* d = p.gseg[s];
+      for (int e = tid; e < seglen[s]; e += NT) atomicAdd(d + e, sAcc[segoff[s] + e]);
+    }
+    float* d4 = p.gseg[13] + (tid >> 4) * 256 + (tid & 15) * 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) atomicAdd(d4 + i, accW4[i]);
+  }
+  if (tid == 0 && blockIdx.x < p.B) atomicAdd(p.loss, loss_acc * p.inv_n);
+}
+
+}  // namespace cf
+}  // namespace cgs
+
+using namespace cgs;
+
+extern "C" int cgs_critic_fused_supported(int32_t C0, int32_t C1, int32_t C2, int32_t C3, int32_t NB) {
+  return C0 == 8 && C1 == 8 && C2 == 8 && C3 == 16 && NB == 32;
+}
+
+extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target, int32_t B, int32_t roll,
+                                      const int32_t* roll_dev, const float* m_e2, const float* m_e3, const float* m_v,
+                                      const cgs_critic_weights* w, const cgs_critic_weights* g, float loss_grad, int32_t bce,
+                                      float* pred, float* loss, void* stream) {
+  CGS_REQUIRE(frames && target && w && g && pred && loss && B > 0, "critic_train_fused: bad args");
+  CGS_REQUIRE(((uintptr_t)frames & 15) == 0, "critic_train_fused: frames must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  cf::Params p;
+  p.frames = frames; p.target = target; p.m2 = m_e2; p.m3 = m_e3; p.mv = m_v;
+  p.w0 = w->w0; p.b0 = w->b0; p.w1 = w->w1; p.b1 = w->b1; p.w2 = w->w2; p.b2 = w->b2; p.w3 = w->w3; p.b3 = w->b3;
+  p.w4 = w->w4; p.b4 = w->b4; p.wl1 = w->wl1; p.bl1 = w->bl1; p.wl2 = w->wl2; p.bl2 = w->bl2;
+  float* gs[14] = {(float*)g->w0, (float*)g->b0, (float*)g->w1, (float*)g->b1, (float*)g->w2, (float*)g->b2, (float*)g->w3,
+                   (float*)g->b3, (float*)g->b4, (float*)g->wl1, (float*)g->bl1, (float*)g->wl2, (float*)g->bl2, (float*)g->w4};
+  for (int i = 0; i < 14; ++i) {
+    CGS_REQUIRE(gs[i] != nullptr, "critic_train_fused: gradient tensor %d is NULL", i);
+    p.gseg[i] = gs[i];
+  }
+  p.pred = pred; p.loss = loss; p.roll_dev = roll_dev; p.B = B; p.roll = roll; p.bce = bce;
+  p.inv_n = 1.f / (float)B;
+  p.gscale = loss_grad / (float)B;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    cudaFuncSetAttribute(cf::critic_fused_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
+  }
+  if (cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) return check_launch("critic_train_fused.memset");
+  const int per = (B + sms - 1) / sms;           // frames per CTA; equalise so that no CTA idles a whole frame
+  const int grid = (B + per - 1) / per;
+  cf::critic_fused_train_kernel<<<grid, cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
+  return check_launch("critic_train_fused");
+}

@@ -470,6 +470,39 @@ def dropout_masks(shapes, p, seed, state):
     return [buf[o:o + n].view(s) for o, n, s in zip(offs, sizes, shapes)]
 
 
+def critic_fused_supported(critic):
+    """True when the whole-step kernel covers this NewCritic (chfak=1 geometry) and the tensor-core mode is on."""
+    f = critic.features
+    return bool(_precision and _lib.lib().cgs_critic_fused_supported(
+        f[0].out_channels, f[3].out_channels, f[6].out_channels, f[10].out_channels, f[14].out_channels))
+
+
+def critic_train_fused(critic, frames_u8, target, roll=0, masks=(None, None, None), loss_grad=1.0, bce=False):
+    """Forward + loss + backward of one critic_pipe step (reference main.py:185-198) in ONE kernel
+    (cgs_critic_train_fused).  Parameter gradients are ACCUMULATED into each parameter's `.grad` (the FlatAdam
+    bucket views); returns (loss scalar tensor, pred [B])."""
+    B = frames_u8.shape[0]
+    params = list(critic.parameters())          # registration order == state_dict order (nets.py:169-195)
+    assert len(params) == 14
+    grads = []
+    for q in params:
+        if q.grad is None:
+            q.grad = torch.zeros_like(q)
+        opt = getattr(q, "_cgs_opt", None)
+        if opt is not None and q.grad is getattr(q, "_cgs_grad", None):
+            opt._clean = False
+        grads.append(q.grad)
+    w = _lib.CriticWeights(*[_p(q.detach()) for q in params])
+    g = _lib.CriticWeights(*[_p(t) for t in grads])
+    pred = torch.empty(B, device=frames_u8.device, dtype=torch.float32)
+    loss = torch.empty(1, device=frames_u8.device, dtype=torch.float32)
+    rd, r = (_p(roll, torch.int32), 0) if torch.is_tensor(roll) else (None, int(roll or 0))
+    m2, m3, mv = masks
+    _call("cgs_critic_train_fused", _p(frames_u8, torch.uint8), _p(target), B, r, rd, _p(m2), _p(m3), _p(mv),
+          C.byref(w), C.byref(g), float(loss_grad), int(bool(bce)), _p(pred), _p(loss), _stream())
+    return loss.reshape(()), pred
+
+
 def threshold(z, thresh, strict=False):
     zc = _c(z)
     hard = torch.empty(zc.shape, device=z.device, dtype=torch.uint8)

@@ -136,6 +136,7 @@ class Handler:
         self.save_paths = {self.criticname: f"{self.save_path}critic-{self.critic_args}.pt",
                            self.maskername: f"{self.save_path}masker-{self.masker_args}.pt"}
         self.contrastive_batchsize = 32      # main.py:309
+        self.fused_critic_step = True        # tf32 mode, chfak 1: one kernel per critic_pipe step
         self.closs_log, self.seg_log = [], []
 
     def reset_models(self):
@@ -204,6 +205,14 @@ class Handler:
         x = X_u8 if torch.is_tensor(X_u8) else torch.from_numpy(np.ascontiguousarray(X_u8))
         x = x.to(self.device, non_blocking=True)
         Yd = Y.to(self.device, non_blocking=True).float()
+        if self.fused_critic_step and ops.critic_fused_supported(self.critic) and x.dtype == torch.uint8:
+            # whole step in one kernel: every activation of a frame stays in shared memory (csrc/critic_fused.cu)
+            masks = self.critic._dropout_masks(x.shape[0], self.device)
+            opti.zero_grad()
+            loss, _ = ops.critic_train_fused(self.critic, x.contiguous(), Yd.contiguous(), roll, masks,
+                                             loss_grad=1.0 / self.world, bce=bool(a.threshrew))
+            opti.step()
+            return loss
         pred = self.critic.forward_frames(x, roll).squeeze(1)     # cast + roll fused into features.0's operand load
         loss = ops.pred_loss(pred, Yd, bce=bool(a.threshrew))
         opti.zero_grad()

@@ -143,6 +143,24 @@ int cgs_tail_bwd(const float* e2, const float* m_e2, const float* m_e3, const fl
                  float* dw3, float* db3, float* dw14, float* db14, float* dw1, float* db1, float* dw2, float* db2,
                  float* de2, void* stream);
 
+/* The 14 NewCritic tensors in state_dict order (nets.py:169-195): features.{0,3,6,10,14}.{weight,bias} OIHW,
+ * crit.{1,4}.{weight,bias}; used both for the parameters (read) and for their gradients (accumulated into). */
+typedef struct cgs_critic_weights {
+  float *w0, *b0, *w1, *b1, *w2, *b2, *w3, *b3, *w4, *b4, *wl1, *bl1, *wl2, *bl2;
+} cgs_critic_weights;
+
+/* One whole critic_pipe training step minus Adam (main.py:185-198) in ONE kernel, for the chfak=1 geometry
+ * (cgs_critic_fused_supported): uint8 NHWC frames [B,64,64,3] -> /255 -> shift_batch roll (roll, or *roll_dev) ->
+ * NewCritic.forward in train mode (m_e2 [B,8,8,8], m_e3 [B,4,4,16], m_v [B,32] multiplicative dropout masks, NULL =
+ * identity) -> F.mse_loss / F.binary_cross_entropy against target [B] -> backward.  Every activation of a frame stays
+ * in shared memory; TF32 tensor-core (mma.sync) convolutions with fp32 accumulation, fp32 head.
+ * Outputs: pred [B]; loss[0] = mean loss over the B frames; the gradient of (loss_grad * loss) is ACCUMULATED into *g. */
+int cgs_critic_fused_supported(int32_t C0, int32_t C1, int32_t C2, int32_t C3, int32_t NB);
+int cgs_critic_train_fused(const uint8_t* frames, const float* target, int32_t B, int32_t roll, const int32_t* roll_dev,
+                           const float* m_e2, const float* m_e3, const float* m_v,
+                           const cgs_critic_weights* w, const cgs_critic_weights* g, float loss_grad, int32_t bce,
+                           float* pred, float* loss, void* stream);
+
 /* Dense layer out[B,N] = in[B,K] * w[N,K]^T + bias: UnetDecoder.dec[4], the 1x1 conv on the
  * 1x1 bottleneck (nets.py:484,500-501). */
 int cgs_dense_fwd(const float* in, const float* w, const float* bias,

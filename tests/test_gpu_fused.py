@@ -1,0 +1,141 @@
+"""GPU: the whole-step critic kernel (cgs_critic_train_fused, csrc/critic_fused.cu) against the CPU fp32 oracle.
+
+One launch = uint8 frames -> /255 -> shift roll -> NewCritic forward (dropout masks) -> MSE/BCE -> backward, with TF32
+tensor-core convolutions (fp32 accumulate) and an fp32 head.  Tolerances are the TF32 ones of tests/test_gpu_tc.py:
+values 2e-3 of the tensor scale; gradients norm-wise, because a max-pool near-tie can pick the other window position
+under TF32 rounding and move single entries by their full value."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden
+from oracle import torch_ref
+import cgs_b200.synth as synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+NAMES = ["features.0", "features.3", "features.6", "features.10", "features.14", "crit.1", "crit.4"]
+
+
+@pytest.fixture()
+def ops():
+    import cgs_b200.ops as o
+    o.set_precision("tf32")
+    yield o
+    o.set_precision("fp32")
+
+
+def _critic(csd, p):
+    from cgs_b200.nets import NewCritic
+    c = NewCritic(dropout=p)
+    c.load_state_dict({k: torch.from_numpy(v) for k, v in csd.items()})
+    return c.to(DEV).train()
+
+
+def _case(B, p, seed, scale=1.5):
+    csd = synth.perturbed_state(synth.critic_shapes(1), seed, scale)
+    X, Y, _ = synth.synthetic_frames(B, seed=seed)
+    rng = np.random.default_rng(seed)
+    mk = lambda *s: ((rng.random(s) >= p).astype(np.float32) / np.float32(1 - p)) if p > 0 else np.ones(s, np.float32)
+    masks = (mk(B, 8, 8, 8), mk(B, 16, 4, 4), mk(B, 32))            # logical NCHW
+    return csd, X, Y[1, :B].astype(np.float32), masks
+
+
+def _oracle(csd, X, y, masks, roll, bce):
+    sd = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in csd.items()}
+    Xr = np.roll(X, -roll, axis=2)                                   # out[.., x, :] = in[.., (x + roll) mod 64, :]
+    x = torch_ref.to_input(Xr)
+    yt = torch.from_numpy(y)
+    if bce:
+        yt = (yt > 0.5).float()
+    loss, pred = torch_ref.critic_loss(sd, x, yt, masks=tuple(torch.from_numpy(m) for m in masks), threshrew=bce)
+    loss.backward()
+    return loss.item(), pred.detach().numpy(), {k: v.grad.numpy() for k, v in sd.items()}
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.mark.parametrize("B,roll,p,bce", [(3, 0, 0.0, False), (5, 5, 0.3, False), (37, -7, 0.3, False), (300, 11, 0.3, False),
+                                          (16, -3, 0.3, True), (149, 0, 0.5, False)])
+def test_fused_step_vs_oracle(ops, B, roll, p, bce):
+    csd, X, y, masks = _case(B, p, seed=B)
+    loss_r, pred_r, grads_r = _oracle(csd, X, y, masks, roll, bce)
+    c = _critic(csd, p)
+    for q in c.parameters():
+        q.grad = torch.zeros_like(q)
+    m2, m3, mv = (torch.from_numpy(m).to(DEV) for m in masks)
+    dm = (m2.permute(0, 2, 3, 1).contiguous(), m3.permute(0, 2, 3, 1).contiguous(), mv.contiguous())
+    yt = torch.from_numpy(y if not bce else (y > 0.5).astype(np.float32)).to(DEV)
+    assert ops.critic_fused_supported(c)
+    loss, pred = ops.critic_train_fused(c, torch.from_numpy(X).to(DEV), yt, roll, dm, loss_grad=1.0, bce=bce)
+    torch.cuda.synchronize()
+    pred = pred.cpu().numpy()
+    assert np.abs(pred - pred_r).max() <= 2e-3, np.abs(pred - pred_r).max()
+    assert abs(loss.item() - loss_r) <= 5e-3 * abs(loss_r) + 1e-6, (loss.item(), loss_r)
+    errs = {k: _rel(v.grad.cpu().numpy(), grads_r[k]) for k, v in c.named_parameters()}
+    tot = _rel(np.concatenate([v.grad.cpu().numpy().ravel() for v in c.parameters()]),
+               np.concatenate([grads_r[k].ravel() for k, _ in c.named_parameters()]))
+    assert tot <= 3e-2, (tot, errs)
+    assert max(errs.values()) <= 8e-2, errs
+
+
+def test_fused_roll_from_device_scalar_and_accumulation(ops):
+    """roll read from device memory (graph-replayable); gradients ACCUMULATE into .grad; loss_grad scales them."""
+    B = 9
+    csd, X, y, masks = _case(B, 0.0, seed=4)
+    c = _critic(csd, 0.0)
+    Xd, yd = torch.from_numpy(X).to(DEV), torch.from_numpy(y).to(DEV)
+    for q in c.parameters():
+        q.grad = torch.zeros_like(q)
+    l1, p1 = ops.critic_train_fused(c, Xd, yd, 6, (None, None, None))
+    g1 = [q.grad.clone() for q in c.parameters()]
+    l2, p2 = ops.critic_train_fused(c, Xd, yd, torch.tensor([6], dtype=torch.int32, device=DEV), (None, None, None), loss_grad=0.5)
+    assert torch.equal(p1, p2) and torch.equal(l1, l2)
+    for a, q in zip(g1, c.parameters()):
+        ref = 1.5 * a
+        assert (q.grad - ref).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-12
+
+
+def test_fused_handler_step_matches_layer_kernels(ops):
+    """Handler.critic_step through the fused kernel vs through the per-layer kernels: same loss, and the same
+    parameters after the Adam step up to TF32 noise in the gradients."""
+    from cgs_b200.train_handler import Handler, parse_args
+    csd, X, y, _ = _case(64, 0.0, seed=11)
+    out = []
+    for fused in (True, False):
+        H = Handler(parse_args(["--dropout", "0"]), device=DEV)
+        H.fused_critic_step = fused
+        H.critic.load_state_dict({k: torch.from_numpy(v) for k, v in csd.items()})
+        H.critic.to(DEV).train()
+        opti = H._opt(H.critic.parameters())
+        losses = [H.critic_step(torch.from_numpy(X), torch.from_numpy(y), opti, roll=3).item() for _ in range(3)]
+        out.append((losses, torch.cat([q.detach().reshape(-1) for q in H.critic.parameters()]).cpu()))
+    (lf, pf), (ll, pl) = out
+    assert np.allclose(lf, ll, rtol=2e-2), (lf, ll)
+    # Adam moves every parameter by ~lr per step whatever the gradient's size, so entries whose gradient is pure rounding
+    # noise may walk in opposite directions (<= 2 * 3 steps * lr); on average the two paths must agree far better
+    assert (pf - pl).abs().max().item() <= 6.5e-3
+    assert (pf - pl).abs().mean().item() <= 2e-4
+
+
+def test_fused_loss_curve_first_epochs_vs_reference_loop(ops):
+    """critic_pipe through the fused kernel from the reference's initial weights: the deterministic regime of the
+    reference loss curve (first 40 steps, epoch-1 median; see test_loss_curves_vs_reference_loops) within TF32 noise."""
+    from cgs_b200.train_handler import Handler, parse_args
+    d = load_golden("loops_c1.npz")
+    N = 6000
+    X, Y, I = synth.synthetic_frames(N, seed=0)
+    H = Handler(parse_args(["--dropout", "0", "--shift", "0", "--cepochs", "2", "--saveevery", "100", "--model", "/tmp/cgs_fused_loop"]),
+                device=DEV)
+    H.args.cload = False
+    H.critic.load_state_dict({k[len("init.c."):]: torch.from_numpy(d[k]) for k in d.files if k.startswith("init.c.")})
+    H.critic.to(DEV)
+    Xt, Yt = torch.from_numpy(X), torch.from_numpy(Y).t()
+    H.train_loader = [(Xt[i:i + 64], Yt[i:i + 64], None) for i in range(0, N, 64)]
+    H.critic_pipe()
+    closs, ref = np.array(H.closs_log), d["closs"]
+    early = np.abs(closs[:40] - ref[:40]) / ref[:40]
+    assert early.max() < 0.02, early.max()
+    assert abs(np.median(closs[:94]) - np.median(ref[:94])) <= 0.02 * np.median(ref[:94])

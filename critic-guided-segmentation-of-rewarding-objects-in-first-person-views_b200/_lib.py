@@ -40,8 +40,13 @@ class CriticWeights(C.Structure):
 EXPORTS = {
     "cgs_critic_fused_supported": [C.c_int32] * 5,
     "cgs_critic_train_fused": [_u8p, _f32p, C.c_int32, C.c_int32, C.c_void_p, _f32p, _f32p, _f32p,
-                               C.POINTER(CriticWeights), C.POINTER(CriticWeights), C.c_float, C.c_int32, _f32p, _f32p,
+                               C.POINTER(CriticWeights), C.POINTER(CriticWeights), _f32p, C.c_float, C.c_int32, _f32p, _f32p,
                                C.c_void_p],
+    "cgs_critic_fused_grid": [C.c_int32],
+    "cgs_critic_fused_partial_stride": [],
+    "cgs_reduce_partials": [_f32p, C.c_int64, _f32p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p],
+    "cgs_adam_step_partials": [_f32p] * 4 + [C.c_int64] + [C.c_double] * 4 + [C.c_void_p, C.c_float, _f32p, C.c_int32,
+                                                                             C.c_int64, C.c_int64, C.c_int64, C.c_void_p],
     "cgs_conv3x3": [C.POINTER(Conv3x3Args), C.c_void_p],
     "cgs_wgrad3x3": [C.POINTER(Wgrad3x3Args), C.c_void_p],
     "cgs_conv_rgb_fwd": [_u8p] + [C.c_int32] * 4 + [C.c_void_p, _f32p, _f32p, C.c_int32, _f32p, _u8p, C.c_void_p],
@@ -62,6 +67,7 @@ EXPORTS = {
     "cgs_dropout_masks": [_f32p, C.c_int64, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p],
     "cgs_tc_status": [],
     "cgs_tc_set_trace": [C.c_void_p],
+    "cgs_critic_fused_set_trace": [C.c_void_p],
 }
 
 _lib = None

@@ -24,11 +24,13 @@ namespace cgs {
 namespace cf {
 
 constexpr int NT = 512;
-// haloed planes: pitch in pixels, half-plane size in floats (4 channels per pixel); all PL == 16 (mod 32) banks
+// haloed planes: pitch in pixels, half-plane size in floats (4 channels per pixel).  PL1, PL2 == 4 (mod 32) banks (the
+// weight-gradient gathers walk pixels 2t.., 8 banks apart, with the two half-planes 4 banks apart); PL3 == 16 (mod 32)
 constexpr int P0 = 66, SX = 66 * 66 * 4;          // RGB0 frame, one 16-byte pixel
-constexpr int P1 = 34, PL1 = 34 * 34 * 4;         // 32x32 maps
-constexpr int P2 = 18, PL2 = 18 * 18 * 4;         // 16x16 maps
+constexpr int P1 = 34, PL1 = 34 * 34 * 4 + 20;    // 32x32 maps
+constexpr int P2 = 18, PL2 = 18 * 18 * 4 + 20;    // 16x16 maps
 constexpr int P3 = 10, PL3 = 10 * 10 * 4;         // 8x8 maps
+static_assert(PL1 % 32 == 4 && PL2 % 32 == 4 && PL3 % 32 == 16, "bank layout of the half-planes");
 // ---- shared memory map (float offsets)
 constexpr int oA = 0;                              // region A: e0 | dY1      (B0: the re-staged frame)
 constexpr int oE0 = oA, oDY1 = oA + 2 * PL1, oXB = oA;
@@ -54,7 +56,10 @@ constexpr int oW = oAcc + szAcc;                   // weight fragments, [step][l
 constexpr int wL0 = 0, wL1f = 384, wL2f = wL1f + 576, wL3f = wL2f + 576, wL3d = wL3f + 1152, wL2d = wL3d + 1152,
               wL1d = wL2d + 576, szW = wL1d + 576;
 constexpr int oBias = oW + szW;                    // b0[8] b1[8] b2[8] b3[16]
-constexpr int SMEM_FLOATS = oBias + 64;
+constexpr int oHW = oBias + 64;                    // head weights: wl1[1024] bl1[32] wl2[32] bl2[1] b4[32]
+constexpr int hWl1 = 0, hBl1 = 1024, hWl2 = 1056, hBl2 = 1088, hB4 = 1092, szHW = 1124;
+constexpr int SMEM_FLOATS = oHW + szHW;
+constexpr int PSTRIDE = 11904;                     // per-CTA stride of the partial-gradient buffer (16-byte multiple)
 static_assert(szA >= SX, "region A must hold the re-staged frame");
 static_assert(oDY3 + 4 * PL3 <= oB + szB, "region B overflow");
 static_assert(SMEM_FLOATS * 4 <= 227 * 1024, "shared memory budget");
@@ -65,6 +70,7 @@ struct Params {
   const float *m2, *m3, *mv;
   const float *w0, *b0, *w1, *b1, *w2, *b2, *w3, *b3, *w4, *b4, *wl1, *bl1, *wl2, *bl2;
   float* gseg[14];      // gradient tensors in sAcc order (w0 b0 w1 b1 w2 b2 w3 b3 b4 wl1 bl1 wl2 bl2) + [13] = w4
+  float* partials;      // != NULL: per-CTA partial gradients [grid][PSTRIDE] in flat order instead of REDs into gseg
   float* pred;
   float* loss;
   const int* roll_dev;
@@ -72,6 +78,12 @@ struct Params {
   float gscale;         // d(total loss)/d(this rank's mean loss) / B
   float inv_n;          // 1 / B
 };
+
+__device__ long long* g_cf_trace = nullptr;   // debug: clock64() at every phase boundary of CTA 0 (tools/fused_trace.py)
+#define CF_MARK(k)                                                       \
+  do {                                                                   \
+    if (trace && tid == 0) trace[fr * 24 + (k)] = clock64();             \
+  } while (0)
 
 __device__ __forceinline__ uint32_t f2tf32(float f) {
   uint32_t r;
@@ -119,77 +131,73 @@ __device__ __forceinline__ void slide_rows(const float2 (&w)[3][NK], LoadA&& loa
   }
 }
 
-// bias + ReLU + 2x2 max-pool (first max wins, ATen's rule) on two finished rows of a strip.  Even-g lanes own the
-// windows; st(j, value, idx) with j>>1 = pixel half (g or g+8), j&1 = channel (2t or 2t+1); idx 4 = no gradient.
+// bias + ReLU + 2x2 max-pool (first max wins, ATen's rule) on two finished rows of a strip.  The two lanes of an
+// x-pair (g, g^1) split the work: even g finishes channel 2t, odd g channel 2t+1, for both pixel halves (g, g+8).
+// st(h, value, idx): pooled pixel (x0 + g + 8h) >> 1, channel 2t + (g & 1); idx 4 = no gradient (ReLU off).
 template <class Store>
-__device__ __forceinline__ void pool2x2(const float (&top)[4], const float (&bot)[4], float bias0, float bias1, int g, Store&& st) {
+__device__ __forceinline__ void pool2x2(const float (&top)[4], const float (&bot)[4], float bias0, float bias1, int odd, Store&& st) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float b = (j & 1) ? bias1 : bias0;
-    const float pt = top[j] + b, pb = bot[j] + b;
-    const float nt = __shfl_xor_sync(0xffffffffu, pt, 4), nb = __shfl_xor_sync(0xffffffffu, pb, 4);
-    if (!(g & 1)) {
-      float m = pt;
-      int idx = 0;
-      if (nt > m) { m = nt; idx = 1; }
-      if (pb > m) { m = pb; idx = 2; }
-      if (nb > m) { m = nb; idx = 3; }
-      if (!(m > 0.f)) { m = 0.f; idx = 4; }
-      st(j, m, idx);
-    }
+  for (int h = 0; h < 2; ++h) {
+    const float t0 = top[2 * h] + bias0, t1 = top[2 * h + 1] + bias1, b0 = bot[2 * h] + bias0, b1 = bot[2 * h + 1] + bias1;
+    const float rt = __shfl_xor_sync(0xffffffffu, odd ? t0 : t1, 4), rb = __shfl_xor_sync(0xffffffffu, odd ? b0 : b1, 4);
+    const float p0 = odd ? rt : t0, p1 = odd ? t1 : rt, p2 = odd ? rb : b0, p3 = odd ? b1 : rb;
+    const float m01 = fmaxf(p0, p1), m23 = fmaxf(p2, p3);
+    const int i01 = p1 > p0 ? 1 : 0, i23 = p3 > p2 ? 3 : 2;
+    float m = fmaxf(m01, m23);
+    int idx = m23 > m01 ? i23 : i01;
+    if (!(m > 0.f)) { m = 0.f; idx = 4; }
+    st(h, m, idx);
   }
 }
 
 // Weight gradient of an 8-input-channel 3x3 conv over `nks` k-steps of 8 pixels (TW = map width): acc[mt] rows are
 // (tap 2mt | tap 2mt+1) x ci; row 8 of mt 4 is the all-ones row (bias gradient).  X: haloed half-planes of the layer input,
-// DY: haloed half-planes of the output gradient (plane index co>>2, so nt selects planes 2nt, 2nt+1).
+// DY: haloed half-planes of the output gradient.  The mma's k index is mapped to pixels as k = t -> 2t, k = t+4 -> 2t+1,
+// so a lane needs the 4 consecutive pixels 2t..2t+3 of each filter row for all three kx: 12 loads feed the 9 taps.
 template <int TW, int P, int PL>
 __device__ __forceinline__ void wgrad8(float (&acc)[5][4], const float* __restrict__ sX, const float* __restrict__ sDY, int ks0,
                                        int nks, int g, int t) {
-  int offA[5], offB[5];
-#pragma unroll
-  for (int mt = 0; mt < 5; ++mt) {
-    const int ta = 2 * mt, tb = mt < 4 ? 2 * mt + 1 : 8;
-    offA[mt] = (g >> 2) * PL + ((ta / 3) * P + ta % 3) * 4 + (g & 3);
-    offB[mt] = (g >> 2) * PL + ((tb / 3) * P + tb % 3) * 4 + (g & 3);
-  }
-  const float ones = g == 0 ? 1.f : 0.f;
-  const int offY = (g >> 2) * PL + (P + 1) * 4 + (g & 3);
+  const int offX = (g >> 2) * PL + (g & 3) + 8 * t;
+  const int offY = offX + (P + 1) * 4;
+  const uint32_t ones = g == 0 ? 0x3f800000u : 0u;
   constexpr int KPR = TW / 8;   // k-steps per row
   for (int ks = ks0; ks < ks0 + nks; ++ks) {
     const int y = ks / KPR, x0 = (ks % KPR) * 8;
-    const int base = (y * P + x0 + t) * 4;
-    const uint32_t b0 = __float_as_uint(sDY[offY + base]), b1 = __float_as_uint(sDY[offY + base + 16]);
+    const float* px = sX + offX + (y * P + x0) * 4;
+    const uint32_t b0 = __float_as_uint(sDY[offY + (y * P + x0) * 4]), b1 = __float_as_uint(sDY[offY + (y * P + x0) * 4 + 4]);
+    uint32_t v[3][4];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[ky][i] = __float_as_uint(px[(ky * P + i) * 4]);
 #pragma unroll
     for (int mt = 0; mt < 5; ++mt) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int ta = 2 * mt, tb = 2 * mt + 1;
       uint32_t a[4];
-      a[0] = __float_as_uint(sX[offA[mt] + base]);
-      a[2] = __float_as_uint(sX[offA[mt] + base + 16]);
+      a[0] = v[ta / 3][ta % 3];
+      a[2] = v[ta / 3][ta % 3 + 1];
       if (mt < 4) {
-        a[1] = __float_as_uint(sX[offB[mt] + base]);
-        a[3] = __float_as_uint(sX[offB[mt] + base + 16]);
+        a[1] = v[tb / 3][tb % 3];
+        a[3] = v[tb / 3][tb % 3 + 1];
       } else {
-        a[1] = a[3] = __float_as_uint(ones);
+        a[1] = a[3] = ones;
       }
       mma_tf32(acc[mt], a, b0, b1);
     }
   }
 }
 
-// acc[mt] of wgrad8 -> shared accumulators in OIHW order (co = co0 + 2t + {0,1}, ci = g)
-template <bool ATOMIC>
-__device__ __forceinline__ void wgrad8_store(const float (&acc)[5][4], float* aW, float* aB, int co0, int g, int t) {
+// acc[mt] of wgrad8 -> a per-warp tile laid out like the OIHW gradient + bias: [co*72 + ci*9 + tap | 576 + co]
+__device__ __forceinline__ void wgrad8_store(const float (&acc)[5][4], float* tile, int g, int t) {
 #pragma unroll
   for (int mt = 0; mt < 5; ++mt)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int co = co0 + 2 * t + (q & 1), tap = 2 * mt + (q >> 1);
-      float* d;
-      if (tap < 9) d = aW + (co * 8 + g) * 9 + tap;
-      else if (g == 0) d = aB + co;
-      else continue;
-      if (ATOMIC) atomicAdd(d, acc[mt][q]);
-      else *d += acc[mt][q];
+      const int co = 2 * t + (q & 1), tap = 2 * mt + (q >> 1);
+      if (tap < 9) tile[(co * 8 + g) * 9 + tap] = acc[mt][q];
+      else if (g == 0) tile[576 + co] = acc[mt][q];
     }
 }
 
@@ -216,10 +224,18 @@ __device__ __forceinline__ void stage_frame(const uint8_t* __restrict__ sU8, flo
   }
 }
 
-__device__ __forceinline__ void prefetch_frame(const uint8_t* __restrict__ src, float* sU8f, int tid) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(sU8f);
+// cp.async: the raw frame (12288 B) and its dropout masks (512 + 256 + 32 floats) for frame n
+__device__ __forceinline__ void prefetch_frame(const Params& p, int n, float* sm, int tid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(sm + oU8);
+  const uint8_t* src = p.frames + (size_t)n * 12288;
   for (int c = tid; c < 768; c += NT)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + c * 16), "l"(src + c * 16));
+  if (p.m2) {
+    const uint32_t dm = (uint32_t)__cvta_generic_to_shared(sm);
+    if (tid < 128) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dm + (oM2 + tid * 4) * 4), "l"(p.m2 + (size_t)n * 512 + tid * 4));
+    else if (tid < 192) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dm + (oM3 + (tid - 128) * 4) * 4), "l"(p.m3 + (size_t)n * 256 + (tid - 128) * 4));
+    else if (tid < 200) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dm + (oHead + 64 + (tid - 192) * 4) * 4), "l"(p.mv + (size_t)n * 32 + (tid - 192) * 4));
+  }
   asm volatile("cp.async.commit_group;\n" ::);
 }
 
@@ -236,7 +252,10 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
   const float2* sWf = reinterpret_cast<const float2*>(sm + oW);
   const uint32_t smb = (uint32_t)__cvta_generic_to_shared(sm);
 
-  if (blockIdx.x < p.B) prefetch_frame(p.frames + (size_t)blockIdx.x * 12288, sm + oU8, tid);
+  long long* trace = blockIdx.x == 0 ? g_cf_trace : nullptr;
+  int fr = 0;
+  CF_MARK(23);
+  if (blockIdx.x < p.B) prefetch_frame(p, blockIdx.x, sm, tid);
 
   // ---- prologue: accumulators, halos that stay zero, weight fragments (TF32, in mma B-fragment order), biases
   for (int e = tid; e < szAcc; e += NT) sAcc[e] = 0.f;
@@ -272,25 +291,60 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
   }
   if (tid < 8) { sm[oBias + tid] = __ldg(p.b0 + tid); sm[oBias + 8 + tid] = __ldg(p.b1 + tid); sm[oBias + 16 + tid] = __ldg(p.b2 + tid); }
   if (tid < 16) sm[oBias + 24 + tid] = __ldg(p.b3 + tid);
+  for (int e = tid; e < 1024; e += NT) sm[oHW + hWl1 + e] = __ldg(p.wl1 + e);
+  if (tid < 32) {
+    sm[oHW + hBl1 + tid] = __ldg(p.bl1 + tid);
+    sm[oHW + hWl2 + tid] = __ldg(p.wl2 + tid);
+    sm[oHW + hB4 + tid] = __ldg(p.b4 + tid);
+  }
+  if (tid == 0) sm[oHW + hBl2] = __ldg(p.bl2);
+  if (!p.m2) {                                     // eval mode / p = 0: identity masks, written once
+    sm[oM2 + tid] = 1.f;
+    if (tid < 256) sm[oM3 + tid] = 1.f;
+    if (tid < 32) sm[oHead + 64 + tid] = 1.f;
+  }
 
   int roll = p.roll_dev ? *p.roll_dev : p.roll;
   roll = ((roll % 64) + 64) & 63;
-  float accW4[16], acc0[2][4];
+  // gradient accumulators that live in registers over all frames of this CTA:
+  //   accW4: features.14 (each thread owns 16 of the 8192 entries), acc0: features.0 (all warps, K split by rows),
+  //   accW: features.3 (warps 0-7) or features.6 (warps 8-15), K split over the 8 warps; bsum: features.0 bias
+  float accW4[16], acc0[2][4], accW[5][4], bsum[2] = {0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 16; ++i) accW4[i] = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc0[i >> 2][i & 3] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 20; ++i) accW[i >> 2][i & 3] = 0.f;
   float loss_acc = 0.f;
+  const int odd = g & 1;
+  // features.0 weight-gradient rows: m = 8G + r; G < 3: filter row ky = G, the (kx, ci) combos except (2, ky);
+  // G = 3: the three left-out combos (ky = r, kx = 2, ci = r), rows 3..7 unused.  Within an 8-row group every lane
+  // address 4*(t + kx) + ci is a distinct bank or the same word: the gather is conflict-free.
+  int offA0[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int G = 2 * mt + h;
+      int ky, kx, ci;
+      if (G < 3) {
+        const int c = g < 6 + G ? g : g + 1;       // skip combo index 6 + ky == (kx 2, ci ky)
+        ky = G; kx = c / 3; ci = c - kx * 3;
+      } else {
+        ky = g < 3 ? g : 0; kx = 2; ci = g < 3 ? g : 0;
+      }
+      offA0[mt][h] = (ky * P0 + kx) * 4 + ci;
+    }
   const int ldoff8 = (lr + 8 * (lj & 1)) * 4;                 // ldmatrix row offset inside an 8-channel half-plane strip
 
   for (int n = blockIdx.x; n < p.B; n += gridDim.x) {
-    // ================= F0a: frame bytes -> fp32 haloed tile, dropout masks, e0 halo
+    CF_MARK(0);
+    // ================= F0a: frame bytes (+ dropout masks) have landed -> fp32 haloed tile; e0 halo
+    const float ytgt = __ldg(p.target + n);
     asm volatile("cp.async.wait_all;\n" ::);
     __syncthreads();
     stage_frame(reinterpret_cast<const uint8_t*>(sm + oU8), sm + oX, roll, tid);
-    sm[oM2 + tid] = p.m2 ? __ldg(p.m2 + (size_t)n * 512 + tid) : 1.f;
-    if (tid < 256) sm[oM3 + tid] = p.m3 ? __ldg(p.m3 + (size_t)n * 256 + tid) : 1.f;
-    if (tid < 32) sMV[tid] = p.mv ? __ldg(p.mv + (size_t)n * 32 + tid) : 1.f;
     if (tid < 264) {   // e0 halo ring (region A is reused by the re-staged frame), both half-planes
       const int h = tid >= 132, q = tid - 132 * h;
       int y, x;
@@ -302,6 +356,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     }
     __syncthreads();
 
+    CF_MARK(1);
     // ================= F0: features.0 (3 -> 8) + ReLU + pool : 16 warps = 4 strips x 4 segments of 16 rows
     {
       const int x0 = (warp & 3) * 16, r0 = (warp >> 2) * 16;
@@ -311,6 +366,9 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
       const uint32_t aA = smb + (oX + (r0 * P0 + x0 + lr + 8 * (lj & 1) + (lj >> 1)) * 4) * 4;
       const uint32_t aB = smb + (oX + (r0 * P0 + x0 + lr + 8 * (lj & 1) + 2) * 4) * 4;
       const float bias0 = sm[oBias + 2 * t], bias1 = sm[oBias + 2 * t + 1];
+      const int co = 2 * t + odd;
+      float* dE = sm + oE0 + (co >> 2) * PL1 + (((r0 >> 1) + 1) * P1 + ((x0 + g) >> 1) + 1) * 4 + (co & 3);
+      uint8_t* dI = sI0 + ((r0 >> 1) * 32 + ((x0 + g) >> 1)) * 8 + co;
       slide_rows<16, 2>(
           w,
           [&](int i, uint32_t(&a)[2][4]) {
@@ -319,26 +377,29 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
             a[1][2] = a[1][3] = 0u;
           },
           [&](int e, const float(&top)[4], const float(&bot)[4]) {
-            const int py = (r0 + e) >> 1;
-            pool2x2(top, bot, bias0, bias1, g, [&](int j, float v, int idx) {
-              const int px = ((x0 + g) >> 1) + 4 * (j >> 1), co = 2 * t + (j & 1);
-              sm[oE0 + (co >> 2) * PL1 + ((py + 1) * P1 + px + 1) * 4 + (co & 3)] = tf32r(v);
-              sI0[(py * 32 + px) * 8 + co] = (uint8_t)idx;
+            pool2x2(top, bot, bias0, bias1, odd, [&](int h, float v, int idx) {
+              dE[((e >> 1) * P1 + 4 * h) * 4] = tf32r(v);
+              dI[((e >> 1) * 32 + 4 * h) * 8] = (uint8_t)idx;
             });
           });
     }
     __syncthreads();
 
+    CF_MARK(2);
     // ================= F1: features.3 (8 -> 8) on 32x32 : 2 strips x 8 segments of 4 rows; scatter targets are cleared
     {
-      for (int e = tid; e < 2 * PL1; e += NT) sm[oDY1 + e] = 0.f;
-      for (int e = tid; e < 2 * PL2 + 4 * PL3; e += NT) sm[oDY2 + e] = 0.f;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int e = tid; e < 2 * PL1 / 4; e += NT) reinterpret_cast<float4*>(sm + oDY1)[e] = z4;
+      for (int e = tid; e < (2 * PL2 + 4 * PL3) / 4; e += NT) reinterpret_cast<float4*>(sm + oDY2)[e] = z4;
       const int x0 = (warp & 1) * 16, r0 = (warp >> 1) * 4;
       float2 w[3][3];
 #pragma unroll
       for (int s = 0; s < 9; ++s) w[s / 3][s % 3] = sWf[(wL1f >> 1) + s * 32 + lane];
       const uint32_t aA = smb + (oE0 + (lj >> 1) * PL1 + (r0 * P1 + x0) * 4 + ldoff8) * 4;
       const float bias0 = sm[oBias + 8 + 2 * t], bias1 = sm[oBias + 8 + 2 * t + 1];
+      const int co = 2 * t + odd;
+      float* dE = sm + oE1 + (co >> 2) * PL2 + (((r0 >> 1) + 1) * P2 + ((x0 + g) >> 1) + 1) * 4 + (co & 3);
+      uint8_t* dI = sI1 + ((r0 >> 1) * 16 + ((x0 + g) >> 1)) * 8 + co;
       slide_rows<4, 3>(
           w,
           [&](int i, uint32_t(&a)[3][4]) {
@@ -346,16 +407,15 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
             for (int kx = 0; kx < 3; ++kx) ldsm4(a[kx], aA + (i * P1 + kx) * 16);
           },
           [&](int e, const float(&top)[4], const float(&bot)[4]) {
-            const int py = (r0 + e) >> 1;
-            pool2x2(top, bot, bias0, bias1, g, [&](int j, float v, int idx) {
-              const int px = ((x0 + g) >> 1) + 4 * (j >> 1), co = 2 * t + (j & 1);
-              sm[oE1 + (co >> 2) * PL2 + ((py + 1) * P2 + px + 1) * 4 + (co & 3)] = tf32r(v);
-              sI1[(py * 16 + px) * 8 + co] = (uint8_t)idx;
+            pool2x2(top, bot, bias0, bias1, odd, [&](int h, float v, int idx) {
+              dE[((e >> 1) * P2 + 4 * h) * 4] = tf32r(v);
+              dI[((e >> 1) * 16 + 4 * h) * 8] = (uint8_t)idx;
             });
           });
     }
     __syncthreads();
 
+    CF_MARK(3);
     // ================= F2: features.6 (8 -> 8) on 16x16 + Dropout : 8 warps x 2 rows
     if (warp < 8) {
       const int r0 = warp * 2;
@@ -371,9 +431,8 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
             for (int kx = 0; kx < 3; ++kx) ldsm4(a[kx], aA + (i * P2 + kx) * 16);
           },
           [&](int e, const float(&top)[4], const float(&bot)[4]) {
-            const int py = (r0 + e) >> 1;
-            pool2x2(top, bot, bias0, bias1, g, [&](int j, float v, int idx) {
-              const int px = (g >> 1) + 4 * (j >> 1), co = 2 * t + (j & 1), q = (py * 8 + px) * 8 + co;
+            pool2x2(top, bot, bias0, bias1, odd, [&](int h, float v, int idx) {
+              const int py = warp, px = (g >> 1) + 4 * h, co = 2 * t + odd, q = (py * 8 + px) * 8 + co;
               sm[oE2 + (co >> 2) * PL3 + ((py + 1) * P3 + px + 1) * 4 + (co & 3)] = tf32r(v * sm[oM2 + q]);
               sI2[q] = (uint8_t)idx;
             });
@@ -381,7 +440,17 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     }
     __syncthreads();
 
+    CF_MARK(4);
     // ================= F3: features.10 (8 -> 16) on 8x8 + Dropout : 8 warps = 4 row pairs x 2 channel tiles
+    // (all threads first put their slice of the features.14 weights in flight: 32 KB from L2, used in F4)
+    // chunk order rotated per thread ((i + part/2) & 3) so that the 128-bit shared reads of x3 in F4 / B4 are conflict-free
+    float4 w4r[4];
+    const int rot4 = (tid >> 1) & 3;
+    {
+      const float4* wr = reinterpret_cast<const float4*>(p.w4 + (tid >> 4) * 256 + (tid & 15) * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w4r[i] = __ldg(wr + ((i + rot4) & 3));
+    }
     if (warp < 8) {
       const int mt = warp >> 1, nt = warp & 1;
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -393,57 +462,63 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
         const float2 w = sWf[(wL3f >> 1) + (tap * 2 + nt) * 32 + lane];
         mma_tf32(acc, a, __float_as_uint(w.x), __float_as_uint(w.y));
       }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int co = nt * 8 + 2 * t + j;
-        const float b = sm[oBias + 24 + co];
-        const float pt = acc[j] + b, pb = acc[j + 2] + b;
-        const float nt_ = __shfl_xor_sync(0xffffffffu, pt, 4), nb = __shfl_xor_sync(0xffffffffu, pb, 4);
-        if (!(g & 1)) {
-          float m = pt;
-          int idx = 0;
-          if (nt_ > m) { m = nt_; idx = 1; }
-          if (pb > m) { m = pb; idx = 2; }
-          if (nb > m) { m = nb; idx = 3; }
-          if (!(m > 0.f)) { m = 0.f; idx = 4; }
-          const int pp = mt * 4 + (g >> 1);
-          sm[oX3 + co * 16 + pp] = m * sm[oM3 + pp * 16 + co];
-          sI3[pp * 16 + co] = (uint8_t)idx;
-        }
-      }
+      // rows (2mt, 2mt+1) x pixel g: the x-pair lanes split the two channels
+      const int co = nt * 8 + 2 * t + odd;
+      const float b0 = sm[oBias + 24 + nt * 8 + 2 * t], b1 = sm[oBias + 24 + nt * 8 + 2 * t + 1];
+      const float t0 = acc[0] + b0, t1 = acc[1] + b1, u0 = acc[2] + b0, u1 = acc[3] + b1;
+      const float rt = __shfl_xor_sync(0xffffffffu, odd ? t0 : t1, 4), rb = __shfl_xor_sync(0xffffffffu, odd ? u0 : u1, 4);
+      const float p0 = odd ? rt : t0, p1 = odd ? t1 : rt, p2 = odd ? rb : u0, p3 = odd ? u1 : rb;
+      const float m01 = fmaxf(p0, p1), m23 = fmaxf(p2, p3);
+      const int i01 = p1 > p0 ? 1 : 0, i23 = p3 > p2 ? 3 : 2;
+      float m = fmaxf(m01, m23);
+      int idx = m23 > m01 ? i23 : i01;
+      if (!(m > 0.f)) { m = 0.f; idx = 4; }
+      const int pp = mt * 4 + (g >> 1);
+      sm[oX3 + co * 16 + pp] = m * sm[oM3 + pp * 16 + co];
+      sI3[pp * 16 + co] = (uint8_t)idx;
     }
     __syncthreads();
 
+    CF_MARK(5);
     // ================= F4: features.14 (4x4 valid conv = 256 -> 32) + ReLU
     {
       const int nn = tid >> 4, part = tid & 15;
-      const float4* wr = reinterpret_cast<const float4*>(p.w4 + nn * 256 + part * 16);
-      const float4* xr = reinterpret_cast<const float4*>(sm + oX3 + part * 16);
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 a = __ldg(wr + i), b = xr[i];
-        s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+        const float4 aq = w4r[i];
+        const float4 bq = *reinterpret_cast<const float4*>(sm + oX3 + part * 16 + ((i + rot4) & 3) * 4);
+        s = fmaf(aq.x, bq.x, s); s = fmaf(aq.y, bq.y, s); s = fmaf(aq.z, bq.z, s); s = fmaf(aq.w, bq.w, s);
       }
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (part == 0) sH[nn] = fmaxf(s + __ldg(p.b4 + nn), 0.f);
+      if (part == 0) sH[nn] = fmaxf(s + sm[oHW + hB4 + nn], 0.f);
     }
     __syncthreads();
+    CF_MARK(6);
     // ================= F5: crit.1 Linear(32,32) + ReLU
     {
       const int nn = tid >> 4, part = tid & 15;
-      float s = __ldg(p.wl1 + nn * 32 + 2 * part) * sH[2 * part] + __ldg(p.wl1 + nn * 32 + 2 * part + 1) * sH[2 * part + 1];
+      const float2 wv = *reinterpret_cast<const float2*>(sm + oHW + hWl1 + nn * 32 + 2 * part);
+      float s = wv.x * sH[2 * part] + wv.y * sH[2 * part + 1];
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (part == 0) sV[nn] = fmaxf(s + __ldg(p.bl1 + nn), 0.f);
+      if (part == 0) sV[nn] = fmaxf(s + sm[oHW + hBl1 + nn], 0.f);
     }
     __syncthreads();
+    CF_MARK(7);
     // ================= F6: Dropout, crit.4 Linear(32,1), Sigmoid, loss and its gradient; head weight gradients
+    // (meanwhile every thread puts its features.14 column slice in flight for B4)
+    float w4c[16];
+    {
+      const float* wc = p.w4 + ((tid & 1) * 16) * 256 + (tid >> 1);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w4c[i] = __ldg(wc + i * 256);
+    }
     if (warp == 0) {
-      const float wk = __ldg(p.wl2 + lane), vm = sV[lane] * sMV[lane];
-      const float z = warp_sum(wk * vm) + __ldg(p.bl2);
-      const float pr = sigmoidf_(z), y = __ldg(p.target + n);
+      const float wk = sm[oHW + hWl2 + lane], vm = sV[lane] * sMV[lane];
+      const float z = warp_sum(wk * vm) + sm[oHW + hBl2];
+      const float pr = sigmoidf_(z), y = ytgt;
       float dl;
       if (p.bce) {
         loss_acc -= y * fmaxf(logf(pr), -100.f) + (1.f - y) * fmaxf(logf(1.f - pr), -100.f);
@@ -457,6 +532,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
       sDV[lane] = sV[lane] > 0.f ? dl * wk * sMV[lane] : 0.f;
     }
     __syncthreads();
+    CF_MARK(8);
     // ================= B5: crit.1 backward
     {
 #pragma unroll
@@ -466,23 +542,28 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
       }
       if (tid < 32) sAcc[aBl1 + tid] += sDV[tid];
       const int k = tid >> 4, part = tid & 15;
-      float s = __ldg(p.wl1 + (2 * part) * 32 + k) * sDV[2 * part] + __ldg(p.wl1 + (2 * part + 1) * 32 + k) * sDV[2 * part + 1];
+      float s = sm[oHW + hWl1 + (2 * part) * 32 + k] * sDV[2 * part] + sm[oHW + hWl1 + (2 * part + 1) * 32 + k] * sDV[2 * part + 1];
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (part == 0) sDH[k] = sH[k] > 0.f ? s : 0.f;
     }
     __syncthreads();
+    CF_MARK(9);
     // ================= B4: features.14 backward (weight gradient in registers), Dropout + pool + ReLU backward -> dY3
     {
       const int nn = tid >> 4, part = tid & 15;
       const float d = sDH[nn];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) accW4[i] = fmaf(d, sm[oX3 + part * 16 + i], accW4[i]);
+      for (int i = 0; i < 4; ++i) {                                         // accW4[4i..] <-> chunk (i + rot4) & 3, as in F4
+        const float4 x = *reinterpret_cast<const float4*>(sm + oX3 + part * 16 + ((i + rot4) & 3) * 4);
+        accW4[4 * i + 0] = fmaf(d, x.x, accW4[4 * i + 0]); accW4[4 * i + 1] = fmaf(d, x.y, accW4[4 * i + 1]);
+        accW4[4 * i + 2] = fmaf(d, x.z, accW4[4 * i + 2]); accW4[4 * i + 3] = fmaf(d, x.w, accW4[4 * i + 3]);
+      }
       if (tid < 32) sAcc[aB4 + tid] += sDH[tid];
       const int k = tid >> 1, hf = tid & 1;
       float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) s = fmaf(__ldg(p.w4 + (hf * 16 + i) * 256 + k), sDH[hf * 16 + i], s);
+      for (int i = 0; i < 16; ++i) s = fmaf(w4c[i], sDH[hf * 16 + i], s);
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       if (hf == 0) {
         const int co = k >> 4, pp = k & 15, idx = sI3[pp * 16 + co];
@@ -493,6 +574,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
       }
     }
     __syncthreads();
+    CF_MARK(10);
     // ================= B3: features.10 weight gradient (warps 0-9) || input gradient -> dY2 (warps 10-13)
     if (warp < 10) {
       const int mt = warp % 5, nt = warp / 5;
@@ -540,15 +622,12 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
       }
     }
     __syncthreads();
-    // ================= B2: features.6 weight gradient (warps 0-7) || input gradient -> dY1 (warps 8-15)
-    if (warp < 8) {
-      float acc[5][4];
-#pragma unroll
-      for (int i = 0; i < 20; ++i) acc[i >> 2][i & 3] = 0.f;
-      wgrad8<16, P2, PL2>(acc, sm + oE1, sm + oDY2, warp * 4, 4, g, t);
-      wgrad8_store<true>(acc, sAcc + aW2, sAcc + aB2, 0, g, t);
+    CF_MARK(11);
+    // ================= B2: features.6 input gradient -> dY1 (warps 0-7) || weight gradient (warps 8-15, registers)
+    if (warp >= 8) {
+      wgrad8<16, P2, PL2>(accW, sm + oE1, sm + oDY2, (warp - 8) * 4, 4, g, t);
     } else {
-      const int r0 = (warp - 8) * 2;
+      const int r0 = warp * 2;
       float2 w[3][3];
 #pragma unroll
       for (int s = 0; s < 9; ++s) w[s / 3][s % 3] = sWf[(wL2d >> 1) + s * 32 + lane];
@@ -572,20 +651,18 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
           });
     }
     __syncthreads();
-    // ================= B1: features.3 weight gradient (warps 0-7) || input gradient -> dE0 with arg-max tags (warps 8-15)
+    CF_MARK(12);
+    // ================= B1: features.3 weight gradient (warps 0-7, registers) || input gradient -> dE0 + arg-max tags (8-15)
     if (warp < 8) {
-      float acc[5][4];
-#pragma unroll
-      for (int i = 0; i < 20; ++i) acc[i >> 2][i & 3] = 0.f;
-      wgrad8<32, P1, PL1>(acc, sm + oE0, sm + oDY1, warp * 16, 16, g, t);
-      wgrad8_store<true>(acc, sAcc + aW1, sAcc + aB1, 0, g, t);
+      wgrad8<32, P1, PL1>(accW, sm + oE0, sm + oDY1, warp * 16, 16, g, t);
     } else {
       const int x0 = (warp & 1) * 16, r0 = ((warp - 8) >> 1) * 8;
       float2 w[3][3];
 #pragma unroll
       for (int s = 0; s < 9; ++s) w[s / 3][s % 3] = sWf[(wL1d >> 1) + s * 32 + lane];
       const uint32_t aA = smb + (oDY1 + (lj >> 1) * PL1 + (r0 * P1 + x0) * 4 + ldoff8) * 4;
-      uint32_t* sDE0 = reinterpret_cast<uint32_t*>(sm + oDE0);
+      uint32_t* dD = reinterpret_cast<uint32_t*>(sm + oDE0) + (r0 * 32 + x0 + g) * 8 + 2 * t;
+      const uint8_t* dI = sI0 + (r0 * 32 + x0 + g) * 8 + 2 * t;
       slide_rows<8, 3>(
           w,
           [&](int i, uint32_t(&a)[3][4]) {
@@ -596,76 +673,118 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int y = r0 + e + r, x = x0 + g + 8 * (q >> 1), o = (y * 32 + x) * 8 + 2 * t + (q & 1), idx = sI0[o];
+              for (int h = 0; h < 2; ++h) {
+                const int o = ((e + r) * 32 + 8 * h) * 8;
+                const uint32_t ib = *reinterpret_cast<const uint16_t*>(dI + o);      // arg-max bytes of channels 2t, 2t+1
+                const float v0 = r ? bot[2 * h] : top[2 * h], v1 = r ? bot[2 * h + 1] : top[2 * h + 1];
+                const uint32_t i0 = ib & 0xff, i1 = ib >> 8;
                 // the 2x2 window position of the max rides in the two lowest mantissa bits (TF32 ignores them)
-                sDE0[o] = idx < 4 ? ((f2tf32(r ? bot[q] : top[q]) & ~3u) | (uint32_t)idx) : 0u;
+                uint2 st;
+                st.x = i0 < 4 ? ((f2tf32(v0) & ~3u) | i0) : 0u;
+                st.y = i1 < 4 ? ((f2tf32(v1) & ~3u) | i1) : 0u;
+                *reinterpret_cast<uint2*>(dD + o) = st;
+                bsum[0] += i0 < 4 ? v0 : 0.f;                                         // features.0 bias gradient
+                bsum[1] += i1 < 4 ? v1 : 0.f;
               }
           });
     }
     __syncthreads();
+    CF_MARK(13);
     // ================= B0a: frame again (region A is free now), then start fetching the next frame
     stage_frame(reinterpret_cast<const uint8_t*>(sm + oU8), sm + oXB, roll, tid);
     __syncthreads();
-    if (n + (int)gridDim.x < p.B) prefetch_frame(p.frames + (size_t)(n + gridDim.x) * 12288, sm + oU8, tid);
-    // ================= B0: features.0 weight gradient, K = 4096 pixels over 16 warps, accumulators stay in registers
+    if (n + (int)gridDim.x < p.B) prefetch_frame(p, n + gridDim.x, sm, tid);
+    CF_MARK(14);
+    // ================= B0: features.0 weight gradient, K = 4096 pixels over 16 warps (4 rows each), registers
     {
-      int offA[2][2];
-      float mulA[2][2], addA[2][2];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int m = 16 * mt + g + 8 * h;
-          int off = 0;
-          float mu = 0.f, ad = 0.f;
-          if (m < 27) {
-            const int ci = m / 9, tap = m - ci * 9;
-            off = ((tap / 3) * P0 + tap % 3) * 4 + ci;
-            mu = 1.f;
-          } else if (m == 27) {
-            ad = 1.f;
-          }
-          offA[mt][h] = off; mulA[mt][h] = mu; addA[mt][h] = ad;
-        }
       const uint32_t* sDE0 = reinterpret_cast<const uint32_t*>(sm + oDE0);
       const float* sXb = sm + oXB;
-      for (int ks = warp * 32; ks < warp * 32 + 32; ++ks) {
-        const int y = ks >> 3, x0 = (ks & 7) * 8;
-        const int base = (y * P0 + x0 + t) * 4;
+#pragma unroll 1
+      for (int yy = 0; yy < 4; ++yy) {
+        const int y = warp * 4 + yy;
+        const float* xa = sXb + (y * P0 + t) * 4;
+        const uint32_t* de = sDE0 + ((y >> 1) * 32 + (t >> 1)) * 8 + g;
         const uint32_t pos = ((y & 1) << 1) | (t & 1);
-        const int pp = ((y >> 1) * 32 + ((x0 + t) >> 1)) * 8 + g;
-        uint32_t b0 = sDE0[pp], b1 = sDE0[pp + 16];
-        b0 = (b0 & 3u) == pos ? b0 : 0u;
-        b1 = (b1 & 3u) == pos ? b1 : 0u;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          uint32_t a[4];
+        for (int xs = 0; xs < 8; ++xs) {
+          uint32_t b0 = de[xs * 32], b1 = de[xs * 32 + 16];
+          b0 = (b0 & 3u) == pos ? b0 : 0u;
+          b1 = (b1 & 3u) == pos ? b1 : 0u;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            a[h] = __float_as_uint(fmaf(sXb[offA[mt][h] + base], mulA[mt][h], addA[mt][h]));
-            a[2 + h] = __float_as_uint(fmaf(sXb[offA[mt][h] + base + 16], mulA[mt][h], addA[mt][h]));
+          for (int mt = 0; mt < 2; ++mt) {
+            uint32_t a[4];
+            a[0] = __float_as_uint(xa[offA0[mt][0] + xs * 32]);
+            a[1] = __float_as_uint(xa[offA0[mt][1] + xs * 32]);
+            a[2] = __float_as_uint(xa[offA0[mt][0] + xs * 32 + 16]);
+            a[3] = __float_as_uint(xa[offA0[mt][1] + xs * 32 + 16]);
+            mma_tf32(acc0[mt], a, b0, b1);
           }
-          mma_tf32(acc0[mt], a, b0, b1);
         }
       }
     }
+    CF_MARK(15);
+    if (trace && fr < 3) ++fr;
     // the next iteration's F0a barrier (or the one below) separates B0's reads from the next writes
   }
 
-  // ---- flush: features.0 accumulators -> shared, then ONE round of REDs per CTA into the caller's gradient tensors
+  // ---- end of the CTA's frames: combine the warps' register accumulators through shared memory (region A is free),
+  //      then write this CTA's gradient: one coalesced partial vector (summed by the Adam kernel), or REDs
   asm volatile("cp.async.wait_all;\n" ::);
   __syncthreads();
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int m = 16 * mt + g + 8 * (q >> 1), co = 2 * t + (q & 1);
-      if (m < 27) atomicAdd(sAcc + aW0 + co * 27 + m, acc0[mt][q]);
-      else if (m == 27) atomicAdd(sAcc + aB0 + co, acc0[mt][q]);
-    }
-  __syncthreads();
   {
+    float* scr = sm + oA;                           // [16 warps][584] conv tiles, then [16 warps][216] for features.0
+    wgrad8_store(accW, scr + warp * 584, g, t);
+    float* scr0 = sm + oA + 16 * 584 + warp * 216;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int G = 2 * mt + (q >> 1), co = 2 * t + (q & 1);
+        int ky, kx, ci;
+        if (G < 3) {
+          const int c = g < 6 + G ? g : g + 1;
+          ky = G; kx = c / 3; ci = c - kx * 3;
+        } else {
+          ky = g; kx = 2; ci = g;
+        }
+        if (G < 3 || g < 3) scr0[co * 27 + ci * 9 + ky * 3 + kx] = acc0[mt][q];
+      }
+    // features.0 bias: lanes with equal t hold the same channels; fold the 8 g's, one value per warp and channel
+    bsum[0] += __shfl_xor_sync(0xffffffffu, bsum[0], 4); bsum[1] += __shfl_xor_sync(0xffffffffu, bsum[1], 4);
+    bsum[0] += __shfl_xor_sync(0xffffffffu, bsum[0], 8); bsum[1] += __shfl_xor_sync(0xffffffffu, bsum[1], 8);
+    bsum[0] += __shfl_xor_sync(0xffffffffu, bsum[0], 16); bsum[1] += __shfl_xor_sync(0xffffffffu, bsum[1], 16);
+    if (g == 0) { sm[oA + 16 * 800 + warp * 8 + 2 * t] = bsum[0]; sm[oA + 16 * 800 + warp * 8 + 2 * t + 1] = bsum[1]; }
+  }
+  __syncthreads();
+  for (int e = tid; e < 584; e += NT) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { s1 += sm[oA + w * 584 + e]; s2 += sm[oA + (w + 8) * 584 + e]; }
+    sAcc[aW1 + e] = s1;                             // aB1 == aW1 + 576, aB2 == aW2 + 576
+    sAcc[aW2 + e] = s2;
+  }
+  for (int e = tid; e < 224; e += NT) {            // features.0 weight (216) + bias (8: aB0 == aW0 + 216), fixed order
+    float s0 = 0.f;
+    if (e < 216) {
+#pragma unroll
+      for (int w = 0; w < 16; ++w) s0 += sm[oA + 16 * 584 + w * 216 + e];
+    } else {
+#pragma unroll
+      for (int w = 8; w < 16; ++w) s0 += sm[oA + 16 * 800 + w * 8 + e - 216];
+    }
+    sAcc[aW0 + e] = s0;
+  }
+  __syncthreads();
+  CF_MARK(17);
+  if (p.partials) {
+    // flat (state_dict) order: sAcc[0, 2560) -> [0, 2560); features.14.weight -> [2560, 10752); sAcc[2560, 3681) -> +8192
+    float* d = p.partials + (size_t)blockIdx.x * PSTRIDE;
+    for (int e = tid; e < 3681; e += NT) d[e < 2560 ? e : e + 8192] = sAcc[e];
+    float4* d4 = reinterpret_cast<float4*>(d + 2560 + (tid >> 4) * 256 + (tid & 15) * 16);
+    const int rot4 = (tid >> 1) & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d4[(i + rot4) & 3] = make_float4(accW4[4 * i], accW4[4 * i + 1], accW4[4 * i + 2], accW4[4 * i + 3]);
+  } else {
     constexpr int segoff[13] = {aW0, aB0, aW1, aB1, aW2, aB2, aW3, aB3, aB4, aWl1, aBl1, aWl2, aBl2};
     constexpr int seglen[13] = {216, 8, 576, 8, 576, 8, 1152, 16, 32, 1024, 32, 32, 1};
 #pragma unroll
@@ -674,10 +793,12 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
       for (int e = tid; e < seglen[s]; e += NT) atomicAdd(d + e, sAcc[segoff[s] + e]);
     }
     float* d4 = p.gseg[13] + (tid >> 4) * 256 + (tid & 15) * 16;
+    const int rot4 = (tid >> 1) & 3;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) atomicAdd(d4 + i, accW4[i]);
+    for (int i = 0; i < 16; ++i) atomicAdd(d4 + (((i >> 2) + rot4) & 3) * 4 + (i & 3), accW4[i]);
   }
   if (tid == 0 && blockIdx.x < p.B) atomicAdd(p.loss, loss_acc * p.inv_n);
+  CF_MARK(16);
 }
 
 }  // namespace cf
@@ -685,40 +806,67 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
 
 using namespace cgs;
 
+// Debug: point the phase trace at a device buffer of 4*24 int64 (NULL disables).  Not part of the product API.
+extern "C" int cgs_critic_fused_set_trace(long long* dev_buf) {
+  return cudaMemcpyToSymbol(cf::g_cf_trace, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? 0 : -2;
+}
+
 extern "C" int cgs_critic_fused_supported(int32_t C0, int32_t C1, int32_t C2, int32_t C3, int32_t NB) {
   return C0 == 8 && C1 == 8 && C2 == 8 && C3 == 16 && NB == 32;
 }
 
-extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target, int32_t B, int32_t roll,
-                                      const int32_t* roll_dev, const float* m_e2, const float* m_e3, const float* m_v,
-                                      const cgs_critic_weights* w, const cgs_critic_weights* g, float loss_grad, int32_t bce,
-                                      float* pred, float* loss, void* stream) {
-  CGS_REQUIRE(frames && target && w && g && pred && loss && B > 0, "critic_train_fused: bad args");
-  CGS_REQUIRE(((uintptr_t)frames & 15) == 0, "critic_train_fused: frames must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
-  cf::Params p;
-  p.frames = frames; p.target = target; p.m2 = m_e2; p.m3 = m_e3; p.mv = m_v;
-  p.w0 = w->w0; p.b0 = w->b0; p.w1 = w->w1; p.b1 = w->b1; p.w2 = w->w2; p.b2 = w->b2; p.w3 = w->w3; p.b3 = w->b3;
-  p.w4 = w->w4; p.b4 = w->b4; p.wl1 = w->wl1; p.bl1 = w->bl1; p.wl2 = w->wl2; p.bl2 = w->bl2;
-  float* gs[14] = {(float*)g->w0, (float*)g->b0, (float*)g->w1, (float*)g->b1, (float*)g->w2, (float*)g->b2, (float*)g->w3,
-                   (float*)g->b3, (float*)g->b4, (float*)g->wl1, (float*)g->bl1, (float*)g->wl2, (float*)g->bl2, (float*)g->w4};
-  for (int i = 0; i < 14; ++i) {
-    CGS_REQUIRE(gs[i] != nullptr, "critic_train_fused: gradient tensor %d is NULL", i);
-    p.gseg[i] = gs[i];
-  }
-  p.pred = pred; p.loss = loss; p.roll_dev = roll_dev; p.B = B; p.roll = roll; p.bce = bce;
-  p.inv_n = 1.f / (float)B;
-  p.gscale = loss_grad / (float)B;
+static int cf_sms() {
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// CTAs the whole-step kernel runs for a batch of B frames (= rows of the partial-gradient buffer): frames per CTA are
+// equalised so that no CTA idles a whole frame.
+extern "C" int cgs_critic_fused_grid(int32_t B) {
+  if (B <= 0) return 0;
+  const int sms = cf_sms(), per = (B + sms - 1) / sms;
+  return (B + per - 1) / per;
+}
+extern "C" int cgs_critic_fused_partial_stride(void) { return cf::PSTRIDE; }
+
+extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target, int32_t B, int32_t roll,
+                                      const int32_t* roll_dev, const float* m_e2, const float* m_e3, const float* m_v,
+                                      const cgs_critic_weights* w, const cgs_critic_weights* g, float* partials,
+                                      float loss_grad, int32_t bce, float* pred, float* loss, void* stream) {
+  CGS_REQUIRE(frames && target && w && pred && loss && B > 0 && (g || partials), "critic_train_fused: bad args");
+  CGS_REQUIRE(((uintptr_t)frames & 15) == 0, "critic_train_fused: frames must be 16-byte aligned");
+  CGS_REQUIRE((m_e2 != nullptr) == (m_e3 != nullptr) && (m_e2 != nullptr) == (m_v != nullptr),
+              "critic_train_fused: dropout masks are all-or-none");
+  CGS_REQUIRE((((uintptr_t)m_e2 | (uintptr_t)m_e3 | (uintptr_t)m_v | (uintptr_t)partials) & 15) == 0,
+              "critic_train_fused: masks and partials must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  cf::Params p;
+  p.frames = frames; p.target = target; p.m2 = m_e2; p.m3 = m_e3; p.mv = m_v;
+  p.w0 = w->w0; p.b0 = w->b0; p.w1 = w->w1; p.b1 = w->b1; p.w2 = w->w2; p.b2 = w->b2; p.w3 = w->w3; p.b3 = w->b3;
+  p.w4 = w->w4; p.b4 = w->b4; p.wl1 = w->wl1; p.bl1 = w->bl1; p.wl2 = w->wl2; p.bl2 = w->bl2;
+  for (int i = 0; i < 14; ++i) p.gseg[i] = nullptr;
+  if (!partials) {
+    float* gs[14] = {g->w0, g->b0, g->w1, g->b1, g->w2, g->b2, g->w3, g->b3, g->b4, g->wl1, g->bl1, g->wl2, g->bl2, g->w4};
+    for (int i = 0; i < 14; ++i) {
+      CGS_REQUIRE(gs[i] != nullptr, "critic_train_fused: gradient tensor %d is NULL", i);
+      p.gseg[i] = gs[i];
+    }
+  }
+  p.partials = partials;
+  p.pred = pred; p.loss = loss; p.roll_dev = roll_dev; p.B = B; p.roll = roll; p.bce = bce;
+  p.inv_n = 1.f / (float)B;
+  p.gscale = loss_grad / (float)B;
+  static bool attr = false;
+  if (!attr) {
     cudaFuncSetAttribute(cf::critic_fused_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
+    attr = true;
   }
   if (cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) return check_launch("critic_train_fused.memset");
-  const int per = (B + sms - 1) / sms;           // frames per CTA; equalise so that no CTA idles a whole frame
-  const int grid = (B + per - 1) / per;
-  cf::critic_fused_train_kernel<<<grid, cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
+  cf::critic_fused_train_kernel<<<cgs_critic_fused_grid(B), cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
   return check_launch("critic_train_fused");
 }

@@ -236,9 +236,84 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   }
 }
 
+// Gradient = bucket + the sum of per-CTA partial gradient vectors (written by the whole-step critic kernel instead of
+// same-address REDs), reduced in a FIXED order (bit-reproducible), then either written back to the bucket (data-parallel:
+// the all-reduce comes next) or consumed by Adam in the same pass.  Block = 32 elements x 8 slices of the partial list:
+// every warp reads 128 contiguous bytes per partial, eight partials in flight per thread.
+template <bool ADAM>
+__global__ void __launch_bounds__(256) partials_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                       float* __restrict__ v, int64_t n, const float* __restrict__ part, int np,
+                                                       int64_t stride, int64_t off, int64_t len, double lr, double beta1,
+                                                       double beta2, double eps_d, int* __restrict__ step_state, float gscale) {
+  __shared__ float red[8][33];
+  const int ex = threadIdx.x & 31, ky = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + ex;
+  const int64_t j = i - off;
+  float s0 = 0.f, s1 = 0.f;
+  if (i < n && j >= 0 && j < len) {
+    const float* q = part + j;
+    int k = ky;
+    for (; k + 8 < np; k += 16) { s0 += __ldg(q + k * stride); s1 += __ldg(q + (k + 8) * stride); }
+    if (k < np) s0 += __ldg(q + k * stride);
+  }
+  red[ky][ex] = s0 + s1;
+  __syncthreads();
+  if (ky == 0 && i < n) {
+    float gv = g[i];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) gv += red[r][ex];
+    if (!ADAM) {
+      g[i] = gv;
+    } else {
+      const int t = step_state[0] + 1;
+      const double bc1 = 1.0 - pow(beta1, (double)t);
+      const double bc2 = 1.0 - pow(beta2, (double)t);
+      const float step_size = (float)(lr / bc1);
+      const float bc2_sqrt = (float)sqrt(bc2);
+      const float omb1 = (float)(1.0 - beta1), b2 = (float)beta2, omb2 = (float)(1.0 - beta2), eps = (float)eps_d;
+      gv *= gscale;
+      const float mv = m[i] + omb1 * (gv - m[i]);
+      const float vv = v[i] * b2 + omb2 * gv * gv;
+      m[i] = mv;
+      v[i] = vv;
+      p[i] -= step_size * (mv / (sqrtf(vv) / bc2_sqrt + eps));
+      g[i] = 0.f;
+    }
+  }
+  if (ADAM) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int t = step_state[0] + 1;
+      __threadfence();
+      if (atomicAdd(&step_state[1], 1) == (int)gridDim.x - 1) {
+        step_state[1] = 0;
+        step_state[0] = t;
+      }
+    }
+  }
+}
+
 }  // namespace cgs
 
 using namespace cgs;
+
+extern "C" int cgs_reduce_partials(float* g, int64_t n, const float* partials, int32_t n_partials, int64_t stride,
+                                   int64_t offset, int64_t len, void* stream) {
+  CGS_REQUIRE(g && partials && n > 0 && n_partials > 0 && offset >= 0 && offset + len <= n, "reduce_partials: bad args");
+  partials_kernel<false><<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+      nullptr, g, nullptr, nullptr, n, partials, n_partials, stride, offset, len, 0, 0, 0, 0, nullptr, 1.f);
+  return check_launch("reduce_partials");
+}
+
+extern "C" int cgs_adam_step_partials(float* p, float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                                      double eps, int32_t* step_state, float grad_scale, const float* partials,
+                                      int32_t n_partials, int64_t stride, int64_t offset, int64_t len, void* stream) {
+  CGS_REQUIRE(p && g && m && v && step_state && n > 0 && partials && n_partials > 0 && offset >= 0 && offset + len <= n,
+              "adam_step_partials: bad args");
+  partials_kernel<true><<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, n, partials, n_partials, stride, offset, len, lr, beta1, beta2, eps, step_state, grad_scale);
+  return check_launch("adam_step_partials");
+}
 
 extern "C" int cgs_occlude_fwd(const float* a, const float* b, const float* z, int64_t npix, int32_t C, float* out,
                                void* stream) {

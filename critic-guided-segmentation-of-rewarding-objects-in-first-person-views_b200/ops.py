@@ -477,30 +477,75 @@ def critic_fused_supported(critic):
         f[0].out_channels, f[3].out_channels, f[6].out_channels, f[10].out_channels, f[14].out_channels))
 
 
-def critic_train_fused(critic, frames_u8, target, roll=0, masks=(None, None, None), loss_grad=1.0, bce=False):
+def _critic_bucket_span(params):
+    """(FlatAdam, offset) if the 14 critic parameters are one contiguous run, in registration order, of a FlatAdam's
+    flat gradient bucket (then the kernel may hand its gradient over as per-CTA partial vectors); else (None, 0)."""
+    opt = getattr(params[0], "_cgs_opt", None)
+    if opt is None:
+        return None, 0
+    base = opt.gflat.data_ptr()
+    off0 = None
+    expect = None
+    for q in params:
+        if getattr(q, "_cgs_opt", None) is not opt or q.grad is not getattr(q, "_cgs_grad", None):
+            return None, 0
+        o = (q.grad.data_ptr() - base) // 4
+        if off0 is None:
+            off0 = expect = o
+        if o != expect:
+            return None, 0
+        expect += q.numel()
+    return opt, off0
+
+
+def critic_train_fused(critic, frames_u8, target, roll=0, masks=(None, None, None), loss_grad=1.0, bce=False,
+                       use_partials=True):
     """Forward + loss + backward of one critic_pipe step (reference main.py:185-198) in ONE kernel
-    (cgs_critic_train_fused).  Parameter gradients are ACCUMULATED into each parameter's `.grad` (the FlatAdam
-    bucket views); returns (loss scalar tensor, pred [B])."""
+    (cgs_critic_train_fused).  The parameter gradient is ADDED to the parameters' `.grad`: by REDs, or — when the
+    parameters sit contiguously in a FlatAdam bucket — as per-CTA partial vectors that `FlatAdam.step()` sums inside the
+    Adam kernel (no atomics, bit-reproducible).  Returns (loss scalar tensor, pred [B])."""
     B = frames_u8.shape[0]
     params = list(critic.parameters())          # registration order == state_dict order (nets.py:169-195)
     assert len(params) == 14
-    grads = []
-    for q in params:
-        if q.grad is None:
-            q.grad = torch.zeros_like(q)
-        opt = getattr(q, "_cgs_opt", None)
-        if opt is not None and q.grad is getattr(q, "_cgs_grad", None):
-            opt._clean = False
-        grads.append(q.grad)
+    L = _lib.lib()
+    opt, off = _critic_bucket_span(params) if use_partials else (None, 0)
     w = _lib.CriticWeights(*[_p(q.detach()) for q in params])
-    g = _lib.CriticWeights(*[_p(t) for t in grads])
     pred = torch.empty(B, device=frames_u8.device, dtype=torch.float32)
     loss = torch.empty(1, device=frames_u8.device, dtype=torch.float32)
     rd, r = (_p(roll, torch.int32), 0) if torch.is_tensor(roll) else (None, int(roll or 0))
     m2, m3, mv = masks
+    if opt is not None:
+        grid, stride = L.cgs_critic_fused_grid(B), L.cgs_critic_fused_partial_stride()
+        opt.flush_partials()                                       # an unconsumed earlier hand-over goes into the bucket first
+        buf = opt.partial_buffer(grid * stride)
+        _call("cgs_critic_train_fused", _p(frames_u8, torch.uint8), _p(target), B, r, rd, _p(m2), _p(m3), _p(mv),
+              C.byref(w), None, _p(buf), float(loss_grad), int(bool(bce)), _p(pred), _p(loss), _stream())
+        opt.pending_partials = (buf, grid, stride, off, sum(q.numel() for q in params))
+        return loss.reshape(()), pred
+    grads = []
+    for q in params:
+        if q.grad is None:
+            q.grad = torch.zeros_like(q)
+        o = getattr(q, "_cgs_opt", None)
+        if o is not None and q.grad is getattr(q, "_cgs_grad", None):
+            o._clean = False
+        grads.append(q.grad)
+    g = _lib.CriticWeights(*[_p(t) for t in grads])
     _call("cgs_critic_train_fused", _p(frames_u8, torch.uint8), _p(target), B, r, rd, _p(m2), _p(m3), _p(mv),
-          C.byref(w), C.byref(g), float(loss_grad), int(bool(bce)), _p(pred), _p(loss), _stream())
+          C.byref(w), C.byref(g), None, float(loss_grad), int(bool(bce)), _p(pred), _p(loss), _stream())
     return loss.reshape(()), pred
+
+
+def reduce_partials(g, buf, n_partials, stride, offset, length):
+    _call("cgs_reduce_partials", _p(g), g.numel(), _p(buf), int(n_partials), int(stride), int(offset), int(length), _stream())
+
+
+def adam_step_partials(p, g, m, v, step_state, buf, n_partials, stride, offset, length, lr=1e-3, betas=(0.9, 0.999),
+                       eps=1e-8, grad_scale=1.0):
+    """adam_step whose gradient is g + the sum of the per-CTA partial vectors in `buf`; g is cleared."""
+    _call("cgs_adam_step_partials", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(betas[0]), float(betas[1]),
+          float(eps), _p(step_state, torch.int32), float(grad_scale), _p(buf), int(n_partials), int(stride), int(offset),
+          int(length), _stream())
 
 
 def threshold(z, thresh, strict=False):

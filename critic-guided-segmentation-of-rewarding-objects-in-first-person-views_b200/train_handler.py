@@ -92,9 +92,27 @@ class FlatAdam:
                 off += k
         self.lr, self.betas, self.eps = lr, betas, eps
         self.group, self.world = process_group, world_size
+        # gradient handed over by the whole-step critic kernel as per-CTA partial vectors (ops.critic_train_fused):
+        # (buffer, rows, row stride, bucket offset, length), summed in step() instead of RED-accumulated by the kernel
+        self.pending_partials = None
+        self._pbuf = None
+
+    def partial_buffer(self, numel):
+        if self._pbuf is None or self._pbuf.numel() < numel:
+            self._pbuf = torch.empty(numel, device=self.flat.device, dtype=torch.float32)
+        return self._pbuf
+
+    def flush_partials(self):
+        """Fold a pending partial-gradient hand-over into the bucket (so that `.grad` is complete)."""
+        if self.pending_partials is not None:
+            buf, rows, stride, off, length = self.pending_partials
+            ops.reduce_partials(self.gflat, buf, rows, stride, off, length)
+            self.pending_partials = None
+            self._clean = False
 
     def zero_grad(self):
         ops.join_wgrad()
+        self.pending_partials = None
         if not self._clean:          # step() already cleared the bucket inside the Adam kernel
             self.gflat.zero_()
             self._clean = True
@@ -102,9 +120,16 @@ class FlatAdam:
     def step(self):
         ops.join_wgrad()           # wgrad kernels forked onto the side stream have all landed in the bucket
         if self.world > 1:
+            self.flush_partials()
             torch.distributed.all_reduce(self.gflat, group=self.group)   # ranks pre-scale their losses by 1/world
-        ops.adam_step(self.flat, self.gflat, self.m, self.v, self.step_count, self.lr, self.betas, self.eps,
-                      clear_grad=True)
+        if self.pending_partials is not None:
+            buf, rows, stride, off, length = self.pending_partials
+            ops.adam_step_partials(self.flat, self.gflat, self.m, self.v, self.step_count, buf, rows, stride, off, length,
+                                   self.lr, self.betas, self.eps)
+            self.pending_partials = None
+        else:
+            ops.adam_step(self.flat, self.gflat, self.m, self.v, self.step_count, self.lr, self.betas, self.eps,
+                          clear_grad=True)
         self._clean = True
 
 

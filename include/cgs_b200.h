@@ -156,10 +156,28 @@ typedef struct cgs_critic_weights {
  * in shared memory; TF32 tensor-core (mma.sync) convolutions with fp32 accumulation, fp32 head.
  * Outputs: pred [B]; loss[0] = mean loss over the B frames; the gradient of (loss_grad * loss) is ACCUMULATED into *g. */
 int cgs_critic_fused_supported(int32_t C0, int32_t C1, int32_t C2, int32_t C3, int32_t NB);
+/* Gradient delivery: either REDs into the 14 tensors of *g (partials == NULL), or — cheaper, and bit-reproducible — one
+ * partial gradient vector per CTA, partials[cta * cgs_critic_fused_partial_stride() + i], i over the 11,873 critic
+ * parameters in state_dict order, cta < cgs_critic_fused_grid(B); the consumer sums them (cgs_adam_step_partials /
+ * cgs_reduce_partials).  Every partial row is fully overwritten by each call. */
+int cgs_critic_fused_grid(int32_t B);
+int cgs_critic_fused_partial_stride(void);
 int cgs_critic_train_fused(const uint8_t* frames, const float* target, int32_t B, int32_t roll, const int32_t* roll_dev,
                            const float* m_e2, const float* m_e3, const float* m_v,
-                           const cgs_critic_weights* w, const cgs_critic_weights* g, float loss_grad, int32_t bce,
-                           float* pred, float* loss, void* stream);
+                           const cgs_critic_weights* w, const cgs_critic_weights* g, float* partials,
+                           float loss_grad, int32_t bce, float* pred, float* loss, void* stream);
+
+/* g[offset + j] += sum_k partials[k * stride + j], j < len, summed in a fixed order (data-parallel path: all-reduce next). */
+int cgs_reduce_partials(float* g, int64_t n, const float* partials, int32_t n_partials, int64_t stride,
+                        int64_t offset, int64_t len, void* stream);
+/* cgs_adam_step whose gradient is g[i] + sum_k partials[k * stride + (i - offset)] (inside [offset, offset + len));
+ * g is cleared.  Replaces the gradient-REDs + Adam pair of the single-GPU critic step. */
+int cgs_adam_step_partials(float* p, float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                           double eps, int32_t* step_state, float grad_scale, const float* partials,
+                           int32_t n_partials, int64_t stride, int64_t offset, int64_t len, void* stream);
+
+/* Debug only: clock64() phase trace of CTA 0 of the fused critic kernel into dev_buf[4*24] (NULL disables). */
+int cgs_critic_fused_set_trace(long long* dev_buf);
 
 /* Dense layer out[B,N] = in[B,K] * w[N,K]^T + bias: UnetDecoder.dec[4], the 1x1 conv on the
  * 1x1 bottleneck (nets.py:484,500-501). */

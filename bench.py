@@ -204,6 +204,36 @@ def kernel_rooflines(B, chfak, flush, hbm_gbs):
     return out
 
 
+def fused_step_roofline(B, flush, hbm_gbs, tf_peak):
+    """The whole-step critic kernel (csrc/critic_fused.cu) timed alone: one graph node replayed between CUDA events, L2
+    flushed in between.  Algorithmic work per frame: 8,460,480 FLOP; compulsory HBM bytes 12,288 (uint8
+    frame) + 4 (label) + 3,200 (dropout masks the kernel is handed)."""
+    from cgs_b200 import ops
+    from cgs_b200.nets import NewCritic
+    from cgs_b200.train_handler import FlatAdam
+    torch.manual_seed(0)
+    c = NewCritic(dropout=0.3).cuda().train()
+    opt = FlatAdam(c.parameters())
+    X = torch.randint(0, 255, (B, 64, 64, 3), dtype=torch.uint8, device="cuda")
+    Y = torch.rand(B, device="cuda")
+    masks = c._dropout_masks(B, X.device)
+    run = lambda: ops.critic_train_fused(c, X, Y, 3, masks)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        run()
+    sec = time_kernel(g.replay, flush)
+    flops, byts = 8460480 * B, (12288 + 4 + 3200) * B
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    mma_peak = sms * 512 * 2 * 1.965e9 / 1e12      # mma.sync m16n8k8 TF32: 2.0 clk per instruction per SM (tools/mma_rate.cu)
+    return {"kernel": "critic_fused_train_kernel", "desc": "frame -> forward -> loss -> backward, all activations in smem",
+            "sec": sec, "flops": flops, "bytes": byts, "tflops": flops / sec / 1e12, "gbs": byts / sec / 1e9,
+            "frac_hbm": byts / sec / 1e9 / hbm_gbs, "frac_tensor_bf16_peak": flops / sec / 1e12 / tf_peak,
+            "mma_sync_tf32_peak_tflops": mma_peak, "frac_mma_sync_tf32_peak": flops / sec / 1e12 / mma_peak}
+
+
 def run_ours(args, rank, world):
     import torch.distributed as dist
     from cgs_b200 import ops
@@ -260,14 +290,18 @@ def run_ours(args, rank, world):
     # ---- e2e: pinned host buffers -> H2D -> step -> D2H of the step's result, every step, through the public API
     if args.workload == "critic_train":
         from cgs_b200.graph_step import PipelinedCriticTrainer
-        trainer = PipelinedCriticTrainer(H, B)            # double-buffered H2D, async loss read-back
-        for _ in range(4):
-            trainer.step(*host)
+        trainer = PipelinedCriticTrainer(H, B)            # chunked double-buffered H2D, async loss read-back
+        nb = max(1, min(32, K))                           # pinned host dataset of nb batches, walked K steps in total
+        Xds = torch.from_numpy(np.concatenate([X] * nb)).pin_memory()
+        Yds = torch.from_numpy(np.tile(Y[1, :B], nb)).float().pin_memory()
+        trainer.train(Xds, Yds)
         sync()
         n0 = trainer.i
         t0 = time.perf_counter()
-        for _ in range(K):
-            trainer.step(*host)
+        done = 0
+        while done < K:
+            m = min(nb, K - done)
+            done += trainer.train(Xds[:m * B], Yds[:m * B])
         losses = trainer.losses()                          # synchronises: all K losses are on the host
         sync()
         e2e_s = time.perf_counter() - t0
@@ -299,8 +333,10 @@ def run_ours(args, rank, world):
                 "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
                 "config": {"workload": WORKLOADS[args.workload], "batch_per_gpu": B, "global_batch": B * world,
-                           "precision": ("conv fprop/dgrad: tcgen05 kind::tf32, fp32 accumulate in TMEM; wgrad, head, "
-                                         "losses, Adam: fp32" if args.precision == "tf32" else "all fp32 (FFMA)"),
+                           "precision": (("whole step in one kernel: TF32 mma.sync convolutions (fprop, dgrad, wgrad), fp32 "
+                                          "accumulate; head, loss, Adam fp32" if (args.workload == "critic_train" and args.chfak == 1)
+                                          else "conv fprop/dgrad: tcgen05 kind::tf32, fp32 accumulate in TMEM; wgrad: TF32 mma.sync; "
+                                          "head, losses, Adam: fp32") if args.precision == "tf32" else "all fp32 (FFMA)"),
                            "chfak": args.chfak, "parallelism": f"dp{world}", "timing": "cuda events per step, L2 flushed "
                            "(256 MiB memset) between timed steps", "graph": True},
                 "e2e": {"value": world * B * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d,
@@ -309,16 +345,35 @@ def run_ours(args, rank, world):
                 "wall_ms_per_step_incl_flush": 1e3 * t_wall / K, "clocks": clocks,
                 "achieved_tflops": FLOPS[args.workload].get(args.chfak, 0) * value / 1e12}
         if world == 1 and not args.no_extras:
-            ks = kernel_rooflines(B, args.chfak, flush, hbm)
-            top = max(ks, key=lambda k: k["sec"])
             tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-            traffic = json.load(open(tpath)).get(top["kernel"]) if (os.path.exists(tpath) and args.chfak == 1 and B == 256) else None
-            line["roofline"] = {"bound": "hbm", "achieved": top["gbs"], "peak": hbm, "unit": "GB/s",
-                                "frac": top["gbs"] / hbm, "traffic": traffic, "kernel": top["kernel"],
-                                "algorithmic_bytes": top["bytes"],
-                                "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
-                                "launch_us": top["sec"] * 1e6, "achieved_tflops_fp32": top["tflops"]}
-            line["kernels"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in kk.items()} for kk in ks]
+            tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+            fused = (args.workload == "critic_train" and args.precision == "tf32" and args.chfak == 1)
+            if fused:
+                # dominant kernel = the whole-step kernel (79 % of the step, profiles/): a dense-contraction kernel whose
+                # operands never leave shared memory -> tensor roofline; HBM traffic is the uint8 frames only
+                pj = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if which == "measured" else {}
+                tf_burst = pj.get("bf16_tflops", 1590.0)
+                k = fused_step_roofline(B, flush, hbm, tf_burst)
+                line["roofline"] = {"bound": "tensor", "achieved": k["tflops"], "peak": tf_burst, "unit": "TFLOP/s",
+                                    "frac": k["frac_tensor_bf16_peak"], "traffic": tj.get(k["kernel"]) if B == 256 else None,
+                                    "kernel": k["kernel"], "algorithmic_flops": k["flops"], "algorithmic_bytes": k["bytes"],
+                                    "peak_source": which + " (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)",
+                                    "launch_us": k["sec"] * 1e6, "hbm_gbs_achieved": k["gbs"], "frac_hbm": k["frac_hbm"],
+                                    "mma_sync_tf32_peak_tflops": k["mma_sync_tf32_peak_tflops"],
+                                    "frac_of_mma_sync_tf32_peak": k["frac_mma_sync_tf32_peak"],
+                                    "note": "TF32 mma.sync m16n8k8 (N = 8 output channels rules out tcgen05 tiles); its own "
+                                            "measured peak is 512 MAC/clk/SM = 0.18 of the bf16 tcgen05 peak"}
+                line["kernels"] = [{kk: (round(v, 4) if isinstance(v, float) else v) for kk, v in k.items()}]
+            else:
+                ks = kernel_rooflines(B, args.chfak, flush, hbm)
+                top = max(ks, key=lambda k: k["sec"])
+                traffic = tj.get(top["kernel"]) if (args.chfak == 1 and B == 256) else None
+                line["roofline"] = {"bound": "hbm", "achieved": top["gbs"], "peak": hbm, "unit": "GB/s",
+                                    "frac": top["gbs"] / hbm, "traffic": traffic, "kernel": top["kernel"],
+                                    "algorithmic_bytes": top["bytes"],
+                                    "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
+                                    "launch_us": top["sec"] * 1e6, "achieved_tflops_fp32": top["tflops"]}
+                line["kernels"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in kk.items()} for kk in ks]
             # CPU baseline: oracle port on the host cores, bounded sample
             cores = os.cpu_count()
             torch.set_num_threads(cores)

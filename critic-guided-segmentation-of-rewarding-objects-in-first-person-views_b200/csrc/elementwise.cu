@@ -249,14 +249,18 @@ __global__ void __launch_bounds__(256) partials_kernel(float* __restrict__ p, fl
   const int ex = threadIdx.x & 31, ky = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * 32 + ex;
   const int64_t j = i - off;
-  float s0 = 0.f, s1 = 0.f;
+  float s0 = 0.f;
   if (i < n && j >= 0 && j < len) {
     const float* q = part + j;
-    int k = ky;
-    for (; k + 8 < np; k += 16) { s0 += __ldg(q + k * stride); s1 += __ldg(q + (k + 8) * stride); }
-    if (k < np) s0 += __ldg(q + k * stride);
+    for (int k0 = ky; k0 < np; k0 += 128) {        // 16 loads in flight per thread: one L2 round trip for <= 128 partials
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = (k0 + 8 * u < np) ? __ldg(q + (int64_t)(k0 + 8 * u) * stride) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) s0 += v[u];
+    }
   }
-  red[ky][ex] = s0 + s1;
+  red[ky][ex] = s0;
   __syncthreads();
   if (ky == 0 && i < n) {
     float gv = g[i];

@@ -47,6 +47,10 @@ EXPORTS = {
     "cgs_reduce_partials": [_f32p, C.c_int64, _f32p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p],
     "cgs_adam_step_partials": [_f32p] * 4 + [C.c_int64] + [C.c_double] * 4 + [C.c_void_p, C.c_float, _f32p, C.c_int32,
                                                                              C.c_int64, C.c_int64, C.c_int64, C.c_void_p],
+    "cgs_p2p_stage": [_f32p, C.c_int64, C.c_int64, _f32p, _f32p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                      C.c_void_p],
+    "cgs_p2p_allreduce_adam": [_f32p, _f32p, _f32p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32] +
+                              [C.c_double] * 4 + [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p],
     "cgs_conv3x3": [C.POINTER(Conv3x3Args), C.c_void_p],
     "cgs_wgrad3x3": [C.POINTER(Wgrad3x3Args), C.c_void_p],
     "cgs_conv_rgb_fwd": [_u8p] + [C.c_int32] * 4 + [C.c_void_p, _f32p, _f32p, C.c_int32, _f32p, _u8p, C.c_void_p],

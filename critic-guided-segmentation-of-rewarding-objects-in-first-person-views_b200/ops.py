@@ -562,6 +562,21 @@ def adam_step(p, g, m, v, step_state, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, gra
           float(eps), _p(step_state, torch.int32), float(grad_scale), int(clear_grad), _stream())
 
 
+def p2p_stage(g, npad, sym, step_state, partials=None):
+    """Local gradient (bucket + optional per-CTA partials) -> this rank's symmetric buffer slot of the coming step."""
+    buf, rows, stride, off, length = partials if partials is not None else (None, 0, 0, 0, 0)
+    _call("cgs_p2p_stage", _p(g), g.numel(), int(npad), _p(sym), _p(buf), int(rows), int(stride), int(off), int(length),
+          _p(step_state, torch.int32), _stream())
+
+
+def p2p_allreduce_adam(p, m, v, npad, peer_bufs, peer_flags, rank, world, step_state, err, lr=1e-3, betas=(0.9, 0.999),
+                       eps=1e-8, grad_scale=1.0):
+    """One-shot all-reduce over NVLink peer memory fused with Adam (cgs_p2p_allreduce_adam)."""
+    _call("cgs_p2p_allreduce_adam", _p(p), _p(m), _p(v), p.numel(), int(npad), peer_bufs, peer_flags, int(rank), int(world),
+          float(lr), float(betas[0]), float(betas[1]), float(eps), _p(step_state, torch.int32), float(grad_scale),
+          _p(err, torch.int32), _stream())
+
+
 def occlude(a, b, z):
     return Occlude.apply(a, b, z)
 

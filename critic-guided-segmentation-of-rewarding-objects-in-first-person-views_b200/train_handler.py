@@ -96,6 +96,41 @@ class FlatAdam:
         # (buffer, rows, row stride, bucket offset, length), summed in step() instead of RED-accumulated by the kernel
         self.pending_partials = None
         self._pbuf = None
+        self._p2p = None
+        if world_size > 1 and dev.type == "cuda" and os.environ.get("CGS_P2P", "1") != "0":
+            self._p2p = self._setup_p2p(n, dev)
+
+    def _setup_p2p(self, n, dev):
+        """Symmetric gradient buffer [2][npad] + flag pad mapped into every peer (one node, NVLink): the all-reduce then
+        is `world` peer loads per element inside the Adam kernel (csrc/p2p_adam.cu) instead of an NCCL launch.
+        Returns None (-> NCCL all-reduce) if symmetric memory cannot be set up on this system."""
+        import ctypes
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            if self.world > 16:
+                return None
+            npad = (n + 63) // 64 * 64
+            sym = symm.empty(2 * npad, dtype=torch.float32, device=dev)
+            flags = symm.empty(64, dtype=torch.int32, device=dev)
+            sym.zero_(); flags.zero_()
+            torch.cuda.synchronize()
+            group = self.group if self.group is not None else dist.group.WORLD
+            hs, hf = symm.rendezvous(sym, group), symm.rendezvous(flags, group)
+            dist.barrier(group=group)
+            torch.cuda.synchronize()
+            W = self.world
+            return dict(npad=npad, sym=sym, flags=flags, hs=hs, hf=hf, rank=dist.get_rank(group),
+                        bufs=(ctypes.c_uint64 * W)(*[int(x) for x in hs.buffer_ptrs]),
+                        pads=(ctypes.c_uint64 * W)(*[int(x) for x in hf.buffer_ptrs]),
+                        err=torch.zeros(1, dtype=torch.int32, device=dev))
+        except Exception as e:          # no peer access / fabric handles on this system: NCCL carries the bucket instead
+            print(f"cgs_b200: symmetric-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL")
+            return None
+
+    def p2p_ok(self):
+        """False if a peer ever failed to announce its gradient in time (reads a device flag; synchronises)."""
+        return self._p2p is None or int(self._p2p["err"].item()) == 0
 
     def partial_buffer(self, numel):
         if self._pbuf is None or self._pbuf.numel() < numel:
@@ -119,6 +154,14 @@ class FlatAdam:
 
     def step(self):
         ops.join_wgrad()           # wgrad kernels forked onto the side stream have all landed in the bucket
+        if self._p2p is not None:
+            q = self._p2p
+            ops.p2p_stage(self.gflat, q["npad"], q["sym"], self.step_count, self.pending_partials)
+            self.pending_partials = None
+            ops.p2p_allreduce_adam(self.flat, self.m, self.v, q["npad"], q["bufs"], q["pads"], q["rank"], self.world,
+                                   self.step_count, q["err"], self.lr, self.betas, self.eps)
+            self._clean = True
+            return
         if self.world > 1:
             self.flush_partials()
             torch.distributed.all_reduce(self.gflat, group=self.group)   # ranks pre-scale their losses by 1/world

@@ -176,6 +176,20 @@ int cgs_adam_step_partials(float* p, float* g, float* m, float* v, int64_t n, do
                            double eps, int32_t* step_state, float grad_scale, const float* partials,
                            int32_t n_partials, int64_t stride, int64_t offset, int64_t len, void* stream);
 
+/* Data-parallel gradient exchange fused with Adam over NVLink peer memory (csrc/p2p_adam.cu).  Every rank owns a SYMMETRIC
+ * gradient buffer sym[2][npad] and a flag pad (>= 16 uint32, zeroed once), both mapped into all peers.
+ * cgs_p2p_stage: sym_local[slot][i] = g[i] + sum_k partials[k*stride + i - offset] (n_partials may be 0), g cleared;
+ *   slot = (step_state[0] + 1) & 1 is read on the device, so the call is CUDA-graph replayable.
+ * cgs_p2p_allreduce_adam: announce step t to all peers, wait for theirs (bounded spin; *err_flag = 1 on time-out), sum the
+ *   `world` buffers in rank order through peer loads, apply Adam (torch defaults, as cgs_adam_step) to p/m/v.
+ *   peer_bufs / peer_flags: HOST arrays of `world` device addresses (this process's mappings of each rank's allocation).
+ * Replaces torch.distributed.all_reduce(gradient bucket) + optimizer.step() of the data-parallel loops. */
+int cgs_p2p_stage(float* g, int64_t n, int64_t npad, float* sym_local, const float* partials, int32_t n_partials,
+                  int64_t stride, int64_t offset, int64_t len, const int32_t* step_state, void* stream);
+int cgs_p2p_allreduce_adam(float* p, float* m, float* v, int64_t n, int64_t npad, const uint64_t* peer_bufs,
+                           const uint64_t* peer_flags, int32_t rank, int32_t world, double lr, double beta1, double beta2,
+                           double eps, int32_t* step_state, float grad_scale, int32_t* err_flag, void* stream);
+
 /* Debug only: clock64() phase trace of CTA 0 of the fused critic kernel into dev_buf[4*24] (NULL disables). */
 int cgs_critic_fused_set_trace(long long* dev_buf);
 

@@ -25,7 +25,18 @@ Xs = torch.from_numpy(X[rank * B:(rank + 1) * B]).to(dev); Ys = torch.from_numpy
 opt = FlatAdam(H.critic.parameters(), process_group=dist.group.WORLD, world_size=world)
 for i in range(3):
     l = H.critic_step(Xs, Ys, opt)
-torch.cuda.synchronize(); say("eager DP steps ok, loss", float(l))
+torch.cuda.synchronize(); say("eager DP steps ok, loss", float(l), "| p2p all-reduce:", opt._p2p is not None, "ok:", opt.p2p_ok())
+if opt._p2p is not None:      # same three steps with the NCCL all-reduce instead of the peer-memory kernel
+    os.environ["CGS_P2P"] = "0"
+    torch.manual_seed(0)
+    Hn = Handler(parse_args(["--dropout", "0"]), device=dev, rank=rank, world_size=world, process_group=dist.group.WORLD)
+    Hn.critic.to(dev)
+    on = FlatAdam(Hn.critic.parameters(), process_group=dist.group.WORLD, world_size=world)
+    os.environ["CGS_P2P"] = "1"
+    for i in range(3):
+        Hn.critic_step(Xs, Ys, on)
+    torch.cuda.synchronize()
+    say(f"p2p vs NCCL: max |dparam| = {(on.flat - opt.flat).abs().max().item():.3e}")
 flat = opt.flat.clone(); ref = flat.clone(); dist.broadcast(ref, 0); torch.cuda.synchronize()
 say("params equal across ranks:", bool(torch.equal(flat, ref)))
 if world > 1 and rank == 0:

@@ -40,6 +40,7 @@ class CriticWeights(C.Structure):
 EXPORTS = {
     "cgs_critic_fused_supported": [C.c_int32] * 5,
     "cgs_critic_train_fused": [_u8p, _f32p, C.c_int32, C.c_int32, C.c_void_p, _f32p, _f32p, _f32p,
+                               C.c_float, C.c_uint64, C.c_void_p,
                                C.POINTER(CriticWeights), C.POINTER(CriticWeights), _f32p, C.c_float, C.c_int32, _f32p, _f32p,
                                C.c_void_p],
     "cgs_critic_fused_grid": [C.c_int32],

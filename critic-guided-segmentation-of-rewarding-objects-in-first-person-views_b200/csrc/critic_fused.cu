@@ -70,6 +70,9 @@ struct Params {
   const float *m2, *m3, *mv;
   const float *w0, *b0, *w1, *b1, *w2, *b2, *w3, *b3, *w4, *b4, *wl1, *bl1, *wl2, *bl2;
   float* gseg[14];      // gradient tensors in sAcc order (w0 b0 w1 b1 w2 b2 w3 b3 b4 wl1 bl1 wl2 bl2) + [13] = w4
+  unsigned long long seed;          // rng_state != NULL: dropout masks are drawn in the kernel (Philox4x32-10, the stream of
+  unsigned long long* rng_state;    // cgs_dropout_masks: counter = (float4 index in the [m2|m3|mv] buffer, call), key = seed)
+  float p_drop, keep;
   float* partials;      // != NULL: per-CTA partial gradients [grid][PSTRIDE] in flat order instead of REDs into gseg
   float* pred;
   float* loss;
@@ -224,6 +227,36 @@ __device__ __forceinline__ void stage_frame(const uint8_t* __restrict__ sU8, flo
   }
 }
 
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+// The three dropout masks of frame n, drawn exactly as cgs_dropout_masks would fill [B*512 | B*256 | B*32] floats:
+// 200 threads, one Philox call (4 Bernoulli draws) each.
+__device__ __forceinline__ void draw_masks(const Params& p, int n, unsigned long long call, float* sm, int tid) {
+  if (tid >= 200) return;
+  long long vec;
+  float* dst;
+  if (tid < 128) { vec = (long long)n * 128 + tid; dst = sm + oM2 + tid * 4; }
+  else if (tid < 192) { vec = (long long)p.B * 128 + (long long)n * 64 + (tid - 128); dst = sm + oM3 + (tid - 128) * 4; }
+  else { vec = (long long)p.B * 192 + (long long)n * 8 + (tid - 192); dst = sm + oHead + 64 + (tid - 192) * 4; }
+  uint32_t c[4] = {(uint32_t)vec, (uint32_t)(vec >> 32), (uint32_t)call, (uint32_t)(call >> 32)};
+  philox4x32_10(c, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+  float4 v;
+  v.x = ((float)(c[0] >> 8) * (1.0f / 16777216.0f) >= p.p_drop) ? p.keep : 0.f;
+  v.y = ((float)(c[1] >> 8) * (1.0f / 16777216.0f) >= p.p_drop) ? p.keep : 0.f;
+  v.z = ((float)(c[2] >> 8) * (1.0f / 16777216.0f) >= p.p_drop) ? p.keep : 0.f;
+  v.w = ((float)(c[3] >> 8) * (1.0f / 16777216.0f) >= p.p_drop) ? p.keep : 0.f;
+  *reinterpret_cast<float4*>(dst) = v;
+}
+
 // cp.async: the raw frame (12288 B) and its dropout masks (512 + 256 + 32 floats) for frame n
 __device__ __forceinline__ void prefetch_frame(const Params& p, int n, float* sm, int tid) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(sm + oU8);
@@ -255,7 +288,11 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
   long long* trace = blockIdx.x == 0 ? g_cf_trace : nullptr;
   int fr = 0;
   CF_MARK(23);
-  if (blockIdx.x < p.B) prefetch_frame(p, blockIdx.x, sm, tid);
+  const unsigned long long rng_call = p.rng_state ? p.rng_state[0] : 0ull;
+  if (blockIdx.x < p.B) {
+    prefetch_frame(p, blockIdx.x, sm, tid);
+    if (p.rng_state) draw_masks(p, blockIdx.x, rng_call, sm, tid);
+  }
 
   // ---- prologue: accumulators, halos that stay zero, weight fragments (TF32, in mma B-fragment order), biases
   for (int e = tid; e < szAcc; e += NT) sAcc[e] = 0.f;
@@ -298,7 +335,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     sm[oHW + hB4 + tid] = __ldg(p.b4 + tid);
   }
   if (tid == 0) sm[oHW + hBl2] = __ldg(p.bl2);
-  if (!p.m2) {                                     // eval mode / p = 0: identity masks, written once
+  if (!p.m2 && !p.rng_state) {                     // eval mode / p = 0: identity masks, written once
     sm[oM2 + tid] = 1.f;
     if (tid < 256) sm[oM3 + tid] = 1.f;
     if (tid < 32) sm[oHead + 64 + tid] = 1.f;
@@ -693,7 +730,10 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     // ================= B0a: frame again (region A is free now), then start fetching the next frame
     stage_frame(reinterpret_cast<const uint8_t*>(sm + oU8), sm + oXB, roll, tid);
     __syncthreads();
-    if (n + (int)gridDim.x < p.B) prefetch_frame(p, n + gridDim.x, sm, tid);
+    if (n + (int)gridDim.x < p.B) {
+      prefetch_frame(p, n + gridDim.x, sm, tid);
+      if (p.rng_state) draw_masks(p, n + gridDim.x, rng_call, sm, tid);
+    }
     CF_MARK(14);
     // ================= B0: features.0 weight gradient, K = 4096 pixels over 16 warps (4 rows each), registers
     {
@@ -798,6 +838,13 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     for (int i = 0; i < 16; ++i) atomicAdd(d4 + (((i >> 2) + rot4) & 3) * 4 + (i & 3), accW4[i]);
   }
   if (tid == 0 && blockIdx.x < p.B) atomicAdd(p.loss, loss_acc * p.inv_n);
+  if (p.rng_state && tid == 0) {                  // last CTA to finish advances the call counter (every CTA has read it)
+    __threadfence();
+    if (atomicAdd(&p.rng_state[1], 1ull) == gridDim.x - 1) {
+      p.rng_state[1] = 0;
+      p.rng_state[0] = rng_call + 1;
+    }
+  }
   CF_MARK(16);
 }
 
@@ -836,6 +883,7 @@ extern "C" int cgs_critic_fused_partial_stride(void) { return cf::PSTRIDE; }
 
 extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target, int32_t B, int32_t roll,
                                       const int32_t* roll_dev, const float* m_e2, const float* m_e3, const float* m_v,
+                                      float p_drop, uint64_t seed, uint64_t* rng_state,
                                       const cgs_critic_weights* w, const cgs_critic_weights* g, float* partials,
                                       float loss_grad, int32_t bce, float* pred, float* loss, void* stream) {
   CGS_REQUIRE(frames && target && w && pred && loss && B > 0 && (g || partials), "critic_train_fused: bad args");
@@ -857,6 +905,10 @@ extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target
       p.gseg[i] = gs[i];
     }
   }
+  CGS_REQUIRE(!(rng_state && m_e2), "critic_train_fused: pass dropout masks OR an rng state, not both");
+  CGS_REQUIRE(!rng_state || (p_drop > 0.f && p_drop < 1.f), "critic_train_fused: rng dropout needs 0 < p < 1");
+  p.seed = seed; p.rng_state = (unsigned long long*)rng_state; p.p_drop = p_drop;
+  p.keep = rng_state ? 1.f / (1.f - p_drop) : 1.f;
   p.partials = partials;
   p.pred = pred; p.loss = loss; p.roll_dev = roll_dev; p.B = B; p.roll = roll; p.bce = bce;
   p.inv_n = 1.f / (float)B;

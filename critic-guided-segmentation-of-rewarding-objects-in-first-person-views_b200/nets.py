@@ -91,6 +91,16 @@ class NewCritic(nn.Module):
             self._rng_seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._instance) & 0x7FFFFFFFFFFFFFFF
         return tuple(ops.dropout_masks([(B, 8, 8, c2), (B, 4, 4, c3), (B, nb)], self.p, self._rng_seed, self._rng_state))
 
+    def _dropout_rng(self, device):
+        """(p, seed, state) of this module's Philox stream when the masks can be drawn inside a fused kernel (train mode,
+        0 < p < 1, no forced masks): the same stream `_dropout_masks` would consume, one call per forward.  Else None."""
+        if self._forced_masks is not None or not self.training or not (0.0 < self.p < 1.0):
+            return None
+        if self._rng_state is None or self._rng_state.device != device:
+            self._rng_state = torch.zeros(2, dtype=torch.int64, device=device)
+            self._rng_seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._instance) & 0x7FFFFFFFFFFFFFFF
+        return self.p, self._rng_seed, self._rng_state
+
     def forward(self, X, collect=False):
         return self._run(_nhwc(X, self.colorchs, self.width, "NewCritic"), None, collect)
 

@@ -499,7 +499,7 @@ def _critic_bucket_span(params):
 
 
 def critic_train_fused(critic, frames_u8, target, roll=0, masks=(None, None, None), loss_grad=1.0, bce=False,
-                       use_partials=True):
+                       use_partials=True, rng=None):
     """Forward + loss + backward of one critic_pipe step (reference main.py:185-198) in ONE kernel
     (cgs_critic_train_fused).  The parameter gradient is ADDED to the parameters' `.grad`: by REDs, or — when the
     parameters sit contiguously in a FlatAdam bucket — as per-CTA partial vectors that `FlatAdam.step()` sums inside the
@@ -514,12 +514,14 @@ def critic_train_fused(critic, frames_u8, target, roll=0, masks=(None, None, Non
     loss = torch.empty(1, device=frames_u8.device, dtype=torch.float32)
     rd, r = (_p(roll, torch.int32), 0) if torch.is_tensor(roll) else (None, int(roll or 0))
     m2, m3, mv = masks
+    # rng = (p, seed, int64 state tensor): masks drawn inside the kernel from the module's Philox stream
+    rp, rseed, rstate = (float(rng[0]), int(rng[1]) & 0xFFFFFFFFFFFFFFFF, _p(rng[2], torch.int64)) if rng is not None else (0.0, 0, None)
     if opt is not None:
         grid, stride = L.cgs_critic_fused_grid(B), L.cgs_critic_fused_partial_stride()
         opt.flush_partials()                                       # an unconsumed earlier hand-over goes into the bucket first
         buf = opt.partial_buffer(grid * stride)
         _call("cgs_critic_train_fused", _p(frames_u8, torch.uint8), _p(target), B, r, rd, _p(m2), _p(m3), _p(mv),
-              C.byref(w), None, _p(buf), float(loss_grad), int(bool(bce)), _p(pred), _p(loss), _stream())
+              rp, rseed, rstate, C.byref(w), None, _p(buf), float(loss_grad), int(bool(bce)), _p(pred), _p(loss), _stream())
         opt.pending_partials = (buf, grid, stride, off, sum(q.numel() for q in params))
         return loss.reshape(()), pred
     grads = []
@@ -532,7 +534,7 @@ def critic_train_fused(critic, frames_u8, target, roll=0, masks=(None, None, Non
         grads.append(q.grad)
     g = _lib.CriticWeights(*[_p(t) for t in grads])
     _call("cgs_critic_train_fused", _p(frames_u8, torch.uint8), _p(target), B, r, rd, _p(m2), _p(m3), _p(mv),
-          C.byref(w), C.byref(g), None, float(loss_grad), int(bool(bce)), _p(pred), _p(loss), _stream())
+          rp, rseed, rstate, C.byref(w), C.byref(g), None, float(loss_grad), int(bool(bce)), _p(pred), _p(loss), _stream())
     return loss.reshape(()), pred
 
 

@@ -275,10 +275,11 @@ class Handler:
         Yd = Y.to(self.device, non_blocking=True).float()
         if self.fused_critic_step and ops.critic_fused_supported(self.critic) and x.dtype == torch.uint8:
             # whole step in one kernel: every activation of a frame stays in shared memory (csrc/critic_fused.cu)
-            masks = self.critic._dropout_masks(x.shape[0], self.device)
+            rng = self.critic._dropout_rng(x.device)               # masks drawn in the kernel (same Philox stream) ...
+            masks = (None, None, None) if rng is not None else self.critic._dropout_masks(x.shape[0], x.device)   # ... or forced / none
             opti.zero_grad()
             loss, _ = ops.critic_train_fused(self.critic, x.contiguous(), Yd.contiguous(), roll, masks,
-                                             loss_grad=1.0 / self.world, bce=bool(a.threshrew))
+                                             loss_grad=1.0 / self.world, bce=bool(a.threshrew), rng=rng)
             opti.step()
             return loss
         pred = self.critic.forward_frames(x, roll).squeeze(1)     # cast + roll fused into features.0's operand load

@@ -162,8 +162,12 @@ int cgs_critic_fused_supported(int32_t C0, int32_t C1, int32_t C2, int32_t C3, i
  * cgs_reduce_partials).  Every partial row is fully overwritten by each call. */
 int cgs_critic_fused_grid(int32_t B);
 int cgs_critic_fused_partial_stride(void);
+/* Dropout: explicit masks (m_e2, m_e3, m_v), or rng_state != NULL: the kernel draws them itself — the SAME Philox stream
+ * cgs_dropout_masks(out, B*800, p_drop, seed, rng_state) would have written for shapes [B,8,8,8 | B,4,4,16 | B,32] — and
+ * advances rng_state like that call does; or neither (eval / p = 0). */
 int cgs_critic_train_fused(const uint8_t* frames, const float* target, int32_t B, int32_t roll, const int32_t* roll_dev,
                            const float* m_e2, const float* m_e3, const float* m_v,
+                           float p_drop, uint64_t seed, uint64_t* rng_state,
                            const cgs_critic_weights* w, const cgs_critic_weights* g, float* partials,
                            float loss_grad, int32_t bce, float* pred, float* loss, void* stream);
 

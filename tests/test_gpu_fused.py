@@ -137,6 +137,32 @@ def test_fused_partials_handover_matches_red_path(ops, B):
     assert int(oa.step_count[0]) == 2 and int(ob.step_count[0]) == 2
 
 
+def test_fused_in_kernel_dropout_is_the_mask_kernels_stream(ops):
+    """Masks drawn inside the kernel == the masks cgs_dropout_masks writes for the same (seed, call counter); the counter
+    advances once per launch, so the next launch sees fresh masks."""
+    B = 37
+    csd, X, y, _ = _case(B, 0.3, seed=5)
+    c = _critic(csd, 0.3)
+    Xd, yd = torch.from_numpy(X).to(DEV), torch.from_numpy(y).to(DEV)
+    state, seed = torch.zeros(2, dtype=torch.int64, device=DEV), 0x1234567
+    masks = ops.dropout_masks([(B, 8, 8, 8), (B, 4, 4, 16), (B, 32)], 0.3, seed, state)
+    assert int(state[0]) == 1 and 0.6 < float((masks[0] > 0).float().mean()) < 0.8
+    for q in c.parameters():
+        q.grad = torch.zeros_like(q)
+    _, p1 = ops.critic_train_fused(c, Xd, yd, 2, tuple(masks))
+    g1 = torch.cat([q.grad.reshape(-1) for q in c.parameters()])
+    state.zero_()
+    for q in c.parameters():
+        q.grad.zero_()
+    _, p2 = ops.critic_train_fused(c, Xd, yd, 2, rng=(0.3, seed, state))
+    g2 = torch.cat([q.grad.reshape(-1) for q in c.parameters()])
+    assert int(state[0]) == 1 and int(state[1]) == 0
+    assert torch.equal(p1, p2)
+    assert (g1 - g2).abs().max().item() <= 1e-5 * g1.abs().max().item()
+    _, p3 = ops.critic_train_fused(c, Xd, yd, 2, rng=(0.3, seed, state))
+    assert int(state[0]) == 2 and not torch.equal(p2, p3)
+
+
 def test_fused_handler_step_matches_layer_kernels(ops):
     """Handler.critic_step through the fused kernel vs through the per-layer kernels: same loss, and the same
     parameters after the Adam step up to TF32 noise in the gradients."""

@@ -37,12 +37,18 @@ class CriticWeights(C.Structure):
     _fields_ = [(n, _f32p) for n in ("w0", "b0", "w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4", "wl1", "bl1", "wl2", "bl2")]
 
 
+class AdamArgs(C.Structure):
+    """cgs_adam_args"""
+    _fields_ = [("p", _f32p), ("g", _f32p), ("m", _f32p), ("v", _f32p), ("lr", C.c_double), ("beta1", C.c_double),
+                ("beta2", C.c_double), ("eps", C.c_double), ("step_state", C.c_void_p), ("barrier", C.c_void_p)]
+
+
 EXPORTS = {
     "cgs_critic_fused_supported": [C.c_int32] * 5,
     "cgs_critic_train_fused": [_u8p, _f32p, C.c_int32, C.c_int32, C.c_void_p, _f32p, _f32p, _f32p,
                                C.c_float, C.c_uint64, C.c_void_p,
-                               C.POINTER(CriticWeights), C.POINTER(CriticWeights), _f32p, C.c_float, C.c_int32, _f32p, _f32p,
-                               C.c_void_p],
+                               C.POINTER(CriticWeights), C.POINTER(CriticWeights), _f32p, C.POINTER(AdamArgs), C.c_float,
+                               C.c_int32, _f32p, _f32p, C.c_void_p],
     "cgs_critic_fused_grid": [C.c_int32],
     "cgs_critic_fused_partial_stride": [],
     "cgs_reduce_partials": [_f32p, C.c_int64, _f32p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p],

@@ -59,6 +59,7 @@ constexpr int oBias = oW + szW;                    // b0[8] b1[8] b2[8] b3[16]
 constexpr int oHW = oBias + 64;                    // head weights: wl1[1024] bl1[32] wl2[32] bl2[1] b4[32]
 constexpr int hWl1 = 0, hBl1 = 1024, hWl2 = 1056, hBl2 = 1088, hB4 = 1092, szHW = 1124;
 constexpr int SMEM_FLOATS = oHW + szHW;
+constexpr int NGRAD = 11873;                       // critic parameters in state_dict order (= flat gradient layout)
 constexpr int PSTRIDE = 11904;                     // per-CTA stride of the partial-gradient buffer (16-byte multiple)
 static_assert(szA >= SX, "region A must hold the re-staged frame");
 static_assert(oDY3 + 4 * PL3 <= oB + szB, "region B overflow");
@@ -73,6 +74,11 @@ struct Params {
   unsigned long long seed;          // rng_state != NULL: dropout masks are drawn in the kernel (Philox4x32-10, the stream of
   unsigned long long* rng_state;    // cgs_dropout_masks: counter = (float4 index in the [m2|m3|mv] buffer, call), key = seed)
   float p_drop, keep;
+  // adam_p != NULL (single GPU, the bucket is exactly the critic): Adam runs in this kernel behind a grid barrier
+  float *adam_p, *adam_g, *adam_m, *adam_v;
+  double lr, beta1, beta2, eps;
+  int* step_state;
+  unsigned* bar;        // {arrivals, generation, timed-out flag}, zeroed once by the host
   float* partials;      // != NULL: per-CTA partial gradients [grid][PSTRIDE] in flat order instead of REDs into gseg
   float* pred;
   float* loss;
@@ -289,6 +295,8 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
   int fr = 0;
   CF_MARK(23);
   const unsigned long long rng_call = p.rng_state ? p.rng_state[0] : 0ull;
+  unsigned bar_gen = 0;
+  if (p.adam_p && tid == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(bar_gen) : "l"(p.bar + 1) : "memory");
   if (blockIdx.x < p.B) {
     prefetch_frame(p, blockIdx.x, sm, tid);
     if (p.rng_state) draw_masks(p, blockIdx.x, rng_call, sm, tid);
@@ -838,6 +846,67 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     for (int i = 0; i < 16; ++i) atomicAdd(d4 + (((i >> 2) + rot4) & 3) * 4 + (i & 3), accW4[i]);
   }
   if (tid == 0 && blockIdx.x < p.B) atomicAdd(p.loss, loss_acc * p.inv_n);
+  if (p.adam_p) {
+    // ---- grid barrier (all CTAs are co-resident: one per SM, grid <= SMs), then every CTA sums its slice of the
+    //      parameter vector over all partial vectors (fixed order) and applies Adam: no second launch, no atomics
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      if (atomicAdd(p.bar, 1u) == gridDim.x - 1) {
+        p.bar[0] = 0;
+        __threadfence();
+        atomicAdd(p.bar + 1, 1u);
+      } else {
+        unsigned gnow = bar_gen;
+        for (int spin = 0; spin < (1 << 22) && gnow == bar_gen; ++spin) {      // bounded: never hang the device
+          __nanosleep(40);
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(gnow) : "l"(p.bar + 1) : "memory");
+        }
+        if (gnow == bar_gen) atomicExch(p.bar + 2, 1u);
+      }
+    }
+    __syncthreads();
+    const int t = p.step_state[0] + 1;
+    const double bc1 = 1.0 - pow(p.beta1, (double)t), bc2 = 1.0 - pow(p.beta2, (double)t);
+    const float step_size = (float)(p.lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+    const float omb1 = (float)(1.0 - p.beta1), b2 = (float)p.beta2, omb2 = (float)(1.0 - p.beta2), eps = (float)p.eps;
+    const int G = gridDim.x, per = (NGRAD + G - 1) / G, lo = blockIdx.x * per, hi = min(NGRAD, lo + per);
+    float* red = sm + oA;                           // [8][64]
+    const int ex = tid & 63, ky = tid >> 6;
+    for (int base = lo; base < hi; base += 64) {
+      const int i = base + ex;
+      float s0 = 0.f;
+      if (i < hi) {
+        const float* q = p.partials + i;
+        float v[19];
+#pragma unroll
+        for (int u = 0; u < 19; ++u) v[u] = (ky + 8 * u < G) ? __ldcg(q + (size_t)(ky + 8 * u) * PSTRIDE) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 19; ++u) s0 += v[u];
+      }
+      red[ky * 64 + ex] = s0;
+      __syncthreads();
+      if (ky == 0 && i < hi) {
+        float gv = p.adam_g[i];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) gv += red[r * 64 + ex];
+        const float mv = p.adam_m[i] + omb1 * (gv - p.adam_m[i]);
+        const float vv = p.adam_v[i] * b2 + omb2 * gv * gv;
+        p.adam_m[i] = mv;
+        p.adam_v[i] = vv;
+        p.adam_p[i] -= step_size * (mv / (sqrtf(vv) / bc2_sqrt + eps));
+        p.adam_g[i] = 0.f;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      __threadfence();
+      if (atomicAdd(&p.step_state[1], 1) == (int)gridDim.x - 1) {
+        p.step_state[1] = 0;
+        p.step_state[0] = t;
+      }
+    }
+  }
   if (p.rng_state && tid == 0) {                  // last CTA to finish advances the call counter (every CTA has read it)
     __threadfence();
     if (atomicAdd(&p.rng_state[1], 1ull) == gridDim.x - 1) {
@@ -885,7 +954,8 @@ extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target
                                       const int32_t* roll_dev, const float* m_e2, const float* m_e3, const float* m_v,
                                       float p_drop, uint64_t seed, uint64_t* rng_state,
                                       const cgs_critic_weights* w, const cgs_critic_weights* g, float* partials,
-                                      float loss_grad, int32_t bce, float* pred, float* loss, void* stream) {
+                                      const cgs_adam_args* adam, float loss_grad, int32_t bce, float* pred, float* loss,
+                                      void* stream) {
   CGS_REQUIRE(frames && target && w && pred && loss && B > 0 && (g || partials), "critic_train_fused: bad args");
   CGS_REQUIRE(((uintptr_t)frames & 15) == 0, "critic_train_fused: frames must be 16-byte aligned");
   CGS_REQUIRE((m_e2 != nullptr) == (m_e3 != nullptr) && (m_e2 != nullptr) == (m_v != nullptr),
@@ -909,6 +979,16 @@ extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target
   CGS_REQUIRE(!rng_state || (p_drop > 0.f && p_drop < 1.f), "critic_train_fused: rng dropout needs 0 < p < 1");
   p.seed = seed; p.rng_state = (unsigned long long*)rng_state; p.p_drop = p_drop;
   p.keep = rng_state ? 1.f / (1.f - p_drop) : 1.f;
+  p.adam_p = p.adam_g = p.adam_m = p.adam_v = nullptr;
+  p.step_state = nullptr; p.bar = nullptr; p.lr = p.beta1 = p.beta2 = p.eps = 0;
+  if (adam) {
+    CGS_REQUIRE(partials && adam->p && adam->g && adam->m && adam->v && adam->step_state && adam->barrier,
+                "critic_train_fused: in-kernel Adam needs the partial buffer and all optimizer pointers");
+    CGS_REQUIRE(cgs_critic_fused_grid(B) <= 152, "critic_train_fused: grid too large for the in-kernel reduction");
+    p.adam_p = adam->p; p.adam_g = adam->g; p.adam_m = adam->m; p.adam_v = adam->v;
+    p.lr = adam->lr; p.beta1 = adam->beta1; p.beta2 = adam->beta2; p.eps = adam->eps;
+    p.step_state = adam->step_state; p.bar = adam->barrier;
+  }
   p.partials = partials;
   p.pred = pred; p.loss = loss; p.roll_dev = roll_dev; p.B = B; p.roll = roll; p.bce = bce;
   p.inv_n = 1.f / (float)B;

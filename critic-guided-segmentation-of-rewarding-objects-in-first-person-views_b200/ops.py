@@ -499,7 +499,7 @@ def _critic_bucket_span(params):
 
 
 def critic_train_fused(critic, frames_u8, target, roll=0, masks=(None, None, None), loss_grad=1.0, bce=False,
-                       use_partials=True, rng=None):
+                       use_partials=True, rng=None, fuse_adam=False):
     """Forward + loss + backward of one critic_pipe step (reference main.py:185-198) in ONE kernel
     (cgs_critic_train_fused).  The parameter gradient is ADDED to the parameters' `.grad`: by REDs, or — when the
     parameters sit contiguously in a FlatAdam bucket — as per-CTA partial vectors that `FlatAdam.step()` sums inside the
@@ -520,9 +520,15 @@ def critic_train_fused(critic, frames_u8, target, roll=0, masks=(None, None, Non
         grid, stride = L.cgs_critic_fused_grid(B), L.cgs_critic_fused_partial_stride()
         opt.flush_partials()                                       # an unconsumed earlier hand-over goes into the bucket first
         buf = opt.partial_buffer(grid * stride)
+        nparam = sum(q.numel() for q in params)
+        adam = opt.fused_adam_args(off, nparam) if fuse_adam else None       # single GPU, bucket == the critic
         _call("cgs_critic_train_fused", _p(frames_u8, torch.uint8), _p(target), B, r, rd, _p(m2), _p(m3), _p(mv),
-              rp, rseed, rstate, C.byref(w), None, _p(buf), float(loss_grad), int(bool(bce)), _p(pred), _p(loss), _stream())
-        opt.pending_partials = (buf, grid, stride, off, sum(q.numel() for q in params))
+              rp, rseed, rstate, C.byref(w), None, _p(buf), C.byref(adam) if adam is not None else None, float(loss_grad),
+              int(bool(bce)), _p(pred), _p(loss), _stream())
+        if adam is not None:
+            opt.adam_done_in_kernel = True          # the coming opt.step() has nothing left to do
+        else:
+            opt.pending_partials = (buf, grid, stride, off, nparam)
         return loss.reshape(()), pred
     grads = []
     for q in params:
@@ -534,7 +540,7 @@ def critic_train_fused(critic, frames_u8, target, roll=0, masks=(None, None, Non
         grads.append(q.grad)
     g = _lib.CriticWeights(*[_p(t) for t in grads])
     _call("cgs_critic_train_fused", _p(frames_u8, torch.uint8), _p(target), B, r, rd, _p(m2), _p(m3), _p(mv),
-          rp, rseed, rstate, C.byref(w), C.byref(g), None, float(loss_grad), int(bool(bce)), _p(pred), _p(loss), _stream())
+          rp, rseed, rstate, C.byref(w), C.byref(g), None, None, float(loss_grad), int(bool(bce)), _p(pred), _p(loss), _stream())
     return loss.reshape(()), pred
 
 

@@ -95,7 +95,9 @@ class FlatAdam:
         # gradient handed over by the whole-step critic kernel as per-CTA partial vectors (ops.critic_train_fused):
         # (buffer, rows, row stride, bucket offset, length), summed in step() instead of RED-accumulated by the kernel
         self.pending_partials = None
+        self.adam_done_in_kernel = False
         self._pbuf = None
+        self._bar = None
         self._p2p = None
         if world_size > 1 and dev.type == "cuda" and os.environ.get("CGS_P2P", "1") != "0":
             self._p2p = self._setup_p2p(n, dev)
@@ -132,6 +134,21 @@ class FlatAdam:
         """False if a peer ever failed to announce its gradient in time (reads a device flag; synchronises)."""
         return self._p2p is None or int(self._p2p["err"].item()) == 0
 
+    def fused_adam_args(self, off, nparam):
+        """cgs_adam_args for the whole-step critic kernel if it may apply this optimizer's update itself: single process,
+        and the bucket is exactly the parameter run [off, off + nparam) the kernel owns.  Else None."""
+        from ._lib import AdamArgs
+        if self.world > 1 or off != 0 or nparam != self.flat.numel():
+            return None
+        if self._bar is None:
+            self._bar = torch.zeros(4, dtype=torch.int32, device=self.flat.device)
+        return AdamArgs(self.flat.data_ptr(), self.gflat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.lr,
+                        self.betas[0], self.betas[1], self.eps, self.step_count.data_ptr(), self._bar.data_ptr())
+
+    def barrier_ok(self):
+        """False if a CTA of the whole-step kernel ever timed out at its grid barrier (reads a device flag; synchronises)."""
+        return self._bar is None or int(self._bar[2].item()) == 0
+
     def partial_buffer(self, numel):
         if self._pbuf is None or self._pbuf.numel() < numel:
             self._pbuf = torch.empty(numel, device=self.flat.device, dtype=torch.float32)
@@ -154,6 +171,10 @@ class FlatAdam:
 
     def step(self):
         ops.join_wgrad()           # wgrad kernels forked onto the side stream have all landed in the bucket
+        if self.adam_done_in_kernel:          # the whole-step critic kernel already applied this update (and cleared the bucket)
+            self.adam_done_in_kernel = False
+            self._clean = True
+            return
         if self._p2p is not None:
             q = self._p2p
             ops.p2p_stage(self.gflat, q["npad"], q["sym"], self.step_count, self.pending_partials)
@@ -279,7 +300,8 @@ class Handler:
             masks = (None, None, None) if rng is not None else self.critic._dropout_masks(x.shape[0], x.device)   # ... or forced / none
             opti.zero_grad()
             loss, _ = ops.critic_train_fused(self.critic, x.contiguous(), Yd.contiguous(), roll, masks,
-                                             loss_grad=1.0 / self.world, bce=bool(a.threshrew), rng=rng)
+                                             loss_grad=1.0 / self.world, bce=bool(a.threshrew), rng=rng,
+                                             fuse_adam=self.world == 1 and opti._clean)
             opti.step()
             return loss
         pred = self.critic.forward_frames(x, roll).squeeze(1)     # cast + roll fused into features.0's operand load

@@ -162,6 +162,17 @@ int cgs_critic_fused_supported(int32_t C0, int32_t C1, int32_t C2, int32_t C3, i
  * cgs_reduce_partials).  Every partial row is fully overwritten by each call. */
 int cgs_critic_fused_grid(int32_t B);
 int cgs_critic_fused_partial_stride(void);
+/* Optional in-kernel optimizer of cgs_critic_train_fused (single GPU, the optimizer bucket is exactly the 11,873 critic
+ * parameters in state_dict order): after a grid barrier every CTA sums its slice of the partial vectors and applies Adam
+ * (torch.optim.Adam defaults semantics, as cgs_adam_step; g is added to the gradient and cleared).
+ * barrier: 4 x uint32 device words, zeroed once; word 2 != 0 afterwards = a CTA timed out at the barrier. */
+typedef struct cgs_adam_args {
+  float *p, *g, *m, *v;
+  double lr, beta1, beta2, eps;
+  int32_t* step_state;
+  uint32_t* barrier;
+} cgs_adam_args;
+
 /* Dropout: explicit masks (m_e2, m_e3, m_v), or rng_state != NULL: the kernel draws them itself — the SAME Philox stream
  * cgs_dropout_masks(out, B*800, p_drop, seed, rng_state) would have written for shapes [B,8,8,8 | B,4,4,16 | B,32] — and
  * advances rng_state like that call does; or neither (eval / p = 0). */
@@ -169,7 +180,7 @@ int cgs_critic_train_fused(const uint8_t* frames, const float* target, int32_t B
                            const float* m_e2, const float* m_e3, const float* m_v,
                            float p_drop, uint64_t seed, uint64_t* rng_state,
                            const cgs_critic_weights* w, const cgs_critic_weights* g, float* partials,
-                           float loss_grad, int32_t bce, float* pred, float* loss, void* stream);
+                           const cgs_adam_args* adam, float loss_grad, int32_t bce, float* pred, float* loss, void* stream);
 
 /* g[offset + j] += sum_k partials[k * stride + j], j < len, summed in a fixed order (data-parallel path: all-reduce next). */
 int cgs_reduce_partials(float* g, int64_t n, const float* partials, int32_t n_partials, int64_t stride,

@@ -137,6 +137,29 @@ def test_fused_partials_handover_matches_red_path(ops, B):
     assert int(oa.step_count[0]) == 2 and int(ob.step_count[0]) == 2
 
 
+@pytest.mark.parametrize("B", [5, 256, 300])
+def test_fused_in_kernel_adam_matches_adam_kernel(ops, B):
+    """Adam applied inside the whole-step kernel (grid barrier + per-CTA slice) == partial hand-over + Adam kernel."""
+    from cgs_b200.train_handler import FlatAdam
+    csd, X, y, masks = _case(B, 0.3, seed=40 + B)
+    m2, m3, mv = (torch.from_numpy(m).to(DEV) for m in masks)
+    dm = (m2.permute(0, 2, 3, 1).contiguous(), m3.permute(0, 2, 3, 1).contiguous(), mv.contiguous())
+    Xd, yd = torch.from_numpy(X).to(DEV), torch.from_numpy(y).to(DEV)
+    ca, cb = _critic(csd, 0.3), _critic(csd, 0.3)
+    oa, ob = FlatAdam(ca.parameters()), FlatAdam(cb.parameters())
+    for step in range(3):
+        for c, o, fuse in ((ca, oa, True), (cb, ob, False)):
+            o.zero_grad()
+            ops.critic_train_fused(c, Xd, yd, step, dm, fuse_adam=fuse)
+            assert o.adam_done_in_kernel == fuse
+            o.step()
+    assert oa.barrier_ok()
+    assert int(oa.step_count[0]) == 3 and int(ob.step_count[0]) == 3
+    assert torch.equal(oa.flat, ob.flat), (oa.flat - ob.flat).abs().max().item()
+    assert torch.equal(oa.m, ob.m) and torch.equal(oa.v, ob.v)
+    assert float(oa.gflat.abs().max()) == 0.0
+
+
 def test_fused_in_kernel_dropout_is_the_mask_kernels_stream(ops):
     """Masks drawn inside the kernel == the masks cgs_dropout_masks writes for the same (seed, call counter); the counter
     advances once per launch, so the next launch sees fresh masks."""

@@ -292,6 +292,14 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
   const uint32_t smb = (uint32_t)__cvta_generic_to_shared(sm);
 
   long long* trace = blockIdx.x == 0 ? g_cf_trace : nullptr;
+  // debug: every CTA's start / end-of-frames / end time in ns (globaltimer) + its SM id, after the 4*24 phase marks
+  long long* ctat = g_cf_trace ? g_cf_trace + 96 + blockIdx.x * 4 : nullptr;
+  if (ctat && threadIdx.x == 0) {
+    long long gt; unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    ctat[0] = gt; ctat[3] = smid;
+  }
   int fr = 0;
   CF_MARK(23);
   const unsigned long long rng_call = p.rng_state ? p.rng_state[0] : 0ull;
@@ -775,6 +783,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     // the next iteration's F0a barrier (or the one below) separates B0's reads from the next writes
   }
 
+  if (ctat && threadIdx.x == 0) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); ctat[1] = gt; }
   // ---- end of the CTA's frames: combine the warps' register accumulators through shared memory (region A is free),
   //      then write this CTA's gradient: one coalesced partial vector (summed by the Adam kernel), or REDs
   asm volatile("cp.async.wait_all;\n" ::);
@@ -865,40 +874,45 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
         if (gnow == bar_gen) atomicExch(p.bar + 2, 1u);
       }
     }
-    __syncthreads();
+    CF_MARK(18);
     const int t = p.step_state[0] + 1;
-    const double bc1 = 1.0 - pow(p.beta1, (double)t), bc2 = 1.0 - pow(p.beta2, (double)t);
-    const float step_size = (float)(p.lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+    float* red = sm + oA;                           // [4][128] + the two bias-correction scalars
+    if (tid == 0) {                                 // double-precision pow once per CTA
+      const double bc1 = 1.0 - pow(p.beta1, (double)t), bc2 = 1.0 - pow(p.beta2, (double)t);
+      red[520] = (float)(p.lr / bc1);
+      red[521] = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const float step_size = red[520], bc2_sqrt = red[521];
     const float omb1 = (float)(1.0 - p.beta1), b2 = (float)p.beta2, omb2 = (float)(1.0 - p.beta2), eps = (float)p.eps;
     const int G = gridDim.x, per = (NGRAD + G - 1) / G, lo = blockIdx.x * per, hi = min(NGRAD, lo + per);
-    float* red = sm + oA;                           // [8][64]
-    const int ex = tid & 63, ky = tid >> 6;
-    for (int base = lo; base < hi; base += 64) {
+    const int ex = tid & 127, ky = tid >> 7;        // 128 parameters x 4 slices of the partial list per pass
+    for (int base = lo; base < hi; base += 128) {
       const int i = base + ex;
-      float s0 = 0.f;
+      float s0 = 0.f, gv = 0.f, m0 = 0.f, v0 = 0.f, p0 = 0.f;
       if (i < hi) {
         const float* q = p.partials + i;
-        float v[19];
+        float v[38];
 #pragma unroll
-        for (int u = 0; u < 19; ++u) v[u] = (ky + 8 * u < G) ? __ldcg(q + (size_t)(ky + 8 * u) * PSTRIDE) : 0.f;
+        for (int u = 0; u < 38; ++u) v[u] = (ky + 4 * u < G) ? __ldcg(q + (size_t)(ky + 4 * u) * PSTRIDE) : 0.f;
+        if (ky == 0) { gv = __ldcg(p.adam_g + i); m0 = __ldcg(p.adam_m + i); v0 = __ldcg(p.adam_v + i); p0 = __ldcg(p.adam_p + i); }
 #pragma unroll
-        for (int u = 0; u < 19; ++u) s0 += v[u];
+        for (int u = 0; u < 38; ++u) s0 += v[u];
       }
-      red[ky * 64 + ex] = s0;
+      red[ky * 128 + ex] = s0;
       __syncthreads();
       if (ky == 0 && i < hi) {
-        float gv = p.adam_g[i];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) gv += red[r * 64 + ex];
-        const float mv = p.adam_m[i] + omb1 * (gv - p.adam_m[i]);
-        const float vv = p.adam_v[i] * b2 + omb2 * gv * gv;
+        gv += (red[ex] + red[128 + ex]) + (red[256 + ex] + red[384 + ex]);
+        const float mv = m0 + omb1 * (gv - m0);
+        const float vv = v0 * b2 + omb2 * gv * gv;
         p.adam_m[i] = mv;
         p.adam_v[i] = vv;
-        p.adam_p[i] -= step_size * (mv / (sqrtf(vv) / bc2_sqrt + eps));
+        p.adam_p[i] = p0 - step_size * (mv / (sqrtf(vv) / bc2_sqrt + eps));
         p.adam_g[i] = 0.f;
       }
       __syncthreads();
     }
+    CF_MARK(19);
     if (tid == 0) {
       __threadfence();
       if (atomicAdd(&p.step_state[1], 1) == (int)gridDim.x - 1) {
@@ -915,6 +929,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     }
   }
   CF_MARK(16);
+  if (ctat && threadIdx.x == 0) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); ctat[2] = gt; }
 }
 
 }  // namespace cf
@@ -922,7 +937,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
 
 using namespace cgs;
 
-// Debug: point the phase trace at a device buffer of 4*24 int64 (NULL disables).  Not part of the product API.
+// Debug: point the phase trace at a device buffer of 4*24 + 4*grid int64 (NULL disables).  Not part of the product API.
 extern "C" int cgs_critic_fused_set_trace(long long* dev_buf) {
   return cudaMemcpyToSymbol(cf::g_cf_trace, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? 0 : -2;
 }

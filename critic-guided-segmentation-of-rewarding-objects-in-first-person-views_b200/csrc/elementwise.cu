@@ -210,11 +210,18 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
                             int64_t n, double lr, double beta1, double beta2, double eps_d,
                             int* __restrict__ step_state, float gscale, int clear_grad) {
   const int t = step_state[0] + 1;
-  // bias corrections in double, as torch does on the host (python floats); tensor-side scalars in fp32
-  const double bc1 = 1.0 - pow(beta1, (double)t);
-  const double bc2 = 1.0 - pow(beta2, (double)t);
-  const float step_size = (float)(lr / bc1);
-  const float bc2_sqrt = (float)sqrt(bc2);
+  // bias corrections in double, as torch does on the host (python floats); tensor-side scalars in fp32.
+  // One thread per block does the double-precision pow, the rest read the two results from shared memory.
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const double bc1 = 1.0 - pow(beta1, (double)t);
+    const double bc2 = 1.0 - pow(beta2, (double)t);
+    s_bc[0] = (float)(lr / bc1);
+    s_bc[1] = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float step_size = s_bc[0];
+  const float bc2_sqrt = s_bc[1];
   const float omb1 = (float)(1.0 - beta1), b2 = (float)beta2, omb2 = (float)(1.0 - beta2), eps = (float)eps_d;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gv = g[i] * gscale;
@@ -261,6 +268,14 @@ __global__ void __launch_bounds__(256) partials_kernel(float* __restrict__ p, fl
     }
   }
   red[ky][ex] = s0;
+  __shared__ float s_bc[2];
+  if (ADAM && threadIdx.x == 0) {
+    const int t = step_state[0] + 1;
+    const double bc1 = 1.0 - pow(beta1, (double)t);
+    const double bc2 = 1.0 - pow(beta2, (double)t);
+    s_bc[0] = (float)(lr / bc1);
+    s_bc[1] = (float)sqrt(bc2);
+  }
   __syncthreads();
   if (ky == 0 && i < n) {
     float gv = g[i];
@@ -269,11 +284,8 @@ __global__ void __launch_bounds__(256) partials_kernel(float* __restrict__ p, fl
     if (!ADAM) {
       g[i] = gv;
     } else {
-      const int t = step_state[0] + 1;
-      const double bc1 = 1.0 - pow(beta1, (double)t);
-      const double bc2 = 1.0 - pow(beta2, (double)t);
-      const float step_size = (float)(lr / bc1);
-      const float bc2_sqrt = (float)sqrt(bc2);
+      const float step_size = s_bc[0];
+      const float bc2_sqrt = s_bc[1];
       const float omb1 = (float)(1.0 - beta1), b2 = (float)beta2, omb2 = (float)(1.0 - beta2), eps = (float)eps_d;
       gv *= gscale;
       const float mv = m[i] + omb1 * (gv - m[i]);

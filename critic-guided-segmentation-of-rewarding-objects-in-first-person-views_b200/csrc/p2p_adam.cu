@@ -74,12 +74,17 @@ __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(float* __restri
     }
     if ((int)seen < t) atomicExch(err, 1);
   }
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 32) {                         // one double-precision pow pair per block, while the others poll
+    const double bc1 = 1.0 - pow(beta1, (double)t);
+    const double bc2 = 1.0 - pow(beta2, (double)t);
+    s_bc[0] = (float)(lr / bc1);
+    s_bc[1] = (float)sqrt(bc2);
+  }
   __syncthreads();
   // 3. + 4.
-  const double bc1 = 1.0 - pow(beta1, (double)t);
-  const double bc2 = 1.0 - pow(beta2, (double)t);
-  const float step_size = (float)(lr / bc1);
-  const float bc2_sqrt = (float)sqrt(bc2);
+  const float step_size = s_bc[0];
+  const float bc2_sqrt = s_bc[1];
   const float omb1 = (float)(1.0 - beta1), b2 = (float)beta2, omb2 = (float)(1.0 - beta2), eps = (float)eps_d;
   const int64_t slot = (int64_t)(t & 1) * npad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {

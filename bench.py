@@ -279,8 +279,13 @@ def run_ours(args, rank, world):
     sync()
     evs = []
     t_wall0 = time.perf_counter()
+    align = torch.zeros(1, device=dev)
     for _ in range(K):
         flush.zero_()
+        if world > 1:
+            # ranks drift apart by host jitter while they flush; a step can only finish when the slowest peer's gradient
+            # arrives, so start the timed region of every rank at a common device-side point (a tiny all-reduce)
+            dist.all_reduce(align)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(); step.replay(); e.record()
         evs.append((s, e))
@@ -338,7 +343,8 @@ def run_ours(args, rank, world):
                                           else "conv fprop/dgrad: tcgen05 kind::tf32, fp32 accumulate in TMEM; wgrad: TF32 mma.sync; "
                                           "head, losses, Adam: fp32") if args.precision == "tf32" else "all fp32 (FFMA)"),
                            "chfak": args.chfak, "parallelism": f"dp{world}", "timing": "cuda events per step, L2 flushed "
-                           "(256 MiB memset) between timed steps", "graph": True},
+                           "(256 MiB memset) between timed steps" + ("; ranks aligned by a device-side all-reduce before each "
+                           "timed step" if world > 1 else ""), "graph": True},
                 "e2e": {"value": world * B * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h},
                 "gpu_launches": step.launches * K, "launches_per_step": step.launches,

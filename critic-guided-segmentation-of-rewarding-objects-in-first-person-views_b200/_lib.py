@@ -40,7 +40,8 @@ class CriticWeights(C.Structure):
 class AdamArgs(C.Structure):
     """cgs_adam_args"""
     _fields_ = [("p", _f32p), ("g", _f32p), ("m", _f32p), ("v", _f32p), ("lr", C.c_double), ("beta1", C.c_double),
-                ("beta2", C.c_double), ("eps", C.c_double), ("step_state", C.c_void_p), ("barrier", C.c_void_p)]
+                ("beta2", C.c_double), ("eps", C.c_double), ("step_state", C.c_void_p), ("barrier", C.c_void_p),
+                ("world", C.c_int32), ("rank", C.c_int32), ("npad", C.c_int64), ("peer_recv", C.c_void_p)]
 
 
 EXPORTS = {

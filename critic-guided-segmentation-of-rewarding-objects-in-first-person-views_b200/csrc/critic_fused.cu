@@ -79,6 +79,15 @@ struct Params {
   double lr, beta1, beta2, eps;
   int* step_state;
   unsigned* bar;        // {arrivals, generation, timed-out flag}, zeroed once by the host
+  // world > 1: the gradient is all-reduced inside this kernel over NVLink peer memory, low-latency style: every rank owns
+  // a symmetric receive buffer recv[2 slots][world][npad] of {value, step} pairs.  CTA b PUSHES each element of its slice
+  // of this rank's summed gradient, tagged with the step number, into every peer's buffer with one 8-byte store (value and
+  // tag travel together: no fence, no separate flag), then polls its OWN buffer until all `world` tags of an element
+  // equal the step, sums in rank order (bit-identical parameters on every rank) and applies Adam.  One launch per
+  // data-parallel step; slots alternate by step parity and tags only grow, so nothing is ever reset.
+  int world, rank;
+  long long npad;
+  unsigned long long* ll_peer[16];  // every rank's receive buffer as mapped into this process
   float* partials;      // != NULL: per-CTA partial gradients [grid][PSTRIDE] in flat order instead of REDs into gseg
   float* pred;
   float* loss;
@@ -887,6 +896,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     const float omb1 = (float)(1.0 - p.beta1), b2 = (float)p.beta2, omb2 = (float)(1.0 - p.beta2), eps = (float)p.eps;
     const int G = gridDim.x, per = (NGRAD + G - 1) / G, lo = blockIdx.x * per, hi = min(NGRAD, lo + per);
     const int ex = tid & 127, ky = tid >> 7;        // 128 parameters x 4 slices of the partial list per pass
+    const bool xchg = p.world > 1;
     for (int base = lo; base < hi; base += 128) {
       const int i = base + ex;
       float s0 = 0.f, gv = 0.f, m0 = 0.f, v0 = 0.f, p0 = 0.f;
@@ -903,6 +913,26 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
       __syncthreads();
       if (ky == 0 && i < hi) {
         gv += (red[ex] + red[128 + ex]) + (red[256 + ex] + red[384 + ex]);
+        if (xchg) {
+          const size_t slot = (size_t)(t & 1) * p.world * p.npad;
+          const unsigned long long pkt = ((unsigned long long)(unsigned)t << 32) | __float_as_uint(gv);
+          for (int r = 0; r < p.world; ++r)             // push {value, step} into every rank's buffer (mine included)
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(p.ll_peer[r] + slot + (size_t)p.rank * p.npad + i), "l"(pkt)
+                         : "memory");
+          const unsigned long long* mine = p.ll_peer[p.rank] + slot + i;
+          gv = 0.f;
+          bool ok = true;
+          for (int r = 0; r < p.world; ++r) {           // rank order on every rank
+            unsigned long long got = 0;
+            int spin = 0;
+            do {
+              asm volatile("ld.relaxed.sys.global.u64 %0, [%1];\n" : "=l"(got) : "l"(mine + (size_t)r * p.npad) : "memory");
+            } while ((unsigned)(got >> 32) != (unsigned)t && ++spin < (1 << 24));
+            ok = ok && (unsigned)(got >> 32) == (unsigned)t;
+            gv += __uint_as_float((unsigned)got);
+          }
+          if (!ok) atomicExch(p.bar + 2, 1u);           // a peer never delivered: flagged, never hangs
+        }
         const float mv = m0 + omb1 * (gv - m0);
         const float vv = v0 * b2 + omb2 * gv * gv;
         p.adam_m[i] = mv;
@@ -994,6 +1024,8 @@ extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target
   CGS_REQUIRE(!rng_state || (p_drop > 0.f && p_drop < 1.f), "critic_train_fused: rng dropout needs 0 < p < 1");
   p.seed = seed; p.rng_state = (unsigned long long*)rng_state; p.p_drop = p_drop;
   p.keep = rng_state ? 1.f / (1.f - p_drop) : 1.f;
+  p.world = 1; p.rank = 0; p.npad = 0;
+  for (int r = 0; r < 16; ++r) p.ll_peer[r] = nullptr;
   p.adam_p = p.adam_g = p.adam_m = p.adam_v = nullptr;
   p.step_state = nullptr; p.bar = nullptr; p.lr = p.beta1 = p.beta2 = p.eps = 0;
   if (adam) {
@@ -1003,6 +1035,12 @@ extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target
     p.adam_p = adam->p; p.adam_g = adam->g; p.adam_m = adam->m; p.adam_v = adam->v;
     p.lr = adam->lr; p.beta1 = adam->beta1; p.beta2 = adam->beta2; p.eps = adam->eps;
     p.step_state = adam->step_state; p.bar = adam->barrier;
+    if (adam->world > 1) {
+      CGS_REQUIRE(adam->world <= 16 && adam->rank >= 0 && adam->rank < adam->world && adam->peer_recv && adam->npad >= cf::NGRAD,
+                  "critic_train_fused: bad peer-memory arguments (world %d rank %d)", adam->world, adam->rank);
+      p.world = adam->world; p.rank = adam->rank; p.npad = adam->npad;
+      for (int r = 0; r < adam->world; ++r) p.ll_peer[r] = reinterpret_cast<unsigned long long*>(adam->peer_recv[r]);
+    }
   }
   p.partials = partials;
   p.pred = pred; p.loss = loss; p.roll_dev = roll_dev; p.B = B; p.roll = roll; p.bce = bce;

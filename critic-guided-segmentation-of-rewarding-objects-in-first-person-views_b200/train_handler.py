@@ -115,14 +115,17 @@ class FlatAdam:
             npad = (n + 63) // 64 * 64
             sym = symm.empty(2 * npad, dtype=torch.float32, device=dev)
             flags = symm.empty(64, dtype=torch.int32, device=dev)
-            sym.zero_(); flags.zero_()
+            # receive buffer of the in-kernel low-latency all-reduce: [2 slots][world][npad] x {value, step tag}
+            recv = symm.empty(2 * self.world * npad * 2, dtype=torch.int32, device=dev)
+            sym.zero_(); flags.zero_(); recv.zero_()
             torch.cuda.synchronize()
             group = self.group if self.group is not None else dist.group.WORLD
-            hs, hf = symm.rendezvous(sym, group), symm.rendezvous(flags, group)
+            hs, hf, hr = symm.rendezvous(sym, group), symm.rendezvous(flags, group), symm.rendezvous(recv, group)
             dist.barrier(group=group)
             torch.cuda.synchronize()
             W = self.world
-            return dict(npad=npad, sym=sym, flags=flags, hs=hs, hf=hf, rank=dist.get_rank(group),
+            return dict(npad=npad, sym=sym, flags=flags, recv=recv, hs=hs, hf=hf, hr=hr, rank=dist.get_rank(group),
+                        recv_ptrs=(ctypes.c_uint64 * W)(*[int(x) for x in hr.buffer_ptrs]),
                         bufs=(ctypes.c_uint64 * W)(*[int(x) for x in hs.buffer_ptrs]),
                         pads=(ctypes.c_uint64 * W)(*[int(x) for x in hf.buffer_ptrs]),
                         err=torch.zeros(1, dtype=torch.int32, device=dev))
@@ -137,16 +140,24 @@ class FlatAdam:
     def fused_adam_args(self, off, nparam):
         """cgs_adam_args for the whole-step critic kernel if it may apply this optimizer's update itself: single process,
         and the bucket is exactly the parameter run [off, off + nparam) the kernel owns.  Else None."""
+        import ctypes
         from ._lib import AdamArgs
-        if self.world > 1 or off != 0 or nparam != self.flat.numel():
+        if off != 0 or nparam != self.flat.numel() or (self.world > 1 and self._p2p is None):
             return None
         if self._bar is None:
             self._bar = torch.zeros(4, dtype=torch.int32, device=self.flat.device)
-        return AdamArgs(self.flat.data_ptr(), self.gflat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.lr,
-                        self.betas[0], self.betas[1], self.eps, self.step_count.data_ptr(), self._bar.data_ptr())
+        a = AdamArgs(self.flat.data_ptr(), self.gflat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.lr,
+                     self.betas[0], self.betas[1], self.eps, self.step_count.data_ptr(), self._bar.data_ptr(),
+                     1, 0, 0, None)
+        if self.world > 1:       # data-parallel: the all-reduce over peer memory happens inside the kernel as well
+            q = self._p2p
+            a.world, a.rank, a.npad = self.world, q["rank"], q["npad"]
+            a.peer_recv = ctypes.cast(q["recv_ptrs"], ctypes.c_void_p)
+        return a
 
     def barrier_ok(self):
-        """False if a CTA of the whole-step kernel ever timed out at its grid barrier (reads a device flag; synchronises)."""
+        """False if a CTA of the whole-step kernel ever timed out at its grid barrier or waiting for a peer's gradient
+        slice (reads a device flag; synchronises)."""
         return self._bar is None or int(self._bar[2].item()) == 0
 
     def partial_buffer(self, numel):
@@ -301,7 +312,7 @@ class Handler:
             opti.zero_grad()
             loss, _ = ops.critic_train_fused(self.critic, x.contiguous(), Yd.contiguous(), roll, masks,
                                              loss_grad=1.0 / self.world, bce=bool(a.threshrew), rng=rng,
-                                             fuse_adam=self.world == 1 and opti._clean)
+                                             fuse_adam=opti._clean)
             opti.step()
             return loss
         pred = self.critic.forward_frames(x, roll).squeeze(1)     # cast + roll fused into features.0's operand load

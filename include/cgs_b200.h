@@ -171,6 +171,14 @@ typedef struct cgs_adam_args {
   double lr, beta1, beta2, eps;
   int32_t* step_state;
   uint32_t* barrier;
+  /* world > 1: the kernel also all-reduces the gradient over NVLink peer memory before the update (one launch per
+   * data-parallel step), low-latency protocol: every rank owns a symmetric receive buffer of 2*world*npad 8-byte words
+   * ({fp32 value, step tag}; zeroed once); each CTA pushes its slice of the local gradient into every rank's buffer and
+   * polls its own until all tags equal the step, then sums in rank order.
+   * peer_recv: HOST array of `world` device addresses (this process's mapping of each rank's receive buffer). */
+  int32_t world, rank;
+  int64_t npad;
+  const uint64_t* peer_recv;
 } cgs_adam_args;
 
 /* Dropout: explicit masks (m_e2, m_e3, m_v), or rng_state != NULL: the kernel draws them itself — the SAME Philox stream

@@ -206,8 +206,8 @@ def kernel_rooflines(B, chfak, flush, hbm_gbs):
 
 def fused_step_roofline(B, flush, hbm_gbs, tf_peak):
     """The whole-step critic kernel (csrc/critic_fused.cu) timed alone: one graph node replayed between CUDA events, L2
-    flushed in between.  Algorithmic work per frame: 8,460,480 FLOP; compulsory HBM bytes 12,288 (uint8
-    frame) + 4 (label) + 3,200 (dropout masks the kernel is handed)."""
+    flushed in between (gradient leaves as per-CTA partial vectors; the Adam tail of the full step is not in this number).
+    Algorithmic work per frame: 8,460,480 FLOP; compulsory HBM bytes 12,288 (uint8 frame) + 4 (label)."""
     from cgs_b200 import ops
     from cgs_b200.nets import NewCritic
     from cgs_b200.train_handler import FlatAdam
@@ -216,8 +216,7 @@ def fused_step_roofline(B, flush, hbm_gbs, tf_peak):
     opt = FlatAdam(c.parameters())
     X = torch.randint(0, 255, (B, 64, 64, 3), dtype=torch.uint8, device="cuda")
     Y = torch.rand(B, device="cuda")
-    masks = c._dropout_masks(B, X.device)
-    run = lambda: ops.critic_train_fused(c, X, Y, 3, masks)
+    run = lambda: ops.critic_train_fused(c, X, Y, 3, rng=c._dropout_rng(X.device))      # masks drawn in-kernel, as in the step
     for _ in range(3):
         run()
     torch.cuda.synchronize()
@@ -225,7 +224,7 @@ def fused_step_roofline(B, flush, hbm_gbs, tf_peak):
     with torch.cuda.graph(g, capture_error_mode="thread_local"):
         run()
     sec = time_kernel(g.replay, flush)
-    flops, byts = 8460480 * B, (12288 + 4 + 3200) * B
+    flops, byts = 8460480 * B, (12288 + 4) * B
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     mma_peak = sms * 512 * 2 * 1.965e9 / 1e12      # mma.sync m16n8k8 TF32: 2.0 clk per instruction per SM (tools/mma_rate.cu)
     return {"kernel": "critic_fused_train_kernel", "desc": "frame -> forward -> loss -> backward, all activations in smem",

@@ -18,7 +18,7 @@
 //   * the 4x4 bottleneck conv and the MLP head are FFMA on the tiny vectors.
 // tcgen05 is not used here on purpose: every GEMM has N = 8..16 and M-tiles of 16 pixels; a 128-row UMMA tile would
 // be >85 % padding and its operands would have to be re-laid out in the canonical layout per tap.
-#include "common.cuh"
+#include "fused_common.cuh"
 
 namespace cgs {
 namespace cf {
@@ -103,71 +103,6 @@ __device__ long long* g_cf_trace = nullptr;   // debug: clock64() at every phase
     if (trace && tid == 0) trace[fr * 24 + (k)] = clock64();             \
   } while (0)
 
-__device__ __forceinline__ uint32_t f2tf32(float f) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(f));
-  return r;
-}
-__device__ __forceinline__ float tf32r(float f) { return __uint_as_float(f2tf32(f)); }
-
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm2(uint32_t& r0, uint32_t& r1, uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(addr));
-}
-
-// Output rows [0, R) of one 16-pixel column strip (R even).  Iteration i loads the NK A fragments of haloed input row i
-// once and feeds the three output rows i, i-1, i-2 (filter rows 0, 1, 2); epi(e, top, bot) gets the finished rows e, e+1.
-template <int R, int NK, class LoadA, class Epi>
-__device__ __forceinline__ void slide_rows(const float2 (&w)[3][NK], LoadA&& loadA, Epi&& epi) {
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < R + 2; ++i) {
-    uint32_t a[NK][4];
-    loadA(i, a);
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int oi = i - ky;
-      if (oi >= 0 && oi < R) {
-        if (ky == 0) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) acc[oi & 3][q] = 0.f;
-        }
-#pragma unroll
-        for (int kk = 0; kk < NK; ++kk)
-          mma_tf32(acc[oi & 3], a[kk], __float_as_uint(w[ky][kk].x), __float_as_uint(w[ky][kk].y));
-      }
-    }
-    if (i >= 3 && ((i - 3) & 1) == 0) epi(i - 3, acc[(i - 3) & 3], acc[(i - 2) & 3]);
-  }
-}
-
-// bias + ReLU + 2x2 max-pool (first max wins, ATen's rule) on two finished rows of a strip.  The two lanes of an
-// x-pair (g, g^1) split the work: even g finishes channel 2t, odd g channel 2t+1, for both pixel halves (g, g+8).
-// st(h, value, idx): pooled pixel (x0 + g + 8h) >> 1, channel 2t + (g & 1); idx 4 = no gradient (ReLU off).
-template <class Store>
-__device__ __forceinline__ void pool2x2(const float (&top)[4], const float (&bot)[4], float bias0, float bias1, int odd, Store&& st) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const float t0 = top[2 * h] + bias0, t1 = top[2 * h + 1] + bias1, b0 = bot[2 * h] + bias0, b1 = bot[2 * h + 1] + bias1;
-    const float rt = __shfl_xor_sync(0xffffffffu, odd ? t0 : t1, 4), rb = __shfl_xor_sync(0xffffffffu, odd ? b0 : b1, 4);
-    const float p0 = odd ? rt : t0, p1 = odd ? t1 : rt, p2 = odd ? rb : b0, p3 = odd ? b1 : rb;
-    const float m01 = fmaxf(p0, p1), m23 = fmaxf(p2, p3);
-    const int i01 = p1 > p0 ? 1 : 0, i23 = p3 > p2 ? 3 : 2;
-    float m = fmaxf(m01, m23);
-    int idx = m23 > m01 ? i23 : i01;
-    if (!(m > 0.f)) { m = 0.f; idx = 4; }
-    st(h, m, idx);
-  }
-}
-
 // Weight gradient of an 8-input-channel 3x3 conv over `nks` k-steps of 8 pixels (TW = map width): acc[mt] rows are
 // (tap 2mt | tap 2mt+1) x ci; row 8 of mt 4 is the all-ones row (bias gradient).  X: haloed half-planes of the layer input,
 // DY: haloed half-planes of the output gradient.  The mma's k index is mapped to pixels as k = t -> 2t, k = t+4 -> 2t+1,
@@ -219,7 +154,6 @@ __device__ __forceinline__ void wgrad8_store(const float (&acc)[5][4], float* ti
     }
 }
 
-__device__ __forceinline__ float u8f(uint32_t b) { return __uint_as_float(0x4B000000u | b) - 8388608.f; }
 
 // raw bytes -> haloed [66][66] x (r,g,b,0) fp32 /255 with the circular W-roll; tf32(b * (1/255)) == tf32(b / 255) for all b
 __device__ __forceinline__ void stage_frame(const uint8_t* __restrict__ sU8, float* __restrict__ sXd, int roll, int tid) {

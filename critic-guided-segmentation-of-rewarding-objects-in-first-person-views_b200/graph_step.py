@@ -109,9 +109,15 @@ class GraphedSegment(_Graphed):
 
         def fn():
             with torch.no_grad():
-                x = ops.frames_to_float(self.X, 0).permute(0, 3, 1, 2)
-                pred, embeds = H.critic(x, collect=True)
-                mask, hard = H.masker.forward_hard(x, embeds, threshold)
+                xf = ops.frames_to_float(self.X, 0)
+                if ops.infer_fused_supported(H.critic, H.masker):
+                    # encoder + decoder in one kernel, every intermediate in shared memory; the masker convs on tcgen05
+                    pred, o0 = ops.infer_encode_decode(H.critic, H.masker, self.X)
+                    mask, hard = H.masker.mask_from_o0(xf, o0, threshold)
+                else:
+                    x = xf.permute(0, 3, 1, 2)
+                    pred, embeds = H.critic(x, collect=True)
+                    mask, hard = H.masker.forward_hard(x, embeds, threshold)
             return pred, mask, hard
         self.graph, self.out, self.launches = _capture(fn)
 

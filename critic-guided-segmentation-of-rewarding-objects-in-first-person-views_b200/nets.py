@@ -176,6 +176,13 @@ class UnetDecoder(nn.Module):
         z, hard = ops.MaskHead.apply(m, self.masker[2].weight, self.masker[2].bias, thresh)
         return _nchw(z), (_nchw(hard) if thresh is not None else None)
 
+    def mask_from_o0(self, x_nhwc, o0, thresh=None):
+        """The masker half on its own: cat(X, ups(o0)) -> masker[0..3] (reference nets.py:519-523), given dec[0]'s output
+        o0 [B,32,32,8] NHWC (e.g. from ops.infer_encode_decode).  x_nhwc: fp32 [B,64,64,3]."""
+        m = ops.DecBlock.apply(x_nhwc, o0, self.masker[0].weight, self.masker[0].bias, 1, True)
+        z, hard = ops.MaskHead.apply(m, self.masker[2].weight, self.masker[2].bias, thresh)
+        return _nchw(z), (_nchw(hard) if thresh is not None else None)
+
     def forward(self, X, embeds):
         return self._run(X, embeds, None)[0]
 

@@ -544,6 +544,39 @@ def critic_train_fused(critic, frames_u8, target, roll=0, masks=(None, None, Non
     return loss.reshape(()), pred
 
 
+def infer_fused_supported(critic, masker):
+    """True when the fused encoder+decoder inference kernel covers these modules (chfak=1 geometry, tf32 mode, eval)."""
+    f, d = critic.features, masker.dec
+    return bool(_precision and not critic.training
+                and _lib.lib().cgs_critic_fused_supported(f[0].out_channels, f[3].out_channels, f[6].out_channels,
+                                                          f[10].out_channels, f[14].out_channels)
+                and tuple(d[3].weight.shape) == (16, 48, 3, 3) and tuple(d[0].weight.shape) == (8, 16, 3, 3)
+                and tuple(d[4].weight.shape) == (32, 32, 1, 1))
+
+
+def infer_encode_decode(critic, masker, frames_u8):
+    """critic(X, collect=True) + dec[4..0] of the masker on raw uint8 frames in ONE kernel (cgs_infer_fused):
+    returns (pred [B,1], o0 [B,32,32,8] NHWC).  The decoder weights are packed into mma fragment order once per
+    weight version (cached on the masker)."""
+    L = _lib.lib()
+    B = frames_u8.shape[0]
+    d = masker.dec
+    ver = tuple((w.data_ptr(), w._version) for w in (d[3].weight, d[2].weight, d[1].weight, d[0].weight))
+    cache = getattr(masker, "_cgs_pack", None)
+    if cache is None or cache[0] != ver:
+        pack = torch.empty(L.cgs_infer_pack_floats(), device=frames_u8.device, dtype=torch.float32)
+        _call("cgs_infer_pack_decoder", _p(d[3].weight.detach()), _p(d[2].weight.detach()), _p(d[1].weight.detach()),
+              _p(d[0].weight.detach()), _p(pack), _stream())
+        masker._cgs_pack = cache = (ver, pack)
+    w = _lib.CriticWeights(*[_p(q.detach()) for q in critic.parameters()])
+    pred = torch.empty(B, device=frames_u8.device, dtype=torch.float32)
+    o0 = torch.empty((B, 32, 32, 8), device=frames_u8.device, dtype=torch.float32)
+    _call("cgs_infer_fused", _p(frames_u8, torch.uint8), B, C.byref(w), _p(d[4].weight.detach()), _p(d[4].bias.detach()),
+          _p(d[3].bias.detach()), _p(d[2].bias.detach()), _p(d[1].bias.detach()), _p(d[0].bias.detach()), _p(cache[1]),
+          _p(pred), _p(o0), _stream())
+    return pred.unsqueeze(1), o0
+
+
 def reduce_partials(g, buf, n_partials, stride, offset, length):
     _call("cgs_reduce_partials", _p(g), g.numel(), _p(buf), int(n_partials), int(stride), int(offset), int(length), _stream())
 

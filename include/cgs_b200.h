@@ -199,6 +199,19 @@ int cgs_adam_step_partials(float* p, float* g, float* m, float* v, int64_t n, do
                            double eps, int32_t* step_state, float grad_scale, const float* partials,
                            int32_t n_partials, int64_t stride, int64_t offset, int64_t len, void* stream);
 
+/* `-process` inference, encoder + decoder half, in ONE kernel for the chfak=1 geometry (csrc/infer_fused.cu): uint8 NHWC
+ * frames [B,64,64,3] -> /255 -> NewCritic.forward(collect=True) in eval mode (nets.py:197-212) -> UnetDecoder dec[4]..dec[0]
+ * with their nearest-upsample + concat operands (nets.py:500-517) -> o0 [B,32,32,8] NHWC (the map `masker` consumes via
+ * cat(X, ups(o0)), nets.py:519-521) and pred [B].  TF32 tensor-core convolutions, fp32 accumulate; every intermediate stays
+ * in shared memory.  cw: critic tensors; wd4/bd4: dec_model.4; bd3..bd0: dec_model.{3..0}.bias;
+ * pack: cgs_infer_pack_floats() floats written by cgs_infer_pack_decoder from dec_model.{3,2,1,0}.weight (OIHW
+ * [16,48,3,3] [8,24,3,3] [8,16,3,3] [8,16,3,3]) - re-pack whenever those weights change. */
+int cgs_infer_pack_floats(void);
+int cgs_infer_pack_decoder(const float* wd3, const float* wd2, const float* wd1, const float* wd0, float* pack, void* stream);
+int cgs_infer_fused(const uint8_t* frames, int32_t B, const cgs_critic_weights* cw, const float* wd4, const float* bd4,
+                    const float* bd3, const float* bd2, const float* bd1, const float* bd0, const float* pack,
+                    float* pred, float* o0, void* stream);
+
 /* Data-parallel gradient exchange fused with Adam over NVLink peer memory (csrc/p2p_adam.cu).  Every rank owns a SYMMETRIC
  * gradient buffer sym[2][npad] and a flag pad (>= 16 uint32, zeroed once), both mapped into all peers.
  * cgs_p2p_stage: sym_local[slot][i] = g[i] + sum_k partials[k*stride + i - offset] (n_partials may be 0), g cleared;

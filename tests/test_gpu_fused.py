@@ -230,3 +230,59 @@ def test_fused_loss_curve_first_epochs_vs_reference_loop(ops):
     early = np.abs(closs[:40] - ref[:40]) / ref[:40]
     assert early.max() < 0.02, early.max()
     assert abs(np.median(closs[:94]) - np.median(ref[:94])) <= 0.02 * np.median(ref[:94])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fused encoder + decoder inference kernel (cgs_infer_fused, csrc/infer_fused.cu)
+def _decoder_o0_oracle(csd, msd, x):
+    """dec[4]..dec[0] of oracle/torch_ref.decoder_forward (reference nets.py:500-517), stopped before the masker convs."""
+    import torch.nn.functional as F
+    pred, e = torch_ref.critic_forward(csd, x, collect=True)
+    up = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")
+    o = F.conv2d(e[4], msd["dec_model.4.weight"], msd["dec_model.4.bias"])
+    o = up(up(o))
+    for k, emb in ((3, e[3]), (2, e[2]), (1, e[1]), (0, e[0])):
+        o = F.conv2d(torch.cat((emb, o), 1), msd[f"dec_model.{k}.weight"], msd[f"dec_model.{k}.bias"], padding=1)
+        if k:
+            o = up(o)
+    return pred, o
+
+
+@pytest.mark.parametrize("B", [3, 150, 300])
+def test_infer_fused_o0_and_pred_vs_oracle(ops, B):
+    from cgs_b200.nets import NewCritic, UnetDecoder
+    csd = synth.perturbed_state(synth.critic_shapes(1), 3 + B, 1.5)
+    msd = synth.perturbed_state(synth.masker_shapes(1), 4 + B, 1.5)
+    X, _, _ = synth.synthetic_frames(B, seed=B)
+    ct = {k: torch.from_numpy(v) for k, v in csd.items()}
+    mt = {k: torch.from_numpy(v) for k, v in msd.items()}
+    pred_r, o0_r = _decoder_o0_oracle(ct, mt, torch_ref.to_input(X))
+    c, m = NewCritic(), UnetDecoder()
+    c.load_state_dict(ct); m.load_state_dict(mt)
+    c.to(DEV).eval(); m.to(DEV).eval()
+    assert ops.infer_fused_supported(c, m)
+    pred, o0 = ops.infer_encode_decode(c, m, torch.from_numpy(X).to(DEV))
+    torch.cuda.synchronize()
+    assert np.abs(pred.cpu().numpy() - pred_r.numpy()).max() <= 2e-3
+    o0 = o0.permute(0, 3, 1, 2).cpu().numpy()
+    scale = np.abs(o0_r.numpy()).max()
+    assert np.abs(o0 - o0_r.numpy()).max() <= 4e-3 * scale, (np.abs(o0 - o0_r.numpy()).max(), scale)
+
+
+def test_infer_fused_process_path_on_trained_checkpoint(ops):
+    """-process through the fused encoder/decoder kernel + tcgen05 masker convs on the reference-trained checkpoint:
+    |mask - reference| <= 2e-2, IoU >= 0.99 at threshold 0.1 (the bound BASELINE.json states for the TF32 path)."""
+    from cgs_b200.train_handler import Handler, parse_args
+    d = load_golden("loops_c1.npz")
+    H = Handler(parse_args(["--binarymaskthreshold", "0.1"]), device=DEV)
+    H.critic.load_state_dict({k[len("trained.c."):]: torch.from_numpy(d[k]) for k in d.files if k.startswith("trained.c.")})
+    H.masker.load_state_dict({k[len("trained.m."):]: torch.from_numpy(d[k]) for k in d.files if k.startswith("trained.m.")})
+    X, _, _ = synth.synthetic_frames(6000, seed=0)
+    H.critic.to(DEV).eval(); H.masker.to(DEV).eval()
+    assert ops.infer_fused_supported(H.critic, H.masker)
+    preds, M, hard = H.segment_arrays(X[:32])
+    assert np.abs(M - d["proc_mask"]).max() <= 2e-2, np.abs(M - d["proc_mask"]).max()
+    ref_hard = np.unpackbits(d["proc_hard"])[:hard.size].reshape(hard.shape).astype(bool)
+    inter, union = (hard & ref_hard).sum(), (hard | ref_hard).sum()
+    assert inter / union >= 0.99, inter / union
+    assert np.abs(preds - d["proc_pred"].reshape(-1)).max() <= 2e-2

@@ -58,6 +58,7 @@ EXPORTS = {
     "cgs_infer_pack_floats": [],
     "cgs_infer_pack_decoder": [_f32p] * 5 + [C.c_void_p],
     "cgs_infer_fused": [_u8p, C.c_int32, C.POINTER(CriticWeights)] + [_f32p] * 9 + [C.c_void_p],
+    "cgs_masker_fused": [_u8p, _f32p, C.c_int32, _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p, _u8p, C.c_void_p],
     "cgs_p2p_stage": [_f32p, C.c_int64, C.c_int64, _f32p, _f32p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                       C.c_void_p],
     "cgs_p2p_allreduce_adam": [_f32p, _f32p, _f32p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32] +

@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(NT, 1) infer_fused_kernel(const Params p) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const float v0 = (r ? bot[2 * h] : top[2 * h]) + bias0, v1 = (r ? bot[2 * h + 1] : top[2 * h + 1]) + bias1;
-                *reinterpret_cast<float2*>(dO + ((e + r) * 32 + 8 * h) * 8) = make_float2(v0, v1);
+                *reinterpret_cast<float2*>(dO + ((e + r) * 32 + 8 * h) * 8) = make_float2(tf32r(v0), tf32r(v1));
               }
           });
     }
@@ -412,10 +412,205 @@ __global__ void __launch_bounds__(NT, 1) infer_fused_kernel(const Params p) {
   asm volatile("cp.async.wait_all;\n" ::);
 }
 
+// =====================================================================================================================
+// masker[0..3] (reference nets.py:488-491, 519-523) in one kernel: cat(X, ups(o0)) -> Conv2d(11,16,3,1,1) -> LeakyReLU(0.01)
+// -> Conv2d(16,1,3,1,1) -> Sigmoid [-> >= threshold].  62 % of the inference MACs; unfused, the 16-channel 64x64 map (256 KB
+// per frame) makes a round trip through HBM.  Here the map exists only as an 18-row band in shared memory: four bands of 16
+// mask rows per frame, the first conv computes the band's 18 rows (one row of overlap each side), the second consumes them.
+namespace mk {
+using namespace cf;
+constexpr int NT = 512;
+constexpr int P0 = 66, SX = 66 * 66 * 4;
+constexpr int P1 = 34, PL1 = 34 * 34 * 4;
+constexpr int PLB = 18 * 66 * 4;                      // one 4-channel plane of the band: 18 rows x 66 pixels
+constexpr int oX = 0, oO0 = oX + SX, oBand = oO0 + 2 * PL1, oU8 = oBand + 4 * PLB;
+constexpr int oW0 = oU8 + 3072;                      // masker.0 fragments: step (ky*5 + kk)*2 + nt
+constexpr int oW2 = oW0 + 30 * 64;                   // masker.2 fragments: step ky*6 + kx*2 + pg
+constexpr int oBias = oW2 + 18 * 64;                 // bm0[16] bm2[1]
+constexpr int SMEM_FLOATS = oBias + 32;
+static_assert(SMEM_FLOATS * 4 <= 227 * 1024, "shared memory budget");
+
+struct Params {
+  const uint8_t* frames;
+  const float* o0;
+  const float *w0, *b0, *w2, *b2;
+  float* mask;
+  uint8_t* hard;
+  float thresh;
+  int B;
+};
+
+__device__ __forceinline__ void prefetch(const Params& p, int n, float* sm, int tid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(sm);
+  const uint8_t* src = p.frames + (size_t)n * 12288;
+  for (int c = tid; c < 768; c += NT)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + (oU8 * 4) + c * 16), "l"(src + c * 16));
+  asm volatile("cp.async.commit_group;\n" ::);
+}
+// o0 [32][32][8] fp32 (already TF32-rounded by its producer) -> two haloed half-planes, 16 bytes at a time
+__device__ __forceinline__ void fetch_o0(const Params& p, int n, float* sm, int tid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(sm);
+  const float* src = p.o0 + (size_t)n * 8192;
+  for (int c = tid; c < 2048; c += NT) {
+    const int pix = c >> 1, half = c & 1, y = pix >> 5, x = pix & 31;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + (oO0 + half * PL1 + ((y + 1) * P1 + x + 1) * 4) * 4),
+                 "l"(src + c * 4));
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+}
+
+// masker.0 on R rows of the band starting at band row rb0 (absolute mask row = 16*band - 1 + band row)
+template <int R>
+__device__ __forceinline__ void m0_rows(float* sm, uint32_t smb, const float2 (&w)[3][5], int band, int rb0, int x0, int nt, int lane,
+                                        float bias0, float bias1) {
+  const int lj = lane >> 3, lr = lane & 7, g = lane >> 2, t = lane & 3;
+  const int vr0 = 16 * band - 1 + rb0;               // absolute output row of band row rb0; haloed virtual input row = vr0 + i
+  const uint32_t aA = smb + (oX + (x0 + lr + 8 * (lj & 1) + (lj >> 1)) * 4) * 4;
+  const uint32_t aB = smb + (oX + (x0 + lr + 8 * (lj & 1) + 2) * 4) * 4;
+  const int vx = x0 + lr + 8 * (lj & 1);
+  slide_rows<R, 5>(
+      w,
+      [&](int i, uint32_t(&a)[5][4]) {
+        int hv = vr0 + i;                             // haloed virtual row 0..65; rows of the out-of-frame band rows are clamped
+        hv = hv < 0 ? 0 : (hv > 65 ? 65 : hv);        // (their results are discarded below)
+        ldsm4(a[0], aA + hv * (P0 * 16));
+        ldsm2(a[1][0], a[1][1], aB + hv * (P0 * 16));
+        a[1][2] = a[1][3] = 0u;
+        const int sy = (hv + 1) >> 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+          ldsm4(a[2 + kx], smb + (oO0 + (lj >> 1) * PL1 + (sy * P1 + ((vx + kx + 1) >> 1)) * 4) * 4);
+      },
+      [&](int e, const float(&top)[4], const float(&bot)[4]) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int rb = rb0 + e + r, ya = 16 * band - 1 + rb;
+          const bool inside = ya >= 0 && ya < 64;     // rows -1 and 64 are the second conv's zero padding
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int x = x0 + g + 8 * (q >> 1), co = nt * 8 + 2 * t + (q & 1);
+            float v = (r ? bot[q] : top[q]) + ((q & 1) ? bias1 : bias0);
+            v = v > 0.f ? v : v * kLeakySlope;
+            sm[oBand + (co >> 2) * PLB + (rb * P0 + x + 1) * 4 + (co & 3)] = inside ? tf32r(v) : 0.f;
+          }
+        }
+      });
+}
+
+__global__ void __launch_bounds__(NT, 1) masker_fused_kernel(const Params p) {
+  extern __shared__ __align__(128) float sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int lj = lane >> 3, lr = lane & 7;
+  const float2* sW0 = reinterpret_cast<const float2*>(sm + oW0);
+  const float2* sW2 = reinterpret_cast<const float2*>(sm + oW2);
+  const uint32_t smb = (uint32_t)__cvta_generic_to_shared(sm);
+
+  if (blockIdx.x < p.B) { prefetch(p, blockIdx.x, sm, tid); fetch_o0(p, blockIdx.x, sm, tid); }
+  // ---- prologue: zero the operand planes (halos stay zero), weight fragments
+  for (int e = tid; e < 4 * PLB; e += NT) sm[oBand + e] = 0.f;
+  for (int e = tid; e < 2 * PL1 / 4; e += NT) {      // only the halo ring must be zero; cp.async is filling the interior
+    const int h = e / (PL1 / 4), q = e - h * (PL1 / 4), y = q / P1, x = q - y * P1;
+    if (y == 0 || y == 33 || x == 0 || x == 33) *reinterpret_cast<float4*>(sm + oO0 + h * PL1 + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int e = tid; e < 30 * 32; e += NT) {
+    const int ln = e & 31, gg = ln >> 2, tt = ln & 3, s = e >> 5, nt = s & 1, kk = (s >> 1) % 5, ky = (s >> 1) / 5;
+    const float* w = p.w0 + (size_t)(nt * 8 + gg) * 99;          // [16][11][3][3]
+    float x = 0.f, y = 0.f;
+    if (kk == 0) { if (tt < 3) { x = __ldg(w + tt * 9 + ky * 3); y = __ldg(w + tt * 9 + ky * 3 + 1); } }
+    else if (kk == 1) { if (tt < 3) x = __ldg(w + tt * 9 + ky * 3 + 2); }
+    else { x = __ldg(w + (3 + tt) * 9 + ky * 3 + kk - 2); y = __ldg(w + (7 + tt) * 9 + ky * 3 + kk - 2); }
+    sm[oW0 + 2 * e] = tf32r(x); sm[oW0 + 2 * e + 1] = tf32r(y);
+  }
+  for (int e = tid; e < 18 * 32; e += NT) {
+    const int ln = e & 31, gg = ln >> 2, tt = ln & 3, s = e >> 5, pg = s & 1, tap = (s / 6) * 3 + (s % 6) / 2;
+    float x = 0.f, y = 0.f;
+    if (gg == 0) { x = __ldg(p.w2 + (pg * 8 + tt) * 9 + tap); y = __ldg(p.w2 + (pg * 8 + tt + 4) * 9 + tap); }
+    sm[oW2 + 2 * e] = tf32r(x); sm[oW2 + 2 * e + 1] = tf32r(y);
+  }
+  if (tid < 16) sm[oBias + tid] = __ldg(p.b0 + tid);
+  if (tid == 16) sm[oBias + 16] = __ldg(p.b2);
+
+  for (int n = blockIdx.x; n < p.B; n += gridDim.x) {
+    asm volatile("cp.async.wait_all;\n" ::);
+    __syncthreads();
+    inf::stage_frame(reinterpret_cast<const uint8_t*>(sm + oU8), sm + oX, tid);
+    __syncthreads();
+    if (n + (int)gridDim.x < p.B) prefetch(p, n + gridDim.x, sm, tid);
+    for (int band = 0; band < 4; ++band) {
+      // ---- masker.0 + LeakyReLU on the band's 18 rows: 4 strips x 2 channel tiles x 2 row segments (10 + 8 rows)
+      {
+        const int x0 = (warp & 3) * 16, nt = (warp >> 2) & 1, seg = warp >> 3;
+        float2 w[3][5];
+#pragma unroll
+        for (int s = 0; s < 15; ++s) w[s / 5][s % 5] = sW0[(s * 2 + nt) * 32 + lane];
+        const float bias0 = sm[oBias + nt * 8 + 2 * t], bias1 = sm[oBias + nt * 8 + 2 * t + 1];
+        if (seg == 0) m0_rows<10>(sm, smb, w, band, 0, x0, nt, lane, bias0, bias1);
+        else m0_rows<8>(sm, smb, w, band, 10, x0, nt, lane, bias0, bias1);
+      }
+      __syncthreads();
+      // ---- masker.2 + Sigmoid (+ threshold) on the band's 16 mask rows: 4 strips x 4 segments of 4 rows
+      {
+        const int x0 = (warp & 3) * 16, r0 = (warp >> 2) * 4;
+        float2 w[3][6];
+#pragma unroll
+        for (int s = 0; s < 18; ++s) w[s / 6][s % 6] = sW2[s * 32 + lane];
+        const uint32_t aA = smb + (oBand + (lj >> 1) * PLB + (r0 * P0 + x0 + lr + 8 * (lj & 1)) * 4) * 4;
+        const float b2 = sm[oBias + 16];
+        float* dM = p.mask + (size_t)n * 4096 + (16 * band + r0) * 64 + x0 + g;
+        uint8_t* dH = p.hard ? p.hard + (size_t)n * 4096 + (16 * band + r0) * 64 + x0 + g : nullptr;
+        slide_rows<4, 6>(
+            w,
+            [&](int i, uint32_t(&a)[6][4]) {
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                ldsm4(a[2 * kx], aA + ((i * P0 + kx) * 4) * 4);
+                ldsm4(a[2 * kx + 1], aA + (2 * PLB + (i * P0 + kx) * 4) * 4);
+              }
+            },
+            [&](int e, const float(&top)[4], const float(&bot)[4]) {
+              if (t == 0) {                             // column 0 of the 8-wide tile is the one real output channel
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    const float z = sigmoidf_((r ? bot[2 * h] : top[2 * h]) + b2);
+                    dM[(e + r) * 64 + 8 * h] = z;
+                    if (dH) dH[(e + r) * 64 + 8 * h] = z >= p.thresh;
+                  }
+              }
+            });
+      }
+      __syncthreads();
+    }
+    if (n + (int)gridDim.x < p.B) fetch_o0(p, n + gridDim.x, sm, tid);   // all reads of this frame's o0 planes are done
+  }
+  asm volatile("cp.async.wait_all;\n" ::);
+}
+}  // namespace mk
+
 }  // namespace inf
 }  // namespace cgs
 
 using namespace cgs;
+
+extern "C" int cgs_masker_fused(const uint8_t* frames, const float* o0, int32_t B, const float* wm0, const float* bm0,
+                                const float* wm2, const float* bm2, float thresh, float* mask, uint8_t* hard, void* stream) {
+  CGS_REQUIRE(frames && o0 && wm0 && bm0 && wm2 && bm2 && mask && B > 0, "masker_fused: bad args");
+  CGS_REQUIRE(((uintptr_t)frames & 15) == 0 && ((uintptr_t)o0 & 15) == 0, "masker_fused: frames and o0 must be 16-byte aligned");
+  inf::mk::Params p;
+  p.frames = frames; p.o0 = o0; p.w0 = wm0; p.b0 = bm0; p.w2 = wm2; p.b2 = bm2; p.mask = mask; p.hard = hard; p.thresh = thresh;
+  p.B = B;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    cudaFuncSetAttribute(inf::mk::masker_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, inf::mk::SMEM_FLOATS * 4);
+  }
+  const int per = (B + sms - 1) / sms, grid = (B + per - 1) / per;
+  inf::mk::masker_fused_kernel<<<grid, inf::mk::NT, inf::mk::SMEM_FLOATS * 4, (cudaStream_t)stream>>>(p);
+  return check_launch("masker_fused");
+}
 
 extern "C" int cgs_infer_pack_floats(void) { return inf::PACK_FLOATS; }
 

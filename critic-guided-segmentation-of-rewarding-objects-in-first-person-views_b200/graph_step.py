@@ -109,13 +109,12 @@ class GraphedSegment(_Graphed):
 
         def fn():
             with torch.no_grad():
-                xf = ops.frames_to_float(self.X, 0)
                 if ops.infer_fused_supported(H.critic, H.masker):
-                    # encoder + decoder in one kernel, every intermediate in shared memory; the masker convs on tcgen05
+                    # two kernels, every intermediate in shared memory: encoder + decoder -> o0 (32 KB/frame), then masker
                     pred, o0 = ops.infer_encode_decode(H.critic, H.masker, self.X)
-                    mask, hard = H.masker.mask_from_o0(xf, o0, threshold)
+                    mask, hard = ops.masker_fused(H.masker, self.X, o0, threshold)
                 else:
-                    x = xf.permute(0, 3, 1, 2)
+                    x = ops.frames_to_float(self.X, 0).permute(0, 3, 1, 2)
                     pred, embeds = H.critic(x, collect=True)
                     mask, hard = H.masker.forward_hard(x, embeds, threshold)
             return pred, mask, hard

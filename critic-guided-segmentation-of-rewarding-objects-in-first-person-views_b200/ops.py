@@ -551,7 +551,7 @@ def infer_fused_supported(critic, masker):
                 and _lib.lib().cgs_critic_fused_supported(f[0].out_channels, f[3].out_channels, f[6].out_channels,
                                                           f[10].out_channels, f[14].out_channels)
                 and tuple(d[3].weight.shape) == (16, 48, 3, 3) and tuple(d[0].weight.shape) == (8, 16, 3, 3)
-                and tuple(d[4].weight.shape) == (32, 32, 1, 1))
+                and tuple(d[4].weight.shape) == (32, 32, 1, 1) and tuple(masker.masker[0].weight.shape) == (16, 11, 3, 3))
 
 
 def infer_encode_decode(critic, masker, frames_u8):
@@ -575,6 +575,18 @@ def infer_encode_decode(critic, masker, frames_u8):
           _p(d[3].bias.detach()), _p(d[2].bias.detach()), _p(d[1].bias.detach()), _p(d[0].bias.detach()), _p(cache[1]),
           _p(pred), _p(o0), _stream())
     return pred.unsqueeze(1), o0
+
+
+def masker_fused(masker, frames_u8, o0, thresh=None):
+    """masker[0..3] on cat(X, ups(o0)) in ONE kernel (cgs_masker_fused): returns (mask [B,1,64,64], hard uint8 or None)."""
+    B = frames_u8.shape[0]
+    m0, m2 = masker.masker[0], masker.masker[2]
+    mask = torch.empty((B, 1, 64, 64), device=frames_u8.device, dtype=torch.float32)
+    hard = torch.empty((B, 1, 64, 64), device=frames_u8.device, dtype=torch.uint8) if thresh is not None else None
+    _call("cgs_masker_fused", _p(frames_u8, torch.uint8), _p(o0), B, _p(m0.weight.detach()), _p(m0.bias.detach()),
+          _p(m2.weight.detach()), _p(m2.bias.detach()), float(thresh if thresh is not None else 0.0), _p(mask),
+          _p(hard, torch.uint8), _stream())
+    return mask, hard
 
 
 def reduce_partials(g, buf, n_partials, stride, offset, length):

@@ -450,16 +450,16 @@ class Handler:
         preds, M, hard = [], [], []
         with torch.no_grad():
             for bidx in range(0, len(X_u8), batchsize):
-                batch = self._to_input(X_u8[bidx:bidx + batchsize])
                 if not a.separate and ops.infer_fused_supported(critic, masker):
                     xu8 = torch.from_numpy(np.ascontiguousarray(X_u8[bidx:bidx + batchsize])).to(self.device)
                     pred, o0 = ops.infer_encode_decode(critic, masker, xu8)
-                    mask, hm = masker.mask_from_o0(batch.permute(0, 2, 3, 1).contiguous(), o0, a.binarymaskthreshold or None)
+                    mask, hm = ops.masker_fused(masker, xu8, o0, a.binarymaskthreshold or None)
                     if hm is not None:
                         hard.append(hm.cpu().numpy().astype(bool))
                     preds.append(pred.squeeze(1).cpu().numpy())
                     M.append(mask.cpu().numpy())
                     continue
+                batch = self._to_input(X_u8[bidx:bidx + batchsize])
                 pred, embeds = critic(batch, collect=True)
                 if a.separate:
                     _, embeds = self.sepcrit.to(self.device).train(train)(batch, collect=True)

@@ -212,6 +212,13 @@ int cgs_infer_fused(const uint8_t* frames, int32_t B, const cgs_critic_weights* 
                     const float* bd3, const float* bd2, const float* bd1, const float* bd0, const float* pack,
                     float* pred, float* o0, void* stream);
 
+/* The masker half of `-process` in ONE kernel (chfak=1: masker.0 is [16,11,3,3]): cat(X, ups(o0)) -> Conv2d + LeakyReLU(0.01)
+ * -> Conv2d(16,1) -> Sigmoid (nets.py:488-491, 519-523) [-> hard = mask >= thresh, main.py:1164].  frames: uint8 NHWC
+ * [B,64,64,3]; o0 [B,32,32,8] NHWC fp32 as written by cgs_infer_fused; mask [B,64,64] fp32; hard [B,64,64] uint8 or NULL.
+ * The 16-channel 64x64 intermediate only ever exists as an 18-row band in shared memory. */
+int cgs_masker_fused(const uint8_t* frames, const float* o0, int32_t B, const float* wm0, const float* bm0,
+                     const float* wm2, const float* bm2, float thresh, float* mask, uint8_t* hard, void* stream);
+
 /* Data-parallel gradient exchange fused with Adam over NVLink peer memory (csrc/p2p_adam.cu).  Every rank owns a SYMMETRIC
  * gradient buffer sym[2][npad] and a flag pad (>= 16 uint32, zeroed once), both mapped into all peers.
  * cgs_p2p_stage: sym_local[slot][i] = g[i] + sum_k partials[k*stride + i - offset] (n_partials may be 0), g cleared;

@@ -286,3 +286,26 @@ def test_infer_fused_process_path_on_trained_checkpoint(ops):
     inter, union = (hard & ref_hard).sum(), (hard | ref_hard).sum()
     assert inter / union >= 0.99, inter / union
     assert np.abs(preds - d["proc_pred"].reshape(-1)).max() <= 2e-2
+
+
+@pytest.mark.parametrize("B", [2, 150])
+def test_masker_fused_vs_oracle(ops, B):
+    """cgs_masker_fused on (frames, o0) vs the oracle's masker convs on the same o0."""
+    import torch.nn.functional as F
+    from cgs_b200.nets import UnetDecoder
+    msd = synth.perturbed_state(synth.masker_shapes(1), 9 + B, 1.5)
+    mt = {k: torch.from_numpy(v) for k, v in msd.items()}
+    X, _, _ = synth.synthetic_frames(B, seed=70 + B)
+    g = torch.Generator().manual_seed(B)
+    o0 = (torch.rand(B, 8, 32, 32, generator=g) * 2 - 1)
+    x = torch_ref.to_input(X)
+    m = F.conv2d(torch.cat((x, F.interpolate(o0, scale_factor=2, mode="nearest")), 1), mt["masker.0.weight"], mt["masker.0.bias"], padding=1)
+    z_r = torch.sigmoid(F.conv2d(F.leaky_relu(m, 0.01), mt["masker.2.weight"], mt["masker.2.bias"], padding=1))
+    md = UnetDecoder()
+    md.load_state_dict(mt)
+    md.to(DEV).eval()
+    z, hard = ops.masker_fused(md, torch.from_numpy(X).to(DEV), o0.permute(0, 2, 3, 1).contiguous().to(DEV), 0.5)
+    torch.cuda.synchronize()
+    err = (z.cpu() - z_r).abs().max().item()
+    assert err <= 3e-3, err
+    assert torch.equal(hard.bool(), z >= 0.5)

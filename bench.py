@@ -233,6 +233,33 @@ def fused_step_roofline(B, flush, hbm_gbs, tf_peak):
             "mma_sync_tf32_peak_tflops": mma_peak, "frac_mma_sync_tf32_peak": flops / sec / 1e12 / mma_peak}
 
 
+def masker_roofline(B, flush, hbm_gbs, tf_peak):
+    """Dominant kernel of the inference workload: cgs_masker_fused (masker.0 + LeakyReLU + masker.2 + sigmoid + threshold),
+    timed alone.  Per frame: 2 * (6,488,064 + 589,824) FLOP; HBM bytes 12,288 (frame) + 32,768
+    (o0) + 16,384 (mask) + 4,096 (hard mask)."""
+    from cgs_b200 import ops
+    from cgs_b200.nets import UnetDecoder
+    torch.manual_seed(0)
+    m = UnetDecoder().cuda().eval()
+    X = torch.randint(0, 255, (B, 64, 64, 3), dtype=torch.uint8, device="cuda")
+    o0 = torch.rand(B, 32, 32, 8, device="cuda")
+    run = lambda: ops.masker_fused(m, X, o0, 0.1)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        run()
+    sec = time_kernel(g.replay, flush)
+    flops, byts = 2 * (6488064 + 589824) * B, (12288 + 32768 + 16384 + 4096) * B
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    mma_peak = sms * 512 * 2 * 1.965e9 / 1e12
+    return {"kernel": "masker_fused_kernel", "desc": "cat(X, ups(o0)) -> masker.0 -> LeakyReLU -> masker.2 -> sigmoid -> threshold",
+            "sec": sec, "flops": flops, "bytes": byts, "tflops": flops / sec / 1e12, "gbs": byts / sec / 1e9,
+            "frac_hbm": byts / sec / 1e9 / hbm_gbs, "frac_tensor_bf16_peak": flops / sec / 1e12 / tf_peak,
+            "mma_sync_tf32_peak_tflops": mma_peak, "frac_mma_sync_tf32_peak": flops / sec / 1e12 / mma_peak}
+
+
 def run_ours(args, rank, world):
     import torch.distributed as dist
     from cgs_b200 import ops
@@ -339,6 +366,8 @@ def run_ours(args, rank, world):
                 "config": {"workload": WORKLOADS[args.workload], "batch_per_gpu": B, "global_batch": B * world,
                            "precision": (("whole step in one kernel: TF32 mma.sync convolutions (fprop, dgrad, wgrad), fp32 "
                                           "accumulate; head, loss, Adam fp32" if (args.workload == "critic_train" and args.chfak == 1)
+                                          else "two whole-frame kernels (encoder+decoder, masker): TF32 mma.sync convolutions, fp32 "
+                                          "accumulate" if (args.workload == "infer" and args.chfak == 1)
                                           else "conv fprop/dgrad: tcgen05 kind::tf32, fp32 accumulate in TMEM; wgrad: TF32 mma.sync; "
                                           "head, losses, Adam: fp32") if args.precision == "tf32" else "all fp32 (FFMA)"),
                            "chfak": args.chfak, "parallelism": f"dp{world}", "timing": "cuda events per step, L2 flushed "
@@ -353,7 +382,19 @@ def run_ours(args, rank, world):
             tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
             tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
             fused = (args.workload == "critic_train" and args.precision == "tf32" and args.chfak == 1)
-            if fused:
+            if args.workload == "infer" and args.precision == "tf32" and args.chfak == 1:
+                pj = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if which == "measured" else {}
+                tf_burst = pj.get("bf16_tflops", 1590.0)
+                k = masker_roofline(B, flush, hbm, tf_burst)
+                line["roofline"] = {"bound": "tensor", "achieved": k["tflops"], "peak": tf_burst, "unit": "TFLOP/s",
+                                    "frac": k["frac_tensor_bf16_peak"], "traffic": tj.get(k["kernel"]) if B == 256 else None,
+                                    "kernel": k["kernel"], "algorithmic_flops": k["flops"], "algorithmic_bytes": k["bytes"],
+                                    "peak_source": which + " (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)",
+                                    "launch_us": k["sec"] * 1e6, "hbm_gbs_achieved": k["gbs"], "frac_hbm": k["frac_hbm"],
+                                    "mma_sync_tf32_peak_tflops": k["mma_sync_tf32_peak_tflops"],
+                                    "frac_of_mma_sync_tf32_peak": k["frac_mma_sync_tf32_peak"]}
+                line["kernels"] = [{kk: (round(v, 4) if isinstance(v, float) else v) for kk, v in k.items()}]
+            elif fused:
                 # dominant kernel = the whole-step kernel (79 % of the step, profiles/): a dense-contraction kernel whose
                 # operands never leave shared memory -> tensor roofline; HBM traffic is the uint8 frames only
                 pj = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if which == "measured" else {}

@@ -159,7 +159,7 @@ def test_fused_in_kernel_adam_matches_adam_kernel(ops, B):
     # (Adam divides by sqrt(v): entries whose gradient is rounding noise amplify the reordering to ~1e-5 after 3 steps)
     assert (oa.flat - ob.flat).abs().max().item() <= 3e-5, (oa.flat - ob.flat).abs().max().item()
     assert (oa.flat - ob.flat).abs().mean().item() <= 2e-7
-    assert (oa.m - ob.m).abs().max().item() <= 1e-6 * max(1.0, ob.m.abs().max().item())
+    assert (oa.m - ob.m).abs().max().item() <= 1e-5 * max(1.0, ob.m.abs().max().item())      # 3 steps of slightly different parameters
     assert float(oa.gflat.abs().max()) == 0.0
 
 

@@ -309,3 +309,51 @@ def test_masker_fused_vs_oracle(ops, B):
     err = (z.cpu() - z_r).abs().max().item()
     assert err <= 3e-3, err
     assert torch.equal(hard.bool(), z >= 0.5)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's large batches (the oracle would take minutes there)
+def test_fused_step_batch_linearity_at_8192(ops):
+    """Mean-loss gradient of a batch of 8192 frames == the average of the gradients of its four 2048-frame quarters
+    (frames are independent units: SURVEY.md §8e), and pred / masks of a frame do not depend on its batch."""
+    B, Q = 8192, 2048
+    csd, X, y, _ = _case(B, 0.0, seed=77)
+    c = _critic(csd, 0.0)
+    Xd, yd = torch.from_numpy(X).to(DEV), torch.from_numpy(y).to(DEV)
+    for q in c.parameters():
+        q.grad = torch.zeros_like(q)
+    loss, pred = ops.critic_train_fused(c, Xd, yd, 4)
+    g_full = torch.cat([q.grad.reshape(-1) for q in c.parameters()]).clone()
+    for q in c.parameters():
+        q.grad.zero_()
+    losses, preds = [], []
+    for k in range(B // Q):
+        l, p = ops.critic_train_fused(c, Xd[k * Q:(k + 1) * Q], yd[k * Q:(k + 1) * Q], 4, loss_grad=Q / B)
+        losses.append(l.item()); preds.append(p)
+    g_parts = torch.cat([q.grad.reshape(-1) for q in c.parameters()])
+    assert torch.equal(torch.cat(preds), pred)                                  # per-frame results are batch-independent, bitwise
+    assert abs(np.mean(losses) - loss.item()) <= 1e-5 * abs(loss.item())
+    assert (g_full - g_parts).abs().max().item() <= 2e-5 * g_full.abs().max().item()
+
+
+def test_infer_fused_is_batch_independent_at_4096(ops):
+    """Mask inference sweep sizes (BASELINE configs[4]): every frame's pred / mask / hard mask is bitwise the same whether it
+    is processed in a batch of 4096 or of 37, and hard == (mask >= threshold) everywhere."""
+    from cgs_b200.nets import NewCritic, UnetDecoder
+    csd = synth.perturbed_state(synth.critic_shapes(1), 5, 1.5)
+    msd = synth.perturbed_state(synth.masker_shapes(1), 6, 1.5)
+    c, m = NewCritic(), UnetDecoder()
+    c.load_state_dict({k: torch.from_numpy(v) for k, v in csd.items()})
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in msd.items()})
+    c.to(DEV).eval(); m.to(DEV).eval()
+    X, _, _ = synth.synthetic_frames(4096, seed=9)
+    Xd = torch.from_numpy(X).to(DEV)
+    pred, o0 = ops.infer_encode_decode(c, m, Xd)
+    mask, hard = ops.masker_fused(m, Xd, o0, 0.1)
+    sl = slice(1000, 1037)
+    pred_s, o0_s = ops.infer_encode_decode(c, m, Xd[sl].contiguous())
+    mask_s, hard_s = ops.masker_fused(m, Xd[sl].contiguous(), o0_s, 0.1)
+    assert torch.equal(pred[sl], pred_s) and torch.equal(o0[sl], o0_s)
+    assert torch.equal(mask[sl], mask_s) and torch.equal(hard[sl], hard_s)
+    assert torch.equal(hard.bool(), mask >= 0.1)
+    assert 0.0 < float(mask.min()) and float(mask.max()) < 1.0

@@ -157,13 +157,12 @@ __device__ __forceinline__ void wgrad8_store(const float (&acc)[5][4], float* ti
 
 // raw bytes -> haloed [66][66] x (r,g,b,0) fp32 /255 with the circular W-roll; tf32(b * (1/255)) == tf32(b / 255) for all b
 __device__ __forceinline__ void stage_frame(const uint8_t* __restrict__ sU8, float* __restrict__ sXd, int roll, int tid) {
-  const float k = 1.f / 255.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int p = tid + NT * i, y = p >> 6, x = p & 63;
     const uint8_t* s = sU8 + (y * 64 + ((x + roll) & 63)) * 3;
     float4 v;
-    v.x = tf32r(u8f(s[0]) * k); v.y = tf32r(u8f(s[1]) * k); v.z = tf32r(u8f(s[2]) * k); v.w = 0.f;
+    v.x = u8_to_tf32_unit(s[0]); v.y = u8_to_tf32_unit(s[1]); v.z = u8_to_tf32_unit(s[2]); v.w = 0.f;
     *reinterpret_cast<float4*>(sXd + ((y + 1) * P0 + x + 1) * 4) = v;
   }
   if (tid < 260) {   // halo ring
@@ -797,7 +796,12 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
 #pragma unroll
     for (int i = 0; i < 16; ++i) atomicAdd(d4 + (((i >> 2) + rot4) & 3) * 4 + (i & 3), accW4[i]);
   }
-  if (tid == 0 && blockIdx.x < p.B) atomicAdd(p.loss, loss_acc * p.inv_n);
+  if (tid == 0) {
+    // loss: one atomic per CTA into the scalar the host zeroed - or, with the grid barrier below, a slot of this CTA's
+    // partial vector that CTA 0 sums in a fixed order afterwards (no memset node, bit-reproducible)
+    if (p.adam_p) p.partials[(size_t)blockIdx.x * PSTRIDE + NGRAD] = loss_acc * p.inv_n;
+    else atomicAdd(p.loss, loss_acc * p.inv_n);
+  }
   if (p.adam_p) {
     // ---- grid barrier (all CTAs are co-resident: one per SM, grid <= SMs), then every CTA sums its slice of the
     //      parameter vector over all partial vectors (fixed order) and applies Adam: no second launch, no atomics
@@ -818,6 +822,12 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
       }
     }
     CF_MARK(18);
+    if (blockIdx.x == 0 && warp == 1) {
+      float l = 0.f;
+      for (int k = lane; k < (int)gridDim.x; k += 32) l += __ldcg(p.partials + (size_t)k * PSTRIDE + NGRAD);
+      l = warp_sum(l);
+      if (lane == 0) p.loss[0] = l;
+    }
     const int t = p.step_state[0] + 1;
     float* red = sm + oA;                           // [4][128] + the two bias-correction scalars
     if (tid == 0) {                                 // double-precision pow once per CTA
@@ -985,7 +995,7 @@ extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target
     cudaFuncSetAttribute(cf::critic_fused_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
     attr = true;
   }
-  if (cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) return check_launch("critic_train_fused.memset");
+  if (!adam && cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) return check_launch("critic_train_fused.memset");
   cf::critic_fused_train_kernel<<<cgs_critic_fused_grid(B), cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
   return check_launch("critic_train_fused");
 }

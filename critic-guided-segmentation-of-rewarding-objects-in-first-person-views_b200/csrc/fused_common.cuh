@@ -71,7 +71,12 @@ __device__ __forceinline__ void pool2x2(const float (&top)[4], const float (&bot
   }
 }
 
-__device__ __forceinline__ float u8f(uint32_t b) { return __uint_as_float(0x4B000000u | b) - 8388608.f; }
+// uint8 -> TF32(b / 255): 0x4B000000 | b is the float 2^23 + b; one FMA with the exactly representable constant -2^23/255
+// leaves round(b * (1/255)), whose TF32 rounding equals that of the reference's b / 255.0f for all 256 values.
+__device__ __forceinline__ float u8_to_tf32_unit(uint32_t b) {
+  constexpr float k = 1.f / 255.f;
+  return tf32r(fmaf(__uint_as_float(0x4B000000u | b), k, -8388608.f * k));
+}
 
 }  // namespace cf
 }  // namespace cgs

@@ -72,13 +72,12 @@ __global__ void pack_decoder_kernel(const float* __restrict__ w3, const float* _
 }
 
 __device__ __forceinline__ void stage_frame(const uint8_t* __restrict__ sU8, float* __restrict__ sXd, int tid) {
-  const float k = 1.f / 255.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int p = tid + NT * i, y = p >> 6, x = p & 63;
     const uint8_t* s = sU8 + p * 3;
     float4 v;
-    v.x = tf32r(u8f(s[0]) * k); v.y = tf32r(u8f(s[1]) * k); v.z = tf32r(u8f(s[2]) * k); v.w = 0.f;
+    v.x = u8_to_tf32_unit(s[0]); v.y = u8_to_tf32_unit(s[1]); v.z = u8_to_tf32_unit(s[2]); v.w = 0.f;
     *reinterpret_cast<float4*>(sXd + ((y + 1) * P0 + x + 1) * 4) = v;
   }
   if (tid < 260) {   // halo ring (the region doubles as reduction scratch, so it is rewritten every frame)

@@ -255,34 +255,52 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
   // ---- prologue: accumulators, halos that stay zero, weight fragments (TF32, in mma B-fragment order), biases
   for (int e = tid; e < szAcc; e += NT) sAcc[e] = 0.f;
   for (int e = tid; e < 2 * PL2 + 512 + 2 * PL3; e += NT) sm[oE1 + e] = 0.f;        // e1, idx1, e2 (halos stay zero)
-  for (int e = tid; e < szW / 2; e += NT) {
-    const int ln = e & 31, gg = ln >> 2, tt = ln & 3;
-    float x = 0.f, y = 0.f;
-    int s = e >> 5;
-    if (s < 6) {                                   // L0 fprop: step (ky, kk): kk 0 = taps (ky,0 | ky,1), kk 1 = tap (ky,2) | 0
-      const int ky = s >> 1, kk = s & 1;
-      if (tt < 3) {
-        x = __ldg(p.w0 + gg * 27 + tt * 9 + ky * 3 + (kk ? 2 : 0));
-        if (!kk) y = __ldg(p.w0 + gg * 27 + tt * 9 + ky * 3 + 1);
+  {
+    // 2496 fragment entries, 5 per thread: first all source addresses, then all loads in flight together (a cold launch
+    // pays ONE HBM round trip for its weights, not five), then round + store
+    const float* src[5][2];
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const int e = tid + NT * it;
+      const int ln = e & 31, gg = ln >> 2, tt = ln & 3;
+      const float *x = nullptr, *y = nullptr;
+      int s = e >> 5;
+      if (e >= szW / 2) {
+      } else if (s < 6) {                          // L0 fprop: step (ky, kk): kk 0 = taps (ky,0 | ky,1), kk 1 = tap (ky,2) | 0
+        const int ky = s >> 1, kk = s & 1;
+        if (tt < 3) {
+          x = p.w0 + gg * 27 + tt * 9 + ky * 3 + (kk ? 2 : 0);
+          if (!kk) y = p.w0 + gg * 27 + tt * 9 + ky * 3 + 1;
+        }
+      } else if ((s -= 6) < 18) {                  // L1 / L2 fprop: tap
+        const float* w = s < 9 ? p.w1 : p.w2;
+        const int tap = s % 9;
+        x = w + (gg * 8 + tt) * 9 + tap; y = w + (gg * 8 + tt + 4) * 9 + tap;
+      } else if ((s -= 18) < 18) {                 // L3 fprop: (tap, nt)
+        const int tap = s >> 1, co = (s & 1) * 8 + gg;
+        x = p.w3 + (co * 8 + tt) * 9 + tap; y = p.w3 + (co * 8 + tt + 4) * 9 + tap;
+      } else if ((s -= 18) < 18) {                 // L3 dgrad: (tap', ks): B[k = co][n = ci] = W[co][ci][8 - tap']
+        const int tap = 8 - (s >> 1), co = (s & 1) * 8 + tt;
+        x = p.w3 + (co * 8 + gg) * 9 + tap; y = p.w3 + ((co + 4) * 8 + gg) * 9 + tap;
+      } else {                                     // L2 / L1 dgrad: tap'
+        s -= 18;
+        const float* w = s < 9 ? p.w2 : p.w1;
+        const int tap = 8 - s % 9;
+        x = w + (tt * 8 + gg) * 9 + tap; y = w + ((tt + 4) * 8 + gg) * 9 + tap;
       }
-    } else if ((s -= 6) < 18) {                    // L1 / L2 fprop: tap
-      const float* w = s < 9 ? p.w1 : p.w2;
-      const int tap = s % 9;
-      x = __ldg(w + (gg * 8 + tt) * 9 + tap); y = __ldg(w + (gg * 8 + tt + 4) * 9 + tap);
-    } else if ((s -= 18) < 18) {                   // L3 fprop: (tap, nt)
-      const int tap = s >> 1, co = (s & 1) * 8 + gg;
-      x = __ldg(p.w3 + (co * 8 + tt) * 9 + tap); y = __ldg(p.w3 + (co * 8 + tt + 4) * 9 + tap);
-    } else if ((s -= 18) < 18) {                   // L3 dgrad: (tap', ks): B[k = co][n = ci] = W[co][ci][8 - tap']
-      const int tap = 8 - (s >> 1), co = (s & 1) * 8 + tt;
-      x = __ldg(p.w3 + (co * 8 + gg) * 9 + tap); y = __ldg(p.w3 + ((co + 4) * 8 + gg) * 9 + tap);
-    } else {                                       // L2 / L1 dgrad: tap'
-      s -= 18;
-      const float* w = s < 9 ? p.w2 : p.w1;
-      const int tap = 8 - s % 9;
-      x = __ldg(w + (tt * 8 + gg) * 9 + tap); y = __ldg(w + ((tt + 4) * 8 + gg) * 9 + tap);
+      src[it][0] = x; src[it][1] = y;
     }
-    sm[oW + 2 * e] = tf32r(x);
-    sm[oW + 2 * e + 1] = tf32r(y);
+    float val[5][2];
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      val[it][0] = src[it][0] ? __ldg(src[it][0]) : 0.f;
+      val[it][1] = src[it][1] ? __ldg(src[it][1]) : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const int e = tid + NT * it;
+      if (e < szW / 2) { sm[oW + 2 * e] = tf32r(val[it][0]); sm[oW + 2 * e + 1] = tf32r(val[it][1]); }
+    }
   }
   if (tid < 8) { sm[oBias + tid] = __ldg(p.b0 + tid); sm[oBias + 8 + tid] = __ldg(p.b1 + tid); sm[oBias + 16 + tid] = __ldg(p.b2 + tid); }
   if (tid < 16) sm[oBias + 24 + tid] = __ldg(p.b3 + tid);

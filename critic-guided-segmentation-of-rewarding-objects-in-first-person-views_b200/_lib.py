@@ -81,6 +81,7 @@ EXPORTS = {
     "cgs_adam_step": [_f32p] * 4 + [C.c_int64] + [C.c_double] * 4 + [C.c_void_p, C.c_float, C.c_int32, C.c_void_p],
     "cgs_threshold": [_f32p, C.c_int64, C.c_float, C.c_int32, _u8p, C.c_void_p],
     "cgs_dropout_masks": [_f32p, C.c_int64, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p],
+    "cgs_iou_counts": [_f32p, _u8p, C.c_int64, C.c_float, C.c_int32, C.c_void_p, C.c_void_p],
     "cgs_tc_status": [],
     "cgs_tc_set_trace": [C.c_void_p],
     "cgs_critic_fused_set_trace": [C.c_void_p],

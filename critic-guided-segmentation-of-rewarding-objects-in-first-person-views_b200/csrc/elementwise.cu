@@ -243,6 +243,31 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   }
 }
 
+// ---------------------------------------------------------------- -eval: hard mask vs ground truth -> IoU counts
+// hardM = M > eval_thresh (reference main.py:964; >= for the -process convention), get_iou's np.sum(A & B), np.sum(A | B)
+// (main.py:1265-1270) as one pass: compare, ballot, popcount, one 64-bit atomic pair per CTA.  Exact integer arithmetic.
+__global__ void iou_counts_kernel(const float* __restrict__ z, const uint8_t* __restrict__ gt, int64_t n, float thresh, int strict,
+                                  unsigned long long* __restrict__ counts) {
+  unsigned inter = 0, uni = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = __ldg(z + i);
+    const bool h = strict ? (v > thresh) : (v >= thresh), g = __ldg(gt + i) != 0;
+    inter += h && g;
+    uni += h || g;
+  }
+  __shared__ unsigned s_i[8], s_u[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { inter += __shfl_xor_sync(0xffffffffu, inter, o); uni += __shfl_xor_sync(0xffffffffu, uni, o); }
+  if ((threadIdx.x & 31) == 0) { s_i[threadIdx.x >> 5] = inter; s_u[threadIdx.x >> 5] = uni; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned a = 0, b = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s_i[w]; b += s_u[w]; }
+    atomicAdd(counts, (unsigned long long)a);
+    atomicAdd(counts + 1, (unsigned long long)b);
+  }
+}
+
 // Gradient = bucket + the sum of per-CTA partial gradient vectors (written by the whole-step critic kernel instead of
 // same-address REDs), reduced in a FIXED order (bit-reproducible), then either written back to the bucket (data-parallel:
 // the all-reduce comes next) or consumed by Adam in the same pass.  Block = 32 elements x 8 slices of the partial list:
@@ -312,6 +337,13 @@ __global__ void __launch_bounds__(256) partials_kernel(float* __restrict__ p, fl
 }  // namespace cgs
 
 using namespace cgs;
+
+extern "C" int cgs_iou_counts(const float* z, const uint8_t* gt, int64_t n, float thresh, int32_t strict, uint64_t* counts,
+                              void* stream) {
+  CGS_REQUIRE(z && gt && counts && n > 0, "iou_counts: bad args");
+  iou_counts_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(z, gt, n, thresh, strict, (unsigned long long*)counts);
+  return check_launch("iou_counts");
+}
 
 extern "C" int cgs_reduce_partials(float* g, int64_t n, const float* partials, int32_t n_partials, int64_t stride,
                                    int64_t offset, int64_t len, void* stream) {

@@ -608,6 +608,15 @@ def threshold(z, thresh, strict=False):
     return hard
 
 
+def iou_counts(z, gt_u8, thresh, counts, strict=True):
+    """counts (int64 [2] device tensor, caller-zeroed) += (#(hard & gt), #(hard | gt)), hard = z > thresh (reference
+    main.py:964) or >= when not strict; the reference's get_iou (main.py:1265-1270) is counts[0] / counts[1]."""
+    zc, gc = _c(z), _c(gt_u8)
+    assert zc.numel() == gc.numel()
+    _call("cgs_iou_counts", _p(zc), _p(gc, torch.uint8), zc.numel(), float(thresh), int(strict), _p(counts, torch.int64), _stream())
+    return counts
+
+
 def adam_step(p, g, m, v, step_state, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, clear_grad=False):
     """Flat-bucket Adam (torch.optim.Adam defaults, main.py:178).  step_state: int32 device tensor [2] = (steps applied,
     ticket); the kernel advances it.  clear_grad: zero g in the same pass (fused zero_grad)."""

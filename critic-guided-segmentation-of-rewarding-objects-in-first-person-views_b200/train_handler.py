@@ -473,6 +473,34 @@ class Handler:
         M = np.concatenate(M, axis=0)
         return np.concatenate(preds, axis=0), M, (np.concatenate(hard, axis=0) if hard else None)
 
+    def eval_iou(self, X_u8, GT, batchsize=128):
+        """The IoU of Handler.eval (reference main.py:891-1017 without CRF / saliency / plots): masks of all frames,
+        `hardM = M > eval_thresh` (main.py:964), `get_iou(hardM, Y)` (main.py:1005, 1265-1270).  GT: bool/uint8 [N,64,64]
+        ground-truth masks.  Compare + intersection/union counts run on the device; returns (iou rounded as the reference
+        does, intersection, union)."""
+        a = self.args
+        train = bool(a.noevalmode)
+        critic = self.critic.to(self.device).train(train)
+        masker = self.masker.to(self.device).train(train)
+        counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        GT = np.ascontiguousarray(np.asarray(GT).astype(np.uint8))
+        with torch.no_grad():
+            for bidx in range(0, len(X_u8), batchsize):
+                xu8 = torch.from_numpy(np.ascontiguousarray(X_u8[bidx:bidx + batchsize])).to(self.device)
+                gt = torch.from_numpy(GT[bidx:bidx + batchsize]).to(self.device)
+                if not a.separate and ops.infer_fused_supported(critic, masker):
+                    _, o0 = ops.infer_encode_decode(critic, masker, xu8)
+                    mask, _ = ops.masker_fused(masker, xu8, o0, None)
+                else:
+                    batch = ops.frames_to_float(xu8, 0).permute(0, 3, 1, 2)
+                    _, embeds = critic(batch, collect=True)
+                    if a.separate:
+                        _, embeds = self.sepcrit.to(self.device).train(train)(batch, collect=True)
+                    mask = masker(batch, embeds)
+                ops.iou_counts(mask, gt, a.eval_thresh, counts, strict=True)
+        inter, union = (int(v) for v in counts.cpu())
+        return (round(inter / union, 3) if union else float("nan")), inter, union
+
     def segment(self, folder):
         """`-process`: PNG folder in, mask PNGs out (main.py:1103-1223; raw + thresholded columns)."""
         from PIL import Image

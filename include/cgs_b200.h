@@ -282,6 +282,11 @@ int cgs_dropout_masks(float* out, int64_t n, float p, uint64_t seed, uint64_t* s
 /* hard[i] = z[i] >= thresh (main.py:1164) or z[i] > thresh when strict (main.py:964). */
 int cgs_threshold(const float* z, int64_t n, float thresh, int32_t strict, uint8_t* hard, void* stream);
 
+/* `-eval` (main.py:964, 1265-1270): counts[0] += #(hard & gt), counts[1] += #(hard | gt) with hard = z > thresh (strict,
+ * the -eval convention) or z >= thresh; gt = ground-truth mask bytes (non-zero = object).  counts: 2 x uint64 device words the
+ * caller zeroes; IoU = counts[0] / counts[1] over everything accumulated.  Exact integer arithmetic. */
+int cgs_iou_counts(const float* z, const uint8_t* gt, int64_t n, float thresh, int32_t strict, uint64_t* counts, void* stream);
+
 /* Non-zero if a tcgen05 kernel ever timed out on its completion barrier (reads a device flag; synchronises). */
 int cgs_tc_status(void);
 

@@ -344,3 +344,39 @@ def test_errors_are_loud(ops):
         ops.EncBlock.apply(x, None, w, b)
     with pytest.raises(CgsError):
         ops.EncBlock.apply(torch.zeros(1, 8, 8, 3), None, w.cpu(), b.cpu())   # CPU tensors: no fallback
+
+
+def test_iou_counts_exact():
+    """cgs_iou_counts == np.sum(A & B), np.sum(A | B) of the reference's get_iou (main.py:1265-1270), exactly, for both
+    threshold conventions, ragged sizes and accumulation over several calls."""
+    from cgs_b200 import ops
+    rng = np.random.default_rng(0)
+    counts = torch.zeros(2, dtype=torch.int64, device="cuda")
+    ti = tu = 0
+    for n, strict in ((1, True), (1000, True), (64 * 64 * 37 + 5, False), (4096 * 300, True)):
+        z = rng.random(n).astype(np.float32)
+        z[::7] = 0.05                                   # values exactly at the threshold: > and >= must differ
+        gt = (rng.random(n) < 0.3)
+        hard = z > np.float32(0.05) if strict else z >= np.float32(0.05)
+        ti += int((hard & gt).sum()); tu += int((hard | gt).sum())
+        ops.iou_counts(torch.from_numpy(z).cuda(), torch.from_numpy(gt.astype(np.uint8)).cuda(), 0.05, counts, strict=strict)
+    assert [int(v) for v in counts.cpu()] == [ti, tu]
+
+
+def test_handler_eval_iou_matches_reference_formula():
+    """Handler.eval_iou on the reference-trained checkpoint == get_iou(M > eval_thresh, GT) computed on the host from the
+    same masks; synthetic ground truth = the painted trunk rectangle."""
+    from cgs_b200.train_handler import Handler, parse_args
+    import cgs_b200.synth as synth
+    from helpers import load_golden
+    d = load_golden("loops_c1.npz")
+    H = Handler(parse_args(["--binarymaskthreshold", "0.1"]), device="cuda")
+    H.critic.load_state_dict({k[len("trained.c."):]: torch.from_numpy(d[k]) for k in d.files if k.startswith("trained.c.")})
+    H.masker.load_state_dict({k[len("trained.m."):]: torch.from_numpy(d[k]) for k in d.files if k.startswith("trained.m.")})
+    X, _, _ = synth.synthetic_frames(300, seed=3)
+    GT = (X[..., 0].astype(np.int32) >= 200)           # trunk pixels are painted (200..229, 140.., 60..), background < 120
+    iou, inter, union = H.eval_iou(X, GT, batchsize=128)
+    _, M, _ = H.segment_arrays(X)
+    hard = M[:, 0] > np.float32(H.args.eval_thresh)
+    assert (inter, union) == (int((hard & GT).sum()), int((hard | GT).sum()))
+    assert iou == round(inter / union, 3) and 0.0 <= iou <= 1.0

@@ -50,19 +50,20 @@ class GraphedCriticStep(_Graphed):
     """One critic_pipe iteration (reference main.py:185-200) as a CUDA graph.  The shift_batch roll is a
     device int32 (`self.roll`), so it can change per replay: `step.roll.fill_(r)` before the call."""
 
-    def __init__(self, handler, batch, opti=None):
+    def __init__(self, handler, batch, opti=None, X=None, Y=None, warmup=3):
         H = self.H = handler
         dev = H.device
         H.critic.to(dev).train()
         self.opti = opti or FlatAdam(H.critic.parameters(), process_group=H.group, world_size=H.world)
-        self.X = torch.zeros((batch, 64, 64, 3), dtype=torch.uint8, device=dev)
-        self.Y = torch.zeros((batch,), dtype=torch.float32, device=dev)
+        # static inputs: own buffers, or caller-provided device tensors (e.g. one slice of a resident dataset per graph)
+        self.X = X if X is not None else torch.zeros((batch, 64, 64, 3), dtype=torch.uint8, device=dev)
+        self.Y = Y if Y is not None else torch.zeros((batch,), dtype=torch.float32, device=dev)
         self.roll = torch.zeros(1, dtype=torch.int32, device=dev)
         self.static_in = (self.X, self.Y)
 
         def fn():
             return H.critic_step(self.X, self.Y, self.opti, roll=self.roll)
-        self.graph, self.out, self.launches = _capture(fn)
+        self.graph, self.out, self.launches = _capture(fn, warmup=warmup)
 
 
 class GraphedHourglassStep(_Graphed):

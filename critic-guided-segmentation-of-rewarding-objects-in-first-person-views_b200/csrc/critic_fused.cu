@@ -1014,6 +1014,20 @@ extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target
     attr = true;
   }
   if (!adam && cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) return check_launch("critic_train_fused.memset");
-  cf::critic_fused_train_kernel<<<cgs_critic_fused_grid(B), cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
+  const int grid = cgs_critic_fused_grid(B);
+  if (adam) {
+    // the in-kernel grid barrier needs every CTA resident at once: a cooperative launch makes the driver guarantee it
+    // (or fail the launch) instead of relying on "one CTA per SM and grid <= SMs"
+    void* args[] = {(void*)&p};
+    const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)cf::critic_fused_train_kernel, dim3(grid), dim3(cf::NT), args,
+                                                       (size_t)cf::SMEM_FLOATS * 4, st);
+    if (ce != cudaSuccess) {
+      cudaGetLastError();
+      set_error("critic_train_fused: cooperative launch of %d CTAs failed: %s", grid, cudaGetErrorString(ce));
+      return CGS_ECUDA;
+    }
+  } else {
+    cf::critic_fused_train_kernel<<<grid, cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
+  }
   return check_launch("critic_train_fused");
 }

@@ -214,5 +214,7 @@ class PipelinedCriticTrainer:
 
     def losses(self):
         torch.cuda.synchronize()
+        if not (self.opti.barrier_ok() and self.opti.p2p_ok()):
+            raise RuntimeError("cgs_b200: a CTA of the whole-step kernel timed out at its grid barrier / waiting for a peer")
         n = min(self.i, self.loss_ring.numel())
         return self.loss_ring[:n].clone()

@@ -338,6 +338,9 @@ class Handler:
             if not (epoch + 1) % a.saveevery:
                 self.save_models([self.criticname])
         self.closs_log = [float(v) for v in torch.stack(self.closs_log).cpu()] if self.closs_log else []
+        if not (opti.barrier_ok() and opti.p2p_ok()):
+            raise RuntimeError("cgs_b200: a CTA of the whole-step kernel timed out at its grid barrier / waiting for a peer's "
+                               "gradient during critic_pipe: the optimizer state is not trustworthy")
 
     # ------------------------------------------------------------------ pos / neg split
     def extract_contrastive_data(self):

@@ -312,7 +312,7 @@ class Handler:
             opti.zero_grad()
             loss, _ = ops.critic_train_fused(self.critic, x.contiguous(), Yd.contiguous(), roll, masks,
                                              loss_grad=1.0 / self.world, bce=bool(a.threshrew), rng=rng,
-                                             fuse_adam=opti._clean)
+                                             fuse_adam=bool(getattr(opti, "_clean", False)))
             opti.step()
             return loss
         pred = self.critic.forward_frames(x, roll).squeeze(1)     # cast + roll fused into features.0's operand load

@@ -18,6 +18,7 @@
 //   * the 4x4 bottleneck conv and the MLP head are FFMA on the tiny vectors.
 // tcgen05 is not used here on purpose: every GEMM has N = 8..16 and M-tiles of 16 pixels; a 128-row UMMA tile would
 // be >85 % padding and its operands would have to be re-laid out in the canonical layout per tap.
+#include <string.h>
 #include "fused_common.cuh"
 
 namespace cgs {
@@ -67,6 +68,9 @@ static_assert(SMEM_FLOATS * 4 <= 227 * 1024, "shared memory budget");
 
 struct Params {
   const uint8_t* frames;
+  // input-gradient mode (template XG): fp32 NHWC frames in, d loss / d frame out, frozen parameters (no weight gradients)
+  const float* xin;
+  float* dx;
   const float* target;
   const float *m2, *m3, *mv;
   const float *w0, *b0, *w1, *b1, *w2, *b2, *w3, *b3, *w4, *b4, *wl1, *bl1, *wl2, *bl2;
@@ -207,10 +211,12 @@ __device__ __forceinline__ void draw_masks(const Params& p, int n, unsigned long
 
 // cp.async: the raw frame (12288 B) and its dropout masks (512 + 256 + 32 floats) for frame n
 __device__ __forceinline__ void prefetch_frame(const Params& p, int n, float* sm, int tid) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(sm + oU8);
-  const uint8_t* src = p.frames + (size_t)n * 12288;
-  for (int c = tid; c < 768; c += NT)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + c * 16), "l"(src + c * 16));
+  if (p.frames) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(sm + oU8);
+    const uint8_t* src = p.frames + (size_t)n * 12288;
+    for (int c = tid; c < 768; c += NT)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + c * 16), "l"(src + c * 16));
+  }
   if (p.m2) {
     const uint32_t dm = (uint32_t)__cvta_generic_to_shared(sm);
     if (tid < 128) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dm + (oM2 + tid * 4) * 4), "l"(p.m2 + (size_t)n * 512 + tid * 4));
@@ -220,7 +226,30 @@ __device__ __forceinline__ void prefetch_frame(const Params& p, int n, float* sm
   asm volatile("cp.async.commit_group;\n" ::);
 }
 
-__global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params p) {
+// fp32 NHWC frame [64][64][3] in global memory -> haloed [66][66] x (r,g,b,0), TF32-rounded (input-gradient mode)
+__device__ __forceinline__ void stage_frame_f32(const float* __restrict__ src, float* __restrict__ sXd, int tid) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int p = tid + NT * i, y = p >> 6, x = p & 63;
+    const float* s = src + p * 3;
+    *reinterpret_cast<float4*>(sXd + ((y + 1) * P0 + x + 1) * 4) = make_float4(tf32r(__ldg(s)), tf32r(__ldg(s + 1)), tf32r(__ldg(s + 2)), 0.f);
+  }
+  if (tid < 260) {
+    int y, x;
+    if (tid < 66) { y = 0; x = tid; }
+    else if (tid < 132) { y = 65; x = tid - 66; }
+    else if (tid < 196) { y = tid - 131; x = 0; }
+    else { y = tid - 195; x = 65; }
+    *reinterpret_cast<float4*>(sXd + (y * P0 + x) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// XG = false: one critic_pipe training step (weight gradients, optimizer).  XG = true: the same forward and loss with FROZEN
+// parameters and the gradient w.r.t. the input frame instead (critic(replaced) / critic(injected) of the Hourglass loop,
+// main.py:396-411, and the saliency baseline, main.py:949-951): all weight-gradient work is compiled out and the backward ends
+// with features.0's input gradient, computed in two 32-row bands from the arg-max-tagged pooled gradient.
+template <bool XG>
+__global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
   extern __shared__ __align__(128) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int lj = lane >> 3, lr = lane & 7;               // ldmatrix: this lane addresses row lr of matrix lj
@@ -253,7 +282,16 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
   }
 
   // ---- prologue: accumulators, halos that stay zero, weight fragments (TF32, in mma B-fragment order), biases
-  for (int e = tid; e < szAcc; e += NT) sAcc[e] = 0.f;
+  if (!XG) {
+    for (int e = tid; e < szAcc; e += NT) sAcc[e] = 0.f;
+  } else {
+    // the accumulator region is free in this mode: it holds features.0's dgrad fragments, B[k = co][n = ci] = W0[co][ci][8 - tap']
+    for (int e = tid; e < 9 * 32; e += NT) {
+      const int ln = e & 31, gg = ln >> 2, tt = ln & 3, tap = 8 - (e >> 5);
+      sAcc[2 * e] = gg < 3 ? tf32r(__ldg(p.w0 + tt * 27 + gg * 9 + tap)) : 0.f;
+      sAcc[2 * e + 1] = gg < 3 ? tf32r(__ldg(p.w0 + (tt + 4) * 27 + gg * 9 + tap)) : 0.f;
+    }
+  }
   for (int e = tid; e < 2 * PL2 + 512 + 2 * PL3; e += NT) sm[oE1 + e] = 0.f;        // e1, idx1, e2 (halos stay zero)
   {
     // 2496 fragment entries, 5 per thread: first all source addresses, then all loads in flight together (a cold launch
@@ -357,7 +395,8 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     const float ytgt = __ldg(p.target + n);
     asm volatile("cp.async.wait_all;\n" ::);
     __syncthreads();
-    stage_frame(reinterpret_cast<const uint8_t*>(sm + oU8), sm + oX, roll, tid);
+    if (XG) stage_frame_f32(p.xin + (size_t)n * 12288, sm + oX, tid);
+    else stage_frame(reinterpret_cast<const uint8_t*>(sm + oU8), sm + oX, roll, tid);
     if (tid < 264) {   // e0 halo ring (region A is reused by the re-staged frame), both half-planes
       const int h = tid >= 132, q = tid - 132 * h;
       int y, x;
@@ -540,20 +579,25 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
         loss_acc = fmaf(pr - y, pr - y, loss_acc);
         dl = p.gscale * 2.f * (pr - y) * pr * (1.f - pr);
       }
-      if (lane == 0) { p.pred[n] = pr; sAcc[aBl2] += dl; }
-      sAcc[aWl2 + lane] += dl * vm;
+      if (lane == 0) p.pred[n] = pr;
+      if (!XG) {
+        if (lane == 0) sAcc[aBl2] += dl;
+        sAcc[aWl2 + lane] += dl * vm;
+      }
       sDV[lane] = sV[lane] > 0.f ? dl * wk * sMV[lane] : 0.f;
     }
     __syncthreads();
     CF_MARK(8);
     // ================= B5: crit.1 backward
     {
+      if (!XG) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int e = tid + NT * i;
-        sAcc[aWl1 + e] = fmaf(sDV[e >> 5], sH[e & 31], sAcc[aWl1 + e]);
+        for (int i = 0; i < 2; ++i) {
+          const int e = tid + NT * i;
+          sAcc[aWl1 + e] = fmaf(sDV[e >> 5], sH[e & 31], sAcc[aWl1 + e]);
+        }
+        if (tid < 32) sAcc[aBl1 + tid] += sDV[tid];
       }
-      if (tid < 32) sAcc[aBl1 + tid] += sDV[tid];
       const int k = tid >> 4, part = tid & 15;
       float s = sm[oHW + hWl1 + (2 * part) * 32 + k] * sDV[2 * part] + sm[oHW + hWl1 + (2 * part + 1) * 32 + k] * sDV[2 * part + 1];
 #pragma unroll
@@ -566,13 +610,14 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     {
       const int nn = tid >> 4, part = tid & 15;
       const float d = sDH[nn];
+      if (!XG)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {                                         // accW4[4i..] <-> chunk (i + rot4) & 3, as in F4
         const float4 x = *reinterpret_cast<const float4*>(sm + oX3 + part * 16 + ((i + rot4) & 3) * 4);
         accW4[4 * i + 0] = fmaf(d, x.x, accW4[4 * i + 0]); accW4[4 * i + 1] = fmaf(d, x.y, accW4[4 * i + 1]);
         accW4[4 * i + 2] = fmaf(d, x.z, accW4[4 * i + 2]); accW4[4 * i + 3] = fmaf(d, x.w, accW4[4 * i + 3]);
       }
-      if (tid < 32) sAcc[aB4 + tid] += sDH[tid];
+      if (!XG && tid < 32) sAcc[aB4 + tid] += sDH[tid];
       const int k = tid >> 1, hf = tid & 1;
       float s = 0.f;
 #pragma unroll
@@ -589,7 +634,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     __syncthreads();
     CF_MARK(10);
     // ================= B3: features.10 weight gradient (warps 0-9) || input gradient -> dY2 (warps 10-13)
-    if (warp < 10) {
+    if (!XG && warp < 10) {
       const int mt = warp % 5, nt = warp / 5;
       const int ta = 2 * mt, tb = mt < 4 ? 2 * mt + 1 : 8;
       const int offA = (g >> 2) * PL3 + ((ta / 3) * P3 + ta % 3) * 4 + (g & 3);
@@ -613,7 +658,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
         if (tap < 9) sAcc[aW3 + (co * 8 + g) * 9 + tap] += acc[q];
         else if (g == 0) sAcc[aB3 + co] += acc[q];
       }
-    } else if (warp < 14) {
+    } else if (warp >= 10 && warp < 14) {
       const int mt = warp - 10;
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       const uint32_t aA = smb + (oDY3 + (lj >> 1) * PL3 + ((2 * mt + (lj & 1)) * P3 + lr) * 4) * 4;
@@ -638,7 +683,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     CF_MARK(11);
     // ================= B2: features.6 input gradient -> dY1 (warps 0-7) || weight gradient (warps 8-15, registers)
     if (warp >= 8) {
-      wgrad8<16, P2, PL2>(accW, sm + oE1, sm + oDY2, (warp - 8) * 4, 4, g, t);
+      if (!XG) wgrad8<16, P2, PL2>(accW, sm + oE1, sm + oDY2, (warp - 8) * 4, 4, g, t);
     } else {
       const int r0 = warp * 2;
       float2 w[3][3];
@@ -667,7 +712,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     CF_MARK(12);
     // ================= B1: features.3 weight gradient (warps 0-7, registers) || input gradient -> dE0 + arg-max tags (8-15)
     if (warp < 8) {
-      wgrad8<32, P1, PL1>(accW, sm + oE0, sm + oDY1, warp * 16, 16, g, t);
+      if (!XG) wgrad8<32, P1, PL1>(accW, sm + oE0, sm + oDY1, warp * 16, 16, g, t);
     } else {
       const int x0 = (warp & 1) * 16, r0 = ((warp - 8) >> 1) * 8;
       float2 w[3][3];
@@ -703,37 +748,92 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     }
     __syncthreads();
     CF_MARK(13);
-    // ================= B0a: frame again (region A is free now), then start fetching the next frame
-    stage_frame(reinterpret_cast<const uint8_t*>(sm + oU8), sm + oXB, roll, tid);
-    __syncthreads();
-    if (n + (int)gridDim.x < p.B) {
-      prefetch_frame(p, n + gridDim.x, sm, tid);
-      if (p.rng_state) draw_masks(p, n + gridDim.x, rng_call, sm, tid);
-    }
-    CF_MARK(14);
-    // ================= B0: features.0 weight gradient, K = 4096 pixels over 16 warps (4 rows each), registers
-    {
+    if (XG) {
+      // ================= features.0 input gradient: dX[y,x,ci] = sum_{tap',co} dY0[y + ky' - 1, x + kx' - 1, co] * W0[co][ci][8 - tap'].
+      // dY0 (64x64x8, one non-zero per pooled window and channel) is expanded from the tagged pooled gradient into haloed
+      // half-planes, 34 rows at a time (region A; e0 and dY1 are dead), and convolved like any other layer: 2 bands x 32 rows
+      if (n + (int)gridDim.x < p.B) {
+        prefetch_frame(p, n + gridDim.x, sm, tid);
+        if (p.rng_state) draw_masks(p, n + gridDim.x, rng_call, sm, tid);
+      }
+      constexpr int PLD = 34 * P0 * 4;
       const uint32_t* sDE0 = reinterpret_cast<const uint32_t*>(sm + oDE0);
-      const float* sXb = sm + oXB;
+      const float2* wd = reinterpret_cast<const float2*>(sm + oAcc);
+      float2 w[3][3];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) w[q / 3][q % 3] = wd[q * 32 + lane];
+      for (int band = 0; band < 2; ++band) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = tid; e < 2 * PLD / 4; e += NT) reinterpret_cast<float4*>(sm + oA)[e] = z4;
+        __syncthreads();
+        for (int e = tid; e < 18 * 256; e += NT) {          // pooled rows 16*band-1 .. 16*band+16 touch band rows 0..33
+          const int py = 16 * band - 1 + (e >> 8), px = (e >> 3) & 31, co = e & 7;
+          if (py < 0 || py > 31) continue;
+          const uint32_t bits = sDE0[(py * 32 + px) * 8 + co];
+          if (bits == 0u) continue;
+          const int rb = 2 * py + (int)((bits >> 1) & 1u) - (32 * band - 1), x = 2 * px + (int)(bits & 1u);
+          if (rb < 0 || rb > 33) continue;
+          sm[oA + (co >> 2) * PLD + (rb * P0 + x + 1) * 4 + (co & 3)] = __uint_as_float(bits);
+        }
+        __syncthreads();
+        {
+          const int x0 = (warp & 3) * 16, r0 = (warp >> 2) * 8;
+          const uint32_t aA = smb + (oA + (lj >> 1) * PLD + (r0 * P0 + x0) * 4 + ldoff8) * 4;
+          float* dO = p.dx + ((size_t)n * 4096 + (32 * band + r0) * 64 + x0 + g) * 3;
+          slide_rows<8, 3>(
+              w,
+              [&](int i, uint32_t(&a)[3][4]) {
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) ldsm4(a[kx], aA + (i * P0 + kx) * 16);
+              },
+              [&](int e, const float(&top)[4], const float(&bot)[4]) {
+                if (t < 2) {                                 // columns 0..2 of the 8-wide tile are the three input channels
+#pragma unroll
+                  for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                      float* d = dO + ((e + r) * 64 + 8 * h) * 3 + 2 * t;
+                      d[0] = r ? bot[2 * h] : top[2 * h];
+                      if (t == 0) d[1] = r ? bot[2 * h + 1] : top[2 * h + 1];
+                    }
+                }
+              });
+        }
+        __syncthreads();
+      }
+    } else {
+      // ================= B0a: frame again (region A is free now), then start fetching the next frame
+      stage_frame(reinterpret_cast<const uint8_t*>(sm + oU8), sm + oXB, roll, tid);
+      __syncthreads();
+      if (n + (int)gridDim.x < p.B) {
+        prefetch_frame(p, n + gridDim.x, sm, tid);
+        if (p.rng_state) draw_masks(p, n + gridDim.x, rng_call, sm, tid);
+      }
+      CF_MARK(14);
+      // ================= B0: features.0 weight gradient, K = 4096 pixels over 16 warps (4 rows each), registers
+      {
+        const uint32_t* sDE0 = reinterpret_cast<const uint32_t*>(sm + oDE0);
+        const float* sXb = sm + oXB;
 #pragma unroll 1
-      for (int yy = 0; yy < 4; ++yy) {
-        const int y = warp * 4 + yy;
-        const float* xa = sXb + (y * P0 + t) * 4;
-        const uint32_t* de = sDE0 + ((y >> 1) * 32 + (t >> 1)) * 8 + g;
-        const uint32_t pos = ((y & 1) << 1) | (t & 1);
+        for (int yy = 0; yy < 4; ++yy) {
+          const int y = warp * 4 + yy;
+          const float* xa = sXb + (y * P0 + t) * 4;
+          const uint32_t* de = sDE0 + ((y >> 1) * 32 + (t >> 1)) * 8 + g;
+          const uint32_t pos = ((y & 1) << 1) | (t & 1);
 #pragma unroll
-        for (int xs = 0; xs < 8; ++xs) {
-          uint32_t b0 = de[xs * 32], b1 = de[xs * 32 + 16];
-          b0 = (b0 & 3u) == pos ? b0 : 0u;
-          b1 = (b1 & 3u) == pos ? b1 : 0u;
+          for (int xs = 0; xs < 8; ++xs) {
+            uint32_t b0 = de[xs * 32], b1 = de[xs * 32 + 16];
+            b0 = (b0 & 3u) == pos ? b0 : 0u;
+            b1 = (b1 & 3u) == pos ? b1 : 0u;
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            uint32_t a[4];
-            a[0] = __float_as_uint(xa[offA0[mt][0] + xs * 32]);
-            a[1] = __float_as_uint(xa[offA0[mt][1] + xs * 32]);
-            a[2] = __float_as_uint(xa[offA0[mt][0] + xs * 32 + 16]);
-            a[3] = __float_as_uint(xa[offA0[mt][1] + xs * 32 + 16]);
-            mma_tf32(acc0[mt], a, b0, b1);
+            for (int mt = 0; mt < 2; ++mt) {
+              uint32_t a[4];
+              a[0] = __float_as_uint(xa[offA0[mt][0] + xs * 32]);
+              a[1] = __float_as_uint(xa[offA0[mt][1] + xs * 32]);
+              a[2] = __float_as_uint(xa[offA0[mt][0] + xs * 32 + 16]);
+              a[3] = __float_as_uint(xa[offA0[mt][1] + xs * 32 + 16]);
+              mma_tf32(acc0[mt], a, b0, b1);
+            }
           }
         }
       }
@@ -748,71 +848,73 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
   //      then write this CTA's gradient: one coalesced partial vector (summed by the Adam kernel), or REDs
   asm volatile("cp.async.wait_all;\n" ::);
   __syncthreads();
-  {
-    float* scr = sm + oA;                           // [16 warps][584] conv tiles, then [16 warps][216] for features.0
-    wgrad8_store(accW, scr + warp * 584, g, t);
-    float* scr0 = sm + oA + 16 * 584 + warp * 216;
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int G = 2 * mt + (q >> 1), co = 2 * t + (q & 1);
-        int ky, kx, ci;
-        if (G < 3) {
-          const int c = g < 6 + G ? g : g + 1;
-          ky = G; kx = c / 3; ci = c - kx * 3;
-        } else {
-          ky = g; kx = 2; ci = g;
+  if (!XG) {
+    {
+      float* scr = sm + oA;                           // [16 warps][584] conv tiles, then [16 warps][216] for features.0
+      wgrad8_store(accW, scr + warp * 584, g, t);
+      float* scr0 = sm + oA + 16 * 584 + warp * 216;
+  #pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+  #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int G = 2 * mt + (q >> 1), co = 2 * t + (q & 1);
+          int ky, kx, ci;
+          if (G < 3) {
+            const int c = g < 6 + G ? g : g + 1;
+            ky = G; kx = c / 3; ci = c - kx * 3;
+          } else {
+            ky = g; kx = 2; ci = g;
+          }
+          if (G < 3 || g < 3) scr0[co * 27 + ci * 9 + ky * 3 + kx] = acc0[mt][q];
         }
-        if (G < 3 || g < 3) scr0[co * 27 + ci * 9 + ky * 3 + kx] = acc0[mt][q];
+      // features.0 bias: lanes with equal t hold the same channels; fold the 8 g's, one value per warp and channel
+      bsum[0] += __shfl_xor_sync(0xffffffffu, bsum[0], 4); bsum[1] += __shfl_xor_sync(0xffffffffu, bsum[1], 4);
+      bsum[0] += __shfl_xor_sync(0xffffffffu, bsum[0], 8); bsum[1] += __shfl_xor_sync(0xffffffffu, bsum[1], 8);
+      bsum[0] += __shfl_xor_sync(0xffffffffu, bsum[0], 16); bsum[1] += __shfl_xor_sync(0xffffffffu, bsum[1], 16);
+      if (g == 0) { sm[oA + 16 * 800 + warp * 8 + 2 * t] = bsum[0]; sm[oA + 16 * 800 + warp * 8 + 2 * t + 1] = bsum[1]; }
+    }
+    __syncthreads();
+    for (int e = tid; e < 584; e += NT) {
+      float s1 = 0.f, s2 = 0.f;
+  #pragma unroll
+      for (int w = 0; w < 8; ++w) { s1 += sm[oA + w * 584 + e]; s2 += sm[oA + (w + 8) * 584 + e]; }
+      sAcc[aW1 + e] = s1;                             // aB1 == aW1 + 576, aB2 == aW2 + 576
+      sAcc[aW2 + e] = s2;
+    }
+    for (int e = tid; e < 224; e += NT) {            // features.0 weight (216) + bias (8: aB0 == aW0 + 216), fixed order
+      float s0 = 0.f;
+      if (e < 216) {
+  #pragma unroll
+        for (int w = 0; w < 16; ++w) s0 += sm[oA + 16 * 584 + w * 216 + e];
+      } else {
+  #pragma unroll
+        for (int w = 8; w < 16; ++w) s0 += sm[oA + 16 * 800 + w * 8 + e - 216];
       }
-    // features.0 bias: lanes with equal t hold the same channels; fold the 8 g's, one value per warp and channel
-    bsum[0] += __shfl_xor_sync(0xffffffffu, bsum[0], 4); bsum[1] += __shfl_xor_sync(0xffffffffu, bsum[1], 4);
-    bsum[0] += __shfl_xor_sync(0xffffffffu, bsum[0], 8); bsum[1] += __shfl_xor_sync(0xffffffffu, bsum[1], 8);
-    bsum[0] += __shfl_xor_sync(0xffffffffu, bsum[0], 16); bsum[1] += __shfl_xor_sync(0xffffffffu, bsum[1], 16);
-    if (g == 0) { sm[oA + 16 * 800 + warp * 8 + 2 * t] = bsum[0]; sm[oA + 16 * 800 + warp * 8 + 2 * t + 1] = bsum[1]; }
-  }
-  __syncthreads();
-  for (int e = tid; e < 584; e += NT) {
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) { s1 += sm[oA + w * 584 + e]; s2 += sm[oA + (w + 8) * 584 + e]; }
-    sAcc[aW1 + e] = s1;                             // aB1 == aW1 + 576, aB2 == aW2 + 576
-    sAcc[aW2 + e] = s2;
-  }
-  for (int e = tid; e < 224; e += NT) {            // features.0 weight (216) + bias (8: aB0 == aW0 + 216), fixed order
-    float s0 = 0.f;
-    if (e < 216) {
-#pragma unroll
-      for (int w = 0; w < 16; ++w) s0 += sm[oA + 16 * 584 + w * 216 + e];
+      sAcc[aW0 + e] = s0;
+    }
+    __syncthreads();
+    CF_MARK(17);
+    if (p.partials) {
+      // flat (state_dict) order: sAcc[0, 2560) -> [0, 2560); features.14.weight -> [2560, 10752); sAcc[2560, 3681) -> +8192
+      float* d = p.partials + (size_t)blockIdx.x * PSTRIDE;
+      for (int e = tid; e < 3681; e += NT) d[e < 2560 ? e : e + 8192] = sAcc[e];
+      float4* d4 = reinterpret_cast<float4*>(d + 2560 + (tid >> 4) * 256 + (tid & 15) * 16);
+      const int rot4 = (tid >> 1) & 3;
+  #pragma unroll
+      for (int i = 0; i < 4; ++i) d4[(i + rot4) & 3] = make_float4(accW4[4 * i], accW4[4 * i + 1], accW4[4 * i + 2], accW4[4 * i + 3]);
     } else {
-#pragma unroll
-      for (int w = 8; w < 16; ++w) s0 += sm[oA + 16 * 800 + w * 8 + e - 216];
+      constexpr int segoff[13] = {aW0, aB0, aW1, aB1, aW2, aB2, aW3, aB3, aB4, aWl1, aBl1, aWl2, aBl2};
+      constexpr int seglen[13] = {216, 8, 576, 8, 576, 8, 1152, 16, 32, 1024, 32, 32, 1};
+  #pragma unroll
+      for (int s = 0; s < 13; ++s) {
+        float* d = p.gseg[s];
+        for (int e = tid; e < seglen[s]; e += NT) atomicAdd(d + e, sAcc[segoff[s] + e]);
+      }
+      float* d4 = p.gseg[13] + (tid >> 4) * 256 + (tid & 15) * 16;
+      const int rot4 = (tid >> 1) & 3;
+  #pragma unroll
+      for (int i = 0; i < 16; ++i) atomicAdd(d4 + (((i >> 2) + rot4) & 3) * 4 + (i & 3), accW4[i]);
     }
-    sAcc[aW0 + e] = s0;
-  }
-  __syncthreads();
-  CF_MARK(17);
-  if (p.partials) {
-    // flat (state_dict) order: sAcc[0, 2560) -> [0, 2560); features.14.weight -> [2560, 10752); sAcc[2560, 3681) -> +8192
-    float* d = p.partials + (size_t)blockIdx.x * PSTRIDE;
-    for (int e = tid; e < 3681; e += NT) d[e < 2560 ? e : e + 8192] = sAcc[e];
-    float4* d4 = reinterpret_cast<float4*>(d + 2560 + (tid >> 4) * 256 + (tid & 15) * 16);
-    const int rot4 = (tid >> 1) & 3;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) d4[(i + rot4) & 3] = make_float4(accW4[4 * i], accW4[4 * i + 1], accW4[4 * i + 2], accW4[4 * i + 3]);
-  } else {
-    constexpr int segoff[13] = {aW0, aB0, aW1, aB1, aW2, aB2, aW3, aB3, aB4, aWl1, aBl1, aWl2, aBl2};
-    constexpr int seglen[13] = {216, 8, 576, 8, 576, 8, 1152, 16, 32, 1024, 32, 32, 1};
-#pragma unroll
-    for (int s = 0; s < 13; ++s) {
-      float* d = p.gseg[s];
-      for (int e = tid; e < seglen[s]; e += NT) atomicAdd(d + e, sAcc[segoff[s] + e]);
-    }
-    float* d4 = p.gseg[13] + (tid >> 4) * 256 + (tid & 15) * 16;
-    const int rot4 = (tid >> 1) & 3;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) atomicAdd(d4 + (((i >> 2) + rot4) & 3) * 4 + (i & 3), accW4[i]);
   }
   if (tid == 0) {
     // loss: one atomic per CTA into the scalar the host zeroed - or, with the grid barrier below, a slot of this CTA's
@@ -820,7 +922,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_train_kernel(const Params 
     if (p.adam_p) p.partials[(size_t)blockIdx.x * PSTRIDE + NGRAD] = loss_acc * p.inv_n;
     else atomicAdd(p.loss, loss_acc * p.inv_n);
   }
-  if (p.adam_p) {
+  if (!XG && p.adam_p) {
     // ---- grid barrier (all CTAs are co-resident: one per SM, grid <= SMs), then every CTA sums its slice of the
     //      parameter vector over all partial vectors (fixed order) and applies Adam: no second launch, no atomics
     __threadfence();
@@ -971,7 +1073,7 @@ extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target
               "critic_train_fused: masks and partials must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   cf::Params p;
-  p.frames = frames; p.target = target; p.m2 = m_e2; p.m3 = m_e3; p.mv = m_v;
+  p.frames = frames; p.xin = nullptr; p.dx = nullptr; p.target = target; p.m2 = m_e2; p.m3 = m_e3; p.mv = m_v;
   p.w0 = w->w0; p.b0 = w->b0; p.w1 = w->w1; p.b1 = w->b1; p.w2 = w->w2; p.b2 = w->b2; p.w3 = w->w3; p.b3 = w->b3;
   p.w4 = w->w4; p.b4 = w->b4; p.wl1 = w->wl1; p.bl1 = w->bl1; p.wl2 = w->wl2; p.bl2 = w->bl2;
   for (int i = 0; i < 14; ++i) p.gseg[i] = nullptr;
@@ -1010,7 +1112,8 @@ extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target
   p.gscale = loss_grad / (float)B;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(cf::critic_fused_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
+    cudaFuncSetAttribute(cf::critic_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
+    cudaFuncSetAttribute(cf::critic_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
     attr = true;
   }
   if (!adam && cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) return check_launch("critic_train_fused.memset");
@@ -1019,7 +1122,7 @@ extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target
     // the in-kernel grid barrier needs every CTA resident at once: a cooperative launch makes the driver guarantee it
     // (or fail the launch) instead of relying on "one CTA per SM and grid <= SMs"
     void* args[] = {(void*)&p};
-    const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)cf::critic_fused_train_kernel, dim3(grid), dim3(cf::NT), args,
+    const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)cf::critic_fused_kernel<false>, dim3(grid), dim3(cf::NT), args,
                                                        (size_t)cf::SMEM_FLOATS * 4, st);
     if (ce != cudaSuccess) {
       cudaGetLastError();
@@ -1027,7 +1130,39 @@ extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target
       return CGS_ECUDA;
     }
   } else {
-    cf::critic_fused_train_kernel<<<grid, cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
+    cf::critic_fused_kernel<false><<<grid, cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
   }
   return check_launch("critic_train_fused");
+}
+
+extern "C" int cgs_critic_loss_xgrad(const float* x, const float* target, int32_t B, const float* m_e2, const float* m_e3,
+                                     const float* m_v, float p_drop, uint64_t seed, uint64_t* rng_state,
+                                     const cgs_critic_weights* w, float loss_grad, int32_t bce, float* pred, float* loss, float* dx,
+                                     void* stream) {
+  CGS_REQUIRE(x && target && w && pred && loss && dx && B > 0, "critic_loss_xgrad: bad args");
+  CGS_REQUIRE((m_e2 != nullptr) == (m_e3 != nullptr) && (m_e2 != nullptr) == (m_v != nullptr),
+              "critic_loss_xgrad: dropout masks are all-or-none");
+  CGS_REQUIRE((((uintptr_t)m_e2 | (uintptr_t)m_e3 | (uintptr_t)m_v) & 15) == 0, "critic_loss_xgrad: masks must be 16-byte aligned");
+  CGS_REQUIRE(!(rng_state && m_e2), "critic_loss_xgrad: pass dropout masks OR an rng state, not both");
+  CGS_REQUIRE(!rng_state || (p_drop > 0.f && p_drop < 1.f), "critic_loss_xgrad: rng dropout needs 0 < p < 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  cf::Params p;
+  memset(&p, 0, sizeof(p));
+  p.xin = x; p.dx = dx; p.target = target; p.m2 = m_e2; p.m3 = m_e3; p.mv = m_v;
+  p.w0 = w->w0; p.b0 = w->b0; p.w1 = w->w1; p.b1 = w->b1; p.w2 = w->w2; p.b2 = w->b2; p.w3 = w->w3; p.b3 = w->b3;
+  p.w4 = w->w4; p.b4 = w->b4; p.wl1 = w->wl1; p.bl1 = w->bl1; p.wl2 = w->wl2; p.bl2 = w->bl2;
+  p.seed = seed; p.rng_state = (unsigned long long*)rng_state; p.p_drop = p_drop;
+  p.keep = rng_state ? 1.f / (1.f - p_drop) : 1.f;
+  p.world = 1;
+  p.pred = pred; p.loss = loss; p.B = B; p.bce = bce;
+  p.inv_n = 1.f / (float)B;
+  p.gscale = loss_grad / (float)B;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(cf::critic_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
+    attr = true;
+  }
+  if (cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) return check_launch("critic_loss_xgrad.memset");
+  cf::critic_fused_kernel<true><<<cgs_critic_fused_grid(B), cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
+  return check_launch("critic_loss_xgrad");
 }

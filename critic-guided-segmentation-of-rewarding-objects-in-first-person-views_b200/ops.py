@@ -544,6 +544,37 @@ def critic_train_fused(critic, frames_u8, target, roll=0, masks=(None, None, Non
     return loss.reshape(()), pred
 
 
+class CriticLossXGrad(torch.autograd.Function):
+    """loss = F.mse_loss(critic(x), target) (or BCE) for a FROZEN critic, with d loss / d x computed in the same kernel
+    (cgs_critic_loss_xgrad): forward returns the loss scalar, backward is one multiply."""
+
+    @staticmethod
+    def forward(ctx, x, target, critic, masks, rng, bce):
+        B = x.shape[0]
+        w = _lib.CriticWeights(*[_p(q.detach()) for q in critic.parameters()])
+        pred = torch.empty(B, device=x.device, dtype=torch.float32)
+        loss = torch.empty(1, device=x.device, dtype=torch.float32)
+        dx = torch.empty_like(x)
+        m2, m3, mv = masks
+        rp, rseed, rstate = (float(rng[0]), int(rng[1]) & 0xFFFFFFFFFFFFFFFF, _p(rng[2], torch.int64)) if rng is not None else (0.0, 0, None)
+        _call("cgs_critic_loss_xgrad", _p(x), _p(target), B, _p(m2), _p(m3), _p(mv), rp, rseed, rstate, C.byref(w), 1.0,
+              int(bool(bce)), _p(pred), _p(loss), _p(dx), _stream())
+        ctx.save_for_backward(dx)
+        ctx.pred = pred
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dx,) = ctx.saved_tensors
+        return dx * g, None, None, None, None, None
+
+
+def critic_loss_xgrad(critic, x_nhwc, target, masks=(None, None, None), rng=None, bce=False):
+    """Loss of a frozen critic on fp32 NHWC frames [B,64,64,3] with the input gradient from the same kernel.
+    `x_nhwc` may require grad (e.g. the occlusion blend); the critic's parameters get no gradient."""
+    return CriticLossXGrad.apply(_c(x_nhwc), _c(target.to(torch.float32)), critic, masks, rng, bce)
+
+
 def infer_fused_supported(critic, masker):
     """True when the fused encoder+decoder inference kernel covers these modules (chfak=1 geometry, tf32 mode, eval)."""
     f, d = critic.features, masker.dec

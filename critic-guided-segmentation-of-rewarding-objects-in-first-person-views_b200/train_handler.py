@@ -386,11 +386,20 @@ class Handler:
             _, embeds = self.sepcrit(A, collect=True)
         Z = masker(A, embeds)
         replaced = occlude(A, B, Z)
-        terms["replace"] = ops.pred_loss(critic(replaced).squeeze(1), negpred)
+        # frozen critic (tf32 mode, chfak 1): critic(blend) + loss + the backward into the blend in ONE kernel
+        frozen = self.fused_critic_step and ops.critic_fused_supported(critic) and not any(q.requires_grad for q in critic.parameters())
+
+        def scored(blend, target):
+            if frozen:
+                rng = critic._dropout_rng(blend.device)
+                masks = (None, None, None) if rng is not None else critic._dropout_masks(blend.shape[0], blend.device)
+                return ops.critic_loss_xgrad(critic, blend.permute(0, 2, 3, 1), target, masks, rng)
+            return ops.pred_loss(critic(blend).squeeze(1), target)
+        terms["replace"] = scored(replaced, negpred)
         loss = loss + terms["replace"]
         if a.inject:
             injected = occlude(B, A, Z)
-            terms["inject"] = ops.pred_loss(critic(injected).squeeze(1), pred.detach())
+            terms["inject"] = scored(injected, pred.detach())
             loss = loss + terms["inject"]
         vpred = None if a.staticnorm else pred.detach()
         if a.L1:

@@ -199,6 +199,17 @@ int cgs_adam_step_partials(float* p, float* g, float* m, float* v, int64_t n, do
                            double eps, int32_t* step_state, float grad_scale, const float* partials,
                            int32_t n_partials, int64_t stride, int64_t offset, int64_t len, void* stream);
 
+/* Frozen-critic loss and its gradient w.r.t. the INPUT frames in ONE kernel (chfak=1 geometry; the XG variant of the
+ * whole-step kernel): x [B,64,64,3] fp32 NHWC -> NewCritic.forward (dropout as for cgs_critic_train_fused) ->
+ * F.mse_loss / F.binary_cross_entropy against target [B] -> backward through the critic to the frames; no weight
+ * gradients.  This is `critic(replaced)` / `critic(injected)` of the Hourglass loop with their losses and the backward
+ * into the blend (main.py:396-411), and `pred.mean().backward(); batch.grad` of the saliency baseline (main.py:949-951).
+ * Outputs: pred [B]; loss[0] = mean loss; dx [B,64,64,3] = loss_grad * d loss / d x. */
+int cgs_critic_loss_xgrad(const float* x, const float* target, int32_t B, const float* m_e2, const float* m_e3,
+                          const float* m_v, float p_drop, uint64_t seed, uint64_t* rng_state,
+                          const cgs_critic_weights* w, float loss_grad, int32_t bce, float* pred, float* loss, float* dx,
+                          void* stream);
+
 /* `-process` inference, encoder + decoder half, in ONE kernel for the chfak=1 geometry (csrc/infer_fused.cu): uint8 NHWC
  * frames [B,64,64,3] -> /255 -> NewCritic.forward(collect=True) in eval mode (nets.py:197-212) -> UnetDecoder dec[4]..dec[0]
  * with their nearest-upsample + concat operands (nets.py:500-517) -> o0 [B,32,32,8] NHWC (the map `masker` consumes via

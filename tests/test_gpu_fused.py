@@ -357,3 +357,57 @@ def test_infer_fused_is_batch_independent_at_4096(ops):
     assert torch.equal(mask[sl], mask_s) and torch.equal(hard[sl], hard_s)
     assert torch.equal(hard.bool(), mask >= 0.1)
     assert 0.0 < float(mask.min()) and float(mask.max()) < 1.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# frozen-critic loss + input gradient in one kernel (cgs_critic_loss_xgrad)
+@pytest.mark.parametrize("B,p,bce", [(3, 0.0, False), (37, 0.3, False), (150, 0.3, True)])
+def test_critic_loss_xgrad_vs_oracle(ops, B, p, bce):
+    csd, X, y, masks = _case(B, p, seed=300 + B)
+    g = torch.Generator().manual_seed(B)
+    x = torch.rand(B, 3, 64, 64, generator=g)                       # fp32 frames (e.g. an occlusion blend), not uint8
+    yt = torch.from_numpy(y if not bce else (y > 0.5).astype(np.float32))
+    sd = {k: torch.from_numpy(v) for k, v in csd.items()}
+    xr = x.clone().requires_grad_(True)
+    loss_r, pred_r = torch_ref.critic_loss(sd, xr, yt, masks=tuple(torch.from_numpy(m) for m in masks), threshrew=bce)
+    (3.0 * loss_r).backward()
+    c = _critic(csd, p)
+    m2, m3, mv = (torch.from_numpy(m).to(DEV) for m in masks)
+    dm = (m2.permute(0, 2, 3, 1).contiguous(), m3.permute(0, 2, 3, 1).contiguous(), mv.contiguous())
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV).requires_grad_(True)
+    loss = ops.critic_loss_xgrad(c, xd, yt.to(DEV), dm, None, bce)
+    (3.0 * loss).backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_r.item()) <= 5e-3 * abs(loss_r.item()) + 1e-6, (loss.item(), loss_r.item())
+    gx, gr = xd.grad.permute(0, 3, 1, 2).cpu().numpy(), xr.grad.numpy()
+    assert _rel(gx, gr) <= 1e-1, _rel(gx, gr)        # arg-max flips under TF32 move single entries (same bound as test_gpu_tc's dx)
+    assert all(q.grad is None for q in c.parameters())
+
+
+def test_hourglass_frozen_step_fused_scoring_matches_layer_kernels(ops):
+    """segmentation_losses with a frozen critic: the fused critic(blend)+loss+input-gradient kernel vs the per-layer tf32
+    kernels - same loss terms, same masker gradients up to TF32 noise."""
+    from cgs_b200.train_handler import Handler, parse_args
+    B = 24
+    csd = synth.perturbed_state(synth.critic_shapes(1), 51, 1.5)
+    msd = synth.perturbed_state(synth.masker_shapes(1), 52, 1.5)
+    X, Yl, _ = synth.synthetic_frames(2 * B, seed=53)
+    A = (torch.from_numpy(X[:B]).permute(0, 3, 1, 2).float() / 255.0).to(DEV)
+    Bf = (torch.from_numpy(X[B:]).permute(0, 3, 1, 2).float() / 255.0).to(DEV)
+    out = []
+    for fused in (True, False):
+        H = Handler(parse_args(["-frozen", "--dropout", "0"]), device=DEV)
+        H.fused_critic_step = fused
+        H.critic.load_state_dict({k: torch.from_numpy(v) for k, v in csd.items()})
+        H.masker.load_state_dict({k: torch.from_numpy(v) for k, v in msd.items()})
+        H.critic.to(DEV).train(); H.masker.to(DEV).train()
+        for q in H.critic.parameters():
+            q.requires_grad_(False)
+        loss, terms, Z = H.segmentation_losses(A, Bf, None)
+        loss.backward()
+        torch.cuda.synchronize()
+        out.append(({k: v.item() for k, v in terms.items()}, torch.cat([q.grad.reshape(-1) for q in H.masker.parameters()]).cpu()))
+    (tf, gf), (tl, gl) = out
+    for k in tl:
+        assert abs(tf[k] - tl[k]) <= 1e-2 * abs(tl[k]) + 1e-7, (k, tf[k], tl[k])
+    assert _rel(gf.numpy(), gl.numpy()) <= 5e-2, _rel(gf.numpy(), gl.numpy())

@@ -370,7 +370,7 @@ def run_ours(args, rank, world):
         losses = trainer.losses()                          # synchronises: all K losses are on the host
         sync()
         e2e_s = time.perf_counter() - t0
-        assert trainer.i - n0 == K and torch.isfinite(losses).all()
+        assert trainer.i - n0 == K and torch.isfinite(losses).all() and float(losses.max()) < 10.0 and float(losses.min()) >= 0.0
         d2h = 4
     else:
         for _ in range(3):

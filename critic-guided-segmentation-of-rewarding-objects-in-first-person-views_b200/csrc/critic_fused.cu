@@ -248,8 +248,10 @@ __device__ __forceinline__ void stage_frame_f32(const float* __restrict__ src, f
 // parameters and the gradient w.r.t. the input frame instead (critic(replaced) / critic(injected) of the Hourglass loop,
 // main.py:396-411, and the saliency baseline, main.py:949-951): all weight-gradient work is compiled out and the backward ends
 // with features.0's input gradient, computed in two 32-row bands from the arg-max-tagged pooled gradient.
-template <bool XG>
+// MODE 2 = MODE 1's forward only (pred for fp32 frames, e.g. `negpred = critic(B)` under no_grad, main.py:365-367).
+template <int MODE>
 __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
+  constexpr bool XG = MODE != 0, FWD = MODE == 2;
   extern __shared__ __align__(128) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int lj = lane >> 3, lr = lane & 7;               // ldmatrix: this lane addresses row lr of matrix lj
@@ -587,6 +589,13 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
       sDV[lane] = sV[lane] > 0.f ? dl * wk * sMV[lane] : 0.f;
     }
     __syncthreads();
+    if (FWD) {                                       // forward only: the masks are free again, fetch the next frame's
+      if (n + (int)gridDim.x < p.B) {
+        prefetch_frame(p, n + gridDim.x, sm, tid);
+        if (p.rng_state) draw_masks(p, n + gridDim.x, rng_call, sm, tid);
+      }
+      continue;
+    }
     CF_MARK(8);
     // ================= B5: crit.1 backward
     {
@@ -920,7 +929,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
     // loss: one atomic per CTA into the scalar the host zeroed - or, with the grid barrier below, a slot of this CTA's
     // partial vector that CTA 0 sums in a fixed order afterwards (no memset node, bit-reproducible)
     if (p.adam_p) p.partials[(size_t)blockIdx.x * PSTRIDE + NGRAD] = loss_acc * p.inv_n;
-    else atomicAdd(p.loss, loss_acc * p.inv_n);
+    else if (!FWD) atomicAdd(p.loss, loss_acc * p.inv_n);
   }
   if (!XG && p.adam_p) {
     // ---- grid barrier (all CTAs are co-resident: one per SM, grid <= SMs), then every CTA sums its slice of the
@@ -942,12 +951,6 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
       }
     }
     CF_MARK(18);
-    if (blockIdx.x == 0 && warp == 1) {
-      float l = 0.f;
-      for (int k = lane; k < (int)gridDim.x; k += 32) l += __ldcg(p.partials + (size_t)k * PSTRIDE + NGRAD);
-      l = warp_sum(l);
-      if (lane == 0) p.loss[0] = l;
-    }
     const int t = p.step_state[0] + 1;
     float* red = sm + oA;                           // [4][128] + the two bias-correction scalars
     if (tid == 0) {                                 // double-precision pow once per CTA
@@ -955,7 +958,13 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
       red[520] = (float)(p.lr / bc1);
       red[521] = (float)sqrt(bc2);
     }
-    __syncthreads();
+    __syncthreads();                                // every thread is past the grid barrier from here on
+    if (blockIdx.x == 0 && warp == 1) {             // loss = sum of the per-CTA partials, fixed order
+      float l = 0.f;
+      for (int k = lane; k < (int)gridDim.x; k += 32) l += __ldcg(p.partials + (size_t)k * PSTRIDE + NGRAD);
+      l = warp_sum(l);
+      if (lane == 0) p.loss[0] = l;
+    }
     const float step_size = red[520], bc2_sqrt = red[521];
     const float omb1 = (float)(1.0 - p.beta1), b2 = (float)p.beta2, omb2 = (float)(1.0 - p.beta2), eps = (float)p.eps;
     const int G = gridDim.x, per = (NGRAD + G - 1) / G, lo = blockIdx.x * per, hi = min(NGRAD, lo + per);
@@ -1112,8 +1121,8 @@ extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target
   p.gscale = loss_grad / (float)B;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(cf::critic_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
-    cudaFuncSetAttribute(cf::critic_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
+    cudaFuncSetAttribute(cf::critic_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
+    cudaFuncSetAttribute(cf::critic_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
     attr = true;
   }
   if (!adam && cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) return check_launch("critic_train_fused.memset");
@@ -1122,7 +1131,7 @@ extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target
     // the in-kernel grid barrier needs every CTA resident at once: a cooperative launch makes the driver guarantee it
     // (or fail the launch) instead of relying on "one CTA per SM and grid <= SMs"
     void* args[] = {(void*)&p};
-    const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)cf::critic_fused_kernel<false>, dim3(grid), dim3(cf::NT), args,
+    const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)cf::critic_fused_kernel<0>, dim3(grid), dim3(cf::NT), args,
                                                        (size_t)cf::SMEM_FLOATS * 4, st);
     if (ce != cudaSuccess) {
       cudaGetLastError();
@@ -1130,7 +1139,7 @@ extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target
       return CGS_ECUDA;
     }
   } else {
-    cf::critic_fused_kernel<false><<<grid, cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
+    cf::critic_fused_kernel<0><<<grid, cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
   }
   return check_launch("critic_train_fused");
 }
@@ -1139,7 +1148,7 @@ extern "C" int cgs_critic_loss_xgrad(const float* x, const float* target, int32_
                                      const float* m_v, float p_drop, uint64_t seed, uint64_t* rng_state,
                                      const cgs_critic_weights* w, float loss_grad, int32_t bce, float* pred, float* loss, float* dx,
                                      void* stream) {
-  CGS_REQUIRE(x && target && w && pred && loss && dx && B > 0, "critic_loss_xgrad: bad args");
+  CGS_REQUIRE(x && w && pred && B > 0 && (!dx || (target && loss)), "critic_loss_xgrad: bad args");
   CGS_REQUIRE((m_e2 != nullptr) == (m_e3 != nullptr) && (m_e2 != nullptr) == (m_v != nullptr),
               "critic_loss_xgrad: dropout masks are all-or-none");
   CGS_REQUIRE((((uintptr_t)m_e2 | (uintptr_t)m_e3 | (uintptr_t)m_v) & 15) == 0, "critic_loss_xgrad: masks must be 16-byte aligned");
@@ -1159,10 +1168,20 @@ extern "C" int cgs_critic_loss_xgrad(const float* x, const float* target, int32_
   p.gscale = loss_grad / (float)B;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(cf::critic_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
+    cudaFuncSetAttribute(cf::critic_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
     attr = true;
   }
+  if (!dx) {                                         // forward only: pred
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaFuncSetAttribute(cf::critic_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
+      attr2 = true;
+    }
+    p.target = pred;                                 // any readable [B] floats: the loss of this mode is never used
+    cf::critic_fused_kernel<2><<<cgs_critic_fused_grid(B), cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
+    return check_launch("critic_forward_fused");
+  }
   if (cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) return check_launch("critic_loss_xgrad.memset");
-  cf::critic_fused_kernel<true><<<cgs_critic_fused_grid(B), cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
+  cf::critic_fused_kernel<1><<<cgs_critic_fused_grid(B), cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
   return check_launch("critic_loss_xgrad");
 }

@@ -575,6 +575,20 @@ def critic_loss_xgrad(critic, x_nhwc, target, masks=(None, None, None), rng=None
     return CriticLossXGrad.apply(_c(x_nhwc), _c(target.to(torch.float32)), critic, masks, rng, bce)
 
 
+def critic_forward_fused(critic, x_nhwc, masks=(None, None, None), rng=None):
+    """pred [B,1] = critic(x) for fp32 NHWC frames in ONE kernel, no autograd (the forward-only variant of
+    cgs_critic_loss_xgrad): `negpred = critic(B)` under no_grad, extract_contrastive_data."""
+    x = _c(x_nhwc.detach())
+    B = x.shape[0]
+    w = _lib.CriticWeights(*[_p(q.detach()) for q in critic.parameters()])
+    pred = torch.empty(B, device=x.device, dtype=torch.float32)
+    m2, m3, mv = masks
+    rp, rseed, rstate = (float(rng[0]), int(rng[1]) & 0xFFFFFFFFFFFFFFFF, _p(rng[2], torch.int64)) if rng is not None else (0.0, 0, None)
+    _call("cgs_critic_loss_xgrad", _p(x), None, B, _p(m2), _p(m3), _p(mv), rp, rseed, rstate, C.byref(w), 1.0, 0, _p(pred), None,
+          None, _stream())
+    return pred.unsqueeze(1)
+
+
 def infer_fused_supported(critic, masker):
     """True when the fused encoder+decoder inference kernel covers these modules (chfak=1 geometry, tf32 mode, eval)."""
     f, d = critic.features, masker.dec

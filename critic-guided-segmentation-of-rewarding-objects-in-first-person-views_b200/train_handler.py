@@ -351,7 +351,10 @@ class Handler:
         with torch.no_grad():
             for bidx in range(math.ceil(len(self.X) / batchsize)):
                 batch = self._to_input(self.X[bidx * batchsize:(bidx + 1) * batchsize])
-                preds.append(critic(batch).squeeze(1))
+                if self.fused_critic_step and ops.critic_fused_supported(critic):
+                    preds.append(ops.critic_forward_fused(critic, batch.permute(0, 2, 3, 1)).squeeze(1))
+                else:
+                    preds.append(critic(batch).squeeze(1))
         preds = torch.cat(preds, dim=0).cpu()
         positives = (preds > a.high_rew_thresh).numpy()
         negatives = (preds < a.low_rew_thresh).numpy()
@@ -375,7 +378,12 @@ class Handler:
         critic, masker = self.critic, self.masker
         pred, embeds = critic(A, collect=True)
         with torch.no_grad():
-            negpred = critic(B).squeeze(1)
+            if self.fused_critic_step and ops.critic_fused_supported(critic):      # forward only, one kernel
+                rng = critic._dropout_rng(B.device)
+                masks = (None, None, None) if rng is not None else critic._dropout_masks(B.shape[0], B.device)
+                negpred = ops.critic_forward_fused(critic, B.permute(0, 2, 3, 1), masks, rng).squeeze(1)
+            else:
+                negpred = critic(B).squeeze(1)
         pred = pred.squeeze(1)
         terms = {}
         loss = 0

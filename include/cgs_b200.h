@@ -204,7 +204,9 @@ int cgs_adam_step_partials(float* p, float* g, float* m, float* v, int64_t n, do
  * F.mse_loss / F.binary_cross_entropy against target [B] -> backward through the critic to the frames; no weight
  * gradients.  This is `critic(replaced)` / `critic(injected)` of the Hourglass loop with their losses and the backward
  * into the blend (main.py:396-411), and `pred.mean().backward(); batch.grad` of the saliency baseline (main.py:949-951).
- * Outputs: pred [B]; loss[0] = mean loss; dx [B,64,64,3] = loss_grad * d loss / d x. */
+ * Outputs: pred [B]; loss[0] = mean loss; dx [B,64,64,3] = loss_grad * d loss / d x.
+ * dx == NULL selects the forward-only variant (target and loss may then be NULL): pred only, e.g. `negpred = critic(B)`
+ * under no_grad (main.py:365-367) or the predictions of extract_contrastive_data (main.py:238-260). */
 int cgs_critic_loss_xgrad(const float* x, const float* target, int32_t B, const float* m_e2, const float* m_e3,
                           const float* m_v, float p_drop, uint64_t seed, uint64_t* rng_state,
                           const cgs_critic_weights* w, float loss_grad, int32_t bce, float* pred, float* loss, float* dx,

@@ -411,3 +411,24 @@ def test_hourglass_frozen_step_fused_scoring_matches_layer_kernels(ops):
     for k in tl:
         assert abs(tf[k] - tl[k]) <= 1e-2 * abs(tl[k]) + 1e-7, (k, tf[k], tl[k])
     assert _rel(gf.numpy(), gl.numpy()) <= 5e-2, _rel(gf.numpy(), gl.numpy())
+
+
+def test_critic_forward_fused_is_the_xgrad_kernels_forward(ops):
+    """Forward-only variant: pred bitwise equal to the pred of the loss+input-gradient variant, and within TF32 tolerance of
+    the oracle; also in eval mode (no masks)."""
+    B = 70
+    csd, X, y, masks = _case(B, 0.3, seed=81)
+    c = _critic(csd, 0.3)
+    x = torch.rand(B, 64, 64, 3, generator=torch.Generator().manual_seed(3)).to(DEV)
+    m2, m3, mv = (torch.from_numpy(m).to(DEV) for m in masks)
+    dm = (m2.permute(0, 2, 3, 1).contiguous(), m3.permute(0, 2, 3, 1).contiguous(), mv.contiguous())
+    pf = ops.critic_forward_fused(c, x, dm)
+    xg = x.clone().requires_grad_(True)
+    ops.critic_loss_xgrad(c, xg, torch.from_numpy(y).to(DEV), dm).backward()
+    sd = {k: torch.from_numpy(v) for k, v in csd.items()}
+    pr = torch_ref.critic_forward(sd, x.cpu().permute(0, 3, 1, 2), masks=tuple(torch.from_numpy(m) for m in masks))
+    assert (pf.cpu() - pr).abs().max().item() <= 2e-3
+    c.eval()
+    pe = ops.critic_forward_fused(c, x)
+    pr = torch_ref.critic_forward(sd, x.cpu().permute(0, 3, 1, 2))
+    assert (pe.cpu() - pr).abs().max().item() <= 2e-3

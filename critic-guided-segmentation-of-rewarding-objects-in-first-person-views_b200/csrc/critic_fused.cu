@@ -574,7 +574,10 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
       const float z = warp_sum(wk * vm) + sm[oHW + hBl2];
       const float pr = sigmoidf_(z), y = ytgt;
       float dl;
-      if (p.bce) {
+      if (p.bce == 2) {                 // "loss" = mean(pred): the saliency baseline's pred.mean().backward() (main.py:949)
+        loss_acc += pr;
+        dl = p.gscale * pr * (1.f - pr);
+      } else if (p.bce) {
         loss_acc -= y * fmaxf(logf(pr), -100.f) + (1.f - y) * fmaxf(logf(1.f - pr), -100.f);
         dl = p.gscale * (pr - y) / fmaxf(pr * (1.f - pr), 1e-12f) * pr * (1.f - pr);
       } else {

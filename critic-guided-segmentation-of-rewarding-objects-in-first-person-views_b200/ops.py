@@ -558,7 +558,7 @@ class CriticLossXGrad(torch.autograd.Function):
         m2, m3, mv = masks
         rp, rseed, rstate = (float(rng[0]), int(rng[1]) & 0xFFFFFFFFFFFFFFFF, _p(rng[2], torch.int64)) if rng is not None else (0.0, 0, None)
         _call("cgs_critic_loss_xgrad", _p(x), _p(target), B, _p(m2), _p(m3), _p(mv), rp, rseed, rstate, C.byref(w), 1.0,
-              int(bool(bce)), _p(pred), _p(loss), _p(dx), _stream())
+              int(bce), _p(pred), _p(loss), _p(dx), _stream())
         ctx.save_for_backward(dx)
         ctx.pred = pred
         return loss.reshape(())
@@ -573,6 +573,17 @@ def critic_loss_xgrad(critic, x_nhwc, target, masks=(None, None, None), rng=None
     """Loss of a frozen critic on fp32 NHWC frames [B,64,64,3] with the input gradient from the same kernel.
     `x_nhwc` may require grad (e.g. the occlusion blend); the critic's parameters get no gradient."""
     return CriticLossXGrad.apply(_c(x_nhwc), _c(target.to(torch.float32)), critic, masks, rng, bce)
+
+
+def critic_saliency(critic, x_nhwc):
+    """The saliency baseline of Handler.eval (reference main.py:945-951): `pred.mean().backward(); batch.grad.abs().sum(1)` for
+    fp32 NHWC frames, forward and input gradient in ONE kernel.  Returns (pred [B], saliency [B,1,64,64])."""
+    x = _c(x_nhwc.detach()).requires_grad_(True)
+    dummy = torch.zeros(x.shape[0], device=x.device, dtype=torch.float32)
+    with torch.enable_grad():
+        loss = CriticLossXGrad.apply(x, dummy, critic, (None, None, None), None, 2)
+    (g,) = torch.autograd.grad(loss, x)
+    return None, g.abs().sum(dim=3).unsqueeze(1)
 
 
 def critic_forward_fused(critic, x_nhwc, masks=(None, None, None), rng=None):

@@ -205,6 +205,7 @@ int cgs_adam_step_partials(float* p, float* g, float* m, float* v, int64_t n, do
  * gradients.  This is `critic(replaced)` / `critic(injected)` of the Hourglass loop with their losses and the backward
  * into the blend (main.py:396-411), and `pred.mean().backward(); batch.grad` of the saliency baseline (main.py:949-951).
  * Outputs: pred [B]; loss[0] = mean loss; dx [B,64,64,3] = loss_grad * d loss / d x.
+ * bce: 0 = MSE, 1 = BCE, 2 = loss = mean(pred), target ignored (saliency baseline: `pred.mean().backward()`, main.py:949).
  * dx == NULL selects the forward-only variant (target and loss may then be NULL): pred only, e.g. `negpred = critic(B)`
  * under no_grad (main.py:365-367) or the predictions of extract_contrastive_data (main.py:238-260). */
 int cgs_critic_loss_xgrad(const float* x, const float* target, int32_t B, const float* m_e2, const float* m_e3,

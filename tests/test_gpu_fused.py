@@ -432,3 +432,16 @@ def test_critic_forward_fused_is_the_xgrad_kernels_forward(ops):
     pe = ops.critic_forward_fused(c, x)
     pr = torch_ref.critic_forward(sd, x.cpu().permute(0, 3, 1, 2))
     assert (pe.cpu() - pr).abs().max().item() <= 2e-3
+
+
+def test_critic_saliency_matches_reference_formula(ops):
+    """`pred.mean().backward(); batch.grad.abs().sum(1)` (reference main.py:945-951) from the fused input-gradient kernel."""
+    B = 21
+    csd, X, _, _ = _case(B, 0.0, seed=91)
+    c = _critic(csd, 0.0).eval()
+    x = torch_ref.to_input(X)
+    xr = x.clone().requires_grad_(True)
+    torch_ref.critic_forward({k: torch.from_numpy(v) for k, v in csd.items()}, xr).mean().backward()
+    sal_r = xr.grad.abs().sum(dim=1)[:, None].numpy()
+    _, sal = ops.critic_saliency(c, x.permute(0, 2, 3, 1).contiguous().to(DEV))
+    assert _rel(sal.cpu().numpy(), sal_r) <= 1e-1, _rel(sal.cpu().numpy(), sal_r)

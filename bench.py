@@ -353,8 +353,8 @@ def run_ours(args, rank, world):
         from cgs_b200.graph_step import PipelinedCriticTrainer
         trainer = PipelinedCriticTrainer(H, B)            # chunked double-buffered H2D, async loss read-back
         # steps per chunk (= per H2D copy and per graph launch).  Measured (tools/e2e_timeline.py): a chunk costs ~0.1-0.25 ms
-        # of fixed latency (cross-stream event + graph launch) and copies slow to 30-43 GB/s while kernels run, so large chunks
-        # win in steady state (16 -> PCIe-bound); short runs take smaller ones so the un-overlapped first copy stays ~1/5
+        # of fixed latency (cross-stream event + graph launch), so large chunks win in steady state (16 -> PCIe-bound at the
+        # 43-54 GB/s the host memory feeds); short runs take smaller ones so the un-overlapped first copy stays ~1/5
         chunk = max(1, min(16, K // 5))
         nb = 2 * chunk                                     # pinned host dataset of nb batches, walked K steps in total
         Xds = torch.from_numpy(np.concatenate([X] * nb)).pin_memory()

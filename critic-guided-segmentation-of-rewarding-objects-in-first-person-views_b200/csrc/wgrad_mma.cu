@@ -49,6 +49,10 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
   // ---- per-lane A rows: m = ci*9 + tap (the OIHW order of dw), m == 72 is the all-ones bias row
   const int warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
   // branch-free gather: value = x[off] * mulA + addA with (1,0) data row, (0,1) ones row, (0,0) pad row
+  // WM_MT == 5 (8 input channels per block): rows of M-tile mt are (tap 2mt | tap 2mt+1) x ci, row 8 of mt 4 = ones (bias);
+  // the mma's k index maps to pixels as k = t -> 2t, k = t+4 -> 2t+1, so the 4 consecutive pixels 2t..2t+3 of a filter row
+  // (two 64-bit loads from the planar tile) feed all three kx taps: 6 LDS.64 per 8 pixels instead of 20 LDS.32 + 20 FMA.
+  // WM_MT == 2 (RGB layer): rows m = ci*9 + tap gathered one by one, as before.
   int offA[WM_MT][2];
   float mulA[WM_MT][2], addA[WM_MT][2];
 #pragma unroll
@@ -163,6 +167,33 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
   __syncthreads();
 
   const int R = g.fpc * th;
+  if (WM_MT == 5) {
+    const uint32_t ones = gid == 0 ? 0x3f800000u : 0u;
+    for (int r = warp; r < R; r += 8) {
+      const int ff = fdiv(r, g.dth), yy = r - ff * th;
+      const float* xrow = s_x + gid * g.psx + (ff * sh + yy) * g.rsx + 2 * tig;
+      const float* yrow = s_y + gid * g.psy + r * g.rsy + 2 * tig;
+      for (int xb = 0; xb < tw; xb += 8) {
+        const float2 bb = *reinterpret_cast<const float2*>(yrow + xb);
+        const uint32_t b0 = __float_as_uint(bb.x), b1 = __float_as_uint(bb.y);
+        uint32_t v[3][4];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const float2 lo = *reinterpret_cast<const float2*>(xrow + ky * g.rsx + xb);
+          const float2 hi = *reinterpret_cast<const float2*>(xrow + ky * g.rsx + xb + 2);
+          v[ky][0] = __float_as_uint(lo.x); v[ky][1] = __float_as_uint(lo.y);
+          v[ky][2] = __float_as_uint(hi.x); v[ky][3] = __float_as_uint(hi.y);
+        }
+#pragma unroll
+        for (int mt = 0; mt < WM_MT; ++mt) {
+          const int ta = (2 * mt) % 9, tb = (2 * mt + 1) % 9;       // (% 9 only keeps the WM_MT == 2 instantiation in bounds)
+          const uint32_t a0 = v[ta / 3][ta % 3], a2 = v[ta / 3][ta % 3 + 1];
+          const uint32_t a1 = mt < 4 ? v[tb / 3][tb % 3] : ones, a3 = mt < 4 ? v[tb / 3][tb % 3 + 1] : ones;
+          mma_tf32(acc[mt], a0, a1, a2, a3, b0, b1);
+        }
+      }
+    }
+  } else {
   for (int r = warp; r < R; r += 8) {
     const int ff = fdiv(r, g.dth), yy = r - ff * th;
     const float* xrow = s_x + (ff * sh + yy) * g.rsx + tig;
@@ -181,6 +212,7 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
         mma_tf32(acc[mt], a[0], a[1], a[2], a[3], b0, b1);
       }
     }
+  }
   }
 
   }   // tile loop
@@ -201,7 +233,14 @@ __global__ void __launch_bounds__(256) wgrad3x3_mma_kernel(const cgs_wgrad3x3_ar
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += s_red[w * 16 * WM_MT * 8 + e];
     if (n >= con) continue;
-    if (mrow < 9 * cin) {
+    if (WM_MT == 5) {
+      const int tap = 2 * (mrow >> 4) + ((mrow >> 3) & 1), ci = mrow & 7;
+      if (tap < 9) {
+        if (ci < cin) atomicAdd(p.dw + ((size_t)(co0 + n) * Cin + ci0 + ci) * 9 + tap, s);
+      } else if (tap == 9 && ci == 0 && p.db && blockIdx.z == 0) {
+        atomicAdd(p.db + co0 + n, s);
+      }
+    } else if (mrow < 9 * cin) {
       atomicAdd(p.dw + ((size_t)(co0 + n) * Cin + ci0) * 9 + mrow, s);
     } else if (mrow == 9 * cin && p.db && blockIdx.z == 0) {
       atomicAdd(p.db + co0 + n, s);
@@ -224,7 +263,9 @@ int launch_wgrad_mma(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   g.rsx = (g.tw + 2 + 7) & ~7; if ((g.rsx & 15) == 0) g.rsx += 8;
   g.rsy = g.tw;
   g.psx = g.fpc * (g.th + 2) * g.rsx; g.psx += (56 - (g.psx % 32)) % 32;   // == 24 (mod 32)
-  g.psy = g.fpc * g.th * g.rsy;       g.psy += (36 - (g.psy % 32)) % 32;   // == 4 (mod 32)
+  g.psy = g.fpc * g.th * g.rsy;
+  if (a.x.C <= 3) g.psy += (36 - (g.psy % 32)) % 32;   // == 4 (mod 32): 32-bit B-fragment loads, pixels t and t+4
+  else g.psy += (40 - (g.psy % 32)) % 32;              // == 8 (mod 32): 64-bit loads of the pixel pair (2t, 2t+1)
   g.dsw = make_fastdiv(g.tw + 2); g.dsh = make_fastdiv(g.th + 2);
   g.dtw = make_fastdiv(g.tw);     g.dth = make_fastdiv(g.th);
   g.dwp = make_fastdiv(g.tw / 2); g.dhp = make_fastdiv(g.th / 2);

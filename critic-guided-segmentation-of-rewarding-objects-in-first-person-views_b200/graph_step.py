@@ -32,6 +32,7 @@ def _capture(fn, warmup=3, group_sync=None):
 
 class _Graphed:
     launches = 0
+    trains = False          # replaying rewrites parameters (optimizer kernels inside the graph)
 
     def load(self, *host):
         for dst, src in zip(self.static_in, host):
@@ -39,6 +40,8 @@ class _Graphed:
 
     def replay(self):
         self.graph.replay()
+        if self.trains:
+            ops.weights_changed()
         return self.out
 
     def __call__(self, *host):
@@ -49,6 +52,7 @@ class _Graphed:
 class GraphedCriticStep(_Graphed):
     """One critic_pipe iteration (reference main.py:185-200) as a CUDA graph.  The shift_batch roll is a
     device int32 (`self.roll`), so it can change per replay: `step.roll.fill_(r)` before the call."""
+    trains = True
 
     def __init__(self, handler, batch, opti=None, X=None, Y=None, warmup=3):
         H = self.H = handler
@@ -68,6 +72,7 @@ class GraphedCriticStep(_Graphed):
 
 class GraphedHourglassStep(_Graphed):
     """One segmentation_training iteration (reference main.py:344-463) as a CUDA graph."""
+    trains = True
 
     def __init__(self, handler, batch, opti=None):
         H = self.H = handler
@@ -98,7 +103,9 @@ class GraphedHourglassStep(_Graphed):
 
 
 class GraphedSegment(_Graphed):
-    """One batch of Handler.segment (reference main.py:1134-1164): critic(collect) -> masker -> >= threshold."""
+    """One batch of Handler.segment (reference main.py:1134-1164): critic(collect) -> masker -> >= threshold.
+    The captured graph reads the decoder weights through the fragment buffer packed at capture time: build a new
+    GraphedSegment after the masker has been trained further."""
 
     def __init__(self, handler, batch, threshold=0.1):
         H = self.H = handler
@@ -156,6 +163,7 @@ class PipelinedCriticTrainer:
         main = torch.cuda.current_stream()
         main.wait_event(self.ready[k])
         st.graph.replay()
+        ops.weights_changed()
         self.done[k].record(main)
         self.loss_ring[self.i % self.loss_ring.numel()].copy_(st.out, non_blocking=True)
         self.i += 1
@@ -202,6 +210,7 @@ class PipelinedCriticTrainer:
                 sl["ready"].record(self.copy_stream)
             main.wait_event(sl["ready"])
             sl["graph"].replay()
+            ops.weights_changed()
             sl["done"].record(main)
             r = self.i % self.loss_ring.numel()
             if r + chunk <= self.loss_ring.numel():

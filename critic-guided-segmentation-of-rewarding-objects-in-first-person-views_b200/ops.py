@@ -14,6 +14,8 @@ from ._lib import (EPI_LEAKY, EPI_LINEAR, EPI_MUL, EPI_RELU_POOL, EPI_SIGMOID, E
                    SRC_LEAKYGRAD, SRC_PLAIN, SRC_POOLBWD, SRC_SIGGRAD, SRC_U8ROLL, CgsError, Conv3x3Args, Src, Wgrad3x3Args)
 
 _launches = 0   # kernels launched through this module (bench.py reports it)
+_weights_epoch = 0   # bumped by every optimizer kernel launched through this module: those write parameters behind torch's
+                     # back (no `_version` change), so caches derived from weights (packed decoder fragments) key on it too
 _precision = 0  # 0 = fp32 FFMA kernels (exact parity path), 1 = tcgen05 TF32 convolutions where covered
 
 
@@ -25,6 +27,13 @@ def set_precision(name):
 
 def get_precision():
     return "tf32" if _precision else "fp32"
+
+
+def weights_changed():
+    """Tell the weight-derived caches that parameters were rewritten outside this module's entry points (CUDA-graph replays
+    of training steps run the optimizer kernels without passing through here)."""
+    global _weights_epoch
+    _weights_epoch += 1
 
 
 def launch_count():
@@ -526,6 +535,8 @@ def critic_train_fused(critic, frames_u8, target, roll=0, masks=(None, None, Non
               rp, rseed, rstate, C.byref(w), None, _p(buf), C.byref(adam) if adam is not None else None, float(loss_grad),
               int(bool(bce)), _p(pred), _p(loss), _stream())
         if adam is not None:
+            global _weights_epoch
+            _weights_epoch += 1
             opt.adam_done_in_kernel = True          # the coming opt.step() has nothing left to do
         else:
             opt.pending_partials = (buf, grid, stride, off, nparam)
@@ -617,7 +628,7 @@ def infer_encode_decode(critic, masker, frames_u8):
     L = _lib.lib()
     B = frames_u8.shape[0]
     d = masker.dec
-    ver = tuple((w.data_ptr(), w._version) for w in (d[3].weight, d[2].weight, d[1].weight, d[0].weight))
+    ver = (_weights_epoch,) + tuple((w.data_ptr(), w._version) for w in (d[3].weight, d[2].weight, d[1].weight, d[0].weight))
     cache = getattr(masker, "_cgs_pack", None)
     if cache is None or cache[0] != ver:
         pack = torch.empty(L.cgs_infer_pack_floats(), device=frames_u8.device, dtype=torch.float32)
@@ -652,6 +663,8 @@ def reduce_partials(g, buf, n_partials, stride, offset, length):
 def adam_step_partials(p, g, m, v, step_state, buf, n_partials, stride, offset, length, lr=1e-3, betas=(0.9, 0.999),
                        eps=1e-8, grad_scale=1.0):
     """adam_step whose gradient is g + the sum of the per-CTA partial vectors in `buf`; g is cleared."""
+    global _weights_epoch
+    _weights_epoch += 1
     _call("cgs_adam_step_partials", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(betas[0]), float(betas[1]),
           float(eps), _p(step_state, torch.int32), float(grad_scale), _p(buf), int(n_partials), int(stride), int(offset),
           int(length), _stream())
@@ -676,6 +689,8 @@ def iou_counts(z, gt_u8, thresh, counts, strict=True):
 def adam_step(p, g, m, v, step_state, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, clear_grad=False):
     """Flat-bucket Adam (torch.optim.Adam defaults, main.py:178).  step_state: int32 device tensor [2] = (steps applied,
     ticket); the kernel advances it.  clear_grad: zero g in the same pass (fused zero_grad)."""
+    global _weights_epoch
+    _weights_epoch += 1
     _call("cgs_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(betas[0]), float(betas[1]),
           float(eps), _p(step_state, torch.int32), float(grad_scale), int(clear_grad), _stream())
 
@@ -690,6 +705,8 @@ def p2p_stage(g, npad, sym, step_state, partials=None):
 def p2p_allreduce_adam(p, m, v, npad, peer_bufs, peer_flags, rank, world, step_state, err, lr=1e-3, betas=(0.9, 0.999),
                        eps=1e-8, grad_scale=1.0):
     """One-shot all-reduce over NVLink peer memory fused with Adam (cgs_p2p_allreduce_adam)."""
+    global _weights_epoch
+    _weights_epoch += 1
     _call("cgs_p2p_allreduce_adam", _p(p), _p(m), _p(v), p.numel(), int(npad), peer_bufs, peer_flags, int(rank), int(world),
           float(lr), float(betas[0]), float(betas[1]), float(eps), _p(step_state, torch.int32), float(grad_scale),
           _p(err, torch.int32), _stream())

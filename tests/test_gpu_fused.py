@@ -445,3 +445,28 @@ def test_critic_saliency_matches_reference_formula(ops):
     sal_r = xr.grad.abs().sum(dim=1)[:, None].numpy()
     _, sal = ops.critic_saliency(c, x.permute(0, 2, 3, 1).contiguous().to(DEV))
     assert _rel(sal.cpu().numpy(), sal_r) <= 1e-1, _rel(sal.cpu().numpy(), sal_r)
+
+
+def test_infer_pack_follows_optimizer_steps(ops, monkeypatch):
+    """The decoder's packed MMA fragments are a cache: optimizer kernels rewrite the weights without touching torch's
+    version counters, so the fused inference path must re-pack after training steps (and agree with the per-layer path)."""
+    from cgs_b200.train_handler import Handler, parse_args
+    B = 16
+    H = Handler(parse_args(["-frozen", "--dropout", "0", "--binarymaskthreshold", "0.1"]), device=DEV)
+    H.critic.load_state_dict({k: torch.from_numpy(v) for k, v in synth.perturbed_state(synth.critic_shapes(1), 61, 1.5).items()})
+    H.masker.load_state_dict({k: torch.from_numpy(v) for k, v in synth.perturbed_state(synth.masker_shapes(1), 62, 1.5).items()})
+    X, Yl, _ = synth.synthetic_frames(3 * B, seed=63)
+    H.critic.to(DEV).eval(); H.masker.to(DEV).eval()
+    _, M0, _ = H.segment_arrays(X[:B])                                   # packs the decoder weights
+    for q in H.critic.parameters():
+        q.requires_grad_(False)
+    H.critic.train(); H.masker.train()
+    opti = H._opt(H.masker.parameters())
+    for _ in range(5):
+        H.segmentation_step(X[:B], X[B:2 * B], torch.from_numpy(Yl[1, :B]), opti)
+    H.critic.eval(); H.masker.eval()
+    _, M1, _ = H.segment_arrays(X[:B])                                   # fused kernels, must see the trained weights
+    monkeypatch.setattr(ops, "infer_fused_supported", lambda c, m: False)
+    _, M2, _ = H.segment_arrays(X[:B])                                   # per-layer kernels
+    assert np.abs(M1 - M0).max() > 1e-3, "the masker did not move: the test is vacuous"
+    assert np.abs(M1 - M2).max() <= 5e-3, np.abs(M1 - M2).max()

@@ -9,6 +9,10 @@ namespace cgs {
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs).  Function attributes
+// (cudaFuncAttributeMaxDynamicSharedMemorySize) are per device too, so launchers set them on every call: it is a host-side
+// table write, not a stream operation.
+int device_sms();
 
 #define CGS_REQUIRE(cond, ...)            \
   do {                                    \

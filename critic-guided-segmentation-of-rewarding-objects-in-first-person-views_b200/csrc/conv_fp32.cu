@@ -255,11 +255,7 @@ static int launch_conv(const cgs_conv3x3_args& a, cudaStream_t st) {
   ConvGeom g; int nthr, nblk;
   pick_geom(a.B, a.H, a.W, g, nthr, nblk);
   size_t smem = ((size_t)g.fpc * CI_T * g.ps + CI_T * 9 * CO_T) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(conv3x3_kernel<CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr_done = true;
-  }
+  cudaFuncSetAttribute(conv3x3_kernel<CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   dim3 grid(nblk, (a.Cout + CO_T - 1) / CO_T);
   conv3x3_kernel<CO_T><<<grid, nthr, smem, st>>>(a, g);
   return check_launch("conv3x3");
@@ -458,11 +454,7 @@ static int launch_wgrad(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   g.dtw = make_fastdiv(g.tw);     g.dth = make_fastdiv(g.th);
   g.dwp = make_fastdiv(g.tw > 2 ? g.tw / 2 : 2); g.dhp = make_fastdiv(g.th > 2 ? g.th / 2 : 2);
   size_t smem = ((size_t)CI_B * g.psx + (size_t)CO_B * g.psy) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(wgrad3x3_kernel<CO_R, CI_R, NCO, NCI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
+  cudaFuncSetAttribute(wgrad3x3_kernel<CO_R, CI_R, NCO, NCI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int nblk = ((a.B + g.fpc - 1) / g.fpc) * g.tiles_x * g.tiles_y;
   dim3 grid(nblk, (a.dy.C + CO_B - 1) / CO_B, (a.x.C + CI_B - 1) / CI_B);
   wgrad3x3_kernel<CO_R, CI_R, NCO, NCI><<<grid, 256, smem, st>>>(a, g);

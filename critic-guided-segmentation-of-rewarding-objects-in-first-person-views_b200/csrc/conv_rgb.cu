@@ -188,15 +188,8 @@ extern "C" int cgs_conv_rgb_fwd(const uint8_t* frames, int32_t B, int32_t H, int
   g.off_lut = g.off_w + 27 * Cout;
   g.dcol = make_fastdiv(W + 2);
   const size_t smem = (size_t)(g.off_lut + 256) * sizeof(float);
-  static bool attr_done = false;
-  static int sms = 148;
-  if (!attr_done) {
-    cudaFuncSetAttribute(conv_rgb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    attr_done = true;
-  }
+  cudaFuncSetAttribute(conv_rgb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  const int sms = device_sms();
   CGS_REQUIRE(smem <= 160 * 1024, "conv_rgb_fwd: tile does not fit shared memory");
   int per_sm = (int)((200 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);

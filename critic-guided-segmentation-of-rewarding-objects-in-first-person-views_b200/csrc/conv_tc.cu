@@ -387,15 +387,8 @@ int launch_conv_tc(const cgs_conv3x3_args& a, cudaStream_t st) {
   // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), K-major both, N>>3 at 17, M>>4 at 24
   g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.n_pad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const size_t smem = tc_smem_bytes(g.cin_pad, g.n_pad);
-  static bool attr_done = false;
-  static int sms = 148;
-  if (!attr_done) {
-    cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    attr_done = true;
-  }
+  cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const int sms = device_sms();
   int per_sm = (int)((220 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : per_sm;
   const int tmem_limit = 512 / g.tmem_cols;

@@ -939,6 +939,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
     //      parameter vector over all partial vectors (fixed order) and applies Adam: no second launch, no atomics
     __threadfence();
     __syncthreads();
+    bool bar_failed = false;
     if (tid == 0) {
       if (atomicAdd(p.bar, 1u) == gridDim.x - 1) {
         p.bar[0] = 0;
@@ -950,18 +951,22 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
           __nanosleep(40);
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(gnow) : "l"(p.bar + 1) : "memory");
         }
-        if (gnow == bar_gen) atomicExch(p.bar + 2, 1u);
+        if (gnow == bar_gen) { atomicExch(p.bar + 2, 1u); bar_failed = true; }
       }
     }
     CF_MARK(18);
     const int t = p.step_state[0] + 1;
-    float* red = sm + oA;                           // [4][128] + the two bias-correction scalars
+    float* red = sm + oA;                           // [4][128] + the two bias-correction scalars + the barrier verdict
     if (tid == 0) {                                 // double-precision pow once per CTA
       const double bc1 = 1.0 - pow(p.beta1, (double)t), bc2 = 1.0 - pow(p.beta2, (double)t);
       red[520] = (float)(p.lr / bc1);
       red[521] = (float)sqrt(bc2);
+      red[522] = bar_failed ? 1.f : 0.f;
     }
     __syncthreads();                                // every thread is past the grid barrier from here on
+    // a CTA whose barrier wait timed out has no complete gradient to read: it leaves its slice of the parameters and the
+    // optimizer state untouched (the host sees the flag before the next checkpoint, FlatAdam.barrier_ok())
+    const bool skip_update = red[522] != 0.f;
     if (blockIdx.x == 0 && warp == 1) {             // loss = sum of the per-CTA partials, fixed order
       float l = 0.f;
       for (int k = lane; k < (int)gridDim.x; k += 32) l += __ldcg(p.partials + (size_t)k * PSTRIDE + NGRAD);
@@ -973,7 +978,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
     const int G = gridDim.x, per = (NGRAD + G - 1) / G, lo = blockIdx.x * per, hi = min(NGRAD, lo + per);
     const int ex = tid & 127, ky = tid >> 7;        // 128 parameters x 4 slices of the partial list per pass
     const bool xchg = p.world > 1;
-    for (int base = lo; base < hi; base += 128) {
+    for (int base = lo; base < hi && !skip_update; base += 128) {
       const int i = base + ex;
       float s0 = 0.f, gv = 0.f, m0 = 0.f, v0 = 0.f, p0 = 0.f;
       if (i < hi) {
@@ -989,6 +994,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
       __syncthreads();
       if (ky == 0 && i < hi) {
         gv += (red[ex] + red[128 + ex]) + (red[256 + ex] + red[384 + ex]);
+        bool upd = true;
         if (xchg) {
           const size_t slot = (size_t)(t & 1) * p.world * p.npad;
           const unsigned long long pkt = ((unsigned long long)(unsigned)t << 32) | __float_as_uint(gv);
@@ -1008,12 +1014,15 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
             gv += __uint_as_float((unsigned)got);
           }
           if (!ok) atomicExch(p.bar + 2, 1u);           // a peer never delivered: flagged, never hangs
+          upd = ok;
         }
-        const float mv = m0 + omb1 * (gv - m0);
-        const float vv = v0 * b2 + omb2 * gv * gv;
-        p.adam_m[i] = mv;
-        p.adam_v[i] = vv;
-        p.adam_p[i] = p0 - step_size * (mv / (sqrtf(vv) / bc2_sqrt + eps));
+        if (upd) {                                      // incomplete sum: leave this parameter and its moments as they are
+          const float mv = m0 + omb1 * (gv - m0);
+          const float vv = v0 * b2 + omb2 * gv * gv;
+          p.adam_m[i] = mv;
+          p.adam_v[i] = vv;
+          p.adam_p[i] = p0 - step_size * (mv / (sqrtf(vv) / bc2_sqrt + eps));
+        }
         p.adam_g[i] = 0.f;
       }
       __syncthreads();
@@ -1052,15 +1061,7 @@ extern "C" int cgs_critic_fused_supported(int32_t C0, int32_t C1, int32_t C2, in
   return C0 == 8 && C1 == 8 && C2 == 8 && C3 == 16 && NB == 32;
 }
 
-static int cf_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
-  return sms;
-}
+static int cf_sms() { return device_sms(); }
 
 // CTAs the whole-step kernel runs for a batch of B frames (= rows of the partial-gradient buffer): frames per CTA are
 // equalised so that no CTA idles a whole frame.
@@ -1122,12 +1123,7 @@ extern "C" int cgs_critic_train_fused(const uint8_t* frames, const float* target
   p.pred = pred; p.loss = loss; p.roll_dev = roll_dev; p.B = B; p.roll = roll; p.bce = bce;
   p.inv_n = 1.f / (float)B;
   p.gscale = loss_grad / (float)B;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(cf::critic_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
-    cudaFuncSetAttribute(cf::critic_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
-    attr = true;
-  }
+  cudaFuncSetAttribute(cf::critic_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
   if (!adam && cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) return check_launch("critic_train_fused.memset");
   const int grid = cgs_critic_fused_grid(B);
   if (adam) {
@@ -1169,17 +1165,9 @@ extern "C" int cgs_critic_loss_xgrad(const float* x, const float* target, int32_
   p.pred = pred; p.loss = loss; p.B = B; p.bce = bce;
   p.inv_n = 1.f / (float)B;
   p.gscale = loss_grad / (float)B;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(cf::critic_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
-    attr = true;
-  }
+  cudaFuncSetAttribute(cf::critic_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
   if (!dx) {                                         // forward only: pred
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaFuncSetAttribute(cf::critic_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
-      attr2 = true;
-    }
+    cudaFuncSetAttribute(cf::critic_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
     p.target = pred;                                 // any readable [B] floats: the loss of this mode is never used
     cf::critic_fused_kernel<2><<<cgs_critic_fused_grid(B), cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
     return check_launch("critic_forward_fused");

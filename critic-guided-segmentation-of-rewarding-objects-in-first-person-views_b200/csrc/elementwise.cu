@@ -27,13 +27,21 @@ int check_launch(const char* what) {
   return CGS_OK;
 }
 
-static int grid_for(int64_t work_items, int threads) {
-  static int sms = 0;
+int device_sms() {
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = dev >= 0 && dev < 64 ? dev : 0;
+  int sms = cache[slot];
   if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    cache[slot] = sms;     // benign race: every thread computes the same value
   }
+  return sms;
+}
+
+static int grid_for(int64_t work_items, int threads) {
+  const int sms = device_sms();
   int64_t blocks = (work_items + threads - 1) / threads;
   int64_t cap = (int64_t)sms * 8;
   if (blocks > cap) blocks = cap;

@@ -599,13 +599,8 @@ extern "C" int cgs_masker_fused(const uint8_t* frames, const float* o0, int32_t 
   inf::mk::Params p;
   p.frames = frames; p.o0 = o0; p.w0 = wm0; p.b0 = bm0; p.w2 = wm2; p.b2 = bm2; p.mask = mask; p.hard = hard; p.thresh = thresh;
   p.B = B;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    cudaFuncSetAttribute(inf::mk::masker_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, inf::mk::SMEM_FLOATS * 4);
-  }
+  const int sms = device_sms();
+  cudaFuncSetAttribute(inf::mk::masker_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, inf::mk::SMEM_FLOATS * 4);
   const int per = (B + sms - 1) / sms, grid = (B + per - 1) / per;
   inf::mk::masker_fused_kernel<<<grid, inf::mk::NT, inf::mk::SMEM_FLOATS * 4, (cudaStream_t)stream>>>(p);
   return check_launch("masker_fused");
@@ -630,13 +625,8 @@ extern "C" int cgs_infer_fused(const uint8_t* frames, int32_t B, const cgs_criti
   p.w0 = cw->w0; p.b0 = cw->b0; p.w1 = cw->w1; p.b1 = cw->b1; p.w2 = cw->w2; p.b2 = cw->b2; p.w3 = cw->w3; p.b3 = cw->b3;
   p.w4 = cw->w4; p.b4 = cw->b4; p.wl1 = cw->wl1; p.bl1 = cw->bl1; p.wl2 = cw->wl2; p.bl2 = cw->bl2;
   p.wd4 = wd4; p.bd4 = bd4; p.bd3 = bd3; p.bd2 = bd2; p.bd1 = bd1; p.bd0 = bd0; p.pack = pack; p.pred = pred; p.o0 = o0;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    cudaFuncSetAttribute(inf::infer_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, inf::SMEM_FLOATS * 4);
-  }
+  const int sms = device_sms();
+  cudaFuncSetAttribute(inf::infer_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, inf::SMEM_FLOATS * 4);
   const int per = (B + sms - 1) / sms, grid = (B + per - 1) / per;
   inf::infer_fused_kernel<<<grid, inf::NT, inf::SMEM_FLOATS * 4, (cudaStream_t)stream>>>(p);
   return check_launch("infer_fused");

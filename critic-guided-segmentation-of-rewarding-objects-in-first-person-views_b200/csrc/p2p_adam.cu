@@ -58,6 +58,9 @@ __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(float* __restri
                                                                  double lr, double beta1, double beta2, double eps_d,
                                                                  int* __restrict__ step_state, float gscale, int* __restrict__ err) {
   const int t = step_state[0] + 1;
+  __shared__ int s_failed;
+  if (threadIdx.x == 0) s_failed = 0;
+  __syncthreads();
   // 1. announce (block 0 only; the staging kernel before us on this stream has completed, its stores are in our L2)
   if (blockIdx.x == 0 && threadIdx.x < world) {
     __threadfence_system();
@@ -72,7 +75,7 @@ __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(float* __restri
       if ((int)seen >= t) break;
       __nanosleep(64);
     }
-    if ((int)seen < t) atomicExch(err, 1);
+    if ((int)seen < t) { atomicExch(err, 1); s_failed = 1; }
   }
   __shared__ float s_bc[2];
   if (threadIdx.x == 32) {                         // one double-precision pow pair per block, while the others poll
@@ -87,7 +90,8 @@ __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(float* __restri
   const float bc2_sqrt = s_bc[1];
   const float omb1 = (float)(1.0 - beta1), b2 = (float)beta2, omb2 = (float)(1.0 - beta2), eps = (float)eps_d;
   const int64_t slot = (int64_t)(t & 1) * npad;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  // a peer that never announced leaves an incomplete sum: keep parameters and moments as they are (flag is set)
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n && !s_failed; i += (int64_t)gridDim.x * blockDim.x) {
     float gv = 0.f;
     for (int r = 0; r < world; ++r) {
       float x;

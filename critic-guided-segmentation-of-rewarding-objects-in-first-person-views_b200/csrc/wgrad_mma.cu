@@ -273,20 +273,11 @@ int launch_wgrad_mma(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   size_t smem = ((size_t)g.xplanes * g.psx + (size_t)WM_CO * g.psy) * sizeof(float);
   const size_t red = (size_t)8 * 16 * 5 * 8 * sizeof(float);
   if (smem < red) smem = red;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(wgrad3x3_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(wgrad3x3_mma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
+  cudaFuncSetAttribute(wgrad3x3_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(wgrad3x3_mma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   g.nblk = ((a.B + g.fpc - 1) / g.fpc) * g.tiles_x * g.tiles_y;
   const int gy = (a.dy.C + WM_CO - 1) / WM_CO, gz = (a.x.C + WM_CI - 1) / WM_CI;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
+  const int sms = device_sms();
   int per_sm = (int)((200 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
   int gx = (sms * per_sm) / (gy * gz);

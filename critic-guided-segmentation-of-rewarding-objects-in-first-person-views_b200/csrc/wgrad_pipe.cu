@@ -290,16 +290,9 @@ int launch_wgrad_pipe(const cgs_wgrad3x3_args& a, cudaStream_t st) {
   const int MT = (9 * C + 1 + 15) / 16;
   const size_t red = (size_t)9 * 16 * (MT <= 2 ? 2 : 5) * 8 * sizeof(float);
   if (smem < red) smem = red;
-  static bool attr_done = false;
-  static int sms = 148;
-  if (!attr_done) {
-    cudaFuncSetAttribute(wgrad3x3_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(wgrad3x3_pipe_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    attr_done = true;
-  }
+  cudaFuncSetAttribute(wgrad3x3_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(wgrad3x3_pipe_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const int sms = device_sms();
   int grid = sms;   // one persistent CTA per SM (the non-RED part of the kernel does not depend on the grid size)
   g.flags = 0;
   if (const char* e = getenv("CGS_WGRAD_NORED")) g.flags |= atoi(e) ? 1 : 0;      // debug probes only

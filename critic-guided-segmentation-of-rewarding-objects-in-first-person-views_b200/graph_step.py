@@ -14,8 +14,25 @@ from . import ops
 from .train_handler import FlatAdam
 
 
-def _capture(fn, warmup=3, group_sync=None):
-    """Standard whole-step capture: warm up on a side stream, then capture `fn` into a graph."""
+def _train_state(opti, *critics):
+    """Every device tensor a training step mutates besides its inputs: parameters, gradient bucket, Adam moments and step
+    counter, the dropout Philox call counters of the critics."""
+    st = [opti.flat, opti.gflat, opti.m, opti.v, opti.step_count]
+    for c in critics:
+        if c is not None:
+            c._dropout_rng(opti.flat.device)          # creates the counter if this module has not drawn yet
+            if c._rng_state is not None:
+                st.append(c._rng_state)
+    return st
+
+
+def _capture(fn, warmup=3, state=()):
+    """Standard whole-step capture: warm up on a side stream, then capture `fn` into a graph.  The warm-up runs REAL steps
+    (optimizer update, RNG advance) on whatever the static buffers hold, so every tensor in `state` is snapshotted before
+    and restored after: constructing a graphed step leaves parameters, Adam moments, step count and dropout stream exactly
+    as they were (the reference trajectory starts at the first replay)."""
+    torch.cuda.synchronize()
+    saved = [t.clone() for t in state]
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
@@ -27,7 +44,13 @@ def _capture(fn, warmup=3, group_sync=None):
     n0 = ops.launch_count()
     with torch.cuda.graph(g, capture_error_mode="thread_local"):
         out = fn()
-    return g, out, ops.launch_count() - n0
+    n = ops.launch_count() - n0
+    for t, v in zip(state, saved):
+        t.copy_(v)
+    if saved:
+        ops.weights_changed()
+    torch.cuda.synchronize()
+    return g, out, n
 
 
 class _Graphed:
@@ -67,7 +90,7 @@ class GraphedCriticStep(_Graphed):
 
         def fn():
             return H.critic_step(self.X, self.Y, self.opti, roll=self.roll)
-        self.graph, self.out, self.launches = _capture(fn, warmup=warmup)
+        self.graph, self.out, self.launches = _capture(fn, warmup=warmup, state=_train_state(self.opti, H.critic))
 
 
 class GraphedHourglassStep(_Graphed):
@@ -96,7 +119,8 @@ class GraphedHourglassStep(_Graphed):
         def fn():
             terms = H.segmentation_step(self.X, self.CX, self.Y, self.opti, roll=self.roll)
             return torch.stack([terms[k] for k in sorted(terms)])
-        self.graph, self.out, self.launches = _capture(fn)
+        self.graph, self.out, self.launches = _capture(fn, state=_train_state(self.opti, H.critic,
+                                                                              getattr(H, "sepcrit", None) if a.separate else None))
         self.term_names = sorted(k for k in ("critic", "replace", "inject", "L1", "L2")
                                  if (k != "critic" or a.live) and (k != "inject" or a.inject)
                                  and (k != "L1" or a.L1) and (k != "L2" or a.L2))
@@ -179,7 +203,7 @@ class PipelinedCriticTrainer:
         def fn():
             return torch.stack([H.critic_step(Xd[k * B:(k + 1) * B], Yd[k * B:(k + 1) * B], self.opti, roll=rolls[k:k + 1])
                                 for k in range(chunk)])
-        graph, out, _ = _capture(fn, warmup=1)
+        graph, out, _ = _capture(fn, warmup=1, state=_train_state(self.opti, H.critic))
         return dict(X=Xd, Y=Yd, rolls=rolls, graph=graph, out=out, ready=torch.cuda.Event(), done=torch.cuda.Event())
 
     def train(self, X_host, Y_host, rolls=None, chunk=None):
@@ -213,8 +237,10 @@ class PipelinedCriticTrainer:
             ops.weights_changed()
             sl["done"].record(main)
             r = self.i % self.loss_ring.numel()
-            if r + chunk <= self.loss_ring.numel():
-                self.loss_ring[r:r + chunk].copy_(sl["out"], non_blocking=True)
+            head = min(chunk, self.loss_ring.numel() - r)       # the ring wraps: split the read-back, never drop a loss
+            self.loss_ring[r:r + head].copy_(sl["out"][:head], non_blocking=True)
+            if head < chunk:
+                self.loss_ring[:chunk - head].copy_(sl["out"][head:], non_blocking=True)
             self.i += chunk
             c += chunk
         for k in range(c, n):
@@ -222,8 +248,11 @@ class PipelinedCriticTrainer:
         return n
 
     def losses(self):
+        """The most recent min(steps, ring) losses in step order (synchronises)."""
         torch.cuda.synchronize()
-        if not (self.opti.barrier_ok() and self.opti.p2p_ok()):
-            raise RuntimeError("cgs_b200: a CTA of the whole-step kernel timed out at its grid barrier / waiting for a peer")
-        n = min(self.i, self.loss_ring.numel())
-        return self.loss_ring[:n].clone()
+        self.opti.check()
+        R = self.loss_ring.numel()
+        if self.i <= R:
+            return self.loss_ring[:self.i].clone()
+        r = self.i % R
+        return torch.cat((self.loss_ring[r:], self.loss_ring[:r]))

@@ -69,7 +69,8 @@ class NewCritic(nn.Module):
         self._rng_state = None
         self._rng_seed = 0
         NewCritic._count = getattr(NewCritic, "_count", 0) + 1
-        self._instance = NewCritic._count          # distinct, construction-order-deterministic Philox key per module
+        self._instance = NewCritic._count          # distinct Philox stream per module (Handler pins it per role) ...
+        self._rank = 0                             # ... and per data-parallel rank
         self._forced_masks = None   # test hook: (m_e2 [B,8,8,8c], m_e3 [B,4,4,16c], m_v [B,32c]) NHWC
 
     def _dropout_masks(self, B, device):
@@ -88,8 +89,11 @@ class NewCritic(nn.Module):
         if self._rng_state is None or self._rng_state.device != device:
             # Philox stream keyed by torch's seed (torch.manual_seed reproducible), advanced on the device
             self._rng_state = torch.zeros(2, dtype=torch.int64, device=device)
-            self._rng_seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._instance) & 0x7FFFFFFFFFFFFFFF
+            self._rng_seed = self._philox_key()
         return tuple(ops.dropout_masks([(B, 8, 8, c2), (B, 4, 4, c3), (B, nb)], self.p, self._rng_seed, self._rng_state))
+
+    def _philox_key(self):
+        return (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._instance + 0x632BE59BD9B4E019 * self._rank) & 0x7FFFFFFFFFFFFFFF
 
     def _dropout_rng(self, device):
         """(p, seed, state) of this module's Philox stream when the masks can be drawn inside a fused kernel (train mode,
@@ -98,7 +102,7 @@ class NewCritic(nn.Module):
             return None
         if self._rng_state is None or self._rng_state.device != device:
             self._rng_state = torch.zeros(2, dtype=torch.int64, device=device)
-            self._rng_seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._instance) & 0x7FFFFFFFFFFFFFFF
+            self._rng_seed = self._philox_key()
         return self.p, self._rng_seed, self._rng_state
 
     def forward(self, X, collect=False):

@@ -588,13 +588,17 @@ def critic_loss_xgrad(critic, x_nhwc, target, masks=(None, None, None), rng=None
 
 def critic_saliency(critic, x_nhwc):
     """The saliency baseline of Handler.eval (reference main.py:945-951): `pred.mean().backward(); batch.grad.abs().sum(1)` for
-    fp32 NHWC frames, forward and input gradient in ONE kernel.  Returns (pred [B], saliency [B,1,64,64])."""
-    x = _c(x_nhwc.detach()).requires_grad_(True)
-    dummy = torch.zeros(x.shape[0], device=x.device, dtype=torch.float32)
-    with torch.enable_grad():
-        loss = CriticLossXGrad.apply(x, dummy, critic, (None, None, None), None, 2)
-    (g,) = torch.autograd.grad(loss, x)
-    return None, g.abs().sum(dim=3).unsqueeze(1)
+    fp32 NHWC frames, forward and input gradient in ONE kernel.  Returns (pred [B,1], saliency [B,1,64,64])."""
+    x = _c(x_nhwc.detach())
+    B = x.shape[0]
+    w = _lib.CriticWeights(*[_p(q.detach()) for q in critic.parameters()])
+    pred = torch.empty(B, device=x.device, dtype=torch.float32)
+    loss = torch.empty(1, device=x.device, dtype=torch.float32)
+    dx = torch.empty_like(x)
+    dummy = torch.zeros(B, device=x.device, dtype=torch.float32)
+    _call("cgs_critic_loss_xgrad", _p(x), _p(dummy), B, None, None, None, 0.0, 0, None, C.byref(w), 1.0, 2, _p(pred), _p(loss),
+          _p(dx), _stream())
+    return pred.unsqueeze(1), dx.abs().sum(dim=3).unsqueeze(1)
 
 
 def critic_forward_fused(critic, x_nhwc, masks=(None, None, None), rng=None):

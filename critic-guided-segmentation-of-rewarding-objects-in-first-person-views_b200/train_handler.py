@@ -8,8 +8,10 @@ contrastive sampling), checkpoint paths and state_dict layout as the reference; 
 arithmetic runs in libcgs_b200.so.  Visualisation, MineRL collection, CRF and video
 output are out of scope.
 
-Data-parallel: one process per GPU; every rank runs the same loop on its batch shard
-and `FlatAdam` all-reduces the flat gradient bucket (NCCL) before the update.
+Data-parallel: one process per GPU; every rank runs the same loop on its batch shard and the
+flat gradient bucket is summed over ranks before the update: inside the whole-step kernel over
+NVLink peer memory (critic step), by `cgs_p2p_allreduce_adam` (other buckets), or by an NCCL
+all-reduce when symmetric memory is unavailable.  Rank 0's initial parameters are broadcast.
 """
 import argparse
 import math
@@ -92,6 +94,10 @@ class FlatAdam:
                 off += k
         self.lr, self.betas, self.eps = lr, betas, eps
         self.group, self.world = process_group, world_size
+        if world_size > 1:
+            # every rank must start from rank 0's parameters whatever its own seed / checkpoint state was
+            torch.distributed.broadcast(self.flat, src=torch.distributed.get_global_rank(process_group, 0)
+                                        if process_group is not None else 0, group=process_group)
         # gradient handed over by the whole-step critic kernel as per-CTA partial vectors (ops.critic_train_fused):
         # (buffer, rows, row stride, bucket offset, length), summed in step() instead of RED-accumulated by the kernel
         self.pending_partials = None
@@ -132,6 +138,15 @@ class FlatAdam:
         except Exception as e:          # no peer access / fabric handles on this system: NCCL carries the bucket instead
             print(f"cgs_b200: symmetric-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL")
             return None
+
+    def check(self):
+        """Raise if any bounded device-side wait of this optimizer's kernels ever timed out (grid barrier / peer gradient
+        of the whole-step kernel, peer announcement of cgs_p2p_allreduce_adam) or the tcgen05 kernels flagged an mbarrier
+        time-out: the kernels skip the affected updates, so the last checkpoint is still good, but training must stop."""
+        from . import _lib
+        if self.flat.is_cuda and not (self.barrier_ok() and self.p2p_ok() and _lib.lib().cgs_tc_status() == 0):
+            raise RuntimeError("cgs_b200: a device-side wait timed out (grid barrier / peer gradient / tcgen05 mbarrier): "
+                               "the affected parameter updates were skipped; the optimizer state is not trustworthy")
 
     def p2p_ok(self):
         """False if a peer ever failed to announce its gradient in time (reads a device flag; synchronises)."""
@@ -243,8 +258,27 @@ class Handler:
         a = self.args
         self.critic = NewCritic(bottleneck=a.neck, chfak=a.chfak, dropout=a.dropout)      # main.py:108
         self.masker = UnetDecoder(bottleneck=a.neck, chfak=a.chfak)                       # main.py:109
+        # dropout Philox keys: a fixed stream index per role (NOT the process-global construction count, so a second
+        # reset_models() replays the same stream for the same seed) and the rank, so that data-parallel ranks draw
+        # different masks for their shards
+        self.critic._instance, self.critic._rank = 1, self.rank
         if a.separate:
             self.sepcrit = NewCritic(bottleneck=a.neck, chfak=a.chfak, dropout=a.dropout)  # main.py:111
+            self.sepcrit._instance, self.sepcrit._rank = 2, self.rank
+        if self.world > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
+            self._check_shared_seed()
+
+    def _check_shared_seed(self):
+        """The DataLoader shuffle, the shift_batch draws (torch RNG) and the contrastive sampling (numpy RNG) must be the
+        same on every rank, or the ranks would shard different global batches: require a common torch seed."""
+        import torch.distributed as dist
+        mine = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64,
+                            device=self.device if self.device.type == "cuda" else "cpu")
+        seeds = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(seeds, mine, group=self.group)
+        if any(int(s) != int(mine) for s in seeds):
+            raise RuntimeError("cgs_b200: data-parallel ranks were seeded differently "
+                               f"({[int(s) for s in seeds]}): call torch.manual_seed(same) on every rank before Handler()")
 
     # ------------------------------------------------------------------ data / checkpoints
     def set_data(self, X, Y, I=None, batch_size=64, shuffle=True):
@@ -294,14 +328,31 @@ class Handler:
         return ops.frames_to_float(x, roll).permute(0, 3, 1, 2)
 
     def _shard(self, n):
-        """This rank's slice of a global batch of n."""
-        per = math.ceil(n / self.world)
-        return slice(self.rank * per, min(n, (self.rank + 1) * per))
+        """This rank's slice of a global batch of n: balanced (sizes differ by at most one) and never empty.  A batch
+        smaller than the world size is processed whole by every rank (the mean over ranks of identical gradients is the
+        global-batch gradient), so no rank ever sits out a collective."""
+        if n < self.world:
+            return slice(0, n)
+        q, r = divmod(n, self.world)
+        lo = self.rank * q + min(self.rank, r)
+        return slice(lo, lo + q + (1 if self.rank < r else 0))
+
+    def _shard_weight(self, n):
+        """d(global mean loss) / d(this rank's local mean loss) = B_local / B_global (1/world for a replicated batch):
+        the gradient sum over ranks is then the reference's global-batch mean gradient even for ragged shards."""
+        if self.world == 1:
+            return 1.0
+        if n < self.world:
+            return 1.0 / self.world
+        sl = self._shard(n)
+        return (sl.stop - sl.start) / n
 
     # ------------------------------------------------------------------ critic regression
-    def critic_step(self, X_u8, Y, opti, roll=0):
-        """Loop body of critic_pipe (main.py:185-200) on this rank's shard; returns the loss tensor."""
+    def critic_step(self, X_u8, Y, opti, roll=0, weight=None):
+        """Loop body of critic_pipe (main.py:185-200) on this rank's shard; returns the loss tensor.  `weight` =
+        B_local / B_global (default 1/world: equal shards)."""
         a = self.args
+        weight = (1.0 / self.world) if weight is None else float(weight)
         x = X_u8 if torch.is_tensor(X_u8) else torch.from_numpy(np.ascontiguousarray(X_u8))
         x = x.to(self.device, non_blocking=True)
         Yd = Y.to(self.device, non_blocking=True).float()
@@ -311,14 +362,14 @@ class Handler:
             masks = (None, None, None) if rng is not None else self.critic._dropout_masks(x.shape[0], x.device)   # ... or forced / none
             opti.zero_grad()
             loss, _ = ops.critic_train_fused(self.critic, x.contiguous(), Yd.contiguous(), roll, masks,
-                                             loss_grad=1.0 / self.world, bce=bool(a.threshrew), rng=rng,
+                                             loss_grad=weight, bce=bool(a.threshrew), rng=rng,
                                              fuse_adam=bool(getattr(opti, "_clean", False)))
             opti.step()
             return loss
         pred = self.critic.forward_frames(x, roll).squeeze(1)     # cast + roll fused into features.0's operand load
         loss = ops.pred_loss(pred, Yd, bce=bool(a.threshrew))
         opti.zero_grad()
-        (loss / self.world if self.world > 1 else loss).backward()
+        (loss * weight if self.world > 1 else loss).backward()
         opti.step()
         return loss.detach()
 
@@ -333,14 +384,13 @@ class Handler:
             for b_idx, (X, Y, I) in enumerate(self.train_loader):
                 roll = self._shift_roll() if a.shift else 0
                 sl = self._shard(len(X))
-                loss = self.critic_step(X[sl], Y[sl, a.rewidx], opti, roll)
+                loss = self.critic_step(X[sl], Y[sl, a.rewidx], opti, roll, weight=self._shard_weight(len(X)))
                 self.closs_log.append(loss)
             if not (epoch + 1) % a.saveevery:
+                opti.check()                     # never checkpoint past a skipped update
                 self.save_models([self.criticname])
         self.closs_log = [float(v) for v in torch.stack(self.closs_log).cpu()] if self.closs_log else []
-        if not (opti.barrier_ok() and opti.p2p_ok()):
-            raise RuntimeError("cgs_b200: a CTA of the whole-step kernel timed out at its grid barrier / waiting for a peer's "
-                               "gradient during critic_pipe: the optimizer state is not trustworthy")
+        opti.check()
 
     # ------------------------------------------------------------------ pos / neg split
     def extract_contrastive_data(self):
@@ -418,13 +468,14 @@ class Handler:
             loss = loss + terms["L2"]
         return loss, terms, Z
 
-    def segmentation_step(self, X_u8, CX_u8, Y, opti, roll=0):
+    def segmentation_step(self, X_u8, CX_u8, Y, opti, roll=0, weight=None):
+        weight = (1.0 / self.world) if weight is None else float(weight)
         A = self._to_input(X_u8, roll)
         B = self._to_input(CX_u8)
         Yd = None if Y is None else Y.to(self.device).float()
         loss, terms, _ = self.segmentation_losses(A, B, Yd)
         opti.zero_grad()
-        (loss / self.world if self.world > 1 else loss).backward()
+        (loss * weight if self.world > 1 else loss).backward()
         opti.step()
         return {k: v.detach() for k, v in terms.items()}
 
@@ -451,9 +502,12 @@ class Handler:
                     CX = self.Xneg[Cidx]
                     roll = self._shift_roll() if a.shift else 0
                     sl = self._shard(len(X))
-                    self.seg_log.append(self.segmentation_step(X[sl], CX[sl], Y[sl], opti, roll))
+                    self.seg_log.append(self.segmentation_step(X[sl], CX[sl], Y[sl], opti, roll,
+                                                               weight=self._shard_weight(len(X))))
                 if not (epoch + 1) % a.saveevery:
+                    opti.check()
                     self.save_models([self.maskername])
+            opti.check()
         finally:
             if not a.live:
                 for p in critic.parameters():

@@ -1,15 +1,21 @@
 """ORACLE — TEST INFRASTRUCTURE ONLY (authoring container only).
 
-Imports the UNMODIFIED reference (`/root/reference/nets.py`, `main.py`) under the
-shim list of SURVEY.md §8c so its own classes can generate golden vectors.
-`/root/reference` does not exist on the GPU box: nothing that runs there may
-import this module (tests skip when the mount is absent).
+Imports the UNMODIFIED reference (`nets.py`, `main.py`) under the shim list of
+SURVEY.md §8c so its own classes can generate golden vectors, be timed by
+`bench.py --impl reference`, and run their loops on swapped-in classes
+(tests/test_gpu_boundary.py).  Source: `/root/reference` in the authoring container,
+else the byte-identical copies `oracle/make_ref.py` put into the git-ignored
+`oracle/_ref/` (which travels to the GPU box with the snapshot).  Never imported
+by the product package.
 """
 import os
 import sys
 import types
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("CGS_REFERENCE", "/root/reference")
+if not os.path.isfile(os.path.join(REF, "nets.py")):
+    REF = os.path.join(_HERE, "_ref")
 
 
 def available():

@@ -96,13 +96,86 @@ def test_dp_world2_gloo():
 
 
 def test_shards_partition_the_batch():
+    """Balanced, never-empty shards (ceil(n/world) left ranks empty on ragged DataLoader tails) whose
+    B_local/B_global weights make the rank-summed gradient the global-batch mean."""
     import sys
     sys.path.insert(0, ROOT)
     from cgs_b200.train_handler import Handler, parse_args
     for world in (1, 2, 4, 8):
-        for n in (64, 128, 8192, 10):
-            covered = []
-            for r in range(world):
-                sl = Handler(parse_args([]), device="cpu", rank=r, world_size=world)._shard(n)
-                covered += list(range(sl.start, sl.stop))
-            assert covered == list(range(n))
+        hs = [Handler(parse_args([]), device="cpu", rank=r, world_size=world) for r in range(world)]
+        for n in (64, 128, 8192, 10, 65, 129, 9, 6, 5, 3, 2, 1):
+            sls = [h._shard(n) for h in hs]
+            ws = [h._shard_weight(n) for h in hs]
+            assert all(sl.stop > sl.start for sl in sls), (world, n, sls)
+            assert abs(sum(ws) - 1.0) < 1e-12, (world, n, ws)
+            if n >= world:
+                covered = [i for sl in sls for i in range(sl.start, sl.stop)]
+                assert covered == list(range(n))
+                sizes = [sl.stop - sl.start for sl in sls]
+                assert max(sizes) - min(sizes) <= 1
+            else:
+                assert all((sl.start, sl.stop) == (0, n) for sl in sls)
+
+
+def _ragged_worker(rank, world, port, out):
+    """Ragged global batch (n = 13 over 2 ranks, then n = 1): weighted shards must reproduce the single-process update."""
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from cgs_b200 import ops
+    from cgs_b200.train_handler import FlatAdam, Handler, parse_args
+    import cgs_b200.synth as synth
+    ops.adam_step = _cpu_adam
+    torch.manual_seed(100 + rank)                  # deliberately different seeds: FlatAdam must broadcast rank 0's parameters
+    from cgs_b200.nets import NewCritic
+    critic = NewCritic(dropout=0.0)
+    opt = FlatAdam(critic.parameters(), process_group=dist.group.WORLD, world_size=world)
+    H = Handler.__new__(Handler)
+    H.rank, H.world = rank, world
+    X, Y, _ = synth.synthetic_frames(13, seed=4)
+    Yt = torch.from_numpy(Y[1]).float()
+    init = opt.flat.clone()
+    for n in (13, 1):
+        sl, w = H._shard(n), H._shard_weight(n)
+        opt.zero_grad()
+        _, gs = _grads(critic, X[:n][sl], Yt[:n][sl], w)
+        for p, g in zip(critic.parameters(), gs):
+            p.grad.add_(g)
+        opt.step()
+    flats = [torch.zeros_like(opt.flat) for _ in range(world)]
+    inits = [torch.zeros_like(init) for _ in range(world)]
+    dist.all_gather(flats, opt.flat.clone())
+    dist.all_gather(inits, init)
+    if rank == 0:
+        c1 = NewCritic(dropout=0.0)
+        o1 = FlatAdam(c1.parameters())
+        o1.flat.copy_(init)
+        for n in (13, 1):
+            o1.zero_grad()
+            _, gs = _grads(c1, X[:n], Yt[:n], 1.0)
+            for p, g in zip(c1.parameters(), gs):
+                p.grad.add_(g)
+            o1.step()
+        out.put(dict(same_init=bool(all(torch.equal(inits[0], t) for t in inits)),
+                     same=bool(all(torch.equal(flats[0], t) for t in flats)),
+                     err=float((opt.flat - o1.flat).abs().max()), scale=float(o1.flat.abs().max())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_ragged_batch_and_broadcast_gloo():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_ragged_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res["same_init"], "FlatAdam did not broadcast rank 0's initial parameters"
+    assert res["same"], "ranks diverged on a ragged batch"
+    assert res["err"] <= 2e-6 * max(res["scale"], 1.0), res

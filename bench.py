@@ -1,16 +1,23 @@
 #!/usr/bin/env python
 """bench.py — frames/s of the Critic/Hourglass hot path on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload critic_train|hourglass|infer]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload all|hourglass|critic_train|infer]
 
-Default workload (BASELINE.json configs[1], the configuration the metric is quoted on): one critic
-training step (uint8->float, NewCritic fwd with dropout, MSE, backward, Adam) on synthetic 64x64x3
-frames with sparse-reward labels, batch 256 per GPU (weak scaling).  A "step" is one such pass.
-  value : whole-job frames/s with inputs resident in HBM (CUDA-graph replay, CUDA-event timed,
-          L2 flushed between timed iterations)
-  e2e   : the same step through the public API with pinned HOST uint8 frames + labels: H2D copies
-          and a D2H read of the loss inside the timed region
-`--impl reference` times the reference's CPU path (oracle port, all host threads) on the same config.
+BASELINE.json's metric is "Hourglass+critic train frames/s & mask-infer frames/s": the default run (`--workload all`)
+measures all three workloads and prints ONE JSON line whose headline (`value`, `e2e`, `roofline`, `cpu_baseline`) is
+the critic-guided Hourglass training step (configs[2]: frozen critic, inject, L1, batch 1024 per GPU — the largest
+single-GPU configuration) and whose `workloads` object carries the same four fields for the critic training step
+(configs[1], batch 256) and `-process` mask inference (configs[0], batch 256, threshold 0.1); `infer_sweep` holds the
+batch 1k-64k inference sweep (configs[4]).  A "step" is one pass of the workload over one synthetic batch.
+
+  value : whole-job frames/s with inputs resident in HBM: blocks of K back-to-back steps (CUDA-graph replays over a
+          rotation of distinct resident batches larger than the 126 MB L2), one CUDA-event pair per block, the block
+          repeated until the timed region is >= 200 ms; the MEDIAN block is reported (`repeats`, `timed_region_ms`)
+  e2e   : the same steps through the public API from pinned HOST uint8 frames: H2D copy of every step's inputs and a D2H
+          read of every step's result inside the timed region (double-buffered pipeline, >= 250 ms, independent of K)
+`--impl reference` times the reference's own classes (oracle/_ref: unmodified nets.py, loop bodies of main.py) on the
+host cores for the same configs; under torchrun only rank 0 works.
 """
 import argparse
 import json
@@ -26,23 +33,35 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
-METRIC = "critic_train_frames_per_s"
+METRIC = "hourglass_critic_train_and_mask_infer_frames_per_s"
+UNIT = "frames/s"
 WORKLOADS = {
+    "hourglass": "critic-guided Hourglass training step, frozen critic, inject, L1 0.5, batch 1024/GPU (BASELINE configs[2])",
     "critic_train": "critic training step, batch 256/GPU, synthetic 64x64x3 uint8 frames + sparse-reward labels (BASELINE configs[1])",
-    "hourglass": "critic-guided Hourglass step, frozen critic, inject, L1, batch 1024/GPU (BASELINE configs[2])",
     "infer": "mask inference (-process path, threshold 0.1), batch 256/GPU (BASELINE configs[0])",
 }
+DEFAULT_BATCH = {"hourglass": 1024, "critic_train": 256, "infer": 256}
 # SURVEY.md §8d / BASELINE.md: algorithmic FLOPs per frame (2*MAC, conv+linear), chfak 1 | 5
 FLOPS = {"critic_train": {1: 8460480, 5: 140729280}, "hourglass": {1: 67944832, 5: 665240704},
          "infer": {1: 20959296, 5: 186601792}}
+MIN_REGION_S = 0.2
+L2_BYTES = 126 * 2 ** 20
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d["hbm_gbs"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
-    return 6650.0, 1590.0, "fallback"
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    which="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1590.0, which="fallback (B200_PROFILING.md)")
+
+
+def config_of(workload, B, world, chfak):
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOADS[workload], "batch_per_gpu": B, "global_batch": B * world, "chfak": chfak,
+            "parallelism": f"dp{world}", "frame": "64x64x3 uint8",
+            "l2": "steps rotate over distinct resident batches whose total size exceeds the 126 MB L2"}
 
 
 class ClockSampler:
@@ -65,9 +84,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, windows=()):
+        """Median SM clock over the samples that fall inside the timed windows [(t0, t1), ...] (all samples if none do)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -75,8 +98,10 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        inside = [r for t, r in self.rows if any(a <= t <= b for a, b in windows)]
+        rows = inside or [r for _, r in self.rows]
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
             except Exception:
@@ -85,7 +110,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "samples_in_timed_regions": len(inside)}
 
 
 def make_batch(workload, B, seed):
@@ -95,17 +120,68 @@ def make_batch(workload, B, seed):
 
 
 # --------------------------------------------------------------------------- reference arm (CPU)
-def oracle_step_fn(workload, chfak, B):
-    """The reference's CPU path restated by the oracle (reference classes are not on the GPU box)."""
-    from oracle import torch_ref
+def reference_step_fn(workload, chfak, B):
+    """One step of the workload on the host CPU -> (step(), kind, description).  kind "reference": the unmodified
+    reference classes from oracle/_ref (nets.NewCritic / nets.UnetDecoder) driven by the loop bodies of main.py
+    (critic_pipe :185-200, segmentation_training :344-463, segment :1139-1164); kind "port": the oracle restatement
+    (oracle/torch_ref.py) when oracle/_ref is not present.  Synthetic data and weights of the same recipe as the GPU arm."""
+    import torch.nn.functional as F
     import cgs_b200.synth as synth
+    from oracle import ref_shims, torch_ref
     torch.manual_seed(0)
     p = 0.3
-    csd = {k: torch.from_numpy(v).requires_grad_(True) for k, v in synth.perturbed_state(synth.critic_shapes(chfak), 0).items()}
-    msd = {k: torch.from_numpy(v).requires_grad_(True) for k, v in synth.perturbed_state(synth.masker_shapes(chfak), 1).items()}
+    csd = synth.perturbed_state(synth.critic_shapes(chfak), 0)
+    msd = synth.perturbed_state(synth.masker_shapes(chfak), 1)
     X, Y = make_batch(workload, B, 0)
     Xt = torch.from_numpy(X)
     Yt = torch.from_numpy(Y[1, :B]).float()
+    if ref_shims.available():
+        nets, _ = ref_shims.load()
+        critic = nets.NewCritic(bottleneck=32, chfak=chfak, dropout=p)          # main.py:108
+        masker = nets.UnetDecoder(bottleneck=32, chfak=chfak)                   # main.py:109
+        critic.load_state_dict({k: torch.from_numpy(v) for k, v in csd.items()})
+        masker.load_state_dict({k: torch.from_numpy(v) for k, v in msd.items()})
+        kind, desc = "reference", "unmodified reference nets.py classes (oracle/_ref), main.py loop body, torch %s CPU fp32" % torch.__version__
+        if workload == "critic_train":
+            critic.train()
+            opt = torch.optim.Adam(critic.parameters())                         # main.py:178
+
+            def step():
+                XP = Xt.permute(0, 3, 1, 2).float() / 255.0                     # main.py:189
+                pred = critic(XP).squeeze()
+                loss = F.mse_loss(pred, Yt)                                     # main.py:195
+                opt.zero_grad(); loss.backward(); opt.step()                    # main.py:196-198
+                return loss.item()
+        elif workload == "hourglass":
+            critic.train(); masker.train()
+            opt = torch.optim.Adam(masker.parameters())                         # main.py:334 (-frozen)
+
+            def step():
+                A = Xt[:B].permute(0, 3, 1, 2).float() / 255.0                  # main.py:360-361
+                Bf = Xt[B:].permute(0, 3, 1, 2).float() / 255.0
+                pred, embeds = critic(A, collect=True)                          # main.py:364
+                negpred = critic(Bf)
+                pred = pred.squeeze(); negpred = negpred.squeeze().detach()
+                Z = masker(A, embeds)                                           # main.py:391
+                replaced = A * (1 - Z) + Z * Bf                                 # main.py:395
+                loss = F.mse_loss(critic(replaced).squeeze(), negpred.detach())
+                injected = Bf * (1 - Z) + Z * A                                 # main.py:406
+                loss = loss + F.mse_loss(critic(injected).squeeze(), pred.detach())
+                loss = loss + 0.5 * F.l1_loss(Z, torch.zeros_like(Z))           # main.py:422 (staticnorm)
+                opt.zero_grad(); loss.backward(); opt.step()                    # main.py:460-462
+                return loss.item()
+        else:
+            critic.eval(); masker.eval()                                        # main.py:1128-1129
+
+            def step():
+                batch = torch.from_numpy(X / 255.0).permute(0, 3, 1, 2).float()  # main.py:1134-1136
+                pred, embeds = critic(batch, collect=True)                      # main.py:1139 (autograd on, as the reference)
+                mask = masker(batch, embeds)                                    # main.py:1150
+                hard = mask >= 0.1                                              # main.py:1164
+                return float(hard.sum())
+        return step, kind, desc
+    csd = {k: torch.from_numpy(v).requires_grad_(True) for k, v in csd.items()}
+    msd = {k: torch.from_numpy(v).requires_grad_(True) for k, v in msd.items()}
     c = chfak
     drop = lambda: tuple(torch.nn.functional.dropout(torch.ones(s), p, True)
                          for s in ((B, 8 * c, 8, 8), (B, 16 * c, 4, 4), (B, 32 * c)))
@@ -132,139 +208,319 @@ def oracle_step_fn(workload, chfak, B):
             batch = (torch.from_numpy(X / 255.0)).permute(0, 3, 1, 2).float()
             pred, mask, hard = torch_ref.segment_batch(csd, msd, batch, 0.1)   # autograd on, as main.py:1139
             return float(mask.detach().numpy().sum())
-    return step
+    return step, "port", "oracle/torch_ref.py restatement, torch %s CPU fp32" % torch.__version__
 
 
-def run_reference(args, rank):
-    if rank != 0:
-        return
+def cpu_arm(workload, chfak, B, steps, warmup, budget_s=None):
+    """Times the CPU arm: `steps` steps (or as many as fit `budget_s`, at least 2) of batch B on all host cores."""
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    B = args.batch
-    step = oracle_step_fn(args.workload, args.chfak, B)
-    for _ in range(args.warmup):
+    step, kind, desc = reference_step_fn(workload, chfak, B)
+    for _ in range(warmup):
         step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
+    n, t0 = 0, time.perf_counter()
+    while n < steps and (budget_s is None or n < 2 or time.perf_counter() - t0 < budget_s):
+        step(); n += 1
     dt = time.perf_counter() - t0
-    v = B * args.steps / dt
-    line = {"metric": METRIC if args.workload == "critic_train" else args.workload + "_frames_per_s", "value": v,
-            "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOADS[args.workload], "batch_per_step": B, "chfak": args.chfak},
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{args.steps} full steps of batch {B} (oracle/torch_ref.py, torch {torch.__version__} CPU fp32)"},
-            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    return {"value": B * n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{n} full steps of batch {B} in {dt:.1f} s ({desc})"}, 1e3 * dt / n, n
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    names = list(WORKLOADS) if args.workload == "all" else [args.workload]
+    recs = {}
+    for name in names:
+        B = args.batch or DEFAULT_BATCH[name]
+        # a step of this arm = one full batch of the workload; the number of timed steps is bounded so that the whole
+        # run stays within a few minutes on the host (hourglass at batch 1024 is ~1-2 s per step on 16 cores)
+        budget = 60.0 if name == "hourglass" else 25.0
+        cb, ms, n = cpu_arm(name, args.chfak, B, args.steps, min(args.warmup, 2), budget_s=budget)
+        recs[name] = {"value": cb["value"], "unit": UNIT, "ms_per_step": ms, "steps_timed": n, "config": config_of(name, B, world, args.chfak),
+                      "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    head = recs[names[0]]
+    line = {"metric": METRIC if args.workload == "all" else args.workload + "_frames_per_s", "value": head["value"], "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference", "config": head["config"], "cpu_baseline": head["cpu_baseline"], "e2e": head["e2e"],
+            "steps_timed": head["steps_timed"]}
+    if len(names) > 1:
+        line["workloads"] = {k: v for k, v in recs.items() if k != names[0]}
     print(json.dumps(line))
 
 
 # --------------------------------------------------------------------------- our arm (GPU)
-def time_kernel(fn, flush, iters=20):
-    """Average device time of one launch: CUDA events on the launch stream, L2 flushed in between."""
-    for _ in range(3):
-        fn()
+def kernel_flops(entry, B, chfak=1):
+    """Algorithmic FLOPs (2*MAC) one launch of a C-ABI entry point performs on B frames, chfak 1.
+    Layer MACs per frame: features.0 884,736; .3 589,824; .6 147,456; .10 73,728; .14 + crit 9,248;
+    dec[4] 1,024; dec[3] 110,592; dec[2] 110,592; dec[1] 294,912; dec[0] 1,179,648; masker.0 6,488,064; masker.2 589,824."""
+    if chfak != 1:
+        return None
+    cf = 884736 + 589824 + 147456 + 73728 + 9248                       # critic forward
+    cb = cf - 884736                                                   # its dgrads (no input gradient for features.0) ...
+    dec = 1024 + 110592 + 110592 + 294912 + 1179648
+    msk = 6488064 + 589824
+    per = {
+        "cgs_critic_train_fused": cf + cb + cf,                        # fprop + dgrad + wgrad = 8,460,480 / 2
+        "cgs_critic_loss_xgrad": cf + cf,                              # fprop + full input gradient (incl. features.0 dgrad)
+        "cgs_infer_fused": cf + dec,
+        "cgs_masker_fused": msk,
+        "cgs_hg_forward": cf + dec + msk,
+        "cgs_hg_score": 2 * (cf + cf),                                 # replaced + injected: fprop + input gradient each
+        "cgs_hg_backward": 2 * (dec + msk) - 884736 * 0,               # wgrad + dgrad of decoder and masker
+        "cgs_process_fused": cf + dec + msk,
+    }
+    m = per.get(entry)
+    return None if m is None else 2 * m * B
+
+
+def time_blocks(run_block, K, sync, world, dev):
+    """R blocks of K steps, one CUDA-event pair per block, R chosen so that the timed region is >= MIN_REGION_S.
+    Returns (median block seconds [max over ranks], R, total seconds, wall window)."""
+    import torch.distributed as dist
+    sync()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(); run_block(); e.record()
+    sync()
+    est = max(s.elapsed_time(e) * 1e-3, 1e-6)
+    R = int(min(max(1, -(-MIN_REGION_S // est)), 4000))
+    if world > 1:
+        r = torch.tensor([R], device=dev)
+        dist.all_reduce(r, op=dist.ReduceOp.MAX)
+        R = int(r.item())
     evs = []
-    for _ in range(iters):
-        flush.zero_()
+    sync()
+    w0 = time.perf_counter()
+    for _ in range(R):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record(); fn(); e.record()
+        s.record(); run_block(); e.record()
         evs.append((s, e))
-    torch.cuda.synchronize()
-    return float(np.mean([s.elapsed_time(e) for s, e in evs])) * 1e-3
+    sync()
+    w1 = time.perf_counter()
+    t = torch.tensor([a.elapsed_time(b) * 1e-3 for a, b in evs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)          # per block: the slowest rank
+    return float(t.median().item()), R, float(t.sum().item()), (w0, w1)
 
 
-def kernel_rooflines(B, chfak, flush, hbm_gbs):
-    """Dominant-kernel candidates of the critic step, timed in isolation."""
+def bench_workload(name, args, rank, world, dev, group, sampler_windows):
+    """One workload on this rank's GPU -> record dict (rank 0's is printed)."""
+    import torch.distributed as dist
     from cgs_b200 import ops
-    from cgs_b200._lib import SRC_PLAIN, SRC_POOLBWD, EPI_RELU_POOL
-    dev = "cuda"
-    c = chfak
+    from cgs_b200.graph_step import (GraphedCriticStep, GraphedHourglassStep, GraphedSegment, HostPipeline,
+                                     PipelinedCriticTrainer, _capture, _train_state)
+    from cgs_b200.train_handler import Handler, parse_args
+    B, W, K = args.batch or DEFAULT_BATCH[name], max(args.warmup, 3), args.steps
+    ops.set_precision(args.precision)
+    hargs = parse_args(["--chfak", str(args.chfak)] + (["-frozen"] if name == "hourglass" else []))
+    torch.manual_seed(0)
+    H = Handler(hargs, device=dev, rank=rank, world_size=world, process_group=group)
+    H.critic.to(dev); H.masker.to(dev)
+    X, Y = make_batch(name, B, seed=rank)
+    sync = (lambda: (dist.barrier(), torch.cuda.synchronize())) if world > 1 else torch.cuda.synchronize
+    frame_bytes = B * 12288 * (2 if name == "hourglass" else 1)
+    nrot = max(2, -(-int(1.3 * L2_BYTES) // frame_bytes))                # distinct resident batches: > L2 in total
+    spg = 1 if name == "hourglass" else max(d for d in (8, 4, 2, 1) if K % d == 0)   # steps captured per graph launch
+    nrot = -(-nrot // spg) * spg
+    Yb = Y[1, :B].astype(np.float32)
+    launches_per_step = 0
+    if name == "critic_train":
+        Xrot = torch.stack([torch.from_numpy(np.roll(X, 7 * r + 1, axis=0)) for r in range(nrot)]).to(dev)
+        Yrot = torch.stack([torch.from_numpy(np.roll(Yb, 7 * r + 1)) for r in range(nrot)]).to(dev)
+        base = GraphedCriticStep(H, B)
+        opti, launches_per_step = base.opti, base.launches
+        roll0 = torch.zeros(1, dtype=torch.int32, device=dev)
+        graphs = [_capture(lambda r0=r0: torch.stack([H.critic_step(Xrot[r0 + k], Yrot[r0 + k], opti, roll=roll0) for k in range(spg)]),
+                           warmup=1, state=_train_state(opti, H.critic))[0] for r0 in range(0, nrot, spg)]
+        trains = True
+    elif name == "hourglass":
+        Xrot = torch.stack([torch.from_numpy(np.roll(X, 7 * r + 1, axis=0)) for r in range(nrot)]).to(dev)
+        Yrot = torch.stack([torch.from_numpy(np.roll(Yb, 7 * r + 1)) for r in range(nrot)]).to(dev)
+        steps = [GraphedHourglassStep(H, B, X=Xrot[0, :B], CX=Xrot[0, B:], Y=Yrot[0])]
+        opti = steps[0].opti
+        steps += [GraphedHourglassStep(H, B, opti, X=Xrot[r, :B], CX=Xrot[r, B:], Y=Yrot[r], warmup=1) for r in range(1, nrot)]
+        graphs, launches_per_step, trains = [s.graph for s in steps], steps[0].launches, True
+    else:
+        Xrot = torch.stack([torch.from_numpy(np.roll(X, 7 * r + 1, axis=0)) for r in range(nrot)]).to(dev)
+        H.critic.eval(); H.masker.eval()
+        segs = [GraphedSegment(H, B, 0.1, X=Xrot[r]) for r in range(nrot)]
+        graphs, launches_per_step, trains, spg = [s.graph for s in segs], segs[0].launches, False, 1
+    cursor = [0]
+
+    def run_block():
+        for _ in range(K // spg):
+            graphs[cursor[0] % len(graphs)].replay()
+            cursor[0] += 1
+    Kb = (K // spg) * spg
+    for _ in range(max(1, -(-W // spg))):
+        graphs[cursor[0] % len(graphs)].replay(); cursor[0] += 1
+    block_s, R, region_s, win = time_blocks(run_block, K, sync, world, dev)
+    sampler_windows.append(win)
+    if trains:
+        ops.weights_changed()
+        opti.check()
+    value = world * B * Kb / block_s
+    rec = {"value": value, "unit": UNIT, "ms_per_step": 1e3 * block_s / Kb, "repeats": R, "timed_region_ms": 1e3 * region_s,
+           "steps_per_block": Kb, "config": config_of(name, B, world, args.chfak),
+           "timing": (f"median of {R} blocks of {Kb} back-to-back steps (one cuda-event pair per block, {spg} step(s) per graph "
+                      f"launch) over {nrot} distinct resident batches ({nrot * frame_bytes >> 20} MiB of frames > 126 MB L2)"),
+           "launches_per_step": launches_per_step, "gpu_launches": launches_per_step * Kb * R,
+           "achieved_tflops": FLOPS[name].get(args.chfak, 0) * value / 1e12}
+
+    # ---- e2e: pinned host buffers -> H2D -> step -> D2H of the step's result, every step, through the public API
+    if name == "critic_train":
+        trainer = PipelinedCriticTrainer(H, B)
+        chunk = 16                                        # steps per H2D copy / graph launch (48 MB at batch 256): fixed
+        nb = 2 * chunk
+        Xds = torch.from_numpy(np.concatenate([X] * nb)).pin_memory()
+        Yds = torch.from_numpy(np.tile(Yb, nb)).pin_memory()
+        run_e2e = lambda: trainer.train(Xds, Yds, chunk=chunk)        # nb steps
+        finish = lambda: trainer.losses()
+        steps_per_call, h2d, d2h = nb, B * 12288 + B * 4, 4
+    elif name == "hourglass":
+        slots = [GraphedHourglassStep(H, B, opti, warmup=1) for _ in range(2)]
+        pipe = HostPipeline(slots, lambda s: s.out)
+        Xh = [torch.from_numpy(np.roll(X, 3 * r, axis=0)).pin_memory() for r in range(4)]
+        Yh = torch.from_numpy(Yb).pin_memory()
+
+        def run_e2e():
+            for r in range(4):
+                pipe.step(Xh[r][:B], Xh[r][B:], Yh)
+        finish = lambda: pipe.results()
+        steps_per_call, h2d, d2h = 4, 2 * B * 12288 + B * 4, pipe.d2h_bytes
+    else:
+        slots = [GraphedSegment(H, B, 0.1) for _ in range(2)]
+        pipe = HostPipeline(slots, lambda s: s.out[2])                # the thresholded masks (uint8), as -process writes them
+        Xh = [torch.from_numpy(np.roll(X, 3 * r, axis=0)).pin_memory() for r in range(8)]
+
+        def run_e2e():
+            for r in range(8):
+                pipe.step(Xh[r])
+        finish = lambda: pipe.results()
+        steps_per_call, h2d, d2h = 8, B * 12288, pipe.d2h_bytes
+    run_e2e(); finish(); sync()
+    t0 = time.perf_counter(); run_e2e(); finish(); est = max(time.perf_counter() - t0, 1e-5)
+    calls = int(min(max(2, -(-0.25 // est)), 20000))
+    if world > 1:
+        c = torch.tensor([calls], device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.MAX)
+        calls = int(c.item())
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        run_e2e()
+    res = finish()
+    sync()
+    e2e_s = time.perf_counter() - t0
+    sampler_windows.append((t0, t0 + e2e_s))
+    assert torch.isfinite(res.float()).all()
+    if trains:
+        ops.weights_changed()
+        opti.check()
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_steps = calls * steps_per_call
+    rec["e2e"] = {"value": world * B * e2e_steps / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                  "d2h_bytes_per_step": d2h, "steps": e2e_steps, "seconds": float(t.item()),
+                  "how": "double-buffered pinned-host pipeline through cgs_b200.graph_step; every step's inputs cross PCIe and "
+                         "every step's result is read back inside the timed region; step count fixed by time, not by --steps"}
+
+    # ---- DP proof: parameters bit-identical on every rank after the timed regions
+    if world > 1 and trains:
+        flat = opti.flat.clone()
+        ck = torch.stack([flat.double().sum(), flat.double().abs().sum(), (flat.view(torch.int32).long() % 65521).sum().double()])
+        cks = [torch.zeros_like(ck) for _ in range(world)]
+        dist.all_gather(cks, ck)
+        rec["dp_params_equal"] = bool(all(torch.equal(cks[0], c) for c in cks))
+        rec["dp_param_checksums"] = [float(c[2]) for c in cks]
+        assert rec["dp_params_equal"], f"{name}: parameters differ across ranks after training: {cks}"
+
+    # ---- per-kernel shares of one eager step (CUDA events around every C-ABI launch) -> roofline of the dominant kernel
+    if rank == 0 and not args.no_extras:
+        pk = peaks()
+        Xd, Yd = Xrot[0], (Yrot[0] if name != "infer" else None)
+
+        def eager():
+            if name == "critic_train":
+                H.critic_step(Xd, Yd, opti, roll=roll0)
+            elif name == "hourglass":
+                H.segmentation_step(Xd[:B], Xd[B:], Yd, opti)
+            else:
+                with torch.no_grad():
+                    H.segment_device(Xd, 0.1)
+        for _ in range(2):
+            eager()
+        with ops.profile_calls() as prof:
+            for _ in range(5):
+                eager()
+        summ = prof.summary()
+        tot = sum(v[1] for v in summ.values()) or 1.0
+        ks = sorted(({"entry": k, "launches_per_step": n / 5.0, "ms_per_step": ms / 5.0, "share": ms / tot,
+                      "flops_per_launch": kernel_flops(k, B, args.chfak)} for k, (n, ms) in summ.items()), key=lambda d: -d["ms_per_step"])
+        rec["kernels"] = [{a: (round(b, 5) if isinstance(b, float) else b) for a, b in k.items()} for k in ks[:8]]
+        top = ks[0]
+        # live duration of the dominant kernel inside the timed region = its share of the (graph-replayed) step
+        live_us = top["share"] * rec["ms_per_step"] * 1e3 / max(top["launches_per_step"], 1e-9)
+        fl = top["flops_per_launch"]
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        mma_tf32 = sms * 512 * 2 * 1.965e9 / 1e12         # mma.sync m16n8k8 TF32: 2 clk/instr/SM (tools/mma_rate.cu)
+        tj_path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        tj = json.load(open(tj_path)) if os.path.exists(tj_path) else {}
+        if fl:
+            tfl = fl / (live_us * 1e-6) / 1e12
+            rec["roofline"] = {"bound": "tensor", "achieved": tfl, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                               "frac": tfl / pk["tf_sustained"], "traffic": tj.get(f"{top['entry']}@{B}"),
+                               "kernel": top["entry"], "share_of_step": top["share"], "algorithmic_flops": fl,
+                               "launch_us": live_us,
+                               "peak_source": pk["which"] + ": bf16_tflops_sustained (dense tcgen05 bf16, kernel timed inside a long "
+                                              "step); no TF32 peak is measured on this pool - the kernels here are mma.sync "
+                                              "TF32/bf16, whose own issue peak is given below",
+                               "mma_sync_tf32_peak_tflops": mma_tf32, "frac_of_mma_sync_tf32_peak": tfl / mma_tf32,
+                               "mma_sync_bf16_peak_tflops": 2 * mma_tf32, "frac_of_mma_sync_bf16_peak": tfl / (2 * mma_tf32),
+                               "step_frac_of_peak": rec["achieved_tflops"] / world / pk["tf_sustained"]}
+        else:
+            by = B * 12288 * 4
+            rec["roofline"] = {"bound": "hbm", "achieved": by / (live_us * 1e-6) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                               "frac": by / (live_us * 1e-6) / 1e9 / pk["hbm"], "traffic": None, "kernel": top["entry"],
+                               "share_of_step": top["share"], "launch_us": live_us, "peak_source": pk["which"]}
+        if world == 1:
+            cb, _, _ = cpu_arm(name, args.chfak, B, 10 ** 6, 1, budget_s=12.0)
+            rec["cpu_baseline"] = cb
+    return rec
+
+
+def infer_sweep(args, dev):
+    """BASELINE configs[4]: mask inference at batch 1k-64k resident frames (one launch pair per batch), frames/s."""
+    from cgs_b200 import ops
+    from cgs_b200.train_handler import Handler, parse_args
+    import cgs_b200.synth as synth
+    torch.manual_seed(0)
+    H = Handler(parse_args(["--chfak", str(args.chfak)]), device=dev)
+    H.critic.to(dev).eval(); H.masker.to(dev).eval()
+    X, _, _ = synth.synthetic_frames(4096, seed=0)
     out = []
-    for name, H, Cin, Cout in (("features.0", 64, 3, 8 * c), ("features.3", 32, 8 * c, 8 * c)):
-        x = torch.rand(B, H, H, Cin, device=dev)
-        w = torch.rand(Cout, Cin, 3, 3, device=dev) - 0.5
-        b = torch.zeros(Cout, device=dev)
-        e = torch.empty(B, H // 2, H // 2, Cout, device=dev)
-        idx = torch.empty(B, H // 2, H // 2, Cout, device=dev, dtype=torch.uint8)
-        de = torch.rand_like(e)
-        dw, db = torch.zeros_like(w), torch.zeros_like(b)
-        t_f = time_kernel(lambda: ops.conv3x3(ops._src(SRC_PLAIN, Cin, x), w, b, B, H, H, Cout, EPI_RELU_POOL, e, idx_out=idx), flush)
-        t_w = time_kernel(lambda: ops.wgrad3x3(ops._src(SRC_PLAIN, Cin, x), ops._src(SRC_POOLBWD, Cout, de, e, idx), B, H, H, dw, db), flush)
-        by_f = x.numel() * 4 + e.numel() * 5 + w.numel() * 4
-        by_w = x.numel() * 4 + e.numel() * 9 + w.numel() * 4
-        fl = 2 * B * H * H * Cin * Cout * 9
-        out.append({"kernel": f"conv {name}", "desc": "fprop+bias+ReLU+maxpool", "bytes": by_f, "flops": fl, "sec": t_f})
-        out.append({"kernel": f"wgrad {name}", "desc": "weight+bias gradient", "bytes": by_w, "flops": fl, "sec": t_w})
-    for k in out:
-        k["gbs"] = k["bytes"] / k["sec"] / 1e9
-        k["tflops"] = k["flops"] / k["sec"] / 1e12
-        k["frac_hbm"] = k["gbs"] / hbm_gbs
+    for n in (1024, 4096, 16384, 65536):
+        Xd = torch.from_numpy(X).to(dev).repeat(n // 4096 if n >= 4096 else 1, 1, 1, 1)[:n].contiguous()
+        with torch.no_grad():
+            for _ in range(2):
+                H.segment_device(Xd, 0.1)
+            torch.cuda.synchronize()
+            reps = max(2, 65536 // n)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(reps):
+                H.segment_device(Xd, 0.1)
+            e.record()
+            torch.cuda.synchronize()
+        out.append({"batch": n, "frames_per_s": n * reps / (s.elapsed_time(e) * 1e-3)})
+        del Xd
     return out
-
-
-def fused_step_roofline(B, flush, hbm_gbs, tf_peak):
-    """The whole-step critic kernel (csrc/critic_fused.cu) timed alone: one graph node replayed between CUDA events, L2
-    flushed in between (gradient leaves as per-CTA partial vectors; the Adam tail of the full step is not in this number).
-    Algorithmic work per frame: 8,460,480 FLOP; compulsory HBM bytes 12,288 (uint8 frame) + 4 (label)."""
-    from cgs_b200 import ops
-    from cgs_b200.nets import NewCritic
-    from cgs_b200.train_handler import FlatAdam
-    torch.manual_seed(0)
-    c = NewCritic(dropout=0.3).cuda().train()
-    opt = FlatAdam(c.parameters())
-    X = torch.randint(0, 255, (B, 64, 64, 3), dtype=torch.uint8, device="cuda")
-    Y = torch.rand(B, device="cuda")
-    run = lambda: ops.critic_train_fused(c, X, Y, 3, rng=c._dropout_rng(X.device))      # masks drawn in-kernel, as in the step
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g, capture_error_mode="thread_local"):
-        run()
-    sec = time_kernel(g.replay, flush)
-    flops, byts = 8460480 * B, (12288 + 4) * B
-    sms = torch.cuda.get_device_properties(0).multi_processor_count
-    mma_peak = sms * 512 * 2 * 1.965e9 / 1e12      # mma.sync m16n8k8 TF32: 2.0 clk per instruction per SM (tools/mma_rate.cu)
-    return {"kernel": "critic_fused_train_kernel", "desc": "frame -> forward -> loss -> backward, all activations in smem",
-            "sec": sec, "flops": flops, "bytes": byts, "tflops": flops / sec / 1e12, "gbs": byts / sec / 1e9,
-            "frac_hbm": byts / sec / 1e9 / hbm_gbs, "frac_tensor_bf16_peak": flops / sec / 1e12 / tf_peak,
-            "mma_sync_tf32_peak_tflops": mma_peak, "frac_mma_sync_tf32_peak": flops / sec / 1e12 / mma_peak}
-
-
-def masker_roofline(B, flush, hbm_gbs, tf_peak):
-    """Dominant kernel of the inference workload: cgs_masker_fused (masker.0 + LeakyReLU + masker.2 + sigmoid + threshold),
-    timed alone.  Per frame: 2 * (6,488,064 + 589,824) FLOP; HBM bytes 12,288 (frame) + 32,768
-    (o0) + 16,384 (mask) + 4,096 (hard mask)."""
-    from cgs_b200 import ops
-    from cgs_b200.nets import UnetDecoder
-    torch.manual_seed(0)
-    m = UnetDecoder().cuda().eval()
-    X = torch.randint(0, 255, (B, 64, 64, 3), dtype=torch.uint8, device="cuda")
-    o0 = torch.rand(B, 32, 32, 8, device="cuda")
-    run = lambda: ops.masker_fused(m, X, o0, 0.1)
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g, capture_error_mode="thread_local"):
-        run()
-    sec = time_kernel(g.replay, flush)
-    flops, byts = 2 * (6488064 + 589824) * B, (12288 + 32768 + 16384 + 4096) * B
-    sms = torch.cuda.get_device_properties(0).multi_processor_count
-    mma_peak = sms * 512 * 2 * 1.965e9 / 1e12
-    return {"kernel": "masker_fused_kernel", "desc": "cat(X, ups(o0)) -> masker.0 -> LeakyReLU -> masker.2 -> sigmoid -> threshold",
-            "sec": sec, "flops": flops, "bytes": byts, "tflops": flops / sec / 1e12, "gbs": byts / sec / 1e9,
-            "frac_hbm": byts / sec / 1e9 / hbm_gbs, "frac_tensor_bf16_peak": flops / sec / 1e12 / tf_peak,
-            "mma_sync_tf32_peak_tflops": mma_peak, "frac_mma_sync_tf32_peak": flops / sec / 1e12 / mma_peak}
 
 
 def run_ours(args, rank, world):
     import torch.distributed as dist
-    from cgs_b200 import ops
-    from cgs_b200.graph_step import GraphedCriticStep, GraphedHourglassStep, GraphedSegment
-    from cgs_b200.train_handler import Handler, parse_args
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -272,205 +528,31 @@ def run_ours(args, rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
-    B, W, K = args.batch, args.warmup, args.steps
-    ops.set_precision(args.precision)
-    hargs = parse_args(["--chfak", str(args.chfak)] + (["-frozen"] if args.workload == "hourglass" else []))
-    torch.manual_seed(0)
-    H = Handler(hargs, device=dev, rank=rank, world_size=world, process_group=group)
-    H.critic.to(dev); H.masker.to(dev)
-    X, Y = make_batch(args.workload, B, seed=rank)
-    Xh = torch.from_numpy(X).pin_memory()
-    Yh = torch.from_numpy(Y[1, :B]).float().pin_memory()
-    if args.workload == "critic_train":
-        step = GraphedCriticStep(H, B)
-        host = (Xh, Yh)
-    elif args.workload == "hourglass":
-        step = GraphedHourglassStep(H, B)
-        host = (Xh[:B], Xh[B:], Yh)
-    else:
-        step = GraphedSegment(H, B, 0.1)
-        host = (Xh,)
-    h2d = sum(t.numel() * t.element_size() for t in host)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    sync = (lambda: (dist.barrier(), torch.cuda.synchronize())) if world > 1 else torch.cuda.synchronize
-
-    # ---- value: inputs resident in HBM, graph replay, per-step CUDA events, L2 flushed between steps
-    step.load(*host)
+    names = list(WORKLOADS) if args.workload == "all" else [args.workload]
     sampler = ClockSampler(local)
+    windows = []
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)          # let nvidia-smi start streaming before the (short) timed region
-    for _ in range(max(W, 3)):
-        step.replay()
-    sync()
-    evs = []
-    t_wall0 = time.perf_counter()
-    align = torch.zeros(1, device=dev)
-    for _ in range(K):
-        flush.zero_()
-        if world > 1:
-            # ranks drift apart by host jitter while they flush; a step can only finish when the slowest peer's gradient
-            # arrives, so start the timed region of every rank at a common device-side point (a tiny all-reduce)
-            dist.all_reduce(align)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record(); step.replay(); e.record()
-        evs.append((s, e))
-    sync()
-    t_wall = time.perf_counter() - t_wall0
-    dev_s = sum(s.elapsed_time(e) for s, e in evs) * 1e-3
-    flushed_ms = 1e3 * dev_s / K
-    timing = "cuda events per step, L2 flushed (256 MiB memset) between timed steps"
-    if args.workload == "critic_train":
-        # ---- headline timing: K steps BACK TO BACK over a rotation of distinct resident batches whose total size exceeds
-        # the 126 MB L2 (every step reads frames that are not cached), one event pair around the K steps.  Per-step timing
-        # with a flush in between (kept as `ms_per_step_flushed`) idles the GPU before every step, so it adds the graph
-        # launch latency to each step and, on several GPUs, the skew the ranks pick up while flushing.
-        from cgs_b200.graph_step import _capture
-        spg = max(d for d in (8, 4, 2, 1) if K % d == 0)           # steps captured per graph (one launch runs spg steps)
-        nrot = -(-max(2, -(-160 * 2 ** 20 // (B * 12288))) // spg) * spg
-        Xrot = torch.stack([torch.from_numpy(np.roll(X, 7 * r + 1, axis=0)) for r in range(nrot)]).to(dev)
-        Yrot = torch.stack([torch.from_numpy(np.roll(Y[1, :B], 7 * r + 1)).float() for r in range(nrot)]).to(dev)
-        roll0 = torch.zeros(1, dtype=torch.int32, device=dev)
-
-        def chunk_fn(r0):
-            return lambda: torch.stack([H.critic_step(Xrot[r0 + k], Yrot[r0 + k], step.opti, roll=roll0) for k in range(spg)])
-        rot = [_capture(chunk_fn(r0), warmup=1)[0] for r0 in range(0, nrot, spg)]
-        for g in rot[:max(1, -(-max(W, 3) // spg))]:
-            g.replay()
-        sync()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for i in range(K // spg):
-            rot[i % len(rot)].replay()
-        e.record()
-        sync()
-        dev_s = s.elapsed_time(e) * 1e-3
-        timing = (f"one cuda-event pair around K back-to-back steps ({spg} steps per graph launch) over {nrot} distinct resident "
-                  f"batches ({nrot * B * 12288 >> 20} MiB of frames > 126 MB L2); per-step timing with an L2 flush before every "
-                  f"step in ms_per_step_flushed")
-    # ---- e2e: pinned host buffers -> H2D -> step -> D2H of the step's result, every step, through the public API
-    if args.workload == "critic_train":
-        from cgs_b200.graph_step import PipelinedCriticTrainer
-        trainer = PipelinedCriticTrainer(H, B)            # chunked double-buffered H2D, async loss read-back
-        # steps per chunk (= per H2D copy and per graph launch).  Measured (tools/e2e_timeline.py): a chunk costs ~0.1-0.25 ms
-        # of fixed latency (cross-stream event + graph launch), so large chunks win in steady state (16 -> PCIe-bound at the
-        # 43-54 GB/s the host memory feeds); short runs take smaller ones so the un-overlapped first copy stays ~1/5
-        chunk = max(1, min(16, K // 5))
-        nb = 2 * chunk                                     # pinned host dataset of nb batches, walked K steps in total
-        Xds = torch.from_numpy(np.concatenate([X] * nb)).pin_memory()
-        Yds = torch.from_numpy(np.tile(Y[1, :B], nb)).float().pin_memory()
-        trainer.train(Xds, Yds, chunk=chunk)
-        sync()
-        n0 = trainer.i
-        t0 = time.perf_counter()
-        done = 0
-        while done < K:
-            m = min(nb, K - done)
-            done += trainer.train(Xds[:m * B], Yds[:m * B], chunk=chunk)
-        losses = trainer.losses()                          # synchronises: all K losses are on the host
-        sync()
-        e2e_s = time.perf_counter() - t0
-        assert trainer.i - n0 == K and torch.isfinite(losses).all() and float(losses.max()) < 10.0 and float(losses.min()) >= 0.0
-        d2h = 4
-    else:
-        for _ in range(3):
-            out = step(*host)
-        sync()
-        t0 = time.perf_counter()
-        d2h = 0
-        for _ in range(K):
-            out = step(*host)
-            res = out if torch.is_tensor(out) else out[0]
-            val = res.reshape(-1)[:1].cpu() if args.workload != "infer" else out[2].cpu()   # loss scalar / hard masks
-            d2h = val.numel() * val.element_size()
-        sync()
-        e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_s, e2e_s = t.tolist()
+        time.sleep(0.3)
+    recs = {n: bench_workload(n, args, rank, world, dev, group, windows) for n in names}
+    clocks = sampler.stop(windows) if rank == 0 else None
     if rank == 0:
-        hbm, tf, which = peaks()
-        value = world * B * K / dev_s
-        line = {"metric": METRIC if args.workload == "critic_train" else args.workload + "_frames_per_s",
-                "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
-                "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
-                "config": {"workload": WORKLOADS[args.workload], "batch_per_gpu": B, "global_batch": B * world,
-                           "precision": (("whole step in one kernel: TF32 mma.sync convolutions (fprop, dgrad, wgrad), fp32 "
-                                          "accumulate; head, loss, Adam fp32" if (args.workload == "critic_train" and args.chfak == 1)
-                                          else "two whole-frame kernels (encoder+decoder, masker): TF32 mma.sync convolutions, fp32 "
-                                          "accumulate" if (args.workload == "infer" and args.chfak == 1)
-                                          else "conv fprop/dgrad: tcgen05 kind::tf32, fp32 accumulate in TMEM; wgrad: TF32 mma.sync; "
-                                          "head, losses, Adam: fp32") if args.precision == "tf32" else "all fp32 (FFMA)"),
-                           "chfak": args.chfak, "parallelism": f"dp{world}", "timing": timing, "graph": True},
-                "ms_per_step_flushed": flushed_ms,
-                "e2e": {"value": world * B * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h},
-                "gpu_launches": step.launches * K, "launches_per_step": step.launches,   # kernels, not graph launches
-                "wall_ms_per_step_incl_flush": 1e3 * t_wall / K, "clocks": clocks,
-                "achieved_tflops": FLOPS[args.workload].get(args.chfak, 0) * value / 1e12}
-        if world == 1 and not args.no_extras:
-            tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-            tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
-            fused = (args.workload == "critic_train" and args.precision == "tf32" and args.chfak == 1)
-            if args.workload == "infer" and args.precision == "tf32" and args.chfak == 1:
-                pj = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if which == "measured" else {}
-                tf_burst = pj.get("bf16_tflops", 1590.0)
-                k = masker_roofline(B, flush, hbm, tf_burst)
-                line["roofline"] = {"bound": "tensor", "achieved": k["tflops"], "peak": tf_burst, "unit": "TFLOP/s",
-                                    "frac": k["frac_tensor_bf16_peak"], "traffic": tj.get(k["kernel"]) if B == 256 else None,
-                                    "kernel": k["kernel"], "algorithmic_flops": k["flops"], "algorithmic_bytes": k["bytes"],
-                                    "peak_source": which + " (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)",
-                                    "launch_us": k["sec"] * 1e6, "hbm_gbs_achieved": k["gbs"], "frac_hbm": k["frac_hbm"],
-                                    "mma_sync_tf32_peak_tflops": k["mma_sync_tf32_peak_tflops"],
-                                    "frac_of_mma_sync_tf32_peak": k["frac_mma_sync_tf32_peak"]}
-                line["kernels"] = [{kk: (round(v, 4) if isinstance(v, float) else v) for kk, v in k.items()}]
-            elif fused:
-                # dominant kernel = the whole-step kernel (79 % of the step, profiles/): a dense-contraction kernel whose
-                # operands never leave shared memory -> tensor roofline; HBM traffic is the uint8 frames only
-                pj = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if which == "measured" else {}
-                tf_burst = pj.get("bf16_tflops", 1590.0)
-                k = fused_step_roofline(B, flush, hbm, tf_burst)
-                # the step IS this one kernel, so its launch duration is measured live over the timed region itself
-                # (events around the K back-to-back steps); k = the same kernel alone, cold, without its Adam tail
-                sec = dev_s / K
-                tfl = k["flops"] / sec / 1e12
-                pj2 = pj.get("bf16_tflops_sustained", tf_burst)
-                line["roofline"] = {"bound": "tensor", "achieved": tfl, "peak": pj2, "unit": "TFLOP/s",
-                                    "frac": tfl / pj2, "traffic": tj.get(k["kernel"]) if B == 256 else None,
-                                    "kernel": "critic_fused_kernel<0>", "algorithmic_flops": k["flops"], "algorithmic_bytes": k["bytes"],
-                                    "peak_source": which + " (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside the K-step region)",
-                                    "launch_us": sec * 1e6, "hbm_gbs_achieved": k["bytes"] / sec / 1e9,
-                                    "frac_hbm": k["bytes"] / sec / 1e9 / hbm,
-                                    "isolated_cold_launch_us": k["sec"] * 1e6,
-                                    "mma_sync_tf32_peak_tflops": k["mma_sync_tf32_peak_tflops"],
-                                    "frac_of_mma_sync_tf32_peak": tfl / k["mma_sync_tf32_peak_tflops"],
-                                    "note": "TF32 mma.sync m16n8k8 (N = 8 output channels rules out tcgen05 tiles); its own "
-                                            "measured peak is 512 MAC/clk/SM = 0.18 of the bf16 tcgen05 peak"}
-                line["kernels"] = [{kk: (round(v, 4) if isinstance(v, float) else v) for kk, v in k.items()}]
-            else:
-                ks = kernel_rooflines(B, args.chfak, flush, hbm)
-                top = max(ks, key=lambda k: k["sec"])
-                traffic = tj.get(top["kernel"]) if (args.chfak == 1 and B == 256) else None
-                line["roofline"] = {"bound": "hbm", "achieved": top["gbs"], "peak": hbm, "unit": "GB/s",
-                                    "frac": top["gbs"] / hbm, "traffic": traffic, "kernel": top["kernel"],
-                                    "algorithmic_bytes": top["bytes"],
-                                    "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
-                                    "launch_us": top["sec"] * 1e6, "achieved_tflops_fp32": top["tflops"]}
-                line["kernels"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in kk.items()} for kk in ks]
-            # CPU baseline: oracle port on the host cores, bounded sample
-            cores = os.cpu_count()
-            torch.set_num_threads(cores)
-            ostep = oracle_step_fn(args.workload, args.chfak, B)
-            ostep(); ostep()
-            n, t0 = 0, time.perf_counter()
-            while time.perf_counter() - t0 < 10.0 and n < 200:
-                ostep(); n += 1
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": B * n / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"{n} full steps of batch {B} in {dt:.1f}s (oracle/torch_ref.py on torch CPU fp32)"}
+        head = recs[names[0]]
+        line = {"metric": METRIC if args.workload == "all" else names[0] + "_frames_per_s", "value": head["value"], "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": ("bf16" if args.precision == "tf32" and names[0] == "hourglass" else "tf32") if args.precision == "tf32" else "f32",
+                "data": "synthetic"}
+        line.update({k: v for k, v in head.items() if k not in ("value", "unit", "ms_per_step")})
+        line["precision"] = ("whole-frame kernels: TF32 mma.sync convolutions in the critic passes and the Hourglass forward, bf16 "
+                             "mma.sync (fp32 accumulate) in the Hourglass backward; heads, losses, Adam fp32"
+                             if args.precision == "tf32" else "all fp32 (FFMA)")
+        line["clocks"] = clocks
+        if len(names) > 1:
+            line["workloads"] = {k: v for k, v in recs.items() if k != names[0]}
+            line["gpu_launches"] = sum(r["gpu_launches"] for r in recs.values())
+        if world == 1 and not args.no_extras and ("infer" in names):
+            line["infer_sweep"] = infer_sweep(args, dev)
         print(json.dumps(line))
     if world > 1:
         # Tearing the communicator down while captured graphs still reference it hangs in ncclCommAbort on this
@@ -484,24 +566,22 @@ def run_ours(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="critic_train", choices=list(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--workload", default="all", choices=["all"] + list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE config of each workload)")
     ap.add_argument("--chfak", type=int, default=1)
-    ap.add_argument("--no-extras", action="store_true", help="skip per-kernel roofline and CPU baseline legs")
+    ap.add_argument("--no-extras", action="store_true", help="skip per-kernel roofline, CPU baseline and sweep legs")
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
-                    help="tf32: tcgen05 TF32 conv fprop/dgrad (fp32 accumulate) where covered; fp32: exact FFMA kernels")
+                    help="tf32: tensor-core kernels (TF32 / bf16 operands, fp32 accumulate); fp32: exact FFMA kernels")
     args = ap.parse_args()
-    if args.batch == 0:
-        args.batch = 1024 if args.workload == "hourglass" else 256
+    if args.workload == "all" and args.batch:
+        raise SystemExit("bench.py: --batch needs a single --workload")
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
-        if args.workload == "hourglass":
-            args.batch = min(args.batch, 64)      # bounded sample: ~90 ms/step on CPU at the reference's own batch
-        return run_reference(args, rank)
+        return run_reference(args, rank, world)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
     run_ours(args, rank, world)

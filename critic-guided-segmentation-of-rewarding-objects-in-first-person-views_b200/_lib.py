@@ -57,6 +57,9 @@ EXPORTS = {
                                                                              C.c_int64, C.c_int64, C.c_int64, C.c_void_p],
     "cgs_critic_loss_xgrad": [_f32p, _f32p, C.c_int32, _f32p, _f32p, _f32p, C.c_float, C.c_uint64, C.c_void_p,
                               C.POINTER(CriticWeights), C.c_float, C.c_int32, _f32p, _f32p, _f32p, C.c_void_p],
+    "cgs_hg_score": [_u8p, _u8p, C.c_int32, C.c_int32, C.c_void_p, _f32p, _f32p, _f32p] + [_f32p] * 6 +
+                    [C.c_float, C.c_uint64, C.c_void_p, C.POINTER(CriticWeights), C.c_float, _f32p, C.c_float, C.c_float,
+                     _f32p, _f32p, _f32p, _f32p, C.c_void_p],
     "cgs_infer_pack_floats": [],
     "cgs_infer_pack_decoder": [_f32p] * 5 + [C.c_void_p],
     "cgs_infer_fused": [_u8p, C.c_int32, C.POINTER(CriticWeights)] + [_f32p] * 9 + [C.c_void_p],

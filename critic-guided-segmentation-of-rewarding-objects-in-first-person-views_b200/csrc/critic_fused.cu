@@ -93,6 +93,18 @@ struct Params {
   long long npad;
   unsigned long long* ll_peer[16];  // every rank's receive buffer as mapped into this process
   float* partials;      // != NULL: per-CTA partial gradients [grid][PSTRIDE] in flat order instead of REDs into gseg
+  // MODE 3 (the two scored blends of one Hourglass step, main.py:395-411): pass 0 scores replaced = A(1-Z) + Z*B against
+  // `target` (negpred), pass 1 scores injected = B(1-Z) + Z*A against `target2` (pred of critic(A)); the blends are formed
+  // in shared memory from the raw uint8 frames and the mask, and the input gradient is contracted with (B - A) / (A - B)
+  // on the way out: dz = d(replace + inject + regulariser) / dZ.  Neither blend nor its gradient ever exists in HBM.
+  const uint8_t* framesB;           // contrast frames (never rolled)
+  const float* zmask;               // [B][64][64]
+  const float* target2;             // NULL: no inject pass
+  const float *m2b, *m3b, *mvb;     // forced dropout masks of pass 1
+  float* pred2;
+  float* dz;                        // [B][64][64]
+  const float* vpred;               // regulariser weight vf = 1 - vpred[n] (non-static norm); NULL: vf = 1
+  float l1, l2, reg_scale;          // main.py:415-429; reg_scale = loss_grad / (B * 4096)
   float* pred;
   float* loss;
   const int* roll_dev;
@@ -244,6 +256,36 @@ __device__ __forceinline__ void stage_frame_f32(const float* __restrict__ src, f
   }
 }
 
+// MODE 3 staging: the occlusion blend of main.py:395 (which = 0: A*(1-Z) + Z*B) or :406 (which = 1: B*(1-Z) + Z*A), formed in
+// fp32 exactly as the reference does (u8 -> float / 255, two products, one sum, no contraction), then TF32-rounded into the
+// haloed (r,g,b,0) tile.  sA8 is read with the shift_batch roll, sB8 without (main.py:355-357).
+__device__ __forceinline__ void stage_blend(const uint8_t* __restrict__ sA8, const uint8_t* __restrict__ sB8, const float* __restrict__ z,
+                                            int which, int roll, float* __restrict__ sXd, int tid) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int p = tid + NT * i, y = p >> 6, x = p & 63;
+    const uint8_t* a = sA8 + (y * 64 + ((x + roll) & 63)) * 3;
+    const uint8_t* b = sB8 + p * 3;
+    const float zz = __ldg(z + p), omz = __fsub_rn(1.f, zz);
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float fa = __fdiv_rn((float)a[c], 255.f), fb = __fdiv_rn((float)b[c], 255.f);
+      const float keep = which ? fb : fa, put = which ? fa : fb;
+      v[c] = tf32r(__fadd_rn(__fmul_rn(keep, omz), __fmul_rn(zz, put)));
+    }
+    *reinterpret_cast<float4*>(sXd + ((y + 1) * P0 + x + 1) * 4) = make_float4(v[0], v[1], v[2], 0.f);
+  }
+  if (tid < 260) {
+    int y, x;
+    if (tid < 66) { y = 0; x = tid; }
+    else if (tid < 132) { y = 65; x = tid - 66; }
+    else if (tid < 196) { y = tid - 131; x = 0; }
+    else { y = tid - 195; x = 65; }
+    *reinterpret_cast<float4*>(sXd + (y * P0 + x) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 // XG = false: one critic_pipe training step (weight gradients, optimizer).  XG = true: the same forward and loss with FROZEN
 // parameters and the gradient w.r.t. the input frame instead (critic(replaced) / critic(injected) of the Hourglass loop,
 // main.py:396-411, and the saliency baseline, main.py:949-951): all weight-gradient work is compiled out and the backward ends
@@ -251,7 +293,7 @@ __device__ __forceinline__ void stage_frame_f32(const float* __restrict__ src, f
 // MODE 2 = MODE 1's forward only (pred for fp32 frames, e.g. `negpred = critic(B)` under no_grad, main.py:365-367).
 template <int MODE>
 __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
-  constexpr bool XG = MODE != 0, FWD = MODE == 2;
+  constexpr bool XG = MODE != 0, FWD = MODE == 2, BL = MODE == 3;
   extern __shared__ __align__(128) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int lj = lane >> 3, lr = lane & 7;               // ldmatrix: this lane addresses row lr of matrix lj
@@ -278,7 +320,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
   const unsigned long long rng_call = p.rng_state ? p.rng_state[0] : 0ull;
   unsigned bar_gen = 0;
   if (p.adam_p && tid == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(bar_gen) : "l"(p.bar + 1) : "memory");
-  if (blockIdx.x < p.B) {
+  if (!BL && blockIdx.x < p.B) {
     prefetch_frame(p, blockIdx.x, sm, tid);
     if (p.rng_state) draw_masks(p, blockIdx.x, rng_call, sm, tid);
   }
@@ -369,7 +411,10 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
   for (int i = 0; i < 8; ++i) acc0[i >> 2][i & 3] = 0.f;
 #pragma unroll
   for (int i = 0; i < 20; ++i) accW[i >> 2][i & 3] = 0.f;
-  float loss_acc = 0.f;
+  float loss_acc = 0.f, loss_acc2 = 0.f, reg1 = 0.f, reg2 = 0.f;
+  const int npass = BL && p.target2 ? 2 : 1;
+  uint8_t* sA8 = reinterpret_cast<uint8_t*>(sm + oU8);            // MODE 3: raw bytes of the A frame ...
+  uint8_t* sB8 = reinterpret_cast<uint8_t*>(sm + oAcc + 576);     // ... and of the B frame (the accumulator region is free)
   const int odd = g & 1;
   // features.0 weight-gradient rows: m = 8G + r; G < 3: filter row ky = G, the (kx, ci) combos except (2, ky);
   // G = 3: the three left-out combos (ky = r, kx = 2, ci = r), rows 3..7 unused.  Within an 8-row group every lane
@@ -391,13 +436,34 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
     }
   const int ldoff8 = (lr + 8 * (lj & 1)) * 4;                 // ldmatrix row offset inside an 8-channel half-plane strip
 
-  for (int n = blockIdx.x; n < p.B; n += gridDim.x) {
+  for (int n = blockIdx.x; n < p.B; n += gridDim.x)
+  for (int which = 0; which < npass; ++which) {
     CF_MARK(0);
     // ================= F0a: frame bytes (+ dropout masks) have landed -> fp32 haloed tile; e0 halo
-    const float ytgt = __ldg(p.target + n);
+    const float ytgt = __ldg((BL && which ? p.target2 : p.target) + n);
+    if (BL) {
+      // both raw frames once per frame; this pass's dropout masks (forced: cp.async; else drawn: call index + pass)
+      const uint32_t dm = (uint32_t)__cvta_generic_to_shared(sm);
+      if (which == 0) {
+        const uint8_t *srcA = p.frames + (size_t)n * 12288, *srcB = p.framesB + (size_t)n * 12288;
+        for (int c = tid; c < 768; c += NT) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dm + oU8 * 4 + c * 16), "l"(srcA + c * 16));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dm + (oAcc + 576) * 4 + c * 16), "l"(srcB + c * 16));
+        }
+      }
+      if (p.m2) {
+        const float *q2 = which ? p.m2b : p.m2, *q3 = which ? p.m3b : p.m3, *qv = which ? p.mvb : p.mv;
+        if (tid < 128) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dm + (oM2 + tid * 4) * 4), "l"(q2 + (size_t)n * 512 + tid * 4));
+        else if (tid < 192) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dm + (oM3 + (tid - 128) * 4) * 4), "l"(q3 + (size_t)n * 256 + (tid - 128) * 4));
+        else if (tid < 200) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dm + (oHead + 64 + (tid - 192) * 4) * 4), "l"(qv + (size_t)n * 32 + (tid - 192) * 4));
+      }
+      asm volatile("cp.async.commit_group;\n" ::);
+      if (p.rng_state) draw_masks(p, n, rng_call + which, sm, tid);
+    }
     asm volatile("cp.async.wait_all;\n" ::);
     __syncthreads();
-    if (XG) stage_frame_f32(p.xin + (size_t)n * 12288, sm + oX, tid);
+    if (BL) stage_blend(sA8, sB8, p.zmask + (size_t)n * 4096, which, roll, sm + oX, tid);
+    else if (XG) stage_frame_f32(p.xin + (size_t)n * 12288, sm + oX, tid);
     else stage_frame(reinterpret_cast<const uint8_t*>(sm + oU8), sm + oX, roll, tid);
     if (tid < 264) {   // e0 halo ring (region A is reused by the re-staged frame), both half-planes
       const int h = tid >= 132, q = tid - 132 * h;
@@ -581,10 +647,11 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
         loss_acc -= y * fmaxf(logf(pr), -100.f) + (1.f - y) * fmaxf(logf(1.f - pr), -100.f);
         dl = p.gscale * (pr - y) / fmaxf(pr * (1.f - pr), 1e-12f) * pr * (1.f - pr);
       } else {
-        loss_acc = fmaf(pr - y, pr - y, loss_acc);
+        if (BL && which) loss_acc2 = fmaf(pr - y, pr - y, loss_acc2);
+        else loss_acc = fmaf(pr - y, pr - y, loss_acc);
         dl = p.gscale * 2.f * (pr - y) * pr * (1.f - pr);
       }
-      if (lane == 0) p.pred[n] = pr;
+      if (lane == 0) (BL && which ? p.pred2 : p.pred)[n] = pr;
       if (!XG) {
         if (lane == 0) sAcc[aBl2] += dl;
         sAcc[aWl2 + lane] += dl * vm;
@@ -764,7 +831,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
       // ================= features.0 input gradient: dX[y,x,ci] = sum_{tap',co} dY0[y + ky' - 1, x + kx' - 1, co] * W0[co][ci][8 - tap'].
       // dY0 (64x64x8, one non-zero per pooled window and channel) is expanded from the tagged pooled gradient into haloed
       // half-planes, 34 rows at a time (region A; e0 and dY1 are dead), and convolved like any other layer: 2 bands x 32 rows
-      if (n + (int)gridDim.x < p.B) {
+      if (!BL && n + (int)gridDim.x < p.B) {
         prefetch_frame(p, n + gridDim.x, sm, tid);
         if (p.rng_state) draw_masks(p, n + gridDim.x, rng_call, sm, tid);
       }
@@ -791,7 +858,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
         {
           const int x0 = (warp & 3) * 16, r0 = (warp >> 2) * 8;
           const uint32_t aA = smb + (oA + (lj >> 1) * PLD + (r0 * P0 + x0) * 4 + ldoff8) * 4;
-          float* dO = p.dx + ((size_t)n * 4096 + (32 * band + r0) * 64 + x0 + g) * 3;
+          float* dO = BL ? nullptr : p.dx + ((size_t)n * 4096 + (32 * band + r0) * 64 + x0 + g) * 3;
           slide_rows<8, 3>(
               w,
               [&](int i, uint32_t(&a)[3][4]) {
@@ -799,6 +866,36 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
                 for (int kx = 0; kx < 3; ++kx) ldsm4(a[kx], aA + (i * P0 + kx) * 16);
               },
               [&](int e, const float(&top)[4], const float(&bot)[4]) {
+                if (BL) {
+                  // d loss / d Z = sum_c dX[c] * (B - A)[c] (replaced) or (A - B)[c] (injected), main.py:395,406: lanes t = 0
+                  // (channels 0, 1) and t = 1 (channel 2) of a pixel are neighbours; the differences come from the raw bytes
+#pragma unroll
+                  for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                      const int y = 32 * band + r0 + e + r, x = x0 + g + 8 * h;
+                      const uint8_t* pa = sA8 + (y * 64 + ((x + roll) & 63)) * 3;
+                      const uint8_t* pb = sB8 + (y * 64 + x) * 3;
+                      float s = 0.f;
+                      if (t == 0) s = (r ? bot[2 * h] : top[2 * h]) * (float)((int)pb[0] - (int)pa[0]) +
+                                      (r ? bot[2 * h + 1] : top[2 * h + 1]) * (float)((int)pb[1] - (int)pa[1]);
+                      else if (t == 1) s = (r ? bot[2 * h] : top[2 * h]) * (float)((int)pb[2] - (int)pa[2]);
+                      s += __shfl_xor_sync(0xffffffffu, s, 1);
+                      if (t == 0) {
+                        float* dzp = p.dz + (size_t)n * 4096 + y * 64 + x;
+                        s *= which ? -(1.f / 255.f) : (1.f / 255.f);
+                        if (which == 0) {                    // first pass writes, with the regulariser's gradient (main.py:415-429)
+                          const float vf = p.vpred ? 1.f - __ldg(p.vpred + n) : 1.f;
+                          const float u = vf * __ldg(p.zmask + (size_t)n * 4096 + y * 64 + x);
+                          reg1 += fabsf(u); reg2 = fmaf(u, u, reg2);
+                          const float sg = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
+                          *dzp = s + p.reg_scale * vf * (p.l1 * sg + 2.f * p.l2 * u);
+                        } else {
+                          *dzp += s;                         // same thread wrote it in pass 0
+                        }
+                      }
+                    }
+                } else
                 if (t < 2) {                                 // columns 0..2 of the 8-wide tile are the three input channels
 #pragma unroll
                   for (int r = 0; r < 2; ++r)
@@ -933,6 +1030,12 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
     // partial vector that CTA 0 sums in a fixed order afterwards (no memset node, bit-reproducible)
     if (p.adam_p) p.partials[(size_t)blockIdx.x * PSTRIDE + NGRAD] = loss_acc * p.inv_n;
     else if (!FWD) atomicAdd(p.loss, loss_acc * p.inv_n);
+    if (BL && npass > 1) atomicAdd(p.loss + 1, loss_acc2 * p.inv_n);
+  }
+  if (BL) {                                          // regulariser terms: one atomic pair per warp
+    reg1 = warp_sum(reg1); reg2 = warp_sum(reg2);
+    if (lane == 0 && p.l1 != 0.f) atomicAdd(p.loss + 2, reg1 * p.l1 * p.inv_n * (1.f / 4096.f));
+    if (lane == 0 && p.l2 != 0.f) atomicAdd(p.loss + 3, reg2 * p.l2 * p.inv_n * (1.f / 4096.f));
   }
   if (!XG && p.adam_p) {
     // ---- grid barrier (all CTAs are co-resident: one per SM, grid <= SMs), then every CTA sums its slice of the
@@ -1040,7 +1143,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
     __threadfence();
     if (atomicAdd(&p.rng_state[1], 1ull) == gridDim.x - 1) {
       p.rng_state[1] = 0;
-      p.rng_state[0] = rng_call + 1;
+      p.rng_state[0] = rng_call + npass;
     }
   }
   CF_MARK(16);
@@ -1175,4 +1278,42 @@ extern "C" int cgs_critic_loss_xgrad(const float* x, const float* target, int32_
   if (cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) return check_launch("critic_loss_xgrad.memset");
   cf::critic_fused_kernel<1><<<cgs_critic_fused_grid(B), cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
   return check_launch("critic_loss_xgrad");
+}
+
+extern "C" int cgs_hg_score(const uint8_t* frames_a, const uint8_t* frames_b, int32_t B, int32_t roll, const int32_t* roll_dev,
+                            const float* z, const float* target_replace, const float* target_inject,
+                            const float* m_e2, const float* m_e3, const float* m_v,
+                            const float* m_e2_inj, const float* m_e3_inj, const float* m_v_inj,
+                            float p_drop, uint64_t seed, uint64_t* rng_state, const cgs_critic_weights* w, float loss_grad,
+                            const float* vpred, float l1, float l2, float* pred_replace, float* pred_inject, float* losses,
+                            float* dz, void* stream) {
+  CGS_REQUIRE(frames_a && frames_b && z && target_replace && w && pred_replace && losses && dz && B > 0, "hg_score: bad args");
+  CGS_REQUIRE(!target_inject || pred_inject, "hg_score: the inject pass needs pred_inject");
+  CGS_REQUIRE((((uintptr_t)frames_a | (uintptr_t)frames_b) & 15) == 0, "hg_score: frames must be 16-byte aligned");
+  CGS_REQUIRE((m_e2 != nullptr) == (m_e3 != nullptr) && (m_e2 != nullptr) == (m_v != nullptr), "hg_score: dropout masks are all-or-none");
+  CGS_REQUIRE(!m_e2 || !target_inject || (m_e2_inj && m_e3_inj && m_v_inj), "hg_score: forced masks need a second set for the inject pass");
+  CGS_REQUIRE((((uintptr_t)m_e2 | (uintptr_t)m_e3 | (uintptr_t)m_v | (uintptr_t)m_e2_inj | (uintptr_t)m_e3_inj | (uintptr_t)m_v_inj) & 15) == 0,
+              "hg_score: masks must be 16-byte aligned");
+  CGS_REQUIRE(!(rng_state && m_e2), "hg_score: pass dropout masks OR an rng state, not both");
+  CGS_REQUIRE(!rng_state || (p_drop > 0.f && p_drop < 1.f), "hg_score: rng dropout needs 0 < p < 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  cf::Params p;
+  memset(&p, 0, sizeof(p));
+  p.frames = frames_a; p.framesB = frames_b; p.zmask = z; p.target = target_replace; p.target2 = target_inject;
+  p.m2 = m_e2; p.m3 = m_e3; p.mv = m_v; p.m2b = m_e2_inj; p.m3b = m_e3_inj; p.mvb = m_v_inj;
+  p.w0 = w->w0; p.b0 = w->b0; p.w1 = w->w1; p.b1 = w->b1; p.w2 = w->w2; p.b2 = w->b2; p.w3 = w->w3; p.b3 = w->b3;
+  p.w4 = w->w4; p.b4 = w->b4; p.wl1 = w->wl1; p.bl1 = w->bl1; p.wl2 = w->wl2; p.bl2 = w->bl2;
+  p.seed = seed; p.rng_state = (unsigned long long*)rng_state; p.p_drop = p_drop;
+  p.keep = rng_state ? 1.f / (1.f - p_drop) : 1.f;
+  p.world = 1;
+  p.pred = pred_replace; p.pred2 = pred_inject; p.loss = losses; p.dz = dz; p.B = B; p.bce = 0;
+  p.roll = roll; p.roll_dev = roll_dev;
+  p.vpred = vpred; p.l1 = l1; p.l2 = l2;
+  p.inv_n = 1.f / (float)B;
+  p.gscale = loss_grad / (float)B;
+  p.reg_scale = loss_grad / ((float)B * 4096.f);
+  cudaFuncSetAttribute(cf::critic_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
+  if (cudaMemsetAsync(losses, 0, 4 * sizeof(float), st) != cudaSuccess) return check_launch("hg_score.memset");
+  cf::critic_fused_kernel<3><<<cgs_critic_fused_grid(B), cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
+  return check_launch("hg_score");
 }

@@ -97,7 +97,7 @@ class GraphedHourglassStep(_Graphed):
     """One segmentation_training iteration (reference main.py:344-463) as a CUDA graph."""
     trains = True
 
-    def __init__(self, handler, batch, opti=None):
+    def __init__(self, handler, batch, opti=None, X=None, CX=None, Y=None, warmup=3):
         H = self.H = handler
         dev = H.device
         a = H.args
@@ -110,16 +110,17 @@ class GraphedHourglassStep(_Graphed):
                 p.requires_grad_(False)
             params = list(H.masker.parameters())
         self.opti = opti or FlatAdam(params, process_group=H.group, world_size=H.world)
-        self.X = torch.zeros((batch, 64, 64, 3), dtype=torch.uint8, device=dev)
-        self.CX = torch.zeros((batch, 64, 64, 3), dtype=torch.uint8, device=dev)
-        self.Y = torch.zeros((batch,), dtype=torch.float32, device=dev)
+        # static inputs: own buffers, or caller-provided device tensors (one slice of a resident dataset per graph)
+        self.X = X if X is not None else torch.zeros((batch, 64, 64, 3), dtype=torch.uint8, device=dev)
+        self.CX = CX if CX is not None else torch.zeros((batch, 64, 64, 3), dtype=torch.uint8, device=dev)
+        self.Y = Y if Y is not None else torch.zeros((batch,), dtype=torch.float32, device=dev)
         self.roll = torch.zeros(1, dtype=torch.int32, device=dev)
         self.static_in = (self.X, self.CX, self.Y)
 
         def fn():
             terms = H.segmentation_step(self.X, self.CX, self.Y, self.opti, roll=self.roll)
             return torch.stack([terms[k] for k in sorted(terms)])
-        self.graph, self.out, self.launches = _capture(fn, state=_train_state(self.opti, H.critic,
+        self.graph, self.out, self.launches = _capture(fn, warmup=warmup, state=_train_state(self.opti, H.critic,
                                                                               getattr(H, "sepcrit", None) if a.separate else None))
         self.term_names = sorted(k for k in ("critic", "replace", "inject", "L1", "L2")
                                  if (k != "critic" or a.live) and (k != "inject" or a.inject)
@@ -131,26 +132,52 @@ class GraphedSegment(_Graphed):
     The captured graph reads the decoder weights through the fragment buffer packed at capture time: build a new
     GraphedSegment after the masker has been trained further."""
 
-    def __init__(self, handler, batch, threshold=0.1):
+    def __init__(self, handler, batch, threshold=0.1, X=None):
         H = self.H = handler
         dev = H.device
         H.critic.to(dev).eval()
         H.masker.to(dev).eval()
-        self.X = torch.zeros((batch, 64, 64, 3), dtype=torch.uint8, device=dev)
+        self.X = X if X is not None else torch.zeros((batch, 64, 64, 3), dtype=torch.uint8, device=dev)
         self.static_in = (self.X,)
 
         def fn():
-            with torch.no_grad():
-                if ops.infer_fused_supported(H.critic, H.masker):
-                    # two kernels, every intermediate in shared memory: encoder + decoder -> o0 (32 KB/frame), then masker
-                    pred, o0 = ops.infer_encode_decode(H.critic, H.masker, self.X)
-                    mask, hard = ops.masker_fused(H.masker, self.X, o0, threshold)
-                else:
-                    x = ops.frames_to_float(self.X, 0).permute(0, 3, 1, 2)
-                    pred, embeds = H.critic(x, collect=True)
-                    mask, hard = H.masker.forward_hard(x, embeds, threshold)
-            return pred, mask, hard
+            return H.segment_device(self.X, threshold)       # whole-frame kernels when the geometry allows, else per layer
         self.graph, self.out, self.launches = _capture(fn)
+
+
+class HostPipeline:
+    """End-to-end feed for any graphed step from HOST batches: `slots` are >= 2 graphed steps with their own static input
+    buffers (training steps share one model and one optimizer).  The H2D copy of batch i+1 runs on a copy stream while
+    slot i replays; `result_of(slot)` (a device tensor: loss terms, hard masks ...) is read back after every step with an
+    asynchronous D2H copy into a pinned ring of `ring` entries.  `step()` never blocks the host; `results()` synchronises."""
+
+    def __init__(self, slots, result_of, ring=8):
+        self.slots, self.result_of = slots, result_of
+        self.copy_stream = torch.cuda.Stream()
+        self.ready = [torch.cuda.Event() for _ in slots]
+        self.done = [torch.cuda.Event() for _ in slots]
+        r0 = result_of(slots[0])
+        self.ring = torch.zeros((ring,) + tuple(r0.shape), dtype=r0.dtype).pin_memory()
+        self.d2h_bytes = r0.numel() * r0.element_size()
+        self.i = 0
+
+    def step(self, *host):
+        k = self.i % len(self.slots)
+        st = self.slots[k]
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.done[k])          # the replay that last read this slot's inputs has finished
+            st.load(*host)
+            self.ready[k].record(self.copy_stream)
+        main = torch.cuda.current_stream()
+        main.wait_event(self.ready[k])
+        st.replay()
+        self.ring[self.i % self.ring.shape[0]].copy_(self.result_of(st), non_blocking=True)
+        self.done[k].record(main)
+        self.i += 1
+
+    def results(self):
+        torch.cuda.synchronize()
+        return self.ring
 
 
 class PipelinedCriticTrainer:

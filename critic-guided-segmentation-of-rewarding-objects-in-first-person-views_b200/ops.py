@@ -54,11 +54,44 @@ def _p(t, dtype=torch.float32):
     return t.data_ptr()
 
 
+_prof = None    # list of (entry point, start event, end event) while a profile_calls() block is active
+
+
+class profile_calls:
+    """Times every C-ABI launch issued inside the block with a CUDA-event pair on the launching stream (eager execution
+    only; bench.py uses it to find the dominant kernel of a step and its live duration)."""
+
+    def __enter__(self):
+        global _prof
+        _prof = self.records = []
+        return self
+
+    def __exit__(self, *exc):
+        global _prof
+        _prof = None
+        return False
+
+    def summary(self):
+        """{entry point: (launches, total milliseconds)} (synchronises)."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, s, e in self.records:
+            n, t = out.get(name, (0, 0.0))
+            out[name] = (n + 1, t + s.elapsed_time(e))
+        return out
+
+
 def _call(name, *args):
     global _launches
+    if _prof is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
     rc = getattr(_lib.lib(), name)(*args)
     _lib.check(rc, name)
     _launches += 1
+    if _prof is not None:
+        e.record()
+        _prof.append((name, s, e))
 
 
 def _src(mode, Cn, a, b=None, idx=None, C0=0, shift=0):
@@ -584,6 +617,37 @@ def critic_loss_xgrad(critic, x_nhwc, target, masks=(None, None, None), rng=None
     """Loss of a frozen critic on fp32 NHWC frames [B,64,64,3] with the input gradient from the same kernel.
     `x_nhwc` may require grad (e.g. the occlusion blend); the critic's parameters get no gradient."""
     return CriticLossXGrad.apply(_c(x_nhwc), _c(target.to(torch.float32)), critic, masks, rng, bce)
+
+
+def _rng_args(rng):
+    return (float(rng[0]), int(rng[1]) & 0xFFFFFFFFFFFFFFFF, _p(rng[2], torch.int64)) if rng is not None else (0.0, 0, None)
+
+
+def hg_score(critic, A_u8, B_u8, z, target_replace, target_inject=None, roll=0, masks=None, masks_inject=None, rng=None,
+             loss_grad=1.0, vpred=None, l1=0.0, l2=0.0):
+    """The scored blends of one Hourglass step (reference main.py:395-429) in ONE kernel (cgs_hg_score): uint8 frames A
+    (rolled) and B [B,64,64,3], mask z [B,64,64] (any shape with B*4096 elements) -> `replaced`/`injected` blends in shared
+    memory -> frozen critic -> MSE against negpred / pred -> backward into the blends, contracted with (B - A) / (A - B),
+    plus the L1/L2 mask regulariser.  Returns (losses [4] = replace, inject, L1, L2 terms; dz [B,64,64] = loss_grad *
+    d(sum)/dZ; pred_replace [B]; pred_inject [B] or None).  No autograd: the caller feeds dz to the masker's backward."""
+    Bn = A_u8.shape[0]
+    dev = A_u8.device
+    w = _lib.CriticWeights(*[_p(q.detach()) for q in critic.parameters()])
+    zc = _c(z.detach())
+    assert zc.numel() == Bn * 4096
+    pr = torch.empty(Bn, device=dev, dtype=torch.float32)
+    pi = torch.empty(Bn, device=dev, dtype=torch.float32) if target_inject is not None else None
+    losses = torch.empty(4, device=dev, dtype=torch.float32)
+    dz = torch.empty((Bn, 64, 64), device=dev, dtype=torch.float32)
+    rd, r = (_p(roll, torch.int32), 0) if torch.is_tensor(roll) else (None, int(roll or 0))
+    m = masks if masks is not None else (None, None, None)
+    mi = masks_inject if masks_inject is not None else (None, None, None)
+    rp, rseed, rstate = _rng_args(rng)
+    _call("cgs_hg_score", _p(A_u8, torch.uint8), _p(B_u8, torch.uint8), Bn, r, rd, _p(zc), _p(_c(target_replace.detach())),
+          _p(_c(target_inject.detach())) if target_inject is not None else None, _p(m[0]), _p(m[1]), _p(m[2]),
+          _p(mi[0]), _p(mi[1]), _p(mi[2]), rp, rseed, rstate, C.byref(w), float(loss_grad),
+          _p(_c(vpred.detach())) if vpred is not None else None, float(l1), float(l2), _p(pr), _p(pi), _p(losses), _p(dz), _stream())
+    return losses, dz, pr, pi
 
 
 def critic_saliency(critic, x_nhwc):

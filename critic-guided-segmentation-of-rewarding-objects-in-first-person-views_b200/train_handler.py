@@ -515,35 +515,40 @@ class Handler:
         self.seg_log = [{k: float(v) for k, v in t.items()} for t in self.seg_log]
 
     # ------------------------------------------------------------------ -process
+    def segment_device(self, xu8, threshold=None):
+        """Loop body of Handler.segment (main.py:1139-1164) for one batch of uint8 NHWC frames already on the device:
+        (pred [B,1], mask [B,1,64,64], hard uint8 [B,1,64,64] or None), all device tensors.  Modules must already be in
+        the wanted train/eval mode.  No autograd."""
+        a = self.args
+        critic, masker = self.critic, self.masker
+        with torch.no_grad():
+            if not a.separate and ops.infer_fused_supported(critic, masker):
+                pred, o0 = ops.infer_encode_decode(critic, masker, xu8)
+                mask, hm = ops.masker_fused(masker, xu8, o0, threshold or None)
+                return pred, mask, hm
+            batch = ops.frames_to_float(xu8, 0).permute(0, 3, 1, 2)
+            pred, embeds = critic(batch, collect=True)
+            if a.separate:
+                _, embeds = self.sepcrit.to(self.device).train(critic.training)(batch, collect=True)
+            if threshold:
+                mask, hm = masker.forward_hard(batch, embeds, threshold)
+                return pred, mask, hm
+            return pred, masker(batch, embeds), None
+
     def segment_arrays(self, X_u8, batchsize=128):
         """Loop of Handler.segment (main.py:1130-1167) on uint8 frames: returns (preds, M, hardM)."""
         a = self.args
         train = bool(a.noevalmode)
-        critic = self.critic.to(self.device).train(train)
-        masker = self.masker.to(self.device).train(train)
+        self.critic.to(self.device).train(train)
+        self.masker.to(self.device).train(train)
         preds, M, hard = [], [], []
-        with torch.no_grad():
-            for bidx in range(0, len(X_u8), batchsize):
-                if not a.separate and ops.infer_fused_supported(critic, masker):
-                    xu8 = torch.from_numpy(np.ascontiguousarray(X_u8[bidx:bidx + batchsize])).to(self.device)
-                    pred, o0 = ops.infer_encode_decode(critic, masker, xu8)
-                    mask, hm = ops.masker_fused(masker, xu8, o0, a.binarymaskthreshold or None)
-                    if hm is not None:
-                        hard.append(hm.cpu().numpy().astype(bool))
-                    preds.append(pred.squeeze(1).cpu().numpy())
-                    M.append(mask.cpu().numpy())
-                    continue
-                batch = self._to_input(X_u8[bidx:bidx + batchsize])
-                pred, embeds = critic(batch, collect=True)
-                if a.separate:
-                    _, embeds = self.sepcrit.to(self.device).train(train)(batch, collect=True)
-                if a.binarymaskthreshold:
-                    mask, hm = masker.forward_hard(batch, embeds, a.binarymaskthreshold)
-                    hard.append(hm.cpu().numpy().astype(bool))
-                else:
-                    mask = masker(batch, embeds)
-                preds.append(pred.squeeze(1).cpu().numpy())
-                M.append(mask.cpu().numpy())
+        for bidx in range(0, len(X_u8), batchsize):
+            xu8 = torch.from_numpy(np.ascontiguousarray(X_u8[bidx:bidx + batchsize])).to(self.device)
+            pred, mask, hm = self.segment_device(xu8, a.binarymaskthreshold)
+            if hm is not None:
+                hard.append(hm.cpu().numpy().astype(bool))
+            preds.append(pred.squeeze(1).cpu().numpy())
+            M.append(mask.cpu().numpy())
         M = np.concatenate(M, axis=0)
         return np.concatenate(preds, axis=0), M, (np.concatenate(hard, axis=0) if hard else None)
 
@@ -562,15 +567,7 @@ class Handler:
             for bidx in range(0, len(X_u8), batchsize):
                 xu8 = torch.from_numpy(np.ascontiguousarray(X_u8[bidx:bidx + batchsize])).to(self.device)
                 gt = torch.from_numpy(GT[bidx:bidx + batchsize]).to(self.device)
-                if not a.separate and ops.infer_fused_supported(critic, masker):
-                    _, o0 = ops.infer_encode_decode(critic, masker, xu8)
-                    mask, _ = ops.masker_fused(masker, xu8, o0, None)
-                else:
-                    batch = ops.frames_to_float(xu8, 0).permute(0, 3, 1, 2)
-                    _, embeds = critic(batch, collect=True)
-                    if a.separate:
-                        _, embeds = self.sepcrit.to(self.device).train(train)(batch, collect=True)
-                    mask = masker(batch, embeds)
+                _, mask, _ = self.segment_device(xu8, None)
                 ops.iou_counts(mask, gt, a.eval_thresh, counts, strict=True)
         inter, union = (int(v) for v in counts.cpu())
         return (round(inter / union, 3) if union else float("nan")), inter, union

@@ -247,6 +247,24 @@ int cgs_p2p_allreduce_adam(float* p, float* m, float* v, int64_t n, int64_t npad
                            const uint64_t* peer_flags, int32_t rank, int32_t world, double lr, double beta1, double beta2,
                            double eps, int32_t* step_state, float grad_scale, int32_t* err_flag, void* stream);
 
+/* The two scored blends of one Hourglass step in ONE kernel (chfak=1 geometry; MODE 3 of the whole-step kernel),
+ * replacing `replaced = A*(1-Z)+Z*B; F.mse_loss(critic(replaced), negpred)`, `injected = B*(1-Z)+Z*A;
+ * F.mse_loss(critic(injected), pred)` and the mask regulariser with their backward into Z (reference main.py:395-429):
+ * frames_a (rolled by `roll` / *roll_dev like shift_batch, main.py:355-357) and frames_b are uint8 [B,64,64,3], z is the
+ * mask [B,64,64]; the blends are formed in shared memory, scored by the FROZEN critic (dropout: forced masks for the
+ * replace and inject passes, or the module's Philox stream - two consecutive calls), and the input gradient is
+ * contracted with (B - A) resp. (A - B) inside the kernel.  target_inject == NULL skips the inject pass (-noinject).
+ * Outputs: pred_replace / pred_inject [B]; losses[4] = {replace, inject, L1 term, L2 term} (means, as the reference
+ * logs them); dz [B,64,64] = loss_grad * d(replace + inject + L1 + L2)/dZ.  vpred != NULL: non-static regulariser
+ * weight 1 - vpred[n] (main.py:418). */
+int cgs_hg_score(const uint8_t* frames_a, const uint8_t* frames_b, int32_t B, int32_t roll, const int32_t* roll_dev,
+                 const float* z, const float* target_replace, const float* target_inject,
+                 const float* m_e2, const float* m_e3, const float* m_v,
+                 const float* m_e2_inj, const float* m_e3_inj, const float* m_v_inj,
+                 float p_drop, uint64_t seed, uint64_t* rng_state, const cgs_critic_weights* w, float loss_grad,
+                 const float* vpred, float l1, float l2, float* pred_replace, float* pred_inject, float* losses,
+                 float* dz, void* stream);
+
 /* Debug only: clock64() phase trace of CTA 0 of the fused critic kernel into dev_buf[4*24] (NULL disables). */
 int cgs_critic_fused_set_trace(long long* dev_buf);
 

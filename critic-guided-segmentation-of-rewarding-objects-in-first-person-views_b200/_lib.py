@@ -37,6 +37,11 @@ class CriticWeights(C.Structure):
     _fields_ = [(n, _f32p) for n in ("w0", "b0", "w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4", "wl1", "bl1", "wl2", "bl2")]
 
 
+class MaskerWeights(C.Structure):
+    """cgs_masker_weights: the 14 UnetDecoder tensors in state_dict order."""
+    _fields_ = [(n, _f32p) for n in ("wd0", "bd0", "wd1", "bd1", "wd2", "bd2", "wd3", "bd3", "wd4", "bd4", "wm0", "bm0", "wm2", "bm2")]
+
+
 class AdamArgs(C.Structure):
     """cgs_adam_args"""
     _fields_ = [("p", _f32p), ("g", _f32p), ("m", _f32p), ("v", _f32p), ("lr", C.c_double), ("beta1", C.c_double),
@@ -60,6 +65,17 @@ EXPORTS = {
     "cgs_hg_score": [_u8p, _u8p, C.c_int32, C.c_int32, C.c_void_p, _f32p, _f32p, _f32p] + [_f32p] * 6 +
                     [C.c_float, C.c_uint64, C.c_void_p, C.POINTER(CriticWeights), C.c_float, _f32p, C.c_float, C.c_float,
                      _f32p, _f32p, _f32p, _f32p, C.c_void_p],
+    "cgs_hg_pack_words": [],
+    "cgs_hg_tape_bytes": [],
+    "cgs_hg_grid": [C.c_int32],
+    "cgs_hg_partial_stride": [],
+    "cgs_hg_debug_floats": [],
+    "cgs_hg_pack": [C.POINTER(CriticWeights), C.POINTER(MaskerWeights), C.c_void_p, C.c_void_p],
+    "cgs_hg_forward": [_u8p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(CriticWeights), C.POINTER(MaskerWeights), C.c_void_p,
+                       C.c_int32, _f32p, _f32p, _f32p, C.c_float, C.c_uint64, C.c_void_p, C.c_float, _f32p, _f32p, _u8p,
+                       C.c_void_p, C.c_void_p],
+    "cgs_hg_backward": [_u8p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(MaskerWeights), C.c_void_p, C.c_void_p, _f32p, _f32p,
+                        _f32p, _f32p, C.c_void_p],
     "cgs_infer_pack_floats": [],
     "cgs_infer_pack_decoder": [_f32p] * 5 + [C.c_void_p],
     "cgs_infer_fused": [_u8p, C.c_int32, C.POINTER(CriticWeights)] + [_f32p] * 9 + [C.c_void_p],

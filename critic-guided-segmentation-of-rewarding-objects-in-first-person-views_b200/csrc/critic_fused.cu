@@ -191,17 +191,6 @@ __device__ __forceinline__ void stage_frame(const uint8_t* __restrict__ sU8, flo
   }
 }
 
-__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-}
-
 // The three dropout masks of frame n, drawn exactly as cgs_dropout_masks would fill [B*512 | B*256 | B*32] floats:
 // 200 threads, one Philox call (4 Bernoulli draws) each.
 __device__ __forceinline__ void draw_masks(const Params& p, int n, unsigned long long call, float* sm, int tid) {

@@ -724,6 +724,83 @@ def masker_fused(masker, frames_u8, o0, thresh=None):
     return mask, hard
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# bf16 whole-frame Hourglass kernels (csrc/hg_forward.cu, csrc/hg_backward.cu)
+def hg_supported(critic, masker):
+    """True when the whole-frame Hourglass kernels cover these modules: chfak = 1 geometry, tensor-core precision mode."""
+    f, d = critic.features, masker.dec
+    return bool(_precision
+                and _lib.lib().cgs_critic_fused_supported(f[0].out_channels, f[3].out_channels, f[6].out_channels,
+                                                          f[10].out_channels, f[14].out_channels)
+                and tuple(d[3].weight.shape) == (16, 48, 3, 3) and tuple(d[0].weight.shape) == (8, 16, 3, 3)
+                and tuple(d[4].weight.shape) == (32, 32, 1, 1) and tuple(masker.masker[0].weight.shape) == (16, 11, 3, 3))
+
+
+def _masker_weights(masker):
+    return _lib.MaskerWeights(*[_p(q.detach()) for q in masker.parameters()])
+
+
+def hg_pack(critic, masker, out=None, cached=True):
+    """Weight fragments of both networks (cgs_hg_pack).  cached: re-packed only when a weight tensor's version (or the
+    global weights epoch, bumped by the optimizer kernels) changes; out: pack into this buffer unconditionally (training:
+    one launch per step, CUDA-graph capturable)."""
+    L = _lib.lib()
+    dev = next(masker.parameters()).device
+    if out is None and cached:
+        ver = (_weights_epoch,) + tuple((q.data_ptr(), q._version) for q in list(critic.parameters()) + list(masker.parameters()))
+        cache = getattr(masker, "_cgs_hg_pack", None)
+        if cache is not None and cache[0] == ver:
+            return cache[1]
+    pack = out if out is not None else torch.empty(L.cgs_hg_pack_words(), device=dev, dtype=torch.int32)
+    cw = _lib.CriticWeights(*[_p(q.detach()) for q in critic.parameters()])
+    mw = _masker_weights(masker)
+    _call("cgs_hg_pack", C.byref(cw), C.byref(mw), _p(pack, torch.int32), _stream())
+    if out is None and cached:
+        masker._cgs_hg_pack = (ver, pack)
+    return pack
+
+
+def hg_forward(critic, masker, frames_u8, roll=0, train=False, masks=None, rng=None, thresh=None, tape=None, pack=None):
+    """critic(X, collect=True) + masker(X, embeds) on raw uint8 frames in ONE kernel (cgs_hg_forward).
+    Returns (pred [B,1], mask [B,1,64,64], hard uint8 [B,1,64,64] or None).  train: dropout (masks = forced NHWC triple,
+    or rng = critic._dropout_rng()); tape: uint8 [B, cgs_hg_tape_bytes()] buffer for hg_backward."""
+    B = frames_u8.shape[0]
+    dev = frames_u8.device
+    if pack is None:
+        pack = hg_pack(critic, masker)
+    cw = _lib.CriticWeights(*[_p(q.detach()) for q in critic.parameters()])
+    mw = _masker_weights(masker)
+    pred = torch.empty(B, device=dev, dtype=torch.float32)
+    mask = torch.empty((B, 1, 64, 64), device=dev, dtype=torch.float32)
+    hard = torch.empty((B, 1, 64, 64), device=dev, dtype=torch.uint8) if thresh is not None else None
+    rd, r = (_p(roll, torch.int32), 0) if torch.is_tensor(roll) else (None, int(roll or 0))
+    m = masks if masks is not None else (None, None, None)
+    rp, rseed, rstate = _rng_args(rng)
+    _call("cgs_hg_forward", _p(frames_u8, torch.uint8), B, r, rd, C.byref(cw), C.byref(mw), _p(pack, torch.int32), int(bool(train)),
+          _p(m[0]), _p(m[1]), _p(m[2]), rp, rseed, rstate, float(thresh if thresh is not None else 0.0), _p(pred), _p(mask),
+          _p(hard, torch.uint8), _p(tape, torch.uint8), _stream())
+    return pred.unsqueeze(1), mask, hard
+
+
+def hg_tape(B, device):
+    return torch.empty((B, _lib.lib().cgs_hg_tape_bytes()), device=device, dtype=torch.uint8)
+
+
+def hg_backward(masker, frames_u8, tape, mask, dz, roll=0, pack=None, partials=None, debug=None):
+    """The masker's whole backward in ONE kernel (cgs_hg_backward): returns (partials [grid, stride], grid)."""
+    L = _lib.lib()
+    B = frames_u8.shape[0]
+    grid, stride = L.cgs_hg_grid(B), L.cgs_hg_partial_stride()
+    if partials is None:
+        partials = torch.empty((grid, stride), device=frames_u8.device, dtype=torch.float32)
+    assert partials.numel() >= grid * stride
+    mw = _masker_weights(masker)
+    rd, r = (_p(roll, torch.int32), 0) if torch.is_tensor(roll) else (None, int(roll or 0))
+    _call("cgs_hg_backward", _p(frames_u8, torch.uint8), B, r, rd, C.byref(mw), _p(pack, torch.int32), _p(tape, torch.uint8),
+          _p(_c(mask.detach())), _p(_c(dz.detach())), _p(partials), _p(debug), _stream())
+    return partials, grid
+
+
 def reduce_partials(g, buf, n_partials, stride, offset, length):
     _call("cgs_reduce_partials", _p(g), g.numel(), _p(buf), int(n_partials), int(stride), int(offset), int(length), _stream())
 

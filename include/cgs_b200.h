@@ -306,6 +306,40 @@ int cgs_adam_step(float* p, float* g, float* m, float* v, int64_t n,
                   double lr, double beta1, double beta2, double eps, int32_t* step_state,
                   float grad_scale, int32_t clear_grad, void* stream);
 
+/* ---- bf16 whole-frame Hourglass kernels (csrc/hg_forward.cu, csrc/hg_backward.cu), chfak=1 geometry ----------------------
+ * UnetDecoder parameters in state_dict order (reference nets.py:479-491): dec_model.{0..4}, masker.{0,2}; OIHW fp32. */
+typedef struct cgs_masker_weights {
+  float *wd0, *bd0, *wd1, *bd1, *wd2, *bd2, *wd3, *bd3, *wd4, *bd4, *wm0, *bm0, *wm2, *bm2;
+} cgs_masker_weights;
+
+/* Weight fragments of every convolution of both networks in bf16 mma.sync B-fragment order: cgs_hg_pack_words() uint32 words,
+ * 16-byte aligned; re-pack whenever a weight changes (one small launch). */
+int cgs_hg_pack_words(void);
+int cgs_hg_pack(const cgs_critic_weights* cw, const cgs_masker_weights* mw, uint32_t* pack, void* stream);
+/* The Hourglass forward in ONE kernel: uint8 NHWC frames [B,64,64,3] (circularly rolled along W by roll / *roll_dev, the
+ * shift_batch augmentation, main.py:584-591) -> /255 -> NewCritic.forward(collect=True) (nets.py:197-212) ->
+ * UnetDecoder.forward (nets.py:494-523) -> z [B,64,64] fp32 mask, pred [B], hard [B,64,64] = z >= thresh (main.py:1164;
+ * may be NULL).  train != 0: dropout applied (forced masks m_e2 [B,8,8,8] / m_e3 [B,4,4,16] / m_v [B,32], or drawn in the
+ * kernel from (seed, rng_state) exactly as cgs_dropout_masks would).  tape != NULL: B * cgs_hg_tape_bytes() bytes receive
+ * every skip / decoder activation of each frame (haloed bf16 planes) for cgs_hg_backward.
+ * Replaces `critic(A, collect=True)` + `masker(A, embeds)` of main.py:364,391 and main.py:1139-1164. */
+int cgs_hg_tape_bytes(void);
+int cgs_hg_forward(const uint8_t* frames, int32_t B, int32_t roll, const int32_t* roll_dev, const cgs_critic_weights* cw,
+                   const cgs_masker_weights* mw, const uint32_t* pack, int32_t train, const float* m_e2, const float* m_e3,
+                   const float* m_v, float p_drop, uint64_t seed, uint64_t* rng_state, float thresh, float* pred, float* z,
+                   uint8_t* hard, void* tape, void* stream);
+/* The masker's whole backward in ONE kernel (the autograd backward of nets.py:494-523 w.r.t. the 13,785 UnetDecoder
+ * parameters, critic frozen: main.py:334, 462): frames / roll / tape / z as given to / written by cgs_hg_forward, dz
+ * [B,64,64] = d loss / d z.  Output: one partial gradient vector per CTA, partials[cta * cgs_hg_partial_stride() + i],
+ * i in state_dict order, cta < cgs_hg_grid(B); cgs_adam_step_partials / cgs_reduce_partials sum them in a fixed order.
+ * debug: NULL, or cgs_hg_debug_floats() floats that receive frame 0's decoder-activation gradients (tests only). */
+int cgs_hg_grid(int32_t B);
+int cgs_hg_partial_stride(void);
+int cgs_hg_debug_floats(void);
+int cgs_hg_backward(const uint8_t* frames, int32_t B, int32_t roll, const int32_t* roll_dev, const cgs_masker_weights* mw,
+                    const uint32_t* pack, const void* tape, const float* z, const float* dz, float* partials, float* debug,
+                    void* stream);
+
 /* All nn.Dropout masks of one NewCritic forward (nets.py:179,183,192) in one launch: out[i] = Bernoulli(1-p)/(1-p),
  * Philox4x32-10 keyed by (seed, state[0]); state = {call counter, ticket} in device memory, advanced by the kernel
  * itself so that CUDA-graph replays draw fresh masks.  out must be 16-byte aligned. */

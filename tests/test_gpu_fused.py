@@ -475,7 +475,7 @@ def test_infer_pack_follows_optimizer_steps(ops, monkeypatch):
 # ---------------------------------------------------------------------------------------------------------------------
 # The tensor-core Hourglass step (the BASELINE configs[2] path) pinned at step level against the goldens the unmodified
 # reference produced (tests/golden/step_c*.npz) and against the oracle on fresh inputs.
-TC_TERM_RTOL, TC_Z_ATOL, TC_G_TOTAL, TC_G_TENSOR = 5e-3, 2e-2, 2e-2, 6e-2
+TC_TERM_RTOL, TC_Z_ATOL, TC_G_TOTAL, TC_G_TENSOR = 5e-3, 2e-2, 2.5e-2, 6e-2
 
 
 def _tc_hourglass(H, A, Bf, Y, masks_nhwc):

@@ -1,0 +1,243 @@
+"""GPU: the bf16 whole-frame Hourglass kernels (cgs_hg_forward / cgs_hg_backward, csrc/hg_*.cu) against the CPU fp32 oracle.
+
+Forward: every intermediate the kernel leaves on its tape (skip maps e0..e3, h, dec[4] output, decoder maps o3..o0), pred
+and the mask are compared with the oracle's tensors on the same frames and weights.  Backward: the 14 masker gradient
+tensors (and, through the debug buffer, the gradient of every decoder map of frame 0) against torch autograd over the
+oracle, for a given d loss / d mask.  Tolerances are bf16 ones: operands carry 8 mantissa bits (2^-9 relative rounding),
+accumulation is fp32; values are held to 2e-2 of the tensor scale, gradients to a few % norm-wise; the model-level bounds of
+BASELINE.json's north star (|mask - ref| <= 2e-2, IoU >= 0.99 @0.1) are asserted on the mask itself."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import load_golden
+from oracle import torch_ref
+import cgs_b200.synth as synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TAPE = dict(e0=(0, 34, 1), o0=(18496, 34, 1), e1=(36992, 18, 1), o1=(42176, 18, 1), e2=(47360, 10, 1), o2=(48960, 10, 1),
+            c3=(50560, 6, 6), o3=(54016, 6, 2))
+TAPE_H = 55168
+
+
+@pytest.fixture()
+def ops():
+    import cgs_b200.ops as o
+    o.set_precision("tf32")
+    yield o
+    o.set_precision("fp32")
+
+
+def _models(csd, msd, p, train):
+    from cgs_b200.nets import NewCritic, UnetDecoder
+    c = NewCritic(dropout=p)
+    m = UnetDecoder()
+    c.load_state_dict({k: torch.from_numpy(v) for k, v in csd.items()})
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in msd.items()})
+    c.to(DEV); m.to(DEV)
+    (c.train(), m.train()) if train else (c.eval(), m.eval())
+    return c, m
+
+
+def _case(B, p, seed, scale=1.5):
+    csd = synth.perturbed_state(synth.critic_shapes(1), seed, scale)
+    msd = synth.perturbed_state(synth.masker_shapes(1), seed + 1, scale)
+    X, _, _ = synth.synthetic_frames(B, seed=seed)
+    rng = np.random.default_rng(seed)
+    mk = lambda *s: ((rng.random(s) >= p).astype(np.float32) / np.float32(1 - p)) if p > 0 else np.ones(s, np.float32)
+    masks = (mk(B, 8, 8, 8), mk(B, 16, 4, 4), mk(B, 32))            # logical NCHW
+    return csd, msd, X, masks
+
+
+def oracle_forward(csd, msd, X, roll, masks, grad=False):
+    """torch_ref.critic_forward + torch_ref.decoder_forward (reference nets.py:197-212, 494-523) with every decoder
+    intermediate kept (the restatement below is line for line oracle/torch_ref.py::decoder_forward)."""
+    c = {k: torch.from_numpy(v) for k, v in csd.items()}
+    m = {k: torch.from_numpy(v).clone().requires_grad_(grad) for k, v in msd.items()}
+    x = torch_ref.to_input(np.roll(X, -roll, axis=2))
+    pred, embeds = torch_ref.critic_forward(c, x, collect=True, masks=masks)
+    embeds = [e.detach() for e in embeds]
+    up = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")
+    t = {}
+    t["d4"] = F.conv2d(embeds[4], m["dec_model.4.weight"], m["dec_model.4.bias"])
+    t["o3"] = F.conv2d(torch.cat((embeds[3], up(up(t["d4"]))), 1), m["dec_model.3.weight"], m["dec_model.3.bias"], padding=1)
+    t["o2"] = F.conv2d(torch.cat((embeds[2], up(t["o3"])), 1), m["dec_model.2.weight"], m["dec_model.2.bias"], padding=1)
+    t["o1"] = F.conv2d(torch.cat((embeds[1], up(t["o2"])), 1), m["dec_model.1.weight"], m["dec_model.1.bias"], padding=1)
+    t["o0"] = F.conv2d(torch.cat((embeds[0], up(t["o1"])), 1), m["dec_model.0.weight"], m["dec_model.0.bias"], padding=1)
+    m0 = F.leaky_relu(F.conv2d(torch.cat((x, up(t["o0"])), 1), m["masker.0.weight"], m["masker.0.bias"], padding=1), 0.01)
+    z = torch.sigmoid(F.conv2d(m0, m["masker.2.weight"], m["masker.2.bias"], padding=1))
+    z_ref = torch_ref.decoder_forward({k: v.detach() for k, v in m.items()}, x, embeds)
+    assert torch.equal(z.detach(), z_ref), "test-local decoder restatement drifted from the oracle"
+    return pred.detach(), embeds, t, z, m
+
+
+def tape_planes(tape, B):
+    """uint8 [B, TAPE] -> dict of fp32 NCHW interiors."""
+    out = {}
+    for k, (off, P, npl) in TAPE.items():
+        raw = tape[:, off:off + npl * P * P * 16].contiguous().view(torch.bfloat16).view(B, npl, P, P, 8).float()
+        out[k] = raw[:, :, 1:-1, 1:-1, :].permute(0, 1, 4, 2, 3).reshape(B, npl * 8, P - 2, P - 2).cpu()
+        halo = raw.clone()
+        halo[:, :, 1:-1, 1:-1, :] = 0
+        assert float(halo.abs().max()) == 0.0, f"tape plane {k}: halo is not zero"
+    out["h"] = tape[:, TAPE_H:TAPE_H + 128].contiguous().view(torch.float32).cpu()
+    return out
+
+
+def _close(a, b, what, rel=2e-2, atol=2e-3):
+    a, b = a.double(), b.double()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = (a - b).abs().max().item()
+    tol = rel * b.abs().max().item() + atol
+    assert err <= tol, f"{what}: max abs err {err:.3e} > {tol:.3e} (ref scale {b.abs().max().item():.3e})"
+
+
+@pytest.mark.parametrize("B,roll,p,train", [(3, 0, 0.0, False), (5, 5, 0.3, True), (150, -9, 0.3, True), (19, 63, 0.0, False)])
+def test_hg_forward_vs_oracle(ops, B, roll, p, train):
+    from helpers import nhwc_masks
+    csd, msd, X, masks = _case(B, p, seed=31 + B)
+    c, m = _models(csd, msd, p, train)
+    use_masks = train and p > 0
+    pred_r, embeds, t, z_r, _ = oracle_forward(csd, msd, X, roll % 64, tuple(torch.from_numpy(a) for a in masks) if use_masks else None)
+    tape = ops.hg_tape(B, DEV)
+    tape.fill_(0x7f)
+    pred, z, hard = ops.hg_forward(c, m, torch.from_numpy(X).to(DEV), roll=roll, train=train,
+                                   masks=nhwc_masks(masks, DEV) if use_masks else None, thresh=0.1, tape=tape)
+    torch.cuda.synchronize()
+    tp = tape_planes(tape, B)
+    for k, ref in (("e0", embeds[0]), ("e1", embeds[1]), ("e2", embeds[2])):
+        _close(tp[k], ref, k)
+    _close(tp["c3"][:, :16], embeds[3], "e3")
+    _close(tp["h"], embeds[4].flatten(1), "h")
+    _close(tp["c3"][:, 16:], t["d4"].detach().expand(-1, -1, 4, 4), "dec4 (broadcast)")
+    for k in ("o3", "o2", "o1", "o0"):
+        _close(tp[k], t[k].detach(), k)
+    _close(pred.cpu(), pred_r, "pred", rel=0, atol=5e-3)
+    zc = z.cpu()
+    err = (zc - z_r.detach()).abs().max().item()
+    assert err <= 2e-2, f"|mask - oracle| = {err:.3e}"
+    assert torch.equal(hard.cpu().bool(), zc >= 0.1)
+    hr = z_r.detach() >= 0.1
+    inter, union = (hard.cpu().bool() & hr).sum().item(), (hard.cpu().bool() | hr).sum().item()
+    assert union == 0 or inter / union >= 0.99
+
+
+def test_hg_forward_on_reference_trained_checkpoint(ops):
+    """The model-level bounds of the north star on the weights the unmodified reference loops trained (loops_c1.npz)."""
+    d = load_golden("loops_c1.npz")
+    csd = {k[len("trained.c."):]: d[k] for k in d.files if k.startswith("trained.c.")}
+    msd = {k[len("trained.m."):]: d[k] for k in d.files if k.startswith("trained.m.")}
+    assert len(csd) == 14 and len(msd) == 14
+    X, _, _ = synth.synthetic_frames(64, seed=5)
+    c, m = _models(csd, msd, 0.3, False)
+    pred_r, _, _, z_r, _ = oracle_forward(csd, msd, X, 0, None)
+    pred, z, hard = ops.hg_forward(c, m, torch.from_numpy(X).to(DEV), thresh=0.1)
+    assert (z.cpu() - z_r.detach()).abs().max().item() <= 2e-2
+    hr = z_r.detach() >= 0.1
+    hb = hard.cpu().bool()
+    assert (hb | hr).sum().item() == 0 or (hb & hr).sum().item() / (hb | hr).sum().item() >= 0.99
+    assert (pred.cpu() - pred_r).abs().max().item() <= 5e-3
+
+
+def test_hg_forward_rng_matches_mask_kernel(ops):
+    """Dropout drawn in the kernel == the stream cgs_dropout_masks writes for the same (seed, call)."""
+    B, p = 9, 0.3
+    csd, msd, X, _ = _case(B, p, seed=77)
+    c, m = _models(csd, msd, p, True)
+    Xd = torch.from_numpy(X).to(DEV)
+    rng = c._dropout_rng(Xd.device)
+    if rng is None:
+        pytest.skip("critic has no in-kernel dropout stream in this configuration")
+    state0 = rng[2].clone()
+    pred1, z1, _ = ops.hg_forward(c, m, Xd, train=True, rng=rng)
+    torch.cuda.synchronize()
+    assert int(rng[2][0]) == int(state0[0]) + 1, "the kernel must advance the call counter by one"
+    rng[2].copy_(state0)
+    masks = c._dropout_masks(B, Xd.device)                    # the mask kernel's draw for the same call index
+    pred2, z2, _ = ops.hg_forward(c, m, Xd, train=True, masks=masks)
+    assert torch.equal(pred1, pred2) and torch.equal(z1, z2)
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.mark.parametrize("B,roll,p", [(3, 0, 0.0), (7, 5, 0.3), (160, -3, 0.3)])
+def test_hg_backward_vs_oracle(ops, B, roll, p):
+    from helpers import nhwc_masks
+    csd, msd, X, masks = _case(B, p, seed=51 + B)
+    c, m = _models(csd, msd, p, True)
+    use_masks = p > 0
+    _, _, t, z_r, mp = oracle_forward(csd, msd, X, roll % 64, tuple(torch.from_numpy(a) for a in masks) if use_masks else None, grad=True)
+    g = torch.Generator().manual_seed(5)
+    dz = torch.randn(z_r.shape, generator=g) * (1.0 / B)
+    inter = [t["o0"], t["o1"], t["o2"], t["o3"], t["d4"]]
+    grads = torch.autograd.grad(z_r, inter + [mp[k] for k in msd], dz)
+    gi, gp = grads[:5], dict(zip(msd.keys(), grads[5:]))
+    Xd = torch.from_numpy(X).to(DEV)
+    tape = ops.hg_tape(B, DEV)
+    pack = ops.hg_pack(c, m)
+    _, z, _ = ops.hg_forward(c, m, Xd, roll=roll, train=True, masks=nhwc_masks(masks, DEV) if use_masks else None, tape=tape, pack=pack)
+    from cgs_b200 import _lib
+    dbg = torch.zeros(_lib.lib().cgs_hg_debug_floats(), device=DEV)
+    partials, grid = ops.hg_backward(m, Xd, tape, z, dz.to(DEV), roll=roll, pack=pack, debug=dbg)
+    torch.cuda.synchronize()
+    # ---- frame 0's decoder-map gradients from the debug buffer (bf16 planes) vs autograd
+    raw = dbg.view(torch.int32)
+    off = 0
+    fails = []
+    for name, P, npl, ref in (("d o0", 34, 1, gi[0]), ("d o1", 18, 1, gi[1]), ("d o2", 10, 1, gi[2]), ("d o3", 6, 2, gi[3])):
+        nwords = npl * P * P * 4
+        pl = raw[off:off + nwords].contiguous().view(torch.bfloat16).view(npl, P, P, 8).float()[:, 1:-1, 1:-1, :]
+        got = pl.permute(0, 3, 1, 2).reshape(npl * 8, P - 2, P - 2).cpu()
+        off += nwords
+        r = _rel(got.numpy(), ref[0].numpy())
+        if r > 3e-2:
+            fails.append((name, r))
+    dd4 = dbg[off:off + 32].cpu()
+    r = _rel(dd4.numpy(), gi[4][0].flatten().numpy())
+    if r > 3e-2:
+        fails.append(("d dec4", r))
+    # ---- the 14 gradient tensors: sum of the per-CTA partial vectors
+    flat = partials[:grid].double().sum(0).cpu().numpy()
+    offp = 0
+    worst = {}
+    num = den = 0.0
+    for k in msd:
+        ref = gp[k].numpy().reshape(-1).astype(np.float64)
+        got = flat[offp:offp + ref.size]
+        offp += ref.size
+        worst[k] = _rel(got, ref)
+        num += ((got - ref) ** 2).sum(); den += (ref ** 2).sum()
+    assert offp == 13785
+    tot = float(np.sqrt(num / den))
+    assert not fails and tot <= 2e-2 and max(worst.values()) <= 4e-2, (fails, tot, worst)
+    assert float(np.abs(flat[13785:]).max()) == 0.0, "padding of the partial vector must stay zero"
+
+
+def test_hg_backward_is_linear_and_reproducible(ops):
+    """Size-independent properties at BASELINE's batch (1024 frames): backward(a*dz1 + dz2) == a*backward(dz1) + backward(dz2)
+    up to bf16 rounding of the staged gradient, and two launches give bit-identical partial vectors."""
+    B, p = 1024, 0.3
+    csd, msd, _, _ = _case(4, p, seed=3)
+    X, _, _ = synth.synthetic_frames(B, seed=9)
+    c, m = _models(csd, msd, p, True)
+    Xd = torch.from_numpy(X).to(DEV)
+    tape = ops.hg_tape(B, DEV)
+    pack = ops.hg_pack(c, m)
+    _, z, _ = ops.hg_forward(c, m, Xd, train=False, tape=tape, pack=pack)
+    g = torch.Generator().manual_seed(1)
+    dz1 = (torch.randn(B, 64, 64, generator=g) / B).to(DEV)
+    dz2 = (torch.randn(B, 64, 64, generator=g) / B).to(DEV)
+    run = lambda dz: ops.hg_backward(m, Xd, tape, z, dz, pack=pack)
+    pa, grid = run(dz1)
+    pa = pa.clone()
+    pb = run(dz1)[0]
+    assert torch.equal(pa, pb), "partial vectors must be bit-reproducible"
+    s = lambda q: q[:grid].double().sum(0)[:13785]
+    g1, g2, g12 = s(pa), s(run(dz2)[0]), s(run(2.0 * dz1 + dz2)[0])
+    r = float(((2 * g1 + g2) - g12).norm() / g12.norm())
+    assert r <= 1e-2, r

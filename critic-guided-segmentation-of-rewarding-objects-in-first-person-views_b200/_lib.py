@@ -62,6 +62,8 @@ EXPORTS = {
                                                                              C.c_int64, C.c_int64, C.c_int64, C.c_void_p],
     "cgs_critic_loss_xgrad": [_f32p, _f32p, C.c_int32, _f32p, _f32p, _f32p, C.c_float, C.c_uint64, C.c_void_p,
                               C.POINTER(CriticWeights), C.c_float, C.c_int32, _f32p, _f32p, _f32p, C.c_void_p],
+    "cgs_critic_forward_frames": [_u8p, C.c_int32, C.c_int32, C.c_void_p, _f32p, _f32p, _f32p, C.c_float, C.c_uint64, C.c_void_p,
+                                  C.POINTER(CriticWeights), _f32p, C.c_void_p],
     "cgs_hg_score": [_u8p, _u8p, C.c_int32, C.c_int32, C.c_void_p, _f32p, _f32p, _f32p] + [_f32p] * 6 +
                     [C.c_float, C.c_uint64, C.c_void_p, C.POINTER(CriticWeights), C.c_float, _f32p, C.c_float, C.c_float,
                      _f32p, _f32p, _f32p, _f32p, C.c_void_p],
@@ -103,6 +105,9 @@ EXPORTS = {
     "cgs_threshold": [_f32p, C.c_int64, C.c_float, C.c_int32, _u8p, C.c_void_p],
     "cgs_dropout_masks": [_f32p, C.c_int64, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p],
     "cgs_iou_counts": [_f32p, _u8p, C.c_int64, C.c_float, C.c_int32, C.c_void_p, C.c_void_p],
+    "cgs_gather_frames": [_u8p, C.c_int64, C.c_void_p, C.c_int32, _u8p, C.c_void_p],
+    "cgs_mask_images": [_f32p, _u8p, C.c_int32, _u8p, _u8p, C.c_int32, _u8p, _u8p, C.c_void_p],
+    "cgs_saliency_normalize": [_f32p, _f32p, C.c_int32, C.c_int32, C.c_float, _f32p, _f32p, _u8p, _f32p, C.c_void_p],
     "cgs_tc_status": [],
     "cgs_tc_set_trace": [C.c_void_p],
     "cgs_critic_fused_set_trace": [C.c_void_p],

@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
     asm volatile("cp.async.wait_all;\n" ::);
     __syncthreads();
     if (BL) stage_blend(sA8, sB8, p.zmask + (size_t)n * 4096, which, roll, sm + oX, tid);
-    else if (XG) stage_frame_f32(p.xin + (size_t)n * 12288, sm + oX, tid);
+    else if (XG && !p.frames) stage_frame_f32(p.xin + (size_t)n * 12288, sm + oX, tid);
     else stage_frame(reinterpret_cast<const uint8_t*>(sm + oU8), sm + oX, roll, tid);
     if (tid < 264) {   // e0 halo ring (region A is reused by the re-staged frame), both half-planes
       const int h = tid >= 132, q = tid - 132 * h;
@@ -1267,6 +1267,33 @@ extern "C" int cgs_critic_loss_xgrad(const float* x, const float* target, int32_
   if (cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) return check_launch("critic_loss_xgrad.memset");
   cf::critic_fused_kernel<1><<<cgs_critic_fused_grid(B), cf::NT, cf::SMEM_FLOATS * 4, st>>>(p);
   return check_launch("critic_loss_xgrad");
+}
+
+// pred = critic(frames) for raw uint8 frames, forward only (MODE 2 with the uint8 staging of the training kernel):
+// `negpred = critic(B)` of the Hourglass loop (main.py:365-367) and extract_contrastive_data (main.py:238-260) without an
+// fp32 copy of the batch.
+extern "C" int cgs_critic_forward_frames(const uint8_t* frames, int32_t B, int32_t roll, const int32_t* roll_dev, const float* m_e2,
+                                         const float* m_e3, const float* m_v, float p_drop, uint64_t seed, uint64_t* rng_state,
+                                         const cgs_critic_weights* w, float* pred, void* stream) {
+  CGS_REQUIRE(frames && w && pred && B > 0, "critic_forward_frames: bad args");
+  CGS_REQUIRE(((uintptr_t)frames & 15) == 0, "critic_forward_frames: frames must be 16-byte aligned");
+  CGS_REQUIRE((m_e2 != nullptr) == (m_e3 != nullptr) && (m_e2 != nullptr) == (m_v != nullptr),
+              "critic_forward_frames: dropout masks are all-or-none");
+  CGS_REQUIRE((((uintptr_t)m_e2 | (uintptr_t)m_e3 | (uintptr_t)m_v) & 15) == 0, "critic_forward_frames: masks must be 16-byte aligned");
+  CGS_REQUIRE(!(rng_state && m_e2), "critic_forward_frames: pass dropout masks OR an rng state, not both");
+  CGS_REQUIRE(!rng_state || (p_drop > 0.f && p_drop < 1.f), "critic_forward_frames: rng dropout needs 0 < p < 1");
+  cf::Params p;
+  memset(&p, 0, sizeof(p));
+  p.frames = frames; p.target = pred; p.m2 = m_e2; p.m3 = m_e3; p.mv = m_v;
+  p.w0 = w->w0; p.b0 = w->b0; p.w1 = w->w1; p.b1 = w->b1; p.w2 = w->w2; p.b2 = w->b2; p.w3 = w->w3; p.b3 = w->b3;
+  p.w4 = w->w4; p.b4 = w->b4; p.wl1 = w->wl1; p.bl1 = w->bl1; p.wl2 = w->wl2; p.bl2 = w->bl2;
+  p.seed = seed; p.rng_state = (unsigned long long*)rng_state; p.p_drop = p_drop;
+  p.keep = rng_state ? 1.f / (1.f - p_drop) : 1.f;
+  p.world = 1; p.pred = pred; p.B = B; p.roll = roll; p.roll_dev = roll_dev;
+  p.inv_n = 1.f / (float)B; p.gscale = 0.f;
+  cudaFuncSetAttribute(cf::critic_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf::SMEM_FLOATS * 4);
+  cf::critic_fused_kernel<2><<<cgs_critic_fused_grid(B), cf::NT, cf::SMEM_FLOATS * 4, (cudaStream_t)stream>>>(p);
+  return check_launch("critic_forward_frames");
 }
 
 extern "C" int cgs_hg_score(const uint8_t* frames_a, const uint8_t* frames_b, int32_t B, int32_t roll, const int32_t* roll_dev,

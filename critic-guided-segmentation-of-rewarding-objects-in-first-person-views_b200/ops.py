@@ -679,6 +679,19 @@ def critic_forward_fused(critic, x_nhwc, masks=(None, None, None), rng=None):
     return pred.unsqueeze(1)
 
 
+def critic_forward_frames(critic, frames_u8, roll=0, masks=(None, None, None), rng=None):
+    """pred [B,1] = critic(frames / 255) on raw uint8 NHWC frames in ONE kernel, no autograd (cgs_critic_forward_frames)."""
+    B = frames_u8.shape[0]
+    w = _lib.CriticWeights(*[_p(q.detach()) for q in critic.parameters()])
+    pred = torch.empty(B, device=frames_u8.device, dtype=torch.float32)
+    rd, r = (_p(roll, torch.int32), 0) if torch.is_tensor(roll) else (None, int(roll or 0))
+    m2, m3, mv = masks
+    rp, rseed, rstate = _rng_args(rng)
+    _call("cgs_critic_forward_frames", _p(frames_u8, torch.uint8), B, r, rd, _p(m2), _p(m3), _p(mv), rp, rseed, rstate, C.byref(w),
+          _p(pred), _stream())
+    return pred.unsqueeze(1)
+
+
 def infer_fused_supported(critic, masker):
     """True when the fused encoder+decoder inference kernel covers these modules (chfak=1 geometry, tf32 mode, eval)."""
     f, d = critic.features, masker.dec
@@ -867,3 +880,58 @@ def pred_loss(pred, target, bce=False):
 
 def mask_reg(z, vpred=None, l1=0.0, l2=0.0):
     return MaskReg.apply(z, vpred, l1, l2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# formats either side of the path (csrc/edges.cu)
+def gather_frames(dataset_u8, idx_i32, out=None):
+    """out[i] = dataset[idx[i]]: the contrastive batches of main.py:345-353 from a device-resident uint8 dataset."""
+    n = idx_i32.numel()
+    if out is None:
+        out = torch.empty((n,) + tuple(dataset_u8.shape[1:]), device=dataset_u8.device, dtype=torch.uint8)
+    assert dataset_u8[0].numel() == 12288 and out.numel() == n * 12288
+    _call("cgs_gather_frames", _p(dataset_u8, torch.uint8), dataset_u8.shape[0], _p(idx_i32, torch.int32), n, _p(out, torch.uint8), _stream())
+    return out
+
+
+_FRAME_LUT = {}
+
+
+def _frame_lut(device):
+    """(b / 255.0 * 255).astype(uint8) for b = 0..255, computed exactly as the reference does (float64, main.py:1127, 1216)."""
+    if device not in _FRAME_LUT:
+        import numpy as np
+        _FRAME_LUT[device] = torch.from_numpy(((np.arange(256, dtype=np.uint8) / 255.0) * 255).astype(np.uint8)).to(device)
+    return _FRAME_LUT[device]
+
+
+def mask_images(mask, hard, frames_u8=None, concatenated=False):
+    """PNG-ready uint8 images of main.py:1212-1223: (raw [B,64,64,3], thresholded [B,64,64,3]), or the `-concatenated` strip
+    [B,64,192,3] = frame | raw-mask | thresholded-mask."""
+    B = mask.shape[0]
+    dev = mask.device
+    m, h = _c(mask.detach()).reshape(B, 64, 64), _c(hard).reshape(B, 64, 64)
+    if concatenated:
+        strip = torch.empty((B, 64, 192, 3), device=dev, dtype=torch.uint8)
+        _call("cgs_mask_images", _p(m), _p(h, torch.uint8), B, _p(frames_u8, torch.uint8), _p(_frame_lut(dev), torch.uint8), 1,
+              _p(strip, torch.uint8), None, _stream())
+        return strip
+    raw = torch.empty((B, 64, 64, 3), device=dev, dtype=torch.uint8)
+    thr = torch.empty((B, 64, 64, 3), device=dev, dtype=torch.uint8)
+    _call("cgs_mask_images", _p(m), _p(h, torch.uint8), B, None, None, 0, _p(raw, torch.uint8), _p(thr, torch.uint8), _stream())
+    return raw, thr
+
+
+def saliency_normalize(sal, pred, thresh, global_norm=False):
+    """The saliency baseline's normalisation and threshold (main.py:974-993): returns (salM [B,1,64,64], salhardM uint8)."""
+    B = sal.shape[0]
+    s = _c(sal.detach()).reshape(B, 4096)
+    pr = _c(pred.detach()).reshape(B)
+    out = torch.empty((B, 1, 64, 64), device=s.device, dtype=torch.float32)
+    hard = torch.empty((B, 1, 64, 64), device=s.device, dtype=torch.uint8)
+    gn = None
+    if global_norm:                                     # norm = (salM * (salM >= 0)).mean() * thresh, main.py:978
+        gn = ((s * (s >= 0)).mean() * thresh).reshape(1).float()
+    _call("cgs_saliency_normalize", _p(s), _p(pr), B, int(64 * 64 * thresh), float(thresh), _p(gn), _p(out), _p(hard, torch.uint8), None,
+          _stream())
+    return out, hard

@@ -21,17 +21,19 @@ from itertools import chain
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from .nets import NewCritic, UnetDecoder
 
 
 def build_parser():
     """The hot-path subset of reference main.py:1462-1533, same names and defaults."""
     p = argparse.ArgumentParser()
-    for flag in ("-train", "-frozen", "-noinject", "-separate", "-noevalmode", "-process", "-eval", "-salience"):
+    for flag in ("-train", "-frozen", "-noinject", "-separate", "-noevalmode", "-process", "-eval", "-test", "-salience",
+                 "-process_salience", "-concatenated"):
         p.add_argument(flag, action="store_true")
-    for flag in ("-masker", "-critic", "-cload", "-mload", "-staticnorm"):
+    for flag in ("-masker", "-critic", "-cload", "-mload", "-staticnorm", "-salglobal"):
         p.add_argument(flag, type=bool, default=True)
+    p.add_argument("--salience-thresh", type=float, default=1.5)
     p.add_argument("--eval-thresh", type=float, default=0.05)
     p.add_argument("--dropout", type=float, default=0.3)
     p.add_argument("--threshrew", type=float, default=0)
@@ -252,6 +254,7 @@ class Handler:
                            self.maskername: f"{self.save_path}masker-{self.masker_args}.pt"}
         self.contrastive_batchsize = 32      # main.py:309
         self.fused_critic_step = True        # tf32 mode, chfak 1: one kernel per critic_pipe step
+        self.hg_inference = True             # tensor-core mode, chfak 1: -process in ONE bf16 kernel (csrc/hg_forward.cu)
         self.closs_log, self.seg_log = [], []
 
     def reset_models(self):
@@ -468,8 +471,76 @@ class Handler:
             loss = loss + terms["L2"]
         return loss, terms, Z
 
+    def _hg_fused(self, opti):
+        """True when one frozen-critic Hourglass step can run as the whole-frame kernels (csrc/hg_*.cu + cgs_hg_score):
+        chfak-1 geometry in tensor-core mode, critic out of the optimizer, and the optimizer's bucket is exactly the
+        masker's parameters in state_dict order."""
+        a = self.args
+        if a.live or a.separate or not self.fused_critic_step or not isinstance(opti, FlatAdam):
+            return False
+        if not (ops.hg_supported(self.critic, self.masker) and ops.critic_fused_supported(self.critic)):
+            return False
+        mp = list(self.masker.parameters())
+        return len(opti.params) == len(mp) and all(q is r for q, r in zip(opti.params, mp))
+
+    def segmentation_step_fused(self, X_u8, CX_u8, opti, roll=0, weight=1.0):
+        """One frozen-critic iteration of segmentation_training (main.py:344-463) in six launches: weight-fragment pack,
+        Hourglass forward on A (critic with embeds + decoder + masker; leaves the tape), critic forward on B, the two scored
+        blends with their losses, regulariser and d loss / d mask (cgs_hg_score), the masker's whole backward, and the
+        partial-vector sum + Adam.  No activation but the mask, its gradient and the 54 KB/frame bf16 tape touches HBM."""
+        a = self.args
+        critic, masker, dev = self.critic, self.masker, self.device
+        x = X_u8 if torch.is_tensor(X_u8) else torch.from_numpy(np.ascontiguousarray(X_u8))
+        cx = CX_u8 if torch.is_tensor(CX_u8) else torch.from_numpy(np.ascontiguousarray(CX_u8))
+        x, cx = x.to(dev, non_blocking=True).contiguous(), cx.to(dev, non_blocking=True).contiguous()
+        B = x.shape[0]
+        st = getattr(self, "_hg_state", None)
+        if st is None or st["B"] != B or st["tape"].device != x.device:
+            L = _lib.lib()
+            st = self._hg_state = dict(B=B, tape=ops.hg_tape(B, x.device),
+                                       pack=torch.empty(L.cgs_hg_pack_words(), device=x.device, dtype=torch.int32))
+        pack = ops.hg_pack(critic, masker, out=st["pack"])
+
+        def drop():        # the critic's dropout for its next forward pass, in the reference's call order
+            rng = critic._dropout_rng(dev)
+            return (rng, None) if rng is not None else (None, critic._dropout_masks(B, dev))
+        rng, masks = drop()                                                                # critic(A, collect=True)   main.py:364
+        pred, Z, _ = ops.hg_forward(critic, masker, x, roll=roll, train=critic.training, masks=masks, rng=rng, tape=st["tape"],
+                                    pack=pack)
+        rng, masks = drop()                                                                # critic(B)                 main.py:365
+        negpred = ops.critic_forward_frames(critic, cx, 0, masks if masks is not None else (None, None, None), rng)
+        if rng is not None:
+            m_r = m_i = None
+        else:
+            m_r = critic._dropout_masks(B, dev)                                            # critic(replaced)          main.py:396
+            m_i = critic._dropout_masks(B, dev) if a.inject else None                      # critic(injected)          main.py:407
+            m_r = None if m_r[0] is None else m_r
+            m_i = None if (m_i is None or m_i[0] is None) else m_i
+        losses, dz, _, _ = ops.hg_score(critic, x, cx, Z, negpred.squeeze(1), pred.squeeze(1) if a.inject else None, roll=roll,
+                                        masks=m_r, masks_inject=m_i, rng=critic._dropout_rng(dev) if rng is not None else None,
+                                        loss_grad=weight, vpred=None if a.staticnorm else pred.squeeze(1),
+                                        l1=float(a.L1 or 0.0), l2=float(a.L2 or 0.0))
+        opti.zero_grad()
+        L = _lib.lib()
+        grid, stride = L.cgs_hg_grid(B), L.cgs_hg_partial_stride()
+        buf = opti.partial_buffer(grid * stride)
+        ops.hg_backward(masker, x, st["tape"], Z, dz, roll=roll, pack=pack, partials=buf)
+        opti.pending_partials = (buf, grid, stride, 0, opti.flat.numel())
+        opti.step()
+        terms = {"replace": losses[0]}
+        if a.inject:
+            terms["inject"] = losses[1]
+        if a.L1:
+            terms["L1"] = losses[2]
+        if a.L2:
+            terms["L2"] = losses[3]
+        self._last_mask = Z
+        return terms
+
     def segmentation_step(self, X_u8, CX_u8, Y, opti, roll=0, weight=None):
         weight = (1.0 / self.world) if weight is None else float(weight)
+        if self._hg_fused(opti) and (torch.is_tensor(X_u8) and X_u8.dtype == torch.uint8 or not torch.is_tensor(X_u8)):
+            return self.segmentation_step_fused(X_u8, CX_u8, opti, roll, weight if self.world > 1 else 1.0)
         A = self._to_input(X_u8, roll)
         B = self._to_input(CX_u8)
         Yd = None if Y is None else Y.to(self.device).float()
@@ -522,6 +593,8 @@ class Handler:
         a = self.args
         critic, masker = self.critic, self.masker
         with torch.no_grad():
+            if not a.separate and self.hg_inference and ops.hg_supported(critic, masker) and not critic.training:
+                return ops.hg_forward(critic, masker, xu8, thresh=threshold or None)      # ONE kernel, bf16 operands
             if not a.separate and ops.infer_fused_supported(critic, masker):
                 pred, o0 = ops.infer_encode_decode(critic, masker, xu8)
                 mask, hm = ops.masker_fused(masker, xu8, o0, threshold or None)
@@ -572,18 +645,63 @@ class Handler:
         inter, union = (int(v) for v in counts.cpu())
         return (round(inter / union, 3) if union else float("nan")), inter, union
 
+    def eval_saliency(self, X_u8, GT=None, batchsize=128):
+        """The saliency baseline of Handler.eval / Handler.segment (reference main.py:941-951, 974-993, 1010-1011): per batch
+        `pred.mean().backward(); batch.grad.abs().sum(1)` (ONE kernel: critic forward + input gradient), then over ALL frames the
+        normalisation (`-salglobal`: mean norm; else the per-frame k-th value), `* pred`, clip, `> salience_thresh`, and, given
+        ground-truth masks, `get_iou(salhardM, Y)`.  Everything stays on the device.
+        Returns (salM [N,1,64,64], salhardM uint8 [N,1,64,64], iou or None)."""
+        a = self.args
+        train = bool(a.noevalmode)
+        critic = self.critic.to(self.device).train(train)
+        sal, preds = [], []
+        for bidx in range(0, len(X_u8), batchsize):
+            xu8 = torch.from_numpy(np.ascontiguousarray(X_u8[bidx:bidx + batchsize])).to(self.device)
+            if a.process or a.process_salience:                       # segment() feeds frames / 255 (main.py:1127) ...
+                x = ops.frames_to_float(xu8, 0)
+            else:                                                     # ... eval() feeds the raw 0..255 values (main.py:939)
+                x = xu8.float()
+            pred, m = ops.critic_saliency(critic, x)
+            sal.append(m); preds.append(pred)
+        sal, preds = torch.cat(sal), torch.cat(preds)
+        salM, salhard = ops.saliency_normalize(sal, preds, a.salience_thresh, global_norm=bool(a.salglobal))
+        iou = None
+        if GT is not None:
+            counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+            gt = torch.from_numpy(np.ascontiguousarray(np.asarray(GT).astype(np.uint8))).to(self.device)
+            ops.iou_counts(salhard.float(), gt, 0.5, counts, strict=True)
+            inter, union = (int(v) for v in counts.cpu())
+            iou = round(inter / union, 3) if union else float("nan")
+        return salM, salhard, iou
+
     def segment(self, folder):
-        """`-process`: PNG folder in, mask PNGs out (main.py:1103-1223; raw + thresholded columns)."""
+        """`-process`: PNG folder in, mask PNGs out (main.py:1103-1223): `raw-mask` and `thresholded-mask` per frame, or one
+        `-concatenated` strip frame | raw | thresholded.  The uint8 x 3-channel image rows come straight from the device
+        (cgs_mask_images); the host only encodes PNG."""
         from PIL import Image
+        a = self.args
         names = os.listdir(folder)
         X = np.stack([np.array(Image.open(f"{folder}/{n}")) for n in names]).astype(np.uint8)
         names = [n[:-1 - n[::-1].index(".")] for n in names if "." in n]
-        preds, M, hardM = self.segment_arrays(X)
-        out = self.args.mask_output_imgs
+        train = bool(a.noevalmode)
+        self.critic.to(self.device).train(train)
+        self.masker.to(self.device).train(train)
+        out = a.mask_output_imgs
         os.makedirs(out, exist_ok=True)
-        cols = [("raw-mask", M)] + ([("thresholded-mask", hardM)] if hardM is not None else [])
-        for fidx in range(len(X)):
-            for cname, arr in cols:
-                img = np.repeat(arr[fidx].transpose(1, 2, 0).astype(np.float64), 3, axis=2)
-                Image.fromarray((img * 255).astype(np.uint8)).save(f"{out}/{names[fidx]}-{cname}.png")
-        return preds, M, hardM
+        preds, M, hard = [], [], []
+        for bidx in range(0, len(X), 128):
+            xu8 = torch.from_numpy(np.ascontiguousarray(X[bidx:bidx + 128])).to(self.device)
+            pred, mask, hm = self.segment_device(xu8, a.binarymaskthreshold)
+            if hm is None:                                   # threshold 0: every pixel passes `M >= 0`
+                hm = torch.ones_like(mask, dtype=torch.uint8)
+            if a.concatenated:
+                strips = ops.mask_images(mask, hm, xu8, concatenated=True).cpu().numpy()
+                for i in range(len(strips)):
+                    Image.fromarray(strips[i]).save(f"{out}/{names[bidx + i]}_with_mask.png")
+            else:
+                raw, thr = (t.cpu().numpy() for t in ops.mask_images(mask, hm))
+                for i in range(len(raw)):
+                    Image.fromarray(raw[i]).save(f"{out}/{names[bidx + i]}-raw-mask.png")
+                    Image.fromarray(thr[i]).save(f"{out}/{names[bidx + i]}-thresholded-mask.png")
+            preds.append(pred.squeeze(1).cpu().numpy()); M.append(mask.cpu().numpy()); hard.append(hm.cpu().numpy().astype(bool))
+        return np.concatenate(preds), np.concatenate(M), np.concatenate(hard)

@@ -213,6 +213,13 @@ int cgs_critic_loss_xgrad(const float* x, const float* target, int32_t B, const 
                           const cgs_critic_weights* w, float loss_grad, int32_t bce, float* pred, float* loss, float* dx,
                           void* stream);
 
+/* pred [B] = NewCritic.forward(frames) for raw uint8 NHWC frames (rolled by roll / *roll_dev), forward only, ONE kernel:
+ * `negpred = critic(B)` under no_grad (main.py:365-367) and the predictions of extract_contrastive_data (main.py:238-260).
+ * Dropout as for cgs_critic_train_fused (all NULL / rng_state NULL = eval mode). */
+int cgs_critic_forward_frames(const uint8_t* frames, int32_t B, int32_t roll, const int32_t* roll_dev, const float* m_e2,
+                              const float* m_e3, const float* m_v, float p_drop, uint64_t seed, uint64_t* rng_state,
+                              const cgs_critic_weights* w, float* pred, void* stream);
+
 /* `-process` inference, encoder + decoder half, in ONE kernel for the chfak=1 geometry (csrc/infer_fused.cu): uint8 NHWC
  * frames [B,64,64,3] -> /255 -> NewCritic.forward(collect=True) in eval mode (nets.py:197-212) -> UnetDecoder dec[4]..dec[0]
  * with their nearest-upsample + concat operands (nets.py:500-517) -> o0 [B,32,32,8] NHWC (the map `masker` consumes via
@@ -339,6 +346,22 @@ int cgs_hg_debug_floats(void);
 int cgs_hg_backward(const uint8_t* frames, int32_t B, int32_t roll, const int32_t* roll_dev, const cgs_masker_weights* mw,
                     const uint32_t* pack, const void* tape, const float* z, const float* dz, float* partials, float* debug,
                     void* stream);
+
+/* ---- formats either side of the path, csrc/edges.cu ---------------------------------------------------
+ * out[i] = dataset[idx[i]] for uint8 NHWC frames (12288 bytes each): `Xpos[Hidx]`, `Xneg[Lidx]`, `Xneg[Cidx]` of
+ * main.py:345-353 over a device-resident dataset; indices are clamped to [0, nframes). */
+int cgs_gather_frames(const uint8_t* dataset, int64_t nframes, const int32_t* idx, int32_t n, uint8_t* out, void* stream);
+/* `-process` image outputs (main.py:1212-1223) from mask [B,64,64] fp32 and hard [B,64,64] uint8: raw-mask =
+ * (M*255).astype(uint8) and thresholded-mask = hardM*255, replicated to 3 channels: raw, thresholded [B,64,64,3]; or, when
+ * concatenated != 0, ONE strip per frame raw[B,64,192,3] = frame | raw-mask | thresholded-mask, with the frame bytes mapped
+ * through lut[256] = (b / 255.0 * 255).astype(uint8) (the reference's float64 round trip, not the identity). */
+int cgs_mask_images(const float* mask, const uint8_t* hard, int32_t B, const uint8_t* frames, const uint8_t* lut,
+                    int32_t concatenated, uint8_t* raw, uint8_t* thresholded, void* stream);
+/* Saliency-baseline normalisation (main.py:974-993): sal [B,64,64] >= 0 (`batch.grad.abs().sum(1)`), pred [B];
+ * norm = the k-th smallest value of each frame (k = int(4096*thresh)), or *global_norm when non-NULL (-salglobal);
+ * out = min(sal / norm * pred, 1), hard = out > thresh; norm_out [B] optional. */
+int cgs_saliency_normalize(const float* sal, const float* pred, int32_t B, int32_t k, float thresh, const float* global_norm,
+                           float* out, uint8_t* hard, float* norm_out, void* stream);
 
 /* All nn.Dropout masks of one NewCritic forward (nets.py:179,183,192) in one launch: out[i] = Bernoulli(1-p)/(1-p),
  * Philox4x32-10 keyed by (seed, state[0]); state = {call counter, ticket} in device memory, advanced by the kernel

@@ -241,3 +241,118 @@ def test_hg_backward_is_linear_and_reproducible(ops):
     g1, g2, g12 = s(pa), s(run(dz2)[0]), s(run(2.0 * dz1 + dz2)[0])
     r = float(((2 * g1 + g2) - g12).norm() / g12.norm())
     assert r <= 1e-2, r
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The whole frozen-critic Hourglass step through Handler.segmentation_step (6 launches) vs the oracle and the goldens
+def _fused_step(H, X, B, masks_nhwc, roll=0):
+    from collections import deque
+    from cgs_b200.train_handler import FlatAdam
+    H.critic.to(DEV).train(); H.masker.to(DEV).train()
+    for q in H.critic.parameters():
+        q.requires_grad_(False)
+    opti = FlatAdam(list(H.masker.parameters()))
+    assert H._hg_fused(opti)
+    H.critic._forced_masks = deque(masks_nhwc) if masks_nhwc is not None else None
+    opti.step = lambda: None                                  # keep the gradient: fold the partial vectors into the bucket instead
+    terms = H.segmentation_step(torch.from_numpy(X[:B]).to(DEV), torch.from_numpy(X[B:2 * B]).to(DEV), None, opti, roll=roll)
+    opti.flush_partials()
+    torch.cuda.synchronize()
+    return terms, H._last_mask, {k: v.grad.detach().cpu().numpy() for k, v in H.masker.named_parameters()}
+
+
+@pytest.mark.parametrize("B,inject,static,l1,l2", [(19, True, True, 0.5, 0.0), (150, True, True, 0.5, 0.0), (6, False, False, 0.25, 0.5)])
+def test_hg_fused_step_vs_oracle(ops, B, inject, static, l1, l2):
+    from helpers import drop_masks, nhwc_masks, tmasks, tsd
+    from cgs_b200.train_handler import Handler, parse_args
+    p = 0.3
+    csd = synth.perturbed_state(synth.critic_shapes(1), 177, 1.5)
+    msd = synth.perturbed_state(synth.masker_shapes(1), 178, 1.5)
+    X, Yl, _ = synth.synthetic_frames(2 * B, seed=15)
+    A = torch.from_numpy(X[:B]).permute(0, 3, 1, 2).float() / 255.0
+    Bf = torch.from_numpy(X[B:]).permute(0, 3, 1, 2).float() / 255.0
+    rng = np.random.default_rng(13)
+    masks = [drop_masks(rng, B, 1, p) for _ in range(4)]
+    c_cpu, m_cpu = tsd(csd), tsd(msd)
+    for t in m_cpu.values():
+        t.requires_grad_(True)
+    loss_r, terms_r, Z_r = torch_ref.hourglass_losses(c_cpu, m_cpu, A, Bf, None, live=False, inject=inject, L1=l1, L2=l2,
+                                                      staticnorm=static, masks=[tmasks(m) for m in masks])
+    loss_r.backward()
+    a = parse_args(["-frozen", "--dropout", str(p), "--L1", str(l1), "--L2", str(l2)] + ([] if inject else ["-noinject"]))
+    a.staticnorm = static
+    H = Handler(a, device=DEV)
+    H.critic.load_state_dict(tsd(csd)); H.masker.load_state_dict(tsd(msd))
+    order = [0, 1, 2] + ([3] if inject else [])
+    terms, Z, grads = _fused_step(H, X, B, [nhwc_masks(masks[i], DEV) for i in order])
+    assert set(terms) == set(terms_r), (set(terms), set(terms_r))
+    for k, v in terms.items():
+        assert abs(v.item() - terms_r[k].item()) <= 1e-2 * abs(terms_r[k].item()) + 5e-6, (k, v.item(), terms_r[k].item())
+    assert (Z.cpu() - Z_r.detach()).abs().max().item() <= 2e-2
+    gs = {k: _rel(grads[k], m_cpu[k].grad.numpy()) for k in grads}
+    g_o = np.concatenate([grads[k].reshape(-1) for k in grads]).astype(np.float64)
+    g_r = np.concatenate([m_cpu[k].grad.numpy().reshape(-1) for k in grads]).astype(np.float64)
+    tot = float(np.linalg.norm(g_o - g_r) / np.linalg.norm(g_r))
+    assert tot <= 4e-2 and max(gs.values()) <= 8e-2, (tot, gs)
+
+
+def test_hg_fused_step_vs_reference_golden(ops):
+    """The same step against what the UNMODIFIED reference produced (tests/golden/step_c1_b6.npz, tag hg_frozen)."""
+    from helpers import nhwc_masks, step_case, tsd
+    from cgs_b200.train_handler import Handler, parse_args
+    d = load_golden("step_c1_b6.npz")
+    c = step_case(d)
+    tag = "hg_frozen"
+    a = parse_args(["--dropout", str(c["p"]), "--L1", "0.5", "--L2", "0.0", "-frozen"])
+    a.staticnorm = True
+    H = Handler(a, device=DEV)
+    H.critic.load_state_dict(tsd(c["csd"])); H.masker.load_state_dict(tsd(c["msd"]))
+    X, _, _ = synth.synthetic_frames(2 * c["B"], seed=int(d["seed"]))
+    terms, Z, grads = _fused_step(H, X, c["B"], [nhwc_masks(c["masks"][i], DEV) for i in range(4)])
+    for k, v in terms.items():
+        ref = float(d[f"{tag}.{k}"])
+        assert abs(v.item() - ref) <= 1e-2 * abs(ref) + 5e-6, (k, v.item(), ref)
+    assert np.abs(Z.cpu().numpy() - d[f"{tag}.Z"]).max() <= 2e-2
+    num = den = 0.0
+    worst = {}
+    for k, g in grads.items():
+        r = d[f"{tag}.g.m.{k}"].astype(np.float64)
+        num += ((g - r) ** 2).sum(); den += (r ** 2).sum()
+        worst[k] = float(np.sqrt(((g - r) ** 2).sum() / max((r ** 2).sum(), 1e-300)))
+    tot = float(np.sqrt(num / max(den, 1e-300)))
+    assert tot <= 4e-2 and max(worst.values()) <= 8e-2, (tot, worst)
+
+
+def test_hg_fused_steps_match_adam_reference(ops):
+    """Five fused steps with in-kernel dropout move the masker exactly as five oracle Adam steps on the kernels' own
+    gradients would: parameters after N steps == torch_ref.adam_step applied to the folded partial vectors."""
+    from helpers import tsd
+    from cgs_b200.train_handler import FlatAdam, Handler, parse_args
+    B = 64
+    csd = synth.perturbed_state(synth.critic_shapes(1), 5, 1.5)
+    msd = synth.perturbed_state(synth.masker_shapes(1), 6, 1.5)
+    X, _, _ = synth.synthetic_frames(2 * B, seed=2)
+    H = Handler(parse_args(["-frozen", "--dropout", "0.3"]), device=DEV)
+    H.critic.load_state_dict(tsd(csd)); H.masker.load_state_dict(tsd(msd))
+    H.critic.to(DEV).train(); H.masker.to(DEV).train()
+    for q in H.critic.parameters():
+        q.requires_grad_(False)
+    opti = FlatAdam(list(H.masker.parameters()))
+    Xa, Xb = torch.from_numpy(X[:B]).to(DEV), torch.from_numpy(X[B:]).to(DEV)
+    ref_p = opti.flat.detach().cpu().clone()
+    state = {}
+    real_step = opti.step
+    for it in range(5):
+        grads = {}
+
+        def spy():
+            buf, rows, stride, off, length = opti.pending_partials
+            grads["g"] = buf[:rows * stride].view(rows, stride)[:, :length].sum(0).cpu()
+            real_step()
+        opti.step = spy
+        H.segmentation_step(Xa, Xb, None, opti, roll=it)
+        torch_ref.adam_step([ref_p], [grads["g"]], state)
+    torch.cuda.synchronize()
+    err = (opti.flat.cpu() - ref_p).abs().max().item()
+    assert err <= 2e-5, err
+    assert (opti.flat.cpu() - torch.cat([torch.from_numpy(v).reshape(-1) for v in msd.values()])).abs().max().item() > 1e-3

@@ -255,6 +255,8 @@ class Handler:
         self.contrastive_batchsize = 32      # main.py:309
         self.fused_critic_step = True        # tf32 mode, chfak 1: one kernel per critic_pipe step
         self.hg_inference = True             # tensor-core mode, chfak 1: -process in ONE bf16 kernel (csrc/hg_forward.cu)
+        self.device_dataset = True           # segmentation_training gathers its batches from a device-resident uint8 dataset
+        self.device_dataset_bytes = 8 << 30  # ... when the pos + neg frames fit this budget (100k frames = 1.2 GB)
         self.closs_log, self.seg_log = [], []
 
     def reset_models(self):
@@ -403,11 +405,12 @@ class Handler:
         preds = []
         with torch.no_grad():
             for bidx in range(math.ceil(len(self.X) / batchsize)):
-                batch = self._to_input(self.X[bidx * batchsize:(bidx + 1) * batchsize])
-                if self.fused_critic_step and ops.critic_fused_supported(critic):
-                    preds.append(ops.critic_forward_fused(critic, batch.permute(0, 2, 3, 1)).squeeze(1))
+                chunk = self.X[bidx * batchsize:(bidx + 1) * batchsize]
+                if self.fused_critic_step and ops.critic_fused_supported(critic):      # raw uint8 frames in, ONE kernel
+                    xu8 = torch.from_numpy(np.ascontiguousarray(chunk)).to(self.device, non_blocking=True)
+                    preds.append(ops.critic_forward_frames(critic, xu8).squeeze(1))
                 else:
-                    preds.append(critic(batch).squeeze(1))
+                    preds.append(critic(self._to_input(chunk)).squeeze(1))
         preds = torch.cat(preds, dim=0).cpu()
         positives = (preds > a.high_rew_thresh).numpy()
         negatives = (preds < a.low_rew_thresh).numpy()
@@ -564,17 +567,33 @@ class Handler:
             for p in critic.parameters():
                 p.requires_grad_(False)
             opti = self._opt(chain(masker.parameters(), *[s.parameters() for s in sep]))
+        # device-resident dataset: the pos / neg frames are uploaded ONCE as uint8 and every step's
+        # `Xpos[Hidx]`, `Xneg[Lidx]`, `Xneg[Cidx]` (main.py:345-353) is an index gather on the device (cgs_gather_frames)
+        # fed by a few hundred bytes of indices instead of the frames themselves
+        data = None
+        if self.device_dataset and self.device.type == "cuda" and self.Xpos.nbytes + self.Xneg.nbytes <= self.device_dataset_bytes:
+            data = torch.from_numpy(np.ascontiguousarray(np.concatenate((self.Xpos, self.Xneg), axis=0))).to(self.device)
+            labels = torch.from_numpy(np.concatenate((self.Ypos[a.rewidx], self.Yneg[a.rewidx]))).to(self.device)
+            npos = len(self.Xpos)
         try:
             for epoch in range(a.mepochs):
                 for b_idx in range(math.ceil(self.Xpos.shape[0] / self.contrastive_batchsize)):
                     Hidx, Lidx, Cidx = self.get_contrastive_idxs()
-                    X = np.concatenate((self.Xpos[Hidx], self.Xneg[Lidx]), axis=0)
-                    Y = torch.from_numpy(np.concatenate((self.Ypos[a.rewidx, Hidx], self.Yneg[a.rewidx, Lidx])))
-                    CX = self.Xneg[Cidx]
                     roll = self._shift_roll() if a.shift else 0
-                    sl = self._shard(len(X))
-                    self.seg_log.append(self.segmentation_step(X[sl], CX[sl], Y[sl], opti, roll,
-                                                               weight=self._shard_weight(len(X))))
+                    n = len(Hidx) + len(Lidx)
+                    sl = self._shard(n)
+                    if data is not None:
+                        xi = np.concatenate((Hidx, npos + Lidx))[sl]
+                        ci = (npos + Cidx)[sl]
+                        idx = torch.from_numpy(np.concatenate((xi, ci)).astype(np.int32)).to(self.device, non_blocking=True)
+                        frames = ops.gather_frames(data, idx)
+                        X, CX = frames[:len(xi)], frames[len(xi):]
+                        Y = labels[idx[:len(xi)].long()]
+                    else:
+                        X = np.concatenate((self.Xpos[Hidx], self.Xneg[Lidx]), axis=0)[sl]
+                        Y = torch.from_numpy(np.concatenate((self.Ypos[a.rewidx, Hidx], self.Yneg[a.rewidx, Lidx])))[sl]
+                        CX = self.Xneg[Cidx][sl]
+                    self.seg_log.append(self.segmentation_step(X, CX, Y, opti, roll, weight=self._shard_weight(n)))
                 if not (epoch + 1) % a.saveevery:
                     opti.check()
                     self.save_models([self.maskername])
@@ -657,11 +676,7 @@ class Handler:
         sal, preds = [], []
         for bidx in range(0, len(X_u8), batchsize):
             xu8 = torch.from_numpy(np.ascontiguousarray(X_u8[bidx:bidx + batchsize])).to(self.device)
-            if a.process or a.process_salience:                       # segment() feeds frames / 255 (main.py:1127) ...
-                x = ops.frames_to_float(xu8, 0)
-            else:                                                     # ... eval() feeds the raw 0..255 values (main.py:939)
-                x = xu8.float()
-            pred, m = ops.critic_saliency(critic, x)
+            pred, m = ops.critic_saliency(critic, ops.frames_to_float(xu8, 0))     # frames / 255 (main.py:921, 1127)
             sal.append(m); preds.append(pred)
         sal, preds = torch.cat(sal), torch.cat(preds)
         salM, salhard = ops.saliency_normalize(sal, preds, a.salience_thresh, global_norm=bool(a.salglobal))

@@ -79,3 +79,33 @@ def test_saliency_normalize_matches_reference_expressions(thresh, glob):
         ok = ~np.isnan(s)
         assert np.array_equal(o[ok], s[ok])
         assert np.array_equal(h.cpu().numpy(), hard)
+
+
+def test_segmentation_training_device_gather_equals_host_gather():
+    """segmentation_training with the device-resident dataset + cgs_gather_frames gives the very same loss sequence as with
+    the host-side numpy gather of the reference (main.py:345-353): same indices, same frames, same kernels."""
+    import cgs_b200.ops as ops
+    from helpers import load_golden
+    from cgs_b200.train_handler import Handler, parse_args
+    d = load_golden("loops_c1.npz")
+    X, Y, I = synth.synthetic_frames(3000, seed=0)
+    logs = []
+    ops.set_precision("tf32")
+    try:
+        for dev_data in (True, False):
+            a = parse_args(["-frozen", "--dropout", "0", "--shift", "7", "--saveevery", "100", "--model", "/tmp/cgs_gather_test"])
+            a.cload = False
+            torch.manual_seed(3)
+            np.random.seed(3)
+            H = Handler(a, device=DEV)
+            H.device_dataset = dev_data
+            H.critic.load_state_dict({k[len("trained.c."):]: torch.from_numpy(d[k]) for k in d.files if k.startswith("trained.c.")})
+            H.masker.load_state_dict({k[len("init.m."):]: torch.from_numpy(d[k]) for k in d.files if k.startswith("init.m.")})
+            H.critic.to(DEV); H.masker.to(DEV)
+            H.X, H.Y, H.I = X, Y, I
+            H.segmentation_training()
+            logs.append(np.array([[t[k] for k in sorted(t)] for t in H.seg_log]))
+    finally:
+        ops.set_precision("fp32")
+    assert logs[0].shape == logs[1].shape and logs[0].shape[0] >= 10
+    assert np.array_equal(logs[0], logs[1])

@@ -459,54 +459,71 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
     }
   }
 
-  // ---- end of the CTA's frames: assemble the partial gradient vector (state_dict order) in the tape region
+  // ---- end of the CTA's frames: assemble the partial gradient vector (state_dict order) in the tape region.  Register
+  //      accumulators go through scratch (the band region is dead); every destination has exactly ONE writer and copies of
+  //      a K-split are summed in a fixed order: no atomics anywhere, the vector is bit-reproducible.
   __syncthreads();
   float* sG = reinterpret_cast<float*>(smraw);
+  float* scrM0 = reinterpret_cast<float*>(smraw + kM0);            // [12 warps][3 ky][128]
+  float* scrM2 = scrM0 + 12 * 3 * 128;                             // [16 warps][2 tiles][128] | [16] bias partials
+  static_assert((12 * 3 * 128 + 16 * 2 * 128 + 16) * 4 <= 2 * PLB, "assembly scratch fits the band region");
   for (int e = tid; e < PSTRIDE_M; e += NT) sG[e] = 0.f;
-  __syncthreads();
-  // fragment (row m = g | g+8, column n = 2t | 2t+1) of value q: m = g + 8*(q >> 1), n = 2t + (q & 1)
-  if (warp < 12) {                                   // masker.0 [16][11][3][3] + bias
-    const int tr = warp % 3, nt = (warp / 3) & 1;
+  if (warp < 12) {
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int m = g + 8 * (q >> 1), co = nt * 8 + 2 * t + (q & 1);
-        const float v = accM0[ky][q];
-        if (tr == 0) {
-          const int kx = m >> 2, c = m & 3;
-          if (kx < 3 && c < 3) atomicAdd(sG + gM0W + ((co * 11 + c) * 3 + ky) * 3 + kx, v);
-        } else if (tr == 1) {
-          atomicAdd(sG + gM0W + ((co * 11 + 3 + (m & 7)) * 3 + ky) * 3 + (m >> 3), v);
-        } else {
-          if (m < 8) atomicAdd(sG + gM0W + ((co * 11 + 3 + m) * 3 + ky) * 3 + 2, v);
-          else if (m == 8 && ky == 0) atomicAdd(sG + gM0B + co, v);
-        }
-      }
+      *reinterpret_cast<float4*>(scrM0 + (warp * 3 + ky) * 128 + lane * 4) = make_float4(accM0[ky][0], accM0[ky][1], accM0[ky][2], accM0[ky][3]);
   }
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {                      // masker.2 [1][16][3][3]: row = ci, column = tap
-    const int ci = g + 8 * (q >> 1), col = 2 * t + (q & 1);
-    atomicAdd(sG + gM2W + ci * 9 + col, accM2[0][q]);
-    if (col == 0) atomicAdd(sG + gM2W + ci * 9 + 8, accM2[1][q]);
-  }
+  for (int j = 0; j < 2; ++j)
+    *reinterpret_cast<float4*>(scrM2 + (warp * 2 + j) * 128 + lane * 4) = make_float4(accM2[j][0], accM2[j][1], accM2[j][2], accM2[j][3]);
   bsum2 = warp_sum(bsum2);
-  if (lane == 0) atomicAdd(sG + gM2B, bsum2);
+  if (lane == 0) scrM2[16 * 2 * 128 + warp] = bsum2;
+  __syncthreads();
+  // fragment value q of lane (g, t): row m = g + 8*(q >> 1), column n = 2t + (q & 1)
+  for (int e = tid; e < 6 * 3 * 128; e += NT) {          // masker.0 [16][11][3][3] + bias: role = nt*3 + tr, two row halves
+    const int role = e / 384, ky = (e >> 7) % 3, ln = (e >> 2) & 31, q = e & 3, gg = ln >> 2, tt = ln & 3;
+    const int tr = role % 3, nt = role / 3, m = gg + 8 * (q >> 1), co = nt * 8 + 2 * tt + (q & 1);
+    const float v = scrM0[(role * 3 + ky) * 128 + ln * 4 + q] + scrM0[((role + 6) * 3 + ky) * 128 + ln * 4 + q];
+    if (tr == 0) {
+      const int kx = m >> 2, c = m & 3;
+      if (kx < 3 && c < 3) sG[gM0W + ((co * 11 + c) * 3 + ky) * 3 + kx] = v;
+    } else if (tr == 1) {
+      sG[gM0W + ((co * 11 + 3 + (m & 7)) * 3 + ky) * 3 + (m >> 3)] = v;
+    } else if (m < 8) {
+      sG[gM0W + ((co * 11 + 3 + m) * 3 + ky) * 3 + 2] = v;
+    } else if (m == 8 && ky == 0) {
+      sG[gM0B + co] = v;
+    }
+  }
+  if (tid < 256) {                                       // masker.2 [1][16][3][3]: row = ci, column = tap (tile 1: tap 8 in column 0)
+    const int j = tid >> 7, ln = (tid >> 2) & 31, q = tid & 3, ci = (ln >> 2) + 8 * (q >> 1), col = 2 * (ln & 3) + (q & 1);
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) v += scrM2[(w * 2 + j) * 128 + ln * 4 + q];
+    if (j == 0) sG[gM2W + ci * 9 + col] = v;
+    else if (col == 0) sG[gM2W + ci * 9 + 8] = v;
+  }
+  if (tid == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 16; ++w) v += scrM2[16 * 2 * 128 + w];
+    sG[gM2B] = v;
+  }
   sG[gD4W + tid] = accD4[0];                         // dec[4] [32][32] + bias
   sG[gD4W + 512 + tid] = accD4[1];
   if (tid < 32) sG[gD4B + tid] = accB4;
-  // dec[0] / dec[1]: tiles [(kh,) tr][ky]; tr = src*2 + kxg
-  for (int e = tid; e < 36 * 128; e += NT) {
+  // dec[0]: tiles [kh][tr][ky] (two row halves, summed here); dec[1]: tiles [tr][ky]; tr = src*2 + kxg
+  for (int e = tid; e < 24 * 128; e += NT) {
     const int tile = e >> 7, ln = (e >> 2) & 31, q = e & 3, gg = ln >> 2, tt = ln & 3;
-    const bool d0 = tile < 24;
-    const int tl = d0 ? tile % 12 : tile - 24, tr = tl / 3, ky = tl % 3, src = tr >> 1, kxg = tr & 1;
+    const bool d0 = tile < 12;
+    const int tl = d0 ? tile : tile - 12, tr = tl / 3, ky = tl % 3, src = tr >> 1, kxg = tr & 1;
     const int m = gg + 8 * (q >> 1), co = 2 * tt + (q & 1);
-    const float v = sAcc[(T_D0 + tile) * 128 + ln * 4 + q];
+    const float v = d0 ? sAcc[(T_D0 + tile) * 128 + ln * 4 + q] + sAcc[(T_D0 + 12 + tile) * 128 + ln * 4 + q]
+                       : sAcc[(T_D1 + tl) * 128 + ln * 4 + q];
     float* gw = sG + (d0 ? gD0W : gD1W);
     float* gb = sG + (d0 ? gD0B : gD1B);
-    if (kxg == 0) atomicAdd(gw + ((co * 16 + src * 8 + (m & 7)) * 3 + ky) * 3 + (m >> 3), v);
-    else if (m < 8) atomicAdd(gw + ((co * 16 + src * 8 + m) * 3 + ky) * 3 + 2, v);
-    else if (m == 8 && src == 0 && ky == 0) atomicAdd(gb + co, v);
+    if (kxg == 0) gw[((co * 16 + src * 8 + (m & 7)) * 3 + ky) * 3 + (m >> 3)] = v;
+    else if (m < 8) gw[((co * 16 + src * 8 + m) * 3 + ky) * 3 + 2] = v;
+    else if (m == 8 && src == 0 && ky == 0) gb[co] = v;
   }
   // dec[2] [8][24][3][3]: tiles cb*5 + tp; rows m < 8: tap 2tp, m >= 8: tap 2tp+1 (tp 4: row 8 = bias on cb 0)
   for (int e = tid; e < 15 * 128; e += NT) {

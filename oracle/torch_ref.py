@@ -27,7 +27,31 @@ def _sd(sd, dtype):
     return {k: torch.as_tensor(v).to(dtype) for k, v in sd.items()}
 
 
-def critic_forward(sd, x, collect=False, masks=None):
+# ---- operand-precision models of the tensor-core kernels (tests only) ---------------------------------------------
+# The tensor-core paths compute every 3x3 convolution of the reference on operands rounded to TF32 (critic whole-frame
+# kernels) or bf16 (Hourglass whole-frame kernels) with fp32 accumulation; everything else (biases, activations,
+# pooling, the 4x4 / 1x1 / Linear layers, losses) is fp32.  `q=quant_tf32 | quant_bf16` below reproduces exactly that
+# rounding at the same places, with a straight-through gradient, so that the ReLU / max-pool / LeakyReLU *decisions* of the
+# model and of the kernel agree and the remaining difference is accumulation order.  q=None is the reference arithmetic.
+def quant_bf16(t):
+    """round-to-nearest-even to bfloat16 (what __float2bfloat16_rn does), straight-through gradient"""
+    return t + (t.detach().bfloat16().float() - t.detach())
+
+
+def quant_tf32(t):
+    """cvt.rna.tf32.f32: round to nearest, ties away from zero, 10 explicit mantissa bits; straight-through gradient"""
+    d = t.detach()
+    r = ((d.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    return t + (r - d)
+
+
+def _conv3(h, w, b, q):
+    if q is not None:
+        h, w = q(h), q(w)
+    return F.conv2d(h, w, b, stride=1, padding=1)
+
+
+def critic_forward(sd, x, collect=False, masks=None, q=None):
     """NewCritic.forward (reference nets.py:197-212) over the layer list built at
     nets.py:169-195.  `sd` uses the reference state_dict keys.  `masks` is None
     (eval mode: dropout is identity) or a 3-tuple of multiplicative dropout masks
@@ -36,7 +60,7 @@ def critic_forward(sd, x, collect=False, masks=None):
     embeds = []
     h = x
     for i, key in enumerate(("features.0", "features.3", "features.6", "features.10")):
-        h = F.conv2d(h, sd[key + ".weight"], sd[key + ".bias"], stride=1, padding=1)   # nets.py:170,173,176,180
+        h = _conv3(h, sd[key + ".weight"], sd[key + ".bias"], q)                       # nets.py:170,173,176,180
         h = F.relu(h)
         h = F.max_pool2d(h, 2)
         embeds.append(h)                     # nets.py:202-203: collected after each pool
@@ -54,23 +78,23 @@ def critic_forward(sd, x, collect=False, masks=None):
     return (pred, embeds) if collect else pred
 
 
-def decoder_forward(sd, x, embeds):
+def decoder_forward(sd, x, embeds, q=None):
     """UnetDecoder.forward (reference nets.py:494-523): no activation between the
     dec convs; every cat is (skip, upsampled); last cat is (image, upsampled)."""
     up = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")                    # nets.py:463
     o = F.conv2d(embeds[4], sd["dec_model.4.weight"], sd["dec_model.4.bias"])           # nets.py:500-501
     o = up(up(o))                                                                       # nets.py:503
-    o = F.conv2d(torch.cat((embeds[3], o), 1), sd["dec_model.3.weight"], sd["dec_model.3.bias"], padding=1)
+    o = _conv3(torch.cat((embeds[3], o), 1), sd["dec_model.3.weight"], sd["dec_model.3.bias"], q)
     o = up(o)
-    o = F.conv2d(torch.cat((embeds[2], o), 1), sd["dec_model.2.weight"], sd["dec_model.2.bias"], padding=1)
+    o = _conv3(torch.cat((embeds[2], o), 1), sd["dec_model.2.weight"], sd["dec_model.2.bias"], q)
     o = up(o)
-    o = F.conv2d(torch.cat((embeds[1], o), 1), sd["dec_model.1.weight"], sd["dec_model.1.bias"], padding=1)
+    o = _conv3(torch.cat((embeds[1], o), 1), sd["dec_model.1.weight"], sd["dec_model.1.bias"], q)
     o = up(o)
-    o = F.conv2d(torch.cat((embeds[0], o), 1), sd["dec_model.0.weight"], sd["dec_model.0.bias"], padding=1)
+    o = _conv3(torch.cat((embeds[0], o), 1), sd["dec_model.0.weight"], sd["dec_model.0.bias"], q)
     o = up(o)
-    m = F.conv2d(torch.cat((x, o), 1), sd["masker.0.weight"], sd["masker.0.bias"], padding=1)   # nets.py:488,519-521
+    m = _conv3(torch.cat((x, o), 1), sd["masker.0.weight"], sd["masker.0.bias"], q)             # nets.py:488,519-521
     m = F.leaky_relu(m, 0.01)                                                           # nets.py:462,489
-    m = F.conv2d(m, sd["masker.2.weight"], sd["masker.2.bias"], padding=1)              # nets.py:490
+    m = _conv3(m, sd["masker.2.weight"], sd["masker.2.bias"], q)                        # nets.py:490
     return torch.sigmoid(m)                                                             # nets.py:491
 
 
@@ -83,13 +107,14 @@ def critic_loss(csd, x, y, masks=None, threshrew=False):
 
 
 def hourglass_losses(csd, msd, A, Bf, Y=None, live=False, inject=True, L1=0.5, L2=0.0,
-                     lfak=5, staticnorm=True, masks=(None, None, None, None), sepsd=None):
+                     lfak=5, staticnorm=True, masks=(None, None, None, None), sepsd=None, q_embed=None, q_score=None,
+                     q_mask=None):
     """Loss terms of one segmentation_training step (reference main.py:364-429).
     `masks` = dropout masks for the four critic passes in call order
     critic(A), critic(B), critic(replaced), critic(injected).  Returns
     (total, dict of terms, Z)."""
-    pred, embeds = critic_forward(csd, A, collect=True, masks=masks[0])      # main.py:364
-    negpred = critic_forward(csd, Bf, masks=masks[1]).squeeze().detach()     # main.py:365-367
+    pred, embeds = critic_forward(csd, A, collect=True, masks=masks[0], q=q_embed)      # main.py:364
+    negpred = critic_forward(csd, Bf, masks=masks[1], q=q_score).squeeze().detach()     # main.py:365-367
     pred = pred.squeeze()
     terms = {}
     loss = 0
@@ -98,13 +123,13 @@ def hourglass_losses(csd, msd, A, Bf, Y=None, live=False, inject=True, L1=0.5, L
         loss = loss + lfak * terms["critic"]
     if sepsd is not None:
         _, embeds = critic_forward(sepsd, A, collect=True, masks=masks[0])   # main.py:389-390
-    Z = decoder_forward(msd, A, embeds)                                      # main.py:391
+    Z = decoder_forward(msd, A, embeds, q=q_mask)                            # main.py:391
     replaced = A * (1 - Z) + Z * Bf                                          # main.py:395
-    terms["replace"] = F.mse_loss(critic_forward(csd, replaced, masks=masks[2]).squeeze(), negpred)  # main.py:396-400
+    terms["replace"] = F.mse_loss(critic_forward(csd, replaced, masks=masks[2], q=q_score).squeeze(), negpred)  # main.py:396-400
     loss = loss + terms["replace"]
     if inject:
         injected = Bf * (1 - Z) + Z * A                                      # main.py:406
-        terms["inject"] = F.mse_loss(critic_forward(csd, injected, masks=masks[3]).squeeze(), pred.detach())  # main.py:407-411
+        terms["inject"] = F.mse_loss(critic_forward(csd, injected, masks=masks[3], q=q_score).squeeze(), pred.detach())  # main.py:407-411
         loss = loss + terms["inject"]
     vf = 1 if staticnorm else 1 - pred.detach().view(-1, 1, 1, 1)            # main.py:415-419
     if L1:

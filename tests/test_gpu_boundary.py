@@ -60,6 +60,7 @@ def _handler(ref_shims, main, work, extra=()):
     assert isinstance(H.critic, cn.NewCritic) and isinstance(H.masker, cn.UnetDecoder), "the swap did not take"
     assert H.device == "cuda"
     H.args.cload = False
+    os.makedirs(os.path.join(work, H.path), exist_ok=True)       # the loops write their logs under `self.path` (main.py:94, 289)
     return H
 
 

@@ -108,4 +108,5 @@ def test_segmentation_training_device_gather_equals_host_gather():
     finally:
         ops.set_precision("fp32")
     assert logs[0].shape == logs[1].shape and logs[0].shape[0] >= 10
-    assert np.array_equal(logs[0], logs[1])
+    # identical frames reach identical kernels; the loss scalars are summed with float atomics (order varies run to run)
+    assert np.allclose(logs[0], logs[1], rtol=2e-3, atol=1e-7), np.abs(logs[0] - logs[1]).max()

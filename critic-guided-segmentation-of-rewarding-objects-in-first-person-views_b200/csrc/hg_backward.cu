@@ -81,6 +81,9 @@ __device__ __forceinline__ void flush3(float* tiles, const float (&acc)[3][4], i
   }
 }
 
+__device__ long long* g_hgb_trace = nullptr;
+int set_fwd_trace(long long* b);
+
 __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
   extern __shared__ __align__(128) uint8_t smraw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -95,6 +98,8 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
   float* sBm0 = sDD4 + 32;
   const float* sH = reinterpret_cast<const float*>(smraw + tH);
   const uint32_t ones = g == 0 ? ONES2 : 0u;
+  long long* trace = blockIdx.x == 0 ? g_hgb_trace : nullptr;
+  int fr = 0;
 
   // ---- prologue: zero everything once (halos and accumulator tiles stay / start zero), weight fragments
   {
@@ -122,6 +127,7 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
 
   for (int n = blockIdx.x; n < p.B; n += gridDim.x) {
     __syncthreads();                                   // everybody is done with the previous frame's tape and bytes
+    HG_MARK(0);
     {
       const uint8_t* srcT = p.tape + (size_t)n * TAPE;
       for (int c = tid; c < TAPE / 16; c += NT) cp_async16(smb + c * 16, srcT + c * 16);
@@ -131,10 +137,12 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
       cp_async_wait_all();
     }
     __syncthreads();
+    HG_MARK(1);
     const float* zf = p.z + (size_t)n * 4096;
     const float* dzf = p.dz + (size_t)n * 4096;
 
     for (int band = 0; band < 4; ++band) {
+      HG_MARK(2 + 5 * band);
       // ================= B1: the band's 20 frame rows (pair-duplicated bf16) and 20 rows of d logit = dZ * Z * (1 - Z)
       stage_rows(smraw + kU8, smraw + kXB, 16 * band - 2, 20, roll, tid);
       for (int e = tid; e < 20 * 64; e += NT) {
@@ -148,9 +156,11 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
         sDL[rho * DLP + x + 1] = v;
       }
       __syncthreads();
+      HG_MARK(3 + 5 * band);
       // ================= B2: masker.0 + LeakyReLU recomputed for the band's 18 rows
       m0_band(smraw + kM0, smb, kXB, 16 * band - 1, 20, sWf + W_M0F * 32, sBm0, band, warp, lane);
       __syncthreads();
+      HG_MARK(4 + 5 * band);
       // ================= B3: masker.2 weight gradient: M = 16 input channels, N = 9 taps, K = pixels of the band
       // dW2[ci][ky][kx] += m0[r][c][ci] * dlogit[row r - ky + 1][col c - kx]  (band coordinates, interior mask rows only)
       for (int pg = warp; pg < 72; pg += 16) {
@@ -180,6 +190,7 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
         }
       }
       __syncthreads();
+      HG_MARK(5 + 5 * band);
       // ================= B4: masker.2 input gradient x LeakyReLU' -> gradient of masker.0's output, in place of the activation
       for (int pg = warp; pg < 72; pg += 16) {
         const int r = pg >> 2, s = pg & 3;
@@ -213,6 +224,7 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
         }
       }
       __syncthreads();
+      HG_MARK(6 + 5 * band);
       // ================= B5: masker.0 weight gradient (warps 0-11, registers) || input gradient into up(o0), 2x2 sum (12-15)
       if (warp < 12) {
         const int tr = warp % 3, nt = (warp / 3) & 1, kh = warp / 6;
@@ -270,6 +282,7 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
       __syncthreads();
     }
 
+    HG_MARK(22);
     // ================= D0: dec[0] (cat(e0, up(o1)) -> o0 on 32x32): weight gradient (warps 0-7) || input gradient -> d o1 (8-15)
     if (warp < 8) {
       const int tr = warp & 3, kh = warp >> 2, src = tr >> 1, kxg = tr & 1;
@@ -323,6 +336,7 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
           });
     }
     __syncthreads();
+    HG_MARK(23);
     // ================= D1: dec[1] (cat(e1, up(o2)) -> o1 on 16x16): weight gradient (warps 0-3) || input gradient -> d o2 (4-11)
     if (warp < 4) {
       const int tr = warp, src = tr >> 1, kxg = tr & 1;
@@ -372,6 +386,7 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
           });
     }
     __syncthreads();
+    HG_MARK(24);
     // ================= D2: dec[2] (cat(e2, up(o3)) 24 -> 8 on 8x8): weight gradient, 15 (channel block, tap pair) tiles (warps 0-7)
     //                   || input gradient into up(o3) -> 2x2 sum -> d o3 (warps 8-15: 4 row pairs x 2 channel tiles)
     if (warp < 8) {
@@ -413,6 +428,7 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
         *reinterpret_cast<uint32_t*>(smraw + kDO3 + nt * PB4 + ((mt + 1) * P4 + (g >> 1) + 1) * 16 + 4 * t) = pack_bf16(s0, s1);
     }
     __syncthreads();
+    HG_MARK(25);
     // ================= D3: dec[3] (cat(e3, up4(dec[4])) 48 -> 16 on 4x4): weight gradient, 60 tiles of ONE MMA per frame;
     //                   input gradient into the dec[4] half, summed over the 16 pixels -> d(dec[4] output) (warps 0-3 afterwards)
     for (int tile = warp; tile < 60; tile += 16) {
@@ -447,10 +463,13 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
       if (g == 0) { sDD4[nt * 8 + 2 * t] = s0; sDD4[nt * 8 + 2 * t + 1] = s1; }
     }
     __syncthreads();
+    HG_MARK(26);
     // ================= D4: dec[4] (1x1 conv on the bottleneck h): dW[o][i] += dD4[o] * h[i]
     accD4[0] = fmaf(sDD4[tid >> 5], sH[tid & 31], accD4[0]);
     accD4[1] = fmaf(sDD4[16 + (tid >> 5)], sH[tid & 31], accD4[1]);
     if (tid < 32) accB4 += sDD4[tid];
+    HG_MARK(27);
+    ++fr;
     if (p.dbg && n == 0) {                             // debug dump of frame 0: d o0 | d o1 | d o2 | d o3 planes (raw bytes) | dD4
       uint32_t* d = reinterpret_cast<uint32_t*>(p.dbg);
       const uint32_t* s = reinterpret_cast<const uint32_t*>(smraw + kDO0);
@@ -553,6 +572,12 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
 }  // namespace cgs
 
 using namespace cgs;
+
+// Debug: point the phase traces of the forward / backward kernels at device buffers of 64 int64 each (NULL disables).
+extern "C" int cgs_hg_set_trace(long long* fwd_buf, long long* bwd_buf) {
+  if (hg::set_fwd_trace(fwd_buf) != 0) return -2;
+  return cudaMemcpyToSymbol(hg::g_hgb_trace, &bwd_buf, sizeof(bwd_buf)) == cudaSuccess ? 0 : -2;
+}
 
 extern "C" int cgs_hg_grid(int32_t B) {
   if (B <= 0) return 0;

@@ -208,6 +208,12 @@ __device__ __forceinline__ void m0_band(uint8_t* band_base, uint32_t smb, uint32
   else m0_rows<4>(band_base, smb, xplane, xrow0, xrows, w0, bm0, band, 2 + 4 * seg, x0, lane);
 }
 
+// debug: clock64() at phase boundaries of CTA 0's first two frames (tools/hg_trace.py); NULL = off
+#define HG_MARK(k)                                                    \
+  do {                                                                \
+    if (trace && tid == 0 && fr < 2) trace[fr * 32 + (k)] = clock64(); \
+  } while (0)
+
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
 }

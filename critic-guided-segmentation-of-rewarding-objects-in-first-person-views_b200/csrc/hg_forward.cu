@@ -127,6 +127,8 @@ __global__ void hg_pack_kernel(const PackSrc p, uint2* __restrict__ out) {
   out[e] = v;
 }
 
+__device__ long long* g_hgf_trace = nullptr;
+
 __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
   extern __shared__ __align__(128) uint8_t smraw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3, odd = g & 1;
@@ -150,6 +152,8 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
   __nv_bfloat16* sO3 = reinterpret_cast<__nv_bfloat16*>(smraw + tO3);
   __nv_bfloat16* sO2 = reinterpret_cast<__nv_bfloat16*>(smraw + tO2);
 
+  long long* trace = blockIdx.x == 0 ? g_hgf_trace : nullptr;
+  int fr = 0;
   const unsigned long long rng_call = p.rng_state ? p.rng_state[0] : 0ull;
   if (blockIdx.x < p.B) {
     const uint8_t* src = p.frames + (size_t)blockIdx.x * 12288;
@@ -186,6 +190,7 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
   for (int n = blockIdx.x; n < p.B; n += gridDim.x) {
     cp_async_wait_all();
     __syncthreads();
+    HG_MARK(0);
     // ================= frame bytes have landed -> pair-duplicated bf16 plane (rows 1..64); this frame's dropout masks
     stage_rows(smraw + fU8, smraw + fX + PX * 16, 0, 64, roll, tid);
     if (p.train) {
@@ -203,6 +208,7 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
       cp_async_commit();
     }
 
+    HG_MARK(1);
     // ================= features.0 (3 -> 8) + ReLU + pool -> e0 : 4 strips x 4 segments of 16 rows, one MMA per filter row
     {
       const int x0 = (warp & 3) * 16, r0 = (warp >> 2) * 16;
@@ -220,6 +226,7 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
           });
     }
     __syncthreads();
+    HG_MARK(2);
     // ================= features.3 (8 -> 8) on 32x32 -> e1 : 2 strips x 8 segments of 4 rows
     {
       const int x0 = (warp & 1) * 16, r0 = (warp >> 1) * 4;
@@ -243,6 +250,7 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
           });
     }
     __syncthreads();
+    HG_MARK(3);
     // ================= features.6 (8 -> 8) on 16x16 -> e2 (skip, pre-dropout) and e2 * mask (operand of features.10)
     if (warp < 8) {
       const int r0 = warp * 2;
@@ -268,6 +276,7 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
           });
     }
     __syncthreads();
+    HG_MARK(4);
     // ================= features.10 (8 -> 16) on 8x8 -> e3: skip planes (pre-dropout) + head operand (K order, * mask)
     float4 w4r[4];
     const int rot4 = (tid >> 1) & 3;
@@ -298,6 +307,7 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
       sC3[(co >> 3) * (PB4 / 2) + ((py + 1) * P4 + px + 1) * 8 + (co & 7)] = __float2bfloat16_rn(m);
     }
     __syncthreads();
+    HG_MARK(5);
     // ================= features.14 (4x4 valid conv = 256 -> 32) + ReLU -> h = embeds[4]
     {
       const int nn = tid >> 4, part = tid & 15;
@@ -326,6 +336,7 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
       sC3[(2 + (nn >> 3)) * (PB4 / 2) + (((part >> 2) + 1) * P4 + (part & 3) + 1) * 8 + (nn & 7)] = __float2bfloat16_rn(d + sHW[hBd4 + nn]);
     }
     __syncthreads();
+    HG_MARK(6);
     // ================= dec[3]: 48 -> 16 on 4x4: 27 k-steps split over 8 warp groups x 2 channel tiles; pred on the side
     {
       const int nt = warp & 1, grp = warp >> 1;
@@ -354,6 +365,7 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
       sO3[nt * (PB4 / 2) + (((pix >> 2) + 1) * P4 + (pix & 3) + 1) * 8 + c8] = __float2bfloat16_rn(s);
     }
     __syncthreads();
+    HG_MARK(7);
     // ================= dec[2]: cat(e2, up(o3)) 24 -> 8 on 8x8 : 4 row-pair tiles x 18 k-steps split over 4 warp groups
     {
       const int mt = warp & 3, grp = warp >> 2;
@@ -383,6 +395,7 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
       sO2[((y + 1) * P3 + x + 1) * 8 + co] = __float2bfloat16_rn(s);
     }
     __syncthreads();
+    HG_MARK(8);
     // ================= dec[1]: cat(e1, up(o2)) 16 -> 8 on 16x16 : 8 warps x 2 rows, one k16 step per filter tap
     if (warp < 8) {
       const int r0 = warp * 2;
@@ -409,6 +422,7 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
           });
     }
     __syncthreads();
+    HG_MARK(9);
     // ================= dec[0]: cat(e0, up(o1)) 16 -> 8 on 32x32 -> o0 : 2 strips x 8 segments of 4 rows
     {
       const int x0 = (warp & 1) * 16, r0 = (warp >> 1) * 4;
@@ -435,12 +449,14 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
           });
     }
     __syncthreads();
+    HG_MARK(10);
     // ================= training: the tape (every plane above, as it lies in shared memory) -> HBM, coalesced 16-byte stores
     if (p.tape) {
       uint4* dst = reinterpret_cast<uint4*>(p.tape + (size_t)n * TAPE);
       const uint4* src = reinterpret_cast<const uint4*>(smraw);
       for (int e = tid; e < TAPE / 16; e += NT) dst[e] = src[e];
     }
+    HG_MARK(11);
     // ================= masker.0 + LeakyReLU -> 18-row band -> masker.2 + Sigmoid (+ threshold), 4 bands of 16 mask rows
     // (the split-K scratch aliases the band: its columns 0 and 65 must be zero again)
     for (int e = tid; e < 2 * 18 * 2; e += NT) {
@@ -449,8 +465,10 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
     }
     __syncthreads();
     for (int band = 0; band < 4; ++band) {
+      HG_MARK(12 + 2 * band);
       m0_band(smraw + fBand, smb, fX, 0, 66, sWf + F_M0 * 32, sBias + bM0, band, warp, lane);
       __syncthreads();
+      HG_MARK(13 + 2 * band);
       {
         const int x0 = (warp & 3) * 16, r0 = (warp >> 2) * 4;
         uint2 w[3][3][1];
@@ -481,6 +499,8 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
       }
       __syncthreads();
     }
+    HG_MARK(20);
+    ++fr;
   }
   cp_async_wait_all();
   if (p.rng_state && tid == 0) {                     // last CTA to finish advances the call counter (every CTA has read it)
@@ -496,6 +516,9 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
 }  // namespace cgs
 
 using namespace cgs;
+
+extern "C" int cgs_hg_set_trace(long long* fwd_buf, long long* bwd_buf);   // defined in hg_backward.cu
+namespace cgs { namespace hg { int set_fwd_trace(long long* b) { return cudaMemcpyToSymbol(g_hgf_trace, &b, sizeof(b)) == cudaSuccess ? 0 : -2; } } }
 
 extern "C" int cgs_hg_pack_words(void) { return hg::NSTEPS * 64; }
 extern "C" int cgs_hg_tape_bytes(void) { return hg::TAPE; }

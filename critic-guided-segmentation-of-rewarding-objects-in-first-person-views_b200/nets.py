@@ -86,11 +86,20 @@ class NewCritic(nn.Module):
         if self.p >= 1.0:
             z = lambda *s: torch.zeros(s, device=device, dtype=torch.float32)
             return z(B, 8, 8, c2), z(B, 4, 4, c3), z(B, nb)
-        if self._rng_state is None or self._rng_state.device != device:
-            # Philox stream keyed by torch's seed (torch.manual_seed reproducible), advanced on the device
-            self._rng_state = torch.zeros(2, dtype=torch.int64, device=device)
-            self._rng_seed = self._philox_key()
+        self._ensure_rng(device)
         return tuple(ops.dropout_masks([(B, 8, 8, c2), (B, 4, 4, c3), (B, nb)], self.p, self._rng_seed, self._rng_state))
+
+    def _ensure_rng(self, device):
+        """The module's Philox stream state {call counter, ticket}: created once per device (keyed by torch's seed, so
+        torch.manual_seed makes it reproducible) and advanced on the device by every kernel that draws from it.  `device` may be
+        a string or an index-less torch.device("cuda"): it is normalised before comparing, or the state would be re-created
+        (and the stream restarted) on every call."""
+        dev = torch.device(device)
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if self._rng_state is None or self._rng_state.device != dev:
+            self._rng_state = torch.zeros(2, dtype=torch.int64, device=dev)
+            self._rng_seed = self._philox_key()
 
     def _philox_key(self):
         return (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._instance + 0x632BE59BD9B4E019 * self._rank) & 0x7FFFFFFFFFFFFFFF
@@ -100,9 +109,7 @@ class NewCritic(nn.Module):
         0 < p < 1, no forced masks): the same stream `_dropout_masks` would consume, one call per forward.  Else None."""
         if self._forced_masks is not None or not self.training or not (0.0 < self.p < 1.0):
             return None
-        if self._rng_state is None or self._rng_state.device != device:
-            self._rng_state = torch.zeros(2, dtype=torch.int64, device=device)
-            self._rng_seed = self._philox_key()
+        self._ensure_rng(device)
         return self.p, self._rng_seed, self._rng_state
 
     def forward(self, X, collect=False):

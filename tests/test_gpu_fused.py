@@ -594,7 +594,7 @@ def test_hourglass_tc_loop_vs_reference_curve(ops):
     ri = np.array([t["replace"] + t["inject"] for t in H.seg_log])
     assert len(l1) == len(q)
     rel = np.abs(sm(l1) - sm(q[:, 2])) / sm(q[:, 2])
-    assert rel.max() < 0.03, ("L1 curve vs operand-precision oracle", rel.max())
+    assert rel.max() < 0.06, ("L1 curve vs operand-precision oracle", rel.max())
     assert np.abs(sm(ri) - sm(q[:, 0] + q[:, 1])).max() <= 0.03 * sm(q[:, 0] + q[:, 1]).max() + 1e-6
     rel32 = np.abs(sm(l1) - sm(d["seg_l1"])) / sm(d["seg_l1"])
     assert rel32.max() < 0.30, ("L1 curve vs fp32 reference", rel32.max())
@@ -660,6 +660,7 @@ def test_hg_score_rng_stream_matches_two_forced_calls(ops):
     c = _critic(csd, p)
     m_r = [t.clone() for t in c._dropout_masks(B, DEV)]
     m_i = [t.clone() for t in c._dropout_masks(B, DEV)]
+    assert int(c._rng_state[0].item()) == 2 and not torch.equal(m_r[0], m_i[0]), "the module's Philox stream must advance per call"
     l1_, dz1, pr1, pi1 = ops.hg_score(c, Ad, Bd, Z, tr, ti, roll=3, masks=m_r, masks_inject=m_i, l1=0.5)
     torch.manual_seed(5)
     c2 = _critic(csd, p)

@@ -44,8 +44,11 @@ def test_graphed_critic_steps_match_eager(precision):
         lg = [g(Xh[i * B:(i + 1) * B], Yh[i * B:(i + 1) * B]).item() for i in range(N)]
         pg = g.opti.flat.clone()
         assert int(g.opti.step_count[0].item()) == N
-        np.testing.assert_allclose(lg, le, rtol=1e-6, atol=1e-9)
-        assert (pg - pe).abs().max().item() <= 1e-7 * max(pe.abs().max().item(), 1.0)
+        # tf32 = the whole-step kernel (fixed-order partial vectors: bit-reproducible); fp32 = per-layer kernels whose weight
+        # gradients arrive by float REDs (summation order varies run to run)
+        ptol = 1e-7 if precision == "tf32" else 2e-6
+        np.testing.assert_allclose(lg, le, rtol=1e-6 if precision == "tf32" else 1e-5, atol=1e-9)
+        assert (pg - pe).abs().max().item() <= ptol * max(pe.abs().max().item(), 1.0)
         # pipelined trainer: chunked path (chunk 2) + ragged tail through step()
         H3 = _handler(["--dropout", "0.3"])
         tr = PipelinedCriticTrainer(H3, B)
@@ -54,8 +57,8 @@ def test_graphed_critic_steps_match_eager(precision):
         tr.train(Xh[:5 * B].pin_memory(), Yh[:5 * B].pin_memory(), rolls=rolls[:5], chunk=2)
         tr.step(Xh[5 * B:].pin_memory(), Yh[5 * B:].pin_memory(), roll=3)
         lp = tr.losses().numpy()
-        np.testing.assert_allclose(lp, le, rtol=1e-6, atol=1e-9)
-        assert (tr.opti.flat - pe).abs().max().item() <= 1e-7 * max(pe.abs().max().item(), 1.0)
+        np.testing.assert_allclose(lp, le, rtol=1e-6 if precision == "tf32" else 1e-5, atol=1e-9)
+        assert (tr.opti.flat - pe).abs().max().item() <= ptol * max(pe.abs().max().item(), 1.0)
     finally:
         ops.set_precision("fp32")
 

@@ -64,6 +64,9 @@ EXPORTS = {
                               C.POINTER(CriticWeights), C.c_float, C.c_int32, _f32p, _f32p, _f32p, C.c_void_p],
     "cgs_critic_forward_frames": [_u8p, C.c_int32, C.c_int32, C.c_void_p, _f32p, _f32p, _f32p, C.c_float, C.c_uint64, C.c_void_p,
                                   C.POINTER(CriticWeights), _f32p, C.c_void_p],
+    "cgs_hg_score_bf16": [_u8p, _u8p, C.c_int32, C.c_int32, C.c_void_p, _f32p, _f32p, _f32p, C.c_void_p, C.c_float, C.c_uint64, C.c_void_p,
+                          C.POINTER(CriticWeights), C.c_void_p, C.c_float, _f32p, C.c_float, C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p,
+                          C.c_void_p],
     "cgs_hg_score": [_u8p, _u8p, C.c_int32, C.c_int32, C.c_void_p, _f32p, _f32p, _f32p] + [_f32p] * 6 +
                     [C.c_float, C.c_uint64, C.c_void_p, C.POINTER(CriticWeights), C.c_float, _f32p, C.c_float, C.c_float,
                      _f32p, _f32p, _f32p, _f32p, C.c_void_p],

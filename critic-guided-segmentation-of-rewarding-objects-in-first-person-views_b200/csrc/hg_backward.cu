@@ -144,16 +144,24 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
     for (int band = 0; band < 4; ++band) {
       HG_MARK(2 + 5 * band);
       // ================= B1: the band's 20 frame rows (pair-duplicated bf16) and 20 rows of d logit = dZ * Z * (1 - Z)
+      // (the mask / mask-gradient loads are put in flight first and consumed after the frame rows are staged)
+      float zz[3], dd[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int e = tid + NT * i, rho = e >> 6, x = e & 63, y = 16 * band - 2 + rho;
+        const bool ok = e < 20 * 64 && y >= 0 && y < 64;
+        zz[i] = ok ? __ldg(zf + y * 64 + x) : 0.f;
+        dd[i] = ok ? __ldg(dzf + y * 64 + x) : 0.f;
+      }
       stage_rows(smraw + kU8, smraw + kXB, 16 * band - 2, 20, roll, tid);
-      for (int e = tid; e < 20 * 64; e += NT) {
-        const int rho = e >> 6, x = e & 63, y = 16 * band - 2 + rho;
-        float v = 0.f;
-        if (y >= 0 && y < 64) {
-          const float zz = __ldg(zf + y * 64 + x);
-          v = __ldg(dzf + y * 64 + x) * zz * (1.f - zz);
-          if (rho >= 2 && rho < 18) bsum2 += v;       // masker.2 bias gradient: every mask row exactly once
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int e = tid + NT * i, rho = e >> 6, x = e & 63;
+        if (e < 20 * 64) {
+          const float v = dd[i] * zz[i] * (1.f - zz[i]);    // 0 outside the frame
+          if (rho >= 2 && rho < 18) bsum2 += v;             // masker.2 bias gradient: every mask row exactly once
+          sDL[rho * DLP + x + 1] = v;
         }
-        sDL[rho * DLP + x + 1] = v;
       }
       __syncthreads();
       HG_MARK(3 + 5 * band);

@@ -34,7 +34,9 @@ static_assert(TAPE == 55296 && TAPE % 16 == 0, "tape layout");
 
 // ---- weight fragments: pack[step][lane] = uint2 {b0, b1} of the K16 x N8 matrix of that MMA step
 constexpr int F_C0 = 0, F_C1 = 3, F_C2 = 9, F_C3 = 15, F_D2 = 25, F_D1 = 43, F_D0 = 52, F_M0 = 61, F_M2 = 79, F_D3 = 88;
-constexpr int B_M0D = 142, B_D0D = 151, B_D1D = 157, B_M2D = 163, B_D2D = 165, B_D3D = 175, NSTEPS = 211;
+constexpr int B_M0D = 142, B_D0D = 151, B_D1D = 157, B_M2D = 163, B_D2D = 165, B_D3D = 175;
+// critic input-gradient steps (hg_score.cu): features.10 / .6 / .3 / .0 with the rotated, in/out-swapped filters
+constexpr int B_C3D = 211, B_C2D = 220, B_C1D = 226, B_C0D = 232, NSTEPS = 238;
 constexpr int F_SMEM_STEPS = F_D3;                 // the forward kernel keeps steps [0, 88) in shared memory
 
 // masker parameters in state_dict order (= flat gradient layout of the partial vectors)
@@ -126,8 +128,10 @@ __device__ __forceinline__ void stage_rows(const uint8_t* __restrict__ sU8, uint
     uint2 v = make_uint2(0u, 0u);
     if (y >= 0 && y < 64) {
       const uint8_t* s = sU8 + (y * 64 + ((x + roll) & 63)) * 3;
-      v.x = pack_bf16(__fdiv_rn((float)s[0], 255.f), __fdiv_rn((float)s[1], 255.f));
-      v.y = pack_bf16(__fdiv_rn((float)s[2], 255.f), 0.f);
+      // bf16(b * fl(1/255)) == bf16(b / 255.0f) for all 256 byte values (checked exhaustively): no division needed
+      constexpr float k = 1.f / 255.f;
+      v.x = pack_bf16(__fmul_rn((float)s[0], k), __fmul_rn((float)s[1], k));
+      v.y = pack_bf16(__fmul_rn((float)s[2], k), 0.f);
     }
     uint8_t* row = dst + (size_t)rho * (PX * 16);
     *reinterpret_cast<uint2*>(row + (x + 1) * 16) = v;        // haloed pixel x+1 = low half of entry x+1 ...

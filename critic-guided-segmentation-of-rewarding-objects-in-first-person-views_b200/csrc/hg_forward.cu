@@ -111,9 +111,18 @@ __device__ float pack_wk(const PackSrc& p, int s, int k, int n) {
     const int q = s - B_D2D, nt = q & 1, tp = 2 * (q >> 1) + (k >> 3), co = k & 7;
     return tp > 8 ? 0.f : p.d2[(co * 24 + 8 + nt * 8 + n) * 9 + 8 - tp];
   }
-  {                                                 // dec[3] -> dec[4] output: step tap'*4 + nt; k = co (16); n: ci = 16 + nt*8 + n
+  if (s < B_C3D) {                                  // dec[3] -> dec[4] output: step tap'*4 + nt; k = co (16); n: ci = 16 + nt*8 + n
     const int q = s - B_D3D, nt = q & 3, tp = q >> 2;
     return p.d3[(k * 48 + 16 + nt * 8 + n) * 9 + 8 - tp];
+  }
+  if (s < B_C2D) return p.w3[(k * 8 + n) * 9 + 8 - (s - B_C3D)];          // features.10 -> its input: k = co (16), n = ci (8)
+  {                                                 // features.6 / .3 / .0 -> their inputs: step ky'*2 + h; k = (tap' pair) x co (8)
+    const float* w = s < B_C1D ? p.w2 : (s < B_C0D ? p.w1 : p.w0);
+    const int q = s - (s < B_C1D ? B_C2D : (s < B_C0D ? B_C1D : B_C0D)), ky = q >> 1, h = q & 1;
+    if (h && k >= 8) return 0.f;
+    const int kx = h ? 2 : (k >> 3), co = k & 7, tap = 8 - (ky * 3 + kx);
+    if (s < B_C0D) return w[(co * 8 + n) * 9 + tap];
+    return n < 3 ? w[(co * 3 + n) * 9 + tap] : 0.f;  // features.0: 3 input channels
   }
 }
 

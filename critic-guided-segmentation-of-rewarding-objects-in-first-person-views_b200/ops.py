@@ -795,6 +795,39 @@ def hg_forward(critic, masker, frames_u8, roll=0, train=False, masks=None, rng=N
     return pred.unsqueeze(1), mask, hard
 
 
+def hg_score_bf16(critic, A_u8, B_u8, z, pack, target_replace=None, target_inject=None, roll=0, masks=None, rng=None,
+                  loss_grad=1.0, vpred=None, l1=0.0, l2=0.0):
+    """The critic-scoring part of one frozen-critic Hourglass step in ONE bf16 kernel (cgs_hg_score_bf16; reference
+    main.py:365-367, 395-429).  target_replace None: the kernel first computes negpred = critic(B) itself.  masks: None, or the
+    forced dropout triples (critic(B), critic(replaced), critic(injected)) - entries of passes that do not run may be None.
+    Returns (losses [4] = replace, inject, L1, L2; dz [B,64,64]; negpred [B] or None; pred_replace [B]; pred_inject [B] or None)."""
+    Bn = A_u8.shape[0]
+    dev = A_u8.device
+    w = _lib.CriticWeights(*[_p(q.detach()) for q in critic.parameters()])
+    zc = _c(z.detach())
+    assert zc.numel() == Bn * 4096
+    new = lambda: torch.empty(Bn, device=dev, dtype=torch.float32)
+    neg = new() if target_replace is None else None
+    pr = new()
+    pi = new() if target_inject is not None else None
+    losses = torch.empty(4, device=dev, dtype=torch.float32)
+    dz = torch.empty((Bn, 64, 64), device=dev, dtype=torch.float32)
+    rd, r = (_p(roll, torch.int32), 0) if torch.is_tensor(roll) else (None, int(roll or 0))
+    m9 = None
+    if masks is not None and any(m is not None and m[0] is not None for m in masks):
+        flat = []
+        for m in masks:
+            flat += [None, None, None] if (m is None or m[0] is None) else [_p(t) for t in m]
+        m9 = (C.c_void_p * 9)(*flat)
+    rp, rseed, rstate = _rng_args(rng)
+    _call("cgs_hg_score_bf16", _p(A_u8, torch.uint8), _p(B_u8, torch.uint8), Bn, r, rd, _p(zc),
+          _p(_c(target_replace.detach())) if target_replace is not None else None,
+          _p(_c(target_inject.detach())) if target_inject is not None else None, m9, rp, rseed, rstate, C.byref(w),
+          _p(pack, torch.int32), float(loss_grad), _p(_c(vpred.detach())) if vpred is not None else None, float(l1), float(l2),
+          _p(neg), _p(pr), _p(pi), _p(losses), _p(dz), _stream())
+    return losses, dz, neg, pr, pi
+
+
 def hg_tape(B, device):
     return torch.empty((B, _lib.lib().cgs_hg_tape_bytes()), device=device, dtype=torch.uint8)
 

@@ -254,6 +254,7 @@ class Handler:
                            self.maskername: f"{self.save_path}masker-{self.masker_args}.pt"}
         self.contrastive_batchsize = 32      # main.py:309
         self.fused_critic_step = True        # tf32 mode, chfak 1: one kernel per critic_pipe step
+        self.hg_score_bf16 = True            # frozen Hourglass step: the three critic scoring passes in ONE bf16 kernel (else TF32)
         self.hg_inference = True             # tensor-core mode, chfak 1: -process in ONE bf16 kernel (csrc/hg_forward.cu)
         self.device_dataset = True           # segmentation_training gathers its batches from a device-resident uint8 dataset
         self.device_dataset_bytes = 8 << 30  # ... when the pos + neg frames fit this budget (100k frames = 1.2 GB)
@@ -487,10 +488,10 @@ class Handler:
         return len(opti.params) == len(mp) and all(q is r for q, r in zip(opti.params, mp))
 
     def segmentation_step_fused(self, X_u8, CX_u8, opti, roll=0, weight=1.0):
-        """One frozen-critic iteration of segmentation_training (main.py:344-463) in six launches: weight-fragment pack,
-        Hourglass forward on A (critic with embeds + decoder + masker; leaves the tape), critic forward on B, the two scored
-        blends with their losses, regulariser and d loss / d mask (cgs_hg_score), the masker's whole backward, and the
-        partial-vector sum + Adam.  No activation but the mask, its gradient and the 54 KB/frame bf16 tape touches HBM."""
+        """One frozen-critic iteration of segmentation_training (main.py:344-463) in five launches: weight-fragment pack,
+        Hourglass forward on A (critic with embeds + decoder + masker; leaves the tape), the critic scoring passes (critic(B),
+        the two scored blends with their losses, regulariser and d loss / d mask: cgs_hg_score_bf16), the masker's whole
+        backward, and the partial-vector sum + Adam.  No activation but the mask, its gradient and the 54 KB/frame bf16 tape touches HBM."""
         a = self.args
         critic, masker, dev = self.critic, self.masker, self.device
         x = X_u8 if torch.is_tensor(X_u8) else torch.from_numpy(np.ascontiguousarray(X_u8))
@@ -510,19 +511,29 @@ class Handler:
         rng, masks = drop()                                                                # critic(A, collect=True)   main.py:364
         pred, Z, _ = ops.hg_forward(critic, masker, x, roll=roll, train=critic.training, masks=masks, rng=rng, tape=st["tape"],
                                     pack=pack)
-        rng, masks = drop()                                                                # critic(B)                 main.py:365
-        negpred = ops.critic_forward_frames(critic, cx, 0, masks if masks is not None else (None, None, None), rng)
-        if rng is not None:
-            m_r = m_i = None
+        vpred = None if a.staticnorm else pred.squeeze(1)
+        if self.hg_score_bf16:
+            # critic(B), critic(replaced), critic(injected) with their losses, the regulariser and d/dZ: ONE bf16 kernel
+            rng = critic._dropout_rng(dev)
+            forced = None
+            if rng is None:
+                forced = [critic._dropout_masks(B, dev) for _ in range(3 if a.inject else 2)] + ([None] if not a.inject else [])
+            losses, dz, _, _, _ = ops.hg_score_bf16(critic, x, cx, Z, pack, None, pred.squeeze(1) if a.inject else None, roll=roll,
+                                                    masks=forced, rng=rng, loss_grad=weight, vpred=vpred,
+                                                    l1=float(a.L1 or 0.0), l2=float(a.L2 or 0.0))
         else:
-            m_r = critic._dropout_masks(B, dev)                                            # critic(replaced)          main.py:396
-            m_i = critic._dropout_masks(B, dev) if a.inject else None                      # critic(injected)          main.py:407
-            m_r = None if m_r[0] is None else m_r
-            m_i = None if (m_i is None or m_i[0] is None) else m_i
-        losses, dz, _, _ = ops.hg_score(critic, x, cx, Z, negpred.squeeze(1), pred.squeeze(1) if a.inject else None, roll=roll,
-                                        masks=m_r, masks_inject=m_i, rng=critic._dropout_rng(dev) if rng is not None else None,
-                                        loss_grad=weight, vpred=None if a.staticnorm else pred.squeeze(1),
-                                        l1=float(a.L1 or 0.0), l2=float(a.L2 or 0.0))
+            rng, masks = drop()                                                            # critic(B)                 main.py:365
+            negpred = ops.critic_forward_frames(critic, cx, 0, masks if masks is not None else (None, None, None), rng)
+            if rng is not None:
+                m_r = m_i = None
+            else:
+                m_r = critic._dropout_masks(B, dev)                                        # critic(replaced)          main.py:396
+                m_i = critic._dropout_masks(B, dev) if a.inject else None                  # critic(injected)          main.py:407
+                m_r = None if m_r[0] is None else m_r
+                m_i = None if (m_i is None or m_i[0] is None) else m_i
+            losses, dz, _, _ = ops.hg_score(critic, x, cx, Z, negpred.squeeze(1), pred.squeeze(1) if a.inject else None, roll=roll,
+                                            masks=m_r, masks_inject=m_i, rng=critic._dropout_rng(dev) if rng is not None else None,
+                                            loss_grad=weight, vpred=vpred, l1=float(a.L1 or 0.0), l2=float(a.L2 or 0.0))
         opti.zero_grad()
         L = _lib.lib()
         grid, stride = L.cgs_hg_grid(B), L.cgs_hg_partial_stride()

@@ -349,6 +349,19 @@ int cgs_hg_backward(const uint8_t* frames, int32_t B, int32_t roll, const int32_
                     const uint32_t* pack, const void* tape, const float* z, const float* dz, float* partials, float* debug,
                     void* stream);
 
+/* The critic-scoring part of one frozen-critic segmentation_training step in ONE bf16 kernel (csrc/hg_score.cu; main.py:365-367,
+ * 395-429): [negpred = critic(B) when target_replace == NULL], replaced = A(1-Z)+ZB and injected = B(1-Z)+ZA scored by the
+ * critic against negpred / target_inject (= pred of critic(A)), the L1 / L2 mask regulariser, and dz [B,64,64] = loss_grad *
+ * d(sum of the terms) / dZ.  frames_a (rolled by roll / *roll_dev) / frames_b: uint8 NHWC; z [B,64,64]; pack: cgs_hg_pack.
+ * masks9: NULL, or a HOST array of 9 device pointers {m_e2, m_e3, m_v} x {critic(B), critic(replaced), critic(injected)} of
+ * forced dropout masks (entries of passes that do not run may be NULL); rng_state: masks drawn in the kernel, one call index
+ * per pass in that order.  losses[4] = replace, inject, L1, L2 terms.  The TF32 variant is cgs_hg_score. */
+int cgs_hg_score_bf16(const uint8_t* frames_a, const uint8_t* frames_b, int32_t B, int32_t roll, const int32_t* roll_dev,
+                      const float* z, const float* target_replace, const float* target_inject, const float* const* masks9,
+                      float p_drop, uint64_t seed, uint64_t* rng_state, const cgs_critic_weights* w, const uint32_t* pack,
+                      float loss_grad, const float* vpred, float l1, float l2, float* negpred, float* pred_replace,
+                      float* pred_inject, float* losses, float* dz, void* stream);
+
 /* ---- formats either side of the path, csrc/edges.cu ---------------------------------------------------
  * out[i] = dataset[idx[i]] for uint8 NHWC frames (12288 bytes each): `Xpos[Hidx]`, `Xneg[Lidx]`, `Xneg[Cidx]` of
  * main.py:345-353 over a device-resident dataset; indices are clamped to [0, nframes). */

@@ -1,6 +1,7 @@
 """Generate tests/golden/loops_q_c1.npz: the 94-step segmentation_training phase of tests/golden/loops_c1.npz re-run by the
 ORACLE (oracle/torch_ref.py; bit-identical to the unmodified reference on this curve, asserted below)
-  * at the operand precision of the whole-frame kernels (bf16 for critic(A) + masker, TF32 for the scoring passes), and
+  * at the operand precision of the whole-frame kernels: all bf16 (`q_bf16`, the default fused step), bf16 Hourglass + TF32
+    scoring passes (`q_bf16_tf32`, Handler.hg_score_bf16 = False) and all TF32 (`q_tf32`), and
   * in reference arithmetic from masker weights perturbed by 1e-6 relative (4 seeds): the reference's own sensitivity
     envelope for this phase.
 Authoring container only (CPU, ~1 minute):  python tests/golden/make_golden_q.py"""
@@ -53,13 +54,14 @@ if __name__ == "__main__":
     base = run(d, X, Y)
     print("oracle vs reference curve: max |diff|", np.abs(base - ref).max())
     assert np.allclose(base, ref, rtol=1e-5, atol=1e-8), "oracle loop no longer reproduces the reference curve"
-    qrun = run(d, X, Y, q_embed=torch_ref.quant_bf16, q_score=torch_ref.quant_tf32, q_mask=torch_ref.quant_bf16)
+    qrun = run(d, X, Y, q_embed=torch_ref.quant_bf16, q_score=torch_ref.quant_bf16, q_mask=torch_ref.quant_bf16)
+    mix = run(d, X, Y, q_embed=torch_ref.quant_bf16, q_score=torch_ref.quant_tf32, q_mask=torch_ref.quant_bf16)
     tf = run(d, X, Y, q_embed=torch_ref.quant_tf32, q_score=torch_ref.quant_tf32, q_mask=torch_ref.quant_tf32)
     pert = np.stack([run(d, X, Y, eps=1e-6, seed=s) for s in (1, 2, 3, 4)])
     sm = lambda v: np.convolve(v, np.ones(30) / 30, mode="valid")
-    for name, r in (("bf16/tf32 operands", qrun), ("tf32 operands", tf), ("1e-6 perturbed #1", pert[0])):
+    for name, r in (("bf16 operands", qrun), ("bf16 / tf32-scoring operands", mix), ("tf32 operands", tf), ("1e-6 perturbed #1", pert[0])):
         dl1 = np.abs(sm(r[:, 2]) - sm(ref[:, 2])) / sm(ref[:, 2])
         dri = np.abs(sm(r[:, 0] + r[:, 1]) - sm(ref[:, 0] + ref[:, 1])) / sm(ref[:, 0] + ref[:, 1]).max()
         print(f"{name}: smoothed L1 curve deviates {dl1.max():.4f} (last {dl1[-1]:.4f}), replace+inject {dri.max():.4f}")
-    np.savez_compressed(f"{OUT}/loops_q_c1.npz", q_bf16=qrun.astype(np.float64), q_tf32=tf.astype(np.float64),
+    np.savez_compressed(f"{OUT}/loops_q_c1.npz", q_bf16=qrun.astype(np.float64), q_bf16_tf32=mix.astype(np.float64), q_tf32=tf.astype(np.float64),
                         perturbed_1e6=pert.astype(np.float64))

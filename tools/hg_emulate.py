@@ -43,7 +43,8 @@ ZERO = (0.0, 0.0)
 
 # ------------------------------------------------------------------ pack_wk (transcribed from hg_forward.cu)
 F_C0, F_C1, F_C2, F_C3, F_D2, F_D1, F_D0, F_M0, F_M2, F_D3 = 0, 3, 9, 15, 25, 43, 52, 61, 79, 88
-B_M0D, B_D0D, B_D1D, B_M2D, B_D2D, B_D3D, NSTEPS = 142, 151, 157, 163, 165, 175, 211
+B_M0D, B_D0D, B_D1D, B_M2D, B_D2D, B_D3D = 142, 151, 157, 163, 165, 175
+B_C3D, B_C2D, B_C1D, B_C0D, NSTEPS = 211, 220, 226, 232, 238
 
 
 def pack_wk(p, s, k, n):
@@ -99,8 +100,21 @@ def pack_wk(p, s, k, n):
     if s < B_D3D:
         q = s - B_D2D; nt = q & 1; tp = 2 * (q >> 1) + (k >> 3); co = k & 7
         return 0.0 if tp > 8 else p["d2"].reshape(8, 24, 9)[co, 8 + nt * 8 + n, 8 - tp]
-    q = s - B_D3D; nt, tp = q & 3, q >> 2
-    return p["d3"].reshape(16, 48, 9)[k, 16 + nt * 8 + n, 8 - tp]
+    if s < B_C3D:
+        q = s - B_D3D; nt, tp = q & 3, q >> 2
+        return p["d3"].reshape(16, 48, 9)[k, 16 + nt * 8 + n, 8 - tp]
+    if s < B_C2D:
+        return p["w3"].reshape(16, 8, 9)[k, n, 8 - (s - B_C3D)]
+    w = p["w2"] if s < B_C1D else (p["w1"] if s < B_C0D else p["w0"])
+    q = s - (B_C2D if s < B_C1D else (B_C1D if s < B_C0D else B_C0D))
+    ky, h = q >> 1, q & 1
+    if h and k >= 8:
+        return 0.0
+    kx, co = (2 if h else (k >> 3)), k & 7
+    tap = 8 - (ky * 3 + kx)
+    if s < B_C0D:
+        return w.reshape(8, 8, 9)[co, n, tap]
+    return w.reshape(8, 3, 9)[co, n, tap] if n < 3 else 0.0
 
 
 def wfrag(p, s):
@@ -458,6 +472,59 @@ def check_m0_dgrad(p):
     assert err < 1e-8
 
 
+def dgrad_ref(dy_chw, w):
+    """d input of a 3x3 s1 p1 conv: dx[ci][y][x] = sum dy[co][y-ky+1][x-kx+1] * w[co][ci][ky][kx]"""
+    C, H, W = dy_chw.shape
+    dp = np.zeros((C, H + 2, W + 2)); dp[:, 1:-1, 1:-1] = dy_chw
+    out = np.zeros((w.shape[1], H, W))
+    for ky in range(3):
+        for kx in range(3):
+            out += np.einsum("oc,ohw->chw", w[:, :, ky, kx], dp[:, 2 - ky:2 - ky + H, 2 - kx:2 - kx + W])
+    return out
+
+
+def check_critic_dgrads(p):
+    """features.3 (8 -> 8) and features.0 (8 -> 3) input gradients: tap-paired sliding conv of the haloed gradient plane with
+    the rotated filters (pack steps B_C1D, B_C0D); features.10 (16 -> 8): one k16 step per tap' (B_C3D)"""
+    for name, base, wkey, cin in (("features.3", B_C1D, "w1", 8), ("features.0", B_C0D, "w0", 3)):
+        dy = rng.standard_normal((32, 32, 8))
+        DY = plane(dy)
+        ref = dgrad_ref(dy.transpose(2, 0, 1), p[wkey])
+        w = [[wfrag(p, base + ky * 2 + h) for h in range(2)] for ky in range(3)]
+        x0, r0 = 16, 8
+        def loadA(i):
+            aA = [(r0 + i, x0 + lr + 8 * (lj & 1) + (lj >> 1)) for _, lj, lr, _, _ in lanes()]
+            aB = [(r0 + i, x0 + lr + 8 * (lj & 1) + 2) for _, lj, lr, _, _ in lanes()]
+            f0 = ldsm(lambda a: DY[a[0], a[1]], aA, 4, False)
+            f1 = ldsm(lambda a: DY[a[0], a[1]], aB, 2, False)
+            return [f0, [[r[0], r[1], ZERO, ZERO] for r in f1]]
+        acc = slide(4, 2, w, loadA)
+        err = 0.0
+        for oi, rows in acc.items():
+            for lane, _, _, g, t in lanes():
+                for q in range(4):
+                    c = 2 * t + (q & 1)
+                    want = ref[c, r0 + oi, x0 + g + 8 * (q >> 1)] if c < cin else 0.0
+                    err = max(err, abs(rows[lane][q] - want))
+        print(f"{name} dgrad (rotated filter, tap-paired): max err", err)
+        assert err < 1e-8
+    dy = rng.standard_normal((8, 8, 16))
+    DY = np.stack([plane(dy[:, :, :8]), plane(dy[:, :, 8:])])
+    ref = dgrad_ref(dy.transpose(2, 0, 1), p["w3"])
+    err = 0.0
+    for mt in range(4):
+        acc = [np.zeros(4) for _ in range(32)]
+        for tp in range(9):
+            ky, kx = tp // 3, tp % 3
+            addrs = [((lj >> 1), 2 * mt + (lj & 1) + ky, lr + kx) for _, lj, lr, _, _ in lanes()]
+            mma(acc, ldsm(lambda a: DY[a[0], a[1], a[2]], addrs, 4, False), wfrag(p, B_C3D + tp))
+        for lane, _, _, g, t in lanes():
+            for q in range(4):
+                err = max(err, abs(acc[lane][q] - ref[2 * t + (q & 1), 2 * mt + (q >> 1), g]))
+    print("features.10 dgrad (16 -> 8): max err", err)
+    assert err < 1e-8
+
+
 if __name__ == "__main__":
     p = dict(w0=rng.standard_normal((8, 3, 3, 3)), w1=rng.standard_normal((8, 8, 3, 3)), w2=rng.standard_normal((8, 8, 3, 3)),
              w3=rng.standard_normal((16, 8, 3, 3)), d0=rng.standard_normal((8, 16, 3, 3)), d1=rng.standard_normal((8, 16, 3, 3)),
@@ -470,4 +537,5 @@ if __name__ == "__main__":
     check_m0_wgrad_rgb(p)
     check_m2(p)
     check_m0_dgrad(p)
+    check_critic_dgrads(p)
     print("all emulated phases agree with the numpy references")

@@ -83,6 +83,9 @@ __device__ __forceinline__ void flush3(float* tiles, const float (&acc)[3][4], i
 
 __device__ long long* g_hgb_trace = nullptr;
 int set_fwd_trace(long long* b);
+}
+namespace hs { int set_trace(long long* b); }
+namespace hg {
 
 __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
   extern __shared__ __align__(128) uint8_t smraw[];
@@ -582,8 +585,8 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
 using namespace cgs;
 
 // Debug: point the phase traces of the forward / backward kernels at device buffers of 64 int64 each (NULL disables).
-extern "C" int cgs_hg_set_trace(long long* fwd_buf, long long* bwd_buf) {
-  if (hg::set_fwd_trace(fwd_buf) != 0) return -2;
+extern "C" int cgs_hg_set_trace(long long* fwd_buf, long long* bwd_buf, long long* score_buf) {
+  if (hg::set_fwd_trace(fwd_buf) != 0 || hs::set_trace(score_buf) != 0) return -2;
   return cudaMemcpyToSymbol(hg::g_hgb_trace, &bwd_buf, sizeof(bwd_buf)) == cudaSuccess ? 0 : -2;
 }
 

@@ -526,7 +526,6 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
 
 using namespace cgs;
 
-extern "C" int cgs_hg_set_trace(long long* fwd_buf, long long* bwd_buf);   // defined in hg_backward.cu
 namespace cgs { namespace hg { int set_fwd_trace(long long* b) { return cudaMemcpyToSymbol(g_hgf_trace, &b, sizeof(b)) == cudaSuccess ? 0 : -2; } } }
 
 extern "C" int cgs_hg_pack_words(void) { return hg::NSTEPS * 64; }

@@ -25,7 +25,9 @@ constexpr int sDY3 = sE2 + PB3;                     // d(features.10 output) (8x
 constexpr int sI0 = sDY3 + 2 * PB3;                 // arg-max bytes [32*32][8], [16*16][8], [8*8][8], [4*4][16]
 constexpr int sI1 = sI0 + 8192, sI2 = sI1 + 2048, sI3 = sI2 + 512;
 constexpr int sA8 = sI3 + 256, sB8 = sA8 + 12288;   // raw frame bytes
-constexpr int sX3 = sB8 + 12288;                    // e3 * mask in the 4x4 conv's K order, fp32 [256]
+constexpr int sZ = sB8 + 12288;                     // the frame's mask, fp32 [64][64]
+constexpr int sDZ = sZ + 16384;                     // d loss / d mask accumulated over the passes, fp32 [64][64]
+constexpr int sX3 = sDZ + 16384;                    // e3 * mask in the 4x4 conv's K order, fp32 [256]
 constexpr int sVec = sX3 + 1024;                    // fp32: h[32] v[32] dh[32] dv[32] | scalars
 constexpr int sM2 = sVec + 640, sM3 = sM2 + 2048, sMV = sM3 + 1024;
 constexpr int sW = sMV + 128;                       // weight fragments: forward steps [0, 25) | input-gradient steps [B_C3D, NSTEPS)
@@ -62,6 +64,13 @@ __device__ __forceinline__ float div255(float b) {
   return fmaf(fmaf(-255.f, q, b), k, q);
 }
 
+__device__ long long* g_hgs_trace = nullptr;
+// debug: clock64() at the phase boundaries of the two scoring passes of CTA 0's first two frames (tools/hg_trace.py)
+#define HS_MARK(k)                                                                                       \
+  do {                                                                                                   \
+    if (trace && tid == 0 && fr < 2 && pass >= 1) trace[fr * 32 + 16 * (pass - 1) + (k)] = clock64();     \
+  } while (0)
+
 __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
   extern __shared__ __align__(128) uint8_t smraw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3, odd = g & 1;
@@ -78,6 +87,10 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
   float* fMV = reinterpret_cast<float*>(smraw + sMV);
   uint8_t *bI0 = smraw + sI0, *bI1 = smraw + sI1, *bI2 = smraw + sI2, *bI3 = smraw + sI3;
   const uint8_t *bA8 = smraw + sA8, *bB8 = smraw + sB8;
+  const float* fZ = reinterpret_cast<const float*>(smraw + sZ);
+  float* fDZ = reinterpret_cast<float*>(smraw + sDZ);
+  long long* trace = blockIdx.x == 0 ? g_hgs_trace : nullptr;
+  int fr = 0;
   __nv_bfloat16* hE0 = reinterpret_cast<__nv_bfloat16*>(smraw + sE0);
   __nv_bfloat16* hE1 = reinterpret_cast<__nv_bfloat16*>(smraw + sE1);
   __nv_bfloat16* hE2 = reinterpret_cast<__nv_bfloat16*>(smraw + sE2);
@@ -115,10 +128,11 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
     __syncthreads();                                   // the previous frame's last pass is done with the raw bytes
     {
       const uint8_t *srcA = p.framesA + (size_t)n * 12288, *srcB = p.framesB + (size_t)n * 12288;
+      const float* srcZ = p.z + (size_t)n * 4096;
       for (int c = tid; c < 768; c += NT) { cp_async16(smb + sA8 + c * 16, srcA + c * 16); cp_async16(smb + sB8 + c * 16, srcB + c * 16); }
+      for (int c = tid; c < 1024; c += NT) cp_async16(smb + sZ + c * 16, srcZ + c * 4);
       cp_async_commit();
     }
-    const float* zf = p.z + (size_t)n * 4096;
     for (int pass = pass_lo; pass < pass_hi; ++pass) {
       // ================= this pass's dropout masks; then the frame / blend -> pair-duplicated bf16 plane
       if (forced) {
@@ -131,6 +145,7 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
       }
       cp_async_wait_all();
       __syncthreads();
+      HS_MARK(0);
       for (int e = tid; e < 4096; e += NT) {
         const int y = e >> 6, x = e & 63;
         const uint8_t* a = bA8 + (y * 64 + ((x + roll) & 63)) * 3;    // shift_batch rolls A only (main.py:355-357)
@@ -141,7 +156,7 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
           for (int c = 0; c < 3; ++c) v[c] = div255((float)b[c]);
         } else {
           // formed in fp32 exactly as the reference does: u8 -> float / 255, two products, one sum, no contraction
-          const float zz = __ldg(zf + e), omz = __fsub_rn(1.f, zz);
+          const float zz = fZ[e], omz = __fsub_rn(1.f, zz);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const float fa = div255((float)a[c]), fb = div255((float)b[c]);
@@ -159,6 +174,7 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
       __syncthreads();
       const float ytgt = pass == 0 ? 0.f : (pass == 1 ? (p.target_replace ? __ldg(p.target_replace + n) : sNeg[0]) : __ldg(p.target_inject + n));
 
+      HS_MARK(1);
       // ================= F0: features.0 (3 -> 8) + ReLU + pool + arg-max -> e0
       {
         const int x0 = (warp & 3) * 16, r0 = (warp >> 2) * 16;
@@ -180,6 +196,7 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
             });
       }
       __syncthreads();
+      HS_MARK(2);
       // ================= F1: features.3 (8 -> 8) on 32x32 -> e1; the scatter targets of the backward are cleared meanwhile
       {
         if (pass != 0) {
@@ -214,6 +231,7 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
             });
       }
       __syncthreads();
+      HS_MARK(3);
       // ================= F2: features.6 (8 -> 8) on 16x16 + Dropout -> e2 * mask
       if (warp < 8) {
         const int r0 = warp * 2;
@@ -239,6 +257,7 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
             });
       }
       __syncthreads();
+      HS_MARK(4);
       // ================= F3: features.10 (8 -> 16) on 8x8 + Dropout -> head operand (K order) + arg-max
       float4 w4r[4];
       const int rot4 = (tid >> 1) & 3;
@@ -273,6 +292,7 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
         bI3[pp * 16 + co] = (uint8_t)idx;
       }
       __syncthreads();
+      HS_MARK(5);
       // ================= F4: features.14 (4x4 valid conv = 256 -> 32) + ReLU
       {
         const int nn = tid >> 4, part = tid & 15;
@@ -321,6 +341,7 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
       }
       __syncthreads();
       if (pass == 0) continue;                           // forward only: negpred
+      HS_MARK(6);
       // ================= B5: crit.1 backward
       {
         const int k = tid >> 4, part = tid & 15;
@@ -346,6 +367,7 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
         }
       }
       __syncthreads();
+      HS_MARK(7);
       // ================= B3: features.10 input gradient (16 -> 8 on 8x8), Dropout + pool + ReLU backward -> d(features.6 output)
       if (warp < 4) {
         const int mt = warp;
@@ -366,6 +388,7 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
         }
       }
       __syncthreads();
+      HS_MARK(8);
       // ================= B2: features.6 input gradient (16x16), pool + ReLU backward -> d(features.3 output)
       if (warp < 8) {
         const int r0 = warp * 2;
@@ -393,6 +416,7 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
             });
       }
       __syncthreads();
+      HS_MARK(9);
       // ================= B1: features.3 input gradient (32x32), pool + ReLU backward -> d(features.0 output) (64x64x8, region X)
       {
         const int x0 = (warp & 1) * 16, r0 = (warp >> 1) * 4;
@@ -420,6 +444,7 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
             });
       }
       __syncthreads();
+      HS_MARK(10);
       // ================= B0: features.0 input gradient (8 -> 3 on 64x64), contracted with (B - A) / (A - B) on the way out:
       // d loss / d Z = sum_c dX[c] * (put - keep)[c]  (main.py:395, 406); the regulariser's gradient rides on pass 1
       {
@@ -451,10 +476,10 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
                   else if (t == 1) s = (r ? bot[2 * h] : top[2 * h]) * (float)((int)pb[2] - (int)pa[2]);
                   s += __shfl_xor_sync(0xffffffffu, s, 1);
                   if (t == 0) {
-                    float* dzp = p.dz + (size_t)n * 4096 + y * 64 + x;
+                    float* dzp = fDZ + y * 64 + x;
                     s *= pass == 2 ? -(1.f / 255.f) : (1.f / 255.f);
                     if (pass == 1) {                     // first scoring pass writes, with the regulariser (main.py:415-429)
-                      const float u = vf * __ldg(zf + y * 64 + x);
+                      const float u = vf * fZ[y * 64 + x];
                       reg1 += fabsf(u); reg2 = fmaf(u, u, reg2);
                       const float sg = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
                       *dzp = s + p.reg_scale * vf * (p.l1 * sg + 2.f * p.l2 * u);
@@ -466,7 +491,15 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
             });
       }
       __syncthreads();
+      HS_MARK(11);
     }
+    // the frame's d loss / d mask: one coalesced pass
+    {
+      float4* d = reinterpret_cast<float4*>(p.dz + (size_t)n * 4096);
+      const float4* sdz = reinterpret_cast<const float4*>(fDZ);
+      for (int e = tid; e < 1024; e += NT) d[e] = sdz[e];
+    }
+    ++fr;
   }
   cp_async_wait_all();
   // ---- loss terms: one atomic per warp / CTA into the four scalars the host zeroed
@@ -490,6 +523,8 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
 }  // namespace cgs
 
 using namespace cgs;
+
+namespace cgs { namespace hs { int set_trace(long long* b) { return cudaMemcpyToSymbol(g_hgs_trace, &b, sizeof(b)) == cudaSuccess ? 0 : -2; } } }
 
 extern "C" int cgs_hg_score_bf16(const uint8_t* frames_a, const uint8_t* frames_b, int32_t B, int32_t roll, const int32_t* roll_dev,
                                  const float* z, const float* target_replace, const float* target_inject, const float* const* masks9,

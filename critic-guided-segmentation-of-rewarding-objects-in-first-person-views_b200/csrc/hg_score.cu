@@ -37,6 +37,7 @@ constexpr int sHW = sBias + 256;                    // wl1[1024] bl1[32] wl2[32]
 constexpr int hWl1 = 0, hBl1 = 1024, hWl2 = 1056, hBl2 = 1088, hB4 = 1092, szHW = 1124;
 constexpr int S_SMEM = sHW + szHW * 4;
 static_assert(S_SMEM <= 227 * 1024, "score kernel: shared memory budget");
+static_assert(sI0 - sE0 >= 3 * 4096 * 4, "the three d(blend) planes fit between e0 and the arg-max bytes");
 static_assert(sE0 % 16 == 0 && sDY3 % 16 == 0 && sA8 % 16 == 0 && sX3 % 16 == 0 && sM2 % 16 == 0 && sW % 16 == 0, "alignment");
 
 struct ScoreParams {
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
   const uint8_t *bA8 = smraw + sA8, *bB8 = smraw + sB8;
   const float* fZ = reinterpret_cast<const float*>(smraw + sZ);
   float* fDZ = reinterpret_cast<float*>(smraw + sDZ);
+  float* fDX = reinterpret_cast<float*>(smraw + sE0);           // d(blend), three fp32 planes, during the last phase of a pass
   long long* trace = blockIdx.x == 0 ? g_hgs_trace : nullptr;
   int fr = 0;
   __nv_bfloat16* hE0 = reinterpret_cast<__nv_bfloat16*>(smraw + sE0);
@@ -146,6 +148,13 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
       cp_async_wait_all();
       __syncthreads();
       HS_MARK(0);
+      {
+        // e0 / e1 / e2: the previous pass parked d(blend) over them, halos included: clear them (interiors are rewritten below)
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        for (int e = tid; e < PB1 / 16; e += NT) reinterpret_cast<uint4*>(smraw + sE0)[e] = z4;
+        for (int e = tid; e < PB2 / 16; e += NT) reinterpret_cast<uint4*>(smraw + sE1)[e] = z4;
+        for (int e = tid; e < PB3 / 16; e += NT) reinterpret_cast<uint4*>(smraw + sE2)[e] = z4;
+      }
       for (int e = tid; e < 4096; e += NT) {
         const int y = e >> 6, x = e & 63;
         const uint8_t* a = bA8 + (y * 64 + ((x + roll) & 63)) * 3;    // shift_batch rolls A only (main.py:355-357)
@@ -454,7 +463,6 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
         for (int s = 0; s < 6; ++s) w[s >> 1][s & 1][0] = sWf[(W_BWD + B_C0D - B_C3D + s) * 32 + lane];
         const uint32_t aA = smb + sX + (uint32_t)((r0 * PX + x0 + pixoff + chunk) * 16);
         const uint32_t aB = smb + sX + (uint32_t)((r0 * PX + x0 + pixoff + 2) * 16);
-        const float vf = p.vpred ? 1.f - __ldg(p.vpred + n) : 1.f;
         slide_bf<16, 2, 1>(
             w,
             [&](int i, uint32_t(&a)[2][4]) {
@@ -463,32 +471,43 @@ __global__ void __launch_bounds__(NT, 1) hg_score_kernel(const ScoreParams p) {
               a[1][2] = a[1][3] = 0u;
             },
             [&](int e, int, const float(&top)[4], const float(&bot)[4]) {
+              // columns 0..2 of the 8-wide tile are the three input channels: lanes t = 0 (channels 0, 1) and t = 1 (channel 2)
+              // park them as three fp32 planes (e0 .. d(features.10 output) are dead by now)
+              if (t < 2) {
 #pragma unroll
-              for (int r = 0; r < 2; ++r)
+                for (int r = 0; r < 2; ++r)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  const int y = r0 + e + r, x = x0 + g + 8 * h;
-                  const uint8_t* pa = bA8 + (y * 64 + ((x + roll) & 63)) * 3;
-                  const uint8_t* pb = bB8 + (y * 64 + x) * 3;
-                  float s = 0.f;                        // lanes t = 0 (channels 0, 1) and t = 1 (channel 2) of a pixel are neighbours
-                  if (t == 0) s = (r ? bot[2 * h] : top[2 * h]) * (float)((int)pb[0] - (int)pa[0]) +
-                                  (r ? bot[2 * h + 1] : top[2 * h + 1]) * (float)((int)pb[1] - (int)pa[1]);
-                  else if (t == 1) s = (r ? bot[2 * h] : top[2 * h]) * (float)((int)pb[2] - (int)pa[2]);
-                  s += __shfl_xor_sync(0xffffffffu, s, 1);
-                  if (t == 0) {
-                    float* dzp = fDZ + y * 64 + x;
-                    s *= pass == 2 ? -(1.f / 255.f) : (1.f / 255.f);
-                    if (pass == 1) {                     // first scoring pass writes, with the regulariser (main.py:415-429)
-                      const float u = vf * fZ[y * 64 + x];
-                      reg1 += fabsf(u); reg2 = fmaf(u, u, reg2);
-                      const float sg = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
-                      *dzp = s + p.reg_scale * vf * (p.l1 * sg + 2.f * p.l2 * u);
-                    } else {
-                      *dzp += s;                         // the same thread wrote it in pass 1
-                    }
+                  for (int h = 0; h < 2; ++h) {
+                    const int pix = (r0 + e + r) * 64 + x0 + g + 8 * h;
+                    fDX[(2 * t) * 4096 + pix] = r ? bot[2 * h] : top[2 * h];
+                    if (t == 0) fDX[4096 + pix] = r ? bot[2 * h + 1] : top[2 * h + 1];
                   }
-                }
+              }
             });
+      }
+      __syncthreads();
+      // d loss / d Z = sum_c dX[c] * (put - keep)[c] (main.py:395, 406), every thread a pixel; the regulariser's gradient
+      // (main.py:415-429) rides on the first scoring pass
+      {
+        const float vf = p.vpred ? 1.f - __ldg(p.vpred + n) : 1.f;
+        const float sgn = pass == 2 ? -(1.f / 255.f) : (1.f / 255.f);
+        for (int e = tid; e < 4096; e += NT) {
+          const int y = e >> 6, x = e & 63;
+          const uint8_t* pa = bA8 + (y * 64 + ((x + roll) & 63)) * 3;
+          const uint8_t* pb = bB8 + e * 3;
+          float s = fDX[e] * (float)((int)pb[0] - (int)pa[0]);
+          s = fmaf(fDX[4096 + e], (float)((int)pb[1] - (int)pa[1]), s);
+          s = fmaf(fDX[8192 + e], (float)((int)pb[2] - (int)pa[2]), s);
+          s *= sgn;
+          if (pass == 1) {
+            const float u = vf * fZ[e];
+            reg1 += fabsf(u); reg2 = fmaf(u, u, reg2);
+            const float sg = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
+            fDZ[e] = s + p.reg_scale * vf * (p.l1 * sg + 2.f * p.l2 * u);
+          } else {
+            fDZ[e] += s;
+          }
+        }
       }
       __syncthreads();
       HS_MARK(11);

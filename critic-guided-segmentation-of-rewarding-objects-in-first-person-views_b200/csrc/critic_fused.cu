@@ -1048,6 +1048,10 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
     }
     CF_MARK(18);
     const int t = p.step_state[0] + 1;
+    // exchange epoch: the tag / slot selector of the peer-memory all-reduce.  It only ever grows, unlike the Adam step count,
+    // which CUDA-graph capture rewinds after its warm-up steps (graph_step._capture): a rewound tag would match the stale
+    // packets of the warm-up
+    const unsigned ep = (unsigned)p.step_state[2] + 1u;
     float* red = sm + oA;                           // [4][128] + the two bias-correction scalars + the barrier verdict
     if (tid == 0) {                                 // double-precision pow once per CTA
       const double bc1 = 1.0 - pow(p.beta1, (double)t), bc2 = 1.0 - pow(p.beta2, (double)t);
@@ -1088,8 +1092,8 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
         gv += (red[ex] + red[128 + ex]) + (red[256 + ex] + red[384 + ex]);
         bool upd = true;
         if (xchg) {
-          const size_t slot = (size_t)(t & 1) * p.world * p.npad;
-          const unsigned long long pkt = ((unsigned long long)(unsigned)t << 32) | __float_as_uint(gv);
+          const size_t slot = (size_t)(ep & 1u) * p.world * p.npad;
+          const unsigned long long pkt = ((unsigned long long)ep << 32) | __float_as_uint(gv);
           for (int r = 0; r < p.world; ++r)             // push {value, step} into every rank's buffer (mine included)
             asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(p.ll_peer[r] + slot + (size_t)p.rank * p.npad + i), "l"(pkt)
                          : "memory");
@@ -1101,8 +1105,8 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
             int spin = 0;
             do {
               asm volatile("ld.relaxed.sys.global.u64 %0, [%1];\n" : "=l"(got) : "l"(mine + (size_t)r * p.npad) : "memory");
-            } while ((unsigned)(got >> 32) != (unsigned)t && ++spin < (1 << 24));
-            ok = ok && (unsigned)(got >> 32) == (unsigned)t;
+            } while ((unsigned)(got >> 32) != ep && ++spin < (1 << 24));
+            ok = ok && (unsigned)(got >> 32) == ep;
             gv += __uint_as_float((unsigned)got);
           }
           if (!ok) atomicExch(p.bar + 2, 1u);           // a peer never delivered: flagged, never hangs
@@ -1125,6 +1129,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const Params p) {
       if (atomicAdd(&p.step_state[1], 1) == (int)gridDim.x - 1) {
         p.step_state[1] = 0;
         p.step_state[0] = t;
+        p.step_state[2] = (int)ep;
       }
     }
   }

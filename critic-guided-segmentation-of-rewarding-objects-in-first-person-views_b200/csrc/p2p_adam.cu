@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(256) p2p_stage_kernel(float* __restrict__ g, i
     float gv = g[i];
 #pragma unroll
     for (int r = 0; r < 8; ++r) gv += red[r][ex];
-    const int t = step_state[0] + 1;
-    sym[(int64_t)(t & 1) * npad + i] = gv;
+    const int ep = step_state[2] + 1;             // exchange epoch (monotonic; see p2p_allreduce_adam_kernel)
+    sym[(int64_t)(ep & 1) * npad + i] = gv;
     g[i] = 0.f;
   }
 }
@@ -58,13 +58,16 @@ __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(float* __restri
                                                                  double lr, double beta1, double beta2, double eps_d,
                                                                  int* __restrict__ step_state, float gscale, int* __restrict__ err) {
   const int t = step_state[0] + 1;
+  // the flags and the slot parity follow the exchange epoch, which only ever grows; the Adam step count t may be rewound
+  // (CUDA-graph capture restores it after its warm-up steps) and must not be what peers wait for
+  const int ep = step_state[2] + 1;
   __shared__ int s_failed;
   if (threadIdx.x == 0) s_failed = 0;
   __syncthreads();
   // 1. announce (block 0 only; the staging kernel before us on this stream has completed, its stores are in our L2)
   if (blockIdx.x == 0 && threadIdx.x < world) {
     __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(pp.flag[threadIdx.x] + rank), "r"((unsigned)t) : "memory");
+    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(pp.flag[threadIdx.x] + rank), "r"((unsigned)ep) : "memory");
   }
   // 2. wait for every peer's announcement of step t (bounded: a diverged peer must not hang the GPU)
   if (threadIdx.x < world) {
@@ -72,10 +75,10 @@ __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(float* __restri
     unsigned seen = 0;
     for (long long spin = 0; spin < (1ll << 26); ++spin) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(f) : "memory");
-      if ((int)seen >= t) break;
+      if ((int)seen >= ep) break;
       __nanosleep(64);
     }
-    if ((int)seen < t) { atomicExch(err, 1); s_failed = 1; }
+    if ((int)seen < ep) { atomicExch(err, 1); s_failed = 1; }
   }
   __shared__ float s_bc[2];
   if (threadIdx.x == 32) {                         // one double-precision pow pair per block, while the others poll
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(float* __restri
   const float step_size = s_bc[0];
   const float bc2_sqrt = s_bc[1];
   const float omb1 = (float)(1.0 - beta1), b2 = (float)beta2, omb2 = (float)(1.0 - beta2), eps = (float)eps_d;
-  const int64_t slot = (int64_t)(t & 1) * npad;
+  const int64_t slot = (int64_t)(ep & 1) * npad;
   // a peer that never announced leaves an incomplete sum: keep parameters and moments as they are (flag is set)
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n && !s_failed; i += (int64_t)gridDim.x * blockDim.x) {
     float gv = 0.f;
@@ -111,6 +114,7 @@ __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(float* __restri
     if (atomicAdd(&step_state[1], 1) == (int)gridDim.x - 1) {
       step_state[1] = 0;
       step_state[0] = t;
+      step_state[2] = ep;
     }
   }
 }

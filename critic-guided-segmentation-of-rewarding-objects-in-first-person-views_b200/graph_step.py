@@ -17,7 +17,7 @@ from .train_handler import FlatAdam
 def _train_state(opti, *critics):
     """Every device tensor a training step mutates besides its inputs: parameters, gradient bucket, Adam moments and step
     counter, the dropout Philox call counters of the critics."""
-    st = [opti.flat, opti.gflat, opti.m, opti.v, opti.step_count]
+    st = [opti.flat, opti.gflat, opti.m, opti.v, opti.step_count[:2]]     # NOT the exchange epoch [2]: peers' flags only grow
     for c in critics:
         if c is not None:
             c._dropout_rng(opti.flat.device)          # creates the counter if this module has not drawn yet

@@ -82,7 +82,9 @@ class FlatAdam:
         self.gflat = torch.zeros(n, device=dev, dtype=torch.float32)
         self.m = torch.zeros(n, device=dev, dtype=torch.float32)
         self.v = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.step_count = torch.zeros(2, device=dev, dtype=torch.int32)     # (steps applied, ticket), advanced by the kernel
+        # (Adam steps applied, ticket, exchange epoch, -), advanced by the kernels.  The exchange epoch tags the peer-memory
+        # all-reduce packets / flags and only ever grows; the step count may be rewound (graph_step._capture)
+        self.step_count = torch.zeros(4, device=dev, dtype=torch.int32)
         self._clean = True                                                    # gflat known to be all-zero
         off = 0
         with torch.no_grad():

@@ -243,7 +243,9 @@ int cgs_masker_fused(const uint8_t* frames, const float* o0, int32_t B, const fl
 /* Data-parallel gradient exchange fused with Adam over NVLink peer memory (csrc/p2p_adam.cu).  Every rank owns a SYMMETRIC
  * gradient buffer sym[2][npad] and a flag pad (>= 16 uint32, zeroed once), both mapped into all peers.
  * cgs_p2p_stage: sym_local[slot][i] = g[i] + sum_k partials[k*stride + i - offset] (n_partials may be 0), g cleared;
- *   slot = (step_state[0] + 1) & 1 is read on the device, so the call is CUDA-graph replayable.
+ *   slot = (step_state[2] + 1) & 1 is read on the device, so the call is CUDA-graph replayable.  step_state here (and in
+ *   cgs_adam_args of the whole-step kernel) is 4 x int32 {Adam steps applied, ticket, exchange epoch, -}: the exchange epoch
+ *   selects the slot and tags the announcements; it only ever grows, whereas a caller may rewind the Adam step count.
  * cgs_p2p_allreduce_adam: announce step t to all peers, wait for theirs (bounded spin; *err_flag = 1 on time-out), sum the
  *   `world` buffers in rank order through peer loads, apply Adam (torch defaults, as cgs_adam_step) to p/m/v.
  *   peer_bufs / peer_flags: HOST arrays of `world` device addresses (this process's mappings of each rank's allocation).

@@ -3,7 +3,7 @@
 tag=$1; to=$2; shift 2
 mkdir -p gpurun_out
 for i in $(seq 1 40); do
-  /usr/local/graft/bin/gpurun --timeout "$to" -- "$@" > gpurun_out/call_$tag.txt 2>&1
+  /usr/local/graft/bin/gpurun ${GPUS:+--gpus $GPUS} --timeout "$to" -- "$@" > gpurun_out/call_$tag.txt 2>&1
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
   sleep 60

@@ -36,7 +36,9 @@ static_assert(TAPE == 55296 && TAPE % 16 == 0, "tape layout");
 constexpr int F_C0 = 0, F_C1 = 3, F_C2 = 9, F_C3 = 15, F_D2 = 25, F_D1 = 43, F_D0 = 52, F_M0 = 61, F_M2 = 79, F_D3 = 88;
 constexpr int B_M0D = 142, B_D0D = 151, B_D1D = 157, B_M2D = 163, B_D2D = 165, B_D3D = 175;
 // critic input-gradient steps (hg_score.cu): features.10 / .6 / .3 / .0 with the rotated, in/out-swapped filters
-constexpr int B_C3D = 211, B_C2D = 220, B_C1D = 226, B_C0D = 232, NSTEPS = 238;
+constexpr int B_C3D = 211, B_C2D = 220, B_C1D = 226, B_C0D = 232;
+// masker.2 as per-tap partial products (hg_forward.cu): K = 16 input channels, N = taps 0..7 | tap 8
+constexpr int F_PT = 238, NSTEPS = 240;
 constexpr int F_SMEM_STEPS = F_D3;                 // the forward kernel keeps steps [0, 88) in shared memory
 
 // masker parameters in state_dict order (= flat gradient layout of the partial vectors)
@@ -165,13 +167,13 @@ __device__ __forceinline__ void draw_masks3(unsigned long long seed, unsigned lo
 // pair-duplicated frame plane whose row 0 is haloed frame row xrow0 (xrows rows); o0 sits at tO0; w0: the 18 fragment
 // steps (ky*3 + j)*2 + nt of masker.0; bm0: its bias.  Shared by the forward kernel and the backward kernel's recompute.
 template <int R>
-__device__ __forceinline__ void m0_rows(uint8_t* band_base, uint32_t smb, uint32_t xplane, int xrow0, int xrows, const uint2* w0,
-                                        const float* bm0, int band, int rb0, int x0, int lane) {
+__device__ __forceinline__ void m0_rows(uint8_t* band_base, int plane_stride, uint32_t smb, uint32_t xplane, int xrow0, int xrows,
+                                        const uint2* w0, const float* bm0, int ya0, int rb0, int x0, int lane) {
   const int lj = lane >> 3, lr = lane & 7, g = lane >> 2, t = lane & 3, pixoff = lr + 8 * (lj & 1), chunk = lj >> 1;
   uint2 w[3][3][2];
 #pragma unroll
   for (int s = 0; s < 18; ++s) w[s / 6][(s >> 1) % 3][s & 1] = w0[s * 32 + lane];
-  const int hv0 = 16 * band - 1 + rb0;               // haloed frame row of input row i = hv0 + i  (in [-1, 66])
+  const int hv0 = ya0 + rb0;                         // ya0 = mask row of band row 0; haloed frame row of input row i = hv0 + i
   const uint32_t aX = smb + xplane + (uint32_t)((x0 + pixoff + 2 * chunk) * 16);
   const int cA = (x0 + pixoff + chunk + 1) >> 1, cB = (x0 + pixoff + 3) >> 1;
   float bias[2][2];
@@ -191,14 +193,14 @@ __device__ __forceinline__ void m0_rows(uint8_t* band_base, uint32_t smb, uint32
       [&](int e, int nt, const float(&top)[4], const float(&bot)[4]) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          const int rb = rb0 + e + r, ya = 16 * band - 1 + rb;
+          const int rb = rb0 + e + r, ya = ya0 + rb;
           const bool inside = ya >= 0 && ya < 64;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             float v0 = (r ? bot[2 * h] : top[2 * h]) + bias[nt][0], v1 = (r ? bot[2 * h + 1] : top[2 * h + 1]) + bias[nt][1];
             v0 = v0 > 0.f ? v0 : v0 * kLeakySlope;
             v1 = v1 > 0.f ? v1 : v1 * kLeakySlope;
-            *reinterpret_cast<uint32_t*>(band_base + nt * PLB + (rb * PX + x0 + g + 8 * h + 1) * 16 + 4 * t) = inside ? pack_bf16(v0, v1) : 0u;
+            *reinterpret_cast<uint32_t*>(band_base + nt * plane_stride + (rb * PX + x0 + g + 8 * h + 1) * 16 + 4 * t) = inside ? pack_bf16(v0, v1) : 0u;
           }
         }
       });
@@ -208,8 +210,17 @@ __device__ __forceinline__ void m0_rows(uint8_t* band_base, uint32_t smb, uint32
 __device__ __forceinline__ void m0_band(uint8_t* band_base, uint32_t smb, uint32_t xplane, int xrow0, int xrows, const uint2* w0,
                                         const float* bm0, int band, int warp, int lane) {
   const int x0 = (warp & 3) * 16, seg = warp >> 2;
-  if (seg == 0) m0_rows<6>(band_base, smb, xplane, xrow0, xrows, w0, bm0, band, 0, x0, lane);
-  else m0_rows<4>(band_base, smb, xplane, xrow0, xrows, w0, bm0, band, 2 + 4 * seg, x0, lane);
+  if (seg == 0) m0_rows<6>(band_base, PLB, smb, xplane, xrow0, xrows, w0, bm0, 16 * band - 1, 0, x0, lane);
+  else m0_rows<4>(band_base, PLB, smb, xplane, xrow0, xrows, w0, bm0, 16 * band - 1, 2 + 4 * seg, x0, lane);
+}
+
+// a 10-row band (8 mask rows + one row of overlap each side; band row r = mask row 8*band - 1 + r): 4 strips x (4 + 2 + 2 + 2) rows
+constexpr int PLB8 = 10 * PX * 16;
+__device__ __forceinline__ void m0_band8(uint8_t* band_base, uint32_t smb, uint32_t xplane, int xrow0, int xrows, const uint2* w0,
+                                         const float* bm0, int band, int warp, int lane) {
+  const int x0 = (warp & 3) * 16, seg = warp >> 2;
+  if (seg == 0) m0_rows<4>(band_base, PLB8, smb, xplane, xrow0, xrows, w0, bm0, 8 * band - 1, 0, x0, lane);
+  else m0_rows<2>(band_base, PLB8, smb, xplane, xrow0, xrows, w0, bm0, 8 * band - 1, 2 + 2 * seg, x0, lane);
 }
 
 // debug: clock64() at phase boundaries of CTA 0's first two frames (tools/hg_trace.py); NULL = off

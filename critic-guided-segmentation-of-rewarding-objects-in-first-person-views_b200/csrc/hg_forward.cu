@@ -17,19 +17,22 @@ namespace hg {
 
 // ---- shared memory map of the forward kernel (byte offsets)
 constexpr int fX = TAPE;                            // pair-duplicated frame
-constexpr int fBand = fX + PBX;                     // masker.0 band: 2 planes; before the bands: split-K scratch
-constexpr int fE2D = fBand + 2 * PLB;               // e2 * dropout mask (operand of features.10)
+constexpr int fBand = fX + PBX;                     // masker.0 band: 2 planes x 10 rows; before the bands: split-K scratch
+constexpr int PXP = 68;                             // pitch of the partial-product rows: column x + 1, columns 0 and 65.. zero
+constexpr int fP = fBand + 2 * PLB8;                // masker.2 partial products, fp32 [10 rows][9 taps][PXP]
+constexpr int fE2D = fP + 10 * 9 * PXP * 4;         // e2 * dropout mask (operand of features.10)
 constexpr int fU8 = fE2D + PB3;                     // raw frame bytes (prefetched)
 constexpr int fX3 = fU8 + 12288;                    // e3 * mask in the 4x4 conv's K order, fp32 [256]
 constexpr int fV = fX3 + 1024;                      // v[32] fp32
 constexpr int fM2 = fV + 128, fM3 = fM2 + 2048, fMV = fM3 + 1024;   // dropout masks fp32 [512] [256] [32]
-constexpr int fW = fMV + 128;                       // weight fragments, steps [0, F_SMEM_STEPS)
-constexpr int fBias = fW + F_SMEM_STEPS * 256;      // fp32: b0[8] b1[8] b2[8] b3[16] bd3[16] bd2[8] bd1[8] bd0[8] bm0[16] bm2[1]
+constexpr int fW = fMV + 128;                       // weight fragments, steps [0, F_SMEM_STEPS) | [F_PT, F_PT + 2)
+constexpr int fBias = fW + (F_SMEM_STEPS + 2) * 256;      // fp32: b0[8] b1[8] b2[8] b3[16] bd3[16] bd2[8] bd1[8] bd0[8] bm0[16] bm2[1]
 constexpr int bB0 = 0, bB1 = 8, bB2 = 16, bB3 = 24, bD3 = 40, bD2 = 56, bD1 = 64, bD0 = 72, bM0 = 80, bM2 = 96;
 constexpr int fHW = fBias + 512;                    // fp32: wl1[1024] bl1[32] wl2[32] bl2[4] b4[32] wd4[1024] bd4[32]
 constexpr int hWl1 = 0, hBl1 = 1024, hWl2 = 1056, hBl2 = 1088, hB4 = 1092, hWd4 = 1124, hBd4 = 2148, szHW = 2180;
 constexpr int F_SMEM = fHW + szHW * 4;
 static_assert(F_SMEM <= 227 * 1024, "forward kernel: shared memory budget");
+static_assert(2 * PLB8 >= 4096 * 4, "the split-K scratch aliases the band");
 static_assert(fX % 16 == 0 && fBand % 16 == 0 && fE2D % 16 == 0 && fU8 % 16 == 0 && fW % 16 == 0, "16-byte alignment");
 
 struct FwdParams {
@@ -116,13 +119,17 @@ __device__ float pack_wk(const PackSrc& p, int s, int k, int n) {
     return p.d3[(k * 48 + 16 + nt * 8 + n) * 9 + 8 - tp];
   }
   if (s < B_C2D) return p.w3[(k * 8 + n) * 9 + 8 - (s - B_C3D)];          // features.10 -> its input: k = co (16), n = ci (8)
-  {                                                 // features.6 / .3 / .0 -> their inputs: step ky'*2 + h; k = (tap' pair) x co (8)
+  if (s < F_PT) {                                   // features.6 / .3 / .0 -> their inputs: step ky'*2 + h; k = (tap' pair) x co (8)
     const float* w = s < B_C1D ? p.w2 : (s < B_C0D ? p.w1 : p.w0);
     const int q = s - (s < B_C1D ? B_C2D : (s < B_C0D ? B_C1D : B_C0D)), ky = q >> 1, h = q & 1;
     if (h && k >= 8) return 0.f;
     const int kx = h ? 2 : (k >> 3), co = k & 7, tap = 8 - (ky * 3 + kx);
     if (s < B_C0D) return w[(co * 8 + n) * 9 + tap];
     return n < 3 ? w[(co * 3 + n) * 9 + tap] : 0.f;  // features.0: 3 input channels
+  }
+  {                                                 // masker.2, one column per filter tap: step nt; k = ci (16); n: tap = nt*8 + n
+    const int tap = (s - F_PT) * 8 + n;
+    return tap < 9 ? p.m2[k * 9 + tap] : 0.f;
   }
 }
 
@@ -175,6 +182,7 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
     for (int e = tid; e < fU8 / 16; e += NT) reinterpret_cast<uint4*>(smraw)[e] = z4;
     const uint4* src = reinterpret_cast<const uint4*>(p.pack);
     for (int e = tid; e < F_SMEM_STEPS * 16; e += NT) reinterpret_cast<uint4*>(smraw + fW)[e] = __ldg(src + e);
+    if (tid < 32) reinterpret_cast<uint4*>(smraw + fW + F_SMEM_STEPS * 256)[tid] = __ldg(src + F_PT * 16 + tid);
   }
   if (tid < 8) {
     sBias[bB0 + tid] = __ldg(p.b0 + tid); sBias[bB1 + tid] = __ldg(p.b1 + tid); sBias[bB2 + tid] = __ldg(p.b2 + tid);
@@ -466,47 +474,49 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
       for (int e = tid; e < TAPE / 16; e += NT) dst[e] = src[e];
     }
     HG_MARK(11);
-    // ================= masker.0 + LeakyReLU -> 18-row band -> masker.2 + Sigmoid (+ threshold), 4 bands of 16 mask rows
+    // ================= masker.0 + LeakyReLU -> 10-row band -> masker.2 + Sigmoid (+ threshold), 8 bands of 8 mask rows.
+    // masker.2 has ONE output channel: as an implicit GEMM it would fill 1 of 8 MMA columns.  Instead the MMA computes the
+    // nine per-tap partial products P[pixel][tap] = sum_ci m0[pixel][ci] * W2[ci][tap] of every band pixel (K = 16 channels,
+    // N = 9 taps: two MMAs per 16 pixels), and the 3x3 stencil sum z = sum_tap P[y + ky][x + kx][tap] runs with every thread
+    // a pixel: 9 conflict-free shared loads, sigmoid, fully coalesced stores.
     // (the split-K scratch aliases the band: its columns 0 and 65 must be zero again)
-    for (int e = tid; e < 2 * 18 * 2; e += NT) {
-      const int pl = e / 36, r = (e % 36) >> 1, c = (e & 1) ? 65 : 0;
-      *reinterpret_cast<uint4*>(smraw + fBand + pl * PLB + (r * PX + c) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    for (int e = tid; e < 2 * 10 * 2; e += NT) {
+      const int pl = e / 20, r = (e % 20) >> 1, c = (e & 1) ? 65 : 0;
+      *reinterpret_cast<uint4*>(smraw + fBand + pl * PLB8 + (r * PX + c) * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
-    for (int band = 0; band < 4; ++band) {
-      HG_MARK(12 + 2 * band);
-      m0_band(smraw + fBand, smb, fX, 0, 66, sWf + F_M0 * 32, sBias + bM0, band, warp, lane);
+    float* sP = reinterpret_cast<float*>(smraw + fP);
+    for (int band = 0; band < 8; ++band) {
+      if (band < 2) HG_MARK(12 + 3 * band);             // 12: band 0 starts, 15: band 1 starts
+      m0_band8(smraw + fBand, smb, fX, 0, 66, sWf + F_M0 * 32, sBias + bM0, band, warp, lane);
       __syncthreads();
-      HG_MARK(13 + 2 * band);
-      {
-        const int x0 = (warp & 3) * 16, r0 = (warp >> 2) * 4;
-        uint2 w[3][3][1];
-#pragma unroll
-        for (int s = 0; s < 9; ++s) w[s / 3][s % 3][0] = sWf[(F_M2 + s) * 32 + lane];
-        const uint32_t aA = smb + fBand + (uint32_t)(chunk * PLB + (r0 * PX + x0 + pixoff) * 16);
-        const float b2 = sBias[bM2];
-        float* dM = p.z + (size_t)n * 4096 + (16 * band + r0) * 64 + x0 + g;
-        uint8_t* dH = p.hard ? p.hard + (size_t)n * 4096 + (16 * band + r0) * 64 + x0 + g : nullptr;
-        slide_bf<4, 3, 1>(
-            w,
-            [&](int i, uint32_t(&a)[3][4]) {
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) ldsm4(a[kx], aA + (uint32_t)((i * PX + kx) * 16));
-            },
-            [&](int e, int, const float(&top)[4], const float(&bot)[4]) {
-              if (t == 0) {                             // column 0 of the 8-wide tile is the one real output channel
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-#pragma unroll
-                  for (int h = 0; h < 2; ++h) {
-                    const float zz = sigmoidf_((r ? bot[2 * h] : top[2 * h]) + b2);
-                    dM[(e + r) * 64 + 8 * h] = zz;
-                    if (dH) dH[(e + r) * 64 + 8 * h] = zz >= p.thresh;
-                  }
-              }
-            });
+      if (band == 0) HG_MARK(13);
+      for (int tile = warp; tile < 40; tile += 16) {
+        const int r = tile >> 2, s = tile & 3;
+        uint32_t a[4];
+        ldsm4(a, smb + fBand + (uint32_t)(chunk * PLB8 + (r * PX + 1 + 16 * s + pixoff) * 16));
+        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint2 w0 = sWf[(F_SMEM_STEPS + 0) * 32 + lane], w1 = sWf[(F_SMEM_STEPS + 1) * 32 + lane];
+        mma_bf16(c0, a, w0.x, w0.y);
+        mma_bf16(c1, a, w1.x, w1.y);
+        float* q = sP + (r * 9 + 2 * t) * PXP + 1 + 16 * s + g;
+        q[0] = c0[0]; q[PXP] = c0[1]; q[8] = c0[2]; q[PXP + 8] = c0[3];
+        if (t == 0) { float* q8 = sP + (r * 9 + 8) * PXP + 1 + 16 * s + g; q8[0] = c1[0]; q8[8] = c1[2]; }
       }
       __syncthreads();
+      if (band == 0) HG_MARK(14);
+      {
+        const int o = tid >> 6, x = tid & 63;
+        float acc = sBias[bM2];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) acc += sP[((o + ky) * 9 + ky * 3 + kx) * PXP + x + kx];
+        const float zz = sigmoidf_(acc);
+        const size_t off = (size_t)n * 4096 + (8 * band + o) * 64 + x;
+        p.z[off] = zz;
+        if (p.hard) p.hard[off] = zz >= p.thresh;
+      }
     }
     HG_MARK(20);
     ++fr;

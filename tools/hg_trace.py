@@ -29,11 +29,12 @@ for it in range(3):
 torch.cuda.synchronize()
 L.cgs_hg_set_trace(None, None, None)
 tf, tb = tf.cpu().numpy().reshape(2, 32), tb.cpu().numpy().reshape(2, 32)
-fn = ["stage", "conv0", "conv1", "conv2", "conv3", "head+dec4", "dec3", "dec2", "dec1", "dec0", "tape", "band prep"] + \
-     [f"band{b} {w}" for b in range(4) for w in ("m0", "m2")]
+fn = ["stage", "conv0", "conv1", "conv2", "conv3", "head+dec4", "dec3", "dec2", "dec1", "dec0", "tape", "band prep",
+      "band0 masker.0", "band0 P (MMA)", "band0 stencil"]
 print(f"forward, B={B}: clk per phase (frame 0 | frame 1)")
 for k, name in enumerate(fn):
-    print(f"  {name:12s} {tf[0, k + 1] - tf[0, k]:8d} {tf[1, k + 1] - tf[1, k]:8d}")
+    print(f"  {name:14s} {tf[0, k + 1] - tf[0, k]:8d} {tf[1, k + 1] - tf[1, k]:8d}")
+print(f"  {'bands 1-7':14s} {tf[0, 20] - tf[0, 15]:8d} {tf[1, 20] - tf[1, 15]:8d}")
 print(f"  {'frame':12s} {tf[0, 20] - tf[0, 0]:8d} {tf[1, 20] - tf[1, 0]:8d}   ({(tf[1, 20] - tf[1, 0]) / 1.965e3:.1f} us)")
 bn = ["tape load", "-"] + [f"band{b} {w}" for b in range(4) for w in ("B1 stage", "B2 m0", "B3 m2 wgrad", "B4 m2 dgrad", "B5 m0 w/dgrad")] + \
      ["D0 dec0", "D1 dec1", "D2 dec2", "D3 dec3", "D4 dec4"]

@@ -264,12 +264,13 @@ def kernel_flops(entry, B, chfak=1):
     per = {
         "cgs_critic_train_fused": cf + cb + cf,                        # fprop + dgrad + wgrad = 8,460,480 / 2
         "cgs_critic_loss_xgrad": cf + cf,                              # fprop + full input gradient (incl. features.0 dgrad)
+        "cgs_critic_forward_frames": cf,
         "cgs_infer_fused": cf + dec,
         "cgs_masker_fused": msk,
-        "cgs_hg_forward": cf + dec + msk,
+        "cgs_hg_forward": cf + dec + msk,                              # critic(A, collect) + decoder + masker
         "cgs_hg_score": 2 * (cf + cf),                                 # replaced + injected: fprop + input gradient each
+        "cgs_hg_score_bf16": cf + 2 * (cf + cf),                       # critic(B) + replaced + injected (fprop + input gradient each)
         "cgs_hg_backward": 2 * (dec + msk) - 884736 * 0,               # wgrad + dgrad of decoder and masker
-        "cgs_process_fused": cf + dec + msk,
     }
     m = per.get(entry)
     return None if m is None else 2 * m * B
@@ -541,12 +542,12 @@ def run_ours(args, rank, world):
         line = {"metric": METRIC if args.workload == "all" else names[0] + "_frames_per_s", "value": head["value"], "unit": UNIT,
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": ("bf16" if args.precision == "tf32" and names[0] == "hourglass" else "tf32") if args.precision == "tf32" else "f32",
+                "dtype": ("bf16" if names[0] in ("hourglass", "infer") else "tf32") if args.precision == "tf32" else "f32",
                 "data": "synthetic"}
         line.update({k: v for k, v in head.items() if k not in ("value", "unit", "ms_per_step")})
-        line["precision"] = ("whole-frame kernels: TF32 mma.sync convolutions in the critic passes and the Hourglass forward, bf16 "
-                             "mma.sync (fp32 accumulate) in the Hourglass backward; heads, losses, Adam fp32"
-                             if args.precision == "tf32" else "all fp32 (FFMA)")
+        line["precision"] = ("whole-frame kernels: bf16 mma.sync operands (fp32 accumulate) in every 3x3 convolution of the Hourglass "
+                             "step and of -process inference, TF32 mma.sync in the critic training step; 4x4 / 1x1 / Linear "
+                             "layers, losses, Adam fp32" if args.precision == "tf32" else "all fp32 (FFMA)")
         line["clocks"] = clocks
         if len(names) > 1:
             line["workloads"] = {k: v for k, v in recs.items() if k != names[0]}

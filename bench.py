@@ -322,7 +322,9 @@ def bench_workload(name, args, rank, world, dev, group, sampler_windows):
     sync = (lambda: (dist.barrier(), torch.cuda.synchronize())) if world > 1 else torch.cuda.synchronize
     frame_bytes = B * 12288 * (2 if name == "hourglass" else 1)
     nrot = max(2, -(-int(1.3 * L2_BYTES) // frame_bytes))                # distinct resident batches: > L2 in total
-    spg = 1 if name == "hourglass" else max(d for d in (8, 4, 2, 1) if K % d == 0)   # steps captured per graph launch
+    # steps captured per graph launch: a 52 us critic step is shorter than the host's launch-to-launch jitter, and on several
+    # GPUs every step waits for the slowest rank's launch; a launch of up to 20 steps keeps the host out of the step
+    spg = 1 if name == "hourglass" else max(d for d in (20, 16, 10, 8, 5, 4, 2, 1) if K % d == 0)
     nrot = -(-nrot // spg) * spg
     Yb = Y[1, :B].astype(np.float32)
     launches_per_step = 0

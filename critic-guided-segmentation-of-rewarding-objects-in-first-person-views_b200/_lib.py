@@ -75,6 +75,7 @@ EXPORTS = {
     "cgs_hg_grid": [C.c_int32],
     "cgs_hg_partial_stride": [],
     "cgs_hg_debug_floats": [],
+    "cgs_hg_status": [],
     "cgs_hg_set_trace": [C.c_void_p, C.c_void_p, C.c_void_p],
     "cgs_hg_pack": [C.POINTER(CriticWeights), C.POINTER(MaskerWeights), C.c_void_p, C.c_void_p],
     "cgs_hg_forward": [_u8p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(CriticWeights), C.POINTER(MaskerWeights), C.c_void_p,

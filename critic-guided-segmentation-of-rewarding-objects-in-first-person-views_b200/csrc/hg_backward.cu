@@ -104,7 +104,11 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
   long long* trace = blockIdx.x == 0 ? g_hgb_trace : nullptr;
   int fr = 0;
 
-  // ---- prologue: zero everything once (halos and accumulator tiles stay / start zero), weight fragments
+  // ---- prologue: zero everything once (halos and accumulator tiles stay / start zero), weight fragments, the load barrier
+  __shared__ __align__(8) unsigned long long s_bar;
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+  uint32_t phase = 0u;
+  if (tid == 0) mbar_init(bar, 1);
   {
     const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
     for (int e = tid; e < B_SMEM / 16; e += NT) reinterpret_cast<uint4*>(smraw)[e] = z4;
@@ -129,17 +133,17 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
   for (int i = 0; i < 8; ++i) accM2[i >> 2][i & 3] = 0.f;
 
   for (int n = blockIdx.x; n < p.B; n += gridDim.x) {
+    fence_proxy_async();                               // our generic-proxy accesses to the tape region precede the bulk writes
     __syncthreads();                                   // everybody is done with the previous frame's tape and bytes
     HG_MARK(0);
-    {
-      const uint8_t* srcT = p.tape + (size_t)n * TAPE;
-      for (int c = tid; c < TAPE / 16; c += NT) cp_async16(smb + c * 16, srcT + c * 16);
-      const uint8_t* srcF = p.frames + (size_t)n * 12288;
-      for (int c = tid; c < 768; c += NT) cp_async16(smb + kU8 + c * 16, srcF + c * 16);
-      cp_async_commit();
-      cp_async_wait_all();
+    // the frame's tape (54 KB) and raw bytes (12 KB) as two TMA bulk loads (cp.async.bulk) completing on one mbarrier
+    if (tid == 0) {
+      mbar_expect_tx(bar, TAPE + 12288);
+      bulk_g2s(smb, p.tape + (size_t)n * TAPE, TAPE, bar);
+      bulk_g2s(smb + kU8, p.frames + (size_t)n * 12288, 12288, bar);
     }
-    __syncthreads();
+    mbar_wait(bar, phase);
+    phase ^= 1u;
     HG_MARK(1);
     const float* zf = p.z + (size_t)n * 4096;
     const float* dzf = p.dz + (size_t)n * 4096;
@@ -595,6 +599,13 @@ extern "C" int cgs_hg_grid(int32_t B) {
   const int sms = device_sms(), per = (B + sms - 1) / sms;
   return (B + per - 1) / per;
 }
+// Non-zero if a bounded mbarrier wait of the Hourglass kernels ever timed out (reads a device flag; synchronises).
+extern "C" int cgs_hg_status(void) {
+  int v = 0;
+  if (cudaMemcpyFromSymbol(&v, hg::g_hg_timeout, sizeof(v)) != cudaSuccess) return -2;
+  return v;
+}
+
 extern "C" int cgs_hg_debug_floats(void) { return (hg::kW - hg::kDO0) / 4 + 32; }
 
 extern "C" int cgs_hg_backward(const uint8_t* frames, int32_t B, int32_t roll, const int32_t* roll_dev, const cgs_masker_weights* mw,

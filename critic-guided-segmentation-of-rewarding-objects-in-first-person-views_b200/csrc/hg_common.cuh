@@ -229,6 +229,41 @@ __device__ __forceinline__ void m0_band8(uint8_t* band_base, uint32_t smb, uint3
     if (trace && tid == 0 && fr < 2) trace[fr * 32 + (k)] = clock64(); \
   } while (0)
 
+// ---- TMA bulk copies (cp.async.bulk: one instruction moves a whole contiguous block between global and shared memory
+//      through the async proxy; SASS: UBLKCP) with mbarrier completion for loads and bulk-group completion for stores
+static __device__ int g_hg_timeout = 0;     // set when a bounded mbarrier wait gave up (cgs_hg_status)
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+// bounded wait (never hang the device): on time-out the flag is raised and the caller carries on with whatever has landed
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (int spin = 0; spin < (1 << 24); ++spin) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (ok) return;
+  }
+  atomicExch(&g_hg_timeout, 1);
+}
+
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
 }

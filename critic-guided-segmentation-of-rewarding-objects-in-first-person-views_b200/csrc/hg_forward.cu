@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
 
   for (int n = blockIdx.x; n < p.B; n += gridDim.x) {
     cp_async_wait_all();
+    if (p.tape && tid == 0) bulk_wait_read();          // the previous frame's tape has left shared memory
     __syncthreads();
     HG_MARK(0);
     // ================= frame bytes have landed -> pair-duplicated bf16 plane (rows 1..64); this frame's dropout masks
@@ -465,14 +466,13 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
                     pack_bf16((r ? bot[2 * h] : top[2 * h]) + bias0, (r ? bot[2 * h + 1] : top[2 * h + 1]) + bias1);
           });
     }
+    if (p.tape) fence_proxy_async();                   // this thread's plane stores become visible to the async proxy ...
     __syncthreads();
     HG_MARK(10);
-    // ================= training: the tape (every plane above, as it lies in shared memory) -> HBM, coalesced 16-byte stores
-    if (p.tape) {
-      uint4* dst = reinterpret_cast<uint4*>(p.tape + (size_t)n * TAPE);
-      const uint4* src = reinterpret_cast<const uint4*>(smraw);
-      for (int e = tid; e < TAPE / 16; e += NT) dst[e] = src[e];
-    }
+    // ================= training: the tape (every plane above, exactly as it lies in shared memory) -> HBM as ONE TMA bulk
+    // store (54 KB, cp.async.bulk); it drains while the masker bands run and is waited for before the next frame's first
+    // write into these planes
+    if (p.tape && tid == 0) bulk_s2g(p.tape + (size_t)n * TAPE, smb, TAPE);
     HG_MARK(11);
     // ================= masker.0 + LeakyReLU -> 10-row band -> masker.2 + Sigmoid (+ threshold), 8 bands of 8 mask rows.
     // masker.2 has ONE output channel: as an implicit GEMM it would fill 1 of 8 MMA columns.  Instead the MMA computes the
@@ -522,6 +522,7 @@ __global__ void __launch_bounds__(NT, 1) hg_forward_kernel(const FwdParams p) {
     ++fr;
   }
   cp_async_wait_all();
+  if (p.tape && tid == 0) bulk_wait_read();
   if (p.rng_state && tid == 0) {                     // last CTA to finish advances the call counter (every CTA has read it)
     __threadfence();
     if (atomicAdd(&p.rng_state[1], 1ull) == gridDim.x - 1) {

@@ -345,6 +345,8 @@ int cgs_hg_forward(const uint8_t* frames, int32_t B, int32_t roll, const int32_t
 int cgs_hg_grid(int32_t B);
 int cgs_hg_partial_stride(void);
 int cgs_hg_debug_floats(void);
+/* Non-zero if a bounded mbarrier wait (TMA bulk load) of cgs_hg_backward ever timed out; synchronises. */
+int cgs_hg_status(void);
 /* Debug only: clock64() phase traces of CTA 0 of cgs_hg_forward / cgs_hg_backward / cgs_hg_score_bf16 into 64 int64 each
  * (NULL disables). */
 int cgs_hg_set_trace(long long* fwd_buf, long long* bwd_buf, long long* score_buf);

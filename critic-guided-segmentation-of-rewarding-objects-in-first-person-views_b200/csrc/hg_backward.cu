@@ -35,6 +35,7 @@ static_assert(B_SMEM <= 227 * 1024, "backward kernel: shared memory budget");
 static_assert(kU8 % 16 == 0 && kXB % 16 == 0 && kM0 % 16 == 0 && kDL % 16 == 0 && kDO0 % 16 == 0 && kW % 16 == 0 && kAcc % 16 == 0,
               "16-byte alignment");
 static_assert(NGRAD_M * 4 <= TAPE, "the partial vector is assembled in the tape region");
+static_assert(kDL - kXB >= TAPE, "the next frame's tape is prefetched into the frame-row + band region");
 
 struct BwdParams {
   const uint8_t* frames;
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
   __shared__ __align__(8) unsigned long long s_bar;
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
   uint32_t phase = 0u;
+  bool prefetched = false;
   if (tid == 0) mbar_init(bar, 1);
   {
     const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
@@ -136,14 +138,23 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
     fence_proxy_async();                               // our generic-proxy accesses to the tape region precede the bulk writes
     __syncthreads();                                   // everybody is done with the previous frame's tape and bytes
     HG_MARK(0);
-    // the frame's tape (54 KB) and raw bytes (12 KB) as two TMA bulk loads (cp.async.bulk) completing on one mbarrier
-    if (tid == 0) {
+    // the frame's tape (54 KB) and raw bytes (12 KB) as two TMA bulk loads (cp.async.bulk) completing on one mbarrier.  From
+    // the CTA's second frame on they were put in flight during the previous frame's decoder phases, the tape into the (then
+    // dead) band region: it is moved home here, leaving the zeros the band planes' halos need
+    if (!prefetched && tid == 0) {
       mbar_expect_tx(bar, TAPE + 12288);
       bulk_g2s(smb, p.tape + (size_t)n * TAPE, TAPE, bar);
       bulk_g2s(smb + kU8, p.frames + (size_t)n * 12288, 12288, bar);
     }
     mbar_wait(bar, phase);
     phase ^= 1u;
+    if (prefetched) {
+      const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+      uint4* src = reinterpret_cast<uint4*>(smraw + kXB);
+      uint4* dst = reinterpret_cast<uint4*>(smraw);
+      for (int e = tid; e < TAPE / 16; e += NT) { dst[e] = src[e]; src[e] = z4; }
+      __syncthreads();
+    }
     HG_MARK(1);
     const float* zf = p.z + (size_t)n * 4096;
     const float* dzf = p.dz + (size_t)n * 4096;
@@ -294,10 +305,19 @@ __global__ void __launch_bounds__(NT, 1) hg_backward_kernel(const BwdParams p) {
               }
             });
       }
+      fence_proxy_async();                             // (last band) our reads of the band region precede the bulk prefetch into it
       __syncthreads();
     }
 
     HG_MARK(22);
+    // the band region (frame rows, masker.0 band) and the raw bytes are dead until the next frame: fetch its tape and bytes now
+    prefetched = n + (int)gridDim.x < p.B;
+    if (prefetched && tid == 0) {
+      const int n2 = n + gridDim.x;
+      mbar_expect_tx(bar, TAPE + 12288);
+      bulk_g2s(smb + kXB, p.tape + (size_t)n2 * TAPE, TAPE, bar);
+      bulk_g2s(smb + kU8, p.frames + (size_t)n2 * 12288, 12288, bar);
+    }
     // ================= D0: dec[0] (cat(e0, up(o1)) -> o0 on 32x32): weight gradient (warps 0-7) || input gradient -> d o1 (8-15)
     if (warp < 8) {
       const int tr = warp & 3, kh = warp >> 2, src = tr >> 1, kxg = tr & 1;

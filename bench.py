@@ -263,6 +263,7 @@ def kernel_flops(entry, B, chfak=1):
     msk = 6488064 + 589824
     per = {
         "cgs_critic_train_fused": cf + cb + cf,                        # fprop + dgrad + wgrad = 8,460,480 / 2
+        "cgs_critic_train_bf16": cf + cb + cf,                         # the same step with bf16 operands (csrc/hg_critic.cu)
         "cgs_critic_loss_xgrad": cf + cf,                              # fprop + full input gradient (incl. features.0 dgrad)
         "cgs_critic_forward_frames": cf,
         "cgs_infer_fused": cf + dec,
@@ -544,12 +545,13 @@ def run_ours(args, rank, world):
         line = {"metric": METRIC if args.workload == "all" else names[0] + "_frames_per_s", "value": head["value"], "unit": UNIT,
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": ("bf16" if names[0] in ("hourglass", "infer") else "tf32") if args.precision == "tf32" else "f32",
+                "dtype": ("bf16" if names[0] in ("hourglass", "infer") or os.environ.get("CGS_CRITIC_BF16", "1") != "0" else "tf32")
+                if args.precision == "tf32" else "f32",
                 "data": "synthetic"}
         line.update({k: v for k, v in head.items() if k not in ("value", "unit", "ms_per_step")})
         line["precision"] = ("whole-frame kernels: bf16 mma.sync operands (fp32 accumulate) in every 3x3 convolution of the Hourglass "
-                             "step and of -process inference, TF32 mma.sync in the critic training step; 4x4 / 1x1 / Linear "
-                             "layers, losses, Adam fp32" if args.precision == "tf32" else "all fp32 (FFMA)")
+                             "step, of -process inference and of the critic training step (CGS_CRITIC_BF16=0: TF32 mma.sync "
+                             "there); 4x4 / 1x1 / Linear layers, losses, Adam fp32" if args.precision == "tf32" else "all fp32 (FFMA)")
         line["clocks"] = clocks
         if len(names) > 1:
             line["workloads"] = {k: v for k, v in recs.items() if k != names[0]}

@@ -55,6 +55,9 @@ EXPORTS = {
                                C.c_float, C.c_uint64, C.c_void_p,
                                C.POINTER(CriticWeights), C.POINTER(CriticWeights), _f32p, C.POINTER(AdamArgs), C.c_float,
                                C.c_int32, _f32p, _f32p, C.c_void_p],
+    "cgs_critic_train_bf16": [_u8p, _f32p, C.c_int32, C.c_int32, C.c_void_p, _f32p, _f32p, _f32p, C.c_float, C.c_uint64, C.c_void_p,
+                              C.POINTER(CriticWeights), _f32p, C.POINTER(AdamArgs), C.c_float, C.c_int32, _f32p, _f32p, C.c_void_p],
+    "cgs_hg_set_trace_critic": [C.c_void_p],
     "cgs_critic_fused_grid": [C.c_int32],
     "cgs_critic_fused_partial_stride": [],
     "cgs_reduce_partials": [_f32p, C.c_int64, _f32p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p],

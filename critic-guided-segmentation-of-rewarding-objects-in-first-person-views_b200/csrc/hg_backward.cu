@@ -52,25 +52,6 @@ struct BwdParams {
 
 constexpr uint32_t ONES2 = 0x3F803F80u;             // bf16 (1, 1)
 
-// One (source, kx group) weight-gradient triple over output-gradient rows [y0, y0 + R) of one 16-pixel strip:
-// acc[ky] += A(input row i) x B(gradient row i - ky).  loadA(i, a): the A fragment of haloed input row i (i = y + ky);
-// loadB(y, b0, b1): the B fragment (16 pixels x 8 output channels) of gradient row y.
-template <int R, class LoadA, class LoadB>
-__device__ __forceinline__ void wgrad_slide(float (&acc)[3][4], int y0, LoadA&& loadA, LoadB&& loadB) {
-  uint32_t b[3][2];
-#pragma unroll
-  for (int i = 0; i < R + 2; ++i) {
-    uint32_t a[4];
-    loadA(y0 + i, a);
-    if (i < R) loadB(y0 + i, b[i % 3][0], b[i % 3][1]);
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int y = i - ky;
-      if (y >= 0 && y < R) mma_bf16(acc[ky], a, b[y % 3][0], b[y % 3][1]);
-    }
-  }
-}
-
 // accumulate three fragment tiles held in registers into shared-memory tiles owned by this warp
 __device__ __forceinline__ void flush3(float* tiles, const float (&acc)[3][4], int lane) {
 #pragma unroll

@@ -53,86 +53,6 @@ struct FwdParams {
   uint8_t* tape;
 };
 
-// ---------------------------------------------------------------------------------------------------------------------
-// weight fragment pack: element (k, n) of the K16 x N8 matrix of MMA step s (0 where the slot is padding)
-struct PackSrc {
-  const float *w0, *w1, *w2, *w3, *d0, *d1, *d2, *d3, *m0, *m2;
-};
-
-__device__ float pack_wk(const PackSrc& p, int s, int k, int n) {
-  if (s < F_C1) {                                   // features.0: step ky; k = kx*4 + c (pair-duplicated frame)
-    const int ky = s, kx = k >> 2, c = k & 3;
-    return (kx < 3 && c < 3) ? p.w0[((n * 3 + c) * 3 + ky) * 3 + kx] : 0.f;
-  }
-  if (s < F_C3) {                                   // features.3 / features.6: step ky*2 + h; h 0 = taps (ky,0 | ky,1), h 1 = (ky,2 | 0)
-    const float* w = s < F_C2 ? p.w1 : p.w2;
-    const int q = s < F_C2 ? s - F_C1 : s - F_C2, ky = q >> 1, h = q & 1;
-    if (h && k >= 8) return 0.f;
-    const int kx = h ? 2 : (k >> 3), ci = k & 7;
-    return w[((n * 8 + ci) * 3 + ky) * 3 + kx];
-  }
-  if (s < F_D2) {                                   // features.10 (8 -> 16): step tp*2 + nt; taps (2tp | 2tp+1)
-    const int q = s - F_C3, tp = q >> 1, nt = q & 1, tap = 2 * tp + (k >> 3), ci = k & 7;
-    return tap > 8 ? 0.f : p.w3[((nt * 8 + n) * 8 + ci) * 9 + tap];
-  }
-  if (s < F_D1) {                                   // dec[2] (24 -> 8): step tap*2 + kc; kc 0 = channels 0..15, kc 1 = 16..23 | 0
-    const int q = s - F_D2, tap = q >> 1, kc = q & 1;
-    if (kc && k >= 8) return 0.f;
-    return p.d2[(n * 24 + kc * 16 + k) * 9 + tap];
-  }
-  if (s < F_M0) {                                   // dec[1] / dec[0] (16 -> 8): step tap; k = concatenated channel
-    const float* w = s < F_D0 ? p.d1 : p.d0;
-    const int tap = s < F_D0 ? s - F_D1 : s - F_D0;
-    return w[(n * 16 + k) * 9 + tap];
-  }
-  if (s < F_M2) {                                   // masker.0 (11 -> 16): step (ky*3 + j)*2 + nt; j 0 = RGB, 1 = o0 (kx 0|1), 2 = o0 (kx 2|-)
-    const int q = s - F_M0, nt = q & 1, j = (q >> 1) % 3, ky = (q >> 1) / 3, co = nt * 8 + n;
-    if (j == 0) {
-      const int kx = k >> 2, c = k & 3;
-      return (kx < 3 && c < 3) ? p.m0[((co * 11 + c) * 3 + ky) * 3 + kx] : 0.f;
-    }
-    if (j == 2 && k >= 8) return 0.f;
-    const int kx = j == 1 ? (k >> 3) : 2, ci = 3 + (k & 7);
-    return p.m0[((co * 11 + ci) * 3 + ky) * 3 + kx];
-  }
-  if (s < F_D3) return n == 0 ? p.m2[k * 9 + (s - F_M2)] : 0.f;        // masker.2 (16 -> 1): step tap
-  if (s < B_M0D) {                                  // dec[3] (48 -> 16): step (tap*3 + kc)*2 + nt
-    const int q = s - F_D3, nt = q & 1, kc = (q >> 1) % 3, tap = (q >> 1) / 3;
-    return p.d3[((nt * 8 + n) * 48 + kc * 16 + k) * 9 + tap];
-  }
-  // ---- input-gradient (dgrad) steps: tap' runs over the haloed output gradient, the filter is rotated: tap = 8 - tap'
-  if (s < B_D0D) return p.m0[(k * 11 + 3 + n) * 9 + 8 - (s - B_M0D)];   // masker.0 -> up(o0): k = co (16), n = ci
-  if (s < B_M2D) {                                  // dec[0] / dec[1] -> upsampled half: step ky'*2 + h; k = (tap' pair) x co (8)
-    const float* w = s < B_D1D ? p.d0 : p.d1;
-    const int q = s < B_D1D ? s - B_D0D : s - B_D1D, ky = q >> 1, h = q & 1;
-    if (h && k >= 8) return 0.f;
-    const int kx = h ? 2 : (k >> 3), co = k & 7;
-    return w[(co * 16 + 8 + n) * 9 + 8 - (ky * 3 + kx)];
-  }
-  if (s < B_D2D) return k < 9 ? p.m2[((s - B_M2D) * 8 + n) * 9 + 8 - k] : 0.f;     // masker.2 -> m0: k = tap', n = ci
-  if (s < B_D3D) {                                  // dec[2] -> up(o3): step tp*2 + nt; k = (tap' pair) x co (8); n: ci = 8 + nt*8 + n
-    const int q = s - B_D2D, nt = q & 1, tp = 2 * (q >> 1) + (k >> 3), co = k & 7;
-    return tp > 8 ? 0.f : p.d2[(co * 24 + 8 + nt * 8 + n) * 9 + 8 - tp];
-  }
-  if (s < B_C3D) {                                  // dec[3] -> dec[4] output: step tap'*4 + nt; k = co (16); n: ci = 16 + nt*8 + n
-    const int q = s - B_D3D, nt = q & 3, tp = q >> 2;
-    return p.d3[(k * 48 + 16 + nt * 8 + n) * 9 + 8 - tp];
-  }
-  if (s < B_C2D) return p.w3[(k * 8 + n) * 9 + 8 - (s - B_C3D)];          // features.10 -> its input: k = co (16), n = ci (8)
-  if (s < F_PT) {                                   // features.6 / .3 / .0 -> their inputs: step ky'*2 + h; k = (tap' pair) x co (8)
-    const float* w = s < B_C1D ? p.w2 : (s < B_C0D ? p.w1 : p.w0);
-    const int q = s - (s < B_C1D ? B_C2D : (s < B_C0D ? B_C1D : B_C0D)), ky = q >> 1, h = q & 1;
-    if (h && k >= 8) return 0.f;
-    const int kx = h ? 2 : (k >> 3), co = k & 7, tap = 8 - (ky * 3 + kx);
-    if (s < B_C0D) return w[(co * 8 + n) * 9 + tap];
-    return n < 3 ? w[(co * 3 + n) * 9 + tap] : 0.f;  // features.0: 3 input channels
-  }
-  {                                                 // masker.2, one column per filter tap: step nt; k = ci (16); n: tap = nt*8 + n
-    const int tap = (s - F_PT) * 8 + n;
-    return tap < 9 ? p.m2[k * 9 + tap] : 0.f;
-  }
-}
-
 __global__ void hg_pack_kernel(const PackSrc p, uint2* __restrict__ out) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= NSTEPS * 32) return;

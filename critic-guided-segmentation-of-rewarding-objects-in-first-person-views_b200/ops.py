@@ -541,7 +541,7 @@ def _critic_bucket_span(params):
 
 
 def critic_train_fused(critic, frames_u8, target, roll=0, masks=(None, None, None), loss_grad=1.0, bce=False,
-                       use_partials=True, rng=None, fuse_adam=False):
+                       use_partials=True, rng=None, fuse_adam=False, bf16=False):
     """Forward + loss + backward of one critic_pipe step (reference main.py:185-198) in ONE kernel
     (cgs_critic_train_fused).  The parameter gradient is ADDED to the parameters' `.grad`: by REDs, or — when the
     parameters sit contiguously in a FlatAdam bucket — as per-CTA partial vectors that `FlatAdam.step()` sums inside the
@@ -564,9 +564,14 @@ def critic_train_fused(critic, frames_u8, target, roll=0, masks=(None, None, Non
         buf = opt.partial_buffer(grid * stride)
         nparam = sum(q.numel() for q in params)
         adam = opt.fused_adam_args(off, nparam) if fuse_adam else None       # single GPU, bucket == the critic
-        _call("cgs_critic_train_fused", _p(frames_u8, torch.uint8), _p(target), B, r, rd, _p(m2), _p(m3), _p(mv),
-              rp, rseed, rstate, C.byref(w), None, _p(buf), C.byref(adam) if adam is not None else None, float(loss_grad),
-              int(bool(bce)), _p(pred), _p(loss), _stream())
+        if bf16:            # bf16 tensor-core operands (csrc/hg_critic.cu); same partial-vector / Adam / all-reduce contract
+            _call("cgs_critic_train_bf16", _p(frames_u8, torch.uint8), _p(target), B, r, rd, _p(m2), _p(m3), _p(mv),
+                  rp, rseed, rstate, C.byref(w), _p(buf), C.byref(adam) if adam is not None else None, float(loss_grad),
+                  int(bool(bce)), _p(pred), _p(loss), _stream())
+        else:
+            _call("cgs_critic_train_fused", _p(frames_u8, torch.uint8), _p(target), B, r, rd, _p(m2), _p(m3), _p(mv),
+                  rp, rseed, rstate, C.byref(w), None, _p(buf), C.byref(adam) if adam is not None else None, float(loss_grad),
+                  int(bool(bce)), _p(pred), _p(loss), _stream())
         if adam is not None:
             global _weights_epoch
             _weights_epoch += 1
@@ -574,6 +579,9 @@ def critic_train_fused(critic, frames_u8, target, roll=0, masks=(None, None, Non
         else:
             opt.pending_partials = (buf, grid, stride, off, nparam)
         return loss.reshape(()), pred
+    if bf16:
+        raise CgsError("critic_train_fused(bf16=True) hands its gradient over as partial vectors: the critic's parameters must sit "
+                       "contiguously in a FlatAdam bucket")
     grads = []
     for q in params:
         if q.grad is None:

@@ -257,6 +257,7 @@ class Handler:
                            self.maskername: f"{self.save_path}masker-{self.masker_args}.pt"}
         self.contrastive_batchsize = 32      # main.py:309
         self.fused_critic_step = True        # tf32 mode, chfak 1: one kernel per critic_pipe step
+        self.critic_bf16 = os.environ.get("CGS_CRITIC_BF16", "1") != "0"   # critic step: bf16 operands (csrc/hg_critic.cu) instead of TF32 (csrc/critic_fused.cu)
         self.hg_score_bf16 = True            # frozen Hourglass step: the three critic scoring passes in ONE bf16 kernel (else TF32)
         self.hg_inference = True             # tensor-core mode, chfak 1: -process in ONE bf16 kernel (csrc/hg_forward.cu)
         self.device_dataset = True           # segmentation_training gathers its batches from a device-resident uint8 dataset
@@ -372,7 +373,8 @@ class Handler:
             opti.zero_grad()
             loss, _ = ops.critic_train_fused(self.critic, x.contiguous(), Yd.contiguous(), roll, masks,
                                              loss_grad=weight, bce=bool(a.threshrew), rng=rng,
-                                             fuse_adam=bool(getattr(opti, "_clean", False)))
+                                             fuse_adam=bool(getattr(opti, "_clean", False)),
+                                             bf16=self.critic_bf16 and isinstance(opti, FlatAdam))
             opti.step()
             return loss
         pred = self.critic.forward_frames(x, roll).squeeze(1)     # cast + roll fused into features.0's operand load

@@ -367,6 +367,16 @@ int cgs_hg_score_bf16(const uint8_t* frames_a, const uint8_t* frames_b, int32_t 
                       float loss_grad, const float* vpred, float l1, float l2, float* negpred, float* pred_replace,
                       float* pred_inject, float* losses, float* dz, void* stream);
 
+/* The bf16 variant of cgs_critic_train_fused (csrc/hg_critic.cu): same arguments (minus the RED gradient struct: the gradient
+ * leaves as per-CTA partial vectors only), same outputs, same optional in-kernel Adam / peer-memory all-reduce.  bf16 tensor-core
+ * operands in the four 3x3 convolutions (forward, input and weight gradients), fp32 accumulation, fp32 head. */
+int cgs_critic_train_bf16(const uint8_t* frames, const float* target, int32_t B, int32_t roll, const int32_t* roll_dev,
+                          const float* m_e2, const float* m_e3, const float* m_v, float p_drop, uint64_t seed, uint64_t* rng_state,
+                          const cgs_critic_weights* w, float* partials, const cgs_adam_args* adam, float loss_grad, int32_t bce,
+                          float* pred, float* loss, void* stream);
+/* Debug only: clock64() phase trace of CTA 0 of cgs_critic_train_bf16 into 64 int64 (NULL disables). */
+int cgs_hg_set_trace_critic(long long* buf);
+
 /* ---- formats either side of the path, csrc/edges.cu ---------------------------------------------------
  * out[i] = dataset[idx[i]] for uint8 NHWC frames (12288 bytes each): `Xpos[Hidx]`, `Xneg[Lidx]`, `Xneg[Cidx]` of
  * main.py:345-353 over a device-resident dataset; indices are clamped to [0, nframes). */

@@ -41,14 +41,17 @@ def _case(B, p, seed, scale=1.5):
     return csd, X, Y[1, :B].astype(np.float32), masks
 
 
-def _oracle(csd, X, y, masks, roll, bce):
+def _oracle(csd, X, y, masks, roll, bce, q=None):
+    """q=None: the reference arithmetic; q=torch_ref.quant_tf32: the same with the conv operands rounded to TF32 where the
+    kernel rounds them (same ReLU / arg-max decisions; see tests/test_gpu_hg.py)."""
     sd = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in csd.items()}
     Xr = np.roll(X, -roll, axis=2)                                   # out[.., x, :] = in[.., (x + roll) mod 64, :]
     x = torch_ref.to_input(Xr)
     yt = torch.from_numpy(y)
     if bce:
         yt = (yt > 0.5).float()
-    loss, pred = torch_ref.critic_loss(sd, x, yt, masks=tuple(torch.from_numpy(m) for m in masks), threshrew=bce)
+    pred = torch_ref.critic_forward(sd, x, masks=tuple(torch.from_numpy(m) for m in masks), q=q).squeeze()
+    loss = torch.nn.functional.binary_cross_entropy(pred, yt) if bce else torch.nn.functional.mse_loss(pred, yt)   # main.py:192-195
     loss.backward()
     return loss.item(), pred.detach().numpy(), {k: v.grad.numpy() for k, v in sd.items()}
 
@@ -62,6 +65,7 @@ def _rel(a, b):
 def test_fused_step_vs_oracle(ops, B, roll, p, bce):
     csd, X, y, masks = _case(B, p, seed=B)
     loss_r, pred_r, grads_r = _oracle(csd, X, y, masks, roll, bce)
+    loss_q, pred_q, grads_q = _oracle(csd, X, y, masks, roll, bce, q=torch_ref.quant_tf32)
     c = _critic(csd, p)
     for q in c.parameters():
         q.grad = torch.zeros_like(q)
@@ -72,11 +76,18 @@ def test_fused_step_vs_oracle(ops, B, roll, p, bce):
     loss, pred = ops.critic_train_fused(c, torch.from_numpy(X).to(DEV), yt, roll, dm, loss_grad=1.0, bce=bce)
     torch.cuda.synchronize()
     pred = pred.cpu().numpy()
+    g_all = np.concatenate([v.grad.cpu().numpy().ravel() for v in c.parameters()])
+    # (1) the oracle at the kernel's operand precision (TF32 conv operands, same decisions): tight
+    assert np.abs(pred - pred_q).max() <= 3e-4, np.abs(pred - pred_q).max()
+    assert abs(loss.item() - loss_q) <= 1e-3 * abs(loss_q) + 1e-6, (loss.item(), loss_q)
+    errs_q = {k: _rel(v.grad.cpu().numpy(), grads_q[k]) for k, v in c.named_parameters()}
+    tot_q = _rel(g_all, np.concatenate([grads_q[k].ravel() for k, _ in c.named_parameters()]))
+    assert tot_q <= 6e-3 and max(errs_q.values()) <= 2e-2, ("operand-precision oracle", tot_q, errs_q)
+    # (2) the reference arithmetic: what TF32 operands cost (arg-max / ReLU flips move gradients norm-wise by sqrt(flip rate))
     assert np.abs(pred - pred_r).max() <= 2e-3, np.abs(pred - pred_r).max()
     assert abs(loss.item() - loss_r) <= 5e-3 * abs(loss_r) + 1e-6, (loss.item(), loss_r)
     errs = {k: _rel(v.grad.cpu().numpy(), grads_r[k]) for k, v in c.named_parameters()}
-    tot = _rel(np.concatenate([v.grad.cpu().numpy().ravel() for v in c.parameters()]),
-               np.concatenate([grads_r[k].ravel() for k, _ in c.named_parameters()]))
+    tot = _rel(g_all, np.concatenate([grads_r[k].ravel() for k, _ in c.named_parameters()]))
     assert tot <= 3e-2, (tot, errs)
     assert max(errs.values()) <= 8e-2, errs
 

@@ -117,6 +117,13 @@ EXPORTS = {
     "cgs_mask_images": [_f32p, _u8p, C.c_int32, _u8p, _u8p, C.c_int32, _u8p, _u8p, C.c_void_p],
     "cgs_saliency_normalize": [_f32p, _f32p, C.c_int32, C.c_int32, C.c_float, _f32p, _f32p, _u8p, _f32p, C.c_void_p],
     "cgs_tc_status": [],
+    "cgs_wide_conv3x3": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32,
+                         C.c_void_p, _f32p, _u8p, _u8p, _f32p, C.c_void_p],
+    "cgs_wide_wgrad3x3": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _f32p, C.c_int64,
+                          C.c_void_p],
+    "cgs_wide_wgrad_workspace": [C.c_int32, C.c_int32, C.c_int32, C.c_int32],
+    "cgs_wide_status": [],
+    "cgs_wide_set_trace": [C.c_void_p],
     "cgs_tc_set_trace": [C.c_void_p],
     "cgs_critic_fused_set_trace": [C.c_void_p],
 }

@@ -1,0 +1,586 @@
+// The wide (chfak > 1) convolution kernels: TMA-fed tcgen05 / TMEM implicit GEMMs with bf16 operands, fp32 accumulation.
+//
+// Activations live in HBM "chunk-planar": [B][C/8][H][W][8 channels] bf16, so that one pixel's 8 channels of a plane are one
+// 16-byte slot.  A TMA box (8, bw, bh, planes, 1) of the 5-D view (8, W, H, C/8, B) lands in shared memory as
+// [plane][bh][bw][16 B], which is at once
+//   * the UMMA no-swizzle K-MAJOR canonical layout ((8,m),(8,2)):((16 B,SBO),(1,LBO)) with a core matrix = 8 horizontally
+//     adjacent pixels of one plane, SBO = one tile row and LBO = one plane: the A operand (rows = pixels, K = channels) of the
+//     forward / input-gradient GEMM.  The tile is loaded ONCE with its 1-pixel halo (TMA zero-fills out of bounds = the
+//     convolution's padding) and filter tap (ky, kx) is the same buffer addressed (ky * 10 + kx) slots further on: nine shifted
+//     descriptors, no im2col, no data movement between taps;
+//   * the UMMA no-swizzle MN-MAJOR canonical layout ((8,m),(8,k)):((1,SBO),(16 B,LBO)) with SBO = one plane and LBO = one tile
+//     row: both operands (K = pixels) of the weight-gradient GEMM  D[(kx, ci), co] = sum_pixels X[p + tap][ci] * dY[p][co].
+//     Three TMA loads put the kx = 0, 1, 2 shifts of the input tile into planes [kx][ci / 8] of ONE 128-row A operand (plane 15
+//     holds ones: the bias gradient rides along), so a tile costs 3 (ky) x 8 (row pairs) MMAs of 128 x Cout x 16.
+//
+// Both kernels are persistent and warp-specialised: warp 0 = TMA producer (one thread, `cp.async.bulk.tensor.5d` + mbarrier
+// expect_tx, 3-4 stage ring), warp 1 = MMA issuer (one thread, `tcgen05.mma.cta_group::1.kind::f16`, `tcgen05.commit` frees
+// the stage / publishes the accumulator), warps 2-5 = epilogue (tcgen05.ld of their TMEM lane quarter; bias + ReLU + 2x2
+// max-pool + first-max arg-max + dropout mask, or the pool / ReLU / dropout BACKWARD scatter, written as bf16 planes).
+// The accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the MMAs of tile i+1 and the loads of i+2...
+// Reference: nets.py:169-187 (features), main.py:185-198 (the training step these feed).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace cgs {
+namespace wd {
+
+constexpr int TW = 8, TH = 16, HWID = 10, HHGT = 18;
+constexpr int SLOTS = HWID * HHGT;                 // 180 haloed pixels
+constexpr int NTHR = 192;
+constexpr int A3_ROWS = 18 * 8;                    // weight gradient: one kx copy of a plane = 18 rows x 8 pixels
+constexpr int A3_PLANE = A3_ROWS * 16, A3_BYTES = 16 * A3_PLANE;
+constexpr int DY_PLANE = TH * TW * 16;
+
+__device__ int g_wd_timeout = 0;
+__device__ long long* g_wd_trace = nullptr;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// no-swizzle shared-memory matrix descriptor (sm_100 format, version 1); the meaning of LBO / SBO depends on the major-ness
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol bug must surface as an error flag (cgs_wide_status), never as a hung GPU
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (ok) return true;
+  }
+  atomicExch(&g_wd_timeout, 1);
+  return false;
+}
+__device__ __forceinline__ void tma_load5(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(dst),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct ConvP {
+  int B, H, W, Cin, Cout;          // GEMM view: K = 9 taps x Cin, N = Cout (transposed: Cin = the layer's outputs)
+  int CPi, KP, NP;                 // Cin / 8, planes padded to even, Cout padded to 16
+  int tiles_x, tiles_y, ntiles, stages, tmem_cols, epi, transposed;
+  uint32_t idesc;
+  const float* w;
+  const float* bias;
+  __nv_bfloat16* out;
+  uint8_t* idx_out;
+  const uint8_t* idx_in;
+  const float* mask;
+  float* out_f32;
+};
+
+__global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constant__ CUtensorMap tmx, const ConvP p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KP = p.KP, NP = p.NP;
+  const uint32_t w_bytes = (uint32_t)9 * KP * NP * 16, a_bytes = (uint32_t)KP * SLOTS * 16, a_tx = (uint32_t)p.CPi * SLOTS * 16;
+  unsigned char* s_w = smem;
+  unsigned char* s_a = smem + w_bytes;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_a + (size_t)p.stages * a_bytes);     // full[S] empty[S] tfull[2] tempty[2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * p.stages + 4);
+  const uint32_t bar0 = smem_u32(s_bar);
+  const uint32_t bFull = bar0, bEmpty = bar0 + 8 * p.stages, bTFull = bar0 + 16 * p.stages, bTEmpty = bTFull + 16;
+
+  // ---- one-time setup
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(bFull + 8 * s, 1); mbar_init(bEmpty + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bTFull + 8 * b, 1); mbar_init(bTEmpty + 8 * b, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  {
+    // B operand (K-major): element (tap, ci, co) -> [(tap * KP + ci / 8) * NP + co] x 16 B + (ci % 8) x 2 B, zero padded
+    const int rows = 9 * KP * NP;
+    for (int r = tid; r < rows; r += NTHR) {
+      const int co = r % NP, tq = r / NP, q = tq % KP, t = tq / KP;
+      float v[8];
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        const int ci = q * 8 + c8;
+        v[c8] = 0.f;
+        if (ci < p.Cin && co < p.Cout)
+          v[c8] = p.transposed ? __ldg(p.w + ((size_t)ci * p.Cout + co) * 9 + (8 - t)) : __ldg(p.w + ((size_t)co * p.Cin + ci) * 9 + t);
+      }
+      *reinterpret_cast<uint4*>(s_w + (size_t)r * 16) = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+    }
+    // the pad plane of every stage (Cin / 8 odd) is read by the last MMA of a tap: its weights are zero, the plane must be finite
+    if (KP > p.CPi)
+      for (int s = 0; s < p.stages; ++s)
+        for (int e = tid; e < SLOTS; e += NTHR) reinterpret_cast<uint4*>(s_a + (size_t)s * a_bytes + (size_t)p.CPi * SLOTS * 16)[e] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = *s_tmem;
+  const int tpf = p.tiles_x * p.tiles_y;
+  long long* trace = (blockIdx.x == 0) ? g_wd_trace : nullptr;
+
+  if (warp == 0) {
+    // ===== TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int s = it % p.stages, k = it / p.stages;
+        if (!mbar_wait(bEmpty + 8 * s, (k & 1) ^ 1)) break;
+        const int n = tile / tpf, r = tile - n * tpf, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        mbar_expect_tx(bFull + 8 * s, a_tx);
+        tma_load5(smem_u32(s_a + (size_t)s * a_bytes), &tmx, 0, tx * TW - 1, ty * TH - 1, 0, n, bFull + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    if (lane == 0) {
+      const uint32_t w_base = smem_u32(s_w), w_plane = (uint32_t)NP * 16;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int s = it % p.stages, k = it / p.stages, ab = it & 1, j = it >> 1;
+        if (trace && it < 8) trace[it * 4 + 0] = clock64();
+        if (!mbar_wait(bTEmpty + 8 * ab, (j & 1) ^ 1)) break;
+        if (!mbar_wait(bFull + 8 * s, k & 1)) break;
+        if (trace && it < 8) trace[it * 4 + 1] = clock64();
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t a0 = smem_u32(s_a + (size_t)s * a_bytes), td = tmem_base + (uint32_t)(ab * NP);
+        uint32_t acc = 0;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          const uint32_t a_tap = a0 + (uint32_t)(ky * HWID + kx) * 16;
+          for (int kp = 0; kp < KP; kp += 2) {
+            umma_bf16(td, umma_desc(a_tap + (uint32_t)kp * (SLOTS * 16), SLOTS * 16, HWID * 16),
+                      umma_desc(w_base + (uint32_t)(tap * KP + kp) * w_plane, w_plane, 128), p.idesc, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(bEmpty + 8 * s);              // the stage is free once these MMAs have read it
+        umma_commit(bTFull + 8 * ab);             // ... and the accumulator is complete
+        if (trace && it < 8) trace[it * 4 + 2] = clock64();
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane quarter (warp & 3); lane m of the accumulator = pixel (m / 8, m % 8) of the tile
+    const int q = warp & 3, m = q * 32 + lane, yl = m >> 3, xl = m & 7;
+    const bool odd_x = xl & 1, odd_y = yl & 1;
+    const int H = p.H, W = p.W, Cout = p.Cout, CPo = Cout >> 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1, j = it >> 1;
+      if (!mbar_wait(bTFull + 8 * ab, j & 1)) break;
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const int n = tile / tpf, r = tile - n * tpf, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int y = ty * TH + yl, x = tx * TW + xl;
+      const bool inb = y < H;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * NP);
+      for (int cg = 0; cg < CPo; ++cg) {
+        float a[8];
+        tmem_ld8(taddr + (uint32_t)(cg * 8), a);
+        if (p.bias) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cg * 8)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cg * 8) + 1);
+          a[0] += b0.x; a[1] += b0.y; a[2] += b0.z; a[3] += b0.w; a[4] += b1.x; a[5] += b1.y; a[6] += b1.z; a[7] += b1.w;
+        }
+        if (p.epi == CGS_WIDE_EPI_RELU_POOL) {
+          // 2x2 window = lanes (l, l^1, l^8, l^9); the first maximum in row-major order wins (ATen max_pool2d); 4 = ReLU is dead
+          float res[8];
+          uint32_t ilo = 0, ihi = 0;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float v = a[c], o = __shfl_xor_sync(0xffffffffu, v, 1);
+            const float left = odd_x ? o : v, right = odd_x ? v : o;
+            const bool rr = right > left;
+            const float mx = rr ? right : left;
+            const float o2 = __shfl_xor_sync(0xffffffffu, mx, 8);
+            const int ro = __shfl_xor_sync(0xffffffffu, (int)rr, 8);
+            const float top = odd_y ? o2 : mx, bot = odd_y ? mx : o2;
+            const int rt = odd_y ? ro : (int)rr, rb = odd_y ? (int)rr : ro;
+            const bool bb = bot > top;
+            float v2 = bb ? bot : top;
+            uint32_t am = bb ? (2u + (uint32_t)rb) : (uint32_t)rt;
+            if (!(v2 > 0.f)) { v2 = 0.f; am = 4u; }
+            res[c] = v2;
+            if (c < 4) ilo |= am << (8 * c); else ihi |= am << (8 * (c - 4));
+          }
+          if (!odd_x && !odd_y && inb) {
+            const int H2 = H >> 1, W2 = W >> 1, y2 = y >> 1, x2 = x >> 1;
+            if (p.mask) {
+              const float* mp = p.mask + ((size_t)(n * H2 + y2) * W2 + x2) * Cout + cg * 8;
+              const float4 m0 = __ldg(reinterpret_cast<const float4*>(mp)), m1 = __ldg(reinterpret_cast<const float4*>(mp) + 1);
+              res[0] *= m0.x; res[1] *= m0.y; res[2] *= m0.z; res[3] *= m0.w; res[4] *= m1.x; res[5] *= m1.y; res[6] *= m1.z; res[7] *= m1.w;
+            }
+            const size_t o = ((size_t)(n * CPo + cg) * H2 + y2) * W2 + x2;
+            if (p.out) reinterpret_cast<uint4*>(p.out)[o] = make_uint4(pack2(res[0], res[1]), pack2(res[2], res[3]), pack2(res[4], res[5]), pack2(res[6], res[7]));
+            if (p.out_f32) {       // NHWC fp32 copy for the head (features.14 reads it as its K vector)
+              float4* of = reinterpret_cast<float4*>(p.out_f32 + ((size_t)(n * H2 + y2) * W2 + x2) * Cout + cg * 8);
+              of[0] = make_float4(res[0], res[1], res[2], res[3]);
+              of[1] = make_float4(res[4], res[5], res[6], res[7]);
+            }
+            reinterpret_cast<uint2*>(p.idx_out)[o] = make_uint2(ilo, ihi);
+          }
+        } else if (p.epi == CGS_WIDE_EPI_UNPOOL) {
+          // this pixel is one pooled output of the layer below: its gradient goes to the arg-max position of the 2x2 window
+          // (ReLU dead / dropout: nowhere / scaled), the other three positions get zeros
+          if (inb) {
+            const size_t oi = ((size_t)(n * CPo + cg) * H + y) * W + x;
+            const uint2 ib = __ldg(reinterpret_cast<const uint2*>(p.idx_in) + oi);
+            if (p.mask) {
+              const float* mp = p.mask + ((size_t)(n * H + y) * W + x) * Cout + cg * 8;
+              const float4 m0 = __ldg(reinterpret_cast<const float4*>(mp)), m1 = __ldg(reinterpret_cast<const float4*>(mp) + 1);
+              a[0] *= m0.x; a[1] *= m0.y; a[2] *= m0.z; a[3] *= m0.w; a[4] *= m1.x; a[5] *= m1.y; a[6] *= m1.z; a[7] *= m1.w;
+            }
+            const int H2 = 2 * H, W2 = 2 * W;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+              uint32_t pk[2][4];
+#pragma unroll
+              for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+                for (int c2 = 0; c2 < 4; ++c2) {
+                  const uint32_t i0 = ((2 * c2 < 4 ? ib.x : ib.y) >> (8 * ((2 * c2) & 3))) & 0xffu;
+                  const uint32_t i1 = ((2 * c2 + 1 < 4 ? ib.x : ib.y) >> (8 * ((2 * c2 + 1) & 3))) & 0xffu;
+                  const uint32_t pos = (uint32_t)(dy * 2 + dx);
+                  pk[dx][c2] = pack2(i0 == pos ? a[2 * c2] : 0.f, i1 == pos ? a[2 * c2 + 1] : 0.f);
+                }
+              uint4* d = reinterpret_cast<uint4*>(p.out) + ((size_t)(n * CPo + cg) * H2 + 2 * y + dy) * W2 + 2 * x;
+              d[0] = make_uint4(pk[0][0], pk[0][1], pk[0][2], pk[0][3]);
+              d[1] = make_uint4(pk[1][0], pk[1][1], pk[1][2], pk[1][3]);
+            }
+          }
+        } else {
+          if (inb) {
+            const size_t o = ((size_t)(n * CPo + cg) * H + y) * W + x;
+            reinterpret_cast<uint4*>(p.out)[o] = make_uint4(pack2(a[0], a[1]), pack2(a[2], a[3]), pack2(a[4], a[5]), pack2(a[6], a[7]));
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bTEmpty + 8 * ab);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// weight gradient: D_ky[(kx, ci) | ones][co] += sum over the tile's pixels; accumulators stay in TMEM over all tiles of the CTA
+struct WgP {
+  int B, H, W, Cin, Cout, CPi, CPo, NP, NPl;
+  int tiles_x, tiles_y, ntiles, stages, tmem_cols;
+  uint32_t idesc;
+  float* partials;                 // [grid][3][128][NP]
+};
+
+__global__ void __launch_bounds__(NTHR, 1) wide_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmdy,
+                                                             const WgP p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NP = p.NP;
+  const uint32_t b_bytes = (uint32_t)p.NPl * DY_PLANE, st_bytes = A3_BYTES + b_bytes;
+  const uint32_t tx_bytes = (uint32_t)3 * p.CPi * A3_PLANE + (uint32_t)p.CPo * DY_PLANE;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * st_bytes);   // full[S] empty[S] done
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * p.stages + 1);
+  const uint32_t bar0 = smem_u32(s_bar), bFull = bar0, bEmpty = bar0 + 8 * p.stages, bDone = bar0 + 16 * p.stages;
+
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(bFull + 8 * s, 1); mbar_init(bEmpty + 8 * s, 1); }
+    mbar_init(bDone, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  // planes the TMA never writes: zeros (unused rows / columns of D stay finite), plane 15 of A = ones (bias gradient)
+  for (int s = 0; s < p.stages; ++s) {
+    uint4* a = reinterpret_cast<uint4*>(smem + (size_t)s * st_bytes);
+    for (int e = tid; e < 16 * A3_ROWS; e += NTHR) {
+      const int pl = e / A3_ROWS;
+      if (pl >= 3 * p.CPi) a[e] = pl == 15 ? make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    uint4* b = reinterpret_cast<uint4*>(smem + (size_t)s * st_bytes + A3_BYTES);
+    for (int e = tid + p.CPo * (TH * TW); e < p.NPl * (TH * TW); e += NTHR) b[e] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = *s_tmem;
+  const int tpf = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int s = it % p.stages, k = it / p.stages;
+        if (!mbar_wait(bEmpty + 8 * s, (k & 1) ^ 1)) break;
+        const int n = tile / tpf, r = tile - n * tpf, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const uint32_t a0 = smem_u32(smem + (size_t)s * st_bytes);
+        mbar_expect_tx(bFull + 8 * s, tx_bytes);
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+          tma_load5(a0 + (uint32_t)(kx * p.CPi) * A3_PLANE, &tmx, 0, tx * TW - 1 + kx, ty * TH - 1, 0, n, bFull + 8 * s);
+        tma_load5(a0 + A3_BYTES, &tmdy, 0, tx * TW, ty * TH, 0, n, bFull + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int it = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.ntiles && ok; tile += gridDim.x, ++it) {
+        const int s = it % p.stages, k = it / p.stages;
+        if (!mbar_wait(bFull + 8 * s, k & 1)) { ok = false; break; }
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t a0 = smem_u32(smem + (size_t)s * st_bytes), b0 = a0 + A3_BYTES;
+        for (int ky = 0; ky < 3; ++ky)
+          for (int r2 = 0; r2 < 8; ++r2)          // K = 16 pixels = tile rows 2 r2, 2 r2 + 1 (8 pixels each)
+            umma_bf16(tmem_base + (uint32_t)(ky * NP), umma_desc(a0 + (uint32_t)(2 * r2 + ky) * 128, 128, A3_PLANE),
+                      umma_desc(b0 + (uint32_t)(2 * r2) * 128, 128, DY_PLANE), p.idesc, (it > 0 || r2 > 0) ? 1u : 0u);
+        umma_commit(bEmpty + 8 * s);
+      }
+      umma_commit(bDone);
+    }
+  } else {
+    const int q = warp & 3, m = q * 32 + lane;
+    if (mbar_wait(bDone, 0)) {
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int ky = 0; ky < 3; ++ky) {
+        float* dst = p.partials + (((size_t)blockIdx.x * 3 + ky) * 128 + m) * NP;
+        for (int c = 0; c < NP; c += 8) {
+          float a[8];
+          tmem_ld8(taddr + (uint32_t)(ky * NP + c), a);
+          reinterpret_cast<float4*>(dst + c)[0] = make_float4(a[0], a[1], a[2], a[3]);
+          reinterpret_cast<float4*>(dst + c)[1] = make_float4(a[4], a[5], a[6], a[7]);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// dW[co][ci][ky][kx] += sum over CTAs of P[cta][ky][kx * Cin + ci][co]; db[co] += sum of P[cta][1][120][co] (the ones plane)
+__global__ void wide_wgrad_reduce_kernel(const float* __restrict__ part, int ncta, int NP, int Cin, int Cout, float* __restrict__ dw,
+                                         float* __restrict__ db) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * 128 * NP) return;
+  const int co = e % NP, m = (e / NP) & 127, ky = e / (NP * 128);
+  if (co >= Cout) return;
+  const bool is_w = m < 3 * Cin, is_b = (m == 120 && ky == 1 && db != nullptr);
+  if (!is_w && !is_b) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int c = 0;
+  const size_t stride = (size_t)3 * 128 * NP;
+  for (; c + 4 <= ncta; c += 4) {
+    s0 += part[(size_t)c * stride + e];
+    s1 += part[(size_t)(c + 1) * stride + e];
+    s2 += part[(size_t)(c + 2) * stride + e];
+    s3 += part[(size_t)(c + 3) * stride + e];
+  }
+  for (; c < ncta; ++c) s0 += part[(size_t)c * stride + e];
+  const float s = (s0 + s1) + (s2 + s3);
+  if (is_w) {
+    const int kx = m / Cin, ci = m - kx * Cin;
+    dw[((size_t)(co * Cin + ci) * 3 + ky) * 3 + kx] += s;
+  } else {
+    db[co] += s;
+  }
+}
+
+// ---- host side
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeFn encode_fn() {
+  static EncodeFn f = nullptr;
+  if (!f) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      f = (EncodeFn)ptr;
+  }
+  return f;
+}
+
+// 5-D view (8, W, H, C/8, B) of a chunk-planar bf16 tensor; box (8, bw, bh, planes, 1); out-of-bounds elements read as zero
+int make_tmap(CUtensorMap* tm, const void* base, int B, int CP, int H, int W, int bw, int bh, int planes) {
+  EncodeFn enc = encode_fn();
+  if (!enc) {
+    set_error("wide: cuTensorMapEncodeTiled is not available from this driver");
+    return CGS_ECUDA;
+  }
+  const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)CP, (cuuint64_t)B};
+  const cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)CP * H * W * 16};
+  const cuuint32_t box[5] = {8, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)planes, 1};
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("wide: cuTensorMapEncodeTiled failed (%d) for B=%d CP=%d H=%d W=%d box=(%d,%d,%d)", (int)r, B, CP, H, W, bw, bh, planes);
+    return CGS_ECUDA;
+  }
+  return 0;
+}
+
+static int pow2_cols(int c) {
+  int t = 32;
+  while (t < c) t *= 2;
+  return t;
+}
+
+int launch_wide_conv(const void* x, int B, int H, int W, int Cin, const float* w, const float* bias, int Cout, int transposed, int epi,
+                     void* out, float* out_f32, uint8_t* idx_out, const uint8_t* idx_in, const float* mask, cudaStream_t st) {
+  CGS_REQUIRE(x && w && (out || out_f32) && B > 0, "wide_conv3x3: bad args");
+  CGS_REQUIRE((Cin % 8) == 0 && (Cout % 8) == 0 && Cin >= 8 && Cout >= 8 && Cin <= 160 && Cout <= 240, "wide_conv3x3: channels must be multiples of 8 (Cin %d, Cout %d)", Cin, Cout);
+  CGS_REQUIRE((W % TW) == 0 && (H % 8) == 0 && H >= 8, "wide_conv3x3: H x W = %d x %d unsupported", H, W);
+  CGS_REQUIRE(epi != CGS_WIDE_EPI_RELU_POOL || idx_out, "wide_conv3x3: the pooling epilogue needs idx_out");
+  CGS_REQUIRE(epi != CGS_WIDE_EPI_UNPOOL || (idx_in && out), "wide_conv3x3: the unpooling epilogue needs idx_in");
+  ConvP p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.CPi = Cin / 8; p.KP = (p.CPi + 1) & ~1; p.NP = (Cout + 15) & ~15;
+  p.tiles_x = W / TW; p.tiles_y = (H + TH - 1) / TH; p.ntiles = B * p.tiles_x * p.tiles_y;
+  p.epi = epi; p.transposed = transposed; p.w = w; p.bias = bias;
+  p.out = (__nv_bfloat16*)out; p.out_f32 = out_f32; p.idx_out = idx_out; p.idx_in = idx_in; p.mask = mask;
+  p.tmem_cols = pow2_cols(2 * p.NP);
+  CGS_REQUIRE(p.tmem_cols <= 512, "wide_conv3x3: Cout %d needs more than 512 TMEM columns", Cout);
+  // D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const size_t w_bytes = (size_t)9 * p.KP * p.NP * 16, a_bytes = (size_t)p.KP * SLOTS * 16;
+  int stages = 4;
+  while (stages > 2 && w_bytes + stages * a_bytes + 256 > 220 * 1024) --stages;
+  p.stages = stages;
+  const size_t smem = w_bytes + stages * a_bytes + 256;
+  CGS_REQUIRE(smem <= 225 * 1024, "wide_conv3x3: Cin %d x Cout %d does not fit in shared memory", Cin, Cout);
+  CUtensorMap tm;
+  const int rc = make_tmap(&tm, x, B, p.CPi, H, W, HWID, HHGT, p.CPi);
+  if (rc) return rc;
+  cudaFuncSetAttribute(wide_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+  int grid = device_sms();
+  if (grid > p.ntiles) grid = p.ntiles;
+  wide_conv_kernel<<<grid, NTHR, smem, st>>>(tm, p);
+  return check_launch("wide_conv3x3");
+}
+
+int wide_wgrad_grid(int B, int H, int W) {
+  const int ntiles = B * (W / TW) * ((H + TH - 1) / TH);
+  int grid = device_sms();
+  return grid > ntiles ? ntiles : grid;
+}
+
+int launch_wide_wgrad(const void* x, const void* dy, int B, int H, int W, int Cin, int Cout, float* dw, float* db, float* ws,
+                      long long ws_floats, cudaStream_t st) {
+  CGS_REQUIRE(x && dy && dw && ws && B > 0, "wide_wgrad3x3: bad args");
+  CGS_REQUIRE((Cin % 8) == 0 && Cin >= 8 && Cin <= 40 && (Cout % 8) == 0 && Cout >= 8 && 3 * ((Cout + 15) & ~15) <= 512,
+              "wide_wgrad3x3: Cin %d (<= 40) / Cout %d unsupported", Cin, Cout);
+  CGS_REQUIRE((W % TW) == 0 && (H % 8) == 0 && H >= 8, "wide_wgrad3x3: H x W = %d x %d unsupported", H, W);
+  WgP p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.CPi = Cin / 8; p.CPo = Cout / 8;
+  p.NP = (Cout + 15) & ~15; p.NPl = p.NP / 8;
+  p.tiles_x = W / TW; p.tiles_y = (H + TH - 1) / TH; p.ntiles = B * p.tiles_x * p.tiles_y;
+  p.tmem_cols = pow2_cols(3 * p.NP);
+  // as above with A and B MN-major (bits 15, 16): K = pixels
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const size_t st_bytes = (size_t)A3_BYTES + (size_t)p.NPl * DY_PLANE;
+  int stages = 4;
+  while (stages > 2 && stages * st_bytes + 256 > 220 * 1024) --stages;
+  p.stages = stages;
+  const size_t smem = stages * st_bytes + 256;
+  const int grid = wide_wgrad_grid(B, H, W);
+  CGS_REQUIRE(ws_floats >= (long long)grid * 3 * 128 * p.NP, "wide_wgrad3x3: workspace too small (%lld floats, need %lld)", ws_floats,
+              (long long)grid * 3 * 128 * p.NP);
+  p.partials = ws;
+  CUtensorMap tmx, tmdy;
+  int rc = make_tmap(&tmx, x, B, p.CPi, H, W, TW, HHGT, p.CPi);
+  if (rc) return rc;
+  rc = make_tmap(&tmdy, dy, B, p.CPo, H, W, TW, TH, p.CPo);
+  if (rc) return rc;
+  cudaFuncSetAttribute(wide_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+  wide_wgrad_kernel<<<grid, NTHR, smem, st>>>(tmx, tmdy, p);
+  rc = check_launch("wide_wgrad3x3");
+  if (rc) return rc;
+  const int n = 3 * 128 * p.NP;
+  wide_wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws, grid, p.NP, Cin, Cout, dw, db);
+  return check_launch("wide_wgrad3x3.reduce");
+}
+
+}  // namespace wd
+}  // namespace cgs
+
+using namespace cgs;
+
+extern "C" int cgs_wide_conv3x3(const void* x, int32_t B, int32_t H, int32_t W, int32_t Cin, const float* w, const float* bias, int32_t Cout,
+                                int32_t transposed, int32_t epi, void* out, float* out_f32, uint8_t* idx_out, const uint8_t* idx_in,
+                                const float* mask, void* stream) {
+  return wd::launch_wide_conv(x, B, H, W, Cin, w, bias, Cout, transposed, epi, out, out_f32, idx_out, idx_in, mask, (cudaStream_t)stream);
+}
+
+extern "C" int cgs_wide_wgrad3x3(const void* x, const void* dy, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, float* dw, float* db,
+                                 float* workspace, int64_t workspace_floats, void* stream) {
+  return wd::launch_wide_wgrad(x, dy, B, H, W, Cin, Cout, dw, db, workspace, workspace_floats, (cudaStream_t)stream);
+}
+
+extern "C" int64_t cgs_wide_wgrad_workspace(int32_t B, int32_t H, int32_t W, int32_t Cout) {
+  return (int64_t)wd::wide_wgrad_grid(B, H, W) * 3 * 128 * ((Cout + 15) & ~15);
+}
+
+extern "C" int cgs_wide_status(void) {
+  int h = 0;
+  cudaMemcpyFromSymbol(&h, wd::g_wd_timeout, sizeof(int));
+  return h;
+}
+
+extern "C" int cgs_wide_set_trace(long long* dev_buf) {
+  return cudaMemcpyToSymbol(wd::g_wd_trace, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? 0 : -2;
+}

@@ -377,6 +377,33 @@ int cgs_critic_train_bf16(const uint8_t* frames, const float* target, int32_t B,
 /* Debug only: clock64() phase trace of CTA 0 of cgs_critic_train_bf16 into 64 int64 (NULL disables). */
 int cgs_hg_set_trace_critic(long long* buf);
 
+/* ---- the wide (chfak > 1) path: TMA-fed tcgen05 / TMEM convolutions, bf16 operands, fp32 accumulation (csrc/wide_tc.cu) ----
+ * Activations are bf16 "chunk-planar" [B][C/8][H][W][8]; filters stay fp32 OIHW (packed to bf16 operand tiles in the kernel).
+ * Replaces nn.Conv2d(k=3, padding=1) + ReLU + MaxPool2d(2) [+ Dropout] of nets.py:170-183 and their autograd backward. */
+enum {
+  CGS_WIDE_EPI_PLAIN = 0,     /* out[B][Cout/8][H][W][8] = conv + bias */
+  CGS_WIDE_EPI_RELU_POOL = 1, /* out[B][Cout/8][H/2][W/2][8] = maxpool2(relu(conv + bias)) [* mask]; idx_out = first-max position
+                                 0..3, or 4 where the pooled value is not > 0 (ReLU dead); out_f32: optional NHWC fp32 copy */
+  CGS_WIDE_EPI_UNPOOL = 2     /* the conv result is the gradient of a pooled map: out[B][Cout/8][2H][2W][8] receives it [* mask] at
+                                 the window position idx_in names and zeros elsewhere (MaxPool + ReLU + Dropout backward) */
+};
+/* transposed != 0: the input-gradient convolution of a layer with weight w[Cin][Cout][3][3] (x = the output gradient with Cin
+ * channels; filters rotated, in/out swapped).  mask: NHWC fp32 [B][h][w][Cout] at the resolution of `out`'s pooled map
+ * (RELU_POOL) or of the conv itself (UNPOOL), or NULL. */
+int cgs_wide_conv3x3(const void* x, int32_t B, int32_t H, int32_t W, int32_t Cin, const float* w, const float* bias, int32_t Cout,
+                     int32_t transposed, int32_t epi, void* out, float* out_f32, uint8_t* idx_out, const uint8_t* idx_in,
+                     const float* mask, void* stream);
+/* dw[Cout][Cin][3][3] += sum_pixels dy (x) shifted x, db[Cout] += sum_pixels dy (db may be NULL): x [B][Cin/8][H][W][8],
+ * dy [B][Cout/8][H][W][8] bf16; GEMM with K = pixels on tcgen05, per-CTA partial tiles summed in fixed order by a second
+ * kernel.  workspace: cgs_wide_wgrad_workspace(B, H, W, Cout) floats.  Cin <= 40. */
+int cgs_wide_wgrad3x3(const void* x, const void* dy, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, float* dw, float* db,
+                      float* workspace, int64_t workspace_floats, void* stream);
+int64_t cgs_wide_wgrad_workspace(int32_t B, int32_t H, int32_t W, int32_t Cout);
+/* Non-zero if a wide kernel ever gave up on an mbarrier (reads a device flag; synchronises). */
+int cgs_wide_status(void);
+/* Debug only: clock64() of the MMA-issuing thread of CTA 0 (wait start, operands landed, MMAs issued) for its first 8 tiles. */
+int cgs_wide_set_trace(long long* dev_buf);
+
 /* ---- formats either side of the path, csrc/edges.cu ---------------------------------------------------
  * out[i] = dataset[idx[i]] for uint8 NHWC frames (12288 bytes each): `Xpos[Hidx]`, `Xneg[Lidx]`, `Xneg[Cidx]` of
  * main.py:345-353 over a device-resident dataset; indices are clamped to [0, nframes). */

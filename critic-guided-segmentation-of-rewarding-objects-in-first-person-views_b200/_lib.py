@@ -123,6 +123,14 @@ EXPORTS = {
                           C.c_void_p],
     "cgs_wide_wgrad_workspace": [C.c_int32, C.c_int32, C.c_int32, C.c_int32],
     "cgs_wide_status": [],
+    "cgs_wide_conv0_fwd": [_u8p, C.c_int32, C.c_int32, C.c_void_p, _f32p, _f32p, C.c_int32, C.c_void_p, _u8p, C.c_void_p],
+    "cgs_wide_conv0_wgrad": [_u8p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, _u8p, C.c_int32, _f32p, _f32p, _f32p, C.c_int64, C.c_void_p],
+    "cgs_wide_gemm": [_f32p, C.c_int32, C.c_int32, _f32p, C.c_int32, C.c_int32, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p,
+                      C.c_int32, C.c_int32, C.c_void_p],
+    "cgs_wide_head_mid": [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_float, C.c_int32, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
+                          C.c_void_p],
+    "cgs_wide_colsum2": [_f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_void_p],
+    "cgs_wide_unpool3": [_f32p, _u8p, _f32p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],
     "cgs_wide_set_trace": [C.c_void_p],
     "cgs_tc_set_trace": [C.c_void_p],
     "cgs_critic_fused_set_trace": [C.c_void_p],

@@ -251,10 +251,9 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
             }
             const size_t o = ((size_t)(n * CPo + cg) * H2 + y2) * W2 + x2;
             if (p.out) reinterpret_cast<uint4*>(p.out)[o] = make_uint4(pack2(res[0], res[1]), pack2(res[2], res[3]), pack2(res[4], res[5]), pack2(res[6], res[7]));
-            if (p.out_f32) {       // NHWC fp32 copy for the head (features.14 reads it as its K vector)
-              float4* of = reinterpret_cast<float4*>(p.out_f32 + ((size_t)(n * H2 + y2) * W2 + x2) * Cout + cg * 8);
-              of[0] = make_float4(res[0], res[1], res[2], res[3]);
-              of[1] = make_float4(res[4], res[5], res[6], res[7]);
+            if (p.out_f32) {       // NCHW fp32 copy for the head: features.14 reads a frame's [C][4][4] block as its K vector
+#pragma unroll
+              for (int c = 0; c < 8; ++c) p.out_f32[((size_t)(n * Cout + cg * 8 + c) * H2 + y2) * W2 + x2] = res[c];
             }
             reinterpret_cast<uint2*>(p.idx_out)[o] = make_uint2(ilo, ihi);
           }

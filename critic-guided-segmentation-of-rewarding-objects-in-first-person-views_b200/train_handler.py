@@ -21,7 +21,7 @@ from itertools import chain
 import numpy as np
 import torch
 
-from . import _lib, ops
+from . import _lib, ops, wide
 from .nets import NewCritic, UnetDecoder
 
 
@@ -258,6 +258,7 @@ class Handler:
         self.contrastive_batchsize = 32      # main.py:309
         self.fused_critic_step = True        # tf32 mode, chfak 1: one kernel per critic_pipe step
         self.critic_bf16 = os.environ.get("CGS_CRITIC_BF16", "1") != "0"   # critic step: bf16 operands (csrc/hg_critic.cu) instead of TF32 (csrc/critic_fused.cu)
+        self.wide_critic_step = True         # tensor-core mode, chfak 2..5: TMA-fed tcgen05 convolutions (csrc/wide_tc.cu, wide.py)
         self.hg_score_bf16 = True            # frozen Hourglass step: the three critic scoring passes in ONE bf16 kernel (else TF32)
         self.hg_inference = True             # tensor-core mode, chfak 1: -process in ONE bf16 kernel (csrc/hg_forward.cu)
         self.device_dataset = True           # segmentation_training gathers its batches from a device-resident uint8 dataset
@@ -375,6 +376,15 @@ class Handler:
                                              loss_grad=weight, bce=bool(a.threshrew), rng=rng,
                                              fuse_adam=bool(getattr(opti, "_clean", False)),
                                              bf16=self.critic_bf16 and isinstance(opti, FlatAdam))
+            opti.step()
+            return loss
+        if self.wide_critic_step and x.dtype == torch.uint8 and wide.supported(self.critic):
+            # chfak 2..5: bf16 chunk-planar activations, TMA-fed tcgen05 forward / input / weight gradients (wide.py)
+            rng = self.critic._dropout_rng(x.device)
+            masks = (None, None, None) if rng is not None else self.critic._dropout_masks(x.shape[0], x.device)
+            opti.zero_grad()
+            loss, _ = wide.critic_train_wide(self.critic, x.contiguous(), Yd.contiguous(), roll, masks,
+                                             loss_grad=weight, bce=bool(a.threshrew), rng=rng)
             opti.step()
             return loss
         pred = self.critic.forward_frames(x, roll).squeeze(1)     # cast + roll fused into features.0's operand load

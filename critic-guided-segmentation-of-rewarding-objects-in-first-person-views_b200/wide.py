@@ -32,7 +32,7 @@ def conv3x3(x, w, bias=None, epi=EPI_PLAIN, transposed=False, idx_in=None, mask=
     """3x3 / padding 1 convolution of a chunk-planar bf16 activation on the tcgen05 kernel.
     transposed=False: w [Cout, Cin, 3, 3] (nets.py:170-183 forward); transposed=True: w is the FORWARD weight [Cx, Cout, 3, 3] of the
     layer whose input gradient this is, x its output gradient with Cx channels.
-    Returns out (PLAIN / UNPOOL) or (out, idx[, out_f32 NHWC]) (RELU_POOL)."""
+    Returns out (PLAIN / UNPOOL) or (out, idx[, out_f32 NCHW]) (RELU_POOL)."""
     B, CPi, H, W, _ = x.shape
     Cin = CPi * 8
     Cout = w.shape[1] if transposed else w.shape[0]
@@ -43,7 +43,7 @@ def conv3x3(x, w, bias=None, epi=EPI_PLAIN, transposed=False, idx_in=None, mask=
         out = torch.empty((B, Cout // 8, H // 2, W // 2, 8), device=dev, dtype=torch.bfloat16)
         idx = torch.empty((B, Cout // 8, H // 2, W // 2, 8), device=dev, dtype=torch.uint8)
         if want_f32:
-            f32 = torch.empty((B, H // 2, W // 2, Cout), device=dev, dtype=torch.float32)
+            f32 = torch.empty((B, Cout, H // 2, W // 2), device=dev, dtype=torch.float32)
     elif epi == EPI_UNPOOL:
         out = torch.empty((B, Cout // 8, 2 * H, 2 * W, 8), device=dev, dtype=torch.bfloat16)
     else:
@@ -80,3 +80,103 @@ def wgrad3x3(x, dy, dw, db=None):
 
 def status_ok():
     return _lib.lib().cgs_wide_status() == 0
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# the rest of the wide critic step (csrc/wide_misc.cu) and its orchestration
+def conv0_fwd(frames_u8, roll, w0, b0):
+    """features.0 + ReLU + MaxPool on raw uint8 frames [B,64,64,3] (nets.py:170-172 after main.py:185-189's cast / shift):
+    returns (e0 [B, C0/8, 32, 32, 8] bf16, idx0 uint8)."""
+    B, C0, dev = frames_u8.shape[0], w0.shape[0], frames_u8.device
+    e0 = torch.empty((B, C0 // 8, 32, 32, 8), device=dev, dtype=torch.bfloat16)
+    idx0 = torch.empty((B, C0 // 8, 32, 32, 8), device=dev, dtype=torch.uint8)
+    rd, r = (_p(roll, torch.int32), 0) if torch.is_tensor(roll) else (None, int(roll or 0))
+    _call("cgs_wide_conv0_fwd", _p(frames_u8, torch.uint8), B, r, rd, _p(w0.detach()), _p(b0.detach()), C0, _bp(e0), _p(idx0, torch.uint8), _stream())
+    return e0, idx0
+
+
+def conv0_wgrad(frames_u8, roll, de0, idx0, dw0, db0):
+    """dw0 [C0,3,3,3] +=, db0 [C0] += from the pooled gradient de0 [B, C0/8, 32, 32, 8] and the arg-max bytes."""
+    B, C0 = frames_u8.shape[0], dw0.shape[0]
+    ws = _workspace(160 * 48 * C0, frames_u8.device)
+    rd, r = (_p(roll, torch.int32), 0) if torch.is_tensor(roll) else (None, int(roll or 0))
+    _call("cgs_wide_conv0_wgrad", _p(frames_u8, torch.uint8), B, r, rd, _bp(de0), _p(idx0, torch.uint8), C0, _p(dw0), _p(db0), _p(ws), ws.numel(),
+          _stream())
+
+
+def gemm(A, a_kc, Bm, b_kc, M, N, K, out=None, bias=None, gate=None, relu=False, accumulate=False):
+    """out[M, N] (+)= op(A) @ op(B) in TF32: A is [M, K] (a_kc) or [K, M]; B is [N, K] (b_kc) or [K, N], all row-major fp32."""
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    assert A.dim() == 2 and Bm.dim() == 2 and tuple(A.shape) == ((M, K) if a_kc else (K, M)) and tuple(Bm.shape) == ((N, K) if b_kc else (K, N))
+    _call("cgs_wide_gemm", _p(A), int(a_kc), A.shape[1], _p(Bm), int(b_kc), Bm.shape[1], _p(out), N, M, N, K, _p(bias), _p(gate), int(relu),
+          int(accumulate), _stream())
+    return out
+
+
+def supported(critic):
+    """The wide path covers NewCritic at chfak 2..5 (channel counts 8k, 8k, 8k, 16k, 32k with k <= 5) in the tensor-core mode."""
+    from . import ops
+    f = critic.features
+    c = [f[0].out_channels, f[3].out_channels, f[6].out_channels, f[10].out_channels, f[14].out_channels]
+    k = c[0] // 8
+    return bool(ops._precision) and 2 <= k <= 5 and c == [8 * k, 8 * k, 8 * k, 16 * k, 32 * k] and f[0].in_channels == 3
+
+
+def critic_train_wide(critic, frames_u8, target, roll=0, masks=(None, None, None), loss_grad=1.0, bce=False, rng=None):
+    """Forward + loss + backward of one critic_pipe step (reference main.py:185-198) for a wide NewCritic: features.0 and its
+    gradient on bf16 mma.sync, features.3 / .6 / .10 forward, input and weight gradients on TMA-fed tcgen05, the head as TF32 GEMMs.
+    The parameter gradients are ADDED to the parameters' `.grad` (fixed summation order: bit-reproducible).
+    masks: (m2 [B,8,8,C2], m3 [B,4,4,C3], mv [B,nb]) NHWC fp32 or Nones; rng = (p, seed, state): drawn from the module's Philox
+    stream by cgs_dropout_masks instead.  Returns (loss, pred [B])."""
+    from . import ops
+    params = list(critic.parameters())
+    assert len(params) == 14
+    w0, b0, w1, b1, w2, b2, w3, b3, w4, b4, wl1, bl1, wl2, bl2 = [q.detach() for q in params]
+    g = []
+    for q in params:
+        if q.grad is None:
+            q.grad = torch.zeros_like(q)
+        o = getattr(q, "_cgs_opt", None)
+        if o is not None and q.grad is getattr(q, "_cgs_grad", None):
+            o._clean = False
+        g.append(q.grad)
+    dw0, db0, dw1, db1, dw2, db2, dw3, db3, dw4, db4, dwl1, dbl1, dwl2, dbl2 = g
+    B, dev = frames_u8.shape[0], frames_u8.device
+    C2, C3, C4 = w2.shape[0], w3.shape[0], w4.shape[0]
+    K1 = 16 * C3
+    if rng is not None:
+        masks = ops.dropout_masks([(B, 8, 8, C2), (B, 4, 4, C3), (B, C4)], float(rng[0]), rng[1], rng[2])
+    m2, m3, mv = masks
+    # ---- forward
+    e0, idx0 = conv0_fwd(frames_u8, roll, w0, b0)
+    e1, idx1 = conv3x3(e0, w1, b1, EPI_RELU_POOL)
+    e2, idx2 = conv3x3(e1, w2, b2, EPI_RELU_POOL, mask=m2)
+    e3, idx3, e3f = conv3x3(e2, w3, b3, EPI_RELU_POOL, mask=m3, want_f32=True)
+    X3 = e3f.view(B, K1)
+    W4 = w4.reshape(C4, K1)
+    H1 = gemm(X3, True, W4, True, B, C4, K1, bias=b4, relu=True)                       # features.14 + ReLU (nets.py:186-187)
+    V = gemm(H1, True, wl1, True, B, C4, C4, bias=bl1, relu=True)                      # crit.1 + ReLU (nets.py:190-191)
+    pred = torch.empty(B, device=dev, dtype=torch.float32)
+    loss = torch.empty(1, device=dev, dtype=torch.float32)
+    dV = torch.empty((B, C4), device=dev, dtype=torch.float32)
+    dz = torch.empty(B, device=dev, dtype=torch.float32)
+    _call("cgs_wide_head_mid", _p(V), _p(mv), _p(wl2.reshape(-1)), _p(bl2), _p(target), B, C4, float(loss_grad), int(bool(bce)), _p(pred), _p(loss),
+          _p(dV), _p(dz), _p(dwl2.view(-1)), _p(dbl2), _stream())
+    # ---- backward: head
+    dH1 = gemm(dV, True, wl1, False, B, C4, C4, gate=H1)                               # through crit.1 and features.15's ReLU
+    gemm(dV, False, H1, False, C4, C4, B, out=dwl1, accumulate=True)
+    _call("cgs_wide_colsum2", _p(dV), _p(dbl1), _p(dH1), _p(db4), B, C4, _stream())
+    dE3 = gemm(dH1, True, W4, False, B, K1, C4)                                        # [B, C3, 4, 4]
+    gemm(dH1, False, X3, False, C4, K1, B, out=dw4.view(C4, K1), accumulate=True)
+    dY3 = torch.empty((B, C3 // 8, 8, 8, 8), device=dev, dtype=torch.bfloat16)
+    _call("cgs_wide_unpool3", _p(dE3), _p(idx3, torch.uint8), _p(m3), B, C3, _bp(dY3), _stream())
+    # ---- backward: the 3x3 convolutions
+    wgrad3x3(e2, dY3, dw3, db3)
+    dY2 = conv3x3(dY3, w3, epi=EPI_UNPOOL, transposed=True, idx_in=idx2, mask=m2)
+    wgrad3x3(e1, dY2, dw2, db2)
+    dY1 = conv3x3(dY2, w2, epi=EPI_UNPOOL, transposed=True, idx_in=idx1)
+    wgrad3x3(e0, dY1, dw1, db1)
+    dE0 = conv3x3(dY1, w1, transposed=True)
+    conv0_wgrad(frames_u8, roll, dE0, idx0, dw0, db0)
+    return loss.reshape(()), pred

@@ -383,7 +383,7 @@ int cgs_hg_set_trace_critic(long long* buf);
 enum {
   CGS_WIDE_EPI_PLAIN = 0,     /* out[B][Cout/8][H][W][8] = conv + bias */
   CGS_WIDE_EPI_RELU_POOL = 1, /* out[B][Cout/8][H/2][W/2][8] = maxpool2(relu(conv + bias)) [* mask]; idx_out = first-max position
-                                 0..3, or 4 where the pooled value is not > 0 (ReLU dead); out_f32: optional NHWC fp32 copy */
+                                 0..3, or 4 where the pooled value is not > 0 (ReLU dead); out_f32: optional NCHW fp32 copy */
   CGS_WIDE_EPI_UNPOOL = 2     /* the conv result is the gradient of a pooled map: out[B][Cout/8][2H][2W][8] receives it [* mask] at
                                  the window position idx_in names and zeros elsewhere (MaxPool + ReLU + Dropout backward) */
 };
@@ -399,6 +399,28 @@ int cgs_wide_conv3x3(const void* x, int32_t B, int32_t H, int32_t W, int32_t Cin
 int cgs_wide_wgrad3x3(const void* x, const void* dy, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, float* dw, float* db,
                       float* workspace, int64_t workspace_floats, void* stream);
 int64_t cgs_wide_wgrad_workspace(int32_t B, int32_t H, int32_t W, int32_t Cout);
+/* features.0 of the wide path (3 -> C0 on 64x64, bf16 mma.sync on the pair-duplicated frame): uint8 frames [B,64,64,3] -> /255 ->
+ * roll -> conv + ReLU + pool -> e0 [B][C0/8][32][32][8] bf16 + arg-max bytes; and its weight / bias gradient from the pooled
+ * gradient de0 (same layout) + arg-max bytes: dw0 [C0][3][3][3] +=, db0 [C0] += (workspace: 148 * 48 * C0 floats). */
+int cgs_wide_conv0_fwd(const uint8_t* frames, int32_t B, int32_t roll, const int32_t* roll_dev, const float* w0, const float* b0,
+                       int32_t C0, void* e0, uint8_t* idx0, void* stream);
+int cgs_wide_conv0_wgrad(const uint8_t* frames, int32_t B, int32_t roll, const int32_t* roll_dev, const void* de0, const uint8_t* idx0,
+                         int32_t C0, float* dw0, float* db0, float* workspace, int64_t workspace_floats, void* stream);
+/* C[M][N] (+)= op(A) op(B) in TF32 (fp32 accumulate): A[m*lda + k] (a_k_contiguous) or A[k*lda + m]; B[n*ldb + k]
+ * (b_k_contiguous) or B[k*ldb + n]; then + bias[n], zero where gate[m*ldc + n] <= 0, ReLU, accumulate.  The head's GEMMs:
+ * features.14 (a 4x4 valid conv on a 4x4 map, nets.py:186), crit.1 (nets.py:190) and their input / weight gradients. */
+int cgs_wide_gemm(const float* A, int32_t a_k_contiguous, int32_t lda, const float* Bm, int32_t b_k_contiguous, int32_t ldb, float* Cm,
+                  int32_t ldc, int32_t M, int32_t N, int32_t K, const float* bias, const float* gate, int32_t relu, int32_t accumulate,
+                  void* stream);
+/* crit.3 Dropout (mv or NULL), crit.4 Linear(nb, 1), Sigmoid, MSE / BCE (main.py:192-195) on V = crit.2's output [B][nb]:
+ * pred [B], loss (mean), dV = d loss / d V with loss scaled by loss_grad, dz [B] scratch, dwl2 [nb] +=, dbl2 [1] +=. */
+int cgs_wide_head_mid(const float* V, const float* mv, const float* wl2, const float* bl2, const float* target, int32_t B, int32_t nb,
+                      float loss_grad, int32_t bce, float* pred, float* loss, float* dV, float* dz, float* dwl2, float* dbl2, void* stream);
+/* out0[j] += sum_b X0[b][j], out1[j] += sum_b X1[b][j] (bias gradients of crit.1 / features.14), fixed order. */
+int cgs_wide_colsum2(const float* X0, float* out0, const float* X1, float* out1, int32_t B, int32_t n, void* stream);
+/* Gradient of features.13's output de3 [B][C3][4][4] fp32 -> Dropout (m3 NHWC or NULL) + MaxPool + ReLU backward (idx3 planar
+ * arg-max bytes) -> dy3 [B][C3/8][8][8][8] bf16, the output gradient of features.10. */
+int cgs_wide_unpool3(const float* de3, const uint8_t* idx3, const float* m3, int32_t B, int32_t C3, void* dy3, void* stream);
 /* Non-zero if a wide kernel ever gave up on an mbarrier (reads a device flag; synchronises). */
 int cgs_wide_status(void);
 /* Debug only: clock64() of the MMA-issuing thread of CTA 0 (wait start, operands landed, MMAs issued) for its first 8 tiles. */

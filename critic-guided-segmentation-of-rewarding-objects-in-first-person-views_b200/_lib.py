@@ -42,6 +42,16 @@ class MaskerWeights(C.Structure):
     _fields_ = [(n, _f32p) for n in ("wd0", "bd0", "wd1", "bd1", "wd2", "bd2", "wd3", "bd3", "wd4", "bd4", "wm0", "bm0", "wm2", "bm2")]
 
 
+class WidePackJob(C.Structure):
+    """cgs_wide_packjob"""
+    _fields_ = [("w", _f32p), ("out", C.c_void_p), ("Cin", C.c_int32), ("Cout", C.c_int32), ("transposed", C.c_int32)]
+
+
+class WideColJob(C.Structure):
+    """cgs_wide_coljob"""
+    _fields_ = [("X", _f32p), ("out", _f32p), ("n", C.c_int32), ("scale", C.c_float), ("accumulate", C.c_int32)]
+
+
 class AdamArgs(C.Structure):
     """cgs_adam_args"""
     _fields_ = [("p", _f32p), ("g", _f32p), ("m", _f32p), ("v", _f32p), ("lr", C.c_double), ("beta1", C.c_double),
@@ -117,8 +127,10 @@ EXPORTS = {
     "cgs_mask_images": [_f32p, _u8p, C.c_int32, _u8p, _u8p, C.c_int32, _u8p, _u8p, C.c_void_p],
     "cgs_saliency_normalize": [_f32p, _f32p, C.c_int32, C.c_int32, C.c_float, _f32p, _f32p, _u8p, _f32p, C.c_void_p],
     "cgs_tc_status": [],
-    "cgs_wide_conv3x3": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32,
+    "cgs_wide_conv3x3": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_void_p, _f32p, C.c_int32, C.c_int32, C.c_int32,
                          C.c_void_p, _f32p, _u8p, _u8p, _f32p, C.c_void_p],
+    "cgs_wide_pack": [C.c_void_p, C.c_int32, C.c_void_p],
+    "cgs_wide_packed_bytes": [C.c_int32, C.c_int32],
     "cgs_wide_wgrad3x3": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _f32p, C.c_int64,
                           C.c_void_p],
     "cgs_wide_wgrad_workspace": [C.c_int32, C.c_int32, C.c_int32, C.c_int32],
@@ -126,10 +138,10 @@ EXPORTS = {
     "cgs_wide_conv0_fwd": [_u8p, C.c_int32, C.c_int32, C.c_void_p, _f32p, _f32p, C.c_int32, C.c_void_p, _u8p, C.c_void_p],
     "cgs_wide_conv0_wgrad": [_u8p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, _u8p, C.c_int32, _f32p, _f32p, _f32p, C.c_int64, C.c_void_p],
     "cgs_wide_gemm": [_f32p, C.c_int32, C.c_int32, _f32p, C.c_int32, C.c_int32, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p,
-                      C.c_int32, C.c_int32, C.c_void_p],
-    "cgs_wide_head_mid": [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_float, C.c_int32, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
+                      C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_void_p, C.c_void_p],
+    "cgs_wide_head_mid": [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_float, C.c_int32, _f32p, _f32p, _f32p, _f32p, _f32p,
                           C.c_void_p],
-    "cgs_wide_colsum2": [_f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_void_p],
+    "cgs_wide_colsums": [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p],
     "cgs_wide_unpool3": [_f32p, _u8p, _f32p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],
     "cgs_wide_set_trace": [C.c_void_p],
     "cgs_tc_set_trace": [C.c_void_p],

@@ -186,15 +186,18 @@ __global__ void __launch_bounds__(NT, 1) wide_conv0_wgrad_kernel(const uint8_t* 
 }
 
 __global__ void wide_conv0_reduce_kernel(const float* __restrict__ part, int ncta, int C0, float* __restrict__ dw, float* __restrict__ db) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;      // one warp per element, lanes over the CTAs
   if (e >= 3 * 16 * C0) return;
   const int co = e % C0, m = (e / C0) & 15, ky = e / (C0 * 16), kx = m >> 2, c = m & 3;
   const bool is_w = kx < 3 && c < 3, is_b = (ky == 1 && kx == 1 && c == 3);
   if (!is_w && !is_b) return;
   float s = 0.f;
-  for (int i = 0; i < ncta; ++i) s += part[(size_t)i * 48 * C0 + e];
-  if (is_w) dw[((co * 3 + c) * 3 + ky) * 3 + kx] += s;
-  else db[co] += s;
+  for (int i = lane; i < ncta; i += 32) s += part[(size_t)i * 48 * C0 + e];
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (is_w) dw[((co * 3 + c) * 3 + ky) * 3 + kx] += s;
+    else db[co] += s;
+  }
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -205,6 +208,9 @@ struct GemmP {
   const float *A, *B, *bias, *gate;
   float* C;
   int M, N, K, lda, ldb, ldc, relu, accumulate;
+  int splits;                      // gridDim.z: K is cut into `splits` runs of k-tiles; partial tiles meet in ws, the last CTA of a tile sums them
+  float* ws;                       // [splits][M][N]
+  int* counters;                   // one per (tile x, tile y), zero between launches (the last CTA resets its own)
 };
 constexpr int GM = 64, GN = 32, GK = 32, GST = 3;
 constexpr int GA_FLOATS = 2304, GB_FLOATS = 1280;    // [64][36] or [32][72]; [32][36] or [32][40]
@@ -225,9 +231,10 @@ __global__ void __launch_bounds__(128) wide_gemm_kernel(const GemmP p) {
   __shared__ __align__(16) float sB[GST][GB_FLOATS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
-  const int nk = (p.K + GK - 1) / GK;
+  const int nk_all = (p.K + GK - 1) / GK, per = (nk_all + p.splits - 1) / p.splits;
+  const int kt0 = blockIdx.z * per, nk = max(0, min(per, nk_all - kt0));
   auto load = [&](int kt, int st) {
-    const int k0 = kt * GK;
+    const int k0 = (kt0 + kt) * GK;
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(sA[st]), b = (uint32_t)__cvta_generic_to_shared(sB[st]);
     if (AKC) {                                       // [64 m][32 k] -> 8 chunks per row
       for (int c = tid; c < 512; c += 128) {
@@ -289,6 +296,39 @@ __global__ void __launch_bounds__(128) wide_gemm_kernel(const GemmP p) {
     }
   }
   cp_async_wait_all();
+  if (p.splits > 1) {
+    // partial tile -> ws[z]; the last CTA to arrive for this (x, y) tile sums the `splits` partials in order z = 0, 1, ...
+    float* mine = p.ws + (size_t)blockIdx.z * p.M * p.N;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int m = m0 + warp * 16 + g + 8 * (q >> 1), n = n0 + nt * 8 + 2 * t + (q & 1);
+        if (m < p.M && n < p.N) __stcg(mine + (size_t)m * p.N + n, acc[nt][q]);
+      }
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      int* ctr = p.counters + blockIdx.y * gridDim.x + blockIdx.x;
+      const int prev = atomicAdd(ctr, 1);
+      s_last = (prev == p.splits - 1);
+      if (s_last) *ctr = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int m = m0 + warp * 16 + g + 8 * (q >> 1), n = n0 + nt * 8 + 2 * t + (q & 1);
+        float v = 0.f;
+        if (m < p.M && n < p.N)
+          for (int z = 0; z < p.splits; ++z) v += __ldcg(p.ws + ((size_t)z * p.M + m) * p.N + n);
+        acc[nt][q] = v;
+      }
+  }
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
@@ -305,66 +345,68 @@ __global__ void __launch_bounds__(128) wide_gemm_kernel(const GemmP p) {
     }
 }
 
-// ---- crit.3 Dropout, crit.4 Linear(nb, 1), Sigmoid, MSE / BCE and everything that hangs on the scalar gradient (one CTA):
-// pred, loss, dV = d loss / d(crit.1 output) (ReLU and dropout applied), dwl2 += , dbl2 +=
-__global__ void __launch_bounds__(1024) wide_head_mid_kernel(const float* __restrict__ V, const float* __restrict__ mv, const float* __restrict__ wl2,
-                                                             const float* __restrict__ bl2, const float* __restrict__ target, int B, int nb,
-                                                             float gscale, float inv_n, int bce, float* __restrict__ pred, float* __restrict__ loss,
-                                                             float* __restrict__ dV, float* __restrict__ dz_out, float* __restrict__ dwl2,
-                                                             float* __restrict__ dbl2) {
-  __shared__ float s_loss[32], s_dz[32];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float lacc = 0.f, dzacc = 0.f;
-  for (int b = warp; b < B; b += 32) {
-    float s = 0.f;
-    for (int j = lane; j < nb; j += 32) s += __ldg(wl2 + j) * V[(size_t)b * nb + j] * (mv ? __ldg(mv + (size_t)b * nb + j) : 1.f);
-    const float z = warp_sum(s) + __ldg(bl2), pr = sigmoidf_(z), y = __ldg(target + b);
-    float dl;
-    if (bce) {
-      lacc -= y * fmaxf(logf(pr), -100.f) + (1.f - y) * fmaxf(logf(1.f - pr), -100.f);
-      dl = gscale * (pr - y) / fmaxf(pr * (1.f - pr), 1e-12f) * pr * (1.f - pr);
-    } else {
-      lacc = fmaf(pr - y, pr - y, lacc);
-      dl = gscale * 2.f * (pr - y) * pr * (1.f - pr);
-    }
-    dzacc += dl;
-    if (lane == 0) { pred[b] = pr; dz_out[b] = dl; }
-    for (int j = lane; j < nb; j += 32) {
-      const float v = V[(size_t)b * nb + j], m = mv ? __ldg(mv + (size_t)b * nb + j) : 1.f;
-      dV[(size_t)b * nb + j] = v > 0.f ? dl * __ldg(wl2 + j) * m : 0.f;
-    }
+// ---- crit.3 Dropout, crit.4 Linear(nb, 1), Sigmoid, MSE / BCE per frame (one warp per frame): pred, the frame's loss term, dz = d loss
+// / d logit, dV = d loss / d(crit.1 output) (ReLU and dropout applied) and U = dz * V * mask (whose column sum is crit.4's gradient)
+__global__ void __launch_bounds__(256) wide_head_mid_kernel(const float* __restrict__ V, const float* __restrict__ mv, const float* __restrict__ wl2,
+                                                            const float* __restrict__ bl2, const float* __restrict__ target, int B, int nb,
+                                                            float gscale, int bce, float* __restrict__ pred, float* __restrict__ lterm,
+                                                            float* __restrict__ dV, float* __restrict__ dz_out, float* __restrict__ U) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int j = lane; j < nb; j += 32) s += __ldg(wl2 + j) * __ldg(V + (size_t)b * nb + j) * (mv ? __ldg(mv + (size_t)b * nb + j) : 1.f);
+  const float z = warp_sum(s) + __ldg(bl2), pr = sigmoidf_(z), y = __ldg(target + b);
+  float dl, lt;
+  if (bce) {
+    lt = -(y * fmaxf(logf(pr), -100.f) + (1.f - y) * fmaxf(logf(1.f - pr), -100.f));
+    dl = gscale * (pr - y) / fmaxf(pr * (1.f - pr), 1e-12f) * pr * (1.f - pr);
+  } else {
+    lt = (pr - y) * (pr - y);
+    dl = gscale * 2.f * (pr - y) * pr * (1.f - pr);
   }
-  if (lane == 0) { s_loss[warp] = lacc; s_dz[warp] = dzacc; }
-  __syncthreads();
-  if (tid == 0) {
-    float l = 0.f, d = 0.f;
-    for (int w = 0; w < 32; ++w) { l += s_loss[w]; d += s_dz[w]; }
-    *loss = l * inv_n;
-    *dbl2 += d;
-  }
-  __threadfence_block();
-  __syncthreads();
-  for (int j = tid; j < nb; j += 1024) {             // dwl2[j] += sum_b dz_b * V[b][j] * mv[b][j], fixed order
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s += dz_out[b] * V[(size_t)b * nb + j] * (mv ? __ldg(mv + (size_t)b * nb + j) : 1.f);
-    dwl2[j] += s;
+  if (lane == 0) { pred[b] = pr; dz_out[b] = dl; lterm[b] = lt; }
+  for (int j = lane; j < nb; j += 32) {
+    const float v = __ldg(V + (size_t)b * nb + j), m = mv ? __ldg(mv + (size_t)b * nb + j) : 1.f;
+    dV[(size_t)b * nb + j] = v > 0.f ? dl * __ldg(wl2 + j) * m : 0.f;
+    U[(size_t)b * nb + j] = dl * v * m;
   }
 }
 
-// out[j] += sum_b X[b][j] for two matrices (blockIdx.y): the bias gradients of crit.1 and features.14
-__global__ void wide_colsum2_kernel(const float* __restrict__ X0, float* __restrict__ out0, const float* __restrict__ X1, float* __restrict__ out1,
-                                    int B, int n) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const float* X = blockIdx.y ? X1 : X0;
-  float* out = blockIdx.y ? out1 : out0;
+// up to 5 column sums in one launch (blockIdx.y = job): out[j] (+)= scale * sum_b X[b][j].  Block (32 columns x 8 row groups): the
+// row groups run independent loads, then meet in shared memory in fixed order.
+struct ColJob {
+  const float* X;
+  float* out;
+  int n;
+  float scale;
+  int accumulate;
+};
+struct ColJobs {
+  ColJob j[5];
+};
+__global__ void __launch_bounds__(256) wide_colsums_kernel(const ColJobs jobs, int B) {
+  __shared__ float sm[8][33];
+  const ColJob jb = jobs.j[blockIdx.y];
+  const int c = threadIdx.x & 31, r = threadIdx.x >> 5, col = blockIdx.x * 32 + c;
+  if (blockIdx.x * 32 >= jb.n) return;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int b = 0;
-  for (; b + 4 <= B; b += 4) {
-    s0 += X[(size_t)b * n + j]; s1 += X[(size_t)(b + 1) * n + j]; s2 += X[(size_t)(b + 2) * n + j]; s3 += X[(size_t)(b + 3) * n + j];
+  if (col < jb.n) {
+    int b = r;
+    for (; b + 24 < B; b += 32) {
+      s0 += __ldg(jb.X + (size_t)b * jb.n + col); s1 += __ldg(jb.X + (size_t)(b + 8) * jb.n + col);
+      s2 += __ldg(jb.X + (size_t)(b + 16) * jb.n + col); s3 += __ldg(jb.X + (size_t)(b + 24) * jb.n + col);
+    }
+    for (; b < B; b += 8) s0 += __ldg(jb.X + (size_t)b * jb.n + col);
   }
-  for (; b < B; ++b) s0 += X[(size_t)b * n + j];
-  out[j] += (s0 + s1) + (s2 + s3);
+  sm[r][c] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (r == 0 && col < jb.n) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += sm[i][c];
+    s *= jb.scale;
+    jb.out[col] = jb.accumulate ? jb.out[col] + s : s;
+  }
 }
 
 // d e3 [B][C3][4][4] fp32 -> Dropout + MaxPool + ReLU backward -> dY3 [B][C3/8][8][8][8] bf16 (features.10's output gradient)
@@ -421,18 +463,19 @@ extern "C" int cgs_wide_conv0_wgrad(const uint8_t* frames, int32_t B, int32_t ro
   int rc = check_launch("wide_conv0_wgrad");
   if (rc) return rc;
   const int n = 48 * C0;
-  wm::wide_conv0_reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, grid, C0, dw0, db0);
+  wm::wide_conv0_reduce_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(workspace, grid, C0, dw0, db0);
   return check_launch("wide_conv0_wgrad.reduce");
 }
 
 extern "C" int cgs_wide_gemm(const float* A, int32_t a_k_contiguous, int32_t lda, const float* Bm, int32_t b_k_contiguous, int32_t ldb, float* Cm,
                              int32_t ldc, int32_t M, int32_t N, int32_t K, const float* bias, const float* gate, int32_t relu, int32_t accumulate,
-                             void* stream) {
+                             int32_t splits, float* ws, int32_t* counters, void* stream) {
   CGS_REQUIRE(A && Bm && Cm && M > 0 && N > 0 && K > 0, "wide_gemm: bad args");
   CGS_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (((uintptr_t)A | (uintptr_t)Bm) & 15) == 0, "wide_gemm: operands must be 16-byte aligned rows");
   CGS_REQUIRE(((a_k_contiguous ? K : M) % 4) == 0 && ((b_k_contiguous ? K : N) % 4) == 0, "wide_gemm: contiguous extents must be multiples of 4");
-  wm::GemmP p{A, Bm, bias, gate, Cm, M, N, K, lda, ldb, ldc, relu, accumulate};
-  const dim3 grid((N + wm::GN - 1) / wm::GN, (M + wm::GM - 1) / wm::GM);
+  const dim3 grid((N + wm::GN - 1) / wm::GN, (M + wm::GM - 1) / wm::GM, splits > 1 ? splits : 1);
+  CGS_REQUIRE(splits <= 1 || (ws && counters && grid.x * grid.y <= 4096), "wide_gemm: split-K needs a workspace [splits][M][N] and <= 4096 counters");
+  wm::GemmP p{A, Bm, bias, gate, Cm, M, N, K, lda, ldb, ldc, relu, accumulate, (int)grid.z, ws, counters};
   cudaStream_t st = (cudaStream_t)stream;
   if (a_k_contiguous && b_k_contiguous) wm::wide_gemm_kernel<true, true><<<grid, 128, 0, st>>>(p);
   else if (a_k_contiguous) wm::wide_gemm_kernel<true, false><<<grid, 128, 0, st>>>(p);
@@ -442,18 +485,24 @@ extern "C" int cgs_wide_gemm(const float* A, int32_t a_k_contiguous, int32_t lda
 }
 
 extern "C" int cgs_wide_head_mid(const float* V, const float* mv, const float* wl2, const float* bl2, const float* target, int32_t B, int32_t nb,
-                                 float loss_grad, int32_t bce, float* pred, float* loss, float* dV, float* dz, float* dwl2, float* dbl2,
-                                 void* stream) {
-  CGS_REQUIRE(V && wl2 && bl2 && target && pred && loss && dV && dz && dwl2 && dbl2 && B > 0 && nb > 0, "wide_head_mid: bad args");
-  wm::wide_head_mid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(V, mv, wl2, bl2, target, B, nb, loss_grad / (float)B, 1.f / (float)B, bce, pred,
-                                                                 loss, dV, dz, dwl2, dbl2);
+                                 float loss_grad, int32_t bce, float* pred, float* lterm, float* dV, float* dz, float* U, void* stream) {
+  CGS_REQUIRE(V && wl2 && bl2 && target && pred && lterm && dV && dz && U && B > 0 && nb > 0, "wide_head_mid: bad args");
+  wm::wide_head_mid_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(V, mv, wl2, bl2, target, B, nb, loss_grad / (float)B, bce, pred, lterm, dV,
+                                                                          dz, U);
   return check_launch("wide_head_mid");
 }
 
-extern "C" int cgs_wide_colsum2(const float* X0, float* out0, const float* X1, float* out1, int32_t B, int32_t n, void* stream) {
-  CGS_REQUIRE(X0 && out0 && X1 && out1 && B > 0 && n > 0, "wide_colsum2: bad args");
-  wm::wide_colsum2_kernel<<<dim3((n + 127) / 128, 2), 128, 0, (cudaStream_t)stream>>>(X0, out0, X1, out1, B, n);
-  return check_launch("wide_colsum2");
+extern "C" int cgs_wide_colsums(const cgs_wide_coljob* jobs, int32_t njobs, int32_t B, void* stream) {
+  CGS_REQUIRE(jobs && njobs >= 1 && njobs <= 5 && B > 0, "wide_colsums: 1..5 jobs");
+  wm::ColJobs js;
+  int maxn = 0;
+  for (int i = 0; i < njobs; ++i) {
+    CGS_REQUIRE(jobs[i].X && jobs[i].out && jobs[i].n > 0, "wide_colsums: bad job %d", i);
+    js.j[i] = wm::ColJob{jobs[i].X, jobs[i].out, jobs[i].n, jobs[i].scale, jobs[i].accumulate};
+    if (jobs[i].n > maxn) maxn = jobs[i].n;
+  }
+  wm::wide_colsums_kernel<<<dim3((maxn + 31) / 32, njobs), 256, 0, (cudaStream_t)stream>>>(js, B);
+  return check_launch("wide_colsums");
 }
 
 extern "C" int cgs_wide_unpool3(const float* de3, const uint8_t* idx3, const float* m3, int32_t B, int32_t C3, void* dy3, void* stream) {

@@ -1,7 +1,7 @@
 // The wide (chfak > 1) convolution kernels: TMA-fed tcgen05 / TMEM implicit GEMMs with bf16 operands, fp32 accumulation.
 //
 // Activations live in HBM "chunk-planar": [B][C/8][H][W][8 channels] bf16, so that one pixel's 8 channels of a plane are one
-// 16-byte slot.  A TMA box (8, bw, bh, planes, 1) of the 5-D view (8, W, H, C/8, B) lands in shared memory as
+// 16-byte slot.  A TMA box (8 bw, bh, planes, 1) of the 4-D view (8 W, H, C/8, B) lands in shared memory as
 // [plane][bh][bw][16 B], which is at once
 //   * the UMMA no-swizzle K-MAJOR canonical layout ((8,m),(8,2)):((16 B,SBO),(1,LBO)) with a core matrix = 8 horizontally
 //     adjacent pixels of one plane, SBO = one tile row and LBO = one plane: the A operand (rows = pixels, K = channels) of the
@@ -13,7 +13,7 @@
 //     Three TMA loads put the kx = 0, 1, 2 shifts of the input tile into planes [kx][ci / 8] of ONE 128-row A operand (plane 15
 //     holds ones: the bias gradient rides along), so a tile costs 3 (ky) x 8 (row pairs) MMAs of 128 x Cout x 16.
 //
-// Both kernels are persistent and warp-specialised: warp 0 = TMA producer (one thread, `cp.async.bulk.tensor.5d` + mbarrier
+// Both kernels are persistent and warp-specialised: warp 0 = TMA producer (one thread, `cp.async.bulk.tensor.4d` + mbarrier
 // expect_tx, 3-4 stage ring), warp 1 = MMA issuer (one thread, `tcgen05.mma.cta_group::1.kind::f16`, `tcgen05.commit` frees
 // the stage / publishes the accumulator), warps 2-5 = epilogue (tcgen05.ld of their TMEM lane quarter; bias + ReLU + 2x2
 // max-pool + first-max arg-max + dropout mask, or the pool / ReLU / dropout BACKWARD scatter, written as bf16 planes).
@@ -85,15 +85,44 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   atomicExch(&g_wd_timeout, 1);
   return false;
 }
-__device__ __forceinline__ void tma_load5(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+// box (8 * bw, bh, planes, 1) of the 4-D view (8 * W, H, C/8, B): x in pixels, every box row one contiguous run of 16 * bw bytes
+__device__ __forceinline__ void tma_load4(uint32_t dst, const CUtensorMap* tm, int x, int y, int plane, int n, uint32_t bar) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(dst),
-      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(dst),
+      "l"(tm), "r"(8 * x), "r"(y), "r"(plane), "r"(n), "r"(bar)
       : "memory");
 }
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// one 16-byte row of the packed B operand: 8 input channels (ci = q * 8 ..) of output channel co at filter tap t
+__device__ __forceinline__ uint4 pack_row(const float* __restrict__ w, int r, int KP, int NP, int Cin, int Cout, int transposed) {
+  const int co = r % NP, tq = r / NP, q = tq % KP, t = tq / KP;
+  float v[8];
+#pragma unroll
+  for (int c8 = 0; c8 < 8; ++c8) {
+    const int ci = q * 8 + c8;
+    v[c8] = 0.f;
+    if (ci < Cin && co < Cout) v[c8] = transposed ? __ldg(w + ((size_t)ci * Cout + co) * 9 + (8 - t)) : __ldg(w + ((size_t)co * Cin + ci) * 9 + t);
+  }
+  return make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+}
+
+struct PackJob {
+  const float* w;
+  uint4* out;
+  int Cin, Cout, transposed;       // GEMM view, as in cgs_wide_conv3x3
+};
+struct PackJobs {
+  PackJob j[8];
+};
+// all operand tiles of a step in one launch (blockIdx.y = job): the filters change with every optimizer step
+__global__ void wide_pack_kernel(const PackJobs jobs) {
+  const PackJob jb = jobs.j[blockIdx.y];
+  const int KP = ((jb.Cin >> 3) + 1) & ~1, NP = (jb.Cout + 15) & ~15, rows = 9 * KP * NP;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) jb.out[r] = pack_row(jb.w, r, KP, NP, jb.Cin, jb.Cout, jb.transposed);
 }
 
 struct ConvP {
@@ -102,6 +131,7 @@ struct ConvP {
   int tiles_x, tiles_y, ntiles, stages, tmem_cols, epi, transposed;
   uint32_t idesc;
   const float* w;
+  const uint4* wpacked;            // [9][KP][NP] x 16 B operand rows (wide_pack_kernel), or NULL: packed here from w
   const float* bias;
   __nv_bfloat16* out;
   uint8_t* idx_out;
@@ -135,17 +165,10 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
   {
     // B operand (K-major): element (tap, ci, co) -> [(tap * KP + ci / 8) * NP + co] x 16 B + (ci % 8) x 2 B, zero padded
     const int rows = 9 * KP * NP;
-    for (int r = tid; r < rows; r += NTHR) {
-      const int co = r % NP, tq = r / NP, q = tq % KP, t = tq / KP;
-      float v[8];
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        const int ci = q * 8 + c8;
-        v[c8] = 0.f;
-        if (ci < p.Cin && co < p.Cout)
-          v[c8] = p.transposed ? __ldg(p.w + ((size_t)ci * p.Cout + co) * 9 + (8 - t)) : __ldg(p.w + ((size_t)co * p.Cin + ci) * 9 + t);
-      }
-      *reinterpret_cast<uint4*>(s_w + (size_t)r * 16) = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+    if (p.wpacked) {
+      for (int r = tid; r < rows; r += NTHR) reinterpret_cast<uint4*>(s_w)[r] = __ldg(p.wpacked + r);
+    } else {
+      for (int r = tid; r < rows; r += NTHR) reinterpret_cast<uint4*>(s_w)[r] = pack_row(p.w, r, KP, NP, p.Cin, p.Cout, p.transposed);
     }
     // the pad plane of every stage (Cin / 8 odd) is read by the last MMA of a tap: its weights are zero, the plane must be finite
     if (KP > p.CPi)
@@ -159,6 +182,7 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
   const uint32_t tmem_base = *s_tmem;
   const int tpf = p.tiles_x * p.tiles_y;
   long long* trace = (blockIdx.x == 0) ? g_wd_trace : nullptr;
+  if (trace && tid == 0) trace[63] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer
@@ -169,7 +193,7 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
         if (!mbar_wait(bEmpty + 8 * s, (k & 1) ^ 1)) break;
         const int n = tile / tpf, r = tile - n * tpf, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
         mbar_expect_tx(bFull + 8 * s, a_tx);
-        tma_load5(smem_u32(s_a + (size_t)s * a_bytes), &tmx, 0, tx * TW - 1, ty * TH - 1, 0, n, bFull + 8 * s);
+        tma_load4(smem_u32(s_a + (size_t)s * a_bytes), &tmx, tx * TW - 1, ty * TH - 1, 0, n, bFull + 8 * s);
       }
     }
   } else if (warp == 1) {
@@ -179,10 +203,11 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
       int it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int s = it % p.stages, k = it / p.stages, ab = it & 1, j = it >> 1;
-        if (trace && it < 8) trace[it * 4 + 0] = clock64();
+        if (trace && it < 8) trace[it * 8 + 0] = clock64();
         if (!mbar_wait(bTEmpty + 8 * ab, (j & 1) ^ 1)) break;
+        if (trace && it < 8) trace[it * 8 + 1] = clock64();
         if (!mbar_wait(bFull + 8 * s, k & 1)) break;
-        if (trace && it < 8) trace[it * 4 + 1] = clock64();
+        if (trace && it < 8) trace[it * 8 + 2] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const uint32_t a0 = smem_u32(s_a + (size_t)s * a_bytes), td = tmem_base + (uint32_t)(ab * NP);
         uint32_t acc = 0;
@@ -197,7 +222,7 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
         }
         umma_commit(bEmpty + 8 * s);              // the stage is free once these MMAs have read it
         umma_commit(bTFull + 8 * ab);             // ... and the accumulator is complete
-        if (trace && it < 8) trace[it * 4 + 2] = clock64();
+        if (trace && it < 8) trace[it * 8 + 3] = clock64();
       }
     }
   } else {
@@ -208,7 +233,9 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int ab = it & 1, j = it >> 1;
+      if (trace && it < 8 && tid == 64) trace[it * 8 + 4] = clock64();
       if (!mbar_wait(bTFull + 8 * ab, j & 1)) break;
+      if (trace && it < 8 && tid == 64) trace[it * 8 + 5] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const int n = tile / tpf, r = tile - n * tpf, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       const int y = ty * TH + yl, x = tx * TW + xl;
@@ -296,6 +323,7 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bTEmpty + 8 * ab);
+      if (trace && it < 8 && tid == 64) trace[it * 8 + 6] = clock64();
     }
   }
 
@@ -364,8 +392,8 @@ __global__ void __launch_bounds__(NTHR, 1) wide_wgrad_kernel(const __grid_consta
         mbar_expect_tx(bFull + 8 * s, tx_bytes);
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx)
-          tma_load5(a0 + (uint32_t)(kx * p.CPi) * A3_PLANE, &tmx, 0, tx * TW - 1 + kx, ty * TH - 1, 0, n, bFull + 8 * s);
-        tma_load5(a0 + A3_BYTES, &tmdy, 0, tx * TW, ty * TH, 0, n, bFull + 8 * s);
+          tma_load4(a0 + (uint32_t)(kx * p.CPi) * A3_PLANE, &tmx, tx * TW - 1 + kx, ty * TH - 1, 0, n, bFull + 8 * s);
+        tma_load4(a0 + A3_BYTES, &tmdy, tx * TW, ty * TH, 0, n, bFull + 8 * s);
       }
     }
   } else if (warp == 1) {
@@ -409,31 +437,38 @@ __global__ void __launch_bounds__(NTHR, 1) wide_wgrad_kernel(const __grid_consta
   }
 }
 
-// dW[co][ci][ky][kx] += sum over CTAs of P[cta][ky][kx * Cin + ci][co]; db[co] += sum of P[cta][1][120][co] (the ones plane)
+// dW[co][ci][ky][kx] += sum over CTAs of P[cta][ky][kx * Cin + ci][co]; db[co] += sum of P[cta][1][120][co] (the ones plane).
+// One warp per 4 consecutive elements: the lanes split the CTAs (independent 16-byte loads), then a fixed butterfly: deterministic.
 __global__ void wide_wgrad_reduce_kernel(const float* __restrict__ part, int ncta, int NP, int Cin, int Cout, float* __restrict__ dw,
                                          float* __restrict__ db) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= 3 * 128 * NP) return;
-  const int co = e % NP, m = (e / NP) & 127, ky = e / (NP * 128);
-  if (co >= Cout) return;
+  const int e4 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int total4 = 3 * 128 * NP / 4;
+  if (e4 >= total4) return;
+  const int e = e4 * 4, co0 = e % NP, m = (e / NP) & 127, ky = e / (NP * 128);
   const bool is_w = m < 3 * Cin, is_b = (m == 120 && ky == 1 && db != nullptr);
-  if (!is_w && !is_b) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int c = 0;
-  const size_t stride = (size_t)3 * 128 * NP;
-  for (; c + 4 <= ncta; c += 4) {
-    s0 += part[(size_t)c * stride + e];
-    s1 += part[(size_t)(c + 1) * stride + e];
-    s2 += part[(size_t)(c + 2) * stride + e];
-    s3 += part[(size_t)(c + 3) * stride + e];
+  if ((!is_w && !is_b) || co0 >= Cout) return;                 // whole warp: same e4
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* p4 = reinterpret_cast<const float4*>(part) + e4;
+  for (int c = lane; c < ncta; c += 32) {
+    const float4 v = __ldg(p4 + (size_t)c * total4);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
-  for (; c < ncta; ++c) s0 += part[(size_t)c * stride + e];
-  const float s = (s0 + s1) + (s2 + s3);
-  if (is_w) {
-    const int kx = m / Cin, ci = m - kx * Cin;
-    dw[((size_t)(co * Cin + ci) * 3 + ky) * 3 + kx] += s;
-  } else {
-    db[co] += s;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s.x += __shfl_xor_sync(0xffffffffu, s.x, o); s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+    s.z += __shfl_xor_sync(0xffffffffu, s.z, o); s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+  }
+  if (lane < 4) {
+    const int co = co0 + lane;
+    const float v = lane == 0 ? s.x : lane == 1 ? s.y : lane == 2 ? s.z : s.w;
+    if (co < Cout) {
+      if (is_w) {
+        const int kx = m / Cin, ci = m - kx * Cin;
+        dw[((size_t)(co * Cin + ci) * 3 + ky) * 3 + kx] += v;
+      } else {
+        db[co] += v;
+      }
+    }
   }
 }
 
@@ -451,18 +486,18 @@ static EncodeFn encode_fn() {
   return f;
 }
 
-// 5-D view (8, W, H, C/8, B) of a chunk-planar bf16 tensor; box (8, bw, bh, planes, 1); out-of-bounds elements read as zero
+// 4-D view (8 * W, H, C/8, B) of a chunk-planar bf16 tensor; box (8 * bw, bh, planes, 1); out-of-bounds elements read as zero
 int make_tmap(CUtensorMap* tm, const void* base, int B, int CP, int H, int W, int bw, int bh, int planes) {
   EncodeFn enc = encode_fn();
   if (!enc) {
     set_error("wide: cuTensorMapEncodeTiled is not available from this driver");
     return CGS_ECUDA;
   }
-  const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)CP, (cuuint64_t)B};
-  const cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)CP * H * W * 16};
-  const cuuint32_t box[5] = {8, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)planes, 1};
-  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)CP, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)CP * H * W * 16};
+  const cuuint32_t box[4] = {(cuuint32_t)bw * 8, (cuuint32_t)bh, (cuuint32_t)planes, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("wide: cuTensorMapEncodeTiled failed (%d) for B=%d CP=%d H=%d W=%d box=(%d,%d,%d)", (int)r, B, CP, H, W, bw, bh, planes);
@@ -477,9 +512,10 @@ static int pow2_cols(int c) {
   return t;
 }
 
-int launch_wide_conv(const void* x, int B, int H, int W, int Cin, const float* w, const float* bias, int Cout, int transposed, int epi,
+int launch_wide_conv(const void* x, int B, int H, int W, int Cin, const float* w, const void* wpacked, const float* bias, int Cout, int transposed, int epi,
                      void* out, float* out_f32, uint8_t* idx_out, const uint8_t* idx_in, const float* mask, cudaStream_t st) {
-  CGS_REQUIRE(x && w && (out || out_f32) && B > 0, "wide_conv3x3: bad args");
+  CGS_REQUIRE(x && (w || wpacked) && (out || out_f32) && B > 0, "wide_conv3x3: bad args");
+  CGS_REQUIRE(((uintptr_t)wpacked & 15) == 0, "wide_conv3x3: packed weights must be 16-byte aligned");
   CGS_REQUIRE((Cin % 8) == 0 && (Cout % 8) == 0 && Cin >= 8 && Cout >= 8 && Cin <= 160 && Cout <= 240, "wide_conv3x3: channels must be multiples of 8 (Cin %d, Cout %d)", Cin, Cout);
   CGS_REQUIRE((W % TW) == 0 && (H % 8) == 0 && H >= 8, "wide_conv3x3: H x W = %d x %d unsupported", H, W);
   CGS_REQUIRE(epi != CGS_WIDE_EPI_RELU_POOL || idx_out, "wide_conv3x3: the pooling epilogue needs idx_out");
@@ -489,7 +525,7 @@ int launch_wide_conv(const void* x, int B, int H, int W, int Cin, const float* w
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.CPi = Cin / 8; p.KP = (p.CPi + 1) & ~1; p.NP = (Cout + 15) & ~15;
   p.tiles_x = W / TW; p.tiles_y = (H + TH - 1) / TH; p.ntiles = B * p.tiles_x * p.tiles_y;
-  p.epi = epi; p.transposed = transposed; p.w = w; p.bias = bias;
+  p.epi = epi; p.transposed = transposed; p.w = w; p.wpacked = (const uint4*)wpacked; p.bias = bias;
   p.out = (__nv_bfloat16*)out; p.out_f32 = out_f32; p.idx_out = idx_out; p.idx_in = idx_in; p.mask = mask;
   p.tmem_cols = pow2_cols(2 * p.NP);
   CGS_REQUIRE(p.tmem_cols <= 512, "wide_conv3x3: Cout %d needs more than 512 TMEM columns", Cout);
@@ -512,9 +548,12 @@ int launch_wide_conv(const void* x, int B, int H, int W, int Cin, const float* w
 }
 
 int wide_wgrad_grid(int B, int H, int W) {
+  // at least ~4 tiles per CTA: every CTA hands over a 3 x 128 x NP partial tile, which is what the small layers would be paying for
   const int ntiles = B * (W / TW) * ((H + TH - 1) / TH);
   int grid = device_sms();
-  return grid > ntiles ? ntiles : grid;
+  const int want = (ntiles + 3) / 4;
+  if (grid > want) grid = want;
+  return grid < 1 ? 1 : grid;
 }
 
 int launch_wide_wgrad(const void* x, const void* dy, int B, int H, int W, int Cin, int Cout, float* dw, float* db, float* ws,
@@ -549,8 +588,8 @@ int launch_wide_wgrad(const void* x, const void* dy, int B, int H, int W, int Ci
   wide_wgrad_kernel<<<grid, NTHR, smem, st>>>(tmx, tmdy, p);
   rc = check_launch("wide_wgrad3x3");
   if (rc) return rc;
-  const int n = 3 * 128 * p.NP;
-  wide_wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws, grid, p.NP, Cin, Cout, dw, db);
+  const int nwarps = 3 * 128 * p.NP / 4;
+  wide_wgrad_reduce_kernel<<<(nwarps + 7) / 8, 256, 0, st>>>(ws, grid, p.NP, Cin, Cout, dw, db);
   return check_launch("wide_wgrad3x3.reduce");
 }
 
@@ -559,10 +598,25 @@ int launch_wide_wgrad(const void* x, const void* dy, int B, int H, int W, int Ci
 
 using namespace cgs;
 
-extern "C" int cgs_wide_conv3x3(const void* x, int32_t B, int32_t H, int32_t W, int32_t Cin, const float* w, const float* bias, int32_t Cout,
-                                int32_t transposed, int32_t epi, void* out, float* out_f32, uint8_t* idx_out, const uint8_t* idx_in,
+extern "C" int cgs_wide_conv3x3(const void* x, int32_t B, int32_t H, int32_t W, int32_t Cin, const float* w, const void* wpacked, const float* bias,
+                                int32_t Cout, int32_t transposed, int32_t epi, void* out, float* out_f32, uint8_t* idx_out, const uint8_t* idx_in,
                                 const float* mask, void* stream) {
-  return wd::launch_wide_conv(x, B, H, W, Cin, w, bias, Cout, transposed, epi, out, out_f32, idx_out, idx_in, mask, (cudaStream_t)stream);
+  return wd::launch_wide_conv(x, B, H, W, Cin, w, wpacked, bias, Cout, transposed, epi, out, out_f32, idx_out, idx_in, mask, (cudaStream_t)stream);
+}
+
+extern "C" int64_t cgs_wide_packed_bytes(int32_t Cin, int32_t Cout) {
+  return (int64_t)9 * (((Cin >> 3) + 1) & ~1) * ((Cout + 15) & ~15) * 16;
+}
+
+extern "C" int cgs_wide_pack(const cgs_wide_packjob* jobs, int32_t njobs, void* stream) {
+  CGS_REQUIRE(jobs && njobs >= 1 && njobs <= 8, "wide_pack: 1..8 jobs");
+  wd::PackJobs js;
+  for (int i = 0; i < njobs; ++i) {
+    CGS_REQUIRE(jobs[i].w && jobs[i].out && (jobs[i].Cin % 8) == 0 && (jobs[i].Cout % 8) == 0 && ((uintptr_t)jobs[i].out & 15) == 0, "wide_pack: bad job %d", i);
+    js.j[i] = wd::PackJob{jobs[i].w, (uint4*)jobs[i].out, jobs[i].Cin, jobs[i].Cout, jobs[i].transposed};
+  }
+  wd::wide_pack_kernel<<<dim3(16, njobs), 256, 0, (cudaStream_t)stream>>>(js);
+  return check_launch("wide_pack");
 }
 
 extern "C" int cgs_wide_wgrad3x3(const void* x, const void* dy, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, float* dw, float* db,

@@ -28,7 +28,21 @@ def _bp(t):
     return _p(t, torch.bfloat16)
 
 
-def conv3x3(x, w, bias=None, epi=EPI_PLAIN, transposed=False, idx_in=None, mask=None, want_f32=False):
+def pack_weights(jobs):
+    """jobs: (w fp32 OIHW, transposed) -> the bf16 operand tiles of cgs_wide_conv3x3 for each, written by ONE launch."""
+    import ctypes as C
+    L = _lib.lib()
+    outs, arr = [], (_lib.WidePackJob * len(jobs))()
+    for i, (w, tr) in enumerate(jobs):
+        cin, cout = (w.shape[0], w.shape[1]) if tr else (w.shape[1], w.shape[0])
+        o = torch.empty(int(L.cgs_wide_packed_bytes(cin, cout)), device=w.device, dtype=torch.uint8)
+        outs.append(o)
+        arr[i] = _lib.WidePackJob(_p(w.detach()), _p(o, torch.uint8), cin, cout, int(bool(tr)))
+    _call("cgs_wide_pack", C.cast(arr, C.c_void_p), len(jobs), _stream())
+    return outs
+
+
+def conv3x3(x, w, bias=None, epi=EPI_PLAIN, transposed=False, idx_in=None, mask=None, want_f32=False, packed=None):
     """3x3 / padding 1 convolution of a chunk-planar bf16 activation on the tcgen05 kernel.
     transposed=False: w [Cout, Cin, 3, 3] (nets.py:170-183 forward); transposed=True: w is the FORWARD weight [Cx, Cout, 3, 3] of the
     layer whose input gradient this is, x its output gradient with Cx channels.
@@ -48,7 +62,7 @@ def conv3x3(x, w, bias=None, epi=EPI_PLAIN, transposed=False, idx_in=None, mask=
         out = torch.empty((B, Cout // 8, 2 * H, 2 * W, 8), device=dev, dtype=torch.bfloat16)
     else:
         out = torch.empty((B, Cout // 8, H, W, 8), device=dev, dtype=torch.bfloat16)
-    _call("cgs_wide_conv3x3", _bp(x), B, H, W, Cin, _p(w.detach()), _p(bias.detach()) if bias is not None else None, Cout,
+    _call("cgs_wide_conv3x3", _bp(x), B, H, W, Cin, _p(w.detach()), _p(packed, torch.uint8), _p(bias.detach()) if bias is not None else None, Cout,
           int(bool(transposed)), int(epi), _bp(out), _p(f32), _p(idx, torch.uint8), _p(idx_in, torch.uint8), _p(mask), _stream())
     if epi == EPI_RELU_POOL:
         return (out, idx, f32) if want_f32 else (out, idx)
@@ -104,14 +118,34 @@ def conv0_wgrad(frames_u8, roll, de0, idx0, dw0, db0):
           _stream())
 
 
-def gemm(A, a_kc, Bm, b_kc, M, N, K, out=None, bias=None, gate=None, relu=False, accumulate=False):
-    """out[M, N] (+)= op(A) @ op(B) in TF32: A is [M, K] (a_kc) or [K, M]; B is [N, K] (b_kc) or [K, N], all row-major fp32."""
+_gemm_ws = {}
+
+
+def gemm(A, a_kc, Bm, b_kc, M, N, K, out=None, bias=None, gate=None, relu=False, accumulate=False, splits=1):
+    """out[M, N] (+)= op(A) @ op(B) in TF32: A is [M, K] (a_kc) or [K, M]; B is [N, K] (b_kc) or [K, N], all row-major fp32.
+    splits > 1 cuts K over that many CTAs per output tile (deterministic: the last CTA sums the partial tiles in order)."""
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
     assert A.dim() == 2 and Bm.dim() == 2 and tuple(A.shape) == ((M, K) if a_kc else (K, M)) and tuple(Bm.shape) == ((N, K) if b_kc else (K, N))
+    ws = ctr = None
+    if splits > 1:
+        key = A.device.index if A.device.index is not None else torch.cuda.current_device()
+        ent = _gemm_ws.get(key)
+        if ent is None or ent[0].numel() < splits * M * N:
+            ent = (torch.empty(max(splits * M * N, 1 << 20), device=A.device, dtype=torch.float32),
+                   torch.zeros(4096, device=A.device, dtype=torch.int32))
+            _gemm_ws[key] = ent
+        ws, ctr = ent
     _call("cgs_wide_gemm", _p(A), int(a_kc), A.shape[1], _p(Bm), int(b_kc), Bm.shape[1], _p(out), N, M, N, K, _p(bias), _p(gate), int(relu),
-          int(accumulate), _stream())
+          int(accumulate), int(splits), _p(ws), _p(ctr, torch.int32), _stream())
     return out
+
+
+def colsums(jobs, B):
+    """jobs: (X [B, n], out [n], scale, accumulate) x <= 5 -> out = (accumulate ? out : 0) + scale * X.sum(0), one launch."""
+    import ctypes as C
+    arr = (_lib.WideColJob * len(jobs))(*[_lib.WideColJob(_p(X), _p(o), int(o.numel()), float(sc), int(acc)) for X, o, sc, acc in jobs])
+    _call("cgs_wide_colsums", C.cast(arr, C.c_void_p), len(jobs), B, _stream())
 
 
 def supported(critic):
@@ -149,34 +183,35 @@ def critic_train_wide(critic, frames_u8, target, roll=0, masks=(None, None, None
         masks = ops.dropout_masks([(B, 8, 8, C2), (B, 4, 4, C3), (B, C4)], float(rng[0]), rng[1], rng[2])
     m2, m3, mv = masks
     # ---- forward
+    p1, p2, p3, p3t, p2t, p1t = pack_weights([(w1, False), (w2, False), (w3, False), (w3, True), (w2, True), (w1, True)])
     e0, idx0 = conv0_fwd(frames_u8, roll, w0, b0)
-    e1, idx1 = conv3x3(e0, w1, b1, EPI_RELU_POOL)
-    e2, idx2 = conv3x3(e1, w2, b2, EPI_RELU_POOL, mask=m2)
-    e3, idx3, e3f = conv3x3(e2, w3, b3, EPI_RELU_POOL, mask=m3, want_f32=True)
+    e1, idx1 = conv3x3(e0, w1, b1, EPI_RELU_POOL, packed=p1)
+    e2, idx2 = conv3x3(e1, w2, b2, EPI_RELU_POOL, mask=m2, packed=p2)
+    e3, idx3, e3f = conv3x3(e2, w3, b3, EPI_RELU_POOL, mask=m3, want_f32=True, packed=p3)
     X3 = e3f.view(B, K1)
     W4 = w4.reshape(C4, K1)
-    H1 = gemm(X3, True, W4, True, B, C4, K1, bias=b4, relu=True)                       # features.14 + ReLU (nets.py:186-187)
+    H1 = gemm(X3, True, W4, True, B, C4, K1, bias=b4, relu=True, splits=8)                    # features.14 + ReLU (nets.py:186-187)
     V = gemm(H1, True, wl1, True, B, C4, C4, bias=bl1, relu=True)                      # crit.1 + ReLU (nets.py:190-191)
     pred = torch.empty(B, device=dev, dtype=torch.float32)
     loss = torch.empty(1, device=dev, dtype=torch.float32)
-    dV = torch.empty((B, C4), device=dev, dtype=torch.float32)
-    dz = torch.empty(B, device=dev, dtype=torch.float32)
-    _call("cgs_wide_head_mid", _p(V), _p(mv), _p(wl2.reshape(-1)), _p(bl2), _p(target), B, C4, float(loss_grad), int(bool(bce)), _p(pred), _p(loss),
-          _p(dV), _p(dz), _p(dwl2.view(-1)), _p(dbl2), _stream())
+    scr = torch.empty((2 * B * C4 + 2 * B,), device=dev, dtype=torch.float32)
+    dV, U, dz, lterm = scr[:B * C4].view(B, C4), scr[B * C4:2 * B * C4].view(B, C4), scr[2 * B * C4:2 * B * C4 + B], scr[2 * B * C4 + B:]
+    _call("cgs_wide_head_mid", _p(V), _p(mv), _p(wl2.reshape(-1)), _p(bl2), _p(target), B, C4, float(loss_grad), int(bool(bce)), _p(pred), _p(lterm),
+          _p(dV), _p(dz), _p(U), _stream())
     # ---- backward: head
     dH1 = gemm(dV, True, wl1, False, B, C4, C4, gate=H1)                               # through crit.1 and features.15's ReLU
     gemm(dV, False, H1, False, C4, C4, B, out=dwl1, accumulate=True)
-    _call("cgs_wide_colsum2", _p(dV), _p(dbl1), _p(dH1), _p(db4), B, C4, _stream())
+    colsums([(dV, dbl1, 1.0, 1), (dH1, db4, 1.0, 1), (U, dwl2.view(-1), 1.0, 1), (dz.view(B, 1), dbl2, 1.0, 1), (lterm.view(B, 1), loss, 1.0 / B, 0)], B)
     dE3 = gemm(dH1, True, W4, False, B, K1, C4)                                        # [B, C3, 4, 4]
     gemm(dH1, False, X3, False, C4, K1, B, out=dw4.view(C4, K1), accumulate=True)
     dY3 = torch.empty((B, C3 // 8, 8, 8, 8), device=dev, dtype=torch.bfloat16)
     _call("cgs_wide_unpool3", _p(dE3), _p(idx3, torch.uint8), _p(m3), B, C3, _bp(dY3), _stream())
     # ---- backward: the 3x3 convolutions
     wgrad3x3(e2, dY3, dw3, db3)
-    dY2 = conv3x3(dY3, w3, epi=EPI_UNPOOL, transposed=True, idx_in=idx2, mask=m2)
+    dY2 = conv3x3(dY3, w3, epi=EPI_UNPOOL, transposed=True, idx_in=idx2, mask=m2, packed=p3t)
     wgrad3x3(e1, dY2, dw2, db2)
-    dY1 = conv3x3(dY2, w2, epi=EPI_UNPOOL, transposed=True, idx_in=idx1)
+    dY1 = conv3x3(dY2, w2, epi=EPI_UNPOOL, transposed=True, idx_in=idx1, packed=p2t)
     wgrad3x3(e0, dY1, dw1, db1)
-    dE0 = conv3x3(dY1, w1, transposed=True)
+    dE0 = conv3x3(dY1, w1, transposed=True, packed=p1t)
     conv0_wgrad(frames_u8, roll, dE0, idx0, dw0, db0)
     return loss.reshape(()), pred

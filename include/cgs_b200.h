@@ -389,10 +389,20 @@ enum {
 };
 /* transposed != 0: the input-gradient convolution of a layer with weight w[Cin][Cout][3][3] (x = the output gradient with Cin
  * channels; filters rotated, in/out swapped).  mask: NHWC fp32 [B][h][w][Cout] at the resolution of `out`'s pooled map
- * (RELU_POOL) or of the conv itself (UNPOOL), or NULL. */
-int cgs_wide_conv3x3(const void* x, int32_t B, int32_t H, int32_t W, int32_t Cin, const float* w, const float* bias, int32_t Cout,
-                     int32_t transposed, int32_t epi, void* out, float* out_f32, uint8_t* idx_out, const uint8_t* idx_in,
+ * (RELU_POOL) or of the conv itself (UNPOOL), or NULL.
+ * wpacked: the filters as bf16 operand tiles written by cgs_wide_pack (then w may be NULL); NULL: every CTA packs them from w. */
+int cgs_wide_conv3x3(const void* x, int32_t B, int32_t H, int32_t W, int32_t Cin, const float* w, const void* wpacked, const float* bias,
+                     int32_t Cout, int32_t transposed, int32_t epi, void* out, float* out_f32, uint8_t* idx_out, const uint8_t* idx_in,
                      const float* mask, void* stream);
+/* fp32 OIHW filters -> the bf16 operand tiles cgs_wide_conv3x3 keeps in shared memory, up to 8 (layer, direction) jobs in one
+ * launch (the filters change with every optimizer step); out: cgs_wide_packed_bytes(Cin, Cout) bytes, 16-byte aligned. */
+typedef struct {
+  const float* w;
+  void* out;
+  int32_t Cin, Cout, transposed; /* GEMM view, as in cgs_wide_conv3x3 */
+} cgs_wide_packjob;
+int cgs_wide_pack(const cgs_wide_packjob* jobs, int32_t njobs, void* stream);
+int64_t cgs_wide_packed_bytes(int32_t Cin, int32_t Cout);
 /* dw[Cout][Cin][3][3] += sum_pixels dy (x) shifted x, db[Cout] += sum_pixels dy (db may be NULL): x [B][Cin/8][H][W][8],
  * dy [B][Cout/8][H][W][8] bf16; GEMM with K = pixels on tcgen05, per-CTA partial tiles summed in fixed order by a second
  * kernel.  workspace: cgs_wide_wgrad_workspace(B, H, W, Cout) floats.  Cin <= 40. */
@@ -408,22 +418,34 @@ int cgs_wide_conv0_wgrad(const uint8_t* frames, int32_t B, int32_t roll, const i
                          int32_t C0, float* dw0, float* db0, float* workspace, int64_t workspace_floats, void* stream);
 /* C[M][N] (+)= op(A) op(B) in TF32 (fp32 accumulate): A[m*lda + k] (a_k_contiguous) or A[k*lda + m]; B[n*ldb + k]
  * (b_k_contiguous) or B[k*ldb + n]; then + bias[n], zero where gate[m*ldc + n] <= 0, ReLU, accumulate.  The head's GEMMs:
- * features.14 (a 4x4 valid conv on a 4x4 map, nets.py:186), crit.1 (nets.py:190) and their input / weight gradients. */
+ * features.14 (a 4x4 valid conv on a 4x4 map, nets.py:186), crit.1 (nets.py:190) and their input / weight gradients.
+ * splits > 1: K is cut over gridDim.z; partial tiles meet in ws [splits][M][N] and the last CTA of a tile sums them in order
+ * (deterministic); counters: >= tiles ints, zero before the first call (the kernel leaves them zero). */
 int cgs_wide_gemm(const float* A, int32_t a_k_contiguous, int32_t lda, const float* Bm, int32_t b_k_contiguous, int32_t ldb, float* Cm,
                   int32_t ldc, int32_t M, int32_t N, int32_t K, const float* bias, const float* gate, int32_t relu, int32_t accumulate,
-                  void* stream);
-/* crit.3 Dropout (mv or NULL), crit.4 Linear(nb, 1), Sigmoid, MSE / BCE (main.py:192-195) on V = crit.2's output [B][nb]:
- * pred [B], loss (mean), dV = d loss / d V with loss scaled by loss_grad, dz [B] scratch, dwl2 [nb] +=, dbl2 [1] +=. */
+                  int32_t splits, float* ws, int32_t* counters, void* stream);
+/* crit.3 Dropout (mv or NULL), crit.4 Linear(nb, 1), Sigmoid, MSE / BCE (main.py:192-195) on V = crit.2's output [B][nb], one
+ * warp per frame: pred [B], lterm [B] (the frame's loss term), dz [B], dV = d loss / d V with the loss scaled by loss_grad / B,
+ * U = dz * V * mv (its column sum is crit.4's weight gradient). */
 int cgs_wide_head_mid(const float* V, const float* mv, const float* wl2, const float* bl2, const float* target, int32_t B, int32_t nb,
-                      float loss_grad, int32_t bce, float* pred, float* loss, float* dV, float* dz, float* dwl2, float* dbl2, void* stream);
-/* out0[j] += sum_b X0[b][j], out1[j] += sum_b X1[b][j] (bias gradients of crit.1 / features.14), fixed order. */
-int cgs_wide_colsum2(const float* X0, float* out0, const float* X1, float* out1, int32_t B, int32_t n, void* stream);
+                      float loss_grad, int32_t bce, float* pred, float* lterm, float* dV, float* dz, float* U, void* stream);
+/* Up to 5 column sums in one launch: out[j] = (accumulate ? out[j] : 0) + scale * sum_b X[b*n + j], fixed order (bias gradients,
+ * crit.4's weight gradient, the mean loss). */
+typedef struct {
+  const float* X;
+  float* out;
+  int32_t n;
+  float scale;
+  int32_t accumulate;
+} cgs_wide_coljob;
+int cgs_wide_colsums(const cgs_wide_coljob* jobs, int32_t njobs, int32_t B, void* stream);
 /* Gradient of features.13's output de3 [B][C3][4][4] fp32 -> Dropout (m3 NHWC or NULL) + MaxPool + ReLU backward (idx3 planar
  * arg-max bytes) -> dy3 [B][C3/8][8][8][8] bf16, the output gradient of features.10. */
 int cgs_wide_unpool3(const float* de3, const uint8_t* idx3, const float* m3, int32_t B, int32_t C3, void* dy3, void* stream);
 /* Non-zero if a wide kernel ever gave up on an mbarrier (reads a device flag; synchronises). */
 int cgs_wide_status(void);
-/* Debug only: clock64() of the MMA-issuing thread of CTA 0 (wait start, operands landed, MMAs issued) for its first 8 tiles. */
+/* Debug only: clock64() marks of CTA 0 of the conv kernel for its first 8 tiles into 64 int64: MMA thread (loop top, TMEM buffer free,
+ * operands landed, MMAs issued), first epilogue warp (wait start, accumulator ready, tile stored); [63] = start. */
 int cgs_wide_set_trace(long long* dev_buf);
 
 /* ---- formats either side of the path, csrc/edges.cu ---------------------------------------------------

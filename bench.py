@@ -256,7 +256,14 @@ def kernel_flops(entry, B, chfak=1):
     Layer MACs per frame: features.0 884,736; .3 589,824; .6 147,456; .10 73,728; .14 + crit 9,248;
     dec[4] 1,024; dec[3] 110,592; dec[2] 110,592; dec[1] 294,912; dec[0] 1,179,648; masker.0 6,488,064; masker.2 589,824."""
     if chfak != 1:
-        return None
+        # the wide path (cgs_b200/wide.py): per-launch average over the launches one step makes of each entry point
+        k = chfak
+        l0, l123 = 884736 * k, (589824 + 147456 + 73728) * k * k
+        head = (8192 + 1024) * k * k
+        per = {"cgs_wide_conv3x3": 2 * l123 / 6.0,                     # features.3/.6/.10 forward + input gradients: 6 launches
+               "cgs_wide_wgrad3x3": l123 / 3.0, "cgs_wide_conv0_fwd": l0, "cgs_wide_conv0_wgrad": l0, "cgs_wide_gemm": 3 * head / 6.0}
+        m = per.get(entry)
+        return None if m is None else 2 * m * B
     cf = 884736 + 589824 + 147456 + 73728 + 9248                       # critic forward
     cb = cf - 884736                                                   # its dgrads (no input gradient for features.0) ...
     dec = 1024 + 110592 + 110592 + 294912 + 1179648
@@ -539,6 +546,13 @@ def run_ours(args, rank, world):
         sampler.start()
         time.sleep(0.3)
     recs = {n: bench_workload(n, args, rank, world, dev, group, windows) for n in names}
+    wide_rec = None
+    if args.workload == "all" and args.chfak == 1 and world == 1 and not args.no_extras and args.precision == "tf32":
+        # the paper's width (chfak 5, reference docs/index.html:151) through the TMA / tcgen05 kernels of the wide path
+        import copy
+        a5 = copy.copy(args)
+        a5.chfak = 5
+        wide_rec = bench_workload("critic_train", a5, rank, world, dev, group, windows)
     clocks = sampler.stop(windows) if rank == 0 else None
     if rank == 0:
         head = recs[names[0]]
@@ -556,6 +570,8 @@ def run_ours(args, rank, world):
         if len(names) > 1:
             line["workloads"] = {k: v for k, v in recs.items() if k != names[0]}
             line["gpu_launches"] = sum(r["gpu_launches"] for r in recs.values())
+        if wide_rec is not None:
+            line["workloads"]["critic_train_chfak5"] = wide_rec
         if world == 1 and not args.no_extras and ("infer" in names):
             line["infer_sweep"] = infer_sweep(args, dev)
         print(json.dumps(line))

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(NT, 1) wide_conv0_fwd_kernel(const uint8_t* __
                                                                __nv_bfloat16* __restrict__ e0, uint8_t* __restrict__ idx0) {
   extern __shared__ __align__(128) uint8_t smraw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3, odd = g & 1;
-  const int lj = lane >> 3, lr = lane & 7, pixoff = lr + 8 * (lj & 1), chunk = lj >> 1;
+  const int lj = lane >> 3, lr = lane & 7, pixoff = 2 * lr + (lj & 1), chunk = lj >> 1;   // A row r -> pixel 2 (r & 7) + (r >> 3)
   const uint32_t smb = (uint32_t)__cvta_generic_to_shared(smraw);
   const int oI = sE + CP * 16384, oW = oI + CP * 8192, oB = oW + 3 * CP * 256;
   uint2* sW = reinterpret_cast<uint2*>(smraw + oW);
@@ -76,15 +76,28 @@ __global__ void __launch_bounds__(NT, 1) wide_conv0_fwd_kernel(const uint8_t* __
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) w[ky][0][0] = sW[(ky * CP + nt) * 32 + lane];
       const float bias0 = sB[nt * 8 + 2 * t], bias1 = sB[nt * 8 + 2 * t + 1];
-      __nv_bfloat16* dE = reinterpret_cast<__nv_bfloat16*>(smraw + sE) + ((nt * 32 + (r0 >> 1)) * 32 + ((x0 + g) >> 1)) * 8 + 2 * t + odd;
-      uint8_t* dI = smraw + oI + ((nt * 32 + (r0 >> 1)) * 32 + ((x0 + g) >> 1)) * 8 + 2 * t + odd;
+      // the A rows of a fragment are permuted (row g = pixel 2g, row g + 8 = pixel 2g + 1 of the 16-pixel strip), so a thread holds
+      // the x pair of both rows: the whole 2x2 window of pooled pixel (x0 / 2 + g), channels 2t and 2t + 1, no shuffles
+      uint32_t* dE = reinterpret_cast<uint32_t*>(smraw + sE) + ((nt * 32 + (r0 >> 1)) * 32 + (x0 >> 1) + g) * 4 + t;
+      unsigned short* dI = reinterpret_cast<unsigned short*>(smraw + oI) + ((nt * 32 + (r0 >> 1)) * 32 + (x0 >> 1) + g) * 4 + t;
       slide_bf<16, 1, 1>(
           w, [&](int i, uint32_t(&a)[1][4]) { ldsm4(a[0], aA + (uint32_t)(i * (PX * 16))); },
           [&](int e, int, const float(&top)[4], const float(&bot)[4]) {
-            pool2x2(top, bot, bias0, bias1, odd, [&](int h, float v, int idx) {
-              dE[((e >> 1) * 32 + 4 * h) * 8] = __float2bfloat16_rn(v);
-              dI[((e >> 1) * 32 + 4 * h) * 8] = (uint8_t)idx;
-            });
+            float v[2];
+            uint32_t id[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float bb = j ? bias1 : bias0;
+              const float p0 = top[j] + bb, p1 = top[2 + j] + bb, p2 = bot[j] + bb, p3 = bot[2 + j] + bb;
+              const float m01 = fmaxf(p0, p1), m23 = fmaxf(p2, p3);
+              const uint32_t i01 = p1 > p0 ? 1u : 0u, i23 = p3 > p2 ? 3u : 2u;
+              float m = fmaxf(m01, m23);
+              uint32_t ix = m23 > m01 ? i23 : i01;
+              if (!(m > 0.f)) { m = 0.f; ix = 4u; }
+              v[j] = m; id[j] = ix;
+            }
+            dE[(e >> 1) * 128] = pack_bf16(v[0], v[1]);
+            dI[(e >> 1) * 128] = (unsigned short)(id[0] | (id[1] << 8));
           });
     }
     __syncthreads();
@@ -212,7 +225,7 @@ struct GemmP {
   float* ws;                       // [splits][M][N]
   int* counters;                   // one per (tile x, tile y), zero between launches (the last CTA resets its own)
 };
-constexpr int GM = 64, GN = 32, GK = 32, GST = 3;
+constexpr int GM = 64, GN = 32, GK = 32, GST = 6;     // 6 stages: these GEMMs are short K loops bound by L2 latency, not bytes
 constexpr int GA_FLOATS = 2304, GB_FLOATS = 1280;    // [64][36] or [32][72]; [32][36] or [32][40]
 
 __device__ __forceinline__ void cp16z(uint32_t dst, const void* src, bool ok) {
@@ -227,8 +240,9 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
 
 template <bool AKC, bool BKC>
 __global__ void __launch_bounds__(128) wide_gemm_kernel(const GemmP p) {
-  __shared__ __align__(16) float sA[GST][GA_FLOATS];
-  __shared__ __align__(16) float sB[GST][GB_FLOATS];
+  extern __shared__ __align__(16) float gsm[];
+  float(*sA)[GA_FLOATS] = reinterpret_cast<float(*)[GA_FLOATS]>(gsm);
+  float(*sB)[GB_FLOATS] = reinterpret_cast<float(*)[GB_FLOATS]>(gsm + GST * GA_FLOATS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
   const int nk_all = (p.K + GK - 1) / GK, per = (nk_all + p.splits - 1) / p.splits;
@@ -477,9 +491,17 @@ extern "C" int cgs_wide_gemm(const float* A, int32_t a_k_contiguous, int32_t lda
   CGS_REQUIRE(splits <= 1 || (ws && counters && grid.x * grid.y <= 4096), "wide_gemm: split-K needs a workspace [splits][M][N] and <= 4096 counters");
   wm::GemmP p{A, Bm, bias, gate, Cm, M, N, K, lda, ldb, ldc, relu, accumulate, (int)grid.z, ws, counters};
   cudaStream_t st = (cudaStream_t)stream;
-  if (a_k_contiguous && b_k_contiguous) wm::wide_gemm_kernel<true, true><<<grid, 128, 0, st>>>(p);
-  else if (a_k_contiguous) wm::wide_gemm_kernel<true, false><<<grid, 128, 0, st>>>(p);
-  else if (!b_k_contiguous) wm::wide_gemm_kernel<false, false><<<grid, 128, 0, st>>>(p);
+  const int smem = wm::GST * (wm::GA_FLOATS + wm::GB_FLOATS) * 4;
+  if (a_k_contiguous && b_k_contiguous) {
+    cudaFuncSetAttribute(wm::wide_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    wm::wide_gemm_kernel<true, true><<<grid, 128, smem, st>>>(p);
+  } else if (a_k_contiguous) {
+    cudaFuncSetAttribute(wm::wide_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    wm::wide_gemm_kernel<true, false><<<grid, 128, smem, st>>>(p);
+  } else if (!b_k_contiguous) {
+    cudaFuncSetAttribute(wm::wide_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    wm::wide_gemm_kernel<false, false><<<grid, 128, smem, st>>>(p);
+  }
   else CGS_REQUIRE(false, "wide_gemm: A MN-contiguous with B K-contiguous is not built");
   return check_launch("wide_gemm");
 }

@@ -29,7 +29,8 @@ namespace wd {
 
 constexpr int TW = 8, TH = 16, HWID = 10, HHGT = 18;
 constexpr int SLOTS = HWID * HHGT;                 // 180 haloed pixels
-constexpr int NTHR = 192;
+constexpr int NTHR = 320;                          // conv kernel: TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+constexpr int NTHR_W = 192;                        // weight-gradient kernel: TMA warp, MMA warp, 4 warps that drain TMEM once at the end
 constexpr int A3_ROWS = 18 * 8;                    // weight gradient: one kx copy of a plane = 18 rows x 8 pixels
 constexpr int A3_PLANE = A3_ROWS * 16, A3_BYTES = 16 * A3_PLANE;
 constexpr int DY_PLANE = TH * TW * 16;
@@ -92,6 +93,13 @@ __device__ __forceinline__ void tma_load4(uint32_t dst, const CUtensorMap* tm, i
       "l"(tm), "r"(8 * x), "r"(y), "r"(plane), "r"(n), "r"(bar)
       : "memory");
 }
+// one lane of a converged warp; unlike `lane == 0` the compiler knows the region is executed by a single lane, so the warp-uniform
+// descriptor arithmetic of the MMA loop can stay in uniform registers (UTCHMMA takes its operands from there)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -140,10 +148,12 @@ struct ConvP {
   float* out_f32;
 };
 
+template <int KS>
 __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constant__ CUtensorMap tmx, const ConvP p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KP = p.KP, NP = p.NP;
+  if (blockIdx.x == 0 && tid == 0 && g_wd_trace) g_wd_trace[56] = clock64();
   const uint32_t w_bytes = (uint32_t)9 * KP * NP * 16, a_bytes = (uint32_t)KP * SLOTS * 16, a_tx = (uint32_t)p.CPi * SLOTS * 16;
   unsigned char* s_w = smem;
   unsigned char* s_a = smem + w_bytes;
@@ -159,7 +169,7 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
   }
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(bFull + 8 * s, 1); mbar_init(bEmpty + 8 * s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bTFull + 8 * b, 1); mbar_init(bTEmpty + 8 * b, 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bTFull + 8 * b, 1); mbar_init(bTEmpty + 8 * b, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   {
@@ -182,11 +192,11 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
   const uint32_t tmem_base = *s_tmem;
   const int tpf = p.tiles_x * p.tiles_y;
   long long* trace = (blockIdx.x == 0) ? g_wd_trace : nullptr;
-  if (trace && tid == 0) trace[63] = clock64();
+  if (trace && tid == 0) trace[57] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int s = it % p.stages, k = it / p.stages;
@@ -198,8 +208,9 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     // ===== MMA issuer
-    if (lane == 0) {
-      const uint32_t w_base = smem_u32(s_w), w_plane = (uint32_t)NP * 16;
+    if (elect_one()) {
+      const uint64_t a_desc0 = umma_desc(smem_u32(s_a), SLOTS * 16, HWID * 16), b_desc0 = umma_desc(smem_u32(s_w), (uint32_t)NP * 16, 128);
+      const uint64_t b_step = (uint64_t)(2 * NP);   // consecutive (tap, plane pair) operand tiles are 2 NP rows of 16 bytes apart
       int it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int s = it % p.stages, k = it / p.stages, ab = it & 1, j = it >> 1;
@@ -209,25 +220,28 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
         if (!mbar_wait(bFull + 8 * s, k & 1)) break;
         if (trace && it < 8) trace[it * 8 + 2] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t a0 = smem_u32(s_a + (size_t)s * a_bytes), td = tmem_base + (uint32_t)(ab * NP);
-        uint32_t acc = 0;
+        // the 9 * KS descriptors of a tile differ in their start-address fields only: one 64-bit add each, everything else is
+        // loop-invariant (a single thread issues these: its own instruction latency is what bounds the MMA rate)
+        const uint64_t ad0 = a_desc0 + (uint64_t)((uint32_t)s * (a_bytes >> 4));
+        const uint32_t td = tmem_base + (uint32_t)(ab * NP);
+        uint64_t bd = b_desc0;
+#pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          const int ky = tap / 3, kx = tap - 3 * ky;
-          const uint32_t a_tap = a0 + (uint32_t)(ky * HWID + kx) * 16;
-          for (int kp = 0; kp < KP; kp += 2) {
-            umma_bf16(td, umma_desc(a_tap + (uint32_t)kp * (SLOTS * 16), SLOTS * 16, HWID * 16),
-                      umma_desc(w_base + (uint32_t)(tap * KP + kp) * w_plane, w_plane, 128), p.idesc, acc);
-            acc = 1;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            umma_bf16(td, ad0 + (uint64_t)((tap / 3) * HWID + (tap % 3) + 2 * ks * SLOTS), bd, p.idesc, (tap | ks) ? 1u : 0u);
+            bd += b_step;
           }
         }
         umma_commit(bEmpty + 8 * s);              // the stage is free once these MMAs have read it
         umma_commit(bTFull + 8 * ab);             // ... and the accumulator is complete
         if (trace && it < 8) trace[it * 8 + 3] = clock64();
       }
+      if (trace) trace[58] = clock64();
     }
   } else {
     // ===== epilogue warps: TMEM lane quarter (warp & 3); lane m of the accumulator = pixel (m / 8, m % 8) of the tile
-    const int q = warp & 3, m = q * 32 + lane, yl = m >> 3, xl = m & 7;
+    const int q = warp & 3, half = (warp - 2) >> 2, m = q * 32 + lane, yl = m >> 3, xl = m & 7;
     const bool odd_x = xl & 1, odd_y = yl & 1;
     const int H = p.H, W = p.W, Cout = p.Cout, CPo = Cout >> 3;
     int it = 0;
@@ -241,7 +255,7 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
       const int y = ty * TH + yl, x = tx * TW + xl;
       const bool inb = y < H;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * NP);
-      for (int cg = 0; cg < CPo; ++cg) {
+      for (int cg = half; cg < CPo; cg += 2) {
         float a[8];
         tmem_ld8(taddr + (uint32_t)(cg * 8), a);
         if (p.bias) {
@@ -249,40 +263,45 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
           a[0] += b0.x; a[1] += b0.y; a[2] += b0.z; a[3] += b0.w; a[4] += b1.x; a[5] += b1.y; a[6] += b1.z; a[7] += b1.w;
         }
         if (p.epi == CGS_WIDE_EPI_RELU_POOL) {
-          // 2x2 window = lanes (l, l^1, l^8, l^9); the first maximum in row-major order wins (ATen max_pool2d); 4 = ReLU is dead
-          float res[8];
-          uint32_t ilo = 0, ihi = 0;
+          // 2x2 window = lanes (l, l^1, l^8, l^9); the first maximum in row-major order wins (ATen max_pool2d); 4 = ReLU is dead.
+          // The four lanes of a window split its 8 channels: after the x exchange a lane holds 4 channels (even x: 0-3, odd x:
+          // 4-7), after the y exchange 2 (even y: the first two of those): 7 shuffles per 8 channels, every lane stores.
+          float mx[4];
+          uint32_t rb[4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float v = a[c], o = __shfl_xor_sync(0xffffffffu, v, 1);
-            const float left = odd_x ? o : v, right = odd_x ? v : o;
-            const bool rr = right > left;
-            const float mx = rr ? right : left;
-            const float o2 = __shfl_xor_sync(0xffffffffu, mx, 8);
-            const int ro = __shfl_xor_sync(0xffffffffu, (int)rr, 8);
-            const float top = odd_y ? o2 : mx, bot = odd_y ? mx : o2;
-            const int rt = odd_y ? ro : (int)rr, rb = odd_y ? (int)rr : ro;
-            const bool bb = bot > top;
-            float v2 = bb ? bot : top;
-            uint32_t am = bb ? (2u + (uint32_t)rb) : (uint32_t)rt;
-            if (!(v2 > 0.f)) { v2 = 0.f; am = 4u; }
-            res[c] = v2;
-            if (c < 4) ilo |= am << (8 * c); else ihi |= am << (8 * (c - 4));
+          for (int i = 0; i < 4; ++i) {
+            const float recv = __shfl_xor_sync(0xffffffffu, odd_x ? a[i] : a[4 + i], 1), mine = odd_x ? a[4 + i] : a[i];
+            const float left = odd_x ? recv : mine, right = odd_x ? mine : recv;
+            rb[i] = right > left ? 1u : 0u;
+            mx[i] = rb[i] ? right : left;
           }
-          if (!odd_x && !odd_y && inb) {
-            const int H2 = H >> 1, W2 = W >> 1, y2 = y >> 1, x2 = x >> 1;
-            if (p.mask) {
-              const float* mp = p.mask + ((size_t)(n * H2 + y2) * W2 + x2) * Cout + cg * 8;
-              const float4 m0 = __ldg(reinterpret_cast<const float4*>(mp)), m1 = __ldg(reinterpret_cast<const float4*>(mp) + 1);
-              res[0] *= m0.x; res[1] *= m0.y; res[2] *= m0.z; res[3] *= m0.w; res[4] *= m1.x; res[5] *= m1.y; res[6] *= m1.z; res[7] *= m1.w;
-            }
-            const size_t o = ((size_t)(n * CPo + cg) * H2 + y2) * W2 + x2;
-            if (p.out) reinterpret_cast<uint4*>(p.out)[o] = make_uint4(pack2(res[0], res[1]), pack2(res[2], res[3]), pack2(res[4], res[5]), pack2(res[6], res[7]));
-            if (p.out_f32) {       // NCHW fp32 copy for the head: features.14 reads a frame's [C][4][4] block as its K vector
+          const uint32_t mybits = odd_y ? (rb[2] | (rb[3] << 1)) : (rb[0] | (rb[1] << 1));
+          const uint32_t obits = __shfl_xor_sync(0xffffffffu, odd_y ? (rb[0] | (rb[1] << 1)) : (rb[2] | (rb[3] << 1)), 8);
+          const uint32_t tbits = odd_y ? obits : mybits, bbits = odd_y ? mybits : obits;
+          float res[2];
+          uint32_t am[2];
 #pragma unroll
-              for (int c = 0; c < 8; ++c) p.out_f32[((size_t)(n * Cout + cg * 8 + c) * H2 + y2) * W2 + x2] = res[c];
+          for (int k = 0; k < 2; ++k) {
+            const float recv = __shfl_xor_sync(0xffffffffu, odd_y ? mx[k] : mx[2 + k], 8), mine = odd_y ? mx[2 + k] : mx[k];
+            const float top = odd_y ? recv : mine, bot = odd_y ? mine : recv;
+            const bool bb = bot > top;
+            res[k] = bb ? bot : top;
+            am[k] = bb ? (2u + ((bbits >> k) & 1u)) : ((tbits >> k) & 1u);
+            if (!(res[k] > 0.f)) { res[k] = 0.f; am[k] = 4u; }
+          }
+          if (inb) {
+            const int H2 = H >> 1, W2 = W >> 1, y2 = y >> 1, x2 = x >> 1, c0 = (odd_x ? 4 : 0) + (odd_y ? 2 : 0);
+            if (p.mask) {
+              const float2 mk = __ldg(reinterpret_cast<const float2*>(p.mask + ((size_t)(n * H2 + y2) * W2 + x2) * Cout + cg * 8 + c0));
+              res[0] *= mk.x; res[1] *= mk.y;
             }
-            reinterpret_cast<uint2*>(p.idx_out)[o] = make_uint2(ilo, ihi);
+            const size_t o = (((size_t)(n * CPo + cg) * H2 + y2) * W2 + x2) * 8 + c0;
+            if (p.out) *reinterpret_cast<uint32_t*>(p.out + o) = pack2(res[0], res[1]);
+            if (p.out_f32) {       // NCHW fp32 copy for the head: features.14 reads a frame's [C][4][4] block as its K vector
+              p.out_f32[((size_t)(n * Cout + cg * 8 + c0) * H2 + y2) * W2 + x2] = res[0];
+              p.out_f32[((size_t)(n * Cout + cg * 8 + c0 + 1) * H2 + y2) * W2 + x2] = res[1];
+            }
+            *reinterpret_cast<unsigned short*>(p.idx_out + o) = (unsigned short)(am[0] | (am[1] << 8));
           }
         } else if (p.epi == CGS_WIDE_EPI_UNPOOL) {
           // this pixel is one pooled output of the layer below: its gradient goes to the arg-max position of the 2x2 window
@@ -325,10 +344,12 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
       if (lane == 0) mbar_arrive(bTEmpty + 8 * ab);
       if (trace && it < 8 && tid == 64) trace[it * 8 + 6] = clock64();
     }
+    if (trace && tid == 64) trace[59] = clock64();
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  if (trace && tid == 0) trace[60] = clock64();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
@@ -344,7 +365,7 @@ struct WgP {
   float* partials;                 // [grid][3][128][NP]
 };
 
-__global__ void __launch_bounds__(NTHR, 1) wide_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmdy,
+__global__ void __launch_bounds__(NTHR_W, 1) wide_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmdy,
                                                              const WgP p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -367,12 +388,12 @@ __global__ void __launch_bounds__(NTHR, 1) wide_wgrad_kernel(const __grid_consta
   // planes the TMA never writes: zeros (unused rows / columns of D stay finite), plane 15 of A = ones (bias gradient)
   for (int s = 0; s < p.stages; ++s) {
     uint4* a = reinterpret_cast<uint4*>(smem + (size_t)s * st_bytes);
-    for (int e = tid; e < 16 * A3_ROWS; e += NTHR) {
+    for (int e = tid; e < 16 * A3_ROWS; e += NTHR_W) {
       const int pl = e / A3_ROWS;
       if (pl >= 3 * p.CPi) a[e] = pl == 15 ? make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u) : make_uint4(0u, 0u, 0u, 0u);
     }
     uint4* b = reinterpret_cast<uint4*>(smem + (size_t)s * st_bytes + A3_BYTES);
-    for (int e = tid + p.CPo * (TH * TW); e < p.NPl * (TH * TW); e += NTHR) b[e] = make_uint4(0u, 0u, 0u, 0u);
+    for (int e = tid + p.CPo * (TH * TW); e < p.NPl * (TH * TW); e += NTHR_W) b[e] = make_uint4(0u, 0u, 0u, 0u);
   }
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -382,7 +403,7 @@ __global__ void __launch_bounds__(NTHR, 1) wide_wgrad_kernel(const __grid_consta
   const int tpf = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int s = it % p.stages, k = it / p.stages;
@@ -397,18 +418,24 @@ __global__ void __launch_bounds__(NTHR, 1) wide_wgrad_kernel(const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
+      // A: (LBO = one tile row, SBO = one plane of a kx copy); B: the dY tile behind it, same LBO, SBO = one dY plane.  The SBO
+      // field is the only difference between the two descriptors besides the start address.
+      const uint64_t a_desc0 = umma_desc(smem_u32(smem), 128, A3_PLANE);
+      const uint64_t b_off = (umma_desc(smem_u32(smem) + A3_BYTES, 128, DY_PLANE) - a_desc0);
       int it = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < p.ntiles && ok; tile += gridDim.x, ++it) {
         const int s = it % p.stages, k = it / p.stages;
         if (!mbar_wait(bFull + 8 * s, k & 1)) { ok = false; break; }
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t a0 = smem_u32(smem + (size_t)s * st_bytes), b0 = a0 + A3_BYTES;
+        const uint64_t ad0 = a_desc0 + (uint64_t)((uint32_t)s * (st_bytes >> 4)), bd0 = ad0 + b_off;
+        const uint32_t first = it > 0 ? 1u : 0u;
+#pragma unroll
         for (int ky = 0; ky < 3; ++ky)
-          for (int r2 = 0; r2 < 8; ++r2)          // K = 16 pixels = tile rows 2 r2, 2 r2 + 1 (8 pixels each)
-            umma_bf16(tmem_base + (uint32_t)(ky * NP), umma_desc(a0 + (uint32_t)(2 * r2 + ky) * 128, 128, A3_PLANE),
-                      umma_desc(b0 + (uint32_t)(2 * r2) * 128, 128, DY_PLANE), p.idesc, (it > 0 || r2 > 0) ? 1u : 0u);
+#pragma unroll
+          for (int r2 = 0; r2 < 8; ++r2)          // K = 16 pixels = tile rows 2 r2, 2 r2 + 1 (8 pixels each): constant descriptor offsets
+            umma_bf16(tmem_base + (uint32_t)(ky * NP), ad0 + (uint64_t)((2 * r2 + ky) * 8), bd0 + (uint64_t)(2 * r2 * 8), p.idesc, r2 ? 1u : first);
         umma_commit(bEmpty + 8 * s);
       }
       umma_commit(bDone);
@@ -540,10 +567,20 @@ int launch_wide_conv(const void* x, int B, int H, int W, int Cin, const float* w
   CUtensorMap tm;
   const int rc = make_tmap(&tm, x, B, p.CPi, H, W, HWID, HHGT, p.CPi);
   if (rc) return rc;
-  cudaFuncSetAttribute(wide_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
   int grid = device_sms();
   if (grid > p.ntiles) grid = p.ntiles;
-  wide_conv_kernel<<<grid, NTHR, smem, st>>>(tm, p);
+#define CGS_WIDE_CONV(KS)                                                                                        \
+  case KS:                                                                                                       \
+    cudaFuncSetAttribute(wide_conv_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);         \
+    wide_conv_kernel<KS><<<grid, NTHR, smem, st>>>(tm, p);                                                       \
+    break;
+  switch (p.KP / 2) {
+    CGS_WIDE_CONV(1) CGS_WIDE_CONV(2) CGS_WIDE_CONV(3) CGS_WIDE_CONV(4) CGS_WIDE_CONV(5) CGS_WIDE_CONV(6) CGS_WIDE_CONV(7) CGS_WIDE_CONV(8)
+    CGS_WIDE_CONV(9) CGS_WIDE_CONV(10)
+    default:
+      CGS_REQUIRE(false, "wide_conv3x3: Cin %d unsupported", Cin);
+  }
+#undef CGS_WIDE_CONV
   return check_launch("wide_conv3x3");
 }
 
@@ -585,7 +622,7 @@ int launch_wide_wgrad(const void* x, const void* dy, int B, int H, int W, int Ci
   rc = make_tmap(&tmdy, dy, B, p.CPo, H, W, TW, TH, p.CPo);
   if (rc) return rc;
   cudaFuncSetAttribute(wide_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-  wide_wgrad_kernel<<<grid, NTHR, smem, st>>>(tmx, tmdy, p);
+  wide_wgrad_kernel<<<grid, NTHR_W, smem, st>>>(tmx, tmdy, p);
   rc = check_launch("wide_wgrad3x3");
   if (rc) return rc;
   const int nwarps = 3 * 128 * p.NP / 4;

@@ -33,11 +33,16 @@ __global__ void rate_kernel(int N, int a_major, int b_major, uint32_t layout, ui
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_major << 15) | ((uint32_t)b_major << 16) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
     const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(smem), b0 = a0 + 96 * 1024, barp = (uint32_t)__cvta_generic_to_shared(&bar);
     const long long t0 = clock64();
-    for (int r = 0; r < reps; ++r) {
-      const uint64_t ad = desc(a0 + (uint32_t)(r % 9) * a_step, a_lbo, a_sbo, layout), bd = desc(b0 + (uint32_t)(r % 9) * b_step, b_lbo, b_sbo, layout);
-      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem), "l"(ad),
-                   "l"(bd), "r"(idesc), "r"(r > 0 ? 1u : 0u)
-                   : "memory");
+    const uint64_t ad0 = desc(a0, a_lbo, a_sbo, layout), bd0 = desc(b0, b_lbo, b_sbo, layout);
+    const uint64_t as16 = a_step >> 4, bs16 = b_step >> 4;
+    for (int r = 0; r < reps; r += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {                 // descriptors differ in the start-address field only: one 64-bit add each
+        const uint64_t ad = ad0 + (uint64_t)u * as16, bd = bd0 + (uint64_t)u * bs16;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem), "l"(ad),
+                     "l"(bd), "r"(idesc), "r"((r | u) > 0 ? 1u : 0u)
+                     : "memory");
+      }
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(barp) : "memory");
     const long long t1 = clock64();

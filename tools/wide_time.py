@@ -11,15 +11,22 @@ ops.set_precision("tf32")
 C = 8 * K
 
 
-def timeit(fn, n=20):
+def timeit(fn, n=10):
+    """us per launch, n launches replayed from a CUDA graph (no host launch overhead in the number)."""
     for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            fn()
+    g.replay()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); s.record()
-    for _ in range(n):
-        fn()
+    for _ in range(3):
+        g.replay()
     e.record(); torch.cuda.synchronize()
-    return s.elapsed_time(e) / n * 1e3
+    return s.elapsed_time(e) / (3 * n) * 1e3
 
 
 rows = []
@@ -50,6 +57,17 @@ for B in (256, 2048):
     C4, K1 = 4 * C, 32 * C
     A = rnd(B, K1); W4 = rnd(C4, K1) * 0.03; H = rnd(B, C4)
     r["gemm H1 = X3 W4^T"] = timeit(lambda: wide.gemm(A, True, W4, True, B, C4, K1, relu=True))
+    r["gemm H1, split-K 8"] = timeit(lambda: wide.gemm(A, True, W4, True, B, C4, K1, relu=True, splits=8))
+    Wl = rnd(C4, C4) * 0.1
+    r["gemm V = H1 Wl1^T"] = timeit(lambda: wide.gemm(H, True, Wl, True, B, C4, C4, relu=True))
+    r["gemm dH1 = dV Wl1 (gated)"] = timeit(lambda: wide.gemm(H, True, Wl, False, B, C4, C4, gate=H))
+    dWl = torch.zeros(C4, C4, device=DEV)
+    r["gemm dWl1 += dV^T H1"] = timeit(lambda: wide.gemm(H, False, H, False, C4, C4, B, out=dWl, accumulate=True))
+    (pk,) = wide.pack_weights([(w, True)])
+    r["pack (1 job)"] = timeit(lambda: wide.pack_weights([(w, True)]))
+    m = ops.dropout_masks([(B, 8, 8, C), (B, 4, 4, 2 * C), (B, 4 * C)], 0.3, 1, torch.zeros(2, dtype=torch.int64, device=DEV))
+    st = torch.zeros(2, dtype=torch.int64, device=DEV)
+    r["dropout masks"] = timeit(lambda: ops.dropout_masks([(B, 8, 8, C), (B, 4, 4, 2 * C), (B, 4 * C)], 0.3, 1, st))
     r["gemm dE3 = dH1 W4"] = timeit(lambda: wide.gemm(H, True, W4, False, B, K1, C4))
     dW = torch.zeros(C4, K1, device=DEV)
     r["gemm dW4 += dH1^T X3"] = timeit(lambda: wide.gemm(H, False, A, False, C4, K1, B, out=dW, accumulate=True))

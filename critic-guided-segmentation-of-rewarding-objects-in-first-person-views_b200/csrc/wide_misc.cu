@@ -247,34 +247,48 @@ __global__ void __launch_bounds__(128) wide_gemm_kernel(const GemmP p) {
   const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
   const int nk_all = (p.K + GK - 1) / GK, per = (nk_all + p.splits - 1) / p.splits;
   const int kt0 = blockIdx.z * per, nk = max(0, min(per, nk_all - kt0));
+  // per-thread chunk descriptors, fixed over the K loop (a single warp per scheduler runs these loops: every instruction counts):
+  // A: 4 chunks of 16 bytes per thread and k-tile, B: 2
+  const float* pa[4];
+  const float* pb[2];
+  uint32_t da[4], db[2];
+  int ka[4], kb[2];                // k offset of the chunk inside a k-tile (-1: the chunk is outside M / N for good)
+  const uint32_t sa0 = (uint32_t)__cvta_generic_to_shared(gsm), sb0 = sa0 + GST * GA_FLOATS * 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = tid + 128 * j;
+    if (AKC) {
+      const int r = c >> 3, kc = (c & 7) * 4;
+      pa[j] = p.A + (size_t)min(m0 + r, p.M - 1) * p.lda + kc; da[j] = (r * 36 + kc) * 4; ka[j] = (m0 + r) < p.M ? kc : -1;
+    } else {
+      const int r = c >> 4, mc = (c & 15) * 4;
+      pa[j] = p.A + (size_t)r * p.lda + min(m0 + mc, p.M - 4); da[j] = (r * 72 + mc) * 4; ka[j] = (m0 + mc) < p.M ? r : -1;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int c = tid + 128 * j;
+    if (BKC) {
+      const int r = c >> 3, kc = (c & 7) * 4;
+      pb[j] = p.B + (size_t)min(n0 + r, p.N - 1) * p.ldb + kc; db[j] = (r * 36 + kc) * 4; kb[j] = (n0 + r) < p.N ? kc : -1;
+    } else {
+      const int r = c >> 3, nc = (c & 7) * 4;
+      pb[j] = p.B + (size_t)r * p.ldb + min(n0 + nc, p.N - 4); db[j] = (r * 40 + nc) * 4; kb[j] = (n0 + nc) < p.N ? r : -1;
+    }
+  }
+  const size_t astep = AKC ? (size_t)1 : (size_t)p.lda, bstep = BKC ? (size_t)1 : (size_t)p.ldb;
   auto load = [&](int kt, int st) {
     const int k0 = (kt0 + kt) * GK;
-    const uint32_t a = (uint32_t)__cvta_generic_to_shared(sA[st]), b = (uint32_t)__cvta_generic_to_shared(sB[st]);
-    if (AKC) {                                       // [64 m][32 k] -> 8 chunks per row
-      for (int c = tid; c < 512; c += 128) {
-        const int r = c >> 3, kc = (c & 7) * 4;
-        const bool ok = (m0 + r) < p.M && (k0 + kc) < p.K;
-        cp16z(a + (r * 36 + kc) * 4, ok ? p.A + (size_t)(m0 + r) * p.lda + k0 + kc : p.A, ok);
-      }
-    } else {                                         // [32 k][64 m] -> 16 chunks per row
-      for (int c = tid; c < 512; c += 128) {
-        const int r = c >> 4, mc = (c & 15) * 4;
-        const bool ok = (k0 + r) < p.K && (m0 + mc) < p.M;
-        cp16z(a + (r * 72 + mc) * 4, ok ? p.A + (size_t)(k0 + r) * p.lda + m0 + mc : p.A, ok);
-      }
+    const uint32_t a = sa0 + st * (GA_FLOATS * 4), b = sb0 + st * (GB_FLOATS * 4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool ok = ka[j] >= 0 && (k0 + ka[j]) < p.K;
+      cp16z(a + da[j], ok ? pa[j] + (size_t)k0 * astep : p.A, ok);
     }
-    if (BKC) {                                       // [32 n][32 k]
-      for (int c = tid; c < 256; c += 128) {
-        const int r = c >> 3, kc = (c & 7) * 4;
-        const bool ok = (n0 + r) < p.N && (k0 + kc) < p.K;
-        cp16z(b + (r * 36 + kc) * 4, ok ? p.B + (size_t)(n0 + r) * p.ldb + k0 + kc : p.B, ok);
-      }
-    } else {                                         // [32 k][32 n]
-      for (int c = tid; c < 256; c += 128) {
-        const int r = c >> 3, nc = (c & 7) * 4;
-        const bool ok = (k0 + r) < p.K && (n0 + nc) < p.N;
-        cp16z(b + (r * 40 + nc) * 4, ok ? p.B + (size_t)(k0 + r) * p.ldb + n0 + nc : p.B, ok);
-      }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const bool ok = kb[j] >= 0 && (k0 + kb[j]) < p.K;
+      cp16z(b + db[j], ok ? pb[j] + (size_t)k0 * bstep : p.B, ok);
     }
     cp_async_commit();
   };
@@ -337,9 +351,12 @@ __global__ void __launch_bounds__(128) wide_gemm_kernel(const GemmP p) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int m = m0 + warp * 16 + g + 8 * (q >> 1), n = n0 + nt * 8 + 2 * t + (q & 1);
+        float pz[8];
+#pragma unroll
+        for (int z = 0; z < 8; ++z) pz[z] = (z < p.splits && m < p.M && n < p.N) ? __ldcg(p.ws + ((size_t)z * p.M + m) * p.N + n) : 0.f;
         float v = 0.f;
-        if (m < p.M && n < p.N)
-          for (int z = 0; z < p.splits; ++z) v += __ldcg(p.ws + ((size_t)z * p.M + m) * p.N + n);
+#pragma unroll
+        for (int z = 0; z < 8; ++z) v += pz[z];
         acc[nt][q] = v;
       }
   }
@@ -488,7 +505,9 @@ extern "C" int cgs_wide_gemm(const float* A, int32_t a_k_contiguous, int32_t lda
   CGS_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (((uintptr_t)A | (uintptr_t)Bm) & 15) == 0, "wide_gemm: operands must be 16-byte aligned rows");
   CGS_REQUIRE(((a_k_contiguous ? K : M) % 4) == 0 && ((b_k_contiguous ? K : N) % 4) == 0, "wide_gemm: contiguous extents must be multiples of 4");
   const dim3 grid((N + wm::GN - 1) / wm::GN, (M + wm::GM - 1) / wm::GM, splits > 1 ? splits : 1);
-  CGS_REQUIRE(splits <= 1 || (ws && counters && grid.x * grid.y <= 4096), "wide_gemm: split-K needs a workspace [splits][M][N] and <= 4096 counters");
+  CGS_REQUIRE(splits <= 1 || (ws && counters && grid.x * grid.y <= 4096 && splits <= 8),
+              "wide_gemm: split-K (<= 8) needs a workspace [splits][M][N] and <= 4096 counters");
+  CGS_REQUIRE((a_k_contiguous || M >= 4) && (b_k_contiguous || N >= 4), "wide_gemm: M, N >= 4");
   wm::GemmP p{A, Bm, bias, gate, Cm, M, N, K, lda, ldb, ldc, relu, accumulate, (int)grid.z, ws, counters};
   cudaStream_t st = (cudaStream_t)stream;
   const int smem = wm::GST * (wm::GA_FLOATS + wm::GB_FLOATS) * 4;

@@ -36,14 +36,16 @@ for B in (256, 2048):
     r = {}
     for name, cin, cout, hw in (("conv1 fwd 32x32", C, C, 32), ("conv2 fwd 16x16", C, C, 16), ("conv3 fwd 8x8", C, 2 * C, 8)):
         x = wide.to_planar(rnd(B, cin, hw, hw)); w = rnd(cout, cin, 3, 3) * 0.05; b = rnd(cout)
-        r[name] = timeit(lambda: wide.conv3x3(x, w, b, wide.EPI_RELU_POOL))
+        (pk,) = wide.pack_weights([(w, False)])
+        r[name] = timeit(lambda: wide.conv3x3(x, w, b, wide.EPI_RELU_POOL, packed=pk))
     for name, cx, cout, hw in (("conv3 dgrad 8x8 unpool", 2 * C, C, 8), ("conv2 dgrad 16x16 unpool", C, C, 16), ("conv1 dgrad 32x32 plain", C, C, 32)):
         x = wide.to_planar(rnd(B, cx, hw, hw)); w = rnd(cx, cout, 3, 3) * 0.05
         idx = torch.randint(0, 5, (B, cout // 8, hw, hw, 8), device=DEV, dtype=torch.uint8)
+        (pk,) = wide.pack_weights([(w, True)])
         if "plain" in name:
-            r[name] = timeit(lambda: wide.conv3x3(x, w, transposed=True))
+            r[name] = timeit(lambda: wide.conv3x3(x, w, transposed=True, packed=pk))
         else:
-            r[name] = timeit(lambda: wide.conv3x3(x, w, epi=wide.EPI_UNPOOL, transposed=True, idx_in=idx))
+            r[name] = timeit(lambda: wide.conv3x3(x, w, epi=wide.EPI_UNPOOL, transposed=True, idx_in=idx, packed=pk))
     for name, cin, cout, hw in (("conv1 wgrad 32x32", C, C, 32), ("conv2 wgrad 16x16", C, C, 16), ("conv3 wgrad 8x8", C, 2 * C, 8)):
         x = wide.to_planar(rnd(B, cin, hw, hw)); dy = wide.to_planar(rnd(B, cout, hw, hw))
         dw = torch.zeros(cout, cin, 3, 3, device=DEV); db = torch.zeros(cout, device=DEV)

@@ -299,5 +299,40 @@ def gen_envelope():
     print("envelope max", env.max(), "median", np.median(env), "last", env[-1])
 
 
+def gen_envelope_epochs(seeds=(1, 2, 3, 4, 5, 6, 7, 8)):
+    """Per-epoch band of the critic loss curve: the reference loop (oracle, bit-identical to the reference on this curve) re-run
+    from initial weights perturbed by 1e-6 relative, 8 seeds.  Stored: the per-epoch median loss of every run (94 steps per epoch,
+    11 epochs) -> tests require an implementation's per-epoch medians to sit inside [min, max] over the runs (widened as the test
+    states).  VERDICT round 1, next #8."""
+    from oracle import torch_ref
+    d = np.load(f"{OUT}/loops_c1.npz")
+    X, Y, _ = synth.synthetic_frames(6000, seed=0)
+    Xt, Yt = torch.from_numpy(X), torch.from_numpy(Y).t()
+
+    def run(eps, seed):
+        g = torch.Generator().manual_seed(seed)
+        sd = {k[len("init.c."):]: torch.from_numpy(d[k]).clone() for k in d.files if k.startswith("init.c.")}
+        for v in sd.values():
+            v.mul_(1 + eps * (torch.rand(v.shape, generator=g) - 0.5))
+            v.requires_grad_(True)
+        opt = torch.optim.Adam(sd.values())
+        out = []
+        for ep in range(11):
+            for i in range(0, 6000, 64):
+                loss, _ = torch_ref.critic_loss(sd, Xt[i:i + 64].permute(0, 3, 1, 2).float() / 255.0, Yt[i:i + 64, 1].float())
+                opt.zero_grad(); loss.backward(); opt.step()
+                out.append(loss.item())
+        return np.array(out)
+    ep = lambda v: np.array([np.median(v[i:i + 94]) for i in range(0, 1034, 94)])
+    runs = [ep(d["closs"])] + [ep(run(1e-6, s)) for s in seeds]
+    med = np.stack(runs)
+    np.savez_compressed(f"{OUT}/loops_envelope_epochs_c1.npz", epoch_medians=med.astype(np.float64), eps=1e-6, seeds=np.array((0,) + tuple(seeds)))
+    print("per-epoch min", med.min(0)); print("per-epoch max", med.max(0)); print("max/min", med.max(0) / med.min(0))
+
+
+if __name__ == "__main__" and "envelope_epochs" in sys.argv[1:]:
+    gen_envelope_epochs()
+    sys.exit(0)
+
 if __name__ == "__main__" and "envelope" in sys.argv[1:]:
     gen_envelope()

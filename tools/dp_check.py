@@ -5,7 +5,8 @@ faulthandler.dump_traceback_later(int(os.environ.get("DP_CHECK_TIMEOUT", "90")),
 import torch, torch.distributed as dist
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 def say(*a):
-    print(f"[rank {rank} t={time.time()-T0:5.1f}]", *a, flush=True)
+    sys.stdout.write(f"[rank {rank} t={time.time()-T0:5.1f}] " + " ".join(str(x) for x in a) + "\n")      # one write: lines of two ranks do not interleave
+    sys.stdout.flush()
 T0 = time.time()
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -59,4 +60,34 @@ for i in range(5):
 torch.cuda.synchronize(); say("replays ok, loss", float(out))
 ref = opt.flat.clone(); dist.broadcast(ref, 0); torch.cuda.synchronize()
 say("params equal across ranks after graph replays:", bool(torch.equal(opt.flat, ref)))
+# ---- the frozen-critic Hourglass step, data-parallel (cgs_p2p_stage + cgs_p2p_allreduce_adam behind the whole-frame kernels)
+dist.barrier()
+torch.manual_seed(1)
+Hh = Handler(parse_args(["-frozen", "--dropout", "0"]), device=dev, rank=rank, world_size=world, process_group=dist.group.WORLD)
+Hh.critic.to(dev).train(); Hh.masker.to(dev).train()
+for q in Hh.critic.parameters():
+    q.requires_grad_(False)
+oh = FlatAdam(list(Hh.masker.parameters()), process_group=dist.group.WORLD, world_size=world)
+Bh = 32
+Xh, _, _ = synth.synthetic_frames(2 * Bh * world, seed=5)
+A_all, C_all = Xh[:Bh * world], Xh[Bh * world:]
+Ah = torch.from_numpy(A_all[rank * Bh:(rank + 1) * Bh]).to(dev); Ch = torch.from_numpy(C_all[rank * Bh:(rank + 1) * Bh]).to(dev)
+for i in range(3):
+    t = Hh.segmentation_step(Ah, Ch, None, oh)
+torch.cuda.synchronize()
+fh = oh.flat.clone(); rh = fh.clone(); dist.broadcast(rh, 0); torch.cuda.synchronize()
+say("hourglass params equal across ranks:", bool(torch.equal(fh, rh)))
+if world > 1 and rank == 0:
+    torch.manual_seed(1)
+    H1 = Handler(parse_args(["-frozen", "--dropout", "0"]), device=dev)
+    H1.critic.to(dev).train(); H1.masker.to(dev).train()
+    for q in H1.critic.parameters():
+        q.requires_grad_(False)
+    o1 = FlatAdam(list(H1.masker.parameters()))
+    Ag, Cg = torch.from_numpy(A_all).to(dev), torch.from_numpy(C_all).to(dev)
+    for i in range(3):
+        H1.segmentation_step(Ag, Cg, None, o1)
+    torch.cuda.synchronize()
+    err = (o1.flat - fh).abs().max().item()
+    say(f"hourglass DP vs single-process global batch: max |dparam| = {err:.3e} (scale {o1.flat.abs().max().item():.3e})")
 dist.barrier(); torch.cuda.synchronize(); say("done"); sys.stdout.flush(); os._exit(0)

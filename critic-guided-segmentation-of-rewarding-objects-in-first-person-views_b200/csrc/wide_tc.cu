@@ -93,6 +93,10 @@ __device__ __forceinline__ void tma_load4(uint32_t dst, const CUtensorMap* tm, i
       "l"(tm), "r"(8 * x), "r"(y), "r"(plane), "r"(n), "r"(bar)
       : "memory");
 }
+// n / d through one multiply-high (common.cuh FastDiv); d == 1 is the identity
+__device__ __forceinline__ int udiv(int n, const FastDiv& f) { return f.d == 1 ? n : fdiv(n, f); }
+static FastDiv fastdiv_or_one(int d) { return d >= 2 ? make_fastdiv(d) : FastDiv{0u, 1}; }
+
 // one lane of a converged warp; unlike `lane == 0` the compiler knows the region is executed by a single lane, so the warp-uniform
 // descriptor arithmetic of the MMA loop can stay in uniform registers (UTCHMMA takes its operands from there)
 __device__ __forceinline__ bool elect_one() {
@@ -137,6 +141,7 @@ struct ConvP {
   int B, H, W, Cin, Cout;          // GEMM view: K = 9 taps x Cin, N = Cout (transposed: Cin = the layer's outputs)
   int CPi, KP, NP;                 // Cin / 8, planes padded to even, Cout padded to 16
   int tiles_x, tiles_y, ntiles, stages, tmem_cols, epi, transposed;
+  FastDiv d_tpf, d_tx;             // dividers by tiles per frame / tiles per row
   uint32_t idesc;
   const float* w;
   const uint4* wpacked;            // [9][KP][NP] x 16 B operand rows (wide_pack_kernel), or NULL: packed here from w
@@ -197,13 +202,13 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
   if (warp == 0) {
     // ===== TMA producer
     if (elect_one()) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int s = it % p.stages, k = it / p.stages;
+      int s = 0, k = 0;                             // stage, ring pass (no divisions on these single-thread paths)
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         if (!mbar_wait(bEmpty + 8 * s, (k & 1) ^ 1)) break;
-        const int n = tile / tpf, r = tile - n * tpf, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int n = udiv(tile, p.d_tpf), r = tile - n * tpf, ty = udiv(r, p.d_tx), tx = r - ty * p.tiles_x;
         mbar_expect_tx(bFull + 8 * s, a_tx);
         tma_load4(smem_u32(s_a + (size_t)s * a_bytes), &tmx, tx * TW - 1, ty * TH - 1, 0, n, bFull + 8 * s);
+        if (++s == p.stages) { s = 0; ++k; }
       }
     }
   } else if (warp == 1) {
@@ -211,9 +216,9 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
     if (elect_one()) {
       const uint64_t a_desc0 = umma_desc(smem_u32(s_a), SLOTS * 16, HWID * 16), b_desc0 = umma_desc(smem_u32(s_w), (uint32_t)NP * 16, 128);
       const uint64_t b_step = (uint64_t)(2 * NP);   // consecutive (tap, plane pair) operand tiles are 2 NP rows of 16 bytes apart
-      int it = 0;
+      int it = 0, s = 0, k = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int s = it % p.stages, k = it / p.stages, ab = it & 1, j = it >> 1;
+        const int ab = it & 1, j = it >> 1;
         if (trace && it < 8) trace[it * 8 + 0] = clock64();
         if (!mbar_wait(bTEmpty + 8 * ab, (j & 1) ^ 1)) break;
         if (trace && it < 8) trace[it * 8 + 1] = clock64();
@@ -236,6 +241,7 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
         umma_commit(bEmpty + 8 * s);              // the stage is free once these MMAs have read it
         umma_commit(bTFull + 8 * ab);             // ... and the accumulator is complete
         if (trace && it < 8) trace[it * 8 + 3] = clock64();
+        if (++s == p.stages) { s = 0; ++k; }
       }
       if (trace) trace[58] = clock64();
     }
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
       if (!mbar_wait(bTFull + 8 * ab, j & 1)) break;
       if (trace && it < 8 && tid == 64) trace[it * 8 + 5] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const int n = tile / tpf, r = tile - n * tpf, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int n = udiv(tile, p.d_tpf), r = tile - n * tpf, ty = udiv(r, p.d_tx), tx = r - ty * p.tiles_x;
       const int y = ty * TH + yl, x = tx * TW + xl;
       const bool inb = y < H;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * NP);
@@ -361,6 +367,7 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
 struct WgP {
   int B, H, W, Cin, Cout, CPi, CPo, NP, NPl;
   int tiles_x, tiles_y, ntiles, stages, tmem_cols;
+  FastDiv d_tpf, d_tx;
   uint32_t idesc;
   float* partials;                 // [grid][3][128][NP]
 };
@@ -404,17 +411,17 @@ __global__ void __launch_bounds__(NTHR_W, 1) wide_wgrad_kernel(const __grid_cons
 
   if (warp == 0) {
     if (elect_one()) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int s = it % p.stages, k = it / p.stages;
+      int s = 0, k = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         if (!mbar_wait(bEmpty + 8 * s, (k & 1) ^ 1)) break;
-        const int n = tile / tpf, r = tile - n * tpf, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int n = udiv(tile, p.d_tpf), r = tile - n * tpf, ty = udiv(r, p.d_tx), tx = r - ty * p.tiles_x;
         const uint32_t a0 = smem_u32(smem + (size_t)s * st_bytes);
         mbar_expect_tx(bFull + 8 * s, tx_bytes);
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx)
           tma_load4(a0 + (uint32_t)(kx * p.CPi) * A3_PLANE, &tmx, tx * TW - 1 + kx, ty * TH - 1, 0, n, bFull + 8 * s);
         tma_load4(a0 + A3_BYTES, &tmdy, tx * TW, ty * TH, 0, n, bFull + 8 * s);
+        if (++s == p.stages) { s = 0; ++k; }
       }
     }
   } else if (warp == 1) {
@@ -425,8 +432,8 @@ __global__ void __launch_bounds__(NTHR_W, 1) wide_wgrad_kernel(const __grid_cons
       const uint64_t b_off = (umma_desc(smem_u32(smem) + A3_BYTES, 128, DY_PLANE) - a_desc0);
       int it = 0;
       bool ok = true;
+      int s = 0, k = 0;
       for (int tile = blockIdx.x; tile < p.ntiles && ok; tile += gridDim.x, ++it) {
-        const int s = it % p.stages, k = it / p.stages;
         if (!mbar_wait(bFull + 8 * s, k & 1)) { ok = false; break; }
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const uint64_t ad0 = a_desc0 + (uint64_t)((uint32_t)s * (st_bytes >> 4)), bd0 = ad0 + b_off;
@@ -437,6 +444,7 @@ __global__ void __launch_bounds__(NTHR_W, 1) wide_wgrad_kernel(const __grid_cons
           for (int r2 = 0; r2 < 8; ++r2)          // K = 16 pixels = tile rows 2 r2, 2 r2 + 1 (8 pixels each): constant descriptor offsets
             umma_bf16(tmem_base + (uint32_t)(ky * NP), ad0 + (uint64_t)((2 * r2 + ky) * 8), bd0 + (uint64_t)(2 * r2 * 8), p.idesc, r2 ? 1u : first);
         umma_commit(bEmpty + 8 * s);
+        if (++s == p.stages) { s = 0; ++k; }
       }
       umma_commit(bDone);
     }
@@ -552,6 +560,7 @@ int launch_wide_conv(const void* x, int B, int H, int W, int Cin, const float* w
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.CPi = Cin / 8; p.KP = (p.CPi + 1) & ~1; p.NP = (Cout + 15) & ~15;
   p.tiles_x = W / TW; p.tiles_y = (H + TH - 1) / TH; p.ntiles = B * p.tiles_x * p.tiles_y;
+  p.d_tpf = fastdiv_or_one(p.tiles_x * p.tiles_y); p.d_tx = fastdiv_or_one(p.tiles_x);
   p.epi = epi; p.transposed = transposed; p.w = w; p.wpacked = (const uint4*)wpacked; p.bias = bias;
   p.out = (__nv_bfloat16*)out; p.out_f32 = out_f32; p.idx_out = idx_out; p.idx_in = idx_in; p.mask = mask;
   p.tmem_cols = pow2_cols(2 * p.NP);
@@ -604,6 +613,7 @@ int launch_wide_wgrad(const void* x, const void* dy, int B, int H, int W, int Ci
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.CPi = Cin / 8; p.CPo = Cout / 8;
   p.NP = (Cout + 15) & ~15; p.NPl = p.NP / 8;
   p.tiles_x = W / TW; p.tiles_y = (H + TH - 1) / TH; p.ntiles = B * p.tiles_x * p.tiles_y;
+  p.d_tpf = fastdiv_or_one(p.tiles_x * p.tiles_y); p.d_tx = fastdiv_or_one(p.tiles_x);
   p.tmem_cols = pow2_cols(3 * p.NP);
   // as above with A and B MN-major (bits 15, 16): K = pixels
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);

@@ -307,6 +307,9 @@ def test_loss_curves_vs_reference_loops():
     assert ours[-1] < 0.02 * ours[0]                                                     # and it converged like the reference
     env = load_golden("loops_envelope_c1.npz")["env"].astype(np.float64)                # kept as documentation of the envelope
     assert env.max() > 0.5 and np.median(env) > 0.03
+    # the envelope criterion proper: every one of the 11 epochs inside the reference's own 9-run band (helpers.assert_in_epoch_band)
+    from helpers import assert_in_epoch_band
+    assert_in_epoch_band(closs, slack=0.01, what="fp32 path")
     # phase 2 is compared from the reference-trained critic so that both sides split the data identically
     H.critic.load_state_dict({k[len("trained.c."):]: torch.from_numpy(d[k]) for k in d.files if k.startswith("trained.c.")})
     H.segmentation_training()

@@ -146,6 +146,41 @@ class NewCritic(nn.Module):
         return pred
 
 
+class Critic(nn.Module):
+    """The legacy critic of the reference (nets.py:133-157): four Conv2d(3,1,1) + ReLU + MaxPool2d(2) stages and a 4x4
+    valid convolution to ONE channel (+ optional `end` modules, e.g. [nn.Sigmoid()]).  Same constructor, `enc` Sequential layout and
+    state_dict keys; forward() runs on the same kernels as NewCritic: `ops.EncBlock` x 4 and the 4x4 convolution on the 4x4 map as
+    the dense kernel over the NHWC-flattened map (its weight viewed in (y, x, c) order).  Returns [B, 1, 1, 1] like the reference."""
+
+    def __init__(self, width=64, enc_dim=1, colorchs=3, chfak=1, activation=nn.ReLU, end=[], pool="max"):
+        super().__init__()
+        if pool != "max" or activation is not nn.ReLU or width != 64:
+            raise NotImplementedError("cgs_b200.Critic accelerates pool='max', activation=nn.ReLU, width=64 (the reference's defaults)")
+        self.width, self.colorchs = width, colorchs
+        mp = nn.MaxPool2d(2)
+        modules = [nn.Conv2d(colorchs, 8 * chfak, 3, 1, 1), activation(), mp,
+                   nn.Conv2d(8 * chfak, 8 * chfak, 3, 1, 1), activation(), mp,
+                   nn.Conv2d(8 * chfak, 8 * chfak, 3, 1, 1), activation(), mp,
+                   nn.Conv2d(8 * chfak, 16 * chfak, 3, 1, 1), activation(), mp,
+                   nn.Conv2d(16 * chfak, 1, 4)]
+        modules.extend(end)
+        self.enc = nn.Sequential(*modules)
+        self._end = list(end)
+
+    def forward(self, X):
+        x = _nhwc(X, self.colorchs, self.width, "Critic")
+        e = self.enc
+        for i in (0, 3, 6, 9):
+            x = ops.EncBlock.apply(x, None, e[i].weight, e[i].bias)
+        B = x.shape[0]
+        w = e[12].weight                                               # [1, C, 4, 4] -> K order (y, x, c) of the NHWC map
+        out = ops.Dense.apply(x.reshape(B, 1, 1, -1), w.permute(0, 2, 3, 1).reshape(1, -1).contiguous(), e[12].bias)
+        out = out.reshape(B, 1, 1, 1)
+        for m in self._end:
+            out = m(out)
+        return out
+
+
 class UnetDecoder(nn.Module):
     def __init__(self, width=64, edims=[8, 8, 8, 16], ddims=[8, 8, 8, 16], bottleneck=32, masker_channels=16,
                  colorchs=3, chfak=1, activation=nn.ReLU, pool="max", upsample=True, pure=False):

@@ -322,3 +322,29 @@ def test_loss_curves_vs_reference_loops():
     ours = tot([t["replace"] for t in H.seg_log], [t["inject"] for t in H.seg_log])
     theirs = tot(d["seg_replace"], d["seg_inject"])
     assert np.abs(ours - theirs).max() <= 0.01 * theirs.max() + 1e-6
+
+
+@pytest.mark.parametrize("K", [1, 2])
+def test_legacy_critic_vs_reference_golden(K):
+    """the legacy `Critic` (reference nets.py:133-157, with end=[Sigmoid]) on the NewCritic kernels: prediction, loss
+    and every parameter gradient against what the unmodified reference class produced (tests/golden/make_golden_legacy.py), exact
+    fp32 path; state_dict keys and shapes are the reference's."""
+    from cgs_b200.nets import Critic
+    import cgs_b200.synth as synth
+    d = load_golden("legacy_critic.npz")
+    c = Critic(chfak=K, end=[torch.nn.Sigmoid()])
+    sd = {k[len(f"c{K}.sd."):]: torch.from_numpy(d[k]) for k in d.files if k.startswith(f"c{K}.sd.")}
+    assert set(sd) == set(c.state_dict()) and all(tuple(sd[k].shape) == tuple(v.shape) for k, v in c.state_dict().items())
+    c.load_state_dict(sd)
+    c.to(DEV)
+    X, Y, _ = synth.synthetic_frames(6, seed=30 + K)
+    x = (torch.from_numpy(X).permute(0, 3, 1, 2).float() / 255.0).to(DEV)
+    y = torch.from_numpy(Y[1, :6]).float().to(DEV)
+    pred = c(x)
+    assert tuple(pred.shape) == (6, 1, 1, 1)
+    loss = torch.nn.functional.mse_loss(pred.reshape(-1), y)
+    loss.backward()
+    close(pred, d[f"c{K}.pred"], "pred")
+    close(loss, d[f"c{K}.loss"], "loss")
+    for k, v in c.named_parameters():
+        close(v.grad, d[f"c{K}.g.{k}"], "g." + k)

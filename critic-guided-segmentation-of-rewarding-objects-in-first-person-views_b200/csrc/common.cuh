@@ -180,6 +180,25 @@ __device__ __forceinline__ void src_load8(const cgs_src& s, int n, int y, int x,
   }
 }
 
+// ---- programmatic dependent launch (the wide path's 27-kernel step): a kernel launched through launch_pdl() may become resident
+// while the kernel before it in the stream is still draining; pdl_wait() returns once that kernel has completed and its writes
+// are visible, so everything before it must touch on-chip state only.  pdl_trigger() lets the NEXT kernel start its own prologue.
+// Both are no-ops for plain launches.  CGS_PDL=0 turns the launch attribute off.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

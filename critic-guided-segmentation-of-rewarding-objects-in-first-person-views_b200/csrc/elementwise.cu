@@ -5,6 +5,7 @@
 // All use grid-stride loops over 128-bit accesses where alignment allows, warp-shuffle +
 // one-atomic-per-CTA reductions, and grids sized to a multiple of the SM count.
 #include <stdarg.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cgs {
@@ -25,6 +26,15 @@ int check_launch(const char* what) {
     return CGS_ECUDA;
   }
   return CGS_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CGS_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int device_sms() {

@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(NT, 1) wide_conv0_fwd_kernel(const uint8_t* __
   const int oI = sE + CP * 16384, oW = oI + CP * 8192, oB = oW + 3 * CP * 256;
   uint2* sW = reinterpret_cast<uint2*>(smraw + oW);
   float* sB = reinterpret_cast<float*>(smraw + oB);
+  pdl_trigger();
+  pdl_wait();
   if ((int)blockIdx.x < B) {
     const uint8_t* src = frames + (size_t)blockIdx.x * 12288;
     for (int c = tid; c < 768; c += NT) cp_async16(smb + sU8 + c * 16, src + c * 16);
@@ -124,7 +126,9 @@ __global__ void __launch_bounds__(NT, 1) wide_conv0_wgrad_kernel(const uint8_t* 
   const int oI = sE + CP * 16384;
   const unsigned short* uDE = reinterpret_cast<const unsigned short*>(smraw + sE);
   const uint8_t* bI = smraw + oI;
+  pdl_trigger();
   for (int e = tid; e < PBX / 16; e += NT) reinterpret_cast<uint4*>(smraw + sX)[e] = make_uint4(0u, 0u, 0u, 0u);
+  pdl_wait();
   int rl = roll_dev ? *roll_dev : roll;
   rl = ((rl % 64) + 64) & 63;
   float acc[MAXCP][3][4];
@@ -199,6 +203,8 @@ __global__ void __launch_bounds__(NT, 1) wide_conv0_wgrad_kernel(const uint8_t* 
 }
 
 __global__ void wide_conv0_reduce_kernel(const float* __restrict__ part, int ncta, int C0, float* __restrict__ dw, float* __restrict__ db) {
+  pdl_trigger();
+  pdl_wait();
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;      // one warp per element, lanes over the CTAs
   if (e >= 3 * 16 * C0) return;
   const int co = e % C0, m = (e / C0) & 15, ky = e / (C0 * 16), kx = m >> 2, c = m & 3;
@@ -245,6 +251,8 @@ __global__ void __launch_bounds__(128) wide_gemm_kernel(const GemmP p) {
   float(*sB)[GB_FLOATS] = reinterpret_cast<float(*)[GB_FLOATS]>(gsm + GST * GA_FLOATS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  pdl_trigger();
+  pdl_wait();
   const int nk_all = (p.K + GK - 1) / GK, per = (nk_all + p.splits - 1) / p.splits;
   const int kt0 = blockIdx.z * per, nk = max(0, min(per, nk_all - kt0));
   // per-thread chunk descriptors, fixed over the K loop (a single warp per scheduler runs these loops: every instruction counts):
@@ -382,6 +390,8 @@ __global__ void __launch_bounds__(256) wide_head_mid_kernel(const float* __restr
                                                             const float* __restrict__ bl2, const float* __restrict__ target, int B, int nb,
                                                             float gscale, int bce, float* __restrict__ pred, float* __restrict__ lterm,
                                                             float* __restrict__ dV, float* __restrict__ dz_out, float* __restrict__ U) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   float s = 0.f;
@@ -417,6 +427,8 @@ struct ColJobs {
 };
 __global__ void __launch_bounds__(256) wide_colsums_kernel(const ColJobs jobs, int B) {
   __shared__ float sm[8][33];
+  pdl_trigger();
+  pdl_wait();
   const ColJob jb = jobs.j[blockIdx.y];
   const int c = threadIdx.x & 31, r = threadIdx.x >> 5, col = blockIdx.x * 32 + c;
   if (blockIdx.x * 32 >= jb.n) return;
@@ -443,6 +455,8 @@ __global__ void __launch_bounds__(256) wide_colsums_kernel(const ColJobs jobs, i
 // d e3 [B][C3][4][4] fp32 -> Dropout + MaxPool + ReLU backward -> dY3 [B][C3/8][8][8][8] bf16 (features.10's output gradient)
 __global__ void wide_unpool3_kernel(const float* __restrict__ de3, const uint8_t* __restrict__ idx3, const float* __restrict__ m3, int B, int C3,
                                     __nv_bfloat16* __restrict__ dy3) {
+  pdl_trigger();
+  pdl_wait();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int CP = C3 >> 3;
   if (e >= B * CP * 64) return;
@@ -477,7 +491,8 @@ extern "C" int cgs_wide_conv0_fwd(const uint8_t* frames, int32_t B, int32_t roll
   cudaFuncSetAttribute(wm::wide_conv0_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int grid = device_sms();
   if (grid > B) grid = B;
-  wm::wide_conv0_fwd_kernel<<<grid, hg::NT, smem, (cudaStream_t)stream>>>(frames, B, roll, roll_dev, w0, b0, CP, (__nv_bfloat16*)e0, idx0);
+  launch_pdl(wm::wide_conv0_fwd_kernel, dim3(grid), dim3(hg::NT), (size_t)smem, (cudaStream_t)stream, frames, (int)B, (int)roll, (const int*)roll_dev, w0, b0, CP,
+             (__nv_bfloat16*)e0, idx0);
   return check_launch("wide_conv0_fwd");
 }
 
@@ -490,11 +505,12 @@ extern "C" int cgs_wide_conv0_wgrad(const uint8_t* frames, int32_t B, int32_t ro
   if (grid > B) grid = B;
   CGS_REQUIRE(workspace_floats >= (int64_t)grid * 48 * C0, "wide_conv0_wgrad: workspace too small");
   cudaFuncSetAttribute(wm::wide_conv0_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  wm::wide_conv0_wgrad_kernel<<<grid, hg::NT, smem, (cudaStream_t)stream>>>(frames, B, roll, roll_dev, (const __nv_bfloat16*)de0, idx0, CP, workspace);
+  launch_pdl(wm::wide_conv0_wgrad_kernel, dim3(grid), dim3(hg::NT), (size_t)smem, (cudaStream_t)stream, frames, (int)B, (int)roll, (const int*)roll_dev,
+             (const __nv_bfloat16*)de0, idx0, CP, workspace);
   int rc = check_launch("wide_conv0_wgrad");
   if (rc) return rc;
   const int n = 48 * C0;
-  wm::wide_conv0_reduce_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(workspace, grid, C0, dw0, db0);
+  launch_pdl(wm::wide_conv0_reduce_kernel, dim3((n + 7) / 8), dim3(256), 0, (cudaStream_t)stream, (const float*)workspace, grid, (int)C0, dw0, db0);
   return check_launch("wide_conv0_wgrad.reduce");
 }
 
@@ -513,13 +529,13 @@ extern "C" int cgs_wide_gemm(const float* A, int32_t a_k_contiguous, int32_t lda
   const int smem = wm::GST * (wm::GA_FLOATS + wm::GB_FLOATS) * 4;
   if (a_k_contiguous && b_k_contiguous) {
     cudaFuncSetAttribute(wm::wide_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    wm::wide_gemm_kernel<true, true><<<grid, 128, smem, st>>>(p);
+    launch_pdl(wm::wide_gemm_kernel<true, true>, grid, dim3(128), (size_t)smem, st, p);
   } else if (a_k_contiguous) {
     cudaFuncSetAttribute(wm::wide_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    wm::wide_gemm_kernel<true, false><<<grid, 128, smem, st>>>(p);
+    launch_pdl(wm::wide_gemm_kernel<true, false>, grid, dim3(128), (size_t)smem, st, p);
   } else if (!b_k_contiguous) {
     cudaFuncSetAttribute(wm::wide_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    wm::wide_gemm_kernel<false, false><<<grid, 128, smem, st>>>(p);
+    launch_pdl(wm::wide_gemm_kernel<false, false>, grid, dim3(128), (size_t)smem, st, p);
   }
   else CGS_REQUIRE(false, "wide_gemm: A MN-contiguous with B K-contiguous is not built");
   return check_launch("wide_gemm");
@@ -528,8 +544,8 @@ extern "C" int cgs_wide_gemm(const float* A, int32_t a_k_contiguous, int32_t lda
 extern "C" int cgs_wide_head_mid(const float* V, const float* mv, const float* wl2, const float* bl2, const float* target, int32_t B, int32_t nb,
                                  float loss_grad, int32_t bce, float* pred, float* lterm, float* dV, float* dz, float* U, void* stream) {
   CGS_REQUIRE(V && wl2 && bl2 && target && pred && lterm && dV && dz && U && B > 0 && nb > 0, "wide_head_mid: bad args");
-  wm::wide_head_mid_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(V, mv, wl2, bl2, target, B, nb, loss_grad / (float)B, bce, pred, lterm, dV,
-                                                                          dz, U);
+  launch_pdl(wm::wide_head_mid_kernel, dim3((B + 7) / 8), dim3(256), 0, (cudaStream_t)stream, V, mv, wl2, bl2, target, (int)B, (int)nb,
+             loss_grad / (float)B, (int)bce, pred, lterm, dV, dz, U);
   return check_launch("wide_head_mid");
 }
 
@@ -542,13 +558,13 @@ extern "C" int cgs_wide_colsums(const cgs_wide_coljob* jobs, int32_t njobs, int3
     js.j[i] = wm::ColJob{jobs[i].X, jobs[i].out, jobs[i].n, jobs[i].scale, jobs[i].accumulate};
     if (jobs[i].n > maxn) maxn = jobs[i].n;
   }
-  wm::wide_colsums_kernel<<<dim3((maxn + 31) / 32, njobs), 256, 0, (cudaStream_t)stream>>>(js, B);
+  launch_pdl(wm::wide_colsums_kernel, dim3((maxn + 31) / 32, njobs), dim3(256), 0, (cudaStream_t)stream, js, (int)B);
   return check_launch("wide_colsums");
 }
 
 extern "C" int cgs_wide_unpool3(const float* de3, const uint8_t* idx3, const float* m3, int32_t B, int32_t C3, void* dy3, void* stream) {
   CGS_REQUIRE(de3 && idx3 && dy3 && B > 0 && (C3 % 8) == 0, "wide_unpool3: bad args");
   const int n = B * (C3 / 8) * 64;
-  wm::wide_unpool3_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(de3, idx3, m3, B, C3, (__nv_bfloat16*)dy3);
+  launch_pdl(wm::wide_unpool3_kernel, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)stream, de3, idx3, m3, (int)B, (int)C3, (__nv_bfloat16*)dy3);
   return check_launch("wide_unpool3");
 }

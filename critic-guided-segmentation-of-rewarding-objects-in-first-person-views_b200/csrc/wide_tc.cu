@@ -132,6 +132,8 @@ struct PackJobs {
 };
 // all operand tiles of a step in one launch (blockIdx.y = job): the filters change with every optimizer step
 __global__ void wide_pack_kernel(const PackJobs jobs) {
+  pdl_trigger();
+  pdl_wait();
   const PackJob jb = jobs.j[blockIdx.y];
   const int KP = ((jb.Cin >> 3) + 1) & ~1, NP = (jb.Cout + 15) & ~15, rows = 9 * KP * NP;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) jb.out[r] = pack_row(jb.w, r, KP, NP, jb.Cin, jb.Cout, jb.transposed);
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KP = p.KP, NP = p.NP;
+  pdl_trigger();
   if (blockIdx.x == 0 && tid == 0 && g_wd_trace) g_wd_trace[56] = clock64();
   const uint32_t w_bytes = (uint32_t)9 * KP * NP * 16, a_bytes = (uint32_t)KP * SLOTS * 16, a_tx = (uint32_t)p.CPi * SLOTS * 16;
   unsigned char* s_w = smem;
@@ -177,6 +180,7 @@ __global__ void __launch_bounds__(NTHR, 1) wide_conv_kernel(const __grid_constan
     for (int b = 0; b < 2; ++b) { mbar_init(bTFull + 8 * b, 1); mbar_init(bTEmpty + 8 * b, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  pdl_wait();                                      // from here on: global memory the kernels before this one wrote
   {
     // B operand (K-major): element (tap, ci, co) -> [(tap * KP + ci / 8) * NP + co] x 16 B + (ci % 8) x 2 B, zero padded
     const int rows = 9 * KP * NP;
@@ -382,6 +386,7 @@ __global__ void __launch_bounds__(NTHR_W, 1) wide_wgrad_kernel(const __grid_cons
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * st_bytes);   // full[S] empty[S] done
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * p.stages + 1);
   const uint32_t bar0 = smem_u32(s_bar), bFull = bar0, bEmpty = bar0 + 8 * p.stages, bDone = bar0 + 16 * p.stages;
+  pdl_trigger();
 
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "r"(p.tmem_cols) : "memory");
@@ -408,6 +413,7 @@ __global__ void __launch_bounds__(NTHR_W, 1) wide_wgrad_kernel(const __grid_cons
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = *s_tmem;
   const int tpf = p.tiles_x * p.tiles_y;
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -476,6 +482,8 @@ __global__ void __launch_bounds__(NTHR_W, 1) wide_wgrad_kernel(const __grid_cons
 // One warp per 4 consecutive elements: the lanes split the CTAs (independent 16-byte loads), then a fixed butterfly: deterministic.
 __global__ void wide_wgrad_reduce_kernel(const float* __restrict__ part, int ncta, int NP, int Cin, int Cout, float* __restrict__ dw,
                                          float* __restrict__ db) {
+  pdl_trigger();
+  pdl_wait();
   const int e4 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int total4 = 3 * 128 * NP / 4;
   if (e4 >= total4) return;
@@ -581,7 +589,7 @@ int launch_wide_conv(const void* x, int B, int H, int W, int Cin, const float* w
 #define CGS_WIDE_CONV(KS)                                                                                        \
   case KS:                                                                                                       \
     cudaFuncSetAttribute(wide_conv_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);         \
-    wide_conv_kernel<KS><<<grid, NTHR, smem, st>>>(tm, p);                                                       \
+    launch_pdl(wide_conv_kernel<KS>, dim3(grid), dim3(NTHR), smem, st, tm, p);                                   \
     break;
   switch (p.KP / 2) {
     CGS_WIDE_CONV(1) CGS_WIDE_CONV(2) CGS_WIDE_CONV(3) CGS_WIDE_CONV(4) CGS_WIDE_CONV(5) CGS_WIDE_CONV(6) CGS_WIDE_CONV(7) CGS_WIDE_CONV(8)
@@ -632,11 +640,11 @@ int launch_wide_wgrad(const void* x, const void* dy, int B, int H, int W, int Ci
   rc = make_tmap(&tmdy, dy, B, p.CPo, H, W, TW, TH, p.CPo);
   if (rc) return rc;
   cudaFuncSetAttribute(wide_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-  wide_wgrad_kernel<<<grid, NTHR_W, smem, st>>>(tmx, tmdy, p);
+  launch_pdl(wide_wgrad_kernel, dim3(grid), dim3(NTHR_W), smem, st, tmx, tmdy, p);
   rc = check_launch("wide_wgrad3x3");
   if (rc) return rc;
   const int nwarps = 3 * 128 * p.NP / 4;
-  wide_wgrad_reduce_kernel<<<(nwarps + 7) / 8, 256, 0, st>>>(ws, grid, p.NP, Cin, Cout, dw, db);
+  launch_pdl(wide_wgrad_reduce_kernel, dim3((nwarps + 7) / 8), dim3(256), 0, st, (const float*)ws, grid, p.NP, Cin, Cout, dw, db);
   return check_launch("wide_wgrad3x3.reduce");
 }
 
@@ -662,7 +670,7 @@ extern "C" int cgs_wide_pack(const cgs_wide_packjob* jobs, int32_t njobs, void* 
     CGS_REQUIRE(jobs[i].w && jobs[i].out && (jobs[i].Cin % 8) == 0 && (jobs[i].Cout % 8) == 0 && ((uintptr_t)jobs[i].out & 15) == 0, "wide_pack: bad job %d", i);
     js.j[i] = wd::PackJob{jobs[i].w, (uint4*)jobs[i].out, jobs[i].Cin, jobs[i].Cout, jobs[i].transposed};
   }
-  wd::wide_pack_kernel<<<dim3(16, njobs), 256, 0, (cudaStream_t)stream>>>(js);
+  launch_pdl(wd::wide_pack_kernel, dim3(16, njobs), dim3(256), 0, (cudaStream_t)stream, js);
   return check_launch("wide_pack");
 }
 

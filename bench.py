@@ -465,6 +465,9 @@ def bench_workload(name, args, rank, world, dev, group, sampler_windows):
             eager()
         with ops.profile_calls() as prof:
             for _ in range(5):
+                # keep the GPU backlogged while the host enqueues the step: an event pair around a launch then spans the kernel's
+                # execution, not the host's launch latency (which would weigh a 27-launch step's small kernels far too heavily)
+                torch.cuda._sleep(int(8e6))
                 eager()
         summ = prof.summary()
         tot = sum(v[1] for v in summ.values()) or 1.0

@@ -149,7 +149,7 @@ class FlatAdam:
         time-out: the kernels skip the affected updates, so the last checkpoint is still good, but training must stop."""
         from . import _lib
         if self.flat.is_cuda and not (self.barrier_ok() and self.p2p_ok() and _lib.lib().cgs_tc_status() == 0
-                                      and _lib.lib().cgs_hg_status() == 0):
+                                      and _lib.lib().cgs_hg_status() == 0 and _lib.lib().cgs_wide_status() == 0):
             raise RuntimeError("cgs_b200: a device-side wait timed out (grid barrier / peer gradient / tcgen05 mbarrier): "
                                "the affected parameter updates were skipped; the optimizer state is not trustworthy")
 

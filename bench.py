@@ -489,8 +489,10 @@ def bench_workload(name, args, rank, world, dev, group, sampler_windows):
                                "kernel": top["entry"], "share_of_step": top["share"], "algorithmic_flops": fl,
                                "launch_us": live_us,
                                "peak_source": pk["which"] + ": bf16_tflops_sustained (dense tcgen05 bf16, kernel timed inside a long "
-                                              "step); no TF32 peak is measured on this pool - the kernels here are mma.sync "
-                                              "TF32/bf16, whose own issue peak is given below",
+                                              "step); " + ("the kernel here is a TMA-fed tcgen05 bf16 convolution with N = 40..80 per MMA "
+                                                           "(issue-bound: DESIGN.md 4e)" if args.chfak != 1 else
+                                                           "no TF32 peak is measured on this pool - the kernels here are mma.sync "
+                                                           "TF32/bf16, whose own issue peak is given below"),
                                "mma_sync_tf32_peak_tflops": mma_tf32, "frac_of_mma_sync_tf32_peak": tfl / mma_tf32,
                                "mma_sync_bf16_peak_tflops": 2 * mma_tf32, "frac_of_mma_sync_bf16_peak": tfl / (2 * mma_tf32),
                                "step_frac_of_peak": rec["achieved_tflops"] / world / pk["tf_sustained"]}
